@@ -1,0 +1,772 @@
+// Host side of the C ABI declared in include/hirm_engine.h: state store, CSR build,
+// label<->slot maps, kernel selection and launches.  No torch, no CPU compute path for
+// the move: every score/sample/apply happens in the CUDA kernels.
+#include "../../include/hirm_engine.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "device_math.cuh"
+#include "engine_types.cuh"
+#include "generic_sweep.cuh"
+#include "dense_sweep.cuh"
+
+using namespace hirm;
+
+static thread_local std::string g_err;
+static int fail(const std::string &msg) { g_err = msg; return -1; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        return cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+    }
+    cudaError_t ensure(size_t count) { return count <= n && p ? cudaSuccess : alloc(count); }
+};
+
+struct RelObs {
+    int kind = -1;                     // -1 unset, 0 CSR, 1 dense
+    int64_t nobs = 0;
+    std::vector<int32_t> h_ids;        // host COO until finalize()
+    std::vector<uint8_t> h_val;
+    DevBuf<int32_t> coo_ids; DevBuf<uint8_t> coo_val;
+    const uint8_t *slab[2] = {nullptr, nullptr};
+    int64_t pitch[2] = {0, 0};
+    DevBuf<uint8_t> own_slab0, own_slab1;   // set_observations_dense_host
+};
+struct DomObs {
+    DevBuf<int64_t> ptr; DevBuf<uint32_t> meta; DevBuf<int32_t> other;
+    int64_t nnz = 0; int n_other = 0; int64_t max_deg = 0;
+};
+// Observation store: immutable after finalize(); shared by the chains of one dataset.
+struct ObsStore {
+    std::vector<RelObs> rel;
+    std::vector<DomObs> dom;
+    bool finalized = false;
+};
+
+struct Irm {
+    int n_domains = 0, n_relations = 0;
+    std::vector<int32_t> n_ent, kcap, arity;
+    std::vector<std::array<int32_t, MAX_ARITY>> rdom;
+    std::shared_ptr<ObsStore> obs;
+    // device state
+    std::vector<DevBuf<int32_t>> z, tab_count, tab_label, hi;
+    std::vector<double> alpha;
+    std::vector<DevBuf<cell_t>> counts, groups;
+    std::vector<std::array<int64_t, MAX_ARITY>> cstride, gstride;
+    std::vector<int64_t> ncells, gcells, gbit0;
+    DevBuf<unsigned long long> gbitmap; DevBuf<int32_t> word_rel; int64_t gwords = 0;
+    DevBuf<int32_t> gl_rel; DevBuf<int64_t> gl_cell; int64_t gl_cap = 0;
+    DevBuf<int32_t> error;
+    DevBuf<RelationDev> d_rel;
+    std::vector<bool> have_z;
+    bool counts_dirty = true, desc_dirty = true, scratch_ready = false;
+    bool alive = true;
+    bool dense_ree = false;            // eligible for the dense fast path
+};
+
+}  // namespace
+
+struct hirm_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<std::unique_ptr<Irm>> irms;
+    DevBuf<IrmDev> d_irms;
+    std::vector<IrmDev> h_irms;
+    // sweep scratch
+    DevBuf<int32_t> s_irm_ids, s_move_dom, s_move_item, s_choice, s_trace_n, s_trace_labels, s_blk;
+    DevBuf<int64_t> s_move_off; DevBuf<double> s_uniforms, s_trace_logps, s_score;
+    DevBuf<uint64_t> s_stream, s_counter;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_launches = 0, last_kind = -1; float last_ms = 0.f;
+    int max_smem_optin = 0, num_sms = 0;
+};
+
+static const char *kerr_text(int code) {
+    switch (code) {
+        case KERR_NO_FREE_SLOT: return "max_tables exhausted: no free table slot for the fresh-table candidate";
+        case KERR_ABSENT_ENTITY: return "an observation names an entity whose assignment is -1";
+        case KERR_GROUP_OVERFLOW: return "group list capacity exceeded";
+        case KERR_BAD_MOVE: return "move names an entity that is not in the domain";
+        default: return "unknown kernel error";
+    }
+}
+
+extern "C" const char *hirm_last_error(void) { return g_err.c_str(); }
+extern "C" int hirm_engine_abi_version(void) { return 1; }
+
+extern "C" int hirm_engine_create(hirm_engine **out, int device) {
+    if (!out) return fail("out is null");
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0)
+        return fail(std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(ce));
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= count) return fail("device ordinal out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) return fail("this engine is built for sm_100a (Blackwell) only");
+    auto e = std::make_unique<hirm_engine>();
+    e->device = device;
+    e->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    e->num_sms = prop.multiProcessorCount;
+    CK(cudaEventCreate(&e->ev0));
+    CK(cudaEventCreate(&e->ev1));
+    // log-factorial table from libm's lgamma (the reference's lbeta, cxx/util_math.cc:13-15)
+    std::vector<double> lf(LF_SIZE);
+    for (int m = 0; m < LF_SIZE; m++) lf[m] = lgamma((double)m + 1.0);
+    CK(cudaMemcpyToSymbol(g_logfact, lf.data(), sizeof(double) * LF_SIZE));
+    *out = e.release();
+    return 0;
+}
+
+extern "C" int hirm_engine_destroy(hirm_engine *e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e;
+    return 0;
+}
+
+extern "C" int hirm_engine_set_stream(hirm_engine *e, void *s) {
+    if (!e) return fail("engine is null");
+    e->stream = (cudaStream_t)s;
+    return 0;
+}
+extern "C" int hirm_engine_synchronize(hirm_engine *e) {
+    if (!e) return fail("engine is null");
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static Irm *get_irm(hirm_engine *e, int32_t id) {
+    if (!e || id < 0 || id >= (int)e->irms.size() || !e->irms[id] || !e->irms[id]->alive) return nullptr;
+    return e->irms[id].get();
+}
+#define GET_IRM(var, e, id)            \
+    Irm *var = get_irm(e, id);         \
+    if (!var) return fail("bad irm id"); \
+    CK(cudaSetDevice(e->device))
+
+extern "C" int hirm_irm_create(hirm_engine *e, int n_domains, const int32_t *n_entities, const int32_t *max_tables,
+                               int n_relations, const int32_t *arity, const int32_t *rel_domains, int32_t *out_irm) {
+    if (!e || !out_irm) return fail("null argument");
+    CK(cudaSetDevice(e->device));
+    if (n_domains < 1 || n_domains > MAX_DOMAINS) return fail("n_domains must be in [1, HIRM_MAX_DOMAINS]");
+    if (n_relations < 0 || n_relations > (int)META_REL_MASK) return fail("too many relations");
+    auto irm = std::make_unique<Irm>();
+    irm->n_domains = n_domains; irm->n_relations = n_relations;
+    for (int d = 0; d < n_domains; d++) {
+        if (n_entities[d] < 0) return fail("negative n_entities");
+        if (max_tables[d] < 2 || max_tables[d] > 255) return fail("max_tables must be in [2, 255]");
+        irm->n_ent.push_back(n_entities[d]); irm->kcap.push_back(max_tables[d]);
+    }
+    irm->alpha.assign(n_domains, 1.0);                 // CRP::alpha default (cxx/hirm.hh:72)
+    irm->have_z.assign(n_domains, false);
+    irm->cstride.resize(n_relations); irm->gstride.resize(n_relations);
+    irm->ncells.resize(n_relations); irm->gcells.resize(n_relations); irm->gbit0.resize(n_relations);
+    const int64_t CELL_BUDGET = (int64_t)1 << 27;      // 1 GiB of packed cells per table
+    for (int r = 0; r < n_relations; r++) {
+        if (arity[r] < 1 || arity[r] > MAX_ARITY) return fail("arity must be in [1, HIRM_MAX_ARITY]");
+        std::array<int32_t, MAX_ARITY> ds{};
+        int64_t cs = 1, gs = 1;
+        for (int p = 0; p < arity[r]; p++) {
+            int d = rel_domains[r * MAX_ARITY + p];
+            if (d < 0 || d >= n_domains) return fail("relation names a domain out of range");
+            ds[p] = d;
+            int occ = 0;
+            for (int q = 0; q <= p; q++) occ += rel_domains[r * MAX_ARITY + q] == d;
+            if (occ > 2) return fail("a domain may occur at most twice in one relation");
+            irm->cstride[r][p] = cs; irm->gstride[r][p] = gs;
+            cs *= irm->kcap[d]; gs *= irm->kcap[d] + 1;
+            if (gs > CELL_BUDGET) return fail("dense count table too large: lower max_tables (hashed tables are not built yet)");
+        }
+        irm->ncells[r] = cs; irm->gcells[r] = gs;
+        irm->arity.push_back(arity[r]); irm->rdom.push_back(ds);
+    }
+    irm->obs = std::make_shared<ObsStore>();
+    irm->obs->rel.resize(n_relations);
+    irm->obs->dom.resize(n_domains);
+    irm->z.resize(n_domains); irm->tab_count.resize(n_domains); irm->tab_label.resize(n_domains); irm->hi.resize(n_domains);
+    for (int d = 0; d < n_domains; d++) {
+        CK(irm->z[d].alloc(n_entities[d]));
+        CK(cudaMemset(irm->z[d].p, 0xFF, std::max(1, n_entities[d]) * sizeof(int32_t)));
+        CK(irm->tab_count[d].alloc(irm->kcap[d])); CK(cudaMemset(irm->tab_count[d].p, 0, irm->kcap[d] * sizeof(int32_t)));
+        CK(irm->tab_label[d].alloc(irm->kcap[d])); CK(cudaMemset(irm->tab_label[d].p, 0, irm->kcap[d] * sizeof(int32_t)));
+        CK(irm->hi[d].alloc(1)); CK(cudaMemset(irm->hi[d].p, 0, sizeof(int32_t)));
+    }
+    irm->counts.resize(n_relations); irm->groups.resize(n_relations);
+    CK(irm->error.alloc(1)); CK(cudaMemset(irm->error.p, 0, sizeof(int32_t)));
+    e->irms.push_back(std::move(irm));
+    *out_irm = (int32_t)e->irms.size() - 1;
+    return 0;
+}
+
+extern "C" int hirm_irm_destroy(hirm_engine *e, int32_t id) {
+    GET_IRM(irm, e, id);
+    CK(cudaStreamSynchronize(e->stream));
+    e->irms[id].reset();
+    return 0;
+}
+
+extern "C" int hirm_irm_set_observations(hirm_engine *e, int32_t id, int rel, int64_t nobs, const int32_t *h_ids,
+                                         const uint8_t *h_val) {
+    GET_IRM(irm, e, id);
+    if (rel < 0 || rel >= irm->n_relations) return fail("bad relation index");
+    if (irm->obs.use_count() > 1 || irm->obs->finalized) return fail("observation store is shared or finalized");
+    if (nobs < 0 || (nobs > 0 && (!h_ids || !h_val))) return fail("null observation arrays");
+    const int a = irm->arity[rel];
+    for (int64_t k = 0; k < nobs; k++) {
+        if (h_val[k] > 1) return fail("observation values must be 0 or 1 (BetaBernoulli)");
+        for (int p = 0; p < a; p++) {
+            int32_t v = h_ids[k * a + p];
+            if (v < 0 || v >= irm->n_ent[irm->rdom[rel][p]]) return fail("entity code out of range");
+        }
+    }
+    RelObs &R = irm->obs->rel[rel];
+    R.kind = 0; R.nobs = nobs;
+    R.h_ids.assign(h_ids, h_ids + nobs * a);
+    R.h_val.assign(h_val, h_val + nobs);
+    return 0;
+}
+
+static int check_dense_rel(Irm *irm, int rel) {
+    if (rel < 0 || rel >= irm->n_relations) return fail("bad relation index");
+    if (irm->arity[rel] != 2) return fail("dense slabs are for binary relations");
+    if (irm->obs.use_count() > 1 || irm->obs->finalized) return fail("observation store is shared or finalized");
+    for (int p = 0; p < 2; p++)
+        if (irm->kcap[irm->rdom[rel][p]] > 64) return fail("dense relations need max_tables <= 64");
+    return 0;
+}
+
+extern "C" int hirm_irm_set_observations_dense(hirm_engine *e, int32_t id, int rel, const uint8_t *d_slab0, int64_t pitch0,
+                                               const uint8_t *d_slab1, int64_t pitch1) {
+    GET_IRM(irm, e, id);
+    if (check_dense_rel(irm, rel)) return -1;
+    const int n0 = irm->n_ent[irm->rdom[rel][0]], n1 = irm->n_ent[irm->rdom[rel][1]];
+    if (!d_slab0 || !d_slab1) return fail("null slab");
+    if (pitch0 % 16 || pitch1 % 16 || pitch0 < n1 || pitch1 < n0) return fail("pitches must be multiples of 16 and cover a row");
+    if (((uintptr_t)d_slab0 | (uintptr_t)d_slab1) & 15) return fail("slabs must be 16-byte aligned");
+    RelObs &R = irm->obs->rel[rel];
+    R.kind = 1; R.nobs = (int64_t)n0 * n1;
+    R.slab[0] = d_slab0; R.slab[1] = d_slab1; R.pitch[0] = pitch0; R.pitch[1] = pitch1;
+    return 0;
+}
+
+extern "C" int hirm_engine_transpose_u8(hirm_engine *e, const uint8_t *d_in, int64_t rows, int64_t cols, int64_t pitch_in,
+                                        uint8_t *d_out, int64_t pitch_out) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64)), block(64, 8);
+    transpose_u8_kernel<<<grid, block, 0, e->stream>>>(d_in, rows, cols, pitch_in, d_out, pitch_out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hirm_irm_set_observations_dense_host(hirm_engine *e, int32_t id, int rel, const uint8_t *h_x, int64_t h_pitch) {
+    GET_IRM(irm, e, id);
+    if (check_dense_rel(irm, rel)) return -1;
+    const int64_t n0 = irm->n_ent[irm->rdom[rel][0]], n1 = irm->n_ent[irm->rdom[rel][1]];
+    if (!h_x || h_pitch < n1) return fail("bad host matrix");
+    RelObs &R = irm->obs->rel[rel];
+    const int64_t p0 = (n1 + 15) & ~(int64_t)15, p1 = (n0 + 15) & ~(int64_t)15;
+    CK(R.own_slab0.alloc((size_t)(n0 * p0)));
+    CK(R.own_slab1.alloc((size_t)(n1 * p1)));
+    CK(cudaMemsetAsync(R.own_slab0.p, 0xFF, (size_t)(n0 * p0), e->stream));
+    CK(cudaMemcpy2DAsync(R.own_slab0.p, (size_t)p0, h_x, (size_t)h_pitch, (size_t)n1, (size_t)n0, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(R.own_slab1.p, 0xFF, (size_t)(n1 * p1), e->stream));
+    if (hirm_engine_transpose_u8(e, R.own_slab0.p, n0, n1, p0, R.own_slab1.p, p1)) return -1;
+    R.kind = 1; R.nobs = n0 * n1;
+    R.slab[0] = R.own_slab0.p; R.slab[1] = R.own_slab1.p; R.pitch[0] = p0; R.pitch[1] = p1;
+    return 0;
+}
+
+extern "C" int hirm_irm_share_observations(hirm_engine *e, int32_t dst, int32_t src) {
+    GET_IRM(a, e, dst);
+    Irm *b = get_irm(e, src);
+    if (!b) return fail("bad source irm id");
+    if (a->n_domains != b->n_domains || a->n_relations != b->n_relations || a->n_ent != b->n_ent || a->kcap != b->kcap ||
+        a->arity != b->arity || a->rdom != b->rdom)
+        return fail("schemas differ");
+    if (!b->obs->finalized) return fail("finalize the source irm first");
+    a->obs = b->obs;
+    a->desc_dirty = true; a->counts_dirty = true; a->scratch_ready = false;
+    return 0;
+}
+
+// Build the per-entity CSR of every domain over all CSR-stored relations (Relation::data_r,
+// cxx/hirm.hh:251,274-280) and upload the COO arrays used for count-table rebuilds.
+static int finalize_store(hirm_engine *e, Irm *irm) {
+    ObsStore &S = *irm->obs;
+    if (S.finalized) return 0;
+    for (int r = 0; r < irm->n_relations; r++)
+        if (S.rel[r].kind < 0) { S.rel[r].kind = 0; S.rel[r].nobs = 0; }   // a relation without observations
+    for (int d = 0; d < irm->n_domains; d++) {
+        const int n = irm->n_ent[d];
+        int max_other = 0;
+        std::vector<int64_t> ptr((size_t)n + 1, 0);
+        for (int pass = 0; pass < 2; pass++) {
+            std::vector<int64_t> fill;
+            std::vector<uint32_t> meta; std::vector<int32_t> other;
+            int64_t nnz = 0;
+            if (pass == 1) {
+                for (int i = 0; i < n; i++) ptr[i + 1] += ptr[i];
+                nnz = ptr[n];
+                fill.assign(ptr.begin(), ptr.end() - 1);
+                meta.resize((size_t)nnz); other.assign((size_t)nnz * std::max(1, max_other), 0);
+            }
+            for (int r = 0; r < irm->n_relations; r++) {
+                RelObs &R = S.rel[r];
+                if (R.kind != 0 || R.nobs == 0) continue;
+                const int a = irm->arity[r];
+                bool touches = false;
+                for (int p = 0; p < a; p++) touches |= irm->rdom[r][p] == d;
+                if (!touches) continue;
+                if (pass == 0) max_other = std::max(max_other, a - 1);
+                for (int64_t k = 0; k < R.nobs; k++) {
+                    const int32_t *ids = &R.h_ids[(size_t)k * a];
+                    for (int p = 0; p < a; p++) {
+                        if (irm->rdom[r][p] != d) continue;
+                        const int32_t ent = ids[p];
+                        bool dup = false; uint32_t selfmask = 0;
+                        for (int q = 0; q < a; q++)
+                            if (irm->rdom[r][q] == d && ids[q] == ent) { if (q < p) dup = true; selfmask |= 1u << q; }
+                        if (dup) continue;          // listed once per entity (set semantics of data_r)
+                        if (pass == 0) { ptr[ent + 1]++; continue; }
+                        const int64_t slot = fill[ent]++;
+                        meta[slot] = (uint32_t)r | ((uint32_t)R.h_val[k] << META_VAL_SHIFT) | (selfmask << META_SELF_SHIFT);
+                        int oi = 0;
+                        for (int q = 0; q < a; q++) { if (q == p) continue; other[(size_t)oi * nnz + slot] = ids[q]; oi++; }
+                    }
+                }
+            }
+            if (pass == 1) {
+                DomObs &D = S.dom[d];
+                D.nnz = nnz; D.n_other = std::max(1, max_other); D.max_deg = 0;
+                for (int i = 0; i < n; i++) D.max_deg = std::max(D.max_deg, ptr[i + 1] - ptr[i]);
+                if (nnz > 0) {
+                    CK(D.ptr.alloc(ptr.size())); CK(cudaMemcpy(D.ptr.p, ptr.data(), ptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+                    CK(D.meta.alloc(meta.size())); CK(cudaMemcpy(D.meta.p, meta.data(), meta.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+                    CK(D.other.alloc(other.size())); CK(cudaMemcpy(D.other.p, other.data(), other.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+                }
+            }
+        }
+    }
+    for (int r = 0; r < irm->n_relations; r++) {
+        RelObs &R = S.rel[r];
+        if (R.kind != 0 || R.nobs == 0) continue;
+        CK(R.coo_ids.alloc(R.h_ids.size())); CK(cudaMemcpy(R.coo_ids.p, R.h_ids.data(), R.h_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(R.coo_val.alloc(R.h_val.size())); CK(cudaMemcpy(R.coo_val.p, R.h_val.data(), R.h_val.size(), cudaMemcpyHostToDevice));
+        std::vector<int32_t>().swap(R.h_ids); std::vector<uint8_t>().swap(R.h_val);
+    }
+    S.finalized = true;
+    return 0;
+}
+
+static int ensure_scratch(hirm_engine *e, Irm *irm) {
+    if (irm->scratch_ready) return 0;
+    ObsStore &S = *irm->obs;
+    int64_t bit = 0;
+    bool any_csr = false;
+    for (int r = 0; r < irm->n_relations; r++) {
+        CK(irm->counts[r].ensure((size_t)irm->ncells[r]));
+        if (S.rel[r].kind == 0) {
+            any_csr = true;
+            CK(irm->groups[r].ensure((size_t)irm->gcells[r]));
+            CK(cudaMemsetAsync(irm->groups[r].p, 0, (size_t)irm->gcells[r] * sizeof(cell_t), e->stream));
+            irm->gbit0[r] = bit;
+            bit += (irm->gcells[r] + 63) / 64 * 64;
+        } else irm->gbit0[r] = 0;
+    }
+    irm->gwords = bit / 64;
+    if (any_csr) {
+        CK(irm->gbitmap.ensure((size_t)irm->gwords));
+        CK(cudaMemsetAsync(irm->gbitmap.p, 0, (size_t)std::max<int64_t>(irm->gwords, 1) * 8, e->stream));
+        std::vector<int32_t> wr((size_t)irm->gwords, 0);
+        for (int r = 0; r < irm->n_relations; r++) {
+            if (S.rel[r].kind != 0) continue;
+            for (int64_t w = irm->gbit0[r] / 64; w < irm->gbit0[r] / 64 + (irm->gcells[r] + 63) / 64; w++) wr[(size_t)w] = r;
+        }
+        CK(irm->word_rel.ensure(wr.size()));
+        if (!wr.empty()) CK(cudaMemcpy(irm->word_rel.p, wr.data(), wr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        int64_t cap = 1;
+        for (int d = 0; d < irm->n_domains; d++) cap = std::max(cap, S.dom[d].max_deg);
+        irm->gl_cap = cap;
+        CK(irm->gl_rel.ensure((size_t)cap)); CK(irm->gl_cell.ensure((size_t)cap));
+    }
+    irm->dense_ree = irm->n_domains == 1 && irm->n_relations == 1 && S.rel[0].kind == 1 && irm->kcap[0] <= 64;
+    irm->scratch_ready = true; irm->desc_dirty = true;
+    return 0;
+}
+
+extern "C" int hirm_irm_finalize(hirm_engine *e, int32_t id) {
+    GET_IRM(irm, e, id);
+    if (finalize_store(e, irm)) return -1;
+    return ensure_scratch(e, irm);
+}
+
+static int upload_desc(hirm_engine *e, int32_t id) {
+    Irm *irm = e->irms[id].get();
+    if (e->h_irms.size() < e->irms.size()) e->h_irms.resize(e->irms.size());
+    if (e->d_irms.n < e->irms.size()) {
+        size_t cap = std::max<size_t>(64, e->irms.size() * 2);
+        CK(cudaStreamSynchronize(e->stream));
+        CK(e->d_irms.alloc(cap));
+        for (auto &p : e->irms) if (p) p->desc_dirty = true;
+        e->h_irms.resize(std::max(e->h_irms.size(), e->irms.size()));
+    }
+    if (!irm->desc_dirty) return 0;
+    ObsStore &S = *irm->obs;
+    std::vector<RelationDev> rd((size_t)irm->n_relations);
+    for (int r = 0; r < irm->n_relations; r++) {
+        RelationDev &R = rd[r];
+        memset(&R, 0, sizeof(R));
+        R.arity = irm->arity[r]; R.kind = S.rel[r].kind;
+        for (int p = 0; p < MAX_ARITY; p++) { R.dom[p] = irm->rdom[r][p]; R.cstride[p] = irm->cstride[r][p]; R.gstride[p] = irm->gstride[r][p]; }
+        R.counts = irm->counts[r].p; R.ncells = irm->ncells[r];
+        R.groups = irm->groups[r].p; R.gcells = irm->gcells[r]; R.gbit0 = irm->gbit0[r];
+        R.slab[0] = S.rel[r].slab[0]; R.slab[1] = S.rel[r].slab[1]; R.pitch[0] = S.rel[r].pitch[0]; R.pitch[1] = S.rel[r].pitch[1];
+        R.coo_ids = S.rel[r].coo_ids.p; R.coo_val = S.rel[r].coo_val.p; R.nobs = S.rel[r].nobs;
+    }
+    CK(irm->d_rel.ensure(rd.size()));
+    if (!rd.empty()) CK(cudaMemcpyAsync(irm->d_rel.p, rd.data(), rd.size() * sizeof(RelationDev), cudaMemcpyHostToDevice, e->stream));
+    IrmDev D;
+    memset(&D, 0, sizeof(D));
+    D.n_domains = irm->n_domains; D.n_relations = irm->n_relations;
+    for (int d = 0; d < irm->n_domains; d++) {
+        DomainDev &dd = D.dom[d];
+        dd.n = irm->n_ent[d]; dd.kcap = irm->kcap[d];
+        dd.z = irm->z[d].p; dd.tab_count = irm->tab_count[d].p; dd.tab_label = irm->tab_label[d].p; dd.hi = irm->hi[d].p;
+        dd.alpha = irm->alpha[d];
+        dd.ptr = S.dom[d].nnz ? S.dom[d].ptr.p : nullptr; dd.meta = S.dom[d].meta.p; dd.other = S.dom[d].other.p;
+        dd.nnz = S.dom[d].nnz; dd.n_other = S.dom[d].n_other;
+    }
+    D.rel = irm->d_rel.p;
+    D.gbitmap = irm->gbitmap.p; D.word_rel = irm->word_rel.p; D.gwords = irm->gwords;
+    D.gl_rel = irm->gl_rel.p; D.gl_cell = irm->gl_cell.p; D.gl_cap = irm->gl_cap;
+    D.error = irm->error.p;
+    e->h_irms[id] = D;
+    // pageable source: make the copy synchronous w.r.t. the host buffers (rd, D are locals)
+    CK(cudaMemcpyAsync(e->d_irms.p + id, &e->h_irms[id], sizeof(IrmDev), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    irm->desc_dirty = false;
+    return 0;
+}
+
+static int check_kernel_error(hirm_engine *e, Irm *irm) {
+    int32_t code = 0;
+    CK(cudaMemcpyAsync(&code, irm->error.p, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (code) {
+        CK(cudaMemsetAsync(irm->error.p, 0, sizeof(int32_t), e->stream));
+        return fail(std::string("kernel error: ") + kerr_text(code));
+    }
+    return 0;
+}
+
+// (re)build every count table from (observations, z)
+static int ensure_counts(hirm_engine *e, int32_t id) {
+    Irm *irm = e->irms[id].get();
+    if (finalize_store(e, irm) || ensure_scratch(e, irm)) return -1;
+    for (int d = 0; d < irm->n_domains; d++)
+        if (!irm->have_z[d]) return fail("set_assignments has not been called for every domain");
+    if (upload_desc(e, id)) return -1;
+    if (!irm->counts_dirty) return 0;
+    ObsStore &S = *irm->obs;
+    for (int r = 0; r < irm->n_relations; r++) {
+        CK(cudaMemsetAsync(irm->counts[r].p, 0, (size_t)irm->ncells[r] * sizeof(cell_t), e->stream));
+        if (S.rel[r].nobs == 0) continue;
+        if (S.rel[r].kind == 0) {
+            int blocks = (int)std::min<int64_t>((S.rel[r].nobs + 255) / 256, 148 * 8);
+            rebuild_counts_coo_kernel<<<blocks, 256, 0, e->stream>>>(e->d_irms.p, id, r);
+        } else {
+            int blocks = std::min(irm->n_ent[irm->rdom[r][0]], e->num_sms * 4);
+            rebuild_counts_dense_kernel<<<blocks, 256, (size_t)irm->ncells[r] * sizeof(cell_t), e->stream>>>(e->d_irms.p, id, r);
+        }
+        CK(cudaGetLastError());
+    }
+    if (check_kernel_error(e, irm)) return -1;
+    irm->counts_dirty = false;
+    return 0;
+}
+
+extern "C" int hirm_irm_set_assignments(hirm_engine *e, int32_t id, int dom, const int32_t *h_labels) {
+    GET_IRM(irm, e, id);
+    if (dom < 0 || dom >= irm->n_domains || !h_labels) return fail("bad domain index");
+    const int n = irm->n_ent[dom], kcap = irm->kcap[dom];
+    // slots in ascending label order (deterministic)
+    std::map<int32_t, int32_t> label_slot;
+    for (int i = 0; i < n; i++) if (h_labels[i] >= 0) label_slot[h_labels[i]] = 0;
+    if ((int)label_slot.size() > kcap) return fail("more tables than max_tables");
+    int s = 0;
+    for (auto &kv : label_slot) kv.second = s++;
+    std::vector<int32_t> z((size_t)std::max(n, 1), -1), cnt((size_t)kcap, 0), lab((size_t)kcap, 0);
+    for (auto &kv : label_slot) lab[kv.second] = kv.first;
+    for (int i = 0; i < n; i++) if (h_labels[i] >= 0) { z[i] = label_slot[h_labels[i]]; cnt[z[i]]++; }
+    int32_t hi = (int32_t)label_slot.size();
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(irm->z[dom].p, z.data(), (size_t)std::max(n, 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(irm->tab_count[dom].p, cnt.data(), kcap * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(irm->tab_label[dom].p, lab.data(), kcap * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(irm->hi[dom].p, &hi, sizeof(int32_t), cudaMemcpyHostToDevice));
+    irm->have_z[dom] = true; irm->counts_dirty = true;
+    return 0;
+}
+
+extern "C" int hirm_irm_get_assignments(hirm_engine *e, int32_t id, int dom, int32_t *h_labels) {
+    GET_IRM(irm, e, id);
+    if (dom < 0 || dom >= irm->n_domains || !h_labels) return fail("bad domain index");
+    const int n = irm->n_ent[dom], kcap = irm->kcap[dom];
+    std::vector<int32_t> z((size_t)std::max(n, 1)), lab((size_t)kcap);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(z.data(), irm->z[dom].p, (size_t)std::max(n, 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lab.data(), irm->tab_label[dom].p, kcap * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) h_labels[i] = z[i] < 0 ? -1 : lab[z[i]];
+    return 0;
+}
+
+extern "C" int hirm_irm_set_alpha(hirm_engine *e, int32_t id, int dom, double alpha) {
+    GET_IRM(irm, e, id);
+    if (dom < 0 || dom >= irm->n_domains) return fail("bad domain index");
+    if (!(alpha > 0)) return fail("alpha must be positive");
+    if (irm->alpha[dom] != alpha) { irm->alpha[dom] = alpha; irm->desc_dirty = true; }
+    return 0;
+}
+
+extern "C" int hirm_irm_get_counts(hirm_engine *e, int32_t id, int rel, int32_t *h_cells, int64_t cap_cells, int64_t *n_cells) {
+    GET_IRM(irm, e, id);
+    if (rel < 0 || rel >= irm->n_relations || !n_cells) return fail("bad relation index");
+    if (ensure_counts(e, id)) return -1;
+    const int a = irm->arity[rel];
+    std::vector<cell_t> tab((size_t)irm->ncells[rel]);
+    CK(cudaMemcpy(tab.data(), irm->counts[rel].p, tab.size() * sizeof(cell_t), cudaMemcpyDeviceToHost));
+    std::vector<std::vector<int32_t>> labs((size_t)a);
+    for (int p = 0; p < a; p++) {
+        const int d = irm->rdom[rel][p];
+        labs[p].resize((size_t)irm->kcap[d]);
+        CK(cudaMemcpy(labs[p].data(), irm->tab_label[d].p, labs[p].size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    std::vector<std::vector<int32_t>> cells;
+    for (int64_t k = 0; k < irm->ncells[rel]; k++) {
+        if (cell_n(tab[(size_t)k]) == 0) continue;     // emptied cells are erased in the reference (cxx/hirm.hh:534-537)
+        std::vector<int32_t> row((size_t)a + 2);
+        int64_t rem = k;
+        for (int p = 0; p < a; p++) { const int kc = irm->kcap[irm->rdom[rel][p]]; row[p] = labs[p][(size_t)(rem % kc)]; rem /= kc; }
+        row[a] = (int32_t)cell_n(tab[(size_t)k]); row[a + 1] = (int32_t)cell_s(tab[(size_t)k]);
+        cells.push_back(std::move(row));
+    }
+    std::sort(cells.begin(), cells.end());
+    *n_cells = (int64_t)cells.size();
+    if (h_cells)
+        for (int64_t k = 0; k < (int64_t)cells.size() && k < cap_cells; k++)
+            memcpy(h_cells + k * (a + 2), cells[(size_t)k].data(), sizeof(int32_t) * (a + 2));
+    return 0;
+}
+
+extern "C" int hirm_irm_logp_score(hirm_engine *e, int32_t id, double *out) {
+    GET_IRM(irm, e, id);
+    if (!out) return fail("out is null");
+    if (ensure_counts(e, id)) return -1;
+    CK(e->s_score.ensure((size_t)std::max(1, irm->n_relations)));
+    for (int r = 0; r < irm->n_relations; r++) {
+        relation_score_kernel<<<1, 1024, 0, e->stream>>>(e->d_irms.p, id, r, e->s_score.p + r);
+        CK(cudaGetLastError());
+    }
+    std::vector<double> rs((size_t)std::max(1, irm->n_relations), 0.0);
+    CK(cudaMemcpyAsync(rs.data(), e->s_score.p, rs.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    double total = 0;
+    for (int r = 0; r < irm->n_relations; r++) total += rs[(size_t)r];
+    // CRP::logp_score (cxx/hirm.hh:123-132): O(K) host arithmetic on the table sizes
+    for (int d = 0; d < irm->n_domains; d++) {
+        std::vector<int32_t> cnt((size_t)irm->kcap[d]);
+        CK(cudaMemcpy(cnt.data(), irm->tab_count[d].p, cnt.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        int N = 0, K = 0; double t2 = 0;
+        for (int c : cnt) if (c > 0) { N += c; K++; t2 += lgamma((double)c); }
+        if (N == 0) continue;
+        total += K * log(irm->alpha[d]) + t2 + lgamma(irm->alpha[d]) - lgamma(N + irm->alpha[d]);
+    }
+    *out = total;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// sweep
+// ---------------------------------------------------------------------------------------
+struct Plan { std::vector<int32_t> generic_blk, dense_blk; DenseLaunch L; };
+
+static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_t flags, Plan &plan) {
+    bool have_dense = false;
+    for (int k = 0; k < n_irms; k++) {
+        Irm *irm = get_irm(e, h_irms[k]);
+        if (!irm) return fail("bad irm id in sweep list");
+        for (int j = 0; j < k; j++) if (h_irms[j] == h_irms[k]) return fail("an irm may appear once per sweep");
+        if (ensure_counts(e, h_irms[k])) return -1;
+        if (irm->dense_ree && !(flags & HIRM_SWEEP_FORCE_GENERIC)) {
+            int hist_words = 8192;                 // 32 KiB of private bins: all 512 threads up to 16 tables
+            int stages = 3;
+            DenseLaunch L = dense_layout(irm->n_ent[0], irm->kcap[0], stages, hist_words);
+            while (L.total_bytes > e->max_smem_optin && stages > 1) L = dense_layout(irm->n_ent[0], irm->kcap[0], --stages, hist_words);
+            if (L.total_bytes > e->max_smem_optin) return fail("domain too large for the dense fast path's shared-memory state");
+            if (have_dense && (L.n != plan.L.n || L.kcap != plan.L.kcap)) return fail("dense irms of one sweep must share a shape");
+            plan.L = L; have_dense = true;
+            plan.dense_blk.push_back(k);
+        } else {
+            for (auto &R : irm->obs->rel)
+                if (R.kind == 1) return fail("no kernel for this irm: dense slabs are supported for a single R(e,e) relation only");
+            plan.generic_blk.push_back(k);
+        }
+    }
+    return 0;
+}
+
+static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args) {
+    e->last_launches = 0; e->last_kind = -1;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    if (!plan.generic_blk.empty()) {
+        generic_sweep_kernel<<<(unsigned)plan.generic_blk.size(), GEN_THREADS, 0, e->stream>>>(args, e->s_blk.p);
+        CK(cudaGetLastError());
+        e->last_launches++; e->last_kind = 0;
+    }
+    if (!plan.dense_blk.empty()) {
+        CK(cudaFuncSetAttribute(dense_ree_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.L.total_bytes));
+        dense_ree_sweep_kernel<<<(unsigned)plan.dense_blk.size(), DENSE_THREADS, (size_t)plan.L.total_bytes, e->stream>>>(
+            args, e->s_blk.p + plan.generic_blk.size(), plan.L);
+        CK(cudaGetLastError());
+        e->last_launches++; e->last_kind = 1;
+    }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    return 0;
+}
+
+static int upload_blk(hirm_engine *e, const Plan &plan) {
+    std::vector<int32_t> blk(plan.generic_blk);
+    blk.insert(blk.end(), plan.dense_blk.begin(), plan.dense_blk.end());
+    CK(e->s_blk.ensure(blk.size()));
+    CK(cudaMemcpyAsync(e->s_blk.p, blk.data(), blk.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int hirm_engine_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, const int64_t *h_move_offsets,
+                                 const int32_t *h_move_dom, const int32_t *h_move_item, const double *h_uniforms,
+                                 uint64_t seed, const uint64_t *h_stream, const uint64_t *h_counter0, uint32_t flags,
+                                 int32_t *h_out_choice, int trace_cap, int32_t *h_trace_n, int32_t *h_trace_labels,
+                                 double *h_trace_logps) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n_irms <= 0) return 0;
+    if (!h_irms || !h_move_offsets || !h_move_dom || !h_move_item) return fail("null argument");
+    if (trace_cap > 0 && (!h_trace_n || !h_trace_labels || !h_trace_logps)) return fail("null trace buffers");
+    if (h_move_offsets[0] != 0) return fail("move offsets must start at 0");
+    for (int k = 0; k < n_irms; k++) if (h_move_offsets[k + 1] < h_move_offsets[k]) return fail("move offsets must be non-decreasing");
+    const int64_t nm = h_move_offsets[n_irms];
+    Plan plan;
+    if (plan_sweep(e, n_irms, h_irms, flags, plan)) return -1;
+    if (upload_blk(e, plan)) return -1;
+    const size_t nmz = (size_t)std::max<int64_t>(nm, 1);
+    std::vector<uint64_t> zeros((size_t)n_irms, 0), streams((size_t)n_irms);
+    for (int k = 0; k < n_irms; k++) streams[(size_t)k] = h_stream ? h_stream[k] : (uint64_t)h_irms[k];
+    CK(e->s_irm_ids.ensure((size_t)n_irms)); CK(e->s_move_off.ensure((size_t)n_irms + 1));
+    CK(e->s_move_dom.ensure(nmz)); CK(e->s_move_item.ensure(nmz)); CK(e->s_choice.ensure(nmz));
+    CK(e->s_stream.ensure((size_t)n_irms)); CK(e->s_counter.ensure((size_t)n_irms));
+    cudaStream_t st = e->stream;
+    CK(cudaMemcpyAsync(e->s_irm_ids.p, h_irms, n_irms * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->s_move_off.p, h_move_offsets, (n_irms + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->s_move_dom.p, h_move_dom, nm * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->s_move_item.p, h_move_item, nm * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->s_stream.p, streams.data(), n_irms * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->s_counter.p, h_counter0 ? h_counter0 : zeros.data(), n_irms * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (h_uniforms) {
+        CK(e->s_uniforms.ensure(nmz));
+        CK(cudaMemcpyAsync(e->s_uniforms.p, h_uniforms, nm * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (trace_cap > 0) {
+        CK(e->s_trace_n.ensure(nmz)); CK(e->s_trace_labels.ensure(nmz * trace_cap)); CK(e->s_trace_logps.ensure(nmz * trace_cap));
+    }
+    SweepArgs args;
+    memset(&args, 0, sizeof(args));
+    args.irms = e->d_irms.p; args.irm_ids = e->s_irm_ids.p; args.move_off = e->s_move_off.p;
+    args.move_dom = e->s_move_dom.p; args.move_item = e->s_move_item.p;
+    args.uniforms = h_uniforms ? e->s_uniforms.p : nullptr;
+    args.seed = seed; args.stream = e->s_stream.p; args.counter0 = e->s_counter.p; args.flags = flags;
+    args.out_choice = e->s_choice.p;
+    args.trace_cap = trace_cap; args.trace_n = e->s_trace_n.p; args.trace_labels = e->s_trace_labels.p; args.trace_logps = e->s_trace_logps.p;
+    if (launch_sweep(e, plan, args)) return -1;
+    if (h_out_choice) CK(cudaMemcpyAsync(h_out_choice, e->s_choice.p, nm * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (trace_cap > 0) {
+        CK(cudaMemcpyAsync(h_trace_n, e->s_trace_n.p, nm * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_trace_labels, e->s_trace_labels.p, nm * trace_cap * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_trace_logps, e->s_trace_logps.p, nm * trace_cap * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    for (int k = 0; k < n_irms; k++)
+        if (check_kernel_error(e, e->irms[h_irms[k]].get())) return -1;
+    return 0;
+}
+
+extern "C" int hirm_engine_sweep_device(hirm_engine *e, int n_irms, const int32_t *h_irms, const int64_t *d_move_offsets,
+                                        const int32_t *d_move_dom, const int32_t *d_move_item, uint64_t seed,
+                                        const uint64_t *d_stream, const uint64_t *d_counter0, uint32_t flags,
+                                        int32_t *d_out_choice) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n_irms <= 0) return 0;
+    if (!h_irms || !d_move_offsets || !d_move_dom || !d_move_item || !d_stream || !d_counter0) return fail("null argument");
+    Plan plan;
+    if (plan_sweep(e, n_irms, h_irms, flags, plan)) return -1;
+    if (upload_blk(e, plan)) return -1;
+    CK(e->s_irm_ids.ensure((size_t)n_irms));
+    CK(cudaMemcpyAsync(e->s_irm_ids.p, h_irms, n_irms * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    SweepArgs args;
+    memset(&args, 0, sizeof(args));
+    args.irms = e->d_irms.p; args.irm_ids = e->s_irm_ids.p; args.move_off = d_move_offsets;
+    args.move_dom = d_move_dom; args.move_item = d_move_item; args.uniforms = nullptr;
+    args.seed = seed; args.stream = d_stream; args.counter0 = d_counter0; args.flags = flags;
+    args.out_choice = d_out_choice; args.trace_cap = 0;
+    return launch_sweep(e, plan, args);
+}
+
+extern "C" int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, int32_t *kernel_kind, float *kernel_ms) {
+    if (!e) return fail("engine is null");
+    if (n_launches) *n_launches = e->last_launches;
+    if (kernel_kind) *kernel_kind = e->last_kind;
+    if (kernel_ms) {
+        CK(cudaEventSynchronize(e->ev1));
+        CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+        *kernel_ms = e->last_ms;
+    }
+    return 0;
+}

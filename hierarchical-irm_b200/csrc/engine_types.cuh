@@ -1,0 +1,98 @@
+// Device-visible descriptors of one IRM's state.  Built by the host (engine.cu),
+// uploaded once per change; all pointers are device pointers.
+#pragma once
+#include <cstdint>
+#include "device_math.cuh"
+
+namespace hirm {
+
+constexpr int MAX_ARITY = 4;
+constexpr int MAX_DOMAINS = 8;
+constexpr int SELF_NONE = -1;
+
+// meta word of one CSR entry: relation index, observed value, mask of the positions
+// at which the row's entity itself sits
+constexpr int META_REL_BITS = 20;
+constexpr uint32_t META_REL_MASK = (1u << META_REL_BITS) - 1;
+constexpr int META_VAL_SHIFT = 20;
+constexpr int META_SELF_SHIFT = 24;
+
+struct DomainDev {
+    int32_t n;            // entities
+    int32_t kcap;         // table slots
+    int32_t *z;           // [n] slot of each entity, -1 = not in the domain        (CRP::assignments, cxx/hirm.hh:75)
+    int32_t *tab_count;   // [kcap] customers per slot, 0 = free                     (CRP::tables sizes, :74)
+    int32_t *tab_label;   // [kcap] reference table label of the slot
+    int32_t *hi;          // [1] highest used slot + 1
+    double alpha;         // CRP::alpha (:72)
+    // per-entity CSR over ALL CSR-stored relations touching this domain            (Relation::data_r, :251)
+    const int64_t *ptr;   // [n+1] or null
+    const uint32_t *meta; // [nnz]
+    const int32_t *other; // [n_other][nnz]: entity ids at every position except the first self position
+    int64_t nnz;
+    int32_t n_other;
+    int32_t pad;
+};
+
+struct RelationDev {
+    int32_t arity;
+    int32_t kind;                 // 0 = CSR, 1 = dense slabs
+    int32_t dom[MAX_ARITY];
+    cell_t *counts;               // dense count table, index = sum_p slot_p * cstride[p]   (Relation::clusters, :246)
+    int64_t cstride[MAX_ARITY];
+    int64_t ncells;
+    cell_t *groups;               // per-move group accumulator, radix (kcap_p + 1), digit kcap_p = "self"
+    int64_t gstride[MAX_ARITY];
+    int64_t gcells;
+    int64_t gbit0;                // first bit of this relation in the IRM's group bitmap (multiple of 64)
+    const uint8_t *slab[2];       // dense: rows by first / by second entity
+    int64_t pitch[2];
+    const int32_t *coo_ids;       // [nobs*arity] (CSR relations: kept for count-table rebuilds)
+    const uint8_t *coo_val;
+    int64_t nobs;
+};
+
+struct IrmDev {
+    int32_t n_domains, n_relations;
+    DomainDev dom[MAX_DOMAINS];
+    const RelationDev *rel;       // [n_relations]
+    // generic-kernel scratch
+    unsigned long long *gbitmap;  // [gwords] one bit per group-accumulator cell that is non-zero
+    int32_t *word_rel;            // [gwords] relation owning each bitmap word
+    int64_t gwords;
+    int32_t *gl_rel;              // compacted group list
+    int64_t *gl_cell;             // index into rel.groups
+    int64_t gl_cap;
+    int32_t *error;               // [1] first error code raised by a kernel (0 = none)
+};
+
+// kernel error codes (reported through hirm_last_error)
+enum : int32_t {
+    KERR_NONE = 0,
+    KERR_NO_FREE_SLOT = 1,     // max_tables exhausted
+    KERR_ABSENT_ENTITY = 2,    // observation endpoint with z = -1
+    KERR_GROUP_OVERFLOW = 3,   // group list capacity exceeded
+    KERR_BAD_MOVE = 4,         // move names an entity outside the domain
+};
+
+__device__ __forceinline__ void raise_error(const IrmDev &irm, int32_t code) { atomicCAS(irm.error, 0, code); }
+
+struct SweepArgs {
+    const IrmDev *irms;           // [all irms of the engine]
+    const int32_t *irm_ids;       // [n_irms] which IRM each block sweeps
+    const int64_t *move_off;      // [n_irms+1]
+    const int32_t *move_dom;
+    const int32_t *move_item;
+    const double *uniforms;       // nullable
+    uint64_t seed;
+    const uint64_t *stream;       // [n_irms]
+    const uint64_t *counter0;     // [n_irms]
+    uint32_t flags;
+    int32_t *out_choice;          // nullable
+    int32_t trace_cap;
+    int32_t *trace_n;
+    int32_t *trace_labels;
+    double *trace_logps;
+};
+
+}  // namespace hirm

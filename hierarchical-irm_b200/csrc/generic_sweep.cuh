@@ -1,0 +1,333 @@
+// Generic sweep kernel: any mix of relations of arity <= 4 stored as per-entity CSR.
+// One thread block per IRM, resident across that IRM's whole move list (moves of one
+// IRM are sequentially dependent, cxx/hirm.hh:606-641; IRMs are independent).
+//
+// Per move (domain d, entity i, current slot c):
+//   A  stream i's CSR row; every observation is (1) removed from its count-table cell
+//      (the "rest" counts) and (2) added to the group accumulator keyed by the cluster
+//      tuple with a SELF digit at i's own positions      -> get_cluster_to_items_list (cxx/hirm.hh:388-397)
+//   B  ordered compaction of the touched accumulator cells into the group list
+//   C  candidate tables + CRP prior, ascending label      -> CRP::tables_weights_gibbs (:147-161)
+//   D  lp[t] = log w_t + sum over target cells of S(N+n, s+sg) - S(N, s)
+//                                                         -> logp_gibbs_exact (:441-461)
+//   E  sample with the injected uniform / Philox          -> log_choice (cxx/util_math.cc:58-65)
+//   F  add the groups back at the chosen slot, re-seat    -> set_cluster_assignment_gibbs (:524-551, :219-224)
+// All state is mutated with integer atomics / L2 (.cg) accesses, so count tables are
+// bit-exact and, because the group list is ordered, log-probabilities are deterministic.
+#pragma once
+#include "engine_types.cuh"
+
+namespace hirm {
+
+constexpr int GEN_THREADS = 256;
+constexpr int GEN_WARPS = GEN_THREADS / 32;
+constexpr int GEN_MAXK = 256;   // kcap <= 255 candidates + 1 fresh
+
+struct GroupRef {
+    const RelationDev *R;
+    int a, b;            // positions of the moved domain (b = -1 if it occurs once)
+    int da, db;          // digits at a, b
+    int64_t rest_g;      // accumulator index without positions a, b
+    int64_t rest_c;      // count-table index without positions a, b
+    int kd;              // SELF digit of the moved domain
+    cell_t own;
+};
+
+__device__ __forceinline__ GroupRef decode_group(const IrmDev &irm, int d, int rel, int64_t cellidx) {
+    GroupRef g;
+    const RelationDev *R = &irm.rel[rel];
+    g.R = R; g.a = -1; g.b = -1; g.da = 0; g.db = 0; g.rest_g = 0; g.rest_c = 0;
+    g.kd = irm.dom[d].kcap;
+    int64_t rem = cellidx;
+    for (int p = 0; p < R->arity; p++) {
+        int radix = irm.dom[R->dom[p]].kcap + 1;
+        int digit = (int)(rem % radix);
+        rem /= radix;
+        if (R->dom[p] == d && g.a < 0) { g.a = p; g.da = digit; }
+        else if (R->dom[p] == d) { g.b = p; g.db = digit; }
+        else { g.rest_g += digit * R->gstride[p]; g.rest_c += digit * R->cstride[p]; }
+    }
+    g.own = __ldcg(&R->groups[cellidx]);
+    return g;
+}
+
+// Resolve the group against candidate slot t: returns false if another group owns the
+// merged target cell; otherwise the merged (n, s) to add and the count-table index.
+__device__ __forceinline__ bool group_target(const GroupRef &g, int t, cell_t &delta, int64_t &cidx) {
+    const RelationDev *R = g.R;
+    if (g.b < 0) {                                   // domain occurs once: no merging
+        delta = g.own;
+        cidx = g.rest_c + t * R->cstride[g.a];
+        return true;
+    }
+    const int64_t ga = R->gstride[g.a], gb = R->gstride[g.b];
+    const int64_t ca = R->cstride[g.a], cb = R->cstride[g.b];
+    const int SELF = g.kd;
+    if (g.da == SELF && g.db == SELF) {              // (i, i): target (t, t); absorbs row/col groups whose other end sits in t
+        delta = g.own + __ldcg(&R->groups[g.rest_g + SELF * ga + t * gb]) + __ldcg(&R->groups[g.rest_g + t * ga + SELF * gb]);
+        cidx = g.rest_c + t * ca + t * cb;
+        return true;
+    }
+    if (g.da == SELF) {                              // i at position a, other end in slot db
+        if (g.db != t) { delta = g.own; cidx = g.rest_c + t * ca + g.db * cb; return true; }
+        if (cell_n(__ldcg(&R->groups[g.rest_g + SELF * ga + SELF * gb])) > 0) return false;
+        delta = g.own + __ldcg(&R->groups[g.rest_g + t * ga + SELF * gb]);
+        cidx = g.rest_c + t * ca + t * cb;
+        return true;
+    }
+    // i at position b, other end in slot da
+    if (g.da != t) { delta = g.own; cidx = g.rest_c + g.da * ca + t * cb; return true; }
+    if (cell_n(__ldcg(&R->groups[g.rest_g + SELF * ga + SELF * gb])) > 0) return false;
+    if (cell_n(__ldcg(&R->groups[g.rest_g + SELF * ga + t * gb])) > 0) return false;
+    delta = g.own;
+    cidx = g.rest_c + t * ca + t * cb;
+    return true;
+}
+
+// count-table index of the group's cell when the entity sits in slot t (no merging: used
+// to add the groups back, where integer adds merge by themselves)
+__device__ __forceinline__ int64_t group_cell_at(const GroupRef &g, int t) {
+    const RelationDev *R = g.R;
+    int64_t c = g.rest_c + (g.da == g.kd ? t : g.da) * R->cstride[g.a];
+    if (g.b >= 0) c += (g.db == g.kd ? t : g.db) * R->cstride[g.b];
+    return c;
+}
+
+__global__ void __launch_bounds__(GEN_THREADS) generic_sweep_kernel(SweepArgs args, const int32_t *blk_list) {
+    const int k_list = blk_list ? blk_list[blockIdx.x] : blockIdx.x;
+    const IrmDev &irm = args.irms[args.irm_ids[k_list]];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    __shared__ int32_t s_cnt[GEN_MAXK], s_lab[GEN_MAXK];
+    __shared__ int32_t s_cslot[GEN_MAXK + 1], s_clabel[GEN_MAXK + 1];
+    __shared__ double s_lp[GEN_MAXK + 1];
+    __shared__ int32_t s_warp_tot[GEN_WARPS];
+    __shared__ int32_t s_ncand, s_choice_slot, s_choice_label, s_fail;
+    __shared__ int64_t s_ngroups;
+
+    const int64_t m0 = args.move_off[k_list], m1 = args.move_off[k_list + 1];
+    for (int64_t m = m0; m < m1; m++) {
+        const int d = args.move_dom[m], item = args.move_item[m];
+        bool bad = d < 0 || d >= irm.n_domains || item < 0 || item >= irm.dom[d < 0 ? 0 : d].n;
+        const DomainDev &dd = irm.dom[bad ? 0 : d];
+        const int c = bad ? -1 : __ldcg(&dd.z[item]);
+        if (c < 0) {                                  // uniform across the block
+            if (tid == 0) {
+                raise_error(irm, KERR_BAD_MOVE);
+                if (args.out_choice) args.out_choice[m] = -1;
+                if (args.trace_cap > 0) args.trace_n[m] = 0;
+            }
+            continue;
+        }
+        if (tid == 0) s_fail = 0;
+
+        // ---- A: remove + group ---------------------------------------------------------
+        if (dd.ptr) {
+            const int64_t beg = dd.ptr[item], end = dd.ptr[item + 1];
+            for (int64_t q = beg + tid; q < end; q += GEN_THREADS) {
+                const uint32_t meta = dd.meta[q];
+                const int rel = meta & META_REL_MASK;
+                const uint32_t val = (meta >> META_VAL_SHIFT) & 1u, selfmask = (meta >> META_SELF_SHIFT) & 0xFu;
+                const RelationDev *R = &irm.rel[rel];
+                int64_t gidx = 0, cidx = 0;
+                int oi = 0; bool first = true, absent = false;
+                for (int p = 0; p < R->arity; p++) {
+                    int slot, gd;
+                    if ((selfmask >> p) & 1u) {
+                        if (first) first = false; else oi++;
+                        slot = c; gd = dd.kcap;
+                    } else {
+                        const int id = dd.other[(int64_t)oi * dd.nnz + q]; oi++;
+                        slot = __ldcg(&irm.dom[R->dom[p]].z[id]);
+                        if (slot < 0) { absent = true; slot = 0; }
+                        gd = slot;
+                    }
+                    gidx += gd * R->gstride[p];
+                    cidx += slot * R->cstride[p];
+                }
+                if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); continue; }
+                const cell_t one = pack_cell(1u, val);
+                const cell_t old = atomicAdd(&R->groups[gidx], one);
+                if (cell_n(old) == 0) {
+                    const int64_t bit = R->gbit0 + gidx;
+                    atomicOr(&irm.gbitmap[bit >> 6], 1ull << (bit & 63));
+                }
+                atomicAdd(&R->counts[cidx], (cell_t)0 - one);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+
+        // ---- B: ordered compaction of the touched accumulator cells -----------------------
+        int64_t base = 0;
+        for (int64_t w0 = 0; w0 < irm.gwords; w0 += GEN_THREADS) {
+            const int64_t w = w0 + tid;
+            unsigned long long bits = w < irm.gwords ? __ldcg(&irm.gbitmap[w]) : 0ull;
+            const int cnt = __popcll(bits);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_warp_tot[warp] = incl;
+            __syncthreads();
+            int woff = 0, total = 0;
+#pragma unroll
+            for (int k = 0; k < GEN_WARPS; k++) { int v = s_warp_tot[k]; if (k < warp) woff += v; total += v; }
+            int64_t off = base + woff + incl - cnt;
+            if (bits) {
+                const int rel = irm.word_rel[w];
+                const int64_t bit0 = irm.rel[rel].gbit0;
+                while (bits) {
+                    const int bpos = __ffsll((long long)bits) - 1;
+                    bits &= bits - 1;
+                    if (off < irm.gl_cap) { irm.gl_rel[off] = rel; irm.gl_cell[off] = w * 64 + bpos - bit0; }
+                    else raise_error(irm, KERR_GROUP_OVERFLOW);
+                    off++;
+                }
+            }
+            base += total;
+            __syncthreads();
+        }
+        const int64_t ngroups = base < irm.gl_cap ? base : irm.gl_cap;
+
+        // ---- C: candidates -------------------------------------------------------------
+        const int hi = __ldcg(dd.hi);
+        for (int k = tid; k < hi; k += GEN_THREADS) { s_cnt[k] = __ldcg(&dd.tab_count[k]); s_lab[k] = __ldcg(&dd.tab_label[k]); }
+        __syncthreads();
+        if (tid == 0) {
+            int n = 0, maxlab = 0, freeslot = -1;      // t_max starts at 0 (cxx/hirm.hh:139)
+            for (int k = 0; k < hi; k++) {
+                if (s_cnt[k] > 0) maxlab = max(maxlab, s_lab[k]);
+                else if (freeslot < 0) freeslot = k;
+            }
+            if (freeslot < 0 && hi < dd.kcap) freeslot = hi;
+            const bool singleton = s_cnt[c] == 1;
+            for (int k = 0; k < hi; k++) {
+                const int cnt = s_cnt[k] - (k == c ? 1 : 0);
+                if (cnt > 0) { s_cslot[n] = k; s_clabel[n] = s_lab[k]; s_lp[n] = log((double)cnt); n++; }
+            }
+            if (singleton) {                           // own table re-offered with weight alpha, no extra fresh table (:152-159)
+                s_cslot[n] = c; s_clabel[n] = s_lab[c]; s_lp[n] = log(dd.alpha); n++;
+            } else if (freeslot >= 0) {                // fresh table, label max+1 (:144)
+                s_cslot[n] = freeslot; s_clabel[n] = maxlab + 1; s_lp[n] = log(dd.alpha); n++;
+            } else {
+                raise_error(irm, KERR_NO_FREE_SLOT); s_fail = 1;
+            }
+            for (int i = 1; i < n; i++) {              // ascending label order
+                const int sl = s_cslot[i], lb = s_clabel[i]; const double lw = s_lp[i];
+                int j = i - 1;
+                while (j >= 0 && s_clabel[j] > lb) { s_cslot[j + 1] = s_cslot[j]; s_clabel[j + 1] = s_clabel[j]; s_lp[j + 1] = s_lp[j]; j--; }
+                s_cslot[j + 1] = sl; s_clabel[j + 1] = lb; s_lp[j + 1] = lw;
+            }
+            s_ncand = n;
+        }
+        __syncthreads();
+        const int ncand = s_ncand;
+
+        // ---- D: score: one warp per candidate, lanes over groups --------------------------
+        for (int t = warp; t < ncand; t += GEN_WARPS) {
+            const int slot_t = s_cslot[t];
+            double acc = 0.0;
+            for (int64_t g = lane; g < ngroups; g += 32) {
+                const GroupRef gr = decode_group(irm, d, irm.gl_rel[g], irm.gl_cell[g]);
+                cell_t delta; int64_t cidx;
+                if (!group_target(gr, slot_t, delta, cidx)) continue;
+                const cell_t cur = __ldcg(&gr.R->counts[cidx]);
+                acc += score_delta(cell_n(cur), cell_s(cur), cell_n(delta), cell_s(delta));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) s_lp[t] += acc;
+        }
+        __syncthreads();
+
+        // ---- E: sample -----------------------------------------------------------------
+        if (tid == 0) {
+            int idx = 0;
+            if (args.flags & 1u) {                     // HIRM_SWEEP_SCORE_ONLY: stay
+                for (int t = 0; t < ncand; t++) if (s_cslot[t] == c) idx = t;
+            } else {
+                const double u = args.uniforms ? args.uniforms[m]
+                                               : philox_uniform(args.seed, args.stream[k_list], args.counter0[k_list] + (uint64_t)(m - m0));
+                idx = choose_index(s_lp, ncand, u);
+            }
+            if (s_fail || ncand == 0) { s_choice_slot = c; s_choice_label = s_lab[c]; }
+            else { s_choice_slot = s_cslot[idx]; s_choice_label = s_clabel[idx]; }
+            if (args.out_choice) args.out_choice[m] = s_choice_label;
+            if (args.trace_cap > 0) args.trace_n[m] = ncand;
+        }
+        if (args.trace_cap > 0) {
+            for (int t = tid; t < ncand && t < args.trace_cap; t += GEN_THREADS) {
+                args.trace_labels[m * args.trace_cap + t] = s_clabel[t];
+                args.trace_logps[m * args.trace_cap + t] = s_lp[t];
+            }
+        }
+        __syncthreads();
+
+        // ---- F: apply ------------------------------------------------------------------
+        const int tnew = s_choice_slot;
+        for (int64_t g = tid; g < ngroups; g += GEN_THREADS) {
+            const int rel = irm.gl_rel[g]; const int64_t cellidx = irm.gl_cell[g];
+            const GroupRef gr = decode_group(irm, d, rel, cellidx);
+            atomicAdd(&gr.R->counts[group_cell_at(gr, tnew)], gr.own);
+            __stcg(&gr.R->groups[cellidx], (cell_t)0);
+            __stcg(&irm.gbitmap[(gr.R->gbit0 + cellidx) >> 6], 0ull);
+        }
+        if (tid == 0 && tnew != c) {
+            __stcg(&dd.z[item], tnew);
+            __stcg(&dd.tab_count[c], s_cnt[c] - 1);
+            const int newcnt = (tnew < hi ? s_cnt[tnew] : 0) + 1;
+            __stcg(&dd.tab_count[tnew], newcnt);
+            if (newcnt == 1) __stcg(&dd.tab_label[tnew], s_choice_label);
+            int nhi = max(hi, tnew + 1);
+            if (s_cnt[c] == 1) {                       // table c emptied: CRP::unincorporate erases it (:95-97)
+                while (nhi > 0 && (nhi - 1 == c || (nhi - 1 != tnew && (nhi - 1 >= hi || s_cnt[nhi - 1] == 0)))) nhi--;
+            }
+            __stcg(dd.hi, nhi);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Count-table rebuild: the table is the histogram of (observations, z)   (cxx/hirm.hh:281-289)
+// ---------------------------------------------------------------------------------------
+__global__ void rebuild_counts_coo_kernel(const IrmDev *irms, int irm_id, int rel) {
+    const IrmDev &irm = irms[irm_id];
+    const RelationDev *R = &irm.rel[rel];
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < R->nobs; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t cidx = 0; bool absent = false;
+        for (int p = 0; p < R->arity; p++) {
+            const int slot = irm.dom[R->dom[p]].z[R->coo_ids[e * R->arity + p]];
+            if (slot < 0) absent = true;
+            cidx += (slot < 0 ? 0 : slot) * R->cstride[p];
+        }
+        if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); continue; }
+        atomicAdd(&R->counts[cidx], pack_cell(1u, R->coo_val[e]));
+    }
+}
+
+// Sum of BetaBernoulli::logp_score over the cells of one relation   (Relation::logp_score, cxx/hirm.hh:516-522)
+// Single block, fixed reduction tree: deterministic.
+__global__ void __launch_bounds__(1024) relation_score_kernel(const IrmDev *irms, int irm_id, int rel, double *out) {
+    const RelationDev *R = &irms[irm_id].rel[rel];
+    __shared__ double s_part[32];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < R->ncells; i += blockDim.x) {
+        const cell_t c = R->counts[i];
+        if (cell_n(c)) acc += cell_score(cell_n(c), cell_s(c));
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) *out = v;
+    }
+}
+
+}  // namespace hirm

@@ -1,0 +1,264 @@
+"""ctypes binding of the C ABI in include/hirm_engine.h (libhirm_engine.so).
+
+This is the only way Python reaches the CUDA kernels; there is no CPU implementation
+behind it -- importing works anywhere (so that the symbol table can be checked on a
+CPU box) but creating an Engine without a CUDA device raises.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+import build as _build  # noqa: E402  (hierarchical-irm_b200/build.py)
+
+MAX_ARITY = 4
+MAX_DOMAINS = 8
+DENSE_MISSING = 0xFF
+SWEEP_SCORE_ONLY = 1
+SWEEP_FORCE_GENERIC = 2
+SWEEP_CLUSTER = 4
+
+EXPORTS = [
+    "hirm_last_error", "hirm_engine_abi_version", "hirm_engine_create", "hirm_engine_destroy",
+    "hirm_engine_set_stream", "hirm_engine_synchronize", "hirm_irm_create", "hirm_irm_destroy",
+    "hirm_irm_set_observations", "hirm_irm_set_observations_dense", "hirm_irm_set_observations_dense_host",
+    "hirm_irm_share_observations", "hirm_irm_finalize", "hirm_irm_set_assignments", "hirm_irm_get_assignments",
+    "hirm_irm_set_alpha", "hirm_irm_get_counts", "hirm_irm_logp_score", "hirm_engine_sweep",
+    "hirm_engine_sweep_device", "hirm_engine_last_sweep_info", "hirm_engine_transpose_u8",
+]
+
+_lib = None
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_u64p = ctypes.POINTER(ctypes.c_uint64)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """dlopen the engine (building it with nvcc if the .so is missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    L = ctypes.CDLL(path)
+    V = ctypes.c_void_p
+    I = ctypes.c_int
+    L.hirm_last_error.restype = ctypes.c_char_p
+    L.hirm_engine_create.argtypes = [ctypes.POINTER(V), I]
+    L.hirm_engine_destroy.argtypes = [V]
+    L.hirm_engine_set_stream.argtypes = [V, V]
+    L.hirm_engine_synchronize.argtypes = [V]
+    L.hirm_irm_create.argtypes = [V, I, c_i32p, c_i32p, I, c_i32p, c_i32p, c_i32p]
+    L.hirm_irm_destroy.argtypes = [V, ctypes.c_int32]
+    L.hirm_irm_set_observations.argtypes = [V, ctypes.c_int32, I, ctypes.c_int64, c_i32p, c_u8p]
+    L.hirm_irm_set_observations_dense.argtypes = [V, ctypes.c_int32, I, V, ctypes.c_int64, V, ctypes.c_int64]
+    L.hirm_irm_set_observations_dense_host.argtypes = [V, ctypes.c_int32, I, V, ctypes.c_int64]
+    L.hirm_irm_share_observations.argtypes = [V, ctypes.c_int32, ctypes.c_int32]
+    L.hirm_irm_finalize.argtypes = [V, ctypes.c_int32]
+    L.hirm_irm_set_assignments.argtypes = [V, ctypes.c_int32, I, c_i32p]
+    L.hirm_irm_get_assignments.argtypes = [V, ctypes.c_int32, I, c_i32p]
+    L.hirm_irm_set_alpha.argtypes = [V, ctypes.c_int32, I, ctypes.c_double]
+    L.hirm_irm_get_counts.argtypes = [V, ctypes.c_int32, I, c_i32p, ctypes.c_int64, c_i64p]
+    L.hirm_irm_logp_score.argtypes = [V, ctypes.c_int32, c_f64p]
+    L.hirm_engine_sweep.argtypes = [V, I, c_i32p, c_i64p, c_i32p, c_i32p, c_f64p, ctypes.c_uint64, c_u64p, c_u64p,
+                                    ctypes.c_uint32, c_i32p, I, c_i32p, c_i32p, c_f64p]
+    L.hirm_engine_sweep_device.argtypes = [V, I, c_i32p, V, V, V, ctypes.c_uint64, V, V, ctypes.c_uint32, V]
+    L.hirm_engine_last_sweep_info.argtypes = [V, c_i32p, c_i32p, ctypes.POINTER(ctypes.c_float)]
+    L.hirm_engine_transpose_u8.argtypes = [V, V, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, V, ctypes.c_int64]
+    _lib = L
+    return L
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+class Engine:
+    """One engine per GPU (hirm_engine_create)."""
+
+    def __init__(self, device=-1):
+        self.L = load()
+        h = ctypes.c_void_p()
+        self._h = None
+        self._ck(self.L.hirm_engine_create(ctypes.byref(h), device))
+        self._h = h
+        self._schemas = {}
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(self.L.hirm_last_error().decode())
+
+    def close(self):
+        if self._h is not None:
+            self.L.hirm_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- schema / observations -------------------------------------------------------
+    def irm_create(self, n_entities, rel_domains, max_tables=32):
+        ne = np.ascontiguousarray(n_entities, dtype=np.int32)
+        if np.isscalar(max_tables):
+            max_tables = [max_tables] * len(ne)
+        mt = np.ascontiguousarray(max_tables, dtype=np.int32)
+        ar = np.ascontiguousarray([len(ds) for ds in rel_domains], dtype=np.int32)
+        rd = np.zeros((max(1, len(rel_domains)), MAX_ARITY), dtype=np.int32)
+        for r, ds in enumerate(rel_domains):
+            rd[r, :len(ds)] = ds
+        out = ctypes.c_int32()
+        self._ck(self.L.hirm_irm_create(self._h, len(ne), _p(ne, c_i32p), _p(mt, c_i32p), len(rel_domains),
+                                        _p(ar, c_i32p), _p(rd, c_i32p), ctypes.byref(out)))
+        self._schemas[out.value] = ([int(x) for x in ne], [list(map(int, ds)) for ds in rel_domains])
+        return out.value
+
+    def irm_destroy(self, irm):
+        self._ck(self.L.hirm_irm_destroy(self._h, irm))
+        self._schemas.pop(irm, None)
+
+    def set_observations(self, irm, rel, ids, val):
+        a = len(self._schemas[irm][1][rel])
+        ids = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1, a)
+        val = np.ascontiguousarray(val, dtype=np.uint8)
+        assert len(ids) == len(val)
+        self._ck(self.L.hirm_irm_set_observations(self._h, irm, rel, len(val), _p(ids, c_i32p), _p(val, c_u8p)))
+
+    def set_observations_dense(self, irm, rel, slab0_ptr, pitch0, slab1_ptr, pitch1):
+        self._ck(self.L.hirm_irm_set_observations_dense(self._h, irm, rel, slab0_ptr, pitch0, slab1_ptr, pitch1))
+
+    def set_observations_dense_host(self, irm, rel, x):
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        self._ck(self.L.hirm_irm_set_observations_dense_host(self._h, irm, rel, x.ctypes.data, x.strides[0]))
+        self.synchronize()
+
+    def set_observations_dense_host_ptr(self, irm, rel, ptr, pitch):
+        self._ck(self.L.hirm_irm_set_observations_dense_host(self._h, irm, rel, ptr, pitch))
+
+    def share_observations(self, dst, src):
+        self._ck(self.L.hirm_irm_share_observations(self._h, dst, src))
+
+    def finalize(self, irm):
+        self._ck(self.L.hirm_irm_finalize(self._h, irm))
+
+    # -- state -------------------------------------------------------------------------
+    def set_assignments(self, irm, dom, labels):
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        assert len(labels) == self._schemas[irm][0][dom]
+        self._ck(self.L.hirm_irm_set_assignments(self._h, irm, dom, _p(labels, c_i32p)))
+
+    def get_assignments(self, irm, dom):
+        out = np.empty(max(1, self._schemas[irm][0][dom]), dtype=np.int32)
+        self._ck(self.L.hirm_irm_get_assignments(self._h, irm, dom, _p(out, c_i32p)))
+        return out[:self._schemas[irm][0][dom]]
+
+    def set_alpha(self, irm, dom, alpha):
+        self._ck(self.L.hirm_irm_set_alpha(self._h, irm, dom, float(alpha)))
+
+    def get_counts(self, irm, rel):
+        a = len(self._schemas[irm][1][rel])
+        n = ctypes.c_int64()
+        self._ck(self.L.hirm_irm_get_counts(self._h, irm, rel, None, 0, ctypes.byref(n)))
+        out = np.empty((max(1, n.value), a + 2), dtype=np.int32)
+        self._ck(self.L.hirm_irm_get_counts(self._h, irm, rel, _p(out, c_i32p), n.value, ctypes.byref(n)))
+        return out[:n.value]
+
+    def logp_score(self, irm):
+        out = ctypes.c_double()
+        self._ck(self.L.hirm_irm_logp_score(self._h, irm, ctypes.byref(out)))
+        return out.value
+
+    # -- the hot path --------------------------------------------------------------------
+    def sweep(self, irms, moves, uniforms=None, seed=0, streams=None, counters=None, flags=0, trace_cap=0):
+        """moves: list (one per irm) of (move_dom, move_item) arrays.
+        Returns dict(choice=[...per irm], trace=[(n, labels, logps) per irm] or None)."""
+        irms = np.ascontiguousarray(irms, dtype=np.int32)
+        off = np.zeros(len(irms) + 1, dtype=np.int64)
+        for k, (md, mi) in enumerate(moves):
+            assert len(md) == len(mi)
+            off[k + 1] = off[k] + len(md)
+        nm = int(off[-1])
+        md = np.ascontiguousarray(np.concatenate([np.asarray(m[0], dtype=np.int32) for m in moves]) if nm else np.zeros(0, np.int32))
+        mi = np.ascontiguousarray(np.concatenate([np.asarray(m[1], dtype=np.int32) for m in moves]) if nm else np.zeros(0, np.int32))
+        un = None
+        if uniforms is not None:
+            un = np.ascontiguousarray(np.concatenate([np.asarray(u, dtype=np.float64) for u in uniforms]))
+            assert len(un) == nm
+        st = None if streams is None else np.ascontiguousarray(streams, dtype=np.uint64)
+        ct = None if counters is None else np.ascontiguousarray(counters, dtype=np.uint64)
+        choice = np.empty(max(nm, 1), dtype=np.int32)
+        tn = tl = tp = None
+        if trace_cap > 0:
+            tn = np.zeros(max(nm, 1), dtype=np.int32)
+            tl = np.zeros((max(nm, 1), trace_cap), dtype=np.int32)
+            tp = np.zeros((max(nm, 1), trace_cap), dtype=np.float64)
+        self._ck(self.L.hirm_engine_sweep(self._h, len(irms), _p(irms, c_i32p), _p(off, c_i64p), _p(md, c_i32p),
+                                          _p(mi, c_i32p), _p(un, c_f64p), seed, _p(st, c_u64p), _p(ct, c_u64p),
+                                          flags, _p(choice, c_i32p), trace_cap, _p(tn, c_i32p), _p(tl, c_i32p),
+                                          _p(tp, c_f64p)))
+        res = dict(choice=[choice[off[k]:off[k + 1]] for k in range(len(irms))], trace=None)
+        if trace_cap > 0:
+            res["trace"] = [(tn[off[k]:off[k + 1]], tl[off[k]:off[k + 1]], tp[off[k]:off[k + 1]]) for k in range(len(irms))]
+        return res
+
+    def sweep_device(self, irms, d_move_off, d_move_dom, d_move_item, seed, d_stream, d_counter, flags=0, d_out_choice=None):
+        irms = np.ascontiguousarray(irms, dtype=np.int32)
+        self._ck(self.L.hirm_engine_sweep_device(self._h, len(irms), _p(irms, c_i32p), d_move_off, d_move_dom,
+                                                 d_move_item, seed, d_stream, d_counter, flags, d_out_choice))
+
+    def last_sweep_info(self):
+        n, k, ms = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_float()
+        self._ck(self.L.hirm_engine_last_sweep_info(self._h, ctypes.byref(n), ctypes.byref(k), ctypes.byref(ms)))
+        return dict(launches=n.value, kernel_kind=k.value, kernel_ms=ms.value)
+
+    def transpose_u8(self, d_in, rows, cols, pitch_in, d_out, pitch_out):
+        self._ck(self.L.hirm_engine_transpose_u8(self._h, d_in, rows, cols, pitch_in, d_out, pitch_out))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.hirm_engine_set_stream(self._h, cuda_stream_ptr))
+
+    def synchronize(self):
+        self._ck(self.L.hirm_engine_synchronize(self._h))
+
+
+class IrmBackend:
+    """score/move/get_* view of one engine IRM (what tests/golden_util.replay drives)."""
+
+    def __init__(self, engine, irm):
+        self.e, self.irm = engine, irm
+
+    def set_alpha(self, dom, alpha):
+        self.e.set_alpha(self.irm, dom, alpha)
+
+    def get_assignments(self, dom):
+        return self.e.get_assignments(self.irm, dom)
+
+    def get_counts(self, rel):
+        return self.e.get_counts(self.irm, rel)
+
+    def logp_score(self):
+        return self.e.logp_score(self.irm)
+
+    def score(self, dom, item, cap=256):
+        r = self.e.sweep([self.irm], [([dom], [item])], flags=SWEEP_SCORE_ONLY, trace_cap=cap)
+        n, labels, lp = r["trace"][0]
+        return labels[0, :n[0]].copy(), lp[0, :n[0]].copy()
+
+    def move(self, dom, item, u):
+        r = self.e.sweep([self.irm], [([dom], [item])], uniforms=[[u]])
+        return int(r["choice"][0][0])

@@ -1,0 +1,135 @@
+/*
+ * hirm_engine.h -- C ABI of the B200 engine for HIRM's collapsed-Gibbs entity move.
+ *
+ * The reference (probsys/hierarchical-irm) has no FFI; its boundary for this path is the
+ * method surface of IRM / Relation / Domain / CRP.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference tree).  Plain C
+ * types only: no torch / STL types cross this boundary.  INTEGRATION.md shows the
+ * ctypes binding used by the Python facade and the C++ shim a maintainer would add to
+ * cxx/hirm.cc.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; hirm_last_error() gives the text
+ *    (thread local).  Nothing aborts or throws across the boundary (the reference
+ *    asserts/aborts: cxx/hirm.hh:35,205,293).
+ *  - h_ = host pointer, d_ = device pointer (caller allocated, never freed by the engine).
+ *  - entities are int32 codes 0..n-1 per domain (cxx/util_io.cc:63-96 encode_observations),
+ *    tables are identified by int32 *labels* exactly as in the reference (new label =
+ *    max label + 1, never compacted: cxx/hirm.hh:133-161); the engine keeps a private
+ *    label<->slot map.
+ *  - one engine per GPU and host thread; one engine holds many IRMs (the relation
+ *    clusters of an HIRM, or independent chains) and sweeps them in one launch.
+ *  - there is no CPU fallback: every call fails with an error if CUDA is unusable.
+ */
+#ifndef HIRM_ENGINE_H
+#define HIRM_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIRM_MAX_ARITY 4      /* positions per relation */
+#define HIRM_MAX_DOMAINS 8    /* domains per IRM */
+#define HIRM_DENSE_MISSING 0xFF
+
+typedef struct hirm_engine hirm_engine;
+
+/* sweep flags */
+#define HIRM_SWEEP_SCORE_ONLY 1u   /* score + trace, do not sample/apply (parity hook) */
+#define HIRM_SWEEP_FORCE_GENERIC 2u /* use the CSR/generic kernel even where a fast path exists */
+#define HIRM_SWEEP_CLUSTER 4u      /* dense path: one thread-block cluster per IRM (single-chain latency mode) */
+
+const char *hirm_last_error(void);
+int hirm_engine_abi_version(void);
+
+/* Engine lifetime.  device < 0 selects the current CUDA device. */
+int hirm_engine_create(hirm_engine **out, int device);
+int hirm_engine_destroy(hirm_engine *e);
+/* run all engine work on this CUDA stream (a cudaStream_t cast to void*); NULL = default stream */
+int hirm_engine_set_stream(hirm_engine *e, void *cuda_stream);
+int hirm_engine_synchronize(hirm_engine *e);
+
+/* IRM::IRM(schema) + IRM::add_relation   (cxx/hirm.hh:570-575,742-757; src/hirm.py:379-386,435-446)
+ * rel_domains: [n_relations * HIRM_MAX_ARITY] domain index per position.
+ * max_tables:  [n_domains] table slots kept on the device per domain (>= tables ever alive + 1). */
+int hirm_irm_create(hirm_engine *e, int n_domains, const int32_t *n_entities, const int32_t *max_tables,
+                    int n_relations, const int32_t *arity, const int32_t *rel_domains, int32_t *out_irm);
+int hirm_irm_destroy(hirm_engine *e, int32_t irm);
+
+/* Bulk IRM::incorporate(r, items, value)   (cxx/hirm.hh:582 -> Relation::incorporate :271-290;
+ * cxx/util_io.cc:98-112 incorporate_observations).  COO on the host: h_ids [nobs*arity], h_val
+ * [nobs] in {0,1}.  Builds the per-entity CSR index that replaces Relation::data_r
+ * (cxx/hirm.hh:251,274-280): one entry per (entity, observation), an observation listed once per
+ * entity even if the entity sits at two positions.  Observations must be distinct
+ * (cxx/hirm.hh:272).  Call for every relation, then hirm_irm_finalize(). */
+int hirm_irm_set_observations(hirm_engine *e, int32_t irm, int rel, int64_t nobs,
+                              const int32_t *h_ids, const uint8_t *h_val);
+/* Dense binary relation R(d0,d1) as two byte slabs in device memory (0, 1, HIRM_DENSE_MISSING):
+ *   d_slab0[i*pitch0 + j] = value of (i, j)   i in d0, j in d1   ("rows by first entity")
+ *   d_slab1[j*pitch1 + i] = value of (i, j)                      ("rows by second entity")
+ * pitches in bytes, multiples of 16; buffers stay owned by the caller and may be shared by many IRMs. */
+int hirm_irm_set_observations_dense(hirm_engine *e, int32_t irm, int rel,
+                                    const uint8_t *d_slab0, int64_t pitch0,
+                                    const uint8_t *d_slab1, int64_t pitch1);
+/* Same, from a host matrix h_x[i*h_pitch + j]; the engine uploads it and builds the transpose on the
+ * device (engine-owned buffers). */
+int hirm_irm_set_observations_dense_host(hirm_engine *e, int32_t irm, int rel, const uint8_t *h_x, int64_t h_pitch);
+/* Make irm_dst use irm_src's observation store (same schema; independent chains over one dataset). */
+int hirm_irm_share_observations(hirm_engine *e, int32_t irm_dst, int32_t irm_src);
+int hirm_irm_finalize(hirm_engine *e, int32_t irm);
+
+/* Domain::incorporate(item, table) for every entity   (cxx/hirm.hh:194-203; forced seats as in
+ * from_txt cxx/util_io.cc:328-337).  h_labels [n_entities[dom]], -1 = entity not in the domain.
+ * The count tables (Relation::clusters, cxx/hirm.hh:246) are rebuilt from (observations, z) on the
+ * device at the next use: they are a histogram (cxx/hirm.hh:281-289). */
+int hirm_irm_set_assignments(hirm_engine *e, int32_t irm, int dom, const int32_t *h_labels);
+/* CRP::assignments read-back (cxx/hirm.hh:75) */
+int hirm_irm_get_assignments(hirm_engine *e, int32_t irm, int dom, int32_t *h_labels);
+/* CRP::alpha (cxx/hirm.hh:72); set by the host after CRP::transition_alpha (:162-173) */
+int hirm_irm_set_alpha(hirm_engine *e, int32_t irm, int dom, double alpha);
+/* Relation::clusters read-back (cxx/hirm.hh:246): non-empty cells, lexicographically sorted,
+ * (arity + 2) int32 per cell: table labels..., N, s.  *n_cells gets the count even if > cap. */
+int hirm_irm_get_counts(hirm_engine *e, int32_t irm, int rel, int32_t *h_cells, int64_t cap_cells, int64_t *n_cells);
+/* IRM::logp_score   (cxx/hirm.hh:730-740) */
+int hirm_irm_logp_score(hirm_engine *e, int32_t irm, double *out);
+
+/* The hot path.  For each listed IRM, in order, the moves
+ *     IRM::transition_cluster_assignment_item(d, item)     (cxx/hirm.hh:606-641; src/hirm.py:401-421)
+ * i.e. CRP::tables_weights_gibbs (:147) + Relation::logp_gibbs_exact (:441) + log_choice
+ * (cxx/util_math.cc:58) + Relation::set_cluster_assignment_gibbs (:524) + Domain::set_cluster_assignment_gibbs (:219),
+ * in the explicit order given (the sweep loops cxx/hirm.hh:590-604, cxx/hirm.cc:45-51,73-81).
+ * IRMs are independent and run concurrently; moves of one IRM are sequential.
+ *   h_move_offsets [n_irms+1]  moves of irm k are [off[k], off[k+1])
+ *   h_move_dom / h_move_item   per move
+ *   h_uniforms     nullable; per move uniform in [0,1) (parity: "same uniforms => same assignment")
+ *                  when NULL move m of irm k uses Philox4x32-10(key=seed, ctr=(h_counter0[k]+m, h_stream[k]))
+ *   h_out_choice   nullable; per move chosen table label
+ *   trace_cap>0:   per move candidate labels/log-probabilities (ascending label order):
+ *                  h_trace_n [n_moves], h_trace_labels/logps [n_moves*trace_cap]
+ */
+int hirm_engine_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, const int64_t *h_move_offsets,
+                      const int32_t *h_move_dom, const int32_t *h_move_item, const double *h_uniforms,
+                      uint64_t seed, const uint64_t *h_stream, const uint64_t *h_counter0, uint32_t flags,
+                      int32_t *h_out_choice, int trace_cap, int32_t *h_trace_n, int32_t *h_trace_labels,
+                      double *h_trace_logps);
+
+/* Same launch with every array already resident on the device and no host synchronisation:
+ * the call bench.py times for the HBM-resident figure.  d_out_choice nullable. */
+int hirm_engine_sweep_device(hirm_engine *e, int n_irms, const int32_t *h_irms, const int64_t *d_move_offsets,
+                             const int32_t *d_move_dom, const int32_t *d_move_item, uint64_t seed,
+                             const uint64_t *d_stream, const uint64_t *d_counter0, uint32_t flags,
+                             int32_t *d_out_choice);
+
+/* statistics of the last sweep: kernel launches made, which kernel ran (0 generic, 1 dense, 2 dense-cluster) */
+int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, int32_t *kernel_kind, float *kernel_ms);
+
+/* device helper: out[j*pitch_out + i] = in[i*pitch_in + j] for a rows x cols byte matrix */
+int hirm_engine_transpose_u8(hirm_engine *e, const uint8_t *d_in, int64_t rows, int64_t cols, int64_t pitch_in,
+                             uint8_t *d_out, int64_t pitch_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
