@@ -34,6 +34,34 @@ __device__ __forceinline__ double lfact_diff(int64_t a, int64_t m) {
     return (y - 0.5) * log1p(dm / y) + dm * log(y + dm) - dm + (stirling_corr(y + dm) - stirling_corr(y));
 }
 
+// 1/y for y >= 1: MUFU.RCP seed + two Newton steps in fp64 (the fp64 divide is a long dependent chain)
+__device__ __forceinline__ double fast_rcp(double y) {
+    double r = (double)__frcp_rn((float)y);
+    r = r * (2.0 - y * r);
+    return r * (2.0 - y * r);
+}
+__device__ __forceinline__ double stirling_corr_r(double r) {   // same series, argument r = 1/y
+    double r2 = r * r;
+    return r * (1.0 / 12.0 - r2 * (1.0 / 360.0 - r2 * (1.0 / 1260.0)));
+}
+// lfact_diff(a, m) split into two halves that each cost at most ONE transcendental, so that two lanes
+// can evaluate them concurrently (fp64 dependent-issue latency is what bounds a move):
+//   lfact_half(a, m, 0) + lfact_half(a, m, 1) == lfact_diff(a, m)   (up to rounding)
+__device__ __forceinline__ double lfact_half(int64_t a, int64_t m, int half) {
+    if (m == 0) return 0.0;
+    if (a + m < LF_SIZE) return half ? 0.0 : g_logfact[a + m] - g_logfact[a];
+    if (m == 1) return half ? 0.0 : log((double)(a + 1));
+    if (a < LF_SIZE) {
+        if (half) return 0.0;
+        const double y2 = (double)(a + m + 1);
+        return (y2 - 0.5) * log(y2) - y2 + 0.91893853320467274178 + stirling_corr_r(fast_rcp(y2)) - g_logfact[a];
+    }
+    const double y = (double)(a + 1), dm = (double)m;
+    if (half) return dm * log(y + dm);
+    const double ry = fast_rcp(y);
+    return (y - 0.5) * log1p(dm * ry) - dm + (stirling_corr_r(fast_rcp(y + dm)) - stirling_corr_r(ry));
+}
+
 // BetaBernoulli::logp_score (cxx/hirm.hh:52-56), alpha = beta = 1:
 //   S(N, s) = lgamma(s+1) + lgamma(N-s+1) - lgamma(N+2)
 // score_delta = S(N+n, s+sg) - S(N, s): what logp_gibbs_exact_variant returns for one
@@ -76,16 +104,17 @@ __device__ __host__ __forceinline__ double philox_uniform(uint64_t seed, uint64_
 // log_choice (cxx/util_math.cc:58-65) with the inversion rule of random.Random.choices
 // (src/util_math.py:24-28): p = exp(lp - logsumexp(lp)); first index whose running sum
 // exceeds u * sum(p); capped at n-1.  Candidates are in ascending label order.
+// The rule is scale invariant -- sum_{j<=i} p_j > u sum_j p_j  <=>  sum_{j<=i} e_j > u sum_j e_j with
+// e_j = exp(lp_j - max lp) -- so one exp per candidate suffices (no log, no second exp on the
+// dependent chain); it picks the same index except when u falls within rounding of a CDF step.
 __device__ __forceinline__ int choose_index(const double *lp, int n, double u) {
     double m = lp[0];
     for (int i = 1; i < n; i++) m = fmax(m, lp[i]);
-    double s = 0;
-    for (int i = 0; i < n; i++) s += exp(lp[i] - m);
-    double Z = log(s) + m, total = 0;
-    for (int i = 0; i < n; i++) total += exp(lp[i] - Z);
+    double total = 0;
+    for (int i = 0; i < n; i++) total += exp(lp[i] - m);
     double x = u * total, c = 0;
     for (int i = 0; i < n; i++) {
-        c += exp(lp[i] - Z);
+        c += exp(lp[i] - m);
         if (c > x) return i;
     }
     return n - 1;

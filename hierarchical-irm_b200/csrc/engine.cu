@@ -106,6 +106,7 @@ struct hirm_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_kind = -1; float last_ms = 0.f;
     int max_smem_optin = 0, num_sms = 0;
+    long long *d_phase_cycles = nullptr;   // debug hook (hirm_engine_debug_phase_cycles)
 };
 
 static const char *kerr_text(int code) {
@@ -633,7 +634,7 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
         for (int j = 0; j < k; j++) if (h_irms[j] == h_irms[k]) return fail("an irm may appear once per sweep");
         if (ensure_counts(e, h_irms[k])) return -1;
         if (irm->dense_ree && !(flags & HIRM_SWEEP_FORCE_GENERIC)) {
-            int hist_words = 8192;                 // 32 KiB of private bins: all 512 threads up to 16 tables
+            int hist_words = std::max(8192, 2 * irm->kcap[0] * irm->kcap[0]);   // 32 KiB of private bins (also the compaction scratch)
             int stages = 3;
             DenseLaunch L = dense_layout(irm->n_ent[0], irm->kcap[0], stages, hist_words);
             while (L.total_bytes > e->max_smem_optin && stages > 1) L = dense_layout(irm->n_ent[0], irm->kcap[0], --stages, hist_words);
@@ -720,7 +721,7 @@ extern "C" int hirm_engine_sweep(hirm_engine *e, int n_irms, const int32_t *h_ir
     args.move_dom = e->s_move_dom.p; args.move_item = e->s_move_item.p;
     args.uniforms = h_uniforms ? e->s_uniforms.p : nullptr;
     args.seed = seed; args.stream = e->s_stream.p; args.counter0 = e->s_counter.p; args.flags = flags;
-    args.out_choice = e->s_choice.p;
+    args.out_choice = e->s_choice.p; args.phase_cycles = e->d_phase_cycles;
     args.trace_cap = trace_cap; args.trace_n = e->s_trace_n.p; args.trace_labels = e->s_trace_labels.p; args.trace_logps = e->s_trace_logps.p;
     if (launch_sweep(e, plan, args)) return -1;
     if (h_out_choice) CK(cudaMemcpyAsync(h_out_choice, e->s_choice.p, nm * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -755,7 +756,7 @@ extern "C" int hirm_engine_sweep_device(hirm_engine *e, int n_irms, const int32_
     args.irms = e->d_irms.p; args.irm_ids = e->s_irm_ids.p; args.move_off = d_move_offsets;
     args.move_dom = d_move_dom; args.move_item = d_move_item; args.uniforms = nullptr;
     args.seed = seed; args.stream = d_stream; args.counter0 = d_counter0; args.flags = flags;
-    args.out_choice = d_out_choice; args.trace_cap = 0;
+    args.out_choice = d_out_choice; args.trace_cap = 0; args.phase_cycles = e->d_phase_cycles;
     return launch_sweep(e, plan, args);
 }
 
@@ -768,5 +769,13 @@ extern "C" int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, 
         CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
         *kernel_ms = e->last_ms;
     }
+    return 0;
+}
+
+// Debug hook: give the dense kernel a device buffer [n_blocks * 16] of int64 to fill with thread 0's
+// per-phase SM cycles (wait, accumulate, reduce, candidates, score, sample, apply).  NULL switches it off.
+extern "C" int hirm_engine_debug_phase_cycles(hirm_engine *e, long long *d_buf) {
+    if (!e) return fail("engine is null");
+    e->d_phase_cycles = d_buf;
     return 0;
 }

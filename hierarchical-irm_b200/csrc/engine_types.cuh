@@ -93,6 +93,7 @@ struct SweepArgs {
     int32_t *trace_n;
     int32_t *trace_labels;
     double *trace_logps;
+    long long *phase_cycles;      // nullable debug hook: [n_blocks][8] SM cycles per phase (thread 0's clock64)
 };
 
 }  // namespace hirm

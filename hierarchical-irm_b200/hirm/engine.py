@@ -13,7 +13,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _PKG not in sys.path:
     sys.path.insert(0, _PKG)
-import build as _build  # noqa: E402  (hierarchical-irm_b200/build.py)
+import build_engine as _build  # noqa: E402  (hierarchical-irm_b200/build_engine.py)
 
 MAX_ARITY = 4
 MAX_DOMAINS = 8
@@ -29,6 +29,7 @@ EXPORTS = [
     "hirm_irm_share_observations", "hirm_irm_finalize", "hirm_irm_set_assignments", "hirm_irm_get_assignments",
     "hirm_irm_set_alpha", "hirm_irm_get_counts", "hirm_irm_logp_score", "hirm_engine_sweep",
     "hirm_engine_sweep_device", "hirm_engine_last_sweep_info", "hirm_engine_transpose_u8",
+    "hirm_engine_debug_phase_cycles",
 ]
 
 _lib = None
@@ -78,6 +79,7 @@ def load():
     L.hirm_engine_sweep_device.argtypes = [V, I, c_i32p, V, V, V, ctypes.c_uint64, V, V, ctypes.c_uint32, V]
     L.hirm_engine_last_sweep_info.argtypes = [V, c_i32p, c_i32p, ctypes.POINTER(ctypes.c_float)]
     L.hirm_engine_transpose_u8.argtypes = [V, V, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, V, ctypes.c_int64]
+    L.hirm_engine_debug_phase_cycles.argtypes = [V, V]
     _lib = L
     return L
 
@@ -228,6 +230,9 @@ class Engine:
 
     def transpose_u8(self, d_in, rows, cols, pitch_in, d_out, pitch_out):
         self._ck(self.L.hirm_engine_transpose_u8(self._h, d_in, rows, cols, pitch_in, d_out, pitch_out))
+
+    def debug_phase_cycles(self, d_buf_ptr):
+        self._ck(self.L.hirm_engine_debug_phase_cycles(self._h, d_buf_ptr))
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.L.hirm_engine_set_stream(self._h, cuda_stream_ptr))

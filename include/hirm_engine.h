@@ -129,6 +129,10 @@ int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, int32_t *ke
 int hirm_engine_transpose_u8(hirm_engine *e, const uint8_t *d_in, int64_t rows, int64_t cols, int64_t pitch_in,
                              uint8_t *d_out, int64_t pitch_out);
 
+/* debug hook: device buffer [n_blocks * 8] int64 that the dense kernel fills with per-phase SM cycles
+ * (wait, accumulate, reduce, candidates, score, sample, apply); NULL switches it off */
+int hirm_engine_debug_phase_cycles(hirm_engine *e, long long *d_buf);
+
 #ifdef __cplusplus
 }
 #endif
