@@ -1,61 +1,77 @@
 // Dense fast path: an IRM with one domain and one dense binary relation R(e, e)
-// (BASELINE.json config 3).  One persistent CTA per IRM / chain, resident across the
-// IRM's whole move list; every chain streams its own rows of the SHARED read-only slabs.
+// (BASELINE.json config 3).  One persistent CTA per IRM / chain, resident across the IRM's
+// whole move list, several CTAs per SM; every chain streams its own rows of the SHARED
+// read-only slabs.
 //
 // HBM traffic per move = row i of slab0 (the observations (i, j)) + row i of slab1 (the
 // observations (j, i)) = 2 * n bytes: exactly the algorithmic bytes of SURVEY.md 8(d).
 // Everything mutable (z as uint8 slots, the K x K count table, CRP table sizes) lives in
 // shared memory for the whole launch.
 //
-//   stage   TMA 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) fetch the two rows
-//           of the moves NS-1 ahead: the move order is static, so the dependent chain
-//           never waits on HBM latency.
-//   A       grouping i's 2n observations by the other entity's table   -> get_cluster_to_items_list
-//           (cxx/hirm.hh:388-397).  Up to 8 live tables: byte-SIMD one-hot masks of z and
-//           dp4a dot products into registers (no shared-memory traffic at all).  More
-//           tables: per-thread private bins hist[slot][tid] with 4 x 8-bit fields.
-//   B       per-slot group sums, removed from the table in the same pass (the "rest" counts)
-//   C       candidates + CRP prior: built by a dedicated warp WHILE the others accumulate
-//   D       score: 6 lanes per target cell, one transcendental per lane (the move is bound
-//           by fp64 dependent-issue latency, so the chain is kept one log deep)
-//   E/F     sample (one exp per candidate) and apply.
-// The per-move loop body is kept small (each transcendental path exists once, noinline):
-// a single warp running cold code out of the instruction cache was the dominant cost of the
-// first version (profiles/r01_notes.md).
+// The move order is static and the moves of one chain depend on each other only through
+// the K x K count table and ONE entry of z, so the CTA is a three-role pipeline:
+//
+//   P  (1 warp)   TMA producer: 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) of
+//                 row chunks into a ring, running ahead across move boundaries.
+//   A  (3 warps)  accumulate: group move r+1's 2n observations by the other entity's table
+//                 (get_cluster_to_items_list, cxx/hirm.hh:388-397) WHILE move r is being decided.
+//                 z[i_r] is still the old value then; the decision warps move that one
+//                 observation pair to the right group afterwards (an O(1) fix-up).
+//                 <= 8 live tables: byte-SIMD one-hot masks of z and dp4a dot products into
+//                 registers; more: per-thread private bins with 4 x 8-bit fields.
+//   D  (4 warps)  decide move r: candidates + CRP prior (CRP::tables_weights_gibbs, :147-161),
+//                 score (logp_gibbs_exact, :441-461) against the table with i's observations
+//                 removed virtually, sample (log_choice, cxx/util_math.cc:58-65), and only
+//                 if the table changed apply (set_cluster_assignment_gibbs, :524-551, :219-224).
+//
+// Live tables always occupy slots 0..K-1 (a dying table is replaced by the last slot), the
+// slots in ascending label order are kept in s_order, and log(count) per table is cached, so
+// that an unchanged move costs no bookkeeping.
 #pragma once
 #include "engine_types.cuh"
 
 namespace hirm {
 
-constexpr int DENSE_THREADS = 512;
-constexpr int DENSE_WARPS = DENSE_THREADS / 32;
-constexpr int DENSE_ACC_THREADS = DENSE_THREADS - 32;   // the last warp builds the candidates during A
-constexpr int DENSE_ACC_WARPS = DENSE_ACC_THREADS / 32;
-constexpr int DENSE_VEC_PER_THREAD = 15;   // 15 * 16 = 240 elements per thread per chunk (< 256: 8-bit fields)
-constexpr int DENSE_MAX_KD = 8;            // dp4a path: live tables in slots 0..7
+constexpr int DN_A_WARPS = 3;
+constexpr int DN_D_WARPS = 4;
+constexpr int DN_NA = 32 * DN_A_WARPS;
+constexpr int DN_ND = 32 * DN_D_WARPS;
+constexpr int DN_THREADS = 32 + DN_NA + DN_ND;   // warp 0 = producer, then the A warps, then the D warps
+constexpr int DN_MAX_STAGES = 16;
+constexpr int DN_MAX_KD = 8;                      // dp4a path: live tables in slots 0..7
+constexpr int DN_LF = 256;                        // shared-memory copy of lgamma(m+1), m < 256; Stirling (error < 1e-19) beyond
+constexpr int DN_FLUSH_VECS = 15;                 // 15 * 16 = 240 elements per thread between bin flushes (8-bit fields)
 
 struct DenseLaunch {
     int32_t n;          // entities
     int32_t npad;       // n rounded up to 16
-    int32_t kcap;
-    int32_t stages;     // NS (<= 8)
-    int32_t hist_words; // 32-bit words reserved for the private bins (>= 32 * kcap, >= 2 * kcap * kcap)
-    // byte offsets into dynamic shared memory (host-computed, see dense_layout())
-    int32_t off_table, off_lp, off_hist, off_ints, off_zs, off_stage, total_bytes;
+    int32_t kt;         // table slots held in shared memory (= max_tables)
+    int32_t chunk;      // bytes of one row chunk (multiple of 16)
+    int32_t nchunks;    // chunks per row
+    int32_t stages;     // ring depth
+    int32_t bins_words; // 32-bit words of private bins (multiple of 32 * kt is not required: HT adapts)
+    // byte offsets into dynamic shared memory
+    int32_t off_lf, off_table, off_dbl, off_wpart, off_bins, off_ints, off_zs, off_ring, total_bytes;
 };
 
 // Shared-memory carve-up: 8-byte things first, then 4-byte, then the byte arrays (16-aligned).
-__host__ __device__ inline DenseLaunch dense_layout(int n, int kcap, int stages, int hist_words) {
+__host__ __device__ inline DenseLaunch dense_layout(int n, int kt, int chunk, int stages, int bins_words) {
     DenseLaunch L;
-    L.n = n; L.npad = (n + 15) & ~15; L.kcap = kcap; L.stages = stages; L.hist_words = hist_words;
-    int off = 64;                                   // mbarriers
-    L.off_table = off; off += kcap * kcap * 8;
-    L.off_lp = off;    off += 2 * ((kcap + 2) & ~1) * 8;  // s_lp, s_tmp (unsorted log-weights / exp scratch)
-    L.off_hist = off;  off += hist_words * 4;
-    L.off_ints = off;  off += (11 * kcap + 16) * 4; // g_rn g_rs g_cn g_cs s_cnt s_lab s_cslot s_clabel u_slot u_label s_map
+    L.n = n; L.npad = (n + 15) & ~15; L.kt = kt;
+    if (chunk > L.npad) chunk = L.npad;
+    if (chunk < 16) chunk = 16;
+    L.chunk = chunk; L.nchunks = (L.npad + chunk - 1) / chunk; L.stages = stages; L.bins_words = bins_words;
+    int off = 8 * (2 * DN_MAX_STAGES + 4);          // mbarriers: full[S], empty[S], ready[2], go
+    L.off_lf = off;    off += DN_LF * 8;
+    L.off_table = off; off += kt * kt * 8;
+    L.off_dbl = off;   off += 4 * (kt + 2) * 8;     // s_lp, s_tmp, s_logcnt, s_logcntm1
+    L.off_wpart = off; off += 2 * DN_A_WARPS * 4 * kt * 4;
+    L.off_bins = off;  off += bins_words * 4;
+    L.off_ints = off;  off += (2 * 4 * kt + 4 * kt + 8) * 4;   // g[2][4kt], s_cnt, s_lab, s_order, s_map
     off = (off + 15) & ~15;
     L.off_zs = off;    off += L.npad;
-    L.off_stage = off; off += stages * 2 * L.npad;
+    off = (off + 127) & ~127;
+    L.off_ring = off;  off += stages * 2 * chunk;
     L.total_bytes = off;
     return L;
 }
@@ -67,6 +83,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done;
@@ -84,504 +103,778 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
+// named barrier among the D warps only
+__device__ __forceinline__ void bar_d() { asm volatile("bar.sync 1, %0;" ::"n"(DN_ND) : "memory"); }
 
 // nibble code (bit0 valid_row, bit1 x_row, bit2 valid_col, bit3 x_col) -> one increment per 8-bit field
 __device__ __forceinline__ uint32_t code_to_inc(uint32_t code) { return (code * 0x00204081u) & 0x01010101u; }
-
 // four elements at once: per byte, the nibble code of (row byte, col byte); a byte is valid iff < 0x80
 __device__ __forceinline__ uint32_t pack_codes(uint32_t xr, uint32_t xc) {
     const uint32_t vr = (~xr >> 7) & 0x01010101u, vc = (~xc >> 7) & 0x01010101u;
     return vr | ((xr & vr) << 1) | (vc << 2) | ((xc & vc) << 3);
 }
+// (n, s) of one observation byte
+__device__ __forceinline__ int byte_n(uint32_t x) { return (x & 0x80u) ? 0 : 1; }
+__device__ __forceinline__ int byte_s(uint32_t x) { return (x & 0x80u) ? 0 : (int)(x & 1u); }
 
-// One copy of each transcendental path (see header comment).
-__device__ __noinline__ double lfact_half_nl(int64_t a, int64_t m, int half) { return lfact_half(a, m, half); }
-__device__ __noinline__ double log_nl(double x) { return log(x); }
-__device__ __noinline__ double exp_nl(double x) { return exp(x); }
+// bytes at or beyond element n are padding: make them "missing" (or 0 where only ones are counted)
+template <bool ZERO = false>
+__device__ __forceinline__ void mask_tail(uint4 &x, int j0, int n) {
+    uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int keep = n - (j0 + 4 * q);
+        const uint32_t pad = keep <= 0 ? 0xFFFFFFFFu : keep < 4 ? ~((1u << (8 * keep)) - 1u) : 0u;
+        w[q] = ZERO ? (w[q] & ~pad) : (w[q] | pad);
+    }
+    x = make_uint4(w[0], w[1], w[2], w[3]);
+}
 
 // ---- A (dp4a variant): one-hot byte masks of the slot word, dot products into registers --------
-template <int KD>
+// FULL = the relation has no missing cell: every byte is 0 or 1, the per-table observation counts follow
+// from the CRP table sizes, and only the counts of ones (rs, cs) are accumulated.
+template <int KD, bool FULL>
 __device__ __forceinline__ void acc_word(uint32_t xr, uint32_t xc, uint32_t z, int (&rn)[KD], int (&rs)[KD], int (&cn)[KD], int (&cs)[KD]) {
     constexpr uint32_t ONES = 0x01010101u;
-    const uint32_t vr = (~xr >> 7) & ONES, vc = (~xc >> 7) & ONES;   // observed?
-    const uint32_t sr = xr & vr, sc = xc & vc;                        // observed and 1
+    uint32_t vr = 0u, vc = 0u, sr = xr, sc = xc;
+    if (!FULL) {
+        vr = (~xr >> 7) & ONES; vc = (~xc >> 7) & ONES;    // observed?
+        sr = xr & vr; sc = xc & vc;                        // observed and 1
+    }
     const uint32_t b0 = z & ONES, b1 = (z >> 1) & ONES, b2 = (z >> 2) & ONES;
 #pragma unroll
     for (int k = 0; k < KD; k++) {
         uint32_t mk = (k & 1) ? b0 : (b0 ^ ONES);
         if (KD > 2) mk &= (k & 2) ? b1 : (b1 ^ ONES);
         if (KD > 4) mk &= (k & 4) ? b2 : (b2 ^ ONES);
-        rn[k] = (int)__dp4a(mk, vr, (unsigned)rn[k]); rs[k] = (int)__dp4a(mk, sr, (unsigned)rs[k]);
-        cn[k] = (int)__dp4a(mk, vc, (unsigned)cn[k]); cs[k] = (int)__dp4a(mk, sc, (unsigned)cs[k]);
+        if (!FULL) { rn[k] = (int)__dp4a(mk, vr, (unsigned)rn[k]); cn[k] = (int)__dp4a(mk, vc, (unsigned)cn[k]); }
+        rs[k] = (int)__dp4a(mk, sr, (unsigned)rs[k]);
+        cs[k] = (int)__dp4a(mk, sc, (unsigned)cs[k]);
     }
 }
 
-template <int KD>
-__device__ __forceinline__ void accumulate_dp4a(const uint8_t *xrow, const uint8_t *xcol, const uint8_t *zs, int n, int tid,
-                                                int warp, int lane, int32_t *wpart /* [ACC_WARPS][4*DENSE_MAX_KD] */) {
+// lfact_diff (device_math.cuh) for a CONVERGED warp -- all 32 lanes call it together, lanes without work pass
+// m = 0 -- against the shared-memory table lf[DN_LF]: branch-free per lane, each transcendental called once
+// for the whole warp and skipped by warp vote when no lane needs it.
+__device__ __forceinline__ double lfact_diff_warp_s(const double *lf, uint32_t a, uint32_t m, long long *pt = nullptr) {
+#define LFP(i) do { if (pt) pt[i] = clk(); } while (0)
+    LFP(0);
+    const uint32_t am = a + m;
+    const bool small = am < (uint32_t)DN_LF;                    // includes m == 0 with a small a
+    const bool need = m != 0u && !small;
+    const bool big = a >= (uint32_t)DN_LF;
+    const double lfa = lf[min(a, (uint32_t)DN_LF - 1u)];
+    double res = (m != 0u && small) ? lf[min(am, (uint32_t)DN_LF - 1u)] - lfa : 0.0;
+    if (__any_sync(0xffffffffu, need)) {
+        const double y = (double)a + 1.0, dm = (double)m, ym = y + dm;
+        LFP(1);
+        const double L = log_nl(need ? (big ? y : ym) : 1.0);
+        LFP(2);
+        const double c2 = stirling_corr_r(fast_rcp(ym));
+        LFP(3);
+        double r = (ym - 0.5) * L - ym + 0.91893853320467274178 + c2 - lfa;      // a small, a + m large
+        if (__any_sync(0xffffffffu, need && big)) {
+            const double ry = fast_rcp(y);
+            LFP(4);
+            const double P = log1p_nl((need && big) ? dm * ry : 0.0);
+            LFP(5);
+            // (y+m-1/2) ln(y+m) - (y-1/2) ln y - m + corr(y+m) - corr(y),  ln(y+m) = ln y + log1p(m/y)
+            const double rb = (ym - 0.5) * P + dm * (L - 1.0) + (c2 - stirling_corr_r(ry));
+            if (big) r = rb;
+        }
+        if (need) res = r;
+    }
+    LFP(6);
+#undef LFP
+    return res;
+}
+
+// ring cursor shared by the producer and the A warps (each keeps its own copy)
+struct RingCursor {
+    int stage; uint32_t parity;
+    __device__ __forceinline__ void advance(int S) { if (++stage == S) { stage = 0; parity ^= 1u; } }
+};
+
+// shared-space loads (the hot loop addresses shared memory by 32-bit offsets: no generic pointers)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// same, for waits with slack (the A warps' go, the producer's empty): sleep between polls so that the
+// spinning does not take issue slots from the decision warps
+__device__ __forceinline__ void mbar_wait_relaxed_s(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// What an A thread needs to stream a move (all by value, shared-space addresses)
+struct APar {
+    uint32_t full, empty, ring, zs;    // shared addresses: full[0], empty[0], ring, zs
+    int n, npad, chunk, nchunks, stages, bins_words;
+};
+
+template <int KD, bool FULL>
+__device__ __forceinline__ void acc_vec(const uint4 &xr, const uint4 &xc, const uint4 &zz, int (&rn)[KD], int (&rs)[KD], int (&cn)[KD], int (&cs)[KD]) {
+    acc_word<KD, FULL>(xr.x, xc.x, zz.x, rn, rs, cn, cs);
+    acc_word<KD, FULL>(xr.y, xc.y, zz.y, rn, rs, cn, cs);
+    acc_word<KD, FULL>(xr.z, xc.z, zz.z, rn, rs, cn, cs);
+    acc_word<KD, FULL>(xr.w, xc.w, zz.w, rn, rs, cn, cs);
+}
+
+// One move on the dp4a path: stream the two rows through the ring, two 16-element vectors per thread in
+// flight, group sums in registers; per-warp sums to wp[4k..4k+3].
+template <int KD, bool FULL>
+__device__ __forceinline__ void a_move_dp4a(const APar p, RingCursor &cur, const int a, const int lane, int32_t *wp) {
     int rn[KD], rs[KD], cn[KD], cs[KD];
 #pragma unroll
     for (int k = 0; k < KD; k++) { rn[k] = 0; rs[k] = 0; cn[k] = 0; cs[k] = 0; }
-    const int nvec = n >> 4;
     #pragma unroll 1
-    for (int v = tid; v < nvec; v += DENSE_ACC_THREADS) {
-        const uint4 xr = *reinterpret_cast<const uint4 *>(xrow + (size_t)v * 16);
-        const uint4 xc = *reinterpret_cast<const uint4 *>(xcol + (size_t)v * 16);
-        const uint4 zz = *reinterpret_cast<const uint4 *>(zs + (size_t)v * 16);
-        acc_word<KD>(xr.x, xc.x, zz.x, rn, rs, cn, cs);
-        acc_word<KD>(xr.y, xc.y, zz.y, rn, rs, cn, cs);
-        acc_word<KD>(xr.z, xc.z, zz.z, rn, rs, cn, cs);
-        acc_word<KD>(xr.w, xc.w, zz.w, rn, rs, cn, cs);
+    for (int q = 0; q < p.nchunks; q++) {
+        const int base = q * p.chunk;
+        const int bytes = min(p.chunk, p.npad - base);
+        const uint32_t xrow = p.ring + (uint32_t)(cur.stage * 2 * p.chunk), xcol = xrow + (uint32_t)p.chunk, zrow = p.zs + (uint32_t)base;
+        const int nv = bytes >> 4;
+        const bool tail = base + bytes > p.n;          // the row's padding lies in this chunk (uniform)
+        mbar_wait_s(p.full + 8u * cur.stage, cur.parity);
+        #pragma unroll 1
+        for (int v = a; v < nv; v += 2 * DN_NA) {
+            const int v2 = v + DN_NA;
+            const bool two = v2 < nv;
+            uint4 xr0 = lds128(xrow + 16u * v), xc0 = lds128(xcol + 16u * v);
+            const uint4 zz0 = lds128(zrow + 16u * v);
+            constexpr uint32_t PAD = FULL ? 0u : ~0u;           // a byte that contributes nothing
+            uint4 xr1 = make_uint4(PAD, PAD, PAD, PAD), xc1 = xr1, zz1 = make_uint4(0u, 0u, 0u, 0u);
+            if (two) { xr1 = lds128(xrow + 16u * v2); xc1 = lds128(xcol + 16u * v2); zz1 = lds128(zrow + 16u * v2); }
+            if (tail) {
+                mask_tail<FULL>(xr0, base + 16 * v, p.n); mask_tail<FULL>(xc0, base + 16 * v, p.n);
+                mask_tail<FULL>(xr1, base + 16 * v2, p.n); mask_tail<FULL>(xc1, base + 16 * v2, p.n);
+            }
+            acc_vec<KD, FULL>(xr0, xc0, zz0, rn, rs, cn, cs);
+            acc_vec<KD, FULL>(xr1, xc1, zz1, rn, rs, cn, cs);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_s(p.empty + 8u * cur.stage);
+        cur.advance(p.stages);
     }
-    const int j = (nvec << 4) + tid;                  // scalar tail, one element per thread; other bytes masked off as missing
-    if (j < n) acc_word<KD>(xrow[j] | 0xFFFFFF00u, xcol[j] | 0xFFFFFF00u, zs[j], rn, rs, cn, cs);
 #pragma unroll
     for (int k = 0; k < KD; k++) {
-        const int a = __reduce_add_sync(0xffffffffu, rn[k]), b = __reduce_add_sync(0xffffffffu, rs[k]);
-        const int c2 = __reduce_add_sync(0xffffffffu, cn[k]), d = __reduce_add_sync(0xffffffffu, cs[k]);
-        if (lane == 0) {
-            int32_t *p = wpart + warp * (4 * DENSE_MAX_KD) + 4 * k;
-            p[0] = a; p[1] = b; p[2] = c2; p[3] = d;
+        const int s1 = __reduce_add_sync(0xffffffffu, rs[k]), s3 = __reduce_add_sync(0xffffffffu, cs[k]);
+        if (lane == 0) { wp[4 * k + 1] = s1; wp[4 * k + 3] = s3; }
+        if (!FULL) {
+            const int s0 = __reduce_add_sync(0xffffffffu, rn[k]), s2 = __reduce_add_sync(0xffffffffu, cn[k]);
+            if (lane == 0) { wp[4 * k] = s0; wp[4 * k + 2] = s2; }
         }
     }
 }
 
-__global__ void __launch_bounds__(DENSE_THREADS, 1) dense_ree_sweep_kernel(SweepArgs args, const int32_t *blk_list, DenseLaunch L) {
+// this warp's private bins -> += wp[4k..4k+3] for every slot, bins zeroed again
+__device__ __forceinline__ void a_flush_bins(uint32_t *bins, int HT, int K, int a, int lane, int32_t *wp) {
+    __syncwarp();
+    if (a - lane >= HT) return;                       // this warp bins nothing (warp-uniform)
+    #pragma unroll 1
+    for (int k = 0; k < K; k++) {
+        uint32_t wv = 0u;
+        if (a < HT) { wv = bins[k * HT + a]; bins[k * HT + a] = 0u; }
+        const int s0 = __reduce_add_sync(0xffffffffu, (int)(wv & 0xFFu)), s1 = __reduce_add_sync(0xffffffffu, (int)((wv >> 8) & 0xFFu));
+        const int s2 = __reduce_add_sync(0xffffffffu, (int)((wv >> 16) & 0xFFu)), s3 = __reduce_add_sync(0xffffffffu, (int)(wv >> 24));
+        if (lane < 4) wp[4 * k + lane] += lane == 0 ? s0 : lane == 1 ? s1 : lane == 2 ? s2 : s3;
+    }
+    __syncwarp();
+}
+
+// One move on the bins path (more than 8 live tables): bins[slot][thread], 4 x 8-bit fields, flushed into
+// wp before any field can overflow.
+__device__ __forceinline__ void a_move_bins(const APar p, RingCursor &cur, const int a, const int lane, uint32_t *bins, const int K, int32_t *wp) {
+    const int HT = min(DN_NA, (p.bins_words / K) & ~31);
+    #pragma unroll 1
+    for (int idx = lane; idx < 4 * K; idx += 32) wp[idx] = 0;
+    __syncwarp();
+    uint32_t *mine = bins + a;
+    int since = 0;                                    // vectors binned by this thread since the last flush
+    #pragma unroll 1
+    for (int q = 0; q < p.nchunks; q++) {
+        const int base = q * p.chunk;
+        const int bytes = min(p.chunk, p.npad - base);
+        const uint32_t xrow = p.ring + (uint32_t)(cur.stage * 2 * p.chunk), xcol = xrow + (uint32_t)p.chunk, zrow = p.zs + (uint32_t)base;
+        const int nv = bytes >> 4;
+        const int per_thread = (nv + HT - 1) / HT;
+        if (since + per_thread > DN_FLUSH_VECS) { a_flush_bins(bins, HT, K, a, lane, wp); since = 0; }
+        since += per_thread;
+        mbar_wait_s(p.full + 8u * cur.stage, cur.parity);
+        if (a < HT) {
+            #pragma unroll 1
+            for (int v = a; v < nv; v += HT) {
+                uint4 xr = lds128(xrow + 16u * v), xc = lds128(xcol + 16u * v);
+                const uint4 zz = lds128(zrow + 16u * v);
+                const int j0 = base + v * 16;
+                if (j0 + 16 > p.n) { mask_tail(xr, j0, p.n); mask_tail(xc, j0, p.n); }
+                const uint32_t xrw[4] = {xr.x, xr.y, xr.z, xr.w}, xcw[4] = {xc.x, xc.y, xc.z, xc.w}, zw[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const uint32_t codes = pack_codes(xrw[w], xcw[w]);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const uint32_t slot = (zw[w] >> (8 * e)) & 0xFFu;
+                        mine[slot * HT] += code_to_inc((codes >> (8 * e)) & 0xFu);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_s(p.empty + 8u * cur.stage);
+        cur.advance(p.stages);
+    }
+    a_flush_bins(bins, HT, K, a, lane, wp);
+}
+
+__global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArgs args, const int32_t *blk_list, DenseLaunch L) {
     const int k_list = blk_list ? blk_list[blockIdx.x] : blockIdx.x;
     const IrmDev &irm = args.irms[args.irm_ids[k_list]];
     const DomainDev &dd = irm.dom[0];
     const RelationDev &R = irm.rel[0];
+    // everything read more than once from the descriptors goes to registers here: the loops below are full of
+    // asm volatile "memory" clobbers, behind which the compiler must re-load through these references
+    const uint8_t *const slab0 = R.slab[0], *const slab1 = R.slab[1];
+    const int64_t pitch0 = R.pitch[0], pitch1 = R.pitch[1];
+    int32_t *const z_g = dd.z;
+    const int kcap_g = dd.kcap;
+    const double alpha = dd.alpha;
+    const bool full_obs = R.full_obs != 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = L.n, npad = L.npad, kcap = L.kcap, NS = L.stages;
+    const int n = L.n, npad = L.npad, kt = L.kt, NS = L.stages;
 
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);                        // [NS]
-    cell_t *table = reinterpret_cast<cell_t *>(smem + L.off_table);             // [kcap*kcap]  Relation::clusters
-    double *s_lp = reinterpret_cast<double *>(smem + L.off_lp);                 // [kcap+1]
-    double *s_tmp = s_lp + ((kcap + 2) & ~1);
-    uint32_t *hist = reinterpret_cast<uint32_t *>(smem + L.off_hist);           // [hist_words] private bins
-    int32_t *g_rn = reinterpret_cast<int32_t *>(smem + L.off_ints);             // group sums per other-slot
-    int32_t *g_rs = g_rn + kcap, *g_cn = g_rs + kcap, *g_cs = g_cn + kcap;
-    int32_t *s_cnt = g_cs + kcap, *s_lab = s_cnt + kcap;                        // CRP table sizes / labels
-    int32_t *s_cslot = s_lab + kcap, *s_clabel = s_cslot + (kcap + 1);          // candidates (ascending label)
-    int32_t *u_slot = s_clabel + (kcap + 1), *u_label = u_slot + (kcap + 1);    // candidates before sorting
-    int32_t *s_map = u_label + (kcap + 1);                                      // slot compaction map
-    uint8_t *zs = smem + L.off_zs;                                              // [npad] slot of every entity
-    uint8_t *stage0 = smem + L.off_stage;                                       // [NS][2][npad] staged rows
-    __shared__ int32_t s_ncand, s_choice_slot, s_choice_label, s_fail, s_hi, s_holes;
-    __shared__ double s_u, s_logalpha;
-    __shared__ double s_part[DENSE_WARPS];
-    __shared__ int32_t s_wpart[DENSE_ACC_WARPS * 4 * DENSE_MAX_KD];
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem);                     // [DN_MAX_STAGES]
+    uint64_t *bar_empty = bar_full + DN_MAX_STAGES;                              // [DN_MAX_STAGES]
+    uint64_t *bar_ready = bar_empty + DN_MAX_STAGES;                             // [2]  A -> D: groups of move r complete
+    uint64_t *bar_go = bar_ready + 2;                                            // [1]  D -> A: z is stable for move r
+    double *s_lf = reinterpret_cast<double *>(smem + L.off_lf);                  // [DN_LF] lgamma(m+1)
+    cell_t *table = reinterpret_cast<cell_t *>(smem + L.off_table);              // [kt*kt]  Relation::clusters, cell (a, b) at a + b*kt
+    double *s_lp = reinterpret_cast<double *>(smem + L.off_dbl);                 // [kt+2]
+    double *s_tmp = s_lp + (kt + 2);
+    double *s_logcnt = s_tmp + (kt + 2);                                         // log(count) per slot
+    double *s_logcntm1 = s_logcnt + (kt + 2);                                    // log(count - 1) per slot
+    int32_t *wpart = reinterpret_cast<int32_t *>(smem + L.off_wpart);            // [2][A_WARPS][4*kt] per-warp group sums
+    uint32_t *bins = reinterpret_cast<uint32_t *>(smem + L.off_bins);            // [bins_words]
+    int32_t *g_buf = reinterpret_cast<int32_t *>(smem + L.off_ints);             // [2][4*kt]: (rn, rs, cn, cs) per other-slot
+    int32_t *s_cnt = g_buf + 8 * kt, *s_lab = s_cnt + kt;                        // CRP table sizes / labels per slot
+    int32_t *s_order = s_lab + kt, *s_map = s_order + kt;                        // slots by ascending label; load-time slot map
+    uint8_t *zs = smem + L.off_zs;                                               // [npad] slot of every entity
+    uint8_t *ring = smem + L.off_ring;                                           // [NS][2][chunk]
+    __shared__ int32_t s_K, s_KA, s_choice_slot, s_choice_label;
+    __shared__ double s_u;
+    __shared__ int32_t s_has_absent;
 
     const int64_t m0 = args.move_off[k_list], m1 = args.move_off[k_list + 1];
     const int64_t nmoves = m1 - m0;
-    const uint32_t row_bytes = (uint32_t)npad;
-    // optional per-phase cycle accounting (thread 0 only; args.phase_cycles is null in production)
-    long long ph[16] = {0}, tlast = 0;
-    const bool prof = args.phase_cycles != nullptr && tid == 0;
-    // BAR.SYNC does not block at issue: a clock read right after __syncthreads() would record thread 0's
-    // ARRIVAL.  In profiling mode a second barrier (block-uniform condition) makes the stamp the release time.
-    const bool prof_any = args.phase_cycles != nullptr;
-#define PHASE(i) do { if (prof) { long long _t = clock64(); ph[i] += _t - tlast; tlast = _t; } } while (0)
-#define SYNC_PHASE(i) do { __syncthreads(); if (prof_any) { __syncthreads(); PHASE(i); } } while (0)
 
-    // ---- load state -------------------------------------------------------------------
-    #pragma unroll 1
-    for (int j = tid; j < npad; j += DENSE_THREADS) zs[j] = j < n ? (uint8_t)dd.z[j] : (uint8_t)0;
-    #pragma unroll 1
-    for (int k = tid; k < kcap * kcap; k += DENSE_THREADS) table[k] = R.counts[k];
-    #pragma unroll 1
-    for (int k = tid; k < kcap; k += DENSE_THREADS) { s_cnt[k] = dd.tab_count[k]; s_lab[k] = dd.tab_label[k]; }
-    #pragma unroll 1
-    for (int k = tid; k < L.hist_words; k += DENSE_THREADS) hist[k] = 0u;
+    // ---- load state, compacting live tables into slots 0..K-1 -----------------------------
+    const int hi_g = *dd.hi;
     if (tid == 0) {
-        s_hi = *dd.hi; s_holes = 1;                  // unknown: check once
-        s_logalpha = log_nl(dd.alpha);
+        int nt = 0;
         #pragma unroll 1
-        for (int s = 0; s < NS; s++) mbar_init(&bars[s], 1);
+        for (int k = 0; k < hi_g; k++) {
+            const int cnt = dd.tab_count[k];
+            s_map[k] = cnt > 0 ? nt : 0;
+            if (cnt > 0) { s_cnt[nt] = cnt; s_lab[nt] = dd.tab_label[k]; nt++; }
+        }
+        s_K = nt; s_KA = nt; s_has_absent = 0;
+        #pragma unroll 1
+        for (int k = nt; k < kt; k++) s_cnt[k] = 0;
+        #pragma unroll 1
+        for (int s = 0; s < NS; s++) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], DN_A_WARPS); }
+        mbar_init(&bar_ready[0], DN_A_WARPS); mbar_init(&bar_ready[1], DN_A_WARPS);
+        mbar_init(bar_go, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    #pragma unroll 1
+    for (int k = tid; k < kt * kt; k += DN_THREADS) table[k] = 0;
+    #pragma unroll 1
+    for (int k = tid; k < L.bins_words; k += DN_THREADS) bins[k] = 0u;
+    #pragma unroll 1
+    for (int k = tid; k < DN_LF; k += DN_THREADS) s_lf[k] = g_logfact[k];
     __syncthreads();
-    if (tid == 0) {
+    const int K0 = s_K;
+    #pragma unroll 1
+    for (int j = tid; j < npad; j += DN_THREADS) {
+        const int zj = j < n ? z_g[j] : 0;
+        if (zj < 0) s_has_absent = 1;                          // rare: moves must then be checked against z = -1
+        zs[j] = zj >= 0 ? (uint8_t)s_map[zj] : (uint8_t)0;     // an absent entity has only missing observations
+    }
+    #pragma unroll 1
+    for (int k = tid; k < hi_g * hi_g; k += DN_THREADS) {
+        const int a = k % hi_g, b = k / hi_g;
+        const cell_t v = R.counts[a + b * kcap_g];
+        if (v) table[s_map[a] + s_map[b] * kt] = v;            // cells of dead slots are empty
+    }
+    #pragma unroll 1
+    for (int k = tid; k < K0; k += DN_THREADS) {
+        int rank = 0;
+        const int lb = s_lab[k];
         #pragma unroll 1
-        for (int s = 0; s < NS && s < nmoves; s++) {
-            const int it = args.move_item[m0 + s];
-            const int64_t row = (it >= 0 && it < n) ? it : 0;
-            mbar_expect_tx(&bars[s], 2 * row_bytes);
-            tma_load_1d(stage0 + (size_t)s * 2 * npad, R.slab[0] + row * R.pitch[0], row_bytes, &bars[s]);
-            tma_load_1d(stage0 + (size_t)s * 2 * npad + npad, R.slab[1] + row * R.pitch[1], row_bytes, &bars[s]);
-        }
+        for (int j = 0; j < K0; j++) rank += s_lab[j] < lb;
+        s_order[rank] = k;
+        s_logcnt[k] = log_nl((double)s_cnt[k]);
+        s_logcntm1[k] = log_nl((double)max(s_cnt[k] - 1, 1));
     }
-    int stage_ctr = 0; uint32_t parity_ctr = 0;
-    int item_next = nmoves > 0 ? args.move_item[m0] : 0;
-    int dom_next = nmoves > 0 ? args.move_dom[m0] : 0;
+    __syncthreads();
 
-    #pragma unroll 1
-    for (int64_t r = 0; r < nmoves; r++) {
-        const int64_t m = m0 + r;
-        const int item = item_next;
-        const bool bad = item < 0 || item >= n || dom_next != 0;
-        // move ids are fetched one move ahead (and the TMA producer's NS ahead): never on the dependent chain
-        if (r + 1 < nmoves) { item_next = args.move_item[m + 1]; dom_next = args.move_dom[m + 1]; }
-        int item_tma = 0;
-        if (tid == 0 && r + NS < nmoves) item_tma = args.move_item[m + NS];
-        const int stage = stage_ctr;
-        const uint32_t parity = parity_ctr;
-        if (++stage_ctr == NS) { stage_ctr = 0; parity_ctr ^= 1u; }
-        const uint8_t *xrow = stage0 + (size_t)stage * 2 * npad, *xcol = xrow + npad;
-
-        // ---- slot compaction: keep live tables in slots 0..ntab-1 so that the dp4a path applies -------
-        const int holes = s_holes;                     // every thread reads it before thread 0 may rewrite it (barrier below)
-        if (holes) {
-            __syncthreads();
-            if (tid == 0) {
-                int nt = 0;
+    if (warp == 0) {
+        // =============================== P: TMA producer ===================================
+        if (lane == 0 && nmoves > 0) {
+            RingCursor cur{0, 0u};
+            int item_next = args.move_item[m0];
+            int64_t issued = 0;                               // chunks issued so far
+            const bool prof = args.phase_cycles != nullptr;
+            long long p_wait = 0, p_t0 = prof ? clk() : 0;
+            #pragma unroll 1
+            for (int64_t r = 0; r < nmoves; r++) {
+                const int it = item_next;
+                if (r + 1 < nmoves) item_next = args.move_item[m0 + r + 1];
+                const int64_t row = (it >= 0 && it < n) ? it : 0;
+                const uint8_t *src0 = slab0 + row * pitch0, *src1 = slab1 + row * pitch1;
                 #pragma unroll 1
-                for (int k = 0; k < s_hi; k++) { s_map[k] = nt; if (s_cnt[k] > 0) nt++; }
-                s_holes = nt != s_hi ? 2 : 0;
-            }
-            __syncthreads();
-            if (s_holes == 2) {                       // block-uniform
-                const int hi0 = s_hi;
-                cell_t *tmp = reinterpret_cast<cell_t *>(hist);          // hist is all-zero between moves; restored below
-                #pragma unroll 1
-                for (int k = tid; k < hi0 * hi0; k += DENSE_THREADS) { const int a = k % hi0, b = k / hi0; tmp[k] = table[a + b * kcap]; }
-                #pragma unroll 1
-                for (int j = tid; j < n; j += DENSE_THREADS) zs[j] = (uint8_t)s_map[zs[j]];
-                __syncthreads();
-                #pragma unroll 1
-                for (int k = tid; k < hi0 * hi0; k += DENSE_THREADS) { const int a = k % hi0, b = k / hi0; table[a + b * kcap] = 0; }
-                __syncthreads();
-                #pragma unroll 1
-                for (int k = tid; k < hi0 * hi0; k += DENSE_THREADS) {
-                    const int a = k % hi0, b = k / hi0;
-                    if (s_cnt[a] > 0 && s_cnt[b] > 0) table[s_map[a] + s_map[b] * kcap] = tmp[k];
+                for (int q = 0; q < L.nchunks; q++) {
+                    const int base = q * L.chunk;
+                    const uint32_t bytes = (uint32_t)min(L.chunk, npad - base);
+                    if (issued++ >= NS) {                     // the slot has been used before: wait until the A warps released it
+                        const long long w0 = prof ? clk() : 0;
+                        mbar_wait_relaxed_s(smem_u32(&bar_empty[cur.stage]), cur.parity ^ 1u);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        if (prof) p_wait += clk() - w0;
+                    }
+                    uint8_t *dst = ring + (size_t)cur.stage * 2 * L.chunk;
+                    mbar_expect_tx(&bar_full[cur.stage], 2 * bytes);
+                    tma_load_1d(dst, src0 + base, bytes, &bar_full[cur.stage]);
+                    tma_load_1d(dst + L.chunk, src1 + base, bytes, &bar_full[cur.stage]);
+                    cur.advance(NS);
                 }
-                __syncthreads();
-                #pragma unroll 1
-                for (int k = tid; k < 2 * hi0 * hi0; k += DENSE_THREADS) hist[k] = 0u;
-                if (tid == 0) {
-                    int nt = 0;
-                    #pragma unroll 1
-                    for (int k = 0; k < hi0; k++) if (s_cnt[k] > 0) { s_cnt[nt] = s_cnt[k]; s_lab[nt] = s_lab[k]; nt++; }
-                    #pragma unroll 1
-                    for (int k = nt; k < hi0; k++) s_cnt[k] = 0;
-                    s_hi = nt; s_holes = 0;
-                }
-                __syncthreads();
             }
+            if (prof) { args.phase_cycles[blockIdx.x * 32 + 0] = clk() - p_t0; args.phase_cycles[blockIdx.x * 32 + 1] = p_wait; }
         }
-        const int c = bad ? 0 : zs[item];
-        const int hi = s_hi;
-        if (tid == 0) s_fail = 0;
-        if (tid == DENSE_THREADS - 1)                  // this move's uniform, off the critical path
-            s_u = args.uniforms ? args.uniforms[m] : philox_uniform(args.seed, args.stream[k_list], args.counter0[k_list] + (uint64_t)r);
-
-        if (prof) tlast = clock64();
-        mbar_wait(&bars[stage], parity);
-        PHASE(0);
-        // the diagonal observation (i, i) sits in both staged rows at j = i; it is ONE observation
-        const uint32_t dcode = bad ? 0u : (pack_codes(xrow[item], xcol[item]) & 0xFu);
-        const int d_n = dcode & 1, d_s = (dcode >> 1) & 1;
-        const bool use_dp4a = hi <= DENSE_MAX_KD;
-
-        if (warp == DENSE_WARPS - 1) {
-            // ---- C: candidates, concurrently with the accumulation done by the other warps ---------
-            //      CRP::tables_weights_gibbs (cxx/hirm.hh:147-161)
-            int maxlab = 0, freeslot = 1 << 30;        // t_max starts at 0 (cxx/hirm.hh:139)
-            #pragma unroll 1
-            for (int k = lane; k < hi; k += 32) {
-                if (s_cnt[k] > 0) maxlab = max(maxlab, s_lab[k]); else freeslot = min(freeslot, k);
+    } else if (warp <= DN_A_WARPS) {
+        // =============================== A: accumulate =====================================
+        APar ap;
+        ap.full = smem_u32(bar_full); ap.empty = smem_u32(bar_empty); ap.ring = smem_u32(ring); ap.zs = smem_u32(zs);
+        ap.n = n; ap.npad = npad; ap.chunk = L.chunk; ap.nchunks = L.nchunks; ap.stages = NS; ap.bins_words = L.bins_words;
+        const int a = tid - 32, aw = warp - 1;
+        const uint32_t go_s = smem_u32(bar_go), ready_s = smem_u32(bar_ready);
+        const bool full = full_obs && s_has_absent == 0;
+        RingCursor cur{0, 0u};
+        const bool prof = args.phase_cycles != nullptr && a == 0;
+        long long a_go = 0, a_t0 = prof ? clk() : 0;
+        #pragma unroll 1
+        for (int64_t r = 0; r < nmoves; r++) {
+            const int buf = (int)(r & 1);
+            int32_t *wp = wpart + (buf * DN_A_WARPS + aw) * 4 * kt;
+            const long long w0 = prof ? clk() : 0;
+            mbar_wait_relaxed_s(go_s, (uint32_t)(r & 1));     // z is stable (except z[i_{r-1}], fixed up by D)
+            if (prof) a_go += clk() - w0;
+            const int KA = s_KA;
+            if (KA > DN_MAX_KD) a_move_bins(ap, cur, a, lane, bins, KA, wp);
+            else if (full) {
+                if (KA <= 2) a_move_dp4a<2, true>(ap, cur, a, lane, wp);
+                else if (KA <= 4) a_move_dp4a<4, true>(ap, cur, a, lane, wp);
+                else a_move_dp4a<8, true>(ap, cur, a, lane, wp);
+            } else {
+                if (KA <= 2) a_move_dp4a<2, false>(ap, cur, a, lane, wp);
+                else if (KA <= 4) a_move_dp4a<4, false>(ap, cur, a, lane, wp);
+                else a_move_dp4a<8, false>(ap, cur, a, lane, wp);
             }
-            maxlab = __reduce_max_sync(0xffffffffu, maxlab);
-            freeslot = __reduce_min_sync(0xffffffffu, freeslot);
-            if (freeslot == (1 << 30)) freeslot = hi < kcap ? hi : -1;
-            const bool singleton = s_cnt[c] == 1;
-            int ncount = 0;
-            #pragma unroll 1
-            for (int base = 0; base < hi; base += 32) {
-                const int k = base + lane;
-                const int cnt = k < hi ? s_cnt[k] - (k == c ? 1 : 0) : 0;
-                const unsigned bal = __ballot_sync(0xffffffffu, cnt > 0);
-                const int pos = ncount + __popc(bal & ((1u << lane) - 1u));
-                if (cnt > 0) { u_slot[pos] = k; u_label[pos] = s_lab[k]; }
-                const double lw = log_nl((double)max(cnt, 1));
-                if (cnt > 0) s_tmp[pos] = lw;
-                ncount += __popc(bal);
-            }
-            if (lane == 0) {
-                if (singleton) { u_slot[ncount] = c; u_label[ncount] = s_lab[c]; s_tmp[ncount] = s_logalpha; }
-                else if (freeslot >= 0) { u_slot[ncount] = freeslot; u_label[ncount] = maxlab + 1; s_tmp[ncount] = s_logalpha; }
-                else { raise_error(irm, KERR_NO_FREE_SLOT); s_fail = 1; }
-            }
-            const int nc = ncount + ((singleton || freeslot >= 0) ? 1 : 0);
             __syncwarp();
-            #pragma unroll 1
-            for (int j = lane; j < nc; j += 32) {      // ascending label order: rank by counting (labels are distinct)
-                const int lb = u_label[j];
-                int rank = 0;
-                #pragma unroll 1
-                for (int i = 0; i < nc; i++) rank += u_label[i] < lb;
-                s_cslot[rank] = u_slot[j]; s_clabel[rank] = lb; s_lp[rank] = s_tmp[j];
-            }
-            if (lane == 0) s_ncand = nc;
-        } else if (use_dp4a) {
-            // ---- A (<= 8 live tables): register accumulation ------------------------------------------
-            if (hi <= 2) accumulate_dp4a<2>(xrow, xcol, zs, n, tid, warp, lane, s_wpart);
-            else if (hi <= 4) accumulate_dp4a<4>(xrow, xcol, zs, n, tid, warp, lane, s_wpart);
-            else accumulate_dp4a<8>(xrow, xcol, zs, n, tid, warp, lane, s_wpart);
+            if (lane == 0) mbar_arrive_s(ready_s + 8u * buf);
         }
-        if (use_dp4a) {
-            SYNC_PHASE(1);
-            // ---- B: per-warp partials -> group sums; thread k owns slot k and removes its cells -------
-            if (tid < hi) {
-                const int k = tid;
-                int rn = 0, rs = 0, cn = 0, cs = 0;
+        if (prof) { args.phase_cycles[blockIdx.x * 32 + 2] = clk() - a_t0; args.phase_cycles[blockIdx.x * 32 + 3] = a_go; }
+    } else {
+        // =============================== D: decide =========================================
+        const int d = tid - 32 - DN_NA;                        // 0..DN_ND-1
+        const int dwarp = d >> 5;
+        const double logalpha = log_nl(alpha);
+        int K = K0;                                            // live slots 0..K-1 (uniform across D threads)
+        int KA_prev = K0;                                      // K the A warps used for the move being decided
+        bool pend_changed = false; int pend_item = -1, pend_old = 0, pend_new = 0, pend_dead = -1;
+        const bool has_absent = s_has_absent != 0;
+        const bool full = full_obs && !has_absent;
+        // move ids are fetched TWO moves ahead and the observation bytes the fix-ups need -- (i, i), (i, i_prev),
+        // (i_prev, i), straight from the slabs -- ONE move ahead, so that no load is ever waited for
+        int item_n1 = nmoves > 0 ? args.move_item[m0] : 0, dom_n1 = nmoves > 0 ? args.move_dom[m0] : 0;
+        int item_n2 = nmoves > 1 ? args.move_item[m0 + 1] : -1, dom_n2 = nmoves > 1 ? args.move_dom[m0 + 1] : 0;
+        uint32_t xb_d_next = 0xFFu, xb_rp_next = 0xFFu, xb_cp_next = 0xFFu;
+        if (item_n1 >= 0 && item_n1 < n) xb_d_next = slab0[(int64_t)item_n1 * pitch0 + item_n1];
+        const bool own_u = d == DN_ND - 1;                     // this thread provides the moves' uniforms
+        const uint64_t u_stream = own_u && !args.uniforms ? args.stream[k_list] : 0, u_ctr0 = own_u && !args.uniforms ? args.counter0[k_list] : 0;
+        double u_next = own_u && args.uniforms && nmoves > 0 ? args.uniforms[m0] : 0.0;
+        if (d == 0) mbar_arrive(bar_go);                       // move 0 may be accumulated
+        const bool prof = args.phase_cycles != nullptr && d == 0;
+        long long ph[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tl = prof ? clk() : 0;
+#define DPHASE(i) do { if (prof) { const long long _t = clk(); ph[i] += _t - tl; tl = _t; } } while (0)
+        #pragma unroll 1
+        for (int64_t r = 0; r < nmoves; r++) {
+            const int64_t m = m0 + r;
+            const int item = item_n1, item_next = item_n2;
+            bool bad = item < 0 || item >= n || dom_n1 != 0;
+            if (has_absent && !bad) bad = z_g[item] < 0;
+            const uint32_t xb_ri = xb_d_next, xb_rp = xb_rp_next, xb_cp = xb_cp_next;
+            item_n1 = item_n2; dom_n1 = dom_n2;
+            if (r + 2 < nmoves) { item_n2 = args.move_item[m + 2]; dom_n2 = args.move_dom[m + 2]; }
+            xb_d_next = 0xFFu; xb_rp_next = 0xFFu; xb_cp_next = 0xFFu;
+            if (r + 1 < nmoves && item_next >= 0 && item_next < n) {
+                const int64_t i2 = item_next;
+                xb_d_next = slab0[i2 * pitch0 + i2];
+                if (!bad) { xb_rp_next = slab0[i2 * pitch0 + item]; xb_cp_next = slab1[i2 * pitch1 + item]; }
+            }
+            if (own_u) {                                       // this move's uniform, before the wait
+                s_u = args.uniforms ? u_next : philox_uniform(args.seed, u_stream, u_ctr0 + (uint64_t)r);
+                if (args.uniforms && r + 1 < nmoves) u_next = args.uniforms[m + 1];
+            }
+            const int buf = (int)(r & 1);
+            int32_t *g = g_buf + buf * 4 * kt;
+            DPHASE(5);
+            mbar_wait(&bar_ready[buf], (uint32_t)((r >> 1) & 1));
+            DPHASE(0);
+            // ---- finish move r-1: z[i_{r-1}] becomes visible, its observation pair changes group ----
+            if (pend_changed && d == 0) zs[pend_item] = (uint8_t)pend_new;
+            int c = bad ? 0 : ((pend_changed && item == pend_item) ? pend_new : (int)zs[item]);
+            const int d_n = bad ? 0 : byte_n(xb_ri), d_s = bad ? 0 : byte_s(xb_ri);   // the diagonal (i, i): ONE observation
+            {
+                const int KG = min(K + 1, kt);                 // slot K: the fresh table (empty groups)
+                const int32_t *wp0 = wpart + buf * DN_A_WARPS * 4 * kt;
                 #pragma unroll 1
-                for (int w = 0; w < DENSE_ACC_WARPS; w++) {
-                    const int32_t *p = s_wpart + w * (4 * DENSE_MAX_KD) + 4 * k;
-                    rn += p[0]; rs += p[1]; cn += p[2]; cs += p[3];
-                }
-                if (k == c) { rn -= d_n; rs -= d_s; cn -= d_n; cs -= d_s; }       // drop the diagonal from both groups
-                g_rn[k] = rn; g_rs[k] = rs; g_cn[k] = cn; g_cs[k] = cs;
-                if (!bad) {
-                    if (k != c) {
-                        table[c + k * kcap] -= pack_cell(rn, rs);
-                        table[k + c * kcap] -= pack_cell(cn, cs);
-                    } else {
-                        table[c + c * kcap] -= pack_cell(rn + cn + d_n, rs + cs + d_s);
+                for (int idx = d; idx < 4 * KG; idx += DN_ND) {
+                    const int k = idx >> 2, f = idx & 3;
+                    int v = 0;
+                    if (full && !(f & 1)) {                     // no missing cell: the observation counts are the table sizes
+                        g[idx] = (k < K && !bad) ? s_cnt[k] - (k == c ? 1 : 0) : 0;
+                        continue;
                     }
+                    if (k < KA_prev) {
+#pragma unroll
+                        for (int w = 0; w < DN_A_WARPS; w++) v += wp0[w * 4 * kt + idx];
+                    }
+                    if (pend_changed) {                        // A saw i_{r-1} in its old slot
+                        const uint32_t xb = f < 2 ? xb_rp : xb_cp;
+                        const int val = (f & 1) ? byte_s(xb) : byte_n(xb);
+                        if (k == pend_old) v -= val;
+                        if (k == pend_new) v += val;
+                    }
+                    if (k == c) v -= (f & 1) ? d_s : d_n;      // drop the diagonal from both groups
+                    g[idx] = v;
                 }
             }
-            SYNC_PHASE(2);
-        } else {
-            // ---- A (> 8 live tables): per-thread private bins, diagonal included, pulled out in B -------
-            const int HT = min(DENSE_ACC_THREADS, (L.hist_words / max(hi, 1)) & ~31);
-            const int nvec = n >> 4;
-            const int chunk_vecs = HT * DENSE_VEC_PER_THREAD;
-            #pragma unroll 1
-            for (int v0 = 0; v0 < nvec || v0 == 0; v0 += chunk_vecs) {
-                if (tid < HT) {
-                    const int vend = min(nvec, v0 + chunk_vecs);
-                    uint32_t *bins = hist + tid;
+            bar_d();
+            if (pend_dead >= 0) {
+                // ---- the table that died in move r-1 is replaced by the last slot ------------------
+                const int dead = pend_dead, last = K - 1;
+                if (dead != last) {
                     #pragma unroll 1
-                    for (int v = v0 + tid; v < vend; v += HT) {
-                        const uint4 xr = *reinterpret_cast<const uint4 *>(xrow + (size_t)v * 16);
-                        const uint4 xc = *reinterpret_cast<const uint4 *>(xcol + (size_t)v * 16);
-                        const uint4 zz = *reinterpret_cast<const uint4 *>(zs + (size_t)v * 16);
-                        const uint32_t xrw[4] = {xr.x, xr.y, xr.z, xr.w}, xcw[4] = {xc.x, xc.y, xc.z, xc.w}, zw[4] = {zz.x, zz.y, zz.z, zz.w};
+                    for (int v = d; v < (npad >> 4); v += DN_ND) {
+                        uint4 zz = *reinterpret_cast<uint4 *>(zs + (size_t)v * 16);
+                        uint32_t w[4] = {zz.x, zz.y, zz.z, zz.w};
+                        bool any = false;
 #pragma unroll
-                        for (int w = 0; w < 4; w++) {
-                            const uint32_t codes = pack_codes(xrw[w], xcw[w]);
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const uint32_t slot = (zw[w] >> (8 * e)) & 0xFFu;
-                                bins[slot * HT] += code_to_inc((codes >> (8 * e)) & 0xFu);
-                            }
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t eq = __vcmpeq4(w[q], (uint32_t)last * 0x01010101u);
+                            if (eq) { w[q] = (w[q] & ~eq) | (((uint32_t)dead * 0x01010101u) & eq); any = true; }
+                        }
+                        if (any) *reinterpret_cast<uint4 *>(zs + (size_t)v * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    // row/column `last` -> `dead` (row/column `dead` is all zero)
+                    #pragma unroll 1
+                    for (int k = d; k < K; k += DN_ND) {
+                        if (k != last && k != dead) {
+                            table[dead + k * kt] = table[last + k * kt]; table[last + k * kt] = 0;
+                            table[k + dead * kt] = table[k + last * kt]; table[k + last * kt] = 0;
+                        } else if (k == last) {
+                            table[dead + dead * kt] = table[last + last * kt]; table[last + last * kt] = 0;
                         }
                     }
-                    if (v0 == 0) {                         // scalar tail: elements nvec*16 .. n-1, one per thread
-                        const int j = (nvec << 4) + tid;
-                        if (j < n) bins[(uint32_t)zs[j] * HT] += code_to_inc(pack_codes(xrow[j], xcol[j]) & 0xFu);
+                    if (d < 4) { g[4 * dead + d] = g[4 * last + d]; g[4 * last + d] = 0; }
+                    if (d == 4) {
+                        s_cnt[dead] = s_cnt[last]; s_lab[dead] = s_lab[last]; s_cnt[last] = 0;
+                        s_logcnt[dead] = s_logcnt[last]; s_logcntm1[dead] = s_logcntm1[last];
+                        #pragma unroll 1
+                        for (int t = 0; t < K - 1; t++) if (s_order[t] == last) s_order[t] = dead;
                     }
+                    if (c == last) c = dead;
                 }
-                SYNC_PHASE(1);
-                // ---- B: bins -> group sums per other-entity slot (accumulated over chunks) ------
+                K -= 1;
+                pend_dead = -1;
+                bar_d();
+            }
+            pend_changed = false;
+            if (d == 0) { s_KA = K; mbar_arrive(bar_go); }    // the A warps may accumulate move r+1
+            DPHASE(1);
+            KA_prev = K;
+            if (bad) {                                        // block-uniform
+                if (d == 0) {
+                    raise_error(irm, KERR_BAD_MOVE);
+                    if (args.out_choice) args.out_choice[m] = -1;
+                    if (args.trace_cap > 0) args.trace_n[m] = 0;
+                }
+                continue;
+            }
+
+            DPHASE(11);
+            // ---- candidates: CRP::tables_weights_gibbs (cxx/hirm.hh:147-161) -------------------------
+            const bool singleton = s_cnt[c] == 1;
+            const bool nofree = !singleton && K >= kt;         // no slot for the fresh-table candidate
+            const int ncand = K + ((singleton || nofree) ? 0 : 1);
+            const int fresh_label = max(0, s_lab[s_order[K - 1]]) + 1;   // t_max starts at 0 (cxx/hirm.hh:139)
+
+            // ---- score.  logp_gibbs_exact (cxx/hirm.hh:441-461): for every candidate t the sum over target
+            //      cells of S(N+n, s+sg) - S(N, s) = D(s, sg) + D(N-s, n-sg) - D(N+1, n), D(a, m) = log((a+m)!/a!),
+            //      with (N, s) the cell WITHOUT i's own observations.  A team of LPC lanes owns a candidate;
+            //      lane partials are combined in a fixed order (deterministic log-probabilities).
+            {
+                int LPC = 32;
+                while (LPC > 1 && ncand * LPC > DN_ND) LPC >>= 1;
+                const int nteams = DN_ND / LPC, team = d / LPC, lt = d - team * LPC;
+                const int items = 3 * (2 * K + 1);
+                const cell_t rem_cc = pack_cell((uint32_t)(g[4 * c] + g[4 * c + 2] + d_n), (uint32_t)(g[4 * c + 1] + g[4 * c + 3] + d_s));
                 #pragma unroll 1
-                for (int k = warp; k < hi; k += DENSE_WARPS) {
-                    int rn = 0, rs = 0, cn = 0, cs = 0;
+                for (int t0 = 0; t0 < ncand; t0 += nteams) {
+                    const int t = t0 + team;
+                    const bool tv = t < ncand;
+                    const int st = tv ? (t < K ? s_order[t] : K) : 0;
+                    double acc = 0.0;
                     #pragma unroll 1
-                    for (int j = lane; j < HT; j += 32) {
-                        const uint32_t wv = hist[k * HT + j];
-                        hist[k * HT + j] = 0u;
-                        rn += wv & 0xFFu; rs += (wv >> 8) & 0xFFu; cn += (wv >> 16) & 0xFFu; cs += wv >> 24;
-                    }
-                    rn = __reduce_add_sync(0xffffffffu, rn); rs = __reduce_add_sync(0xffffffffu, rs);
-                    cn = __reduce_add_sync(0xffffffffu, cn); cs = __reduce_add_sync(0xffffffffu, cs);
-                    if (lane == 0) {
-                        if (v0 == 0) {
-                            if (k == c) { rn -= d_n; rs -= d_s; cn -= d_n; cs -= d_s; }   // drop the diagonal from both groups
-                        } else { rn += g_rn[k]; rs += g_rs[k]; cn += g_cn[k]; cs += g_cs[k]; }
-                        g_rn[k] = rn; g_rs[k] = rs; g_cn[k] = cn; g_cs[k] = cs;
-                        // g_r[k] = (n, s) of observations (i, j), j != i, z_j = k;  g_c[k] likewise for (j, i);
-                        // (d_n, d_s) = (i, i).  Last chunk: remove them from the table ("rest" counts) right here --
-                        // this lane is the only one touching cells (c, k) and (k, c).
-                        if (v0 + chunk_vecs >= nvec && !bad) {
-                            if (k != c) {
-                                table[c + k * kcap] -= pack_cell(rn, rs);
-                                table[k + c * kcap] -= pack_cell(cn, cs);
+                    for (int w0 = 0; w0 < items; w0 += LPC) {
+                        // gather the operands (cheap, lanes may diverge), then ONE converged evaluation for the warp
+                        const int w = w0 + lt;
+                        uint32_t a = 0u, mm = 0u; bool neg = false;
+                        if (tv && w < items) {
+                            const int q = w / 3, term = w - 3 * q;
+                            int gn = 0, gs = 0; cell_t cur = 0;
+                            if (q == 2 * K) {                  // the (t, t) cell of the fresh slot: the diagonal only
+                                if (st >= K) { gn = d_n; gs = d_s; }
                             } else {
-                                table[c + c * kcap] -= pack_cell(rn + cn + d_n, rs + cs + d_s);
+                                const int k = q >> 1, col = q & 1;
+                                if (k == st) {                 // merged target cell (t, t): row group + column group + diagonal
+                                    if (!col) {
+                                        gn = g[4 * k] + g[4 * k + 2] + d_n; gs = g[4 * k + 1] + g[4 * k + 3] + d_s;
+                                        cur = table[st + st * kt];
+                                        if (st == c) cur -= rem_cc;
+                                    }
+                                } else if (!col) {             // (i, j), z_j = k  ->  cell (t, k)
+                                    gn = g[4 * k]; gs = g[4 * k + 1];
+                                    cur = table[st + k * kt];
+                                    if (st == c) cur -= pack_cell((uint32_t)gn, (uint32_t)gs);
+                                    else if (k == c) cur -= pack_cell((uint32_t)g[4 * st + 2], (uint32_t)g[4 * st + 3]);   // i's column group with slot t sits in (t, c)
+                                } else {                       // (j, i), z_j = k  ->  cell (k, t)
+                                    gn = g[4 * k + 2]; gs = g[4 * k + 3];
+                                    cur = table[k + st * kt];
+                                    if (st == c) cur -= pack_cell((uint32_t)gn, (uint32_t)gs);
+                                    else if (k == c) cur -= pack_cell((uint32_t)g[4 * st], (uint32_t)g[4 * st + 1]);       // i's row group with slot t sits in (c, t)
+                                }
                             }
+                            const uint32_t N = cell_n(cur), sv = cell_s(cur);
+                            a = term == 0 ? sv : term == 1 ? N - sv : N + 1u;
+                            mm = (uint32_t)(term == 0 ? gs : term == 1 ? gn - gs : gn);
+                            neg = term == 2;
                         }
+                        __syncwarp();
+                        long long pt[7] = {0, 0, 0, 0, 0, 0, 0};
+                        const double v = lfact_diff_warp_s(s_lf, a, mm, prof ? pt : nullptr);
+                        if (prof) for (int i = 0; i < 6; i++) args.phase_cycles[blockIdx.x * 32 + 24 + i] += pt[i + 1] - pt[i];
+                        acc += neg ? -v : v;
+                    }
+                    DPHASE(6);
+                    for (int o = LPC >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    DPHASE(7);
+                    if (tv && lt == 0) {
+                        const double prior = st == c ? (singleton ? logalpha : s_logcntm1[c]) : (t < K ? s_logcnt[st] : logalpha);
+                        s_lp[t] = prior + acc;
                     }
                 }
-                SYNC_PHASE(2);
             }
-        }
-        // stage buffer is free again: prefetch the rows of move r + NS
-        if (tid == 0 && r + NS < nmoves) {
-            const int64_t row = (item_tma >= 0 && item_tma < n) ? item_tma : 0;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&bars[stage], 2 * row_bytes);
-            tma_load_1d(stage0 + (size_t)stage * 2 * npad, R.slab[0] + row * R.pitch[0], row_bytes, &bars[stage]);
-            tma_load_1d(stage0 + (size_t)stage * 2 * npad + npad, R.slab[1] + row * R.pitch[1], row_bytes, &bars[stage]);
-        }
-        if (bad) {                                    // block-uniform
-            if (tid == 0) {
-                raise_error(irm, KERR_BAD_MOVE);
-                if (args.out_choice) args.out_choice[m] = -1;
-                if (args.trace_cap > 0) args.trace_n[m] = 0;
-            }
-            continue;
-        }
-        PHASE(3);
-        const int ncand = s_ncand;
+            bar_d();
+            DPHASE(2);
 
-        // ---- D: score.  logp_gibbs_exact (cxx/hirm.hh:441-461): for every candidate t the sum over target
-        //      cells of S(N+n, s+sg) - S(N, s).  Each difference is three log-factorial differences and each
-        //      of those two halves of at most one transcendental: 6 lanes per target cell, so the dependent
-        //      fp64 chain of a move is ONE log deep.  A candidate is owned by a team of `wpc` whole warps;
-        //      lane partials are combined in a fixed order (deterministic log-probabilities).
-        {
-            const int nq = 2 * hi, items = 6 * nq + 6;      // +6: the (t,t) cell of a fresh slot past hi (diagonal only)
-            int wpc = ncand <= DENSE_WARPS ? DENSE_WARPS / ncand : 1;
-            wpc = max(1, min(wpc, (items + 31) / 32));
-            const int rounds = ncand <= DENSE_WARPS ? 1 : (ncand + DENSE_WARPS - 1) / DENSE_WARPS;
-            #pragma unroll 1
-            for (int rd = 0; rd < rounds; rd++) {
-                const int t = rounds == 1 ? warp / wpc : rd * DENSE_WARPS + warp;
-                const int j = rounds == 1 ? warp - t * wpc : 0;
-                double acc = 0.0;
-                if (t < ncand) {
-                    const int st = s_cslot[t];
+            // ---- sample (D warp 0): log_choice (cxx/util_math.cc:58-65); sums in index order ----------
+            if (dwarp == 0) {
+                int idx = 0;
+                if (args.flags & 1u) {                         // HIRM_SWEEP_SCORE_ONLY: stay
                     #pragma unroll 1
-                    for (int w = j * 32 + lane; w < items; w += wpc * 32) {
-                        const int q = w / 6, part = w - q * 6;
-                        const int term = part >> 1, half = part & 1;
-                        const int k = q >> 1, col = q & 1;
-                        int gn, gs; cell_t cur;
-                        if (q == nq) {                     // fresh slot beyond hi: only the diagonal lands in (t, t)
-                            if (st < hi) continue;
-                            gn = d_n; gs = d_s; cur = 0;
-                        } else if (k == st) {              // merged target cell (t, t): row group + column group + diagonal
-                            if (col) continue;
-                            gn = g_rn[k] + g_cn[k] + d_n; gs = g_rs[k] + g_cs[k] + d_s;
-                            cur = table[st + st * kcap];
-                        } else {
-                            gn = col ? g_cn[k] : g_rn[k]; gs = col ? g_cs[k] : g_rs[k];
-                            cur = col ? table[k + st * kcap] : table[st + k * kcap];
+                    for (int t = lane; t < ncand; t += 32) if ((t < K ? s_order[t] : K) == c) idx = t;
+                    idx = __reduce_max_sync(0xffffffffu, idx);
+                } else if (ncand > 1) {
+                    double mx = -1.0 / 0.0;
+                    if (ncand <= 8) {
+                        #pragma unroll 1
+                        for (int t = 0; t < ncand; t++) mx = fmax(mx, s_lp[t]);
+                    } else {
+                        #pragma unroll 1
+                        for (int t = lane; t < ncand; t += 32) mx = fmax(mx, s_lp[t]);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    }
+                    DPHASE(8);
+                    #pragma unroll 1
+                    for (int t = lane; t < ncand; t += 32) s_tmp[t] = exp_nl(s_lp[t] - mx);   // scale-invariant rule: one exp each
+                    __syncwarp();
+                    DPHASE(9);
+                    if (ncand <= 32) {                         // lane t: running sum up to t, in index order
+                        double cum = 0.0, total = 0.0;
+                        #pragma unroll 1
+                        for (int t = 0; t < ncand; t++) { total += s_tmp[t]; if (t == lane) cum = total; }
+                        const double x = s_u * total;
+                        const unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && cum > x);
+                        idx = hit ? __ffs(hit) - 1 : ncand - 1;
+                    } else {
+                        if (lane == 0) {
+                            double total = 0.0;
+                            #pragma unroll 1
+                            for (int t = 0; t < ncand; t++) total += s_tmp[t];
+                            const double x = s_u * total;
+                            double cum = 0.0;
+                            idx = ncand - 1;
+                            #pragma unroll 1
+                            for (int t = 0; t < ncand; t++) { cum += s_tmp[t]; if (cum > x) { idx = t; break; } }
                         }
-                        if (gn == 0) continue;
-                        const int64_t N = cell_n(cur), sv = cell_s(cur);
-                        // S(N+n, s+sg) - S(N, s) = D(s, sg) + D(N-s, n-sg) - D(N+1, n),  D(a, m) = log((a+m)!/a!)
-                        const int64_t a = term == 0 ? sv : term == 1 ? N - sv : N + 1;
-                        const int64_t mm = term == 0 ? gs : term == 1 ? gn - gs : gn;
-                        const double v = lfact_half_nl(a, mm, half);
-                        acc += term == 2 ? -v : v;
+                        idx = __shfl_sync(0xffffffffu, idx, 0);
                     }
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (rounds == 1) {
-                    if (lane == 0) s_part[warp] = acc;
-                } else if (lane == 0 && t < ncand) s_lp[t] += acc;
-            }
-            PHASE(8);
-            if (rounds == 1) {
-                SYNC_PHASE(9);
-                if (tid < ncand) { double a = 0.0; for (int j = 0; j < wpc; j++) a += s_part[tid * wpc + j]; s_lp[tid] += a; }
-            }
-        }
-        SYNC_PHASE(4);
-
-        // ---- E: sample (warp 0): log_choice (cxx/util_math.cc:58-65); exp() lane-parallel, sums in index order ----
-        if (warp == 0) {
-            int idx = 0;
-            if (args.flags & 1u) {                     // HIRM_SWEEP_SCORE_ONLY: stay
-                #pragma unroll 1
-                for (int t = lane; t < ncand; t += 32) if (s_cslot[t] == c) idx = t;
-                idx = __reduce_max_sync(0xffffffffu, idx);
-            } else if (ncand > 1) {
-                double mx = -1.0 / 0.0;
-                #pragma unroll 1
-                for (int t = lane; t < ncand; t += 32) mx = fmax(mx, s_lp[t]);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                PHASE(10);
-                #pragma unroll 1
-                for (int t = lane; t < ncand; t += 32) s_tmp[t] = exp_nl(s_lp[t] - mx);   // scale-invariant rule: one exp each
-                __syncwarp();
-                PHASE(11);
+                DPHASE(10);
                 if (lane == 0) {
-                    double total = 0.0;
-                    #pragma unroll 1
-                    for (int t = 0; t < ncand; t++) total += s_tmp[t];
-                    const double x = s_u * total;
-                    double cum = 0.0;
-                    idx = ncand - 1;
-                    #pragma unroll 1
-                    for (int t = 0; t < ncand; t++) { cum += s_tmp[t]; if (cum > x) { idx = t; break; } }
+                    if (nofree) raise_error(irm, KERR_NO_FREE_SLOT);
+                    int cs, cl;
+                    if (nofree || ncand == 0) { cs = c; cl = s_lab[c]; }
+                    else { cs = idx < K ? s_order[idx] : K; cl = idx < K ? s_lab[cs] : fresh_label; }
+                    s_choice_slot = cs; s_choice_label = cl;
+                    if (args.out_choice) args.out_choice[m] = cl;
+                    if (args.trace_cap > 0) args.trace_n[m] = ncand;
                 }
-                idx = __shfl_sync(0xffffffffu, idx, 0);
-                PHASE(12);
             }
-            if (lane == 0) {
-                if (s_fail || ncand == 0) { s_choice_slot = c; s_choice_label = s_lab[c]; }
-                else { s_choice_slot = s_cslot[idx]; s_choice_label = s_clabel[idx]; }
-                if (args.out_choice) args.out_choice[m] = s_choice_label;
-                if (args.trace_cap > 0) args.trace_n[m] = ncand;
+            if (args.trace_cap > 0) {
+                #pragma unroll 1
+                for (int t = d; t < ncand && t < args.trace_cap; t += DN_ND) {
+                    args.trace_labels[m * args.trace_cap + t] = t < K ? s_lab[s_order[t]] : fresh_label;
+                    args.trace_logps[m * args.trace_cap + t] = s_lp[t];
+                }
             }
-        }
-        if (args.trace_cap > 0) {
-            #pragma unroll 1
-            for (int t = tid; t < ncand && t < args.trace_cap; t += DENSE_THREADS) {
-                args.trace_labels[m * args.trace_cap + t] = s_clabel[t];
-                args.trace_logps[m * args.trace_cap + t] = s_lp[t];
-            }
-        }
-        SYNC_PHASE(5);
+            bar_d();
+            DPHASE(3);
 
-        // ---- F: apply: add the groups back at the chosen slot -------------------------------
-        const int tnew = s_choice_slot;
-        if (tid < hi) {
-            const int k = tid;                         // groups are keyed by the OTHER entity's slot, which does not move
-            if (k != tnew) {
-                table[tnew + k * kcap] += pack_cell(g_rn[k], g_rs[k]);
-                table[k + tnew * kcap] += pack_cell(g_cn[k], g_cs[k]);
+            // ---- apply, only if the table changed ------------------------------------------------------
+            const int tnew = s_choice_slot;
+            if (tnew != c) {
+                const int newlabel = s_choice_label;
+                const bool died = singleton;
+                #pragma unroll 1
+                for (int k = d; k < K; k += DN_ND) {          // i's observations leave row / column c
+                    if (k != c) {
+                        table[c + k * kt] -= pack_cell((uint32_t)g[4 * k], (uint32_t)g[4 * k + 1]);
+                        table[k + c * kt] -= pack_cell((uint32_t)g[4 * k + 2], (uint32_t)g[4 * k + 3]);
+                    } else {
+                        table[c + c * kt] -= pack_cell((uint32_t)(g[4 * c] + g[4 * c + 2] + d_n), (uint32_t)(g[4 * c + 1] + g[4 * c + 3] + d_s));
+                    }
+                }
+                if (d == DN_ND - 1) {                          // Domain::set_cluster_assignment_gibbs (cxx/hirm.hh:219-224)
+                    s_cnt[c] -= 1;
+                    if (tnew == K) { s_cnt[K] = 1; s_lab[K] = newlabel; s_order[K] = K; }
+                    else s_cnt[tnew] += 1;
+                    if (died) {                                // CRP::unincorporate erases the empty table (:95-97)
+                        int pos = 0;
+                        #pragma unroll 1
+                        for (int t = 0; t < K; t++) if (s_order[t] == c) pos = t;
+                        #pragma unroll 1
+                        for (int t = pos; t + 1 < K; t++) s_order[t] = s_order[t + 1];
+                    }
+                }
+                bar_d();
+                const int K2 = max(K, tnew + 1);
+                #pragma unroll 1
+                for (int k = d; k < K2; k += DN_ND) {         // ... and enter row / column tnew
+                    if (k != tnew) {
+                        table[tnew + k * kt] += pack_cell((uint32_t)g[4 * k], (uint32_t)g[4 * k + 1]);
+                        table[k + tnew * kt] += pack_cell((uint32_t)g[4 * k + 2], (uint32_t)g[4 * k + 3]);
+                    } else {
+                        table[tnew + tnew * kt] += pack_cell((uint32_t)(g[4 * k] + g[4 * k + 2] + d_n), (uint32_t)(g[4 * k + 1] + g[4 * k + 3] + d_s));
+                    }
+                }
+                if (d >= DN_ND - 4) {                          // cached log(count), log(count - 1) of the two tables
+                    const int j = d - (DN_ND - 4);
+                    const int slot = (j & 2) ? tnew : c;
+                    const int cnt = s_cnt[slot] - (j & 1);
+                    const double v = log_nl((double)max(cnt, 1));
+                    if (j & 1) s_logcntm1[slot] = v; else s_logcnt[slot] = v;
+                }
+                pend_changed = true; pend_item = item; pend_old = c; pend_new = tnew;
+                if (tnew == K) K += 1;
+                if (died) pend_dead = c;
             }
+            DPHASE(4);
         }
-        if (tid == DENSE_THREADS - 32) {
-            int gn = d_n, gs = d_s;
-            if (tnew < hi) { gn += g_rn[tnew] + g_cn[tnew]; gs += g_rs[tnew] + g_cs[tnew]; }
-            table[tnew + tnew * kcap] += pack_cell(gn, gs);
+        if (prof) for (int i = 0; i < 14; i++) args.phase_cycles[blockIdx.x * 32 + 8 + i] = ph[i];
+#undef DPHASE
+        // ---- finish the last move -----------------------------------------------------------------
+        bar_d();
+        if (pend_changed && d == 0) zs[pend_item] = (uint8_t)pend_new;
+        bar_d();
+        if (pend_dead >= 0) {
+            const int dead = pend_dead, last = K - 1;
+            if (dead != last) {
+                #pragma unroll 1
+                for (int j = d; j < n; j += DN_ND) if (zs[j] == last) zs[j] = (uint8_t)dead;
+                #pragma unroll 1
+                for (int k = d; k < K; k += DN_ND) {
+                    if (k != last && k != dead) {
+                        table[dead + k * kt] = table[last + k * kt]; table[last + k * kt] = 0;
+                        table[k + dead * kt] = table[k + last * kt]; table[k + last * kt] = 0;
+                    } else if (k == last) {
+                        table[dead + dead * kt] = table[last + last * kt]; table[last + last * kt] = 0;
+                    }
+                }
+                if (d == 4) { s_cnt[dead] = s_cnt[last]; s_lab[dead] = s_lab[last]; s_cnt[last] = 0; }
+            }
+            K -= 1;
         }
-        if (tid == 0 && tnew != c) {
-            zs[item] = (uint8_t)tnew;
-            s_cnt[c] -= 1;
-            const int newcnt = (tnew < hi ? s_cnt[tnew] : 0) + 1;
-            s_cnt[tnew] = newcnt;
-            if (newcnt == 1) s_lab[tnew] = s_choice_label;
-            int nhi = max(hi, tnew + 1);
-            while (nhi > 0 && s_cnt[nhi - 1] == 0) nhi--;
-            s_hi = nhi;
-            if (s_cnt[c] == 0 && c < nhi) s_holes = 1;   // a table died below the top: compact before the next move
-        }
-        SYNC_PHASE(6);
+        if (d == 0) s_K = K;
     }
-    if (prof) for (int i = 0; i < 16; i++) args.phase_cycles[blockIdx.x * 16 + i] = ph[i];
-#undef PHASE
-#undef SYNC_PHASE
+    __syncthreads();
 
-    // ---- store state ------------------------------------------------------------------
+    // ---- store state (slots 0..K-1, compact) ------------------------------------------------
+    const int Kf = s_K;
     #pragma unroll 1
-    for (int j = tid; j < n; j += DENSE_THREADS) dd.z[j] = zs[j];
+    for (int j = tid; j < n; j += DN_THREADS) if (z_g[j] >= 0) z_g[j] = zs[j];
+    const int span = max(hi_g, Kf);
     #pragma unroll 1
-    for (int k = tid; k < kcap * kcap; k += DENSE_THREADS) R.counts[k] = table[k];
+    for (int k = tid; k < span * span; k += DN_THREADS) {
+        const int a = k % span, b = k / span;
+        R.counts[a + b * kcap_g] = (a < Kf && b < Kf) ? table[a + b * kt] : (cell_t)0;
+    }
     #pragma unroll 1
-    for (int k = tid; k < kcap; k += DENSE_THREADS) { dd.tab_count[k] = s_cnt[k]; dd.tab_label[k] = s_lab[k]; }
-    if (tid == 0) *dd.hi = s_hi;
+    for (int k = tid; k < span; k += DN_THREADS) {
+        dd.tab_count[k] = k < Kf ? s_cnt[k] : 0;
+        if (k < Kf) dd.tab_label[k] = s_lab[k];
+    }
+    if (tid == 0) *dd.hi = Kf;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -609,6 +902,16 @@ __global__ void __launch_bounds__(256) rebuild_counts_dense_kernel(const IrmDev 
     }
     __syncthreads();
     for (int64_t k = threadIdx.x; k < nc; k += blockDim.x) if (s_tab[k]) atomicAdd(&R->counts[k], s_tab[k]);
+}
+
+// flag = 1 if any cell (i, j), i < rows, j < cols, is missing (byte >= 0x80)
+__global__ void __launch_bounds__(256) dense_any_missing_kernel(const uint8_t *slab, int64_t rows, int64_t cols, int64_t pitch, int32_t *flag) {
+    bool any = false;
+    for (int64_t i = blockIdx.x; i < rows; i += gridDim.x) {
+        const uint8_t *row = slab + i * pitch;
+        for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) any |= (row[j] & 0x80) != 0;
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(flag, 1);
 }
 
 __global__ void transpose_u8_kernel(const uint8_t *in, int64_t rows, int64_t cols, int64_t pitch_in, uint8_t *out, int64_t pitch_out) {

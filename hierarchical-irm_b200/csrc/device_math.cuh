@@ -62,6 +62,13 @@ __device__ __forceinline__ double lfact_half(int64_t a, int64_t m, int half) {
     return (y - 0.5) * log1p(dm * ry) - dm + (stirling_corr_r(fast_rcp(y + dm)) - stirling_corr_r(ry));
 }
 
+// Single out-of-line copies of the fp64 transcendentals for the dense sweep kernel: its decision warps
+// run a long, once-per-move code path, and every inlined copy of log/log1p/exp (hundreds of bytes of
+// SASS each) is instruction-cache traffic on that path.
+__device__ __noinline__ double log_nl(double x) { return log(x); }
+__device__ __noinline__ double log1p_nl(double x) { return log1p(x); }
+__device__ __noinline__ double exp_nl(double x) { return exp(x); }
+
 // BetaBernoulli::logp_score (cxx/hirm.hh:52-56), alpha = beta = 1:
 //   S(N, s) = lgamma(s+1) + lgamma(N-s+1) - lgamma(N+2)
 // score_delta = S(N+n, s+sg) - S(N, s): what logp_gibbs_exact_variant returns for one

@@ -7,6 +7,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -58,6 +59,7 @@ struct RelObs {
     const uint8_t *slab[2] = {nullptr, nullptr};
     int64_t pitch[2] = {0, 0};
     DevBuf<uint8_t> own_slab0, own_slab1;   // set_observations_dense_host
+    int full_obs = -1;                      // dense: 1 = no missing cell, 0 = some, -1 = not scanned yet
 };
 struct DomObs {
     DevBuf<int64_t> ptr; DevBuf<uint32_t> meta; DevBuf<int32_t> other;
@@ -104,8 +106,8 @@ struct hirm_engine {
     DevBuf<int64_t> s_move_off; DevBuf<double> s_uniforms, s_trace_logps, s_score;
     DevBuf<uint64_t> s_stream, s_counter;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int last_launches = 0, last_kind = -1; float last_ms = 0.f;
-    int max_smem_optin = 0, num_sms = 0;
+    int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
+    int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0;
     long long *d_phase_cycles = nullptr;   // debug hook (hirm_engine_debug_phase_cycles)
 };
 
@@ -138,6 +140,7 @@ extern "C" int hirm_engine_create(hirm_engine **out, int device) {
     e->device = device;
     e->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     e->num_sms = prop.multiProcessorCount;
+    e->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
     // log-factorial table from libm's lgamma (the reference's lbeta, cxx/util_math.cc:13-15)
@@ -385,6 +388,21 @@ static int finalize_store(hirm_engine *e, Irm *irm) {
     }
     for (int r = 0; r < irm->n_relations; r++) {
         RelObs &R = S.rel[r];
+        if (R.kind != 1) continue;                     // dense: is any cell missing?  (selects the kernel's counting scheme)
+        const int64_t n0 = irm->n_ent[irm->rdom[r][0]], n1 = irm->n_ent[irm->rdom[r][1]];
+        DevBuf<int32_t> flag;
+        CK(flag.alloc(1)); CK(cudaMemsetAsync(flag.p, 0, sizeof(int32_t), e->stream));
+        if (n0 > 0 && n1 > 0) {
+            dense_any_missing_kernel<<<(unsigned)std::min<int64_t>(n0, e->num_sms * 8), 256, 0, e->stream>>>(R.slab[0], n0, n1, R.pitch[0], flag.p);
+            CK(cudaGetLastError());
+        }
+        int32_t h = 0;
+        CK(cudaMemcpyAsync(&h, flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        R.full_obs = h ? 0 : 1;
+    }
+    for (int r = 0; r < irm->n_relations; r++) {
+        RelObs &R = S.rel[r];
         if (R.kind != 0 || R.nobs == 0) continue;
         CK(R.coo_ids.alloc(R.h_ids.size())); CK(cudaMemcpy(R.coo_ids.p, R.h_ids.data(), R.h_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         CK(R.coo_val.alloc(R.h_val.size())); CK(cudaMemcpy(R.coo_val.p, R.h_val.data(), R.h_val.size(), cudaMemcpyHostToDevice));
@@ -458,6 +476,7 @@ static int upload_desc(hirm_engine *e, int32_t id) {
         R.groups = irm->groups[r].p; R.gcells = irm->gcells[r]; R.gbit0 = irm->gbit0[r];
         R.slab[0] = S.rel[r].slab[0]; R.slab[1] = S.rel[r].slab[1]; R.pitch[0] = S.rel[r].pitch[0]; R.pitch[1] = S.rel[r].pitch[1];
         R.coo_ids = S.rel[r].coo_ids.p; R.coo_val = S.rel[r].coo_val.p; R.nobs = S.rel[r].nobs;
+        R.full_obs = S.rel[r].full_obs > 0 ? 1 : 0;
     }
     CK(irm->d_rel.ensure(rd.size()));
     if (!rd.empty()) CK(cudaMemcpyAsync(irm->d_rel.p, rd.data(), rd.size() * sizeof(RelationDev), cudaMemcpyHostToDevice, e->stream));
@@ -634,13 +653,29 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
         for (int j = 0; j < k; j++) if (h_irms[j] == h_irms[k]) return fail("an irm may appear once per sweep");
         if (ensure_counts(e, h_irms[k])) return -1;
         if (irm->dense_ree && !(flags & HIRM_SWEEP_FORCE_GENERIC)) {
-            int hist_words = std::max(8192, 2 * irm->kcap[0] * irm->kcap[0]);   // 32 KiB of private bins (also the compaction scratch)
-            int stages = 3;
-            DenseLaunch L = dense_layout(irm->n_ent[0], irm->kcap[0], stages, hist_words);
-            while (L.total_bytes > e->max_smem_optin && stages > 1) L = dense_layout(irm->n_ent[0], irm->kcap[0], --stages, hist_words);
-            if (L.total_bytes > e->max_smem_optin) return fail("domain too large for the dense fast path's shared-memory state");
-            if (have_dense && (L.n != plan.L.n || L.kcap != plan.L.kcap)) return fail("dense irms of one sweep must share a shape");
-            plan.L = L; have_dense = true;
+            if (!have_dense) {
+                // shared-memory plan: as many chains per SM as the launch has (up to 4), the rest of the
+                // SM's shared memory goes to the TMA ring of each CTA
+                int n_dense = 0;
+                for (int j = 0; j < n_irms; j++) { Irm *o = get_irm(e, h_irms[j]); if (o && o->dense_ree) n_dense++; }
+                const int kt = irm->kcap[0];
+                const int bins_words = std::min(4096, std::max(2048, 64 * kt));
+                int chunk = 2 * 16 * DN_NA, want = std::min(4, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
+                if (const char *s = getenv("HIRM_DENSE_CHUNK")) chunk = std::max(16, atoi(s) & ~15);
+                if (const char *s = getenv("HIRM_DENSE_CTAS_PER_SM")) want = std::max(1, atoi(s));
+                DenseLaunch L{};
+                for (; want >= 1; want--) {
+                    const int budget = std::min(e->max_smem_optin, e->smem_per_sm / want - 1024) - 512;   // 1 KiB reserved per CTA + the kernel's static shared memory
+                    const DenseLaunch L0 = dense_layout(irm->n_ent[0], kt, chunk, 0, bins_words);
+                    int stages = L0.chunk > 0 ? (budget - L0.total_bytes) / (2 * L0.chunk) : 0;
+                    stages = std::min(stages, std::min(DN_MAX_STAGES, 2 * L0.nchunks + 2));
+                    if (stages >= 2 || (want == 1 && stages >= 1)) { L = dense_layout(irm->n_ent[0], kt, chunk, stages, bins_words); break; }
+                }
+                if (L.stages < 1) return fail("domain too large for the dense fast path's shared-memory state");
+                plan.L = L; have_dense = true;
+            } else if (irm->n_ent[0] != plan.L.n || irm->kcap[0] != plan.L.kt) {
+                return fail("dense irms of one sweep must share a shape");
+            }
             plan.dense_blk.push_back(k);
         } else {
             for (auto &R : irm->obs->rel)
@@ -661,10 +696,13 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
     }
     if (!plan.dense_blk.empty()) {
         CK(cudaFuncSetAttribute(dense_ree_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.L.total_bytes));
-        dense_ree_sweep_kernel<<<(unsigned)plan.dense_blk.size(), DENSE_THREADS, (size_t)plan.L.total_bytes, e->stream>>>(
+        dense_ree_sweep_kernel<<<(unsigned)plan.dense_blk.size(), DN_THREADS, (size_t)plan.L.total_bytes, e->stream>>>(
             args, e->s_blk.p + plan.generic_blk.size(), plan.L);
         CK(cudaGetLastError());
         e->last_launches++; e->last_kind = 1;
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense_ree_sweep_kernel, DN_THREADS, (size_t)plan.L.total_bytes);
+        e->last_occupancy = occ; e->last_stages = plan.L.stages; e->last_chunk = plan.L.chunk; e->last_smem = plan.L.total_bytes;
     }
     CK(cudaEventRecord(e->ev1, e->stream));
     return 0;
@@ -769,6 +807,15 @@ extern "C" int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, 
         CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
         *kernel_ms = e->last_ms;
     }
+    return 0;
+}
+
+extern "C" int hirm_engine_last_dense_plan(hirm_engine *e, int32_t *ctas_per_sm, int32_t *stages, int32_t *chunk_bytes, int32_t *smem_bytes) {
+    if (!e) return fail("engine is null");
+    if (ctas_per_sm) *ctas_per_sm = e->last_occupancy;
+    if (stages) *stages = e->last_stages;
+    if (chunk_bytes) *chunk_bytes = e->last_chunk;
+    if (smem_bytes) *smem_bytes = e->last_smem;
     return 0;
 }
 

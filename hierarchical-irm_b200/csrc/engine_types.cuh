@@ -50,6 +50,8 @@ struct RelationDev {
     const int32_t *coo_ids;       // [nobs*arity] (CSR relations: kept for count-table rebuilds)
     const uint8_t *coo_val;
     int64_t nobs;
+    int32_t full_obs;             // dense: 1 if no cell of the relation is missing
+    int32_t pad;
 };
 
 struct IrmDev {

@@ -29,7 +29,7 @@ EXPORTS = [
     "hirm_irm_share_observations", "hirm_irm_finalize", "hirm_irm_set_assignments", "hirm_irm_get_assignments",
     "hirm_irm_set_alpha", "hirm_irm_get_counts", "hirm_irm_logp_score", "hirm_engine_sweep",
     "hirm_engine_sweep_device", "hirm_engine_last_sweep_info", "hirm_engine_transpose_u8",
-    "hirm_engine_debug_phase_cycles",
+    "hirm_engine_debug_phase_cycles", "hirm_engine_last_dense_plan",
 ]
 
 _lib = None
@@ -80,6 +80,7 @@ def load():
     L.hirm_engine_last_sweep_info.argtypes = [V, c_i32p, c_i32p, ctypes.POINTER(ctypes.c_float)]
     L.hirm_engine_transpose_u8.argtypes = [V, V, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, V, ctypes.c_int64]
     L.hirm_engine_debug_phase_cycles.argtypes = [V, V]
+    L.hirm_engine_last_dense_plan.argtypes = [V, c_i32p, c_i32p, c_i32p, c_i32p]
     _lib = L
     return L
 
@@ -227,6 +228,11 @@ class Engine:
         n, k, ms = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_float()
         self._ck(self.L.hirm_engine_last_sweep_info(self._h, ctypes.byref(n), ctypes.byref(k), ctypes.byref(ms)))
         return dict(launches=n.value, kernel_kind=k.value, kernel_ms=ms.value)
+
+    def last_dense_plan(self):
+        a, b, c, d = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self._ck(self.L.hirm_engine_last_dense_plan(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
+        return dict(ctas_per_sm=a.value, stages=b.value, chunk_bytes=c.value, smem_bytes=d.value)
 
     def transpose_u8(self, d_in, rows, cols, pitch_in, d_out, pitch_out):
         self._ck(self.L.hirm_engine_transpose_u8(self._h, d_in, rows, cols, pitch_in, d_out, pitch_out))

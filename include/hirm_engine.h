@@ -125,12 +125,16 @@ int hirm_engine_sweep_device(hirm_engine *e, int n_irms, const int32_t *h_irms, 
 /* statistics of the last sweep: kernel launches made, which kernel ran (0 generic, 1 dense, 2 dense-cluster) */
 int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, int32_t *kernel_kind, float *kernel_ms);
 
+/* shared-memory plan of the last dense launch: resident CTAs (chains) per SM, TMA ring stages, bytes per
+ * row chunk, dynamic shared memory per CTA */
+int hirm_engine_last_dense_plan(hirm_engine *e, int32_t *ctas_per_sm, int32_t *stages, int32_t *chunk_bytes, int32_t *smem_bytes);
+
 /* device helper: out[j*pitch_out + i] = in[i*pitch_in + j] for a rows x cols byte matrix */
 int hirm_engine_transpose_u8(hirm_engine *e, const uint8_t *d_in, int64_t rows, int64_t cols, int64_t pitch_in,
                              uint8_t *d_out, int64_t pitch_out);
 
-/* debug hook: device buffer [n_blocks * 8] int64 that the dense kernel fills with per-phase SM cycles
- * (wait, accumulate, reduce, candidates, score, sample, apply); NULL switches it off */
+/* debug hook: device buffer [n_blocks * 16] int64 that the dense kernel fills with SM cycles per role
+ * (producer, accumulate warps, decision warps: see profiles/phase_breakdown.py); NULL switches it off */
 int hirm_engine_debug_phase_cycles(hirm_engine *e, long long *d_buf);
 
 #ifdef __cplusplus

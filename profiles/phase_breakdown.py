@@ -19,19 +19,19 @@ for h in hs:
     if os.environ.get('INIT', 'crp') == 'crp': z = bench.crp_prior_labels_fast(n, 1.0, rng)
     else: z = (np.arange(n) >= n//2).astype(np.int32)
     eng.set_assignments(h, 0, z)
-buf = torch.zeros(chains*16, dtype=torch.int64, device='cuda')
+buf = torch.zeros(chains*32, dtype=torch.int64, device='cuda')
 def run(Mm, seedoff):
     moves = [(np.zeros(Mm, np.int32), rng.permutation(n).astype(np.int32)[:Mm]) for _ in hs]
     t0 = time.perf_counter(); eng.sweep(hs, moves, seed=seedoff, streams=np.arange(chains, dtype=np.uint64)); t1 = time.perf_counter()
     return eng.last_sweep_info()['kernel_ms']
 if burn: run(burn, 1)
 run(50, 2)
-eng.debug_phase_cycles(buf.data_ptr())
+if not os.environ.get('NOPHASE'): eng.debug_phase_cycles(buf.data_ptr())
 ms = run(M, 3)
-ph = buf.cpu().numpy().reshape(chains, 16).astype(np.float64) / M
-names = ['wait','accum','reduce','tma-issue','score(tail)','sample(tail)','apply','-','score:teams','score:sync1','sample:max','sample:exp','sample:scan']
+ph = buf.cpu().numpy().reshape(chains, 32).astype(np.float64) / M
+names = ['P total','P wait-empty','A total','A wait-go','-','-','-','-','D wait-ready','D fix+go','D score:bar','D sample:bar','D apply','D loop-top','D score:items','D score:shfl','D sample:max','D sample:exp','D sample:scan','D cand-setup','-','-','-','-','lf:pre','lf:log','lf:rcp+corr','lf:rcp2','lf:log1p','lf:post']
 print('n=%d chains=%d M=%d kernel_ms=%.3f us/move=%.3f' % (n, chains, M, ms, ms*1e3/M))
-print('cycles/move per phase (mean over chains):')
-for i, nm in enumerate(names): print('  %-12s %9.0f' % (nm, ph[:, i].mean()))
-print('  total        %9.0f  (%.2f us at 1.965 GHz)' % (ph.sum(1).mean(), ph.sum(1).mean()/1965))
+print('cycles/move (mean over chains):')
+for i, nm in enumerate(names):
+    if nm != '-': print('  %-14s %9.0f' % (nm, ph[:, i].mean()))
 print('tables alive:', [len(np.unique(eng.get_assignments(h,0))) for h in hs[:6]])
