@@ -13,16 +13,20 @@
 //
 //   P  (1 warp)   TMA producer: 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) of
 //                 row chunks into a ring, running ahead across move boundaries.
-//   A  (3 warps)  accumulate: group move r+1's 2n observations by the other entity's table
+//   A  (2 warps)  accumulate: group move r+1's 2n observations by the other entity's table
 //                 (get_cluster_to_items_list, cxx/hirm.hh:388-397) WHILE move r is being decided.
 //                 z[i_r] is still the old value then; the decision warps move that one
 //                 observation pair to the right group afterwards (an O(1) fix-up).
 //                 <= 8 live tables: byte-SIMD one-hot masks of z and dp4a dot products into
 //                 registers; more: per-thread private bins with 4 x 8-bit fields.
-//   D  (4 warps)  decide move r: candidates + CRP prior (CRP::tables_weights_gibbs, :147-161),
+//   D  (2 warps)  decide move r: candidates + CRP prior (CRP::tables_weights_gibbs, :147-161),
 //                 score (logp_gibbs_exact, :441-461) against the table with i's observations
 //                 removed virtually, sample (log_choice, cxx/util_math.cc:58-65), and only
 //                 if the table changed apply (set_cluster_assignment_gibbs, :524-551, :219-224).
+//
+// Tiers: the launch's shared-memory table holds kt slots.  With kt < max_tables more chains fit on an SM; a
+// chain that needs slot kt stops BEFORE that move, stores its state and its position in progress[], and the
+// host's next launch (kt = max_tables) resumes it.  Chains that are done exit at once.
 //
 // Live tables always occupy slots 0..K-1 (a dying table is replaced by the last slot), the
 // slots in ascending label order are kept in s_order, and log(count) per table is cached, so
@@ -32,8 +36,8 @@
 
 namespace hirm {
 
-constexpr int DN_A_WARPS = 3;
-constexpr int DN_D_WARPS = 4;
+constexpr int DN_A_WARPS = 2;
+constexpr int DN_D_WARPS = 2;
 constexpr int DN_NA = 32 * DN_A_WARPS;
 constexpr int DN_ND = 32 * DN_D_WARPS;
 constexpr int DN_THREADS = 32 + DN_NA + DN_ND;   // warp 0 = producer, then the A warps, then the D warps
@@ -45,7 +49,8 @@ constexpr int DN_FLUSH_VECS = 15;                 // 15 * 16 = 240 elements per 
 struct DenseLaunch {
     int32_t n;          // entities
     int32_t npad;       // n rounded up to 16
-    int32_t kt;         // table slots held in shared memory (= max_tables)
+    int32_t kt;         // table slots held in shared memory (<= max_tables: a chain that needs more stops and is
+                        // resumed by the next, larger tier -- see progress[] below)
     int32_t chunk;      // bytes of one row chunk (multiple of 16)
     int32_t nchunks;    // chunks per row
     int32_t stages;     // ring depth
@@ -157,9 +162,7 @@ __device__ __forceinline__ void acc_word(uint32_t xr, uint32_t xc, uint32_t z, i
 // lfact_diff (device_math.cuh) for a CONVERGED warp -- all 32 lanes call it together, lanes without work pass
 // m = 0 -- against the shared-memory table lf[DN_LF]: branch-free per lane, each transcendental called once
 // for the whole warp and skipped by warp vote when no lane needs it.
-__device__ __forceinline__ double lfact_diff_warp_s(const double *lf, uint32_t a, uint32_t m, long long *pt = nullptr) {
-#define LFP(i) do { if (pt) pt[i] = clk(); } while (0)
-    LFP(0);
+__device__ __forceinline__ double lfact_diff_warp_s(const double *lf, uint32_t a, uint32_t m) {
     const uint32_t am = a + m;
     const bool small = am < (uint32_t)DN_LF;                    // includes m == 0 with a small a
     const bool need = m != 0u && !small;
@@ -168,25 +171,18 @@ __device__ __forceinline__ double lfact_diff_warp_s(const double *lf, uint32_t a
     double res = (m != 0u && small) ? lf[min(am, (uint32_t)DN_LF - 1u)] - lfa : 0.0;
     if (__any_sync(0xffffffffu, need)) {
         const double y = (double)a + 1.0, dm = (double)m, ym = y + dm;
-        LFP(1);
         const double L = log_nl(need ? (big ? y : ym) : 1.0);
-        LFP(2);
         const double c2 = stirling_corr_r(fast_rcp(ym));
-        LFP(3);
         double r = (ym - 0.5) * L - ym + 0.91893853320467274178 + c2 - lfa;      // a small, a + m large
         if (__any_sync(0xffffffffu, need && big)) {
             const double ry = fast_rcp(y);
-            LFP(4);
             const double P = log1p_nl((need && big) ? dm * ry : 0.0);
-            LFP(5);
             // (y+m-1/2) ln(y+m) - (y-1/2) ln y - m + corr(y+m) - corr(y),  ln(y+m) = ln y + log1p(m/y)
             const double rb = (ym - 0.5) * P + dm * (L - 1.0) + (c2 - stirling_corr_r(ry));
             if (big) r = rb;
         }
         if (need) res = r;
     }
-    LFP(6);
-#undef LFP
     return res;
 }
 
@@ -227,6 +223,16 @@ __device__ __forceinline__ void mbar_wait_relaxed_s(uint32_t bar, uint32_t parit
         if (done) break;
         __nanosleep(64);
     }
+}
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -352,7 +358,7 @@ __device__ __forceinline__ void a_move_bins(const APar p, RingCursor &cur, const
     a_flush_bins(bins, HT, K, a, lane, wp);
 }
 
-__global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArgs args, const int32_t *blk_list, DenseLaunch L) {
+__global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArgs args, const int32_t *blk_list, DenseLaunch L) {
     const int k_list = blk_list ? blk_list[blockIdx.x] : blockIdx.x;
     const IrmDev &irm = args.irms[args.irm_ids[k_list]];
     const DomainDev &dd = irm.dom[0];
@@ -389,23 +395,33 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
     __shared__ int32_t s_K, s_KA, s_choice_slot, s_choice_label;
     __shared__ double s_u;
     __shared__ int32_t s_has_absent;
+    __shared__ long long s_limit, s_issued, s_consumed, s_done;
+    __shared__ long long s_ph[14];                        // profiling only   // first move NOT to be made (tier overflow); ring chunks issued / consumed
 
     const int64_t m0 = args.move_off[k_list], m1 = args.move_off[k_list + 1];
     const int64_t nmoves = m1 - m0;
+    const int64_t r_begin = args.progress ? args.progress[blockIdx.x] : 0;   // moves already made by an earlier tier
+    if (r_begin >= nmoves) return;
 
     // ---- load state, compacting live tables into slots 0..K-1 -----------------------------
     const int hi_g = *dd.hi;
     if (tid == 0) {
         int nt = 0;
         #pragma unroll 1
-        for (int k = 0; k < hi_g; k++) {
-            const int cnt = dd.tab_count[k];
-            s_map[k] = cnt > 0 ? nt : 0;
-            if (cnt > 0) { s_cnt[nt] = cnt; s_lab[nt] = dd.tab_label[k]; nt++; }
-        }
+        for (int k = 0; k < hi_g; k++) nt += dd.tab_count[k] > 0;
         s_K = nt; s_KA = nt; s_has_absent = 0;
-        #pragma unroll 1
-        for (int k = nt; k < kt; k++) s_cnt[k] = 0;
+        s_limit = nmoves; s_issued = 0; s_consumed = 0;
+        if (nt <= kt) {
+            nt = 0;
+            #pragma unroll 1
+            for (int k = 0; k < hi_g; k++) {
+                const int cnt = dd.tab_count[k];
+                s_map[k] = cnt > 0 ? nt : 0;
+                if (cnt > 0) { s_cnt[nt] = cnt; s_lab[nt] = dd.tab_label[k]; nt++; }
+            }
+            #pragma unroll 1
+            for (int k = nt; k < kt; k++) s_cnt[k] = 0;
+        }
         #pragma unroll 1
         for (int s = 0; s < NS; s++) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], DN_A_WARPS); }
         mbar_init(&bar_ready[0], DN_A_WARPS); mbar_init(&bar_ready[1], DN_A_WARPS);
@@ -421,6 +437,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
     for (int k = tid; k < DN_LF; k += DN_THREADS) s_lf[k] = g_logfact[k];
     __syncthreads();
     const int K0 = s_K;
+    if (K0 > kt) return;                                       // more live tables than this tier holds: left to the next tier
     #pragma unroll 1
     for (int j = tid; j < npad; j += DN_THREADS) {
         const int zj = j < n ? z_g[j] : 0;
@@ -447,14 +464,16 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
 
     if (warp == 0) {
         // =============================== P: TMA producer ===================================
-        if (lane == 0 && nmoves > 0) {
+        if (lane == 0) {
             RingCursor cur{0, 0u};
-            int item_next = args.move_item[m0];
+            int item_next = args.move_item[m0 + r_begin];
             int64_t issued = 0;                               // chunks issued so far
             const bool prof = args.phase_cycles != nullptr;
             long long p_wait = 0, p_t0 = prof ? clk() : 0;
+            const volatile long long *limit = &s_limit;
+            bool stop = false;
             #pragma unroll 1
-            for (int64_t r = 0; r < nmoves; r++) {
+            for (int64_t r = r_begin; r < nmoves && !stop; r++) {
                 const int it = item_next;
                 if (r + 1 < nmoves) item_next = args.move_item[m0 + r + 1];
                 const int64_t row = (it >= 0 && it < n) ? it : 0;
@@ -463,9 +482,15 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
                 for (int q = 0; q < L.nchunks; q++) {
                     const int base = q * L.chunk;
                     const uint32_t bytes = (uint32_t)min(L.chunk, npad - base);
-                    if (issued++ >= NS) {                     // the slot has been used before: wait until the A warps released it
+                    if (r >= *limit) { stop = true; break; }  // the chain stops before this move (tier overflow)
+                    if (issued >= NS) {                       // the slot has been used before: wait until the A warps released it
                         const long long w0 = prof ? clk() : 0;
-                        mbar_wait_relaxed_s(smem_u32(&bar_empty[cur.stage]), cur.parity ^ 1u);
+                        const uint32_t eb = smem_u32(&bar_empty[cur.stage]);
+                        while (!mbar_try_wait_s(eb, cur.parity ^ 1u)) {
+                            if (r >= *limit) { stop = true; break; }
+                            __nanosleep(128);
+                        }
+                        if (stop) break;
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         if (prof) p_wait += clk() - w0;
                     }
@@ -473,9 +498,11 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
                     mbar_expect_tx(&bar_full[cur.stage], 2 * bytes);
                     tma_load_1d(dst, src0 + base, bytes, &bar_full[cur.stage]);
                     tma_load_1d(dst + L.chunk, src1 + base, bytes, &bar_full[cur.stage]);
+                    issued++;
                     cur.advance(NS);
                 }
             }
+            s_issued = issued;
             if (prof) { args.phase_cycles[blockIdx.x * 32 + 0] = clk() - p_t0; args.phase_cycles[blockIdx.x * 32 + 1] = p_wait; }
         }
     } else if (warp <= DN_A_WARPS) {
@@ -489,13 +516,17 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
         RingCursor cur{0, 0u};
         const bool prof = args.phase_cycles != nullptr && a == 0;
         long long a_go = 0, a_t0 = prof ? clk() : 0;
+        const volatile long long *limit = &s_limit;
+        int64_t consumed = 0;
         #pragma unroll 1
-        for (int64_t r = 0; r < nmoves; r++) {
-            const int buf = (int)(r & 1);
+        for (int64_t r = r_begin; r < nmoves; r++) {
+            const int64_t rr = r - r_begin;                   // barrier phases count from this launch's first move
+            const int buf = (int)(rr & 1);
             int32_t *wp = wpart + (buf * DN_A_WARPS + aw) * 4 * kt;
             const long long w0 = prof ? clk() : 0;
-            mbar_wait_relaxed_s(go_s, (uint32_t)(r & 1));     // z is stable (except z[i_{r-1}], fixed up by D)
+            mbar_wait_relaxed_s(go_s, (uint32_t)(rr & 1));    // z is stable (except z[i_{r-1}], fixed up by D)
             if (prof) a_go += clk() - w0;
+            if (r >= *limit) break;                           // the chain stops before this move (tier overflow)
             const int KA = s_KA;
             if (KA > DN_MAX_KD) a_move_bins(ap, cur, a, lane, bins, KA, wp);
             else if (full) {
@@ -507,9 +538,11 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
                 else if (KA <= 4) a_move_dp4a<4, false>(ap, cur, a, lane, wp);
                 else a_move_dp4a<8, false>(ap, cur, a, lane, wp);
             }
+            consumed += L.nchunks;
             __syncwarp();
             if (lane == 0) mbar_arrive_s(ready_s + 8u * buf);
         }
+        if (a == 0) s_consumed = consumed;
         if (prof) { args.phase_cycles[blockIdx.x * 32 + 2] = clk() - a_t0; args.phase_cycles[blockIdx.x * 32 + 3] = a_go; }
     } else {
         // =============================== D: decide =========================================
@@ -523,20 +556,23 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
         const bool full = full_obs && !has_absent;
         // move ids are fetched TWO moves ahead and the observation bytes the fix-ups need -- (i, i), (i, i_prev),
         // (i_prev, i), straight from the slabs -- ONE move ahead, so that no load is ever waited for
-        int item_n1 = nmoves > 0 ? args.move_item[m0] : 0, dom_n1 = nmoves > 0 ? args.move_dom[m0] : 0;
-        int item_n2 = nmoves > 1 ? args.move_item[m0 + 1] : -1, dom_n2 = nmoves > 1 ? args.move_dom[m0 + 1] : 0;
+        int item_n1 = args.move_item[m0 + r_begin], dom_n1 = args.move_dom[m0 + r_begin];
+        int item_n2 = r_begin + 1 < nmoves ? args.move_item[m0 + r_begin + 1] : -1, dom_n2 = r_begin + 1 < nmoves ? args.move_dom[m0 + r_begin + 1] : 0;
         uint32_t xb_d_next = 0xFFu, xb_rp_next = 0xFFu, xb_cp_next = 0xFFu;
         if (item_n1 >= 0 && item_n1 < n) xb_d_next = slab0[(int64_t)item_n1 * pitch0 + item_n1];
         const bool own_u = d == DN_ND - 1;                     // this thread provides the moves' uniforms
         const uint64_t u_stream = own_u && !args.uniforms ? args.stream[k_list] : 0, u_ctr0 = own_u && !args.uniforms ? args.counter0[k_list] : 0;
-        double u_next = own_u && args.uniforms && nmoves > 0 ? args.uniforms[m0] : 0.0;
+        double u_next = own_u && args.uniforms ? args.uniforms[m0 + r_begin] : 0.0;
         if (d == 0) mbar_arrive(bar_go);                       // move 0 may be accumulated
         const bool prof = args.phase_cycles != nullptr && d == 0;
-        long long ph[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tl = prof ? clk() : 0;
-#define DPHASE(i) do { if (prof) { const long long _t = clk(); ph[i] += _t - tl; tl = _t; } } while (0)
+        long long tl = prof ? clk() : 0;
+        if (prof) for (int i = 0; i < 14; i++) s_ph[i] = 0;
+#define DPHASE(i) do { if (prof) { const long long _t = clk(); s_ph[i] += _t - tl; tl = _t; } } while (0)
+        int64_t r_done = nmoves;                               // first move not made
         #pragma unroll 1
-        for (int64_t r = 0; r < nmoves; r++) {
+        for (int64_t r = r_begin; r < nmoves; r++) {
             const int64_t m = m0 + r;
+            const int64_t rr = r - r_begin;                    // barrier phases count from this launch's first move
             const int item = item_n1, item_next = item_n2;
             bool bad = item < 0 || item >= n || dom_n1 != 0;
             if (has_absent && !bad) bad = z_g[item] < 0;
@@ -553,10 +589,10 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
                 s_u = args.uniforms ? u_next : philox_uniform(args.seed, u_stream, u_ctr0 + (uint64_t)r);
                 if (args.uniforms && r + 1 < nmoves) u_next = args.uniforms[m + 1];
             }
-            const int buf = (int)(r & 1);
+            const int buf = (int)(rr & 1);
             int32_t *g = g_buf + buf * 4 * kt;
             DPHASE(5);
-            mbar_wait(&bar_ready[buf], (uint32_t)((r >> 1) & 1));
+            mbar_wait(&bar_ready[buf], (uint32_t)((rr >> 1) & 1));
             DPHASE(0);
             // ---- finish move r-1: z[i_{r-1}] becomes visible, its observation pair changes group ----
             if (pend_changed && d == 0) zs[pend_item] = (uint8_t)pend_new;
@@ -644,6 +680,20 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
             // ---- candidates: CRP::tables_weights_gibbs (cxx/hirm.hh:147-161) -------------------------
             const bool singleton = s_cnt[c] == 1;
             const bool nofree = !singleton && K >= kt;         // no slot for the fresh-table candidate
+            if (nofree && kt < kcap_g) {
+                // ---- this tier's table is full: stop BEFORE the move; the next tier resumes here.  Move r+1 is
+                //      already being accumulated: let it finish, then release the A warps once more so that they
+                //      see the limit.
+                r_done = r;
+                if (d == 0) {
+                    s_limit = r + 2;
+                    if (r + 1 < nmoves) {
+                        mbar_wait(&bar_ready[buf ^ 1], (uint32_t)(((rr + 1) >> 1) & 1));
+                        if (r + 2 < nmoves) mbar_arrive(bar_go);
+                    }
+                }
+                break;
+            }
             const int ncand = K + ((singleton || nofree) ? 0 : 1);
             const int fresh_label = max(0, s_lab[s_order[K - 1]]) + 1;   // t_max starts at 0 (cxx/hirm.hh:139)
 
@@ -699,9 +749,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
                             neg = term == 2;
                         }
                         __syncwarp();
-                        long long pt[7] = {0, 0, 0, 0, 0, 0, 0};
-                        const double v = lfact_diff_warp_s(s_lf, a, mm, prof ? pt : nullptr);
-                        if (prof) for (int i = 0; i < 6; i++) args.phase_cycles[blockIdx.x * 32 + 24 + i] += pt[i + 1] - pt[i];
+                        const double v = lfact_diff_warp_s(s_lf, a, mm);
                         acc += neg ? -v : v;
                     }
                     DPHASE(6);
@@ -831,7 +879,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
             }
             DPHASE(4);
         }
-        if (prof) for (int i = 0; i < 14; i++) args.phase_cycles[blockIdx.x * 32 + 8 + i] = ph[i];
+        if (prof) for (int i = 0; i < 14; i++) args.phase_cycles[blockIdx.x * 32 + 8 + i] = s_ph[i];
 #undef DPHASE
         // ---- finish the last move -----------------------------------------------------------------
         bar_d();
@@ -855,7 +903,16 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_ree_sweep_kernel(SweepArg
             }
             K -= 1;
         }
-        if (d == 0) s_K = K;
+        if (d == 0) { s_K = K; s_done = r_done; }
+    }
+    __syncthreads();
+
+    // ---- bulk copies issued for moves that will not be made here must land before the CTA exits ----
+    if (tid == 0) {
+        #pragma unroll 1
+        for (long long cidx = s_consumed; cidx < s_issued; cidx++)
+            mbar_wait(&bar_full[cidx % NS], (uint32_t)((cidx / NS) & 1));
+        if (args.progress) args.progress[blockIdx.x] = s_done;
     }
     __syncthreads();
 

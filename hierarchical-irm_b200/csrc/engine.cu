@@ -105,6 +105,7 @@ struct hirm_engine {
     DevBuf<int32_t> s_irm_ids, s_move_dom, s_move_item, s_choice, s_trace_n, s_trace_labels, s_blk;
     DevBuf<int64_t> s_move_off; DevBuf<double> s_uniforms, s_trace_logps, s_score;
     DevBuf<uint64_t> s_stream, s_counter;
+    DevBuf<long long> s_progress;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
     int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0;
@@ -643,7 +644,30 @@ extern "C" int hirm_irm_logp_score(hirm_engine *e, int32_t id, double *out) {
 // ---------------------------------------------------------------------------------------
 // sweep
 // ---------------------------------------------------------------------------------------
-struct Plan { std::vector<int32_t> generic_blk, dense_blk; DenseLaunch L; };
+struct Plan {
+    std::vector<int32_t> generic_blk, dense_blk;
+    DenseLaunch L{};      // dense tier A: a small shared-memory table, more chains per SM
+    DenseLaunch LB{};     // dense tier B: all max_tables slots, resumes the chains tier A had to stop (stages == 0: not needed)
+    int n_ent = 0, kcap = 0;
+};
+
+// Shared-memory plan of one dense tier: as many chains per SM as the launch has (up to 4) and fit; the rest of
+// each CTA's share of the SM's shared memory goes to its TMA ring.
+static bool plan_dense_tier(hirm_engine *e, int n, int kt, int n_dense, DenseLaunch &L) {
+    const int bins_words = std::min(4096, std::max(32 * DN_A_WARPS * 16, 32 * kt));
+    int chunk = 4 * 16 * DN_NA, want = std::min(4, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
+    if (const char *s = getenv("HIRM_DENSE_CHUNK")) chunk = std::max(16, atoi(s) & ~15);
+    if (const char *s = getenv("HIRM_DENSE_CTAS_PER_SM")) want = std::max(1, atoi(s));
+    L = DenseLaunch{};
+    for (; want >= 1; want--) {
+        const int budget = std::min(e->max_smem_optin, e->smem_per_sm / want - 1024) - 512;   // 1 KiB reserved per CTA + the kernel's static shared memory
+        const DenseLaunch L0 = dense_layout(n, kt, chunk, 0, bins_words);
+        int stages = (budget - L0.total_bytes) / (2 * L0.chunk);
+        stages = std::min(stages, std::min(DN_MAX_STAGES, 2 * L0.nchunks + 2));
+        if (stages >= 2 || (want == 1 && stages >= 1)) { L = dense_layout(n, kt, chunk, stages, bins_words); return true; }
+    }
+    return false;
+}
 
 static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_t flags, Plan &plan) {
     bool have_dense = false;
@@ -654,26 +678,17 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
         if (ensure_counts(e, h_irms[k])) return -1;
         if (irm->dense_ree && !(flags & HIRM_SWEEP_FORCE_GENERIC)) {
             if (!have_dense) {
-                // shared-memory plan: as many chains per SM as the launch has (up to 4), the rest of the
-                // SM's shared memory goes to the TMA ring of each CTA
                 int n_dense = 0;
                 for (int j = 0; j < n_irms; j++) { Irm *o = get_irm(e, h_irms[j]); if (o && o->dense_ree) n_dense++; }
-                const int kt = irm->kcap[0];
-                const int bins_words = std::min(4096, std::max(2048, 64 * kt));
-                int chunk = 2 * 16 * DN_NA, want = std::min(4, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
-                if (const char *s = getenv("HIRM_DENSE_CHUNK")) chunk = std::max(16, atoi(s) & ~15);
-                if (const char *s = getenv("HIRM_DENSE_CTAS_PER_SM")) want = std::max(1, atoi(s));
-                DenseLaunch L{};
-                for (; want >= 1; want--) {
-                    const int budget = std::min(e->max_smem_optin, e->smem_per_sm / want - 1024) - 512;   // 1 KiB reserved per CTA + the kernel's static shared memory
-                    const DenseLaunch L0 = dense_layout(irm->n_ent[0], kt, chunk, 0, bins_words);
-                    int stages = L0.chunk > 0 ? (budget - L0.total_bytes) / (2 * L0.chunk) : 0;
-                    stages = std::min(stages, std::min(DN_MAX_STAGES, 2 * L0.nchunks + 2));
-                    if (stages >= 2 || (want == 1 && stages >= 1)) { L = dense_layout(irm->n_ent[0], kt, chunk, stages, bins_words); break; }
-                }
-                if (L.stages < 1) return fail("domain too large for the dense fast path's shared-memory state");
-                plan.L = L; have_dense = true;
-            } else if (irm->n_ent[0] != plan.L.n || irm->kcap[0] != plan.L.kt) {
+                const int kcap = irm->kcap[0];
+                int kt_a = std::min(kcap, 32);
+                if (const char *s = getenv("HIRM_DENSE_TIER_SLOTS")) kt_a = std::min(kcap, std::max(2, atoi(s)));
+                if (!plan_dense_tier(e, irm->n_ent[0], kcap, n_dense, plan.LB))
+                    return fail("domain too large for the dense fast path's shared-memory state");
+                if (kt_a < kcap) plan_dense_tier(e, irm->n_ent[0], kt_a, n_dense, plan.L);
+                if (kt_a >= kcap || plan.L.stages < 1) { plan.L = plan.LB; plan.LB = DenseLaunch{}; }
+                plan.n_ent = irm->n_ent[0]; plan.kcap = kcap; have_dense = true;
+            } else if (irm->n_ent[0] != plan.n_ent || irm->kcap[0] != plan.kcap) {
                 return fail("dense irms of one sweep must share a shape");
             }
             plan.dense_blk.push_back(k);
@@ -695,11 +710,23 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         e->last_launches++; e->last_kind = 0;
     }
     if (!plan.dense_blk.empty()) {
-        CK(cudaFuncSetAttribute(dense_ree_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.L.total_bytes));
-        dense_ree_sweep_kernel<<<(unsigned)plan.dense_blk.size(), DN_THREADS, (size_t)plan.L.total_bytes, e->stream>>>(
-            args, e->s_blk.p + plan.generic_blk.size(), plan.L);
+        const unsigned nb = (unsigned)plan.dense_blk.size();
+        SweepArgs a2 = args;
+        if (plan.LB.stages > 0) {                      // two tiers: per-chain progress hands the stopped chains over
+            CK(e->s_progress.ensure(nb));
+            CK(cudaMemsetAsync(e->s_progress.p, 0, nb * sizeof(long long), e->stream));
+            a2.progress = e->s_progress.p;
+        }
+        const int smem_max = std::max(plan.L.total_bytes, plan.LB.total_bytes);
+        CK(cudaFuncSetAttribute(dense_ree_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        dense_ree_sweep_kernel<<<nb, DN_THREADS, (size_t)plan.L.total_bytes, e->stream>>>(a2, e->s_blk.p + plan.generic_blk.size(), plan.L);
         CK(cudaGetLastError());
         e->last_launches++; e->last_kind = 1;
+        if (plan.LB.stages > 0) {
+            dense_ree_sweep_kernel<<<nb, DN_THREADS, (size_t)plan.LB.total_bytes, e->stream>>>(a2, e->s_blk.p + plan.generic_blk.size(), plan.LB);
+            CK(cudaGetLastError());
+            e->last_launches++;
+        }
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense_ree_sweep_kernel, DN_THREADS, (size_t)plan.L.total_bytes);
         e->last_occupancy = occ; e->last_stages = plan.L.stages; e->last_chunk = plan.L.chunk; e->last_smem = plan.L.total_bytes;

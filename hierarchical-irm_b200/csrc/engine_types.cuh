@@ -95,6 +95,7 @@ struct SweepArgs {
     int32_t *trace_n;
     int32_t *trace_labels;
     double *trace_logps;
+    long long *progress;          // nullable: [n_blocks] moves of the block's IRM already made / made so far (dense tiers)
     long long *phase_cycles;      // nullable debug hook: [n_blocks][8] SM cycles per phase (thread 0's clock64)
 };
 

@@ -1,0 +1,165 @@
+"""GPU parity tests of the dense R(e,e) kernel's less-travelled paths, each against the CPU oracle on
+the same seeded inputs: the private-bins accumulation (> 8 live tables) with a mid-row flush, table
+births / deaths with slot compaction, the two-tier hand-over (a chain that outgrows the small
+shared-memory table is resumed by the second launch), repeated and out-of-range moves."""
+import os
+
+import numpy as np
+import pytest
+
+import engine_util as U
+import golden_util as G
+from hirm import engine as E
+from oracle import hirm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = E.Engine()
+    yield e
+    e.close()
+
+
+class env:
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        os.environ.update({k: str(v) for k, v in self.kw.items()})
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def build(eng, n, z0, seed, missing=0.0, kcap=32):
+    x = U.planted_ree(n, seed=seed, missing=missing)
+    ids, val = U.dense_to_coo(x)
+    o = O.Oracle([n], [[0, 0]])
+    o.set_observations(0, ids, val)
+    o.set_assignments(0, z0)
+    h = eng.irm_create([n], [[0, 0]], max_tables=kcap)
+    eng.set_observations_dense_host(h, 0, x)
+    eng.finalize(h)
+    eng.set_assignments(h, 0, z0)
+    return o, h
+
+
+def run_and_compare(eng, o, h, order, seed, stream, trace_cap=72):
+    dom = np.zeros_like(order)
+    res = eng.sweep([h], [(dom, order)], seed=seed, streams=[stream], counters=[0], trace_cap=trace_cap)
+    assert eng.last_sweep_info()["kernel_kind"] == 1
+    un = [O.uniform(seed, stream, m) for m in range(len(order))]
+    U.assert_traces_match(res["trace"][0], o, dom, order, un)
+    np.testing.assert_array_equal(eng.get_assignments(h, 0), o.get_assignments(0))
+    np.testing.assert_array_equal(eng.get_counts(h, 0), o.get_counts(0))
+    assert G.close(eng.logp_score(h), o.logp_score())
+    return res
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.2])
+def test_many_tables_bins_path_births_and_deaths(eng, missing):
+    """20 random tables over 500 entities collapse towards the planted blocks: the bins path (K > 8),
+    then the dp4a paths (K <= 8, 4, 2), many table deaths (slot compaction) and a few births."""
+    n = 500
+    z0 = np.random.default_rng(5).integers(0, 20, n).astype(np.int32) * 3 + 1     # labels with holes
+    o, h = build(eng, n, z0, seed=11, missing=missing)
+    rng = np.random.default_rng(8)
+    order = np.concatenate([rng.permutation(n) for _ in range(3)]).astype(np.int32)
+    res = run_and_compare(eng, o, h, order, seed=3, stream=9)
+    assert len(np.unique(eng.get_assignments(h, 0))) < 20
+    eng.irm_destroy(h)
+
+
+def test_bins_flush_inside_a_row(eng):
+    """40 tables, 64-byte ring chunks: the 8-bit private bins are flushed in the middle of a row."""
+    n = 1200
+    z0 = np.random.default_rng(6).integers(0, 40, n).astype(np.int32)
+    with env(HIRM_DENSE_CHUNK=64):
+        o, h = build(eng, n, z0, seed=12, kcap=48)
+        order = np.random.default_rng(9).permutation(n).astype(np.int32)[:300]
+        run_and_compare(eng, o, h, order, seed=4, stream=2)
+        assert eng.last_dense_plan()["chunk_bytes"] == 64
+    eng.irm_destroy(h)
+
+
+@pytest.mark.parametrize("tier_slots", [3, 6])
+def test_tier_handover_matches_oracle(eng, tier_slots):
+    """A first tier with `tier_slots` shared-memory table slots: chains stop when they need one more table and
+    the second launch resumes them at the same move with the same Philox counters -- the trajectory is the
+    oracle's, bit for bit."""
+    n = 300
+    z0 = U.crp_prior_labels(n, 1.5, np.random.default_rng(14))
+    with env(HIRM_DENSE_TIER_SLOTS=tier_slots):
+        o, h = build(eng, n, z0, seed=13)
+        rng = np.random.default_rng(10)
+        order = np.concatenate([rng.permutation(n) for _ in range(2)]).astype(np.int32)
+        run_and_compare(eng, o, h, order, seed=5, stream=1)
+        assert eng.last_sweep_info()["launches"] == 2
+    eng.irm_destroy(h)
+
+
+def test_tier_handover_many_chains_device_resident(eng):
+    """Eight chains over one dataset, on-device Philox, tier hand-over in the middle: each chain equals its
+    own oracle chain."""
+    n, chains = 160, 8
+    x = U.planted_ree(n, seed=3)
+    ids, val = U.dense_to_coo(x)
+    rng = np.random.default_rng(4)
+    hs, zs = [], []
+    for c in range(chains):
+        h = eng.irm_create([n], [[0, 0]], max_tables=24)
+        if c == 0:
+            eng.set_observations_dense_host(h, 0, x)
+            eng.finalize(h)
+        else:
+            eng.share_observations(h, hs[0])
+        z = rng.integers(0, 2 + c, n).astype(np.int32)
+        eng.set_assignments(h, 0, z)
+        hs.append(h); zs.append(z)
+    order = np.concatenate([rng.permutation(n) for _ in range(2)]).astype(np.int32)
+    mv = (np.zeros_like(order), order)
+    with env(HIRM_DENSE_TIER_SLOTS=4):
+        eng.sweep(hs, [mv] * chains, seed=21, streams=np.arange(chains, dtype=np.uint64) + 5, counters=np.full(chains, 7, np.uint64))
+    for c in range(chains):
+        o = O.Oracle([n], [[0, 0]])
+        o.set_observations(0, ids, val)
+        o.set_assignments(0, zs[c])
+        o.sweep(mv[0], mv[1], seed=21, stream=5 + c, offset=7)
+        np.testing.assert_array_equal(eng.get_assignments(hs[c], 0), o.get_assignments(0))
+        np.testing.assert_array_equal(eng.get_counts(hs[c], 0), o.get_counts(0))
+    for h in hs:
+        eng.irm_destroy(h)
+
+
+def test_repeated_and_bad_moves(eng):
+    """The same entity moved several times in a row (the fix-up of the previous move IS the diagonal), and
+    an out-of-range move in the middle of a list (reported, the other moves are still made)."""
+    n = 64
+    z0 = np.random.default_rng(1).integers(0, 5, n).astype(np.int32)
+    o, h = build(eng, n, z0, seed=2, missing=0.1)
+    order = np.asarray([5, 5, 5, 6, 5, 6, 6, 0, 63, 63, 1, 0, 0], dtype=np.int32)
+    run_and_compare(eng, o, h, order, seed=8, stream=4)
+    bad = np.asarray([3, 64, 4], dtype=np.int32)
+    with pytest.raises(E.EngineError):
+        eng.sweep([h], [(np.zeros_like(bad), bad)], seed=9, streams=[1], counters=[0])
+    o.move(0, 3, O.uniform(9, 1, 0)); o.move(0, 4, O.uniform(9, 1, 2))
+    np.testing.assert_array_equal(eng.get_assignments(h, 0), o.get_assignments(0))
+    np.testing.assert_array_equal(eng.get_counts(h, 0), o.get_counts(0))
+    eng.irm_destroy(h)
+
+
+def test_max_tables_exhausted_is_reported(eng):
+    n = 40
+    z0 = (np.arange(n) % 4).astype(np.int32)
+    o, h = build(eng, n, z0, seed=3, kcap=4)
+    with pytest.raises(E.EngineError) as ei:
+        eng.sweep([h], [(np.zeros(3, np.int32), np.arange(3, dtype=np.int32))], seed=1, streams=[0], counters=[0])
+    assert "max_tables" in str(ei.value)
+    eng.irm_destroy(h)
