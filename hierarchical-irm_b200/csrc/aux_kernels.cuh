@@ -1,0 +1,130 @@
+// Small batched kernels around the sweep: sweep-order generation, IRM::logp_score, CRP::transition_alpha.
+// One thread block per IRM; fixed reduction trees (deterministic results).
+#pragma once
+#include "engine_types.cuh"
+
+namespace hirm {
+
+constexpr int AUX_THREADS = 256;
+constexpr uint64_t ALPHA_SEED_TAG = 0x616c706861ull;   // "alpha": separates the alpha moves' Philox key from the entity moves'
+constexpr uint64_t ORDER_SEED_TAG = 0x6f72646572ull;   // "order"
+
+__device__ __forceinline__ double block_sum(double v, double *s_part) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_part[w];      // same order in every thread
+    return t;
+}
+
+// CRP::logp_score (cxx/hirm.hh:123-132) for table sizes cnt[0..hi): K log(alpha) + sum lgamma(cnt) + lgamma(alpha) - lgamma(N + alpha)
+__device__ __forceinline__ double crp_score_terms(const int32_t *cnt, int hi, int &K, int &N) {
+    K = 0; N = 0;
+    double t2 = 0.0;
+    for (int k = 0; k < hi; k++) {
+        const int c = cnt[k];
+        if (c > 0) { K++; N += c; t2 += lgamma((double)c); }
+    }
+    return t2;
+}
+
+// IRM::logp_score (cxx/hirm.hh:730-740) = sum_d CRP::logp_score + sum_r Relation::logp_score (:516-522)
+__global__ void __launch_bounds__(AUX_THREADS) logp_scores_kernel(const IrmDev *irms, const int32_t *irm_ids, double *out) {
+    const IrmDev &irm = irms[irm_ids[blockIdx.x]];
+    __shared__ double s_part[AUX_THREADS / 32];
+    double acc = 0.0;
+    for (int r = 0; r < irm.n_relations; r++) {
+        const RelationDev *R = &irm.rel[r];
+        for (int64_t i = threadIdx.x; i < R->ncells; i += blockDim.x) {
+            const cell_t c = R->counts[i];
+            if (cell_n(c)) acc += cell_score(cell_n(c), cell_s(c));
+        }
+    }
+    double total = block_sum(acc, s_part);
+    if (threadIdx.x == 0) {
+        for (int d = 0; d < irm.n_domains; d++) {
+            const DomainDev &dd = irm.dom[d];
+            int K, N;
+            const double t2 = crp_score_terms(dd.tab_count, *dd.hi, K, N);
+            if (N > 0) total += K * log(dd.alpha) + t2 + lgamma(dd.alpha) - lgamma(N + dd.alpha);
+        }
+        out[blockIdx.x] = total;
+    }
+}
+
+// CRP::transition_alpha (cxx/hirm.hh:162-173; src/hirm.py:109-116): grid-Gibbs over log_linspace(1/N, N+1, ngrid)
+// (cxx/util_math.cc:17-32), the index drawn with the engine's inversion rule.  Writes alpha into the device
+// descriptor and out_alpha[block * MAX_DOMAINS + d]; optional trace of the grid log-probabilities.
+__global__ void __launch_bounds__(64) transition_alpha_kernel(IrmDev *irms, const int32_t *irm_ids, int ngrid, uint64_t seed,
+                                                              const uint64_t *stream, const uint64_t *counter, const double *uniforms,
+                                                              double *out_alpha, double *trace_lp /* nullable [blocks][MAX_DOMAINS][ngrid] */) {
+    IrmDev &irm = irms[irm_ids[blockIdx.x]];
+    __shared__ double s_lp[64];
+    __shared__ double s_grid[64];
+    for (int d = 0; d < irm.n_domains; d++) {
+        DomainDev &dd = irm.dom[d];
+        int K, N;
+        const double t2 = crp_score_terms(dd.tab_count, *dd.hi, K, N);       // every thread: the same value
+        double alpha_new = dd.alpha;
+        if (N > 0) {                                                          // `if (N == 0) return;` (cxx/hirm.hh:163)
+            const double lo = log(1.0 / N), hi = log((double)N + 1.0);
+            const double step = (hi - lo) / (ngrid - 1);
+            const int g = threadIdx.x;
+            if (g < ngrid) {
+                const double a = exp(lo + step * g);
+                s_grid[g] = a;
+                s_lp[g] = K * log(a) + t2 + lgamma(a) - lgamma(N + a);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const double u = uniforms ? uniforms[blockIdx.x * MAX_DOMAINS + d]
+                                          : philox_uniform(seed ^ ALPHA_SEED_TAG, stream[blockIdx.x], counter[blockIdx.x] * MAX_DOMAINS + d);
+                alpha_new = s_grid[choose_index(s_lp, ngrid, u)];
+                dd.alpha = alpha_new;
+            }
+            if (trace_lp && threadIdx.x < ngrid) trace_lp[((int64_t)blockIdx.x * MAX_DOMAINS + d) * ngrid + threadIdx.x] = s_lp[threadIdx.x];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out_alpha[blockIdx.x * MAX_DOMAINS + d] = alpha_new;
+    }
+}
+
+__device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; }
+
+// Sweep order (the loops of cxx/hirm.cc:45-51 / IRM::transition_cluster_assignments_all, cxx/hirm.hh:590-596): for every
+// sweep, every domain in index order, every entity once -- in the order j -> (a j + b) mod n with (a, b) drawn per
+// (irm, sweep, domain) from Philox, gcd(a, n) = 1 (the reference's order is a hash-container artefact).
+// Block k fills moves [off[k], off[k+1]).
+__global__ void __launch_bounds__(AUX_THREADS) gen_moves_kernel(const IrmDev *irms, const int32_t *irm_ids, const int64_t *move_off,
+                                                                int n_sweeps, uint64_t seed, const uint64_t *stream, const uint64_t *sweep0,
+                                                                int32_t *move_dom, int32_t *move_item) {
+    const IrmDev &irm = irms[irm_ids[blockIdx.x]];
+    int64_t pos = move_off[blockIdx.x];
+    __shared__ uint32_t s_a, s_b;
+    for (int s = 0; s < n_sweeps; s++) {
+        for (int d = 0; d < irm.n_domains; d++) {
+            const uint32_t n = (uint32_t)irm.dom[d].n;
+            if (n == 0) continue;
+            if (threadIdx.x == 0) {
+                uint32_t w[4];
+                const uint64_t ctr = (sweep0[blockIdx.x] + (uint64_t)s) * MAX_DOMAINS + d, st = stream[blockIdx.x], sd = seed ^ ORDER_SEED_TAG;
+                philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)st, (uint32_t)(st >> 32), (uint32_t)sd, (uint32_t)(sd >> 32), w);
+                uint32_t a = n > 1 ? 1u + w[0] % (n - 1u) : 1u;
+                while (gcd_u32(a, n) != 1u) a = a + 1u >= n ? 1u : a + 1u;
+                s_a = a; s_b = w[1] % n;
+            }
+            __syncthreads();
+            const uint64_t a = s_a, b = s_b;
+            for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+                move_dom[pos + j] = d;
+                move_item[pos + j] = (int32_t)((a * j + b) % n);
+            }
+            pos += n;
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace hirm

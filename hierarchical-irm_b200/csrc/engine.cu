@@ -18,6 +18,7 @@
 #include "engine_types.cuh"
 #include "generic_sweep.cuh"
 #include "dense_sweep.cuh"
+#include "aux_kernels.cuh"
 
 using namespace hirm;
 
@@ -87,10 +88,11 @@ struct Irm {
     DevBuf<int32_t> gl_rel; DevBuf<int64_t> gl_cell; int64_t gl_cap = 0;
     DevBuf<int32_t> error;
     DevBuf<RelationDev> d_rel;
-    std::vector<bool> have_z;
+    std::vector<bool> have_z, has_absent;
     bool counts_dirty = true, desc_dirty = true, scratch_ready = false;
     bool alive = true;
     bool dense_ree = false;            // eligible for the dense fast path
+    uint64_t rng_stream = 0, move_counter = 0, sweep_counter = 0, alpha_counter = 0;   // Philox positions of sweep_all / transition_alpha
 };
 
 }  // namespace
@@ -106,6 +108,8 @@ struct hirm_engine {
     DevBuf<int64_t> s_move_off; DevBuf<double> s_uniforms, s_trace_logps, s_score;
     DevBuf<uint64_t> s_stream, s_counter;
     DevBuf<long long> s_progress;
+    DevBuf<double> s_alpha;
+    DevBuf<uint64_t> s_sweep0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
     int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0;
@@ -196,7 +200,7 @@ extern "C" int hirm_irm_create(hirm_engine *e, int n_domains, const int32_t *n_e
         irm->n_ent.push_back(n_entities[d]); irm->kcap.push_back(max_tables[d]);
     }
     irm->alpha.assign(n_domains, 1.0);                 // CRP::alpha default (cxx/hirm.hh:72)
-    irm->have_z.assign(n_domains, false);
+    irm->have_z.assign(n_domains, false); irm->has_absent.assign(n_domains, false);
     irm->cstride.resize(n_relations); irm->gstride.resize(n_relations);
     irm->ncells.resize(n_relations); irm->gcells.resize(n_relations); irm->gbit0.resize(n_relations);
     const int64_t CELL_BUDGET = (int64_t)1 << 27;      // 1 GiB of packed cells per table
@@ -231,6 +235,7 @@ extern "C" int hirm_irm_create(hirm_engine *e, int n_domains, const int32_t *n_e
     }
     irm->counts.resize(n_relations); irm->groups.resize(n_relations);
     CK(irm->error.alloc(1)); CK(cudaMemset(irm->error.p, 0, sizeof(int32_t)));
+    irm->rng_stream = (uint64_t)e->irms.size();
     e->irms.push_back(std::move(irm));
     *out_irm = (int32_t)e->irms.size() - 1;
     return 0;
@@ -561,6 +566,8 @@ extern "C" int hirm_irm_set_assignments(hirm_engine *e, int32_t id, int dom, con
     CK(cudaMemcpy(irm->tab_label[dom].p, lab.data(), kcap * sizeof(int32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(irm->hi[dom].p, &hi, sizeof(int32_t), cudaMemcpyHostToDevice));
     irm->have_z[dom] = true; irm->counts_dirty = true;
+    irm->has_absent[dom] = false;
+    for (int i = 0; i < n; i++) if (h_labels[i] < 0) irm->has_absent[dom] = true;
     return 0;
 }
 
@@ -614,30 +621,97 @@ extern "C" int hirm_irm_get_counts(hirm_engine *e, int32_t id, int rel, int32_t 
     return 0;
 }
 
-extern "C" int hirm_irm_logp_score(hirm_engine *e, int32_t id, double *out) {
-    GET_IRM(irm, e, id);
-    if (!out) return fail("out is null");
-    if (ensure_counts(e, id)) return -1;
-    CK(e->s_score.ensure((size_t)std::max(1, irm->n_relations)));
-    for (int r = 0; r < irm->n_relations; r++) {
-        relation_score_kernel<<<1, 1024, 0, e->stream>>>(e->d_irms.p, id, r, e->s_score.p + r);
-        CK(cudaGetLastError());
+extern "C" int hirm_engine_logp_scores(hirm_engine *e, int n_irms, const int32_t *h_irms, double *h_out) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n_irms <= 0) return 0;
+    if (!h_irms || !h_out) return fail("null argument");
+    for (int k = 0; k < n_irms; k++) {
+        if (!get_irm(e, h_irms[k])) return fail("bad irm id");
+        if (ensure_counts(e, h_irms[k])) return -1;
     }
-    std::vector<double> rs((size_t)std::max(1, irm->n_relations), 0.0);
-    CK(cudaMemcpyAsync(rs.data(), e->s_score.p, rs.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(e->s_irm_ids.ensure((size_t)n_irms)); CK(e->s_score.ensure((size_t)n_irms));
+    CK(cudaMemcpyAsync(e->s_irm_ids.p, h_irms, n_irms * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    logp_scores_kernel<<<n_irms, AUX_THREADS, 0, e->stream>>>(e->d_irms.p, e->s_irm_ids.p, e->s_score.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_out, e->s_score.p, n_irms * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    double total = 0;
-    for (int r = 0; r < irm->n_relations; r++) total += rs[(size_t)r];
-    // CRP::logp_score (cxx/hirm.hh:123-132): O(K) host arithmetic on the table sizes
-    for (int d = 0; d < irm->n_domains; d++) {
-        std::vector<int32_t> cnt((size_t)irm->kcap[d]);
-        CK(cudaMemcpy(cnt.data(), irm->tab_count[d].p, cnt.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        int N = 0, K = 0; double t2 = 0;
-        for (int c : cnt) if (c > 0) { N += c; K++; t2 += lgamma((double)c); }
-        if (N == 0) continue;
-        total += K * log(irm->alpha[d]) + t2 + lgamma(irm->alpha[d]) - lgamma(N + irm->alpha[d]);
+    return 0;
+}
+
+extern "C" int hirm_irm_logp_score(hirm_engine *e, int32_t id, double *out) {
+    if (!out) return fail("out is null");
+    return hirm_engine_logp_scores(e, 1, &id, out);
+}
+
+extern "C" int hirm_engine_transition_alpha(hirm_engine *e, int n_irms, const int32_t *h_irms, int ngrid, uint64_t seed,
+                                            const double *h_uniforms, double *h_out_alpha, double *h_trace_lp) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n_irms <= 0) return 0;
+    if (!h_irms) return fail("null argument");
+    if (ngrid < 2 || ngrid > 64) return fail("ngrid must be in [2, 64]");
+    std::vector<uint64_t> st((size_t)n_irms), ct((size_t)n_irms);
+    for (int k = 0; k < n_irms; k++) {
+        Irm *irm = get_irm(e, h_irms[k]);
+        if (!irm) return fail("bad irm id");
+        for (int j = 0; j < k; j++) if (h_irms[j] == h_irms[k]) return fail("an irm may appear once per call");
+        if (ensure_counts(e, h_irms[k])) return -1;
+        st[(size_t)k] = irm->rng_stream; ct[(size_t)k] = irm->alpha_counter++;
     }
-    *out = total;
+    const size_t na = (size_t)n_irms * MAX_DOMAINS;
+    CK(e->s_irm_ids.ensure((size_t)n_irms)); CK(e->s_stream.ensure((size_t)n_irms)); CK(e->s_counter.ensure((size_t)n_irms));
+    CK(e->s_alpha.ensure(na));
+    cudaStream_t s0 = e->stream;
+    CK(cudaMemcpyAsync(e->s_irm_ids.p, h_irms, n_irms * sizeof(int32_t), cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(e->s_stream.p, st.data(), n_irms * sizeof(uint64_t), cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(e->s_counter.p, ct.data(), n_irms * sizeof(uint64_t), cudaMemcpyHostToDevice, s0));
+    if (h_uniforms) {
+        CK(e->s_uniforms.ensure(na));
+        CK(cudaMemcpyAsync(e->s_uniforms.p, h_uniforms, na * sizeof(double), cudaMemcpyHostToDevice, s0));
+    }
+    if (h_trace_lp) CK(e->s_trace_logps.ensure(na * ngrid));
+    transition_alpha_kernel<<<n_irms, 64, 0, s0>>>(e->d_irms.p, e->s_irm_ids.p, ngrid, seed, e->s_stream.p, e->s_counter.p,
+                                                  h_uniforms ? e->s_uniforms.p : nullptr, e->s_alpha.p, h_trace_lp ? e->s_trace_logps.p : nullptr);
+    CK(cudaGetLastError());
+    std::vector<double> al(na);
+    CK(cudaMemcpyAsync(al.data(), e->s_alpha.p, na * sizeof(double), cudaMemcpyDeviceToHost, s0));
+    if (h_trace_lp) CK(cudaMemcpyAsync(h_trace_lp, e->s_trace_logps.p, na * ngrid * sizeof(double), cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    for (int k = 0; k < n_irms; k++) {                 // host mirror of CRP::alpha (the kernel wrote the device descriptors)
+        Irm *irm = e->irms[h_irms[k]].get();
+        for (int d = 0; d < irm->n_domains; d++) { irm->alpha[d] = al[(size_t)k * MAX_DOMAINS + d]; e->h_irms[h_irms[k]].dom[d].alpha = irm->alpha[d]; }
+    }
+    if (h_out_alpha) memcpy(h_out_alpha, al.data(), na * sizeof(double));
+    return 0;
+}
+
+extern "C" int hirm_irm_get_alpha(hirm_engine *e, int32_t id, int dom, double *out) {
+    GET_IRM(irm, e, id);
+    if (dom < 0 || dom >= irm->n_domains || !out) return fail("bad domain index");
+    *out = irm->alpha[dom];
+    return 0;
+}
+
+extern "C" int hirm_irm_get_tables(hirm_engine *e, int32_t id, int dom, int32_t *h_labels, int32_t *h_counts, int cap, int32_t *n_tables) {
+    GET_IRM(irm, e, id);
+    if (dom < 0 || dom >= irm->n_domains || !n_tables) return fail("bad domain index");
+    const int kcap = irm->kcap[dom];
+    std::vector<int32_t> cnt((size_t)kcap), lab((size_t)kcap);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(cnt.data(), irm->tab_count[dom].p, kcap * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lab.data(), irm->tab_label[dom].p, kcap * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<std::pair<int32_t, int32_t>> t;
+    for (int k = 0; k < kcap; k++) if (cnt[(size_t)k] > 0) t.push_back({lab[(size_t)k], cnt[(size_t)k]});
+    std::sort(t.begin(), t.end());
+    *n_tables = (int32_t)t.size();
+    for (int k = 0; k < (int)t.size() && k < cap; k++) { if (h_labels) h_labels[k] = t[(size_t)k].first; if (h_counts) h_counts[k] = t[(size_t)k].second; }
+    return 0;
+}
+
+extern "C" int hirm_irm_set_rng(hirm_engine *e, int32_t id, uint64_t stream, uint64_t move_counter) {
+    GET_IRM(irm, e, id);
+    irm->rng_stream = stream; irm->move_counter = move_counter;
     return 0;
 }
 
@@ -802,14 +876,9 @@ extern "C" int hirm_engine_sweep(hirm_engine *e, int n_irms, const int32_t *h_ir
     return 0;
 }
 
-extern "C" int hirm_engine_sweep_device(hirm_engine *e, int n_irms, const int32_t *h_irms, const int64_t *d_move_offsets,
-                                        const int32_t *d_move_dom, const int32_t *d_move_item, uint64_t seed,
-                                        const uint64_t *d_stream, const uint64_t *d_counter0, uint32_t flags,
-                                        int32_t *d_out_choice) {
-    if (!e) return fail("engine is null");
-    CK(cudaSetDevice(e->device));
-    if (n_irms <= 0) return 0;
-    if (!h_irms || !d_move_offsets || !d_move_dom || !d_move_item || !d_stream || !d_counter0) return fail("null argument");
+static int sweep_device_impl(hirm_engine *e, int n_irms, const int32_t *h_irms, const int64_t *d_move_offsets,
+                             const int32_t *d_move_dom, const int32_t *d_move_item, uint64_t seed,
+                             const uint64_t *d_stream, const uint64_t *d_counter0, uint32_t flags, int32_t *d_out_choice) {
     Plan plan;
     if (plan_sweep(e, n_irms, h_irms, flags, plan)) return -1;
     if (upload_blk(e, plan)) return -1;
@@ -823,6 +892,75 @@ extern "C" int hirm_engine_sweep_device(hirm_engine *e, int n_irms, const int32_
     args.seed = seed; args.stream = d_stream; args.counter0 = d_counter0; args.flags = flags;
     args.out_choice = d_out_choice; args.trace_cap = 0; args.phase_cycles = e->d_phase_cycles;
     return launch_sweep(e, plan, args);
+}
+
+extern "C" int hirm_engine_sweep_device(hirm_engine *e, int n_irms, const int32_t *h_irms, const int64_t *d_move_offsets,
+                                        const int32_t *d_move_dom, const int32_t *d_move_item, uint64_t seed,
+                                        const uint64_t *d_stream, const uint64_t *d_counter0, uint32_t flags,
+                                        int32_t *d_out_choice) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n_irms <= 0) return 0;
+    if (!h_irms || !d_move_offsets || !d_move_dom || !d_move_item || !d_stream || !d_counter0) return fail("null argument");
+    return sweep_device_impl(e, n_irms, h_irms, d_move_offsets, d_move_dom, d_move_item, seed, d_stream, d_counter0, flags, d_out_choice);
+}
+
+// IRM::transition_cluster_assignments_all (cxx/hirm.hh:590-596), n_sweeps times, for every listed IRM: the sweep order
+// is generated on the device (gen_moves_kernel), nothing but the IRM ids crosses the bus on the way in.
+extern "C" int hirm_engine_sweep_all(hirm_engine *e, int n_irms, const int32_t *h_irms, int n_sweeps, uint64_t seed, uint32_t flags,
+                                     int64_t cap_moves, int32_t *h_out_dom, int32_t *h_out_item, int32_t *h_out_choice, int64_t *n_moves) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n_moves) *n_moves = 0;
+    if (n_irms <= 0 || n_sweeps <= 0) return 0;
+    if (!h_irms) return fail("null argument");
+    std::vector<int64_t> off((size_t)n_irms + 1, 0);
+    std::vector<uint64_t> st((size_t)n_irms), ct((size_t)n_irms), sw((size_t)n_irms);
+    for (int k = 0; k < n_irms; k++) {
+        Irm *irm = get_irm(e, h_irms[k]);
+        if (!irm) return fail("bad irm id in sweep list");
+        int64_t per = 0;
+        for (int d = 0; d < irm->n_domains; d++) {
+            if (!irm->have_z[d]) return fail("set_assignments has not been called for every domain");
+            if (irm->has_absent[d]) return fail("sweep_all needs every entity seated: pass an explicit move list to hirm_engine_sweep");
+            per += irm->n_ent[d];
+        }
+        off[(size_t)k + 1] = off[(size_t)k] + per * n_sweeps;
+        st[(size_t)k] = irm->rng_stream; ct[(size_t)k] = irm->move_counter; sw[(size_t)k] = irm->sweep_counter;
+    }
+    const int64_t nm = off[(size_t)n_irms];
+    if (n_moves) *n_moves = nm;
+    if ((h_out_dom || h_out_item || h_out_choice) && cap_moves < nm) return fail("output buffers are too small for the generated moves");
+    const size_t nmz = (size_t)std::max<int64_t>(nm, 1);
+    // descriptors must be on the device before the order kernel reads the domain sizes
+    for (int k = 0; k < n_irms; k++) if (ensure_counts(e, h_irms[k])) return -1;
+    CK(e->s_irm_ids.ensure((size_t)n_irms)); CK(e->s_move_off.ensure((size_t)n_irms + 1));
+    CK(e->s_move_dom.ensure(nmz)); CK(e->s_move_item.ensure(nmz)); CK(e->s_choice.ensure(nmz));
+    CK(e->s_stream.ensure((size_t)n_irms)); CK(e->s_counter.ensure((size_t)n_irms)); CK(e->s_sweep0.ensure((size_t)n_irms));
+    cudaStream_t s0 = e->stream;
+    CK(cudaMemcpyAsync(e->s_irm_ids.p, h_irms, n_irms * sizeof(int32_t), cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(e->s_move_off.p, off.data(), (n_irms + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(e->s_stream.p, st.data(), n_irms * sizeof(uint64_t), cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(e->s_counter.p, ct.data(), n_irms * sizeof(uint64_t), cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(e->s_sweep0.p, sw.data(), n_irms * sizeof(uint64_t), cudaMemcpyHostToDevice, s0));
+    CK(cudaStreamSynchronize(s0));                      // the sources above are locals
+    gen_moves_kernel<<<n_irms, AUX_THREADS, 0, s0>>>(e->d_irms.p, e->s_irm_ids.p, e->s_move_off.p, n_sweeps, seed, e->s_stream.p, e->s_sweep0.p,
+                                                    e->s_move_dom.p, e->s_move_item.p);
+    CK(cudaGetLastError());
+    if (sweep_device_impl(e, n_irms, h_irms, e->s_move_off.p, e->s_move_dom.p, e->s_move_item.p, seed, e->s_stream.p, e->s_counter.p, flags, e->s_choice.p))
+        return -1;
+    e->last_launches++;                                 // the order kernel
+    for (int k = 0; k < n_irms; k++) {
+        Irm *irm = e->irms[h_irms[k]].get();
+        irm->move_counter += (uint64_t)(off[(size_t)k + 1] - off[(size_t)k]); irm->sweep_counter += (uint64_t)n_sweeps;
+    }
+    if (h_out_dom) CK(cudaMemcpyAsync(h_out_dom, e->s_move_dom.p, nm * sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
+    if (h_out_item) CK(cudaMemcpyAsync(h_out_item, e->s_move_item.p, nm * sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
+    if (h_out_choice) CK(cudaMemcpyAsync(h_out_choice, e->s_choice.p, nm * sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    for (int k = 0; k < n_irms; k++)
+        if (check_kernel_error(e, e->irms[h_irms[k]].get())) return -1;
+    return 0;
 }
 
 extern "C" int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, int32_t *kernel_kind, float *kernel_ms) {

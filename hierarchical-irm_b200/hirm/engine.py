@@ -29,7 +29,8 @@ EXPORTS = [
     "hirm_irm_share_observations", "hirm_irm_finalize", "hirm_irm_set_assignments", "hirm_irm_get_assignments",
     "hirm_irm_set_alpha", "hirm_irm_get_counts", "hirm_irm_logp_score", "hirm_engine_sweep",
     "hirm_engine_sweep_device", "hirm_engine_last_sweep_info", "hirm_engine_transpose_u8",
-    "hirm_engine_debug_phase_cycles", "hirm_engine_last_dense_plan",
+    "hirm_engine_debug_phase_cycles", "hirm_engine_last_dense_plan", "hirm_engine_sweep_all", "hirm_irm_set_rng",
+    "hirm_engine_logp_scores", "hirm_engine_transition_alpha", "hirm_irm_get_alpha", "hirm_irm_get_tables",
 ]
 
 _lib = None
@@ -81,6 +82,12 @@ def load():
     L.hirm_engine_transpose_u8.argtypes = [V, V, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, V, ctypes.c_int64]
     L.hirm_engine_debug_phase_cycles.argtypes = [V, V]
     L.hirm_engine_last_dense_plan.argtypes = [V, c_i32p, c_i32p, c_i32p, c_i32p]
+    L.hirm_engine_sweep_all.argtypes = [V, I, c_i32p, I, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_i64p]
+    L.hirm_irm_set_rng.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
+    L.hirm_engine_logp_scores.argtypes = [V, I, c_i32p, c_f64p]
+    L.hirm_engine_transition_alpha.argtypes = [V, I, c_i32p, I, ctypes.c_uint64, c_f64p, c_f64p, c_f64p]
+    L.hirm_irm_get_alpha.argtypes = [V, ctypes.c_int32, I, c_f64p]
+    L.hirm_irm_get_tables.argtypes = [V, ctypes.c_int32, I, c_i32p, c_i32p, I, c_i32p]
     _lib = L
     return L
 
@@ -229,6 +236,53 @@ class Engine:
         self._ck(self.L.hirm_engine_last_sweep_info(self._h, ctypes.byref(n), ctypes.byref(k), ctypes.byref(ms)))
         return dict(launches=n.value, kernel_kind=k.value, kernel_ms=ms.value)
 
+    def sweep_all(self, irms, n_sweeps=1, seed=0, flags=0, want_moves=False):
+        """transition_cluster_assignments_all for every listed IRM, order generated on the device.
+        Returns the number of moves, or (n_moves, dom, item, choice) when want_moves."""
+        irms = np.ascontiguousarray(irms, dtype=np.int32)
+        n = ctypes.c_int64()
+        if not want_moves:
+            self._ck(self.L.hirm_engine_sweep_all(self._h, len(irms), _p(irms, c_i32p), n_sweeps, seed, flags, 0, None, None, None, ctypes.byref(n)))
+            return n.value
+        total = sum(sum(self._schemas[int(h)][0]) for h in irms) * n_sweeps
+        dom = np.empty(max(total, 1), np.int32); item = np.empty(max(total, 1), np.int32); choice = np.empty(max(total, 1), np.int32)
+        self._ck(self.L.hirm_engine_sweep_all(self._h, len(irms), _p(irms, c_i32p), n_sweeps, seed, flags, total, _p(dom, c_i32p),
+                                              _p(item, c_i32p), _p(choice, c_i32p), ctypes.byref(n)))
+        return n.value, dom[:n.value], item[:n.value], choice[:n.value]
+
+    def set_rng(self, irm, stream, move_counter=0):
+        self._ck(self.L.hirm_irm_set_rng(self._h, irm, stream, move_counter))
+
+    def logp_scores(self, irms):
+        irms = np.ascontiguousarray(irms, dtype=np.int32)
+        out = np.empty(max(len(irms), 1), np.float64)
+        self._ck(self.L.hirm_engine_logp_scores(self._h, len(irms), _p(irms, c_i32p), _p(out, c_f64p)))
+        return out[:len(irms)]
+
+    def transition_alpha(self, irms, ngrid=20, seed=0, uniforms=None, trace=False):
+        """CRP::transition_alpha for every domain of every listed IRM; returns alpha [n_irms, MAX_DOMAINS]
+        (and the grid log-probabilities [n_irms, MAX_DOMAINS, ngrid] when trace)."""
+        irms = np.ascontiguousarray(irms, dtype=np.int32)
+        un = None
+        if uniforms is not None:
+            un = np.zeros((len(irms), MAX_DOMAINS), np.float64)
+            u = np.asarray(uniforms, np.float64).reshape(len(irms), -1)
+            un[:, :u.shape[1]] = u
+        out = np.empty((max(len(irms), 1), MAX_DOMAINS), np.float64)
+        tr = np.zeros((max(len(irms), 1), MAX_DOMAINS, ngrid), np.float64) if trace else None
+        self._ck(self.L.hirm_engine_transition_alpha(self._h, len(irms), _p(irms, c_i32p), ngrid, seed, _p(un, c_f64p), _p(out, c_f64p), _p(tr, c_f64p)))
+        return (out[:len(irms)], tr[:len(irms)]) if trace else out[:len(irms)]
+
+    def get_alpha(self, irm, dom):
+        out = ctypes.c_double()
+        self._ck(self.L.hirm_irm_get_alpha(self._h, irm, dom, ctypes.byref(out)))
+        return out.value
+
+    def get_tables(self, irm, dom, cap=256):
+        lab = np.empty(cap, np.int32); cnt = np.empty(cap, np.int32); n = ctypes.c_int32()
+        self._ck(self.L.hirm_irm_get_tables(self._h, irm, dom, _p(lab, c_i32p), _p(cnt, c_i32p), cap, ctypes.byref(n)))
+        return lab[:n.value].copy(), cnt[:n.value].copy()
+
     def last_dense_plan(self):
         a, b, c, d = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         self._ck(self.L.hirm_engine_last_dense_plan(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
@@ -264,6 +318,18 @@ class IrmBackend:
 
     def logp_score(self):
         return self.e.logp_score(self.irm)
+
+    def transition_alpha(self, dom, u, ngrid):
+        """CRP::transition_alpha of ONE domain with an injected uniform (the engine call moves every domain
+        of the IRM: the others are put back).  Returns (alpha, grid log-probabilities)."""
+        nd = len(self.e._schemas[self.irm][0])
+        before = [self.e.get_alpha(self.irm, k) for k in range(nd)]
+        un = np.zeros(MAX_DOMAINS); un[dom] = u
+        alpha, lp = self.e.transition_alpha([self.irm], ngrid=ngrid, uniforms=[un], trace=True)
+        for k in range(nd):
+            if k != dom:
+                self.e.set_alpha(self.irm, k, before[k])
+        return float(alpha[0, dom]), lp[0, dom]
 
     def score(self, dom, item, cap=256):
         r = self.e.sweep([self.irm], [([dom], [item])], flags=SWEEP_SCORE_ONLY, trace_cap=cap)

@@ -122,6 +122,30 @@ int hirm_engine_sweep_device(hirm_engine *e, int n_irms, const int32_t *h_irms, 
                              const uint64_t *d_stream, const uint64_t *d_counter0, uint32_t flags,
                              int32_t *d_out_choice);
 
+/* IRM::transition_cluster_assignments_all (cxx/hirm.hh:590-596; src/hirm.py:392-400; the item loops of
+ * cxx/hirm.cc:45-51,73-81), n_sweeps times for every listed IRM.  The sweep order is engine-defined and generated
+ * on the device: per sweep every domain in index order, its entities in the order j -> (a j + b) mod n with (a, b)
+ * drawn per (irm, sweep, domain) from Philox (the reference's order is a hash-container artefact).  Uniforms:
+ * Philox4x32-10(key = seed, ctr = (irm's move counter + m, irm's stream)), see hirm_irm_set_rng.
+ * Outputs nullable: the generated moves and chosen labels (cap_moves entries each); *n_moves = moves made. */
+int hirm_engine_sweep_all(hirm_engine *e, int n_irms, const int32_t *h_irms, int n_sweeps, uint64_t seed, uint32_t flags,
+                          int64_t cap_moves, int32_t *h_out_dom, int32_t *h_out_item, int32_t *h_out_choice, int64_t *n_moves);
+/* Philox stream id (default: the irm id) and move counter used by hirm_engine_sweep_all / _transition_alpha */
+int hirm_irm_set_rng(hirm_engine *e, int32_t irm, uint64_t stream, uint64_t move_counter);
+
+/* IRM::logp_score for many IRMs in one launch   (cxx/hirm.hh:730-740) */
+int hirm_engine_logp_scores(hirm_engine *e, int n_irms, const int32_t *h_irms, double *h_out);
+
+/* CRP::transition_alpha for every domain of every listed IRM   (cxx/hirm.hh:162-173: 20-point grid; src/hirm.py:109-116:
+ * 30 points).  Grid = log_linspace(1/N, N+1, ngrid) (cxx/util_math.cc:17-32), index drawn with the engine's inversion
+ * rule from h_uniforms[k * HIRM_MAX_DOMAINS + d] or, when NULL, Philox.  h_out_alpha [n_irms * HIRM_MAX_DOMAINS] and
+ * h_trace_lp [n_irms * HIRM_MAX_DOMAINS * ngrid] (grid log-probabilities) are nullable. */
+int hirm_engine_transition_alpha(hirm_engine *e, int n_irms, const int32_t *h_irms, int ngrid, uint64_t seed,
+                                 const double *h_uniforms, double *h_out_alpha, double *h_trace_lp);
+int hirm_irm_get_alpha(hirm_engine *e, int32_t irm, int dom, double *out);
+/* CRP::tables read-back (cxx/hirm.hh:74): labels ascending and customers per table */
+int hirm_irm_get_tables(hirm_engine *e, int32_t irm, int dom, int32_t *h_labels, int32_t *h_counts, int cap, int32_t *n_tables);
+
 /* statistics of the last sweep: kernel launches made, which kernel ran (0 generic, 1 dense, 2 dense-cluster) */
 int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, int32_t *kernel_kind, float *kernel_ms);
 

@@ -455,3 +455,27 @@ double hirm_oracle_logp_score(hirm_oracle *o) {
     }
     return crp + rel;
 }
+
+/* CRP::transition_alpha (cxx/hirm.hh:162-173; 30 grid points in src/hirm.py:109-116): grid-Gibbs over
+ * log_linspace(1/N, N+1, ngrid) (cxx/util_math.cc:17-32, endpoint included), each grid point scored with
+ * CRP::logp_score (cxx/hirm.hh:123-132); the index is drawn with the shared inversion rule from the injected
+ * uniform.  out_grid / out_lp (nullable) receive the grid and its log-probabilities.  Returns the new alpha
+ * (which it also sets), or the unchanged alpha if the domain is empty (:163). */
+double hirm_oracle_transition_alpha(hirm_oracle *o, int dom, int ngrid, double u, double *out_grid, double *out_lp) {
+    int N = 0;
+    for (int k = 0; k < o->n_tab[dom]; k++) N += o->tab_count[dom][k];
+    if (N == 0 || ngrid < 2 || ngrid > 64) return o->alpha[dom];
+    double t2 = 0;
+    for (int k = 0; k < o->n_tab[dom]; k++) t2 += lgamma((double)o->tab_count[dom][k]);
+    double grid[64], lp[64];
+    const double lo = log(1.0 / N), hi = log((double)N + 1.0);
+    const double step = (hi - lo) / (ngrid - 1);           /* linspace(start, stop, num, endpoint = true) */
+    for (int g = 0; g < ngrid; g++) {
+        grid[g] = exp(lo + step * g);
+        lp[g] = o->n_tab[dom] * log(grid[g]) + t2 + lgamma(grid[g]) - lgamma(N + grid[g]);
+        if (out_grid) out_grid[g] = grid[g];
+        if (out_lp) out_lp[g] = lp[g];
+    }
+    o->alpha[dom] = grid[hirm_oracle_choose(lp, ngrid, u)];
+    return o->alpha[dom];
+}

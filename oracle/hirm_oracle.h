@@ -38,6 +38,8 @@ int hirm_oracle_sweep(hirm_oracle *o, int64_t n_moves, const int32_t *move_dom, 
 /* non-empty cells, lexicographically sorted, (arity + 2) int32 per cell: labels..., N, s */
 int64_t hirm_oracle_get_counts(hirm_oracle *o, int rel, int32_t *out, int64_t cap_cells);
 double hirm_oracle_logp_score(hirm_oracle *o);
+/* CRP::transition_alpha with an injected uniform; returns (and sets) the new alpha */
+double hirm_oracle_transition_alpha(hirm_oracle *o, int dom, int ngrid, double u, double *out_grid, double *out_lp);
 void hirm_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double hirm_oracle_uniform(uint64_t seed, uint64_t stream, uint64_t counter);
 #endif

@@ -48,6 +48,9 @@ def lib():
         L.hirm_oracle_get_counts.argtypes = [P, ctypes.c_int, i32p, ctypes.c_int64]
         L.hirm_oracle_logp_score.restype = ctypes.c_double
         L.hirm_oracle_logp_score.argtypes = [P]
+        L.hirm_oracle_transition_alpha.restype = ctypes.c_double
+        L.hirm_oracle_transition_alpha.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                   ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.hirm_oracle_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32)] * 3
         L.hirm_oracle_uniform.restype = ctypes.c_double
         L.hirm_oracle_uniform.argtypes = [ctypes.c_uint64] * 3
@@ -140,6 +143,13 @@ class Oracle:
 
     def logp_score(self):
         return self.L.hirm_oracle_logp_score(self.h)
+
+    def transition_alpha(self, dom, u, ngrid=20):
+        """Returns (alpha, grid, grid log-probabilities)."""
+        grid = np.zeros(ngrid, np.float64); lp = np.zeros(ngrid, np.float64)
+        dp = ctypes.POINTER(ctypes.c_double)
+        a = self.L.hirm_oracle_transition_alpha(self.h, dom, ngrid, float(u), grid.ctypes.data_as(dp), lp.ctypes.data_as(dp))
+        return a, grid, lp
 
 
 def philox4x32_10(ctr, key):

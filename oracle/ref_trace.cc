@@ -227,9 +227,24 @@ static void traced_sweeps(IRM &irm, int sweeps, bool shuffle, bool alpha_moves, 
         dump_state(irm, dnames, rnames);
         printf("}");
         if (alpha_moves) {
-            // the reference's own alpha grid-Gibbs (cxx/hirm.hh:162), so that later
-            // sweeps exercise log(alpha) != 0 for the fresh-table candidate
-            for (const auto &d : dnames) irm.domains.at(d)->crp.transition_alpha();
+            // the reference's alpha grid-Gibbs (cxx/hirm.hh:162-173) with its own grid (log_linspace,
+            // cxx/util_math.cc:26) and its own CRP::logp_score (:123) per grid point; the index is drawn with
+            // the engine's inversion rule from a traced uniform, so that later sweeps
+            // exercise log(alpha) != 0 for the fresh-table candidate
+            for (const auto &d : dnames) {
+                CRP &crp = irm.domains.at(d)->crp;
+                if (crp.N == 0) continue;
+                auto grid = log_linspace(1. / crp.N, crp.N + 1, 20, true);
+                vector<double> lps;
+                for (const auto &g : grid) { crp.alpha = g; lps.push_back(crp.logp_score()); }
+                double u = std::generate_canonical<double, 53>(urng);
+                int idx = choose(lps, u);
+                crp.alpha = grid[idx];
+                printf(",\n{\"amove\":\"%s\",\"N\":%d,\"ngrid\":20,\"grid\":", d.c_str(), crp.N);
+                jdoubles(grid);
+                printf(",\"lp\":"); jdoubles(lps);
+                printf(",\"u\":%.17g,\"idx\":%d,\"alpha\":%.17g}", u, idx, crp.alpha);
+            }
         }
     }
     printf("\n]");

@@ -57,10 +57,19 @@ def check_state(backend, spec, state):
 def replay(backend, spec, check_candidates=True):
     """Drive `backend` through the reference's trace; returns summary counters."""
     check_state(backend, spec, spec.raw["init"])
-    n_moves = n_changed = n_repeated = 0
+    n_moves = n_changed = n_repeated = n_alpha = 0
     for mv in spec.moves:
         if "ckpt" in mv:
             check_state(backend, spec, mv["state"])
+            continue
+        if "amove" in mv:
+            # CRP::transition_alpha: the reference's grid (log_linspace) and per-point CRP::logp_score, same
+            # uniform => same grid point
+            d = spec.dindex[mv["amove"]]
+            alpha, lp = backend.transition_alpha(d, mv["u"], mv["ngrid"])
+            assert close(lp, mv["lp"]), (mv, lp)
+            assert abs(alpha - mv["alpha"]) <= 1e-12 * mv["alpha"], (mv, alpha)
+            n_alpha += 1
             continue
         d = spec.dindex[mv["d"]]
         backend.set_alpha(d, mv["alpha"])
@@ -81,4 +90,4 @@ def replay(backend, spec, check_candidates=True):
         assert choice == mv["choice"], (mv, choice)
         n_moves += 1
         n_changed += int(choice != mv["cur"])
-    return dict(moves=n_moves, changed=n_changed, repeated=n_repeated)
+    return dict(moves=n_moves, changed=n_changed, repeated=n_repeated, alpha_moves=n_alpha)

@@ -163,3 +163,71 @@ def test_max_tables_exhausted_is_reported(eng):
         eng.sweep([h], [(np.zeros(3, np.int32), np.arange(3, dtype=np.int32))], seed=1, streams=[0], counters=[0])
     assert "max_tables" in str(ei.value)
     eng.irm_destroy(h)
+
+
+def test_sweep_all_device_generated_order_and_batched_alpha_and_scores(eng):
+    """hirm_engine_sweep_all (order generated on the device), hirm_engine_transition_alpha (Philox) and
+    hirm_engine_logp_scores over several chains: the oracle, fed the generated order and the same Philox
+    positions, ends in the same state; every sweep visits every entity exactly once."""
+    n, chains, sweeps = 120, 3, 2
+    x = U.planted_ree(n, seed=31, missing=0.05)
+    ids, val = U.dense_to_coo(x)
+    rng = np.random.default_rng(32)
+    hs, os_ = [], []
+    for c in range(chains):
+        h = eng.irm_create([n], [[0, 0]], max_tables=32)
+        if c == 0:
+            eng.set_observations_dense_host(h, 0, x)
+            eng.finalize(h)
+        else:
+            eng.share_observations(h, hs[0])
+        z = rng.integers(0, 3 + c, n).astype(np.int32)
+        eng.set_assignments(h, 0, z)
+        eng.set_rng(h, 100 + c, 17 * c)
+        o = O.Oracle([n], [[0, 0]])
+        o.set_observations(0, ids, val)
+        o.set_assignments(0, z)
+        hs.append(h); os_.append(o)
+    for rnd in range(2):
+        nm, dom, item, choice = eng.sweep_all(hs, n_sweeps=sweeps, seed=55, want_moves=True)
+        assert nm == chains * sweeps * n
+        for c in range(chains):
+            sl = slice(c * sweeps * n, (c + 1) * sweeps * n)
+            for s in range(sweeps):
+                assert sorted(item[sl][s * n:(s + 1) * n]) == list(range(n))        # a permutation per sweep
+            os_[c].sweep(dom[sl], item[sl], seed=55, stream=100 + c, offset=17 * c + rnd * sweeps * n)
+            np.testing.assert_array_equal(eng.get_assignments(hs[c], 0), os_[c].get_assignments(0))
+            np.testing.assert_array_equal(eng.get_counts(hs[c], 0), os_[c].get_counts(0))
+        # alpha moves: Philox(seed ^ "alpha", stream, counter * MAX_DOMAINS + d)
+        alphas = eng.transition_alpha(hs, ngrid=20, seed=55)
+        for c in range(chains):
+            u = O.uniform(55 ^ 0x616c706861, 100 + c, rnd * E.MAX_DOMAINS + 0)
+            a, _, _ = os_[c].transition_alpha(0, u, 20)
+            assert abs(alphas[c, 0] - a) <= 1e-12 * a
+            assert eng.get_alpha(hs[c], 0) == alphas[c, 0]
+        sc = eng.logp_scores(hs)
+        for c in range(chains):
+            assert G.close(sc[c], os_[c].logp_score())
+            lab, cnt = eng.get_tables(hs[c], 0)
+            zz = os_[c].get_assignments(0)
+            np.testing.assert_array_equal(lab, np.unique(zz))
+            np.testing.assert_array_equal(cnt, [int((zz == t).sum()) for t in lab])
+    for h in hs:
+        eng.irm_destroy(h)
+
+
+def test_sweep_all_generic_kernel_multi_domain(eng):
+    """sweep_all on a mixed-arity CSR IRM (generic kernel): per sweep every domain in index order, every entity once."""
+    spec = G.IrmSpec(G.load("synth_mixed_irm")["irms"][0])
+    h = U.engine_from_spec(eng, spec)
+    o = U.oracle_from_spec(spec)
+    eng.set_rng(h, 9, 0)
+    nm, dom, item, choice = eng.sweep_all([h], n_sweeps=2, seed=4, want_moves=True)
+    per = sum(spec.n_entities)
+    assert nm == 2 * per and list(dom[:per]) == sorted(dom[:per])
+    o.sweep(dom, item, seed=4, stream=9, offset=0)
+    for d in range(len(spec.dnames)):
+        np.testing.assert_array_equal(eng.get_assignments(h, d), o.get_assignments(d))
+    for r in range(len(spec.rnames)):
+        np.testing.assert_array_equal(eng.get_counts(h, r), o.get_counts(r))
+    eng.irm_destroy(h)

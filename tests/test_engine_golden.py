@@ -24,7 +24,7 @@ def test_engine_replays_reference_trace(eng, case):
     reference (brute force for repeated domains), same uniform => same table, and bit-exact
     assignments / count tables at every checkpoint."""
     fx = G.load(case)
-    total = dict(moves=0, changed=0, repeated=0)
+    total = dict(moves=0, changed=0, repeated=0, alpha_moves=0)
     for irm in fx["irms"]:
         spec = G.IrmSpec(irm)
         h = U.engine_from_spec(eng, spec)

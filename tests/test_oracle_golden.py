@@ -7,8 +7,14 @@ import golden_util as G
 from oracle import hirm_oracle as O
 
 
+class OracleBackend(O.Oracle):
+    def transition_alpha(self, dom, u, ngrid):
+        a, grid, lp = O.Oracle.transition_alpha(self, dom, u, ngrid)
+        return a, lp
+
+
 def make_oracle(spec):
-    o = O.Oracle(spec.n_entities, spec.rel_domains)
+    o = OracleBackend(spec.n_entities, spec.rel_domains)
     for r in range(len(spec.rnames)):
         o.set_observations(r, spec.obs_ids[r], spec.obs_val[r])
     for d in range(len(spec.dnames)):
@@ -20,13 +26,15 @@ def make_oracle(spec):
 @pytest.mark.parametrize("case", G.CASES)
 def test_oracle_replays_reference_trace(case):
     fx = G.load(case)
-    total = dict(moves=0, changed=0, repeated=0)
+    total = dict(moves=0, changed=0, repeated=0, alpha_moves=0)
     for irm in fx["irms"]:
         spec = G.IrmSpec(irm)
         res = G.replay(make_oracle(spec), spec)
         for k in total:
             total[k] += res[k]
     assert total["moves"] > 0 and total["changed"] > 0
+    if fx["mode"] == "irm":
+        assert total["alpha_moves"] > 0  # CRP::transition_alpha is pinned against the reference's grid and scores
     if case in ("nations_binary_irm", "synth_ree40_irm", "synth_mixed_irm"):
         assert total["repeated"] > 0     # the Q1 (repeated-domain) path is exercised
 
