@@ -5,7 +5,8 @@ Workload (config.workload): BASELINE.json config 3 -- one dense `bernoulli R e e
 n = 20000 entities (4e8 observed cells), planted two-block structure (SURVEY.md 8d generator,
 numpy default_rng(0)), `chains` independent seeded Gibbs chains per GPU sharing the
 read-only observation slabs (800 MB in HBM, > L2), each chain making `moves_per_step`
-sequential entity moves per step.  One step = one launch of the persistent sweep kernel.
+sequential entity moves per step (default: one full sweep).  One step = one launch of the persistent
+sweep kernel per shared-memory tier.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]           # this engine
     python bench.py --impl reference ...                          # the reference's CPU code
@@ -39,8 +40,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=20000)
-    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = one per SM)")
-    ap.add_argument("--moves-per-step", type=int, default=1000, help="moves per chain per step")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = four per SM)")
+    ap.add_argument("--moves-per-step", type=int, default=0, help="moves per chain per step (0 = n: one full sweep)")
     ap.add_argument("--max-tables", type=int, default=64)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--ref-n", type=int, default=1000, help="entities of the reference arm's bounded sample")
@@ -210,8 +211,9 @@ def main_b200(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     props = torch.cuda.get_device_properties(dev)
-    n, M = args.n, args.moves_per_step
-    chains = args.chains or props.multi_processor_count
+    n = args.n
+    M = args.moves_per_step or n                  # one step = one full sweep of every chain
+    chains = args.chains or 4 * props.multi_processor_count
     pitch = (n + 15) // 16 * 16
 
     # ---- ingest: observations from pinned host memory (timed once, reported in config) -------
@@ -233,24 +235,24 @@ def main_b200(args, rank, world, local_rank):
     rng = np.random.default_rng(1000 + args.seed + rank)
     t0 = time.perf_counter()
     for c, h in enumerate(hs):
-        eng.set_assignments(h, 0, crp_prior_labels_fast(n, 1.0, rng))
-    k0 = len(eng.get_counts(hs[0], 0))           # forces the count-table build of chain 0
+        eng.set_assignments(h, 0, crp_prior_labels_fast(n, 1.0, rng))     # Domain::incorporate: sequential CRP(1) prior draw
+        eng.set_rng(h, rank * chains + c, 0)
+    k0 = [len(np.unique(eng.get_assignments(h, 0))) for h in hs[:8]]
+    eng.logp_scores(hs)                           # forces every chain's count-table build
     build_s = time.perf_counter() - t0
 
-    # ---- move lists: every chain walks its own random permutation, M moves per step ------------
-    total_steps = 2 * (args.warmup + args.steps) + 2
-    perms = [rng.permutation(n).astype(np.int32) for _ in hs]
-
-    def step_moves(s):
-        idx = (np.arange(M) + s * M) % n
-        return [p[idx] for p in perms]
-
+    # ---- move lists resident in HBM: every chain walks its own fresh random permutation per sweep ----------
+    nsteps = args.warmup + args.steps
+    gen = torch.Generator(device=dev); gen.manual_seed(7 + args.seed + rank)
+    d_items = []
+    for s in range(nsteps):
+        perm = torch.argsort(torch.rand(chains, n, device=dev, generator=gen), dim=1).to(torch.int32)
+        d_items.append(perm[:, :M].contiguous().view(-1))
     irm_ids = np.asarray(hs, dtype=np.int32)
     d_off = torch.arange(chains + 1, dtype=torch.int64, device=dev) * M
     d_dom = torch.zeros(chains * M, dtype=torch.int32, device=dev)
     d_stream = (torch.arange(chains, dtype=torch.int64, device=dev) + rank * chains)
-    d_items = [torch.from_numpy(np.concatenate(step_moves(s))).to(dev) for s in range(args.warmup + args.steps)]
-    d_ctr = [torch.full((chains,), s * M, dtype=torch.int64, device=dev) for s in range(args.warmup + args.steps)]
+    d_ctr = [torch.full((chains,), s * M, dtype=torch.int64, device=dev) for s in range(nsteps)]
     torch.cuda.synchronize()
 
     def device_step(s):
@@ -262,15 +264,20 @@ def main_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- HBM-resident timing: W warm-up launches, then exactly K launches between CUDA events ----
+    # ---- HBM-resident timing: W warm-up sweeps (the first one is the burn-in from the CRP prior), then exactly
+    #      K sweeps between CUDA events ----
+    burn_ms = None
     for s in range(args.warmup):
         device_step(s)
+        if s == 0:
+            burn_ms = eng.last_sweep_info()["kernel_ms"]
     barrier()
-    sampler = ClockSampler(getattr(props, "uuid", None) and "GPU-" + str(props.uuid) or local_rank)
+    launches_per_step = eng.last_sweep_info()["launches"] if args.warmup else 1
+    sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
     ev0.record()
-    for s in range(args.warmup, args.warmup + args.steps):
+    for s in range(args.warmup, nsteps):
         device_step(s)
     ev1.record()
     torch.cuda.synchronize()
@@ -281,11 +288,12 @@ def main_b200(args, rank, world, local_rank):
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    kind = eng.last_sweep_info()["kernel_kind"]
+    info = eng.last_sweep_info()
+    plan = eng.last_dense_plan()
     moves_per_gpu_step = chains * M
     value = world * moves_per_gpu_step * args.steps / (elapsed_ms * 1e-3)
 
-    # roofline of the dominant (only) kernel: algorithmic bytes = 2 rows of n bytes per move
+    # roofline of the dominant kernel: algorithmic bytes = 2 rows of n bytes per move
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
@@ -297,6 +305,8 @@ def main_b200(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel": "dense_ree_sweep_kernel",
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
+                "launch_timing": "CUDA events around the K timed steps on the engine's stream; one step = the sweep kernel's "
+                                 "tier launches (the second tier exits at once when no chain overflowed)",
                 "frac_of_nominal_8000": achieved / 8000.0}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -307,40 +317,44 @@ def main_b200(args, rank, world, local_rank):
         except Exception:
             pass
 
-    # ---- end to end through the C ABI with HOST buffers --------------------------------------
-    # per step: host move lists -> device (inside hirm_engine_sweep), sweep, every chain's
-    # assignments + every move's chosen table back to the host.
-    base = args.warmup + args.steps
-    host_moves = [[(np.zeros(M, np.int32), mv) for mv in step_moves(base + s)] for s in range(args.steps + 1)]
-    streams = np.arange(chains, dtype=np.uint64) + rank * chains
-
+    # ---- end to end through the public C ABI, as the reference's loop makes it (cxx/hirm.cc:39-59) -------------
+    # per step: transition_cluster_assignments_all of every chain (hirm_engine_sweep_all: HOST irm ids in, sweep
+    # order generated on the device), CRP::transition_alpha of every chain (alphas back to the host), and
+    # IRM::logp_score of every chain (scores back to the host) -- the per-iteration work and read-backs of
+    # inference_irm with --verbose.  Observations were ingested once (IRM.incorporate precedes the loop).
     def host_step(s):
-        r = eng.sweep(hs, host_moves[s], seed=args.seed, streams=streams,
-                      counters=np.full(chains, (base + s) * M, dtype=np.uint64))
-        zs = [eng.get_assignments(h, 0) for h in hs]
-        return r, zs
+        eng.sweep_all(hs, n_sweeps=1, seed=args.seed + 1)
+        al = eng.transition_alpha(hs, ngrid=20, seed=args.seed + 1)
+        return al, eng.logp_scores(hs)
 
     host_step(0)
     barrier()
     t0 = time.perf_counter()
-    for s in range(1, args.steps + 1):
-        host_step(s)
+    for s in range(args.steps):
+        al, sc = host_step(s)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": world * moves_per_gpu_step * args.steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(moves_per_gpu_step * 8 + chains * 24 + (chains + 1) * 8),
-           "d2h_bytes_per_step": int(moves_per_gpu_step * 4 + chains * (n * 4 + args.max_tables * 4)),
+    e2e = {"value": world * chains * n * args.steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(3 * chains * 4 + (chains + 1) * 8 + 3 * 3 * chains * 8),
+           "d2h_bytes_per_step": int(chains * 8 * 8 + chains * 8 + 2 * chains * 4),
            "ms_per_step": 1e3 * e2e_s / args.steps,
-           "note": "observations ingested once before (as IRM.incorporate precedes transition_cluster_assignments); "
-                   "ingest of the 400 MB host matrix (H2D + device transpose) took %.3f s" % ingest_s}
+           "note": "public API with host buffers: hirm_engine_sweep_all + hirm_engine_transition_alpha + hirm_engine_logp_scores "
+                   "per step (irm ids / Philox positions in; alphas, scores and kernel error words out); the 400 MB observation "
+                   "matrix was ingested once before the loop (H2D + device transpose: %.3f s)" % ingest_s}
 
-    # number of tables now alive (explains the fp64 work per move)
+    # the same step through the explicit-move-list entry point (host move lists in, every chosen table out)
+    host_moves = [(np.zeros(M, np.int32), np.ascontiguousarray(rng.permutation(n).astype(np.int32)[:M])) for _ in hs]
+    streams = np.arange(chains, dtype=np.uint64) + rank * chains
+    eng.sweep(hs, host_moves, seed=args.seed + 2, streams=streams, counters=np.zeros(chains, np.uint64))
+    t0 = time.perf_counter()
+    eng.sweep(hs, host_moves, seed=args.seed + 2, streams=streams, counters=np.full(chains, M, np.uint64))
+    lists_s = time.perf_counter() - t0
+
     ktabs = [len(np.unique(eng.get_assignments(h, 0))) for h in hs[:8]]
-
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline, _ = run_reference(args.ref_n, 1, 1, per_round_s=8.0)
@@ -350,14 +364,18 @@ def main_b200(args, rank, world, local_rank):
                 "warmup": args.warmup, "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(n), "n_entities": n, "chains_per_gpu": chains,
+                           "step": "one full Gibbs sweep (%d entity moves) of each of the %d independent chains per GPU" % (M, chains),
                            "moves_per_chain_per_step": M, "max_tables": args.max_tables,
-                           "tables_alive_first_chains": ktabs, "tables_at_start": int(k0),
-                           "l2": "inputs (2 x %d MB slabs) larger than L2; every chain streams different rows" % (n * pitch // 1000000),
-                           "parallelism": "%d independent chains per GPU, replicas across GPUs (no collective)" % chains,
+                           "init": "sequential CRP(alpha=1) prior draw per chain; warm-up sweeps are the burn-in",
+                           "tables_at_start_first_chains": k0, "tables_alive_first_chains": ktabs,
+                           "burn_in_first_sweep_moves_per_s": (moves_per_gpu_step / (burn_ms * 1e-3)) if burn_ms else None,
+                           "l2": "inputs (2 x %d MB slabs) larger than L2; every chain streams its own random permutation of rows" % (n * pitch // 1000000),
+                           "parallelism": "%d independent chains per GPU (%d per SM), replicas across GPUs (no collective)" % (chains, plan["ctas_per_sm"]),
                            "sweeps_per_s": value / n, "ingest_s": ingest_s, "state_build_s": build_s,
-                           "kernel_kind": kind},
+                           "kernel_kind": info["kernel_kind"], "dense_plan": plan,
+                           "explicit_move_lists_moves_per_s": moves_per_gpu_step / lists_s},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-                "gpu_launches": args.steps, "clocks": clocks}
+                "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

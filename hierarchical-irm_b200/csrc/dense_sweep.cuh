@@ -46,6 +46,15 @@ constexpr int DN_MAX_KD = 8;                      // dp4a path: live tables in s
 constexpr int DN_LF = 256;                        // shared-memory copy of lgamma(m+1), m < 256; Stirling (error < 1e-19) beyond
 constexpr int DN_FLUSH_VECS = 15;                 // 15 * 16 = 240 elements per thread between bin flushes (8-bit fields)
 
+// What the producer hands the decision warps for one move (through shared memory, ahead of the move's rows):
+// nothing in the decision loop ever waits on a global load.
+struct MoveCtl {
+    int32_t item;
+    uint32_t bytes;     // byte 0: observation (i, i); byte 1: (i, i_prev); byte 2: (i_prev, i); bit 24: bad move
+    double u;           // the move's uniform
+};
+constexpr int DN_CTL = 32;                        // ring of control records (the producer is at most stages + 2 moves ahead)
+
 struct DenseLaunch {
     int32_t n;          // entities
     int32_t npad;       // n rounded up to 16
@@ -69,10 +78,10 @@ __host__ __device__ inline DenseLaunch dense_layout(int n, int kt, int chunk, in
     int off = 8 * (2 * DN_MAX_STAGES + 4);          // mbarriers: full[S], empty[S], ready[2], go
     L.off_lf = off;    off += DN_LF * 8;
     L.off_table = off; off += kt * kt * 8;
-    L.off_dbl = off;   off += 4 * (kt + 2) * 8;     // s_lp, s_tmp, s_logcnt, s_logcntm1
+    L.off_dbl = off;   off += 5 * (kt + 2) * 8;     // s_lp[2], s_tmp, s_logcnt, s_logcntm1
     L.off_wpart = off; off += 2 * DN_A_WARPS * 4 * kt * 4;
     L.off_bins = off;  off += bins_words * 4;
-    L.off_ints = off;  off += (2 * 4 * kt + 4 * kt + 8) * 4;   // g[2][4kt], s_cnt, s_lab, s_order, s_map
+    L.off_ints = off;  off += (2 * DN_D_WARPS * 4 * kt + 4 * kt + 8) * 4;   // g[2][D warps][4kt], s_cnt, s_lab, s_order, s_map
     off = (off + 15) & ~15;
     L.off_zs = off;    off += L.npad;
     off = (off + 127) & ~127;
@@ -209,19 +218,24 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
             "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
+// try_wait with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the time is up
+__device__ __forceinline__ bool mbar_try_wait_hint_s(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return done != 0;
+}
 // same, for waits with slack (the A warps' go, the producer's empty): sleep between polls so that the
 // spinning does not take issue slots from the decision warps
 __device__ __forceinline__ void mbar_wait_relaxed_s(uint32_t bar, uint32_t parity) {
     uint32_t done;
     for (;;) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        done = mbar_try_wait_hint_s(bar, parity, 20000u) ? 1u : 0u;
         if (done) break;
-        __nanosleep(64);
     }
 }
 __device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
@@ -381,19 +395,19 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
     uint64_t *bar_go = bar_ready + 2;                                            // [1]  D -> A: z is stable for move r
     double *s_lf = reinterpret_cast<double *>(smem + L.off_lf);                  // [DN_LF] lgamma(m+1)
     cell_t *table = reinterpret_cast<cell_t *>(smem + L.off_table);              // [kt*kt]  Relation::clusters, cell (a, b) at a + b*kt
-    double *s_lp = reinterpret_cast<double *>(smem + L.off_dbl);                 // [kt+2]
-    double *s_tmp = s_lp + (kt + 2);
+    double *s_lp2 = reinterpret_cast<double *>(smem + L.off_dbl);                // [2][kt+2] candidate log-probabilities, by move parity
+    double *s_tmp = s_lp2 + 2 * (kt + 2);
     double *s_logcnt = s_tmp + (kt + 2);                                         // log(count) per slot
     double *s_logcntm1 = s_logcnt + (kt + 2);                                    // log(count - 1) per slot
     int32_t *wpart = reinterpret_cast<int32_t *>(smem + L.off_wpart);            // [2][A_WARPS][4*kt] per-warp group sums
     uint32_t *bins = reinterpret_cast<uint32_t *>(smem + L.off_bins);            // [bins_words]
-    int32_t *g_buf = reinterpret_cast<int32_t *>(smem + L.off_ints);             // [2][4*kt]: (rn, rs, cn, cs) per other-slot
-    int32_t *s_cnt = g_buf + 8 * kt, *s_lab = s_cnt + kt;                        // CRP table sizes / labels per slot
+    int32_t *g_buf = reinterpret_cast<int32_t *>(smem + L.off_ints);             // [2][D warps][4*kt]: (rn, rs, cn, cs) per other-slot, one copy per D warp
+    int32_t *s_cnt = g_buf + 2 * DN_D_WARPS * 4 * kt, *s_lab = s_cnt + kt;                        // CRP table sizes / labels per slot
     int32_t *s_order = s_lab + kt, *s_map = s_order + kt;                        // slots by ascending label; load-time slot map
     uint8_t *zs = smem + L.off_zs;                                               // [npad] slot of every entity
     uint8_t *ring = smem + L.off_ring;                                           // [NS][2][chunk]
-    __shared__ int32_t s_K, s_KA, s_choice_slot, s_choice_label;
-    __shared__ double s_u;
+    __shared__ int32_t s_K, s_KA, s_choice_idx;
+    __shared__ MoveCtl s_ctl[DN_CTL];
     __shared__ int32_t s_has_absent;
     __shared__ long long s_limit, s_issued, s_consumed, s_done;
     __shared__ long long s_ph[14];                        // profiling only   // first move NOT to be made (tier overflow); ring chunks issued / consumed
@@ -466,16 +480,44 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
         // =============================== P: TMA producer ===================================
         if (lane == 0) {
             RingCursor cur{0, 0u};
-            int item_next = args.move_item[m0 + r_begin];
             int64_t issued = 0;                               // chunks issued so far
             const bool prof = args.phase_cycles != nullptr;
             long long p_wait = 0, p_t0 = prof ? clk() : 0;
             const volatile long long *limit = &s_limit;
+            const bool has_absent = s_has_absent != 0;
+            const uint64_t u_stream = args.uniforms ? 0 : args.stream[k_list], u_ctr0 = args.uniforms ? 0 : args.counter0[k_list];
+            // software pipeline over the moves: ids two ahead, observation bytes and the injected uniform one ahead
+            int it_cur = args.move_item[m0 + r_begin], dm_cur = args.move_dom[m0 + r_begin];
+            int it_nxt = r_begin + 1 < nmoves ? args.move_item[m0 + r_begin + 1] : -1, dm_nxt = r_begin + 1 < nmoves ? args.move_dom[m0 + r_begin + 1] : 0;
+            bool bad_cur = it_cur < 0 || it_cur >= n || dm_cur != 0;
+            if (has_absent && !bad_cur) bad_cur = z_g[it_cur] < 0;
+            uint32_t b_d = bad_cur ? 0xFFu : slab0[(int64_t)it_cur * pitch0 + it_cur], b_rp = 0xFFu, b_cp = 0xFFu;
+            double u_cur = args.uniforms ? args.uniforms[m0 + r_begin] : 0.0;
             bool stop = false;
             #pragma unroll 1
             for (int64_t r = r_begin; r < nmoves && !stop; r++) {
-                const int it = item_next;
-                if (r + 1 < nmoves) item_next = args.move_item[m0 + r + 1];
+                const int it = it_cur;
+                // ---- this move's control record
+                MoveCtl ctl;
+                ctl.item = it; ctl.bytes = (b_d & 0xFFu) | ((b_rp & 0xFFu) << 8) | ((b_cp & 0xFFu) << 16) | (bad_cur ? 1u << 24 : 0u);
+                ctl.u = args.uniforms ? u_cur : philox_uniform(args.seed, u_stream, u_ctr0 + (uint64_t)r);
+                s_ctl[r % DN_CTL] = ctl;
+                // ---- loads for the next moves (consumed one iteration later)
+                const bool bad_prev = bad_cur;
+                it_cur = it_nxt; dm_cur = dm_nxt;
+                if (r + 2 < nmoves) { it_nxt = args.move_item[m0 + r + 2]; dm_nxt = args.move_dom[m0 + r + 2]; }
+                b_d = 0xFFu; b_rp = 0xFFu; b_cp = 0xFFu;
+                bad_cur = true;
+                if (r + 1 < nmoves) {
+                    bad_cur = it_cur < 0 || it_cur >= n || dm_cur != 0;
+                    if (has_absent && !bad_cur) bad_cur = z_g[it_cur] < 0;
+                    if (!bad_cur) {
+                        const int64_t i2 = it_cur;
+                        b_d = slab0[i2 * pitch0 + i2];
+                        if (!bad_prev) { b_rp = slab0[i2 * pitch0 + it]; b_cp = slab1[i2 * pitch1 + it]; }
+                    }
+                    if (args.uniforms) u_cur = args.uniforms[m0 + r + 1];
+                }
                 const int64_t row = (it >= 0 && it < n) ? it : 0;
                 const uint8_t *src0 = slab0 + row * pitch0, *src1 = slab1 + row * pitch1;
                 #pragma unroll 1
@@ -486,9 +528,8 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
                     if (issued >= NS) {                       // the slot has been used before: wait until the A warps released it
                         const long long w0 = prof ? clk() : 0;
                         const uint32_t eb = smem_u32(&bar_empty[cur.stage]);
-                        while (!mbar_try_wait_s(eb, cur.parity ^ 1u)) {
+                        while (!mbar_try_wait_hint_s(eb, cur.parity ^ 1u, 20000u)) {
                             if (r >= *limit) { stop = true; break; }
-                            __nanosleep(128);
                         }
                         if (stop) break;
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -552,17 +593,7 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
         int K = K0;                                            // live slots 0..K-1 (uniform across D threads)
         int KA_prev = K0;                                      // K the A warps used for the move being decided
         bool pend_changed = false; int pend_item = -1, pend_old = 0, pend_new = 0, pend_dead = -1;
-        const bool has_absent = s_has_absent != 0;
-        const bool full = full_obs && !has_absent;
-        // move ids are fetched TWO moves ahead and the observation bytes the fix-ups need -- (i, i), (i, i_prev),
-        // (i_prev, i), straight from the slabs -- ONE move ahead, so that no load is ever waited for
-        int item_n1 = args.move_item[m0 + r_begin], dom_n1 = args.move_dom[m0 + r_begin];
-        int item_n2 = r_begin + 1 < nmoves ? args.move_item[m0 + r_begin + 1] : -1, dom_n2 = r_begin + 1 < nmoves ? args.move_dom[m0 + r_begin + 1] : 0;
-        uint32_t xb_d_next = 0xFFu, xb_rp_next = 0xFFu, xb_cp_next = 0xFFu;
-        if (item_n1 >= 0 && item_n1 < n) xb_d_next = slab0[(int64_t)item_n1 * pitch0 + item_n1];
-        const bool own_u = d == DN_ND - 1;                     // this thread provides the moves' uniforms
-        const uint64_t u_stream = own_u && !args.uniforms ? args.stream[k_list] : 0, u_ctr0 = own_u && !args.uniforms ? args.counter0[k_list] : 0;
-        double u_next = own_u && args.uniforms ? args.uniforms[m0 + r_begin] : 0.0;
+        const bool full = full_obs && s_has_absent == 0;
         if (d == 0) mbar_arrive(bar_go);                       // move 0 may be accumulated
         const bool prof = args.phase_cycles != nullptr && d == 0;
         long long tl = prof ? clk() : 0;
@@ -573,36 +604,28 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
         for (int64_t r = r_begin; r < nmoves; r++) {
             const int64_t m = m0 + r;
             const int64_t rr = r - r_begin;                    // barrier phases count from this launch's first move
-            const int item = item_n1, item_next = item_n2;
-            bool bad = item < 0 || item >= n || dom_n1 != 0;
-            if (has_absent && !bad) bad = z_g[item] < 0;
-            const uint32_t xb_ri = xb_d_next, xb_rp = xb_rp_next, xb_cp = xb_cp_next;
-            item_n1 = item_n2; dom_n1 = dom_n2;
-            if (r + 2 < nmoves) { item_n2 = args.move_item[m + 2]; dom_n2 = args.move_dom[m + 2]; }
-            xb_d_next = 0xFFu; xb_rp_next = 0xFFu; xb_cp_next = 0xFFu;
-            if (r + 1 < nmoves && item_next >= 0 && item_next < n) {
-                const int64_t i2 = item_next;
-                xb_d_next = slab0[i2 * pitch0 + i2];
-                if (!bad) { xb_rp_next = slab0[i2 * pitch0 + item]; xb_cp_next = slab1[i2 * pitch1 + item]; }
-            }
-            if (own_u) {                                       // this move's uniform, before the wait
-                s_u = args.uniforms ? u_next : philox_uniform(args.seed, u_stream, u_ctr0 + (uint64_t)r);
-                if (args.uniforms && r + 1 < nmoves) u_next = args.uniforms[m + 1];
-            }
             const int buf = (int)(rr & 1);
-            int32_t *g = g_buf + buf * 4 * kt;
+            int32_t *g = g_buf + (buf * DN_D_WARPS + dwarp) * 4 * kt;     // this warp's copy of the group sums
+            double *s_lp = s_lp2 + buf * (kt + 2);
             DPHASE(5);
             mbar_wait(&bar_ready[buf], (uint32_t)((rr >> 1) & 1));
             DPHASE(0);
+            const MoveCtl ctl = s_ctl[r % DN_CTL];              // written by the producer before it issued this move's rows
+            const int item = ctl.item;
+            const bool bad = (ctl.bytes >> 24) & 1u;
+            const uint32_t xb_ri = ctl.bytes & 0xFFu, xb_rp = (ctl.bytes >> 8) & 0xFFu, xb_cp = (ctl.bytes >> 16) & 0xFFu;
             // ---- finish move r-1: z[i_{r-1}] becomes visible, its observation pair changes group ----
-            if (pend_changed && d == 0) zs[pend_item] = (uint8_t)pend_new;
+            if (d == 0) {
+                if (pend_changed) zs[pend_item] = (uint8_t)pend_new;
+                if (pend_dead < 0) { s_KA = K; mbar_arrive(bar_go); }   // z is final: the A warps may accumulate move r+1
+            }
             int c = bad ? 0 : ((pend_changed && item == pend_item) ? pend_new : (int)zs[item]);
             const int d_n = bad ? 0 : byte_n(xb_ri), d_s = bad ? 0 : byte_s(xb_ri);   // the diagonal (i, i): ONE observation
             {
                 const int KG = min(K + 1, kt);                 // slot K: the fresh table (empty groups)
                 const int32_t *wp0 = wpart + buf * DN_A_WARPS * 4 * kt;
                 #pragma unroll 1
-                for (int idx = d; idx < 4 * KG; idx += DN_ND) {
+                for (int idx = lane; idx < 4 * KG; idx += 32) {      // every D warp computes all of them: no barrier
                     const int k = idx >> 2, f = idx & 3;
                     int v = 0;
                     if (full && !(f & 1)) {                     // no missing cell: the observation counts are the table sizes
@@ -623,8 +646,9 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
                     g[idx] = v;
                 }
             }
-            bar_d();
+            __syncwarp();
             if (pend_dead >= 0) {
+                bar_d();
                 // ---- the table that died in move r-1 is replaced by the last slot ------------------
                 const int dead = pend_dead, last = K - 1;
                 if (dead != last) {
@@ -650,7 +674,10 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
                             table[dead + dead * kt] = table[last + last * kt]; table[last + last * kt] = 0;
                         }
                     }
-                    if (d < 4) { g[4 * dead + d] = g[4 * last + d]; g[4 * last + d] = 0; }
+                    if (d < 4 * DN_D_WARPS) {
+                        int32_t *gw = g_buf + (buf * DN_D_WARPS + (d >> 2)) * 4 * kt;
+                        gw[4 * dead + (d & 3)] = gw[4 * last + (d & 3)]; gw[4 * last + (d & 3)] = 0;
+                    }
                     if (d == 4) {
                         s_cnt[dead] = s_cnt[last]; s_lab[dead] = s_lab[last]; s_cnt[last] = 0;
                         s_logcnt[dead] = s_logcnt[last]; s_logcntm1[dead] = s_logcntm1[last];
@@ -662,9 +689,9 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
                 K -= 1;
                 pend_dead = -1;
                 bar_d();
+                if (d == 0) { s_KA = K; mbar_arrive(bar_go); }
             }
             pend_changed = false;
-            if (d == 0) { s_KA = K; mbar_arrive(bar_go); }    // the A warps may accumulate move r+1
             DPHASE(1);
             KA_prev = K;
             if (bad) {                                        // block-uniform
@@ -764,42 +791,57 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
             bar_d();
             DPHASE(2);
 
-            // ---- sample (D warp 0): log_choice (cxx/util_math.cc:58-65); sums in index order ----------
-            if (dwarp == 0) {
-                int idx = 0;
+            // ---- sample: log_choice (cxx/util_math.cc:58-65); sums in index order.  Up to 32 candidates every D warp
+            //      draws the (same) table by itself -- registers and shuffles only, no barrier afterwards.
+            int idx = 0;
+            if (ncand <= 32) {
                 if (args.flags & 1u) {                         // HIRM_SWEEP_SCORE_ONLY: stay
-                    #pragma unroll 1
-                    for (int t = lane; t < ncand; t += 32) if ((t < K ? s_order[t] : K) == c) idx = t;
-                    idx = __reduce_max_sync(0xffffffffu, idx);
+                    const unsigned me = __ballot_sync(0xffffffffu, lane < ncand && (lane < K ? s_order[lane] : K) == c);
+                    idx = me ? __ffs(me) - 1 : 0;
                 } else if (ncand > 1) {
-                    double mx = -1.0 / 0.0;
-                    if (ncand <= 8) {
+                    const double lp_t = lane < ncand ? s_lp[lane] : -1.0 / 0.0;
+                    double mx = lp_t;
+                    if (ncand <= 4) {
                         #pragma unroll 1
                         for (int t = 0; t < ncand; t++) mx = fmax(mx, s_lp[t]);
                     } else {
-                        #pragma unroll 1
-                        for (int t = lane; t < ncand; t += 32) mx = fmax(mx, s_lp[t]);
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                     }
                     DPHASE(8);
-                    #pragma unroll 1
-                    for (int t = lane; t < ncand; t += 32) s_tmp[t] = exp_nl(s_lp[t] - mx);   // scale-invariant rule: one exp each
-                    __syncwarp();
+                    const double e = exp_nl(lane < ncand ? lp_t - mx : -800.0);   // scale-invariant rule: one exp each; exp(-800) = 0
                     DPHASE(9);
-                    if (ncand <= 32) {                         // lane t: running sum up to t, in index order
-                        double cum = 0.0, total = 0.0;
+                    double cum = 0.0, total = 0.0;             // lane t: running sum up to t, in index order
+                    #pragma unroll 1
+                    for (int t = 0; t < ncand; t++) { total += __shfl_sync(0xffffffffu, e, t); if (t == lane) cum = total; }
+                    const double x = ctl.u * total;
+                    const unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && cum > x);
+                    idx = hit ? __ffs(hit) - 1 : ncand - 1;
+                }
+            } else {                                          // many candidates: D warp 0 draws, shared memory carries the result
+                if (dwarp == 0) {
+                    if (args.flags & 1u) {
                         #pragma unroll 1
-                        for (int t = 0; t < ncand; t++) { total += s_tmp[t]; if (t == lane) cum = total; }
-                        const double x = s_u * total;
-                        const unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && cum > x);
-                        idx = hit ? __ffs(hit) - 1 : ncand - 1;
+                        for (int t = lane; t < ncand; t += 32) if ((t < K ? s_order[t] : K) == c) idx = t;
+                        idx = __reduce_max_sync(0xffffffffu, idx);
                     } else {
+                        double mx = -1.0 / 0.0;
+                        #pragma unroll 1
+                        for (int t = lane; t < ncand; t += 32) mx = fmax(mx, s_lp[t]);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        #pragma unroll 1
+                        for (int t0 = 0; t0 < ncand; t0 += 32) {
+                            const int t = t0 + lane;
+                            const double e = exp_nl(t < ncand ? s_lp[t] - mx : -800.0);
+                            if (t < ncand) s_tmp[t] = e;
+                        }
+                        __syncwarp();
                         if (lane == 0) {
                             double total = 0.0;
                             #pragma unroll 1
                             for (int t = 0; t < ncand; t++) total += s_tmp[t];
-                            const double x = s_u * total;
+                            const double x = ctl.u * total;
                             double cum = 0.0;
                             idx = ncand - 1;
                             #pragma unroll 1
@@ -807,17 +849,19 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
                         }
                         idx = __shfl_sync(0xffffffffu, idx, 0);
                     }
+                    if (lane == 0) s_choice_idx = idx;
                 }
-                DPHASE(10);
-                if (lane == 0) {
-                    if (nofree) raise_error(irm, KERR_NO_FREE_SLOT);
-                    int cs, cl;
-                    if (nofree || ncand == 0) { cs = c; cl = s_lab[c]; }
-                    else { cs = idx < K ? s_order[idx] : K; cl = idx < K ? s_lab[cs] : fresh_label; }
-                    s_choice_slot = cs; s_choice_label = cl;
-                    if (args.out_choice) args.out_choice[m] = cl;
-                    if (args.trace_cap > 0) args.trace_n[m] = ncand;
-                }
+                bar_d();
+                idx = s_choice_idx;
+            }
+            DPHASE(10);
+            int tnew, newlabel;
+            if (nofree || ncand == 0) { tnew = c; newlabel = s_lab[c]; }
+            else { tnew = idx < K ? s_order[idx] : K; newlabel = idx < K ? s_lab[tnew] : fresh_label; }
+            if (d == 0) {
+                if (nofree) raise_error(irm, KERR_NO_FREE_SLOT);
+                if (args.out_choice) args.out_choice[m] = newlabel;
+                if (args.trace_cap > 0) args.trace_n[m] = ncand;
             }
             if (args.trace_cap > 0) {
                 #pragma unroll 1
@@ -826,14 +870,12 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
                     args.trace_logps[m * args.trace_cap + t] = s_lp[t];
                 }
             }
-            bar_d();
             DPHASE(3);
 
             // ---- apply, only if the table changed ------------------------------------------------------
-            const int tnew = s_choice_slot;
             if (tnew != c) {
-                const int newlabel = s_choice_label;
                 const bool died = singleton;
+                bar_d();                                       // both D warps have drawn: the bookkeeping below may be rewritten
                 #pragma unroll 1
                 for (int k = d; k < K; k += DN_ND) {          // i's observations leave row / column c
                     if (k != c) {
@@ -876,6 +918,7 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
                 pend_changed = true; pend_item = item; pend_old = c; pend_new = tnew;
                 if (tnew == K) K += 1;
                 if (died) pend_dead = c;
+                bar_d();                                       // the table and the cached logs are final before anyone scores again
             }
             DPHASE(4);
         }
@@ -937,28 +980,58 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
 // ---------------------------------------------------------------------------------------
 // helpers for dense relations
 // ---------------------------------------------------------------------------------------
-// count-table rebuild from slab0: cell (z0[i], z1[j]) += (1, x) for every observed (i, j)
-__global__ void __launch_bounds__(256) rebuild_counts_dense_kernel(const IrmDev *irms, int irm_id, int rel) {
+// Count-table rebuild from slab0: cell (z0[i], z1[j]) += (1, x) for every observed (i, j)   (Relation::incorporate,
+// cxx/hirm.hh:281-289: the table is the histogram of (observations, z)).  A CTA takes rows i = blockIdx.x, + gridDim.x, ...;
+// the row is streamed with 16-byte loads and binned by z1[j] into per-thread private bins (n | s << 16 per slot, no
+// atomics), the bins are folded into the CTA's copy of the table at the end of the row, the copy into the global table
+// at the end.  Dynamic shared memory: zs1[n1 padded to 16] bytes, bins[k1 * RB_THREADS] words, tab[ncells] cells.
+constexpr int RB_THREADS = 256;
+__global__ void __launch_bounds__(RB_THREADS) rebuild_counts_dense_kernel(const IrmDev *irms, int irm_id, int rel) {
     const IrmDev &irm = irms[irm_id];
     const RelationDev *R = &irm.rel[rel];
     const DomainDev &d0 = irm.dom[R->dom[0]], &d1 = irm.dom[R->dom[1]];
-    extern __shared__ cell_t s_tab[];
-    const int64_t nc = R->ncells;
-    for (int64_t k = threadIdx.x; k < nc; k += blockDim.x) s_tab[k] = 0;
+    const int n0 = d0.n, n1 = d1.n, k1 = d1.kcap, n1pad = (n1 + 15) & ~15;
+    const int64_t nc = R->ncells, cs0 = R->cstride[0], cs1 = R->cstride[1];
+    extern __shared__ __align__(16) uint8_t rb_smem[];
+    uint8_t *zs1 = rb_smem;
+    uint32_t *bins = reinterpret_cast<uint32_t *>(rb_smem + n1pad);
+    cell_t *tab = reinterpret_cast<cell_t *>(rb_smem + n1pad + (size_t)k1 * RB_THREADS * 4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool absent = false;
+    for (int j = tid; j < n1pad; j += RB_THREADS) { const int zj = j < n1 ? d1.z[j] : 0; zs1[j] = zj < 0 ? (uint8_t)0xFF : (uint8_t)zj; }
+    for (int k = tid; k < k1 * RB_THREADS; k += RB_THREADS) bins[k] = 0u;
+    for (int64_t k = tid; k < nc; k += RB_THREADS) tab[k] = 0;
     __syncthreads();
-    for (int i = blockIdx.x; i < d0.n; i += gridDim.x) {
+    uint32_t *mine = bins + tid;
+    for (int i = blockIdx.x; i < n0; i += gridDim.x) {
         const int zi = d0.z[i];
         const uint8_t *row = R->slab[0] + (int64_t)i * R->pitch[0];
-        for (int j = threadIdx.x; j < d1.n; j += blockDim.x) {
-            const uint8_t x = row[j];
-            if (x & 0x80) continue;
-            const int zj = d1.z[j];
-            if (zi < 0 || zj < 0) { raise_error(irm, KERR_ABSENT_ENTITY); continue; }
-            atomicAdd(&s_tab[zi * R->cstride[0] + zj * R->cstride[1]], pack_cell(1u, x & 1u));
+        for (int v = tid; v < (n1pad >> 4); v += RB_THREADS) {
+            const uint4 xv = *reinterpret_cast<const uint4 *>(row + (size_t)v * 16);
+            const uint4 zv = *reinterpret_cast<const uint4 *>(zs1 + (size_t)v * 16);
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, zw[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t x = (xw[w] >> (8 * b)) & 0xFFu, slot = (zw[w] >> (8 * b)) & 0xFFu;
+                    if ((x & 0x80u) || v * 16 + w * 4 + b >= n1) continue;        // missing / row padding
+                    if (slot == 0xFFu || zi < 0) { absent = true; continue; }
+                    mine[slot * RB_THREADS] += 1u | ((x & 1u) << 16);
+                }
+            }
         }
+        __syncthreads();
+        for (int k = warp; k < k1; k += RB_THREADS / 32) {         // fold the bins of slot k into cell (zi, k); this warp owns slot k
+            uint32_t nn = 0, ss = 0;
+            for (int t = lane; t < RB_THREADS; t += 32) { const uint32_t w = bins[k * RB_THREADS + t]; bins[k * RB_THREADS + t] = 0u; nn += w & 0xFFFFu; ss += w >> 16; }
+            nn = __reduce_add_sync(0xffffffffu, nn); ss = __reduce_add_sync(0xffffffffu, ss);
+            if (lane == 0 && nn && zi >= 0) tab[zi * cs0 + k * cs1] += pack_cell(nn, ss);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int64_t k = threadIdx.x; k < nc; k += blockDim.x) if (s_tab[k]) atomicAdd(&R->counts[k], s_tab[k]);
+    if (__syncthreads_or(absent) && tid == 0) raise_error(irm, KERR_ABSENT_ENTITY);
+    for (int64_t k = tid; k < nc; k += RB_THREADS) if (tab[k]) atomicAdd(&R->counts[k], tab[k]);
 }
 
 // flag = 1 if any cell (i, j), i < rows, j < cols, is missing (byte >= 0x80)

@@ -536,8 +536,13 @@ static int ensure_counts(hirm_engine *e, int32_t id) {
             int blocks = (int)std::min<int64_t>((S.rel[r].nobs + 255) / 256, 148 * 8);
             rebuild_counts_coo_kernel<<<blocks, 256, 0, e->stream>>>(e->d_irms.p, id, r);
         } else {
-            int blocks = std::min(irm->n_ent[irm->rdom[r][0]], e->num_sms * 4);
-            rebuild_counts_dense_kernel<<<blocks, 256, (size_t)irm->ncells[r] * sizeof(cell_t), e->stream>>>(e->d_irms.p, id, r);
+            const int n0 = irm->n_ent[irm->rdom[r][0]], n1 = irm->n_ent[irm->rdom[r][1]], k1 = irm->kcap[irm->rdom[r][1]];
+            const size_t smem = (size_t)((n1 + 15) & ~15) + (size_t)k1 * RB_THREADS * 4 + (size_t)irm->ncells[r] * sizeof(cell_t);
+            if (smem > (size_t)e->max_smem_optin) return fail("dense relation: domain too large for the count-table build");
+            const int per_sm = std::max(1, std::min(4, (int)((size_t)e->smem_per_sm / (smem + 1024))));
+            int blocks = std::max(1, std::min(n0, e->num_sms * per_sm));
+            CK(cudaFuncSetAttribute(rebuild_counts_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            rebuild_counts_dense_kernel<<<blocks, RB_THREADS, smem, e->stream>>>(e->d_irms.p, id, r);
         }
         CK(cudaGetLastError());
     }

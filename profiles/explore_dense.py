@@ -33,6 +33,10 @@ def init(kind):
             z = bench.crp_prior_labels_fast(n, 1.0, rng)
         elif kind == 'rand64':
             z = rng.integers(0, min(kcap - 1, 63), n).astype(np.int32)
+        elif kind.startswith('truth') and len(kind) > 5:      # truthK: the two planted blocks plus K-2 small tables of 7 entities
+            z = (np.arange(n) >= n // 2).astype(np.int32)
+            for t in range(2, int(kind[5:])):
+                z[rng.choice(n, 7, replace=False)] = t
         else:
             z = (np.arange(n) >= n // 2).astype(np.int32)
         eng.set_assignments(h, 0, z)
@@ -52,7 +56,7 @@ for kind in os.environ.get('INITS', 'truth,crp').split(','):
         os.environ['HIRM_DENSE_CTAS_PER_SM'] = cps
         hsub = hs[:int(cps) * sms]
         init(kind)
-        run(hsub, 200, 1)
+        run(hsub, 50, 1)
         ms = run(hsub, M, 2)
         moves = len(hsub) * M
         tabs = [len(np.unique(eng.get_assignments(h, 0))) for h in hsub[:4]]
