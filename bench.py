@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=20000)
-    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = four per SM)")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = sixteen per SM: four resident, the rest queued)")
     ap.add_argument("--moves-per-step", type=int, default=0, help="moves per chain per step (0 = n: one full sweep)")
     ap.add_argument("--max-tables", type=int, default=64)
     ap.add_argument("--seed", type=int, default=0)
@@ -213,7 +213,7 @@ def main_b200(args, rank, world, local_rank):
     props = torch.cuda.get_device_properties(dev)
     n = args.n
     M = args.moves_per_step or n                  # one step = one full sweep of every chain
-    chains = args.chains or 4 * props.multi_processor_count
+    chains = args.chains or 16 * props.multi_processor_count   # 4 resident per SM, the rest queue: the block scheduler balances chains of different cost
     pitch = (n + 15) // 16 * 16
 
     # ---- ingest: observations from pinned host memory (timed once, reported in config) -------

@@ -78,7 +78,7 @@ __host__ __device__ inline DenseLaunch dense_layout(int n, int kt, int chunk, in
     int off = 8 * (2 * DN_MAX_STAGES + 4);          // mbarriers: full[S], empty[S], ready[2], go
     L.off_lf = off;    off += DN_LF * 8;
     L.off_table = off; off += kt * kt * 8;
-    L.off_dbl = off;   off += 5 * (kt + 2) * 8;     // s_lp[2], s_tmp, s_logcnt, s_logcntm1
+    L.off_dbl = off;   off += 2 * (kt + 2) * 8;     // s_logcnt, s_logcntm1
     L.off_wpart = off; off += 2 * DN_A_WARPS * 4 * kt * 4;
     L.off_bins = off;  off += bins_words * 4;
     L.off_ints = off;  off += (2 * DN_D_WARPS * 4 * kt + 4 * kt + 8) * 4;   // g[2][D warps][4kt], s_cnt, s_lab, s_order, s_map
@@ -166,33 +166,6 @@ __device__ __forceinline__ void acc_word(uint32_t xr, uint32_t xc, uint32_t z, i
         rs[k] = (int)__dp4a(mk, sr, (unsigned)rs[k]);
         cs[k] = (int)__dp4a(mk, sc, (unsigned)cs[k]);
     }
-}
-
-// lfact_diff (device_math.cuh) for a CONVERGED warp -- all 32 lanes call it together, lanes without work pass
-// m = 0 -- against the shared-memory table lf[DN_LF]: branch-free per lane, each transcendental called once
-// for the whole warp and skipped by warp vote when no lane needs it.
-__device__ __forceinline__ double lfact_diff_warp_s(const double *lf, uint32_t a, uint32_t m) {
-    const uint32_t am = a + m;
-    const bool small = am < (uint32_t)DN_LF;                    // includes m == 0 with a small a
-    const bool need = m != 0u && !small;
-    const bool big = a >= (uint32_t)DN_LF;
-    const double lfa = lf[min(a, (uint32_t)DN_LF - 1u)];
-    double res = (m != 0u && small) ? lf[min(am, (uint32_t)DN_LF - 1u)] - lfa : 0.0;
-    if (__any_sync(0xffffffffu, need)) {
-        const double y = (double)a + 1.0, dm = (double)m, ym = y + dm;
-        const double L = log_nl(need ? (big ? y : ym) : 1.0);
-        const double c2 = stirling_corr_r(fast_rcp(ym));
-        double r = (ym - 0.5) * L - ym + 0.91893853320467274178 + c2 - lfa;      // a small, a + m large
-        if (__any_sync(0xffffffffu, need && big)) {
-            const double ry = fast_rcp(y);
-            const double P = log1p_nl((need && big) ? dm * ry : 0.0);
-            // (y+m-1/2) ln(y+m) - (y-1/2) ln y - m + corr(y+m) - corr(y),  ln(y+m) = ln y + log1p(m/y)
-            const double rb = (ym - 0.5) * P + dm * (L - 1.0) + (c2 - stirling_corr_r(ry));
-            if (big) r = rb;
-        }
-        if (need) res = r;
-    }
-    return res;
 }
 
 // ring cursor shared by the producer and the A warps (each keeps its own copy)
@@ -395,9 +368,7 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
     uint64_t *bar_go = bar_ready + 2;                                            // [1]  D -> A: z is stable for move r
     double *s_lf = reinterpret_cast<double *>(smem + L.off_lf);                  // [DN_LF] lgamma(m+1)
     cell_t *table = reinterpret_cast<cell_t *>(smem + L.off_table);              // [kt*kt]  Relation::clusters, cell (a, b) at a + b*kt
-    double *s_lp2 = reinterpret_cast<double *>(smem + L.off_dbl);                // [2][kt+2] candidate log-probabilities, by move parity
-    double *s_tmp = s_lp2 + 2 * (kt + 2);
-    double *s_logcnt = s_tmp + (kt + 2);                                         // log(count) per slot
+    double *s_logcnt = reinterpret_cast<double *>(smem + L.off_dbl);                                         // log(count) per slot
     double *s_logcntm1 = s_logcnt + (kt + 2);                                    // log(count - 1) per slot
     int32_t *wpart = reinterpret_cast<int32_t *>(smem + L.off_wpart);            // [2][A_WARPS][4*kt] per-warp group sums
     uint32_t *bins = reinterpret_cast<uint32_t *>(smem + L.off_bins);            // [bins_words]
@@ -406,8 +377,9 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
     int32_t *s_order = s_lab + kt, *s_map = s_order + kt;                        // slots by ascending label; load-time slot map
     uint8_t *zs = smem + L.off_zs;                                               // [npad] slot of every entity
     uint8_t *ring = smem + L.off_ring;                                           // [NS][2][chunk]
-    __shared__ int32_t s_K, s_KA, s_choice_idx;
+    __shared__ int32_t s_K, s_KA;
     __shared__ MoveCtl s_ctl[DN_CTL];
+    __shared__ double s_val[2 * DN_ND];                   // one round of cell scores, double-buffered
     __shared__ int32_t s_has_absent;
     __shared__ long long s_limit, s_issued, s_consumed, s_done;
     __shared__ long long s_ph[14];                        // profiling only   // first move NOT to be made (tier overflow); ring chunks issued / consumed
@@ -600,13 +572,13 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
         if (prof) for (int i = 0; i < 14; i++) s_ph[i] = 0;
 #define DPHASE(i) do { if (prof) { const long long _t = clk(); s_ph[i] += _t - tl; tl = _t; } } while (0)
         int64_t r_done = nmoves;                               // first move not made
+        int vb = 0;                                            // s_val buffer of the next scoring round (alternates for the whole launch)
         #pragma unroll 1
         for (int64_t r = r_begin; r < nmoves; r++) {
             const int64_t m = m0 + r;
             const int64_t rr = r - r_begin;                    // barrier phases count from this launch's first move
             const int buf = (int)(rr & 1);
             int32_t *g = g_buf + (buf * DN_D_WARPS + dwarp) * 4 * kt;     // this warp's copy of the group sums
-            double *s_lp = s_lp2 + buf * (kt + 2);
             DPHASE(5);
             mbar_wait(&bar_ready[buf], (uint32_t)((rr >> 1) & 1));
             DPHASE(0);
@@ -724,137 +696,118 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
             const int ncand = K + ((singleton || nofree) ? 0 : 1);
             const int fresh_label = max(0, s_lab[s_order[K - 1]]) + 1;   // t_max starts at 0 (cxx/hirm.hh:139)
 
-            // ---- score.  logp_gibbs_exact (cxx/hirm.hh:441-461): for every candidate t the sum over target
-            //      cells of S(N+n, s+sg) - S(N, s) = D(s, sg) + D(N-s, n-sg) - D(N+1, n), D(a, m) = log((a+m)!/a!),
-            //      with (N, s) the cell WITHOUT i's own observations.  A team of LPC lanes owns a candidate;
-            //      lane partials are combined in a fixed order (deterministic log-probabilities).
+            // ---- score.  logp_gibbs_exact (cxx/hirm.hh:441-461): for every candidate t the sum over its 2K+1 target
+            //      cells of S(N+n, s+sg) - S(N, s), with (N, s) the cell WITHOUT i's own observations.  The
+            //      (candidate, cell) pairs are laid flat over the D lanes, DN_ND per round; a lane evaluates one
+            //      cell (branch-free, six independent log chains).  Then lane t of EVERY D warp adds up candidate
+            //      t's cells in index order (a segmented reduction with a fixed order: deterministic, and identical
+            //      in both warps), so that each warp can go on to draw the table by itself.
+            constexpr int MAXJ = 3;                            // candidates per lane: t = lane + 32 j (at most 64 tables + a fresh one)
+            double lp[MAXJ];
+#pragma unroll
+            for (int j = 0; j < MAXJ; j++) lp[j] = 0.0;
             {
-                int LPC = 32;
-                while (LPC > 1 && ncand * LPC > DN_ND) LPC >>= 1;
-                const int nteams = DN_ND / LPC, team = d / LPC, lt = d - team * LPC;
-                const int items = 3 * (2 * K + 1);
+                const int IPC = 2 * K + 1, total = ncand * IPC;
                 const cell_t rem_cc = pack_cell((uint32_t)(g[4 * c] + g[4 * c + 2] + d_n), (uint32_t)(g[4 * c + 1] + g[4 * c + 3] + d_s));
                 #pragma unroll 1
-                for (int t0 = 0; t0 < ncand; t0 += nteams) {
-                    const int t = t0 + team;
-                    const bool tv = t < ncand;
-                    const int st = tv ? (t < K ? s_order[t] : K) : 0;
-                    double acc = 0.0;
-                    #pragma unroll 1
-                    for (int w0 = 0; w0 < items; w0 += LPC) {
-                        // gather the operands (cheap, lanes may diverge), then ONE converged evaluation for the warp
-                        const int w = w0 + lt;
-                        uint32_t a = 0u, mm = 0u; bool neg = false;
-                        if (tv && w < items) {
-                            const int q = w / 3, term = w - 3 * q;
-                            int gn = 0, gs = 0; cell_t cur = 0;
-                            if (q == 2 * K) {                  // the (t, t) cell of the fresh slot: the diagonal only
-                                if (st >= K) { gn = d_n; gs = d_s; }
-                            } else {
-                                const int k = q >> 1, col = q & 1;
-                                if (k == st) {                 // merged target cell (t, t): row group + column group + diagonal
-                                    if (!col) {
-                                        gn = g[4 * k] + g[4 * k + 2] + d_n; gs = g[4 * k + 1] + g[4 * k + 3] + d_s;
-                                        cur = table[st + st * kt];
-                                        if (st == c) cur -= rem_cc;
-                                    }
-                                } else if (!col) {             // (i, j), z_j = k  ->  cell (t, k)
-                                    gn = g[4 * k]; gs = g[4 * k + 1];
-                                    cur = table[st + k * kt];
-                                    if (st == c) cur -= pack_cell((uint32_t)gn, (uint32_t)gs);
-                                    else if (k == c) cur -= pack_cell((uint32_t)g[4 * st + 2], (uint32_t)g[4 * st + 3]);   // i's column group with slot t sits in (t, c)
-                                } else {                       // (j, i), z_j = k  ->  cell (k, t)
-                                    gn = g[4 * k + 2]; gs = g[4 * k + 3];
-                                    cur = table[k + st * kt];
-                                    if (st == c) cur -= pack_cell((uint32_t)gn, (uint32_t)gs);
-                                    else if (k == c) cur -= pack_cell((uint32_t)g[4 * st], (uint32_t)g[4 * st + 1]);       // i's row group with slot t sits in (c, t)
+                for (int base = 0; base < total; base += DN_ND) {
+                    const int w = base + d;
+                    uint32_t N = 0u, sv = 0u, gn = 0u, gs = 0u;
+                    if (w < total) {                           // gather the cell's operands (cheap; lanes may diverge)
+                        const int t = w / IPC, q = w - t * IPC;
+                        const int st = t < K ? s_order[t] : K;
+                        cell_t cur = 0;
+                        if (q == 2 * K) {                      // the (t, t) cell of the fresh slot: the diagonal only
+                            if (st >= K) { gn = d_n; gs = d_s; }
+                        } else {
+                            const int k = q >> 1, col = q & 1;
+                            if (k == st) {                     // merged target cell (t, t): row group + column group + diagonal
+                                if (!col) {
+                                    gn = g[4 * k] + g[4 * k + 2] + d_n; gs = g[4 * k + 1] + g[4 * k + 3] + d_s;
+                                    cur = table[st + st * kt];
+                                    if (st == c) cur -= rem_cc;
                                 }
+                            } else if (!col) {                 // (i, j), z_j = k  ->  cell (t, k)
+                                gn = g[4 * k]; gs = g[4 * k + 1];
+                                cur = table[st + k * kt];
+                                if (st == c) cur -= pack_cell(gn, gs);
+                                else if (k == c) cur -= pack_cell((uint32_t)g[4 * st + 2], (uint32_t)g[4 * st + 3]);   // i's column group with slot t sits in (t, c)
+                            } else {                           // (j, i), z_j = k  ->  cell (k, t)
+                                gn = g[4 * k + 2]; gs = g[4 * k + 3];
+                                cur = table[k + st * kt];
+                                if (st == c) cur -= pack_cell(gn, gs);
+                                else if (k == c) cur -= pack_cell((uint32_t)g[4 * st], (uint32_t)g[4 * st + 1]);       // i's row group with slot t sits in (c, t)
                             }
-                            const uint32_t N = cell_n(cur), sv = cell_s(cur);
-                            a = term == 0 ? sv : term == 1 ? N - sv : N + 1u;
-                            mm = (uint32_t)(term == 0 ? gs : term == 1 ? gn - gs : gn);
-                            neg = term == 2;
                         }
-                        __syncwarp();
-                        const double v = lfact_diff_warp_s(s_lf, a, mm);
-                        acc += neg ? -v : v;
+                        N = cell_n(cur); sv = cell_s(cur);
                     }
-                    DPHASE(6);
-                    for (int o = LPC >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    DPHASE(7);
-                    if (tv && lt == 0) {
-                        const double prior = st == c ? (singleton ? logalpha : s_logcntm1[c]) : (t < K ? s_logcnt[st] : logalpha);
-                        s_lp[t] = prior + acc;
+                    __syncwarp();
+                    s_val[vb * DN_ND + d] = score_delta_bf<DN_LF>(s_lf, N, sv, gn, gs);
+                    bar_d();
+#pragma unroll
+                    for (int j = 0; j < MAXJ; j++) {
+                        const int t = lane + 32 * j;
+                        if (t < ncand) {
+                            const int w0 = max(t * IPC, base) - base, w1 = min((t + 1) * IPC, base + DN_ND) - base;
+                            #pragma unroll 1
+                            for (int ww = w0; ww < w1; ww++) lp[j] += s_val[vb * DN_ND + ww];
+                        }
+                    }
+                    vb ^= 1;
+                }
+#pragma unroll
+                for (int j = 0; j < MAXJ; j++) {
+                    const int t = lane + 32 * j;
+                    if (t < ncand) {
+                        const int st = t < K ? s_order[t] : K;
+                        lp[j] += st == c ? (singleton ? logalpha : s_logcntm1[c]) : (t < K ? s_logcnt[st] : logalpha);
                     }
                 }
             }
-            bar_d();
             DPHASE(2);
 
-            // ---- sample: log_choice (cxx/util_math.cc:58-65); sums in index order.  Up to 32 candidates every D warp
-            //      draws the (same) table by itself -- registers and shuffles only, no barrier afterwards.
+            // ---- sample: log_choice (cxx/util_math.cc:58-65); sums in index order.  Every D warp draws the (same)
+            //      table by itself: registers and shuffles only, no barrier afterwards.
             int idx = 0;
-            if (ncand <= 32) {
-                if (args.flags & 1u) {                         // HIRM_SWEEP_SCORE_ONLY: stay
-                    const unsigned me = __ballot_sync(0xffffffffu, lane < ncand && (lane < K ? s_order[lane] : K) == c);
-                    idx = me ? __ffs(me) - 1 : 0;
-                } else if (ncand > 1) {
-                    const double lp_t = lane < ncand ? s_lp[lane] : -1.0 / 0.0;
-                    double mx = lp_t;
-                    if (ncand <= 4) {
-                        #pragma unroll 1
-                        for (int t = 0; t < ncand; t++) mx = fmax(mx, s_lp[t]);
-                    } else {
+            if (args.flags & 1u) {                             // HIRM_SWEEP_SCORE_ONLY: stay
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    }
-                    DPHASE(8);
-                    const double e = exp_nl(lane < ncand ? lp_t - mx : -800.0);   // scale-invariant rule: one exp each; exp(-800) = 0
-                    DPHASE(9);
-                    double cum = 0.0, total = 0.0;             // lane t: running sum up to t, in index order
-                    #pragma unroll 1
-                    for (int t = 0; t < ncand; t++) { total += __shfl_sync(0xffffffffu, e, t); if (t == lane) cum = total; }
-                    const double x = ctl.u * total;
-                    const unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && cum > x);
-                    idx = hit ? __ffs(hit) - 1 : ncand - 1;
+                for (int j = 0; j < MAXJ; j++) {
+                    const int t = lane + 32 * j;
+                    if (t < ncand && (t < K ? s_order[t] : K) == c) idx = t;
                 }
-            } else {                                          // many candidates: D warp 0 draws, shared memory carries the result
-                if (dwarp == 0) {
-                    if (args.flags & 1u) {
-                        #pragma unroll 1
-                        for (int t = lane; t < ncand; t += 32) if ((t < K ? s_order[t] : K) == c) idx = t;
-                        idx = __reduce_max_sync(0xffffffffu, idx);
-                    } else {
-                        double mx = -1.0 / 0.0;
-                        #pragma unroll 1
-                        for (int t = lane; t < ncand; t += 32) mx = fmax(mx, s_lp[t]);
+                idx = __reduce_max_sync(0xffffffffu, idx);
+            } else if (ncand > 1) {
+                double mx = -1.0 / 0.0;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                        #pragma unroll 1
-                        for (int t0 = 0; t0 < ncand; t0 += 32) {
-                            const int t = t0 + lane;
-                            const double e = exp_nl(t < ncand ? s_lp[t] - mx : -800.0);
-                            if (t < ncand) s_tmp[t] = e;
-                        }
-                        __syncwarp();
-                        if (lane == 0) {
-                            double total = 0.0;
-                            #pragma unroll 1
-                            for (int t = 0; t < ncand; t++) total += s_tmp[t];
-                            const double x = ctl.u * total;
-                            double cum = 0.0;
-                            idx = ncand - 1;
-                            #pragma unroll 1
-                            for (int t = 0; t < ncand; t++) { cum += s_tmp[t]; if (cum > x) { idx = t; break; } }
-                        }
-                        idx = __shfl_sync(0xffffffffu, idx, 0);
-                    }
-                    if (lane == 0) s_choice_idx = idx;
+                for (int j = 0; j < MAXJ; j++) if (lane + 32 * j < ncand) mx = fmax(mx, lp[j]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                double e[MAXJ];
+#pragma unroll
+                for (int j = 0; j < MAXJ; j++) {
+                    e[j] = 0.0;
+                    if (32 * j < ncand) e[j] = exp_nl(lane + 32 * j < ncand ? lp[j] - mx : -800.0);   // scale-invariant rule: one exp each; exp(-800) = 0
                 }
-                bar_d();
-                idx = s_choice_idx;
+                double total = 0.0, cum[MAXJ];                 // lane t: running sum up to t, in index order
+#pragma unroll
+                for (int j = 0; j < MAXJ; j++) {
+                    cum[j] = 0.0;
+                    if (32 * j < ncand) {
+                        const int nt = min(32, ncand - 32 * j);
+                        #pragma unroll 1
+                        for (int t = 0; t < nt; t++) { total += __shfl_sync(0xffffffffu, e[j], t); if (t == lane) cum[j] = total; }
+                    }
+                }
+                const double x = ctl.u * total;
+                idx = ncand - 1;
+#pragma unroll
+                for (int j = MAXJ - 1; j >= 0; j--) {
+                    if (32 * j < ncand) {
+                        const unsigned hit = __ballot_sync(0xffffffffu, lane + 32 * j < ncand && cum[j] > x);
+                        if (hit) idx = 32 * j + __ffs(hit) - 1;
+                    }
+                }
             }
-            DPHASE(10);
             int tnew, newlabel;
             if (nofree || ncand == 0) { tnew = c; newlabel = s_lab[c]; }
             else { tnew = idx < K ? s_order[idx] : K; newlabel = idx < K ? s_lab[tnew] : fresh_label; }
@@ -863,11 +816,14 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
                 if (args.out_choice) args.out_choice[m] = newlabel;
                 if (args.trace_cap > 0) args.trace_n[m] = ncand;
             }
-            if (args.trace_cap > 0) {
-                #pragma unroll 1
-                for (int t = d; t < ncand && t < args.trace_cap; t += DN_ND) {
-                    args.trace_labels[m * args.trace_cap + t] = t < K ? s_lab[s_order[t]] : fresh_label;
-                    args.trace_logps[m * args.trace_cap + t] = s_lp[t];
+            if (args.trace_cap > 0 && dwarp == 0) {
+#pragma unroll
+                for (int j = 0; j < MAXJ; j++) {
+                    const int t = lane + 32 * j;
+                    if (t < ncand && t < args.trace_cap) {
+                        args.trace_labels[m * args.trace_cap + t] = t < K ? s_lab[s_order[t]] : fresh_label;
+                        args.trace_logps[m * args.trace_cap + t] = lp[j];
+                    }
                 }
             }
             DPHASE(3);

@@ -62,12 +62,73 @@ __device__ __forceinline__ double lfact_half(int64_t a, int64_t m, int half) {
     return (y - 0.5) * log1p(dm * ry) - dm + (stirling_corr_r(fast_rcp(y + dm)) - stirling_corr_r(ry));
 }
 
-// Single out-of-line copies of the fp64 transcendentals for the dense sweep kernel: its decision warps
-// run a long, once-per-move code path, and every inlined copy of log/log1p/exp (hundreds of bytes of
-// SASS each) is instruction-cache traffic on that path.
+// Single out-of-line copies of the library transcendentals for the dense sweep kernel's rare paths
+// (every inlined copy is instruction-cache traffic on a once-per-move code path).
 __device__ __noinline__ double log_nl(double x) { return log(x); }
-__device__ __noinline__ double log1p_nl(double x) { return log1p(x); }
 __device__ __noinline__ double exp_nl(double x) { return exp(x); }
+
+// ---------------------------------------------------------------------------------
+// Branch-free fp64 building blocks for the dense kernel's scoring.  The move's critical path is a chain of
+// DEPENDENT fp64 instructions (DFMA issues back to back only every ~23 cycles on sm_100), so the score of a
+// target cell is written as straight-line code whose six logarithms are independent chains the scheduler can
+// interleave -- no calls, no special-case branches (arguments are positive, finite and >= 1 by construction).
+// ---------------------------------------------------------------------------------
+// 1/x for a normal positive x: MUFU.RCP64H seed and two Newton steps (error ~1 ulp)
+__device__ __forceinline__ double rcp_nr(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+// ln(v) for a normal v >= 1.  Argument reduction v = 2^k m, m in [sqrt(1/2), sqrt(2)); with f = m - 1 and
+// s = f / (2 + f):  ln(m) = f - f^2/2 + s (f^2/2 + R(s^2)),  R the degree-7 minimax polynomial of W. Kahan's
+// classic scheme (as in 4.3BSD libm / fdlibm's log); error < 1 ulp, checked against mpmath in tests.
+__device__ __forceinline__ double log_core(double v) {
+    int hi = __double2hiint(v);
+    const int lo = __double2loint(v);
+    int k = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int i = (hi + 0x95f64) & 0x100000;          // mantissa >= sqrt(2): use m / 2 and k + 1
+    hi |= i ^ 0x3ff00000;
+    k += i >> 20;
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double s = f * rcp_nr(2.0 + f);
+    const double dk = (double)k;
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
+}
+// log((a+m)! / a!) against a table lf[LFS] of lgamma(j+1), branch-free (selects only):
+//   a + m < LFS          lf[a+m] - lf[a]
+//   a < LFS <= a + m     Stirling(a+m+1) - lf[a]
+//   a >= LFS             (y+m-1/2) log1p(m/y) + m (ln y - 1) + corr(y+m) - corr(y),  y = a + 1   (no cancellation)
+// log1p(x) = ln(u) + (x - (u - 1)) / u with u = 1 + x.
+template <int LFS>
+__device__ __forceinline__ double lfact_diff_bf(const double *lf, uint32_t a, uint32_t m) {
+    const uint32_t am = a + m;
+    const bool small = am < (uint32_t)LFS, big = a >= (uint32_t)LFS;
+    const double lfa = lf[min(a, (uint32_t)LFS - 1u)];
+    const double tab = lf[min(am, (uint32_t)LFS - 1u)] - lfa;
+    const double y = (double)a + 1.0, dm = (double)m, ym = y + dm;
+    const double ry = rcp_nr(y), rym = rcp_nr(ym);
+    const double x = dm * ry, u = 1.0 + x;
+    const double L = log_core(big ? y : ym);
+    const double P = log_core(u) + (x - (u - 1.0)) * rcp_nr(u);
+    const double c2 = stirling_corr_r(rym);
+    const double rb = fma(ym - 0.5, P, dm * (L - 1.0)) + (c2 - stirling_corr_r(ry));
+    const double rm = fma(ym - 0.5, L, -ym) + 0.91893853320467274178 + c2 - lfa;
+    return m == 0u ? 0.0 : small ? tab : big ? rb : rm;
+}
+// S(N+n, s+sg) - S(N, s) = D(s, sg) + D(N-s, n-sg) - D(N+1, n)   (see score_delta below), branch-free
+template <int LFS>
+__device__ __forceinline__ double score_delta_bf(const double *lf, uint32_t N, uint32_t sv, uint32_t gn, uint32_t gs) {
+    return (lfact_diff_bf<LFS>(lf, sv, gs) + lfact_diff_bf<LFS>(lf, N - sv, gn - gs)) - lfact_diff_bf<LFS>(lf, N + 1u, gn);
+}
 
 // BetaBernoulli::logp_score (cxx/hirm.hh:52-56), alpha = beta = 1:
 //   S(N, s) = lgamma(s+1) + lgamma(N-s+1) - lgamma(N+2)

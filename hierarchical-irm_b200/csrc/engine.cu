@@ -112,7 +112,7 @@ struct hirm_engine {
     DevBuf<uint64_t> s_sweep0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
-    int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0;
+    int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0, dense_static_smem = 0;
     long long *d_phase_cycles = nullptr;   // debug hook (hirm_engine_debug_phase_cycles)
 };
 
@@ -146,6 +146,9 @@ extern "C" int hirm_engine_create(hirm_engine **out, int device) {
     e->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     e->num_sms = prop.multiProcessorCount;
     e->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, dense_ree_sweep_kernel));
+    e->dense_static_smem = (int)fa.sharedSizeBytes + 64;
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
     // log-factorial table from libm's lgamma (the reference's lbeta, cxx/util_math.cc:13-15)
@@ -734,12 +737,12 @@ struct Plan {
 // each CTA's share of the SM's shared memory goes to its TMA ring.
 static bool plan_dense_tier(hirm_engine *e, int n, int kt, int n_dense, DenseLaunch &L) {
     const int bins_words = std::min(4096, std::max(32 * DN_A_WARPS * 16, 32 * kt));
-    int chunk = 4 * 16 * DN_NA, want = std::min(4, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
+    int chunk = 2 * 16 * DN_NA, want = std::min(4, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
     if (const char *s = getenv("HIRM_DENSE_CHUNK")) chunk = std::max(16, atoi(s) & ~15);
     if (const char *s = getenv("HIRM_DENSE_CTAS_PER_SM")) want = std::max(1, atoi(s));
     L = DenseLaunch{};
     for (; want >= 1; want--) {
-        const int budget = std::min(e->max_smem_optin, e->smem_per_sm / want - 1024) - 512;   // 1 KiB reserved per CTA + the kernel's static shared memory
+        const int budget = std::min(e->max_smem_optin, e->smem_per_sm / want - 1024) - e->dense_static_smem;   // 1 KiB reserved per CTA + the kernel's static shared memory
         const DenseLaunch L0 = dense_layout(n, kt, chunk, 0, bins_words);
         int stages = (budget - L0.total_bytes) / (2 * L0.chunk);
         stages = std::min(stages, std::min(DN_MAX_STAGES, 2 * L0.nchunks + 2));
