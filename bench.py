@@ -234,9 +234,11 @@ def main_b200(args, rank, world, local_rank):
         hs.append(h)
     rng = np.random.default_rng(1000 + args.seed + rank)
     t0 = time.perf_counter()
+    from hirm import shard
+    stream_ids = shard.chain_streams(world * chains, rank, world)          # global chain index = Philox stream, whatever N
     for c, h in enumerate(hs):
         eng.set_assignments(h, 0, crp_prior_labels_fast(n, 1.0, rng))     # Domain::incorporate: sequential CRP(1) prior draw
-        eng.set_rng(h, rank * chains + c, 0)
+        eng.set_rng(h, stream_ids[c], 0)
     k0 = [len(np.unique(eng.get_assignments(h, 0))) for h in hs[:8]]
     eng.logp_scores(hs)                           # forces every chain's count-table build
     build_s = time.perf_counter() - t0
@@ -251,7 +253,7 @@ def main_b200(args, rank, world, local_rank):
     irm_ids = np.asarray(hs, dtype=np.int32)
     d_off = torch.arange(chains + 1, dtype=torch.int64, device=dev) * M
     d_dom = torch.zeros(chains * M, dtype=torch.int32, device=dev)
-    d_stream = (torch.arange(chains, dtype=torch.int64, device=dev) + rank * chains)
+    d_stream = torch.tensor(stream_ids, dtype=torch.int64, device=dev)
     d_ctr = [torch.full((chains,), s * M, dtype=torch.int64, device=dev) for s in range(nsteps)]
     torch.cuda.synchronize()
 
@@ -348,7 +350,7 @@ def main_b200(args, rank, world, local_rank):
 
     # the same step through the explicit-move-list entry point (host move lists in, every chosen table out)
     host_moves = [(np.zeros(M, np.int32), np.ascontiguousarray(rng.permutation(n).astype(np.int32)[:M])) for _ in hs]
-    streams = np.arange(chains, dtype=np.uint64) + rank * chains
+    streams = np.asarray(stream_ids, dtype=np.uint64)
     eng.sweep(hs, host_moves, seed=args.seed + 2, streams=streams, counters=np.zeros(chains, np.uint64))
     t0 = time.perf_counter()
     eng.sweep(hs, host_moves, seed=args.seed + 2, streams=streams, counters=np.full(chains, M, np.uint64))
