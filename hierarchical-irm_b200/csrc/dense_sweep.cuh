@@ -17,8 +17,9 @@
 //                 (get_cluster_to_items_list, cxx/hirm.hh:388-397) WHILE move r is being decided.
 //                 z[i_r] is still the old value then; the decision warps move that one
 //                 observation pair to the right group afterwards (an O(1) fix-up).
-//                 <= 8 live tables: byte-SIMD one-hot masks of z and dp4a dot products into
-//                 registers; more: per-thread private bins with 4 x 8-bit fields.
+//                 z lives in shared memory as bit planes (32 entities per word), the observation bytes
+//                 are packed to bits with dp4a, and "ones of row i in table k" is popc(bits & mask_k):
+//                 <= 8 live tables in registers, more in per-thread private shared-memory accumulators.
 //   D  (2 warps)  decide move r: candidates + CRP prior (CRP::tables_weights_gibbs, :147-161),
 //                 score (logp_gibbs_exact, :441-461) against the table with i's observations
 //                 removed virtually, sample (log_choice, cxx/util_math.cc:58-65), and only
@@ -42,9 +43,7 @@ constexpr int DN_NA = 32 * DN_A_WARPS;
 constexpr int DN_ND = 32 * DN_D_WARPS;
 constexpr int DN_THREADS = 32 + DN_NA + DN_ND;   // warp 0 = producer, then the A warps, then the D warps
 constexpr int DN_MAX_STAGES = 16;
-constexpr int DN_MAX_KD = 8;                      // dp4a path: live tables in slots 0..7
 constexpr int DN_LF = 256;                        // shared-memory copy of lgamma(m+1), m < 256; Stirling (error < 1e-19) beyond
-constexpr int DN_FLUSH_VECS = 15;                 // 15 * 16 = 240 elements per thread between bin flushes (8-bit fields)
 
 // What the producer hands the decision warps for one move (through shared memory, ahead of the move's rows):
 // nothing in the decision loop ever waits on a global load.
@@ -60,30 +59,33 @@ struct DenseLaunch {
     int32_t npad;       // n rounded up to 16
     int32_t kt;         // table slots held in shared memory (<= max_tables: a chain that needs more stops and is
                         // resumed by the next, larger tier -- see progress[] below)
-    int32_t chunk;      // bytes of one row chunk (multiple of 16)
+    int32_t kcap;       // max_tables of the domain (slot space of the global state)
+    int32_t np;         // bit planes of z kept in shared memory: 2^np >= kt
+    int32_t full;       // 1: the relation has no missing cell and the domain no absent entity
+    int32_t chunk;      // bytes of one row chunk (multiple of 32)
     int32_t nchunks;    // chunks per row
     int32_t stages;     // ring depth
-    int32_t bins_words; // 32-bit words of private bins (multiple of 32 * kt is not required: HT adapts)
     // byte offsets into dynamic shared memory
-    int32_t off_lf, off_table, off_dbl, off_wpart, off_bins, off_ints, off_zs, off_ring, total_bytes;
+    int32_t off_lf, off_table, off_dbl, off_wpart, off_acc, off_ints, off_zp, off_ring, total_bytes;
 };
 
-// Shared-memory carve-up: 8-byte things first, then 4-byte, then the byte arrays (16-aligned).
-__host__ __device__ inline DenseLaunch dense_layout(int n, int kt, int chunk, int stages, int bins_words) {
+// Shared-memory carve-up: 8-byte things first, then 4-byte, then the ring (128-aligned).
+__host__ __device__ inline DenseLaunch dense_layout(int n, int kt, int kcap, int full, int chunk, int stages) {
     DenseLaunch L;
-    L.n = n; L.npad = (n + 15) & ~15; L.kt = kt;
-    if (chunk > L.npad) chunk = L.npad;
-    if (chunk < 16) chunk = 16;
-    L.chunk = chunk; L.nchunks = (L.npad + chunk - 1) / chunk; L.stages = stages; L.bins_words = bins_words;
+    L.n = n; L.npad = (n + 15) & ~15; L.kt = kt; L.kcap = kcap; L.full = full;
+    L.np = kt <= 8 ? 3 : kt <= 16 ? 4 : kt <= 32 ? 5 : 6;
+    chunk &= ~31;
+    if (chunk > ((L.npad + 31) & ~31)) chunk = (L.npad + 31) & ~31;
+    if (chunk < 32) chunk = 32;
+    L.chunk = chunk; L.nchunks = (L.npad + chunk - 1) / chunk; L.stages = stages;
     int off = 8 * (2 * DN_MAX_STAGES + 4);          // mbarriers: full[S], empty[S], ready[2], go
     L.off_lf = off;    off += DN_LF * 8;
     L.off_table = off; off += kt * kt * 8;
     L.off_dbl = off;   off += 2 * (kt + 2) * 8;     // s_logcnt, s_logcntm1
     L.off_wpart = off; off += 2 * DN_A_WARPS * 4 * kt * 4;
-    L.off_bins = off;  off += bins_words * 4;
-    L.off_ints = off;  off += (2 * DN_D_WARPS * 4 * kt + 4 * kt + 8) * 4;   // g[2][D warps][4kt], s_cnt, s_lab, s_order, s_map
-    off = (off + 15) & ~15;
-    L.off_zs = off;    off += L.npad;
+    L.off_acc = off;   off += kt > 8 ? (full ? 1 : 2) * kt * DN_NA * 4 : 0;   // private accumulators of the > 8 tables path
+    L.off_ints = off;  off += (2 * DN_D_WARPS * 4 * kt + 3 * kt + kcap + 8) * 4;   // g[2][D warps][4kt], s_cnt, s_lab, s_order, s_map[kcap]
+    L.off_zp = off;    off += ((n + 31) / 32) * L.np * 4;
     off = (off + 127) & ~127;
     L.off_ring = off;  off += stages * 2 * chunk;
     L.total_bytes = off;
@@ -121,19 +123,12 @@ __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 
 // named barrier among the D warps only
 __device__ __forceinline__ void bar_d() { asm volatile("bar.sync 1, %0;" ::"n"(DN_ND) : "memory"); }
 
-// nibble code (bit0 valid_row, bit1 x_row, bit2 valid_col, bit3 x_col) -> one increment per 8-bit field
-__device__ __forceinline__ uint32_t code_to_inc(uint32_t code) { return (code * 0x00204081u) & 0x01010101u; }
-// four elements at once: per byte, the nibble code of (row byte, col byte); a byte is valid iff < 0x80
-__device__ __forceinline__ uint32_t pack_codes(uint32_t xr, uint32_t xc) {
-    const uint32_t vr = (~xr >> 7) & 0x01010101u, vc = (~xc >> 7) & 0x01010101u;
-    return vr | ((xr & vr) << 1) | (vc << 2) | ((xc & vc) << 3);
-}
 // (n, s) of one observation byte
 __device__ __forceinline__ int byte_n(uint32_t x) { return (x & 0x80u) ? 0 : 1; }
 __device__ __forceinline__ int byte_s(uint32_t x) { return (x & 0x80u) ? 0 : (int)(x & 1u); }
 
 // bytes at or beyond element n are padding: make them "missing" (or 0 where only ones are counted)
-template <bool ZERO = false>
+template <bool ZERO>
 __device__ __forceinline__ void mask_tail(uint4 &x, int j0, int n) {
     uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -145,28 +140,53 @@ __device__ __forceinline__ void mask_tail(uint4 &x, int j0, int n) {
     x = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// ---- A (dp4a variant): one-hot byte masks of the slot word, dot products into registers --------
-// FULL = the relation has no missing cell: every byte is 0 or 1, the per-table observation counts follow
-// from the CRP table sizes, and only the counts of ones (rs, cs) are accumulated.
-template <int KD, bool FULL>
-__device__ __forceinline__ void acc_word(uint32_t xr, uint32_t xc, uint32_t z, int (&rn)[KD], int (&rs)[KD], int (&cn)[KD], int (&cs)[KD]) {
-    constexpr uint32_t ONES = 0x01010101u;
-    uint32_t vr = 0u, vc = 0u, sr = xr, sc = xc;
-    if (!FULL) {
-        vr = (~xr >> 7) & ONES; vc = (~xc >> 7) & ONES;    // observed?
-        sr = xr & vr; sc = xc & vc;                        // observed and 1
-    }
-    const uint32_t b0 = z & ONES, b1 = (z >> 1) & ONES, b2 = (z >> 2) & ONES;
+// ---- z as bit planes ---------------------------------------------------------------------------------
+// The slot of every entity is kept in shared memory as NP bit planes, 32 entities per word:
+// zp[g * NP + p] bit b = bit p of the slot of entity 32 g + b.  A live table's members are then a mask
+// (an AND over the planes), and "how many of row i's ones fall into table k" is a popcount.
+__device__ __forceinline__ int planes_get(const uint32_t *zp, int NP, int item) {
+    const uint32_t *w = zp + (item >> 5) * NP;
+    int slot = 0;
+    for (int p = 0; p < NP; p++) slot |= (int)((w[p] >> (item & 31)) & 1u) << p;
+    return slot;
+}
+__device__ __forceinline__ void planes_set(uint32_t *zp, int NP, int item, int slot) {
+    uint32_t *w = zp + (item >> 5) * NP;
+    const uint32_t bit = 1u << (item & 31);
+    for (int p = 0; p < NP; p++) w[p] = ((slot >> p) & 1) ? (w[p] | bit) : (w[p] & ~bit);
+}
+// members of slot k among the 32 entities of a group, from its plane words P[0..NPL)
+template <int NPL>
+__device__ __forceinline__ uint32_t planes_mask(const uint32_t (&P)[NPL], int k) {
+    uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
-    for (int k = 0; k < KD; k++) {
-        uint32_t mk = (k & 1) ? b0 : (b0 ^ ONES);
-        if (KD > 2) mk &= (k & 2) ? b1 : (b1 ^ ONES);
-        if (KD > 4) mk &= (k & 4) ? b2 : (b2 ^ ONES);
-        if (!FULL) { rn[k] = (int)__dp4a(mk, vr, (unsigned)rn[k]); cn[k] = (int)__dp4a(mk, vc, (unsigned)cn[k]); }
-        rs[k] = (int)__dp4a(mk, sr, (unsigned)rs[k]);
-        cs[k] = (int)__dp4a(mk, sc, (unsigned)cs[k]);
+    for (int p = 0; p < NPL; p++) m &= ((k >> p) & 1) ? P[p] : ~P[p];
+    return m;
+}
+// every entity in slot `from` moves to slot `to` (slot compaction when a table died)
+__device__ __forceinline__ void planes_rename(uint32_t *zp, int NP, int G, int from, int to, int t, int nt) {
+    #pragma unroll 1
+    for (int g = t; g < G; g += nt) {
+        uint32_t *w = zp + g * NP;
+        uint32_t m = 0xFFFFFFFFu;
+        for (int p = 0; p < NP; p++) m &= ((from >> p) & 1) ? w[p] : ~w[p];
+        if (m) for (int p = 0; p < NP; p++) w[p] = ((to >> p) & 1) ? (w[p] | m) : (w[p] & ~m);
     }
 }
+
+// 32 observation bytes (two uint4: elements 0..15 and 16..31, each byte 0 or 1) -> 32 bits.  dp4a with the
+// weights 1, 2, 4, 8 / 16, 32, 64, 128 turns eight bytes into one byte of bits.
+__device__ __forceinline__ uint32_t pack32(const uint4 &lo, const uint4 &hi) {
+    constexpr uint32_t W0 = 0x08040201u, W1 = 0x80402010u;
+    const uint32_t b0 = __dp4a(lo.y, W1, __dp4a(lo.x, W0, 0u)), b1 = __dp4a(lo.w, W1, __dp4a(lo.z, W0, 0u));
+    const uint32_t b2 = __dp4a(hi.y, W1, __dp4a(hi.x, W0, 0u)), b3 = __dp4a(hi.w, W1, __dp4a(hi.z, W0, 0u));
+    return (b0 | (b1 << 8)) | ((b2 | (b3 << 8)) << 16);
+}
+__device__ __forceinline__ uint4 valid_bytes(const uint4 &x) {     // 1 where the byte is an observation (< 0x80)
+    constexpr uint32_t ONES = 0x01010101u;
+    return make_uint4((~x.x >> 7) & ONES, (~x.y >> 7) & ONES, (~x.z >> 7) & ONES, (~x.w >> 7) & ONES);
+}
+__device__ __forceinline__ uint4 and4(const uint4 &a, const uint4 &b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
 
 // ring cursor shared by the producer and the A warps (each keeps its own copy)
 struct RingCursor {
@@ -178,6 +198,11 @@ struct RingCursor {
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
@@ -202,24 +227,9 @@ __device__ __forceinline__ bool mbar_try_wait_hint_s(uint32_t bar, uint32_t pari
         "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(ns) : "memory");
     return done != 0;
 }
-// same, for waits with slack (the A warps' go, the producer's empty): sleep between polls so that the
-// spinning does not take issue slots from the decision warps
+// for waits with slack (the A warps' go, the producer's empty): suspended in hardware, no issue slots taken
 __device__ __forceinline__ void mbar_wait_relaxed_s(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    for (;;) {
-        done = mbar_try_wait_hint_s(bar, parity, 20000u) ? 1u : 0u;
-        if (done) break;
-    }
-}
-__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done != 0;
+    while (!mbar_try_wait_hint_s(bar, parity, 20000u)) { }
 }
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -227,22 +237,39 @@ __device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
 
 // What an A thread needs to stream a move (all by value, shared-space addresses)
 struct APar {
-    uint32_t full, empty, ring, zs;    // shared addresses: full[0], empty[0], ring, zs
-    int n, npad, chunk, nchunks, stages, bins_words;
+    uint32_t full, empty, ring, zp;    // shared addresses: full[0], empty[0], ring, the bit planes
+    int n, npad, chunk, nchunks, stages, np;
 };
 
-template <int KD, bool FULL>
-__device__ __forceinline__ void acc_vec(const uint4 &xr, const uint4 &xc, const uint4 &zz, int (&rn)[KD], int (&rs)[KD], int (&cn)[KD], int (&cs)[KD]) {
-    acc_word<KD, FULL>(xr.x, xc.x, zz.x, rn, rs, cn, cs);
-    acc_word<KD, FULL>(xr.y, xc.y, zz.y, rn, rs, cn, cs);
-    acc_word<KD, FULL>(xr.z, xc.z, zz.z, rn, rs, cn, cs);
-    acc_word<KD, FULL>(xr.w, xc.w, zz.w, rn, rs, cn, cs);
-}
+// One group of 32 elements: the row's / column's bits (and, unless the relation is fully observed, the
+// "observed" bits) and the NPL plane words of the group.
+template <bool FULL, int NPL>
+struct Group32 {
+    uint32_t sr, sc, vr, vc, P[NPL];
+    __device__ __forceinline__ void load(const APar &p, uint32_t xrow, uint32_t xcol, int base, int g, bool tail) {
+        uint4 r0 = lds128(xrow + 32u * g), r1 = lds128(xrow + 32u * g + 16u);
+        uint4 c0 = lds128(xcol + 32u * g), c1 = lds128(xcol + 32u * g + 16u);
+        const uint32_t pw = p.zp + 4u * (uint32_t)(((base >> 5) + g) * p.np);
+#pragma unroll
+        for (int q = 0; q < NPL; q++) P[q] = lds32(pw + 4u * q);
+        if (tail) {
+            const int j0 = base + 32 * g;
+            mask_tail<FULL>(r0, j0, p.n); mask_tail<FULL>(r1, j0 + 16, p.n);
+            mask_tail<FULL>(c0, j0, p.n); mask_tail<FULL>(c1, j0 + 16, p.n);
+        }
+        if (FULL) {
+            sr = pack32(r0, r1); sc = pack32(c0, c1); vr = 0u; vc = 0u;
+        } else {
+            const uint4 a0 = valid_bytes(r0), a1 = valid_bytes(r1), b0 = valid_bytes(c0), b1 = valid_bytes(c1);
+            vr = pack32(a0, a1); vc = pack32(b0, b1);
+            sr = pack32(and4(r0, a0), and4(r1, a1)); sc = pack32(and4(c0, b0), and4(c1, b1));
+        }
+    }
+};
 
-// One move on the dp4a path: stream the two rows through the ring, two 16-element vectors per thread in
-// flight, group sums in registers; per-warp sums to wp[4k..4k+3].
-template <int KD, bool FULL>
-__device__ __forceinline__ void a_move_dp4a(const APar p, RingCursor &cur, const int a, const int lane, int32_t *wp) {
+// One move with at most KD live tables: group sums in registers; per-warp sums to wp[4k..4k+3].
+template <int KD, int NPL, bool FULL>
+__device__ __forceinline__ void a_move_regs(const APar p, RingCursor &cur, const int a, const int lane, int32_t *wp) {
     int rn[KD], rs[KD], cn[KD], cs[KD];
 #pragma unroll
     for (int k = 0; k < KD; k++) { rn[k] = 0; rs[k] = 0; cn[k] = 0; cs[k] = 0; }
@@ -250,25 +277,20 @@ __device__ __forceinline__ void a_move_dp4a(const APar p, RingCursor &cur, const
     for (int q = 0; q < p.nchunks; q++) {
         const int base = q * p.chunk;
         const int bytes = min(p.chunk, p.npad - base);
-        const uint32_t xrow = p.ring + (uint32_t)(cur.stage * 2 * p.chunk), xcol = xrow + (uint32_t)p.chunk, zrow = p.zs + (uint32_t)base;
-        const int nv = bytes >> 4;
-        const bool tail = base + bytes > p.n;          // the row's padding lies in this chunk (uniform)
+        const uint32_t xrow = p.ring + (uint32_t)(cur.stage * 2 * p.chunk), xcol = xrow + (uint32_t)p.chunk;
+        const int ng = (bytes + 31) >> 5;
+        const bool tail = base + 32 * ng > p.n;        // the row's padding lies in this chunk (uniform)
         mbar_wait_s(p.full + 8u * cur.stage, cur.parity);
         #pragma unroll 1
-        for (int v = a; v < nv; v += 2 * DN_NA) {
-            const int v2 = v + DN_NA;
-            const bool two = v2 < nv;
-            uint4 xr0 = lds128(xrow + 16u * v), xc0 = lds128(xcol + 16u * v);
-            const uint4 zz0 = lds128(zrow + 16u * v);
-            constexpr uint32_t PAD = FULL ? 0u : ~0u;           // a byte that contributes nothing
-            uint4 xr1 = make_uint4(PAD, PAD, PAD, PAD), xc1 = xr1, zz1 = make_uint4(0u, 0u, 0u, 0u);
-            if (two) { xr1 = lds128(xrow + 16u * v2); xc1 = lds128(xcol + 16u * v2); zz1 = lds128(zrow + 16u * v2); }
-            if (tail) {
-                mask_tail<FULL>(xr0, base + 16 * v, p.n); mask_tail<FULL>(xc0, base + 16 * v, p.n);
-                mask_tail<FULL>(xr1, base + 16 * v2, p.n); mask_tail<FULL>(xc1, base + 16 * v2, p.n);
+        for (int g = a; g < ng; g += DN_NA) {
+            Group32<FULL, NPL> G;
+            G.load(p, xrow, xcol, base, g, tail);
+#pragma unroll
+            for (int k = 0; k < KD; k++) {
+                const uint32_t m = planes_mask<NPL>(G.P, k);
+                rs[k] += __popc(G.sr & m); cs[k] += __popc(G.sc & m);
+                if (!FULL) { rn[k] += __popc(G.vr & m); cn[k] += __popc(G.vc & m); }
             }
-            acc_vec<KD, FULL>(xr0, xc0, zz0, rn, rs, cn, cs);
-            acc_vec<KD, FULL>(xr1, xc1, zz1, rn, rs, cn, cs);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_s(p.empty + 8u * cur.stage);
@@ -285,64 +307,58 @@ __device__ __forceinline__ void a_move_dp4a(const APar p, RingCursor &cur, const
     }
 }
 
-// this warp's private bins -> += wp[4k..4k+3] for every slot, bins zeroed again
-__device__ __forceinline__ void a_flush_bins(uint32_t *bins, int HT, int K, int a, int lane, int32_t *wp) {
-    __syncwarp();
-    if (a - lane >= HT) return;                       // this warp bins nothing (warp-uniform)
+// One move with more than 8 live tables: per-thread private accumulators in shared memory,
+// acc[(k * F + f) * DN_NA + a] with 16-bit fields (rs | cs << 16, and rn | cn << 16 unless FULL).
+template <int NPL, bool FULL>
+__device__ __forceinline__ void a_move_acc(const APar p, RingCursor &cur, const int a, const int lane, uint32_t *acc, const int K, int32_t *wp) {
+    constexpr int F = FULL ? 1 : 2;
+    uint32_t *mine = acc + a;
     #pragma unroll 1
-    for (int k = 0; k < K; k++) {
-        uint32_t wv = 0u;
-        if (a < HT) { wv = bins[k * HT + a]; bins[k * HT + a] = 0u; }
-        const int s0 = __reduce_add_sync(0xffffffffu, (int)(wv & 0xFFu)), s1 = __reduce_add_sync(0xffffffffu, (int)((wv >> 8) & 0xFFu));
-        const int s2 = __reduce_add_sync(0xffffffffu, (int)((wv >> 16) & 0xFFu)), s3 = __reduce_add_sync(0xffffffffu, (int)(wv >> 24));
-        if (lane < 4) wp[4 * k + lane] += lane == 0 ? s0 : lane == 1 ? s1 : lane == 2 ? s2 : s3;
-    }
-    __syncwarp();
-}
-
-// One move on the bins path (more than 8 live tables): bins[slot][thread], 4 x 8-bit fields, flushed into
-// wp before any field can overflow.
-__device__ __forceinline__ void a_move_bins(const APar p, RingCursor &cur, const int a, const int lane, uint32_t *bins, const int K, int32_t *wp) {
-    const int HT = min(DN_NA, (p.bins_words / K) & ~31);
-    #pragma unroll 1
-    for (int idx = lane; idx < 4 * K; idx += 32) wp[idx] = 0;
-    __syncwarp();
-    uint32_t *mine = bins + a;
-    int since = 0;                                    // vectors binned by this thread since the last flush
+    for (int k = 0; k < K * F; k++) mine[k * DN_NA] = 0u;
     #pragma unroll 1
     for (int q = 0; q < p.nchunks; q++) {
         const int base = q * p.chunk;
         const int bytes = min(p.chunk, p.npad - base);
-        const uint32_t xrow = p.ring + (uint32_t)(cur.stage * 2 * p.chunk), xcol = xrow + (uint32_t)p.chunk, zrow = p.zs + (uint32_t)base;
-        const int nv = bytes >> 4;
-        const int per_thread = (nv + HT - 1) / HT;
-        if (since + per_thread > DN_FLUSH_VECS) { a_flush_bins(bins, HT, K, a, lane, wp); since = 0; }
-        since += per_thread;
+        const uint32_t xrow = p.ring + (uint32_t)(cur.stage * 2 * p.chunk), xcol = xrow + (uint32_t)p.chunk;
+        const int ng = (bytes + 31) >> 5;
+        const bool tail = base + 32 * ng > p.n;
         mbar_wait_s(p.full + 8u * cur.stage, cur.parity);
-        if (a < HT) {
-            #pragma unroll 1
-            for (int v = a; v < nv; v += HT) {
-                uint4 xr = lds128(xrow + 16u * v), xc = lds128(xcol + 16u * v);
-                const uint4 zz = lds128(zrow + 16u * v);
-                const int j0 = base + v * 16;
-                if (j0 + 16 > p.n) { mask_tail(xr, j0, p.n); mask_tail(xc, j0, p.n); }
-                const uint32_t xrw[4] = {xr.x, xr.y, xr.z, xr.w}, xcw[4] = {xc.x, xc.y, xc.z, xc.w}, zw[4] = {zz.x, zz.y, zz.z, zz.w};
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const uint32_t codes = pack_codes(xrw[w], xcw[w]);
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const uint32_t slot = (zw[w] >> (8 * e)) & 0xFFu;
-                        mine[slot * HT] += code_to_inc((codes >> (8 * e)) & 0xFu);
-                    }
-                }
+        #pragma unroll 1
+        for (int g = a; g < ng; g += DN_NA) {
+            Group32<FULL, NPL> G;
+            G.load(p, xrow, xcol, base, g, tail);
+            #pragma unroll 2
+            for (int k = 0; k < K; k++) {
+                const uint32_t m = planes_mask<NPL>(G.P, k);
+                mine[(k * F) * DN_NA] += (uint32_t)__popc(G.sr & m) | ((uint32_t)__popc(G.sc & m) << 16);
+                if (!FULL) mine[(k * F + 1) * DN_NA] += (uint32_t)__popc(G.vr & m) | ((uint32_t)__popc(G.vc & m) << 16);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_s(p.empty + 8u * cur.stage);
         cur.advance(p.stages);
     }
-    a_flush_bins(bins, HT, K, a, lane, wp);
+    #pragma unroll 1
+    for (int k = 0; k < K; k++) {                          // this warp's 32 private accumulators -> wp
+        const uint32_t w0 = mine[(k * F) * DN_NA];
+        const int s1 = __reduce_add_sync(0xffffffffu, (int)(w0 & 0xFFFFu)), s3 = __reduce_add_sync(0xffffffffu, (int)(w0 >> 16));
+        if (lane == 0) { wp[4 * k + 1] = s1; wp[4 * k + 3] = s3; }
+        if (!FULL) {
+            const uint32_t w1 = mine[(k * F + 1) * DN_NA];
+            const int s0 = __reduce_add_sync(0xffffffffu, (int)(w1 & 0xFFFFu)), s2 = __reduce_add_sync(0xffffffffu, (int)(w1 >> 16));
+            if (lane == 0) { wp[4 * k] = s0; wp[4 * k + 2] = s2; }
+        }
+    }
+}
+
+template <bool FULL>
+__device__ __forceinline__ void a_move(const APar p, RingCursor &cur, const int a, const int lane, uint32_t *acc, const int K, int32_t *wp) {
+    if (K <= 2) a_move_regs<2, 1, FULL>(p, cur, a, lane, wp);
+    else if (K <= 4) a_move_regs<4, 2, FULL>(p, cur, a, lane, wp);
+    else if (K <= 8) a_move_regs<8, 3, FULL>(p, cur, a, lane, wp);
+    else if (K <= 16) a_move_acc<4, FULL>(p, cur, a, lane, acc, K, wp);
+    else if (K <= 32) a_move_acc<5, FULL>(p, cur, a, lane, acc, K, wp);
+    else a_move_acc<6, FULL>(p, cur, a, lane, acc, K, wp);
 }
 
 __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArgs args, const int32_t *blk_list, DenseLaunch L) {
@@ -357,7 +373,7 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
     int32_t *const z_g = dd.z;
     const int kcap_g = dd.kcap;
     const double alpha = dd.alpha;
-    const bool full_obs = R.full_obs != 0;
+    const bool full = L.full != 0;                  // host: the relation has no missing cell and no entity is absent
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = L.n, npad = L.npad, kt = L.kt, NS = L.stages;
 
@@ -371,11 +387,12 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
     double *s_logcnt = reinterpret_cast<double *>(smem + L.off_dbl);                                         // log(count) per slot
     double *s_logcntm1 = s_logcnt + (kt + 2);                                    // log(count - 1) per slot
     int32_t *wpart = reinterpret_cast<int32_t *>(smem + L.off_wpart);            // [2][A_WARPS][4*kt] per-warp group sums
-    uint32_t *bins = reinterpret_cast<uint32_t *>(smem + L.off_bins);            // [bins_words]
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem + L.off_acc);              // [F*kt][DN_NA] (kt > 8 only)
     int32_t *g_buf = reinterpret_cast<int32_t *>(smem + L.off_ints);             // [2][D warps][4*kt]: (rn, rs, cn, cs) per other-slot, one copy per D warp
     int32_t *s_cnt = g_buf + 2 * DN_D_WARPS * 4 * kt, *s_lab = s_cnt + kt;                        // CRP table sizes / labels per slot
     int32_t *s_order = s_lab + kt, *s_map = s_order + kt;                        // slots by ascending label; load-time slot map
-    uint8_t *zs = smem + L.off_zs;                                               // [npad] slot of every entity
+    uint32_t *zp = reinterpret_cast<uint32_t *>(smem + L.off_zp);                // [G][np] bit planes of the slot of every entity
+    const int NP = L.np, G = (n + 31) >> 5;
     uint8_t *ring = smem + L.off_ring;                                           // [NS][2][chunk]
     __shared__ int32_t s_K, s_KA;
     __shared__ MoveCtl s_ctl[DN_CTL];
@@ -418,17 +435,21 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
     #pragma unroll 1
     for (int k = tid; k < kt * kt; k += DN_THREADS) table[k] = 0;
     #pragma unroll 1
-    for (int k = tid; k < L.bins_words; k += DN_THREADS) bins[k] = 0u;
-    #pragma unroll 1
     for (int k = tid; k < DN_LF; k += DN_THREADS) s_lf[k] = g_logfact[k];
     __syncthreads();
     const int K0 = s_K;
     if (K0 > kt) return;                                       // more live tables than this tier holds: left to the next tier
     #pragma unroll 1
-    for (int j = tid; j < npad; j += DN_THREADS) {
+    for (int g = warp; g < G; g += DN_THREADS / 32) {          // a warp turns 32 assignments into one word per plane
+        const int j = 32 * g + lane;
         const int zj = j < n ? z_g[j] : 0;
         if (zj < 0) s_has_absent = 1;                          // rare: moves must then be checked against z = -1
-        zs[j] = zj >= 0 ? (uint8_t)s_map[zj] : (uint8_t)0;     // an absent entity has only missing observations
+        const int slot = zj >= 0 ? s_map[zj] : 0;              // an absent entity has only missing observations
+        #pragma unroll 1
+        for (int p = 0; p < NP; p++) {
+            const uint32_t w = __ballot_sync(0xffffffffu, (slot >> p) & 1);
+            if (lane == 0) zp[g * NP + p] = w;
+        }
     }
     #pragma unroll 1
     for (int k = tid; k < hi_g * hi_g; k += DN_THREADS) {
@@ -521,11 +542,10 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
     } else if (warp <= DN_A_WARPS) {
         // =============================== A: accumulate =====================================
         APar ap;
-        ap.full = smem_u32(bar_full); ap.empty = smem_u32(bar_empty); ap.ring = smem_u32(ring); ap.zs = smem_u32(zs);
-        ap.n = n; ap.npad = npad; ap.chunk = L.chunk; ap.nchunks = L.nchunks; ap.stages = NS; ap.bins_words = L.bins_words;
+        ap.full = smem_u32(bar_full); ap.empty = smem_u32(bar_empty); ap.ring = smem_u32(ring); ap.zp = smem_u32(zp);
+        ap.n = n; ap.npad = npad; ap.chunk = L.chunk; ap.nchunks = L.nchunks; ap.stages = NS; ap.np = NP;
         const int a = tid - 32, aw = warp - 1;
         const uint32_t go_s = smem_u32(bar_go), ready_s = smem_u32(bar_ready);
-        const bool full = full_obs && s_has_absent == 0;
         RingCursor cur{0, 0u};
         const bool prof = args.phase_cycles != nullptr && a == 0;
         long long a_go = 0, a_t0 = prof ? clk() : 0;
@@ -541,16 +561,8 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
             if (prof) a_go += clk() - w0;
             if (r >= *limit) break;                           // the chain stops before this move (tier overflow)
             const int KA = s_KA;
-            if (KA > DN_MAX_KD) a_move_bins(ap, cur, a, lane, bins, KA, wp);
-            else if (full) {
-                if (KA <= 2) a_move_dp4a<2, true>(ap, cur, a, lane, wp);
-                else if (KA <= 4) a_move_dp4a<4, true>(ap, cur, a, lane, wp);
-                else a_move_dp4a<8, true>(ap, cur, a, lane, wp);
-            } else {
-                if (KA <= 2) a_move_dp4a<2, false>(ap, cur, a, lane, wp);
-                else if (KA <= 4) a_move_dp4a<4, false>(ap, cur, a, lane, wp);
-                else a_move_dp4a<8, false>(ap, cur, a, lane, wp);
-            }
+            if (full) a_move<true>(ap, cur, a, lane, acc, KA, wp);
+            else a_move<false>(ap, cur, a, lane, acc, KA, wp);
             consumed += L.nchunks;
             __syncwarp();
             if (lane == 0) mbar_arrive_s(ready_s + 8u * buf);
@@ -565,7 +577,6 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
         int K = K0;                                            // live slots 0..K-1 (uniform across D threads)
         int KA_prev = K0;                                      // K the A warps used for the move being decided
         bool pend_changed = false; int pend_item = -1, pend_old = 0, pend_new = 0, pend_dead = -1;
-        const bool full = full_obs && s_has_absent == 0;
         if (d == 0) mbar_arrive(bar_go);                       // move 0 may be accumulated
         const bool prof = args.phase_cycles != nullptr && d == 0;
         long long tl = prof ? clk() : 0;
@@ -588,10 +599,10 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
             const uint32_t xb_ri = ctl.bytes & 0xFFu, xb_rp = (ctl.bytes >> 8) & 0xFFu, xb_cp = (ctl.bytes >> 16) & 0xFFu;
             // ---- finish move r-1: z[i_{r-1}] becomes visible, its observation pair changes group ----
             if (d == 0) {
-                if (pend_changed) zs[pend_item] = (uint8_t)pend_new;
+                if (pend_changed) planes_set(zp, NP, pend_item, pend_new);
                 if (pend_dead < 0) { s_KA = K; mbar_arrive(bar_go); }   // z is final: the A warps may accumulate move r+1
             }
-            int c = bad ? 0 : ((pend_changed && item == pend_item) ? pend_new : (int)zs[item]);
+            int c = bad ? 0 : ((pend_changed && item == pend_item) ? pend_new : planes_get(zp, NP, item));
             const int d_n = bad ? 0 : byte_n(xb_ri), d_s = bad ? 0 : byte_s(xb_ri);   // the diagonal (i, i): ONE observation
             {
                 const int KG = min(K + 1, kt);                 // slot K: the fresh table (empty groups)
@@ -624,18 +635,7 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
                 // ---- the table that died in move r-1 is replaced by the last slot ------------------
                 const int dead = pend_dead, last = K - 1;
                 if (dead != last) {
-                    #pragma unroll 1
-                    for (int v = d; v < (npad >> 4); v += DN_ND) {
-                        uint4 zz = *reinterpret_cast<uint4 *>(zs + (size_t)v * 16);
-                        uint32_t w[4] = {zz.x, zz.y, zz.z, zz.w};
-                        bool any = false;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const uint32_t eq = __vcmpeq4(w[q], (uint32_t)last * 0x01010101u);
-                            if (eq) { w[q] = (w[q] & ~eq) | (((uint32_t)dead * 0x01010101u) & eq); any = true; }
-                        }
-                        if (any) *reinterpret_cast<uint4 *>(zs + (size_t)v * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
+                    planes_rename(zp, NP, G, last, dead, d, DN_ND);
                     // row/column `last` -> `dead` (row/column `dead` is all zero)
                     #pragma unroll 1
                     for (int k = d; k < K; k += DN_ND) {
@@ -882,13 +882,12 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
 #undef DPHASE
         // ---- finish the last move -----------------------------------------------------------------
         bar_d();
-        if (pend_changed && d == 0) zs[pend_item] = (uint8_t)pend_new;
+        if (pend_changed && d == 0) planes_set(zp, NP, pend_item, pend_new);
         bar_d();
         if (pend_dead >= 0) {
             const int dead = pend_dead, last = K - 1;
             if (dead != last) {
-                #pragma unroll 1
-                for (int j = d; j < n; j += DN_ND) if (zs[j] == last) zs[j] = (uint8_t)dead;
+                planes_rename(zp, NP, G, last, dead, d, DN_ND);
                 #pragma unroll 1
                 for (int k = d; k < K; k += DN_ND) {
                     if (k != last && k != dead) {
@@ -918,7 +917,7 @@ __global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArg
     // ---- store state (slots 0..K-1, compact) ------------------------------------------------
     const int Kf = s_K;
     #pragma unroll 1
-    for (int j = tid; j < n; j += DN_THREADS) if (z_g[j] >= 0) z_g[j] = zs[j];
+    for (int j = tid; j < n; j += DN_THREADS) if (z_g[j] >= 0) z_g[j] = planes_get(zp, NP, j);
     const int span = max(hi_g, Kf);
     #pragma unroll 1
     for (int k = tid; k < span * span; k += DN_THREADS) {

@@ -728,25 +728,23 @@ extern "C" int hirm_irm_set_rng(hirm_engine *e, int32_t id, uint64_t stream, uin
 // ---------------------------------------------------------------------------------------
 struct Plan {
     std::vector<int32_t> generic_blk, dense_blk;
-    DenseLaunch L{};      // dense tier A: a small shared-memory table, more chains per SM
-    DenseLaunch LB{};     // dense tier B: all max_tables slots, resumes the chains tier A had to stop (stages == 0: not needed)
+    std::vector<DenseLaunch> tiers;   // dense: shared-memory tiers, smallest table first; the last one holds all max_tables slots
     int n_ent = 0, kcap = 0;
 };
 
 // Shared-memory plan of one dense tier: as many chains per SM as the launch has (up to 4) and fit; the rest of
 // each CTA's share of the SM's shared memory goes to its TMA ring.
-static bool plan_dense_tier(hirm_engine *e, int n, int kt, int n_dense, DenseLaunch &L) {
-    const int bins_words = std::min(4096, std::max(32 * DN_A_WARPS * 16, 32 * kt));
-    int chunk = 2 * 16 * DN_NA, want = std::min(4, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
-    if (const char *s = getenv("HIRM_DENSE_CHUNK")) chunk = std::max(16, atoi(s) & ~15);
+static bool plan_dense_tier(hirm_engine *e, int n, int kt, int kcap, int full, int n_dense, DenseLaunch &L) {
+    int chunk = 64 * DN_NA, want = std::min(4, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
+    if (const char *s = getenv("HIRM_DENSE_CHUNK")) chunk = std::max(32, atoi(s) & ~31);
     if (const char *s = getenv("HIRM_DENSE_CTAS_PER_SM")) want = std::max(1, atoi(s));
     L = DenseLaunch{};
     for (; want >= 1; want--) {
         const int budget = std::min(e->max_smem_optin, e->smem_per_sm / want - 1024) - e->dense_static_smem;   // 1 KiB reserved per CTA + the kernel's static shared memory
-        const DenseLaunch L0 = dense_layout(n, kt, chunk, 0, bins_words);
+        const DenseLaunch L0 = dense_layout(n, kt, kcap, full, chunk, 0);
         int stages = (budget - L0.total_bytes) / (2 * L0.chunk);
         stages = std::min(stages, std::min(DN_MAX_STAGES, 2 * L0.nchunks + 2));
-        if (stages >= 2 || (want == 1 && stages >= 1)) { L = dense_layout(n, kt, chunk, stages, bins_words); return true; }
+        if (stages >= 2 || (want == 1 && stages >= 1)) { L = dense_layout(n, kt, kcap, full, chunk, stages); return true; }
     }
     return false;
 }
@@ -760,15 +758,24 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
         if (ensure_counts(e, h_irms[k])) return -1;
         if (irm->dense_ree && !(flags & HIRM_SWEEP_FORCE_GENERIC)) {
             if (!have_dense) {
-                int n_dense = 0;
-                for (int j = 0; j < n_irms; j++) { Irm *o = get_irm(e, h_irms[j]); if (o && o->dense_ree) n_dense++; }
+                int n_dense = 0, full = 1;
+                for (int j = 0; j < n_irms; j++) {
+                    Irm *o = get_irm(e, h_irms[j]);
+                    if (!o || !o->dense_ree) continue;
+                    n_dense++;
+                    if (o->obs->rel[0].full_obs <= 0 || o->has_absent[0]) full = 0;   // one launch, one counting scheme
+                }
                 const int kcap = irm->kcap[0];
-                int kt_a = std::min(kcap, 32);
-                if (const char *s = getenv("HIRM_DENSE_TIER_SLOTS")) kt_a = std::min(kcap, std::max(2, atoi(s)));
-                if (!plan_dense_tier(e, irm->n_ent[0], kcap, n_dense, plan.LB))
+                std::vector<int> kts = {8, 32};
+                if (const char *s = getenv("HIRM_DENSE_TIER_SLOTS")) kts = {std::max(2, atoi(s))};
+                for (int kt : kts) {
+                    DenseLaunch L;
+                    if (kt < kcap && plan_dense_tier(e, irm->n_ent[0], kt, kcap, full, n_dense, L)) plan.tiers.push_back(L);
+                }
+                DenseLaunch LB;
+                if (!plan_dense_tier(e, irm->n_ent[0], kcap, kcap, full, n_dense, LB))
                     return fail("domain too large for the dense fast path's shared-memory state");
-                if (kt_a < kcap) plan_dense_tier(e, irm->n_ent[0], kt_a, n_dense, plan.L);
-                if (kt_a >= kcap || plan.L.stages < 1) { plan.L = plan.LB; plan.LB = DenseLaunch{}; }
+                plan.tiers.push_back(LB);
                 plan.n_ent = irm->n_ent[0]; plan.kcap = kcap; have_dense = true;
             } else if (irm->n_ent[0] != plan.n_ent || irm->kcap[0] != plan.kcap) {
                 return fail("dense irms of one sweep must share a shape");
@@ -794,24 +801,24 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
     if (!plan.dense_blk.empty()) {
         const unsigned nb = (unsigned)plan.dense_blk.size();
         SweepArgs a2 = args;
-        if (plan.LB.stages > 0) {                      // two tiers: per-chain progress hands the stopped chains over
+        if (plan.tiers.size() > 1) {                   // several tiers: per-chain progress hands the stopped chains over
             CK(e->s_progress.ensure(nb));
             CK(cudaMemsetAsync(e->s_progress.p, 0, nb * sizeof(long long), e->stream));
             a2.progress = e->s_progress.p;
         }
-        const int smem_max = std::max(plan.L.total_bytes, plan.LB.total_bytes);
+        int smem_max = 0;
+        for (const DenseLaunch &L : plan.tiers) smem_max = std::max(smem_max, L.total_bytes);
         CK(cudaFuncSetAttribute(dense_ree_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        dense_ree_sweep_kernel<<<nb, DN_THREADS, (size_t)plan.L.total_bytes, e->stream>>>(a2, e->s_blk.p + plan.generic_blk.size(), plan.L);
-        CK(cudaGetLastError());
-        e->last_launches++; e->last_kind = 1;
-        if (plan.LB.stages > 0) {
-            dense_ree_sweep_kernel<<<nb, DN_THREADS, (size_t)plan.LB.total_bytes, e->stream>>>(a2, e->s_blk.p + plan.generic_blk.size(), plan.LB);
+        for (const DenseLaunch &L : plan.tiers) {
+            dense_ree_sweep_kernel<<<nb, DN_THREADS, (size_t)L.total_bytes, e->stream>>>(a2, e->s_blk.p + plan.generic_blk.size(), L);
             CK(cudaGetLastError());
             e->last_launches++;
         }
+        e->last_kind = 1;
+        const DenseLaunch &L0 = plan.tiers.front();
         int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense_ree_sweep_kernel, DN_THREADS, (size_t)plan.L.total_bytes);
-        e->last_occupancy = occ; e->last_stages = plan.L.stages; e->last_chunk = plan.L.chunk; e->last_smem = plan.L.total_bytes;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense_ree_sweep_kernel, DN_THREADS, (size_t)L0.total_bytes);
+        e->last_occupancy = occ; e->last_stages = L0.stages; e->last_chunk = L0.chunk; e->last_smem = L0.total_bytes;
     }
     CK(cudaEventRecord(e->ev1, e->stream));
     return 0;
