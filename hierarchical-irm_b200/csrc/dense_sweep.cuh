@@ -361,7 +361,7 @@ __device__ __forceinline__ void a_move(const APar p, RingCursor &cur, const int 
     else a_move_acc<6, FULL>(p, cur, a, lane, acc, K, wp);
 }
 
-__global__ void __launch_bounds__(DN_THREADS, 4) dense_ree_sweep_kernel(SweepArgs args, const int32_t *blk_list, DenseLaunch L) {
+__global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArgs args, const int32_t *blk_list, DenseLaunch L) {
     const int k_list = blk_list ? blk_list[blockIdx.x] : blockIdx.x;
     const IrmDev &irm = args.irms[args.irm_ids[k_list]];
     const DomainDev &dd = irm.dom[0];

@@ -732,10 +732,10 @@ struct Plan {
     int n_ent = 0, kcap = 0;
 };
 
-// Shared-memory plan of one dense tier: as many chains per SM as the launch has (up to 4) and fit; the rest of
+// Shared-memory plan of one dense tier: as many chains per SM as the launch has (up to 5: the register budget) and fit; the rest of
 // each CTA's share of the SM's shared memory goes to its TMA ring.
 static bool plan_dense_tier(hirm_engine *e, int n, int kt, int kcap, int full, int n_dense, DenseLaunch &L) {
-    int chunk = 64 * DN_NA, want = std::min(4, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
+    int chunk = 64 * DN_NA, want = std::min(5, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
     if (const char *s = getenv("HIRM_DENSE_CHUNK")) chunk = std::max(32, atoi(s) & ~31);
     if (const char *s = getenv("HIRM_DENSE_CTAS_PER_SM")) want = std::max(1, atoi(s));
     L = DenseLaunch{};

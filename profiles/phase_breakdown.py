@@ -29,7 +29,7 @@ run(50, 2)
 if not os.environ.get('NOPHASE'): eng.debug_phase_cycles(buf.data_ptr())
 ms = run(M, 3)
 ph = buf.cpu().numpy().reshape(chains, 32).astype(np.float64) / M
-names = ['P total','P wait-empty','A total','A wait-go','-','-','-','-','D wait-ready','D fix+go','D score:bar','D sample:bar','D apply','D loop-top','D score:items','D score:shfl','D sample:max','D sample:exp','D sample:scan','D cand-setup','-','-','-','-','lf:pre','lf:log','lf:rcp+corr','lf:rcp2','lf:log1p','lf:post']
+names = ['P total','P wait-empty','A total','A wait-go','-','-','-','-','D wait-ready','D fix+go','D score','D sample','D apply','D loop-top','-','-','-','-','-','D cand-setup']
 print('n=%d chains=%d M=%d kernel_ms=%.3f us/move=%.3f' % (n, chains, M, ms, ms*1e3/M))
 print('cycles/move (mean over chains):')
 for i, nm in enumerate(names):
