@@ -91,6 +91,44 @@ __global__ void __launch_bounds__(64) transition_alpha_kernel(IrmDev *irms, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// K4: Relation::logp_score of relation (src irm, rel) under the domain partitions of OTHER IRMs -- what
+// HIRM::transition_cluster_assignment_relation computes for every candidate table by re-incorporating the
+// relation's data there (cxx/hirm.hh:859-866; src/hirm.py:497-505).  The count table of the relation under a
+// partition is a histogram, so nothing is moved: pass 1 bins the observations by the candidate's z arrays into a
+// scratch table, pass 2 sums BetaBernoulli::logp_score over the cells (fixed reduction tree).
+struct RelCand {
+    const int32_t *z[MAX_ARITY];   // candidate's slot array per position of the relation
+    int64_t stride[MAX_ARITY];     // scratch-table stride per position
+    cell_t *table;                 // scratch count table (zeroed), `ncells` cells
+    int64_t ncells;
+};
+__global__ void __launch_bounds__(AUX_THREADS) rel_hist_kernel(const int32_t *coo_ids, const uint8_t *coo_val, int64_t nobs, int arity,
+                                                               const RelCand *cands, int32_t *error) {
+    const RelCand &C = cands[blockIdx.y];
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < nobs; o += (int64_t)gridDim.x * blockDim.x) {
+        int64_t idx = 0; bool absent = false;
+        for (int p = 0; p < arity; p++) {
+            const int slot = C.z[p][coo_ids[o * arity + p]];
+            if (slot < 0) absent = true;
+            idx += (slot < 0 ? 0 : slot) * C.stride[p];
+        }
+        if (absent) { atomicCAS(error, 0, KERR_ABSENT_ENTITY); continue; }
+        atomicAdd(&C.table[idx], pack_cell(1u, coo_val[o]));
+    }
+}
+__global__ void __launch_bounds__(AUX_THREADS) rel_score_kernel(const RelCand *cands, double *out) {
+    const RelCand &C = cands[blockIdx.x];
+    __shared__ double s_part[AUX_THREADS / 32];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < C.ncells; i += blockDim.x) {
+        const cell_t c = C.table[i];
+        if (cell_n(c)) acc += cell_score(cell_n(c), cell_s(c));
+    }
+    const double total = block_sum(acc, s_part);
+    if (threadIdx.x == 0) out[blockIdx.x] = total;
+}
+
 __device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; }
 
 // Sweep order (the loops of cxx/hirm.cc:45-51 / IRM::transition_cluster_assignments_all, cxx/hirm.hh:590-596): for every

@@ -109,6 +109,7 @@ struct hirm_engine {
     DevBuf<uint64_t> s_stream, s_counter;
     DevBuf<long long> s_progress;
     DevBuf<double> s_alpha;
+    DevBuf<cell_t> s_reltab; DevBuf<RelCand> s_relcand; DevBuf<int32_t> s_relerr;
     DevBuf<uint64_t> s_sweep0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
@@ -714,6 +715,96 @@ extern "C" int hirm_irm_get_tables(hirm_engine *e, int32_t id, int dom, int32_t 
     std::sort(t.begin(), t.end());
     *n_tables = (int32_t)t.size();
     for (int k = 0; k < (int)t.size() && k < cap; k++) { if (h_labels) h_labels[k] = t[(size_t)k].first; if (h_counts) h_counts[k] = t[(size_t)k].second; }
+    return 0;
+}
+
+extern "C" int hirm_engine_relation_scores(hirm_engine *e, int32_t src, int rel, int n_cand, const int32_t *h_cand_irms,
+                                           const int32_t *h_cand_doms, double *h_out) {
+    GET_IRM(S, e, src);
+    if (rel < 0 || rel >= S->n_relations || n_cand < 0 || (n_cand > 0 && (!h_cand_irms || !h_cand_doms || !h_out))) return fail("bad argument");
+    if (n_cand == 0) return 0;
+    if (finalize_store(e, S)) return -1;
+    RelObs &R = S->obs->rel[rel];
+    if (R.kind != 0) return fail("relation scores under other partitions are built for CSR-stored relations only");
+    const int a = S->arity[rel];
+    std::vector<RelCand> cands((size_t)n_cand);
+    int64_t total_cells = 0;
+    for (int k = 0; k < n_cand; k++) {
+        Irm *C = get_irm(e, h_cand_irms[k]);
+        if (!C) return fail("bad candidate irm id");
+        RelCand &rc = cands[(size_t)k];
+        memset(&rc, 0, sizeof(rc));
+        int64_t stride = 1;
+        for (int p = 0; p < a; p++) {
+            const int d = h_cand_doms[k * MAX_ARITY + p];
+            if (d < 0 || d >= C->n_domains) return fail("candidate domain index out of range");
+            if (C->n_ent[d] < S->n_ent[S->rdom[rel][p]]) return fail("candidate domain has fewer entity codes than the relation's");
+            if (!C->have_z[d]) return fail("candidate irm without assignments");
+            rc.z[p] = C->z[d].p; rc.stride[p] = stride; stride *= C->kcap[d];
+        }
+        rc.ncells = stride; total_cells += stride;
+    }
+    CK(e->s_reltab.ensure((size_t)total_cells)); CK(e->s_relcand.ensure((size_t)n_cand)); CK(e->s_score.ensure((size_t)n_cand));
+    CK(e->s_relerr.ensure(1));
+    int64_t off = 0;
+    for (auto &rc : cands) { rc.table = e->s_reltab.p + off; off += rc.ncells; }
+    cudaStream_t s0 = e->stream;
+    CK(cudaMemsetAsync(e->s_reltab.p, 0, (size_t)total_cells * sizeof(cell_t), s0));
+    CK(cudaMemsetAsync(e->s_relerr.p, 0, sizeof(int32_t), s0));
+    CK(cudaMemcpyAsync(e->s_relcand.p, cands.data(), cands.size() * sizeof(RelCand), cudaMemcpyHostToDevice, s0));
+    if (R.nobs > 0) {
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((R.nobs + AUX_THREADS - 1) / AUX_THREADS, e->num_sms * 4)), (unsigned)n_cand);
+        rel_hist_kernel<<<grid, AUX_THREADS, 0, s0>>>(R.coo_ids.p, R.coo_val.p, R.nobs, a, e->s_relcand.p, e->s_relerr.p);
+        CK(cudaGetLastError());
+    }
+    rel_score_kernel<<<n_cand, AUX_THREADS, 0, s0>>>(e->s_relcand.p, e->s_score.p);
+    CK(cudaGetLastError());
+    int32_t err = 0;
+    CK(cudaMemcpyAsync(h_out, e->s_score.p, n_cand * sizeof(double), cudaMemcpyDeviceToHost, s0));
+    CK(cudaMemcpyAsync(&err, e->s_relerr.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    if (err) return fail(std::string("kernel error: ") + kerr_text(err) + " (seat the relation's entities in the candidate first: hirm_irm_seat_entities)");
+    return 0;
+}
+
+// Domain::incorporate(item, table) for entities that are not yet in the domain (cxx/hirm.hh:194-203): what
+// Relation::incorporate does to the domains of a candidate IRM when HIRM::transition_cluster_assignment_relation
+// tries a relation there (:859-864).  The entities have no observation in this IRM, so the count tables stand.
+extern "C" int hirm_irm_seat_entities(hirm_engine *e, int32_t id, int dom, int n, const int32_t *h_items, const int32_t *h_labels) {
+    GET_IRM(irm, e, id);
+    if (dom < 0 || dom >= irm->n_domains || n < 0 || (n > 0 && (!h_items || !h_labels))) return fail("bad argument");
+    if (!irm->have_z[dom]) return fail("set_assignments first");
+    if (n == 0) return 0;
+    const int ne = irm->n_ent[dom], kcap = irm->kcap[dom];
+    std::vector<int32_t> z((size_t)std::max(ne, 1)), cnt((size_t)kcap), lab((size_t)kcap);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(z.data(), irm->z[dom].p, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cnt.data(), irm->tab_count[dom].p, kcap * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lab.data(), irm->tab_label[dom].p, kcap * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    int32_t hi = 0;
+    CK(cudaMemcpy(&hi, irm->hi[dom].p, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; k++) {
+        const int it = h_items[k], lb = h_labels[k];
+        if (it < 0 || it >= ne || lb < 0) return fail("entity code or label out of range");
+        if (z[(size_t)it] >= 0) return fail("entity is already seated (Domain::incorporate asserts table is None)");
+        int slot = -1, free_slot = -1;
+        for (int s = 0; s < kcap; s++) {
+            if (cnt[(size_t)s] > 0 && lab[(size_t)s] == lb) { slot = s; break; }
+            if (cnt[(size_t)s] == 0 && free_slot < 0) free_slot = s;
+        }
+        if (slot < 0) {
+            if (free_slot < 0) return fail("more tables than max_tables");
+            slot = free_slot; lab[(size_t)slot] = lb;
+        }
+        cnt[(size_t)slot]++; z[(size_t)it] = slot; hi = std::max(hi, slot + 1);
+    }
+    CK(cudaMemcpy(irm->z[dom].p, z.data(), (size_t)ne * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(irm->tab_count[dom].p, cnt.data(), kcap * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(irm->tab_label[dom].p, lab.data(), kcap * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(irm->hi[dom].p, &hi, sizeof(int32_t), cudaMemcpyHostToDevice));
+    bool absent = false;
+    for (int i = 0; i < ne; i++) if (z[(size_t)i] < 0) absent = true;
+    irm->has_absent[dom] = absent;
     return 0;
 }
 

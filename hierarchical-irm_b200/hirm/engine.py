@@ -31,6 +31,7 @@ EXPORTS = [
     "hirm_engine_sweep_device", "hirm_engine_last_sweep_info", "hirm_engine_transpose_u8",
     "hirm_engine_debug_phase_cycles", "hirm_engine_last_dense_plan", "hirm_engine_sweep_all", "hirm_irm_set_rng",
     "hirm_engine_logp_scores", "hirm_engine_transition_alpha", "hirm_irm_get_alpha", "hirm_irm_get_tables",
+    "hirm_engine_relation_scores", "hirm_irm_seat_entities",
 ]
 
 _lib = None
@@ -88,6 +89,8 @@ def load():
     L.hirm_engine_transition_alpha.argtypes = [V, I, c_i32p, I, ctypes.c_uint64, c_f64p, c_f64p, c_f64p]
     L.hirm_irm_get_alpha.argtypes = [V, ctypes.c_int32, I, c_f64p]
     L.hirm_irm_get_tables.argtypes = [V, ctypes.c_int32, I, c_i32p, c_i32p, I, c_i32p]
+    L.hirm_engine_relation_scores.argtypes = [V, ctypes.c_int32, I, I, c_i32p, c_i32p, c_f64p]
+    L.hirm_irm_seat_entities.argtypes = [V, ctypes.c_int32, I, I, c_i32p, c_i32p]
     _lib = L
     return L
 
@@ -282,6 +285,22 @@ class Engine:
         lab = np.empty(cap, np.int32); cnt = np.empty(cap, np.int32); n = ctypes.c_int32()
         self._ck(self.L.hirm_irm_get_tables(self._h, irm, dom, _p(lab, c_i32p), _p(cnt, c_i32p), cap, ctypes.byref(n)))
         return lab[:n.value].copy(), cnt[:n.value].copy()
+
+    def relation_scores(self, src_irm, rel, cand_irms, cand_doms):
+        """Relation.logp_score of (src_irm, rel) under each candidate IRM's partitions; cand_doms[k] = the candidate's
+        domain index for every position of the relation."""
+        ci = np.ascontiguousarray(cand_irms, dtype=np.int32)
+        cd = np.zeros((max(len(ci), 1), MAX_ARITY), dtype=np.int32)
+        for k, ds in enumerate(cand_doms):
+            cd[k, :len(ds)] = ds
+        out = np.empty(max(len(ci), 1), np.float64)
+        self._ck(self.L.hirm_engine_relation_scores(self._h, src_irm, rel, len(ci), _p(ci, c_i32p), _p(cd, c_i32p), _p(out, c_f64p)))
+        return out[:len(ci)]
+
+    def seat_entities(self, irm, dom, items, labels):
+        it = np.ascontiguousarray(items, dtype=np.int32); lb = np.ascontiguousarray(labels, dtype=np.int32)
+        assert len(it) == len(lb)
+        self._ck(self.L.hirm_irm_seat_entities(self._h, irm, dom, len(it), _p(it, c_i32p), _p(lb, c_i32p)))
 
     def last_dense_plan(self):
         a, b, c, d = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()

@@ -10,7 +10,9 @@ What runs where
     transition_cluster_assignments / transition_cluster_assignment_item / transition_crp_alphas /
     logp_score are engine calls; there is no host implementation of the move;
   * crp.tables / crp.assignments / relation.clusters are read-back views, refreshed lazily.
-Out of scope: IRM.logp (predictive), HIRM relation moves, plotting.
+  * HIRM (src/hirm.py:457-571) keeps the relation CRP on the host and gets every candidate table's data term
+    from the device (hirm_engine_relation_scores).
+Out of scope: IRM.logp / HIRM.logp (predictive), plotting.
 """
 import random
 
@@ -72,14 +74,36 @@ class CRP:
         self._d._irm.transition_crp_alphas([self._d.name])
 
 
+class CodeSpace:
+    """entity -> int code by first appearance (cxx/util_io.cc:63-96).  One per domain name; an HIRM shares it
+    between its IRMs so that a relation's observations can be scored under any IRM's partition."""
+
+    def __init__(self):
+        self.codes, self.names = {}, []
+
+    def code(self, item):
+        c = self.codes.get(item)
+        if c is None:
+            c = self.codes[item] = len(self.names)
+            self.names.append(item)
+        return c
+
+
 class Domain:
-    def __init__(self, name, irm):
+    def __init__(self, name, irm, space=None):
         self.name, self._irm = name, irm
         self.items = set()
-        self._codes = {}          # entity -> int code, first appearance order (cxx/util_io.cc:63-96)
-        self._names = []
+        self._space = space or CodeSpace()
         self._z = {}              # entity -> table label (host mirror)
         self.crp = CRP(self)
+
+    @property
+    def _codes(self):
+        return self._space.codes
+
+    @property
+    def _names(self):
+        return self._space.names
 
     def incorporate(self, item, table=None):
         """Domain.incorporate (src/hirm.py:130-136): an unseen entity is seated by a CRP-prior draw."""
@@ -99,10 +123,14 @@ class Domain:
                 w = [sizes[t] for t in sizes] + [irm._alpha[self.name]]
                 table = irm.prng.choices(tabs, weights=w)[0]
         self.items.add(item)
-        self._codes[item] = len(self._names)
-        self._names.append(item)
+        grew = item not in self._space.codes
+        code = self._space.code(item)
         self._z[item] = int(table)
-        irm._dirty = True
+        if irm._h is not None and not irm._dirty and not grew and self.name in irm._dorder and code < irm._n_ent[irm._dorder.index(self.name)]:
+            # the entity has a code on the device already (absent so far): seat it there, the count tables stand
+            irm._eng.seat_entities(irm._h, irm._dorder.index(self.name), [code], [int(table)])
+        else:
+            irm._dirty = True
 
     def unincorporate(self, item):
         raise NotImplementedError()
@@ -158,9 +186,11 @@ class Relation:
 class IRM:
     """src/hirm.py:378-455 on the GPU engine.  `max_tables` bounds the tables per domain kept on the device."""
 
-    def __init__(self, schema, prng=None, engine=None, max_tables=None):
+    def __init__(self, schema, prng=None, engine=None, max_tables=None, spaces=None):
         self.schema, self.domains, self.relations, self.domain_to_relations = {}, {}, {}, {}
         self.prng = prng or random
+        self._spaces = spaces          # {domain name: CodeSpace} shared with other IRMs (HIRM), or None
+        self._dorder, self._n_ent = [], []
         self._eng = engine
         self._max_tables = max_tables
         self._alpha = {}
@@ -179,7 +209,7 @@ class IRM:
         self._pull()
         for d in domains:
             if d not in self.domains:
-                self.domains[d] = Domain(d, self)
+                self.domains[d] = Domain(d, self, None if self._spaces is None else self._spaces.setdefault(d, CodeSpace()))
                 self.domain_to_relations[d] = set()
                 self._alpha[d] = 1.0
             self.domain_to_relations[d].add(r)
@@ -213,8 +243,8 @@ class IRM:
         for k, d in enumerate(self._dorder):
             dom = self.domains[d]
             lab = self._eng.get_assignments(self._h, k)
-            for code, item in enumerate(dom._names[:len(lab)]):
-                dom._z[item] = int(lab[code])
+            for item in dom.items:
+                dom._z[item] = int(lab[dom._codes[item]])
             self._alpha[d] = self._eng.get_alpha(self._h, k)
         self._stale = False
 
@@ -236,7 +266,7 @@ class IRM:
         self._rorder = list(self.relations)
         self._rindex = {r: k for k, r in enumerate(self._rorder)}
         dindex = {d: k for k, d in enumerate(self._dorder)}
-        n_ent = [len(self.domains[d]._names) for d in self._dorder]
+        n_ent = self._n_ent = [len(self.domains[d]._names) for d in self._dorder]
         rel_domains = [[dindex[d.name] for d in self.relations[r].domains] for r in self._rorder]
         dense = self._dense_candidate()
         kcap = []
@@ -262,7 +292,7 @@ class IRM:
         self._eng.finalize(self._h)
         for k, d in enumerate(self._dorder):
             dom = self.domains[d]
-            self._eng.set_assignments(self._h, k, np.asarray([dom._z[it] for it in dom._names], dtype=np.int32))
+            self._eng.set_assignments(self._h, k, np.asarray([dom._z.get(it, -1) for it in dom._names], dtype=np.int32))
             self._eng.set_alpha(self._h, k, self._alpha[d])
         if self._seed is None:
             self._seed = self.prng.getrandbits(62)
@@ -275,20 +305,22 @@ class IRM:
             return False
         rel = next(iter(self.relations.values()))
         n = len(rel.domains[0]._names)
-        return len(rel.domains) == 2 and n >= 2 and len(rel.data) == n * n
+        return len(rel.domains) == 2 and n >= 2 and len(rel.data) == n * n and len(rel.domains[0].items) == n
 
     # ---- inference ---------------------------------------------------------------------------
     def transition_cluster_assignments(self, domains=None):
         """One sweep over the given domains (default: all), src/hirm.py:392-400.  The order of the moves is
         engine-defined (the reference's is the iteration order of a Python set)."""
         self._push()
+        if domains is None and any(len(self.domains[d].items) < n for d, n in zip(self._dorder, self._n_ent)):
+            domains = list(self._dorder)                         # some codes are not seated here: explicit lists
         if domains is None:
             self._moves += self._eng.sweep_all([self._h], n_sweeps=1, seed=self._seed)
         else:
             md, mi = [], []
             for d in domains:
                 k = self._dorder.index(d)
-                order = list(range(len(self.domains[d]._names)))
+                order = sorted(self.domains[d]._codes[it] for it in self.domains[d].items)
                 self.prng.shuffle(order)
                 md += [k] * len(order)
                 mi += order
@@ -324,3 +356,245 @@ class IRM:
 
     def logp(self, observations):
         raise NotImplementedError("predictive queries are outside the engine's scope (SURVEY.md section 2)")
+
+
+def choose_index(logps, u):
+    """The engine's inversion rule (cxx/util_math.cc:58-65 / random.Random.choices): first index whose running
+    sum of exp(lp - max) exceeds u * total, sums in index order."""
+    lp = np.asarray(logps, dtype=np.float64)
+    e = np.exp(lp - lp.max())
+    total = 0.0
+    for v in e:
+        total += float(v)
+    x, cum = u * total, 0.0
+    for i, v in enumerate(e):
+        cum += float(v)
+        if cum > x:
+            return i
+    return len(e) - 1
+
+
+class RelationCRP:
+    """The CRP over relations of an HIRM (src/hirm.py:459; cxx/hirm.hh:790): small, kept on the host."""
+
+    def __init__(self, prng):
+        self.alpha, self.prng = 1.0, prng
+        self.assignments, self.tables = {}, {}
+
+    @property
+    def N(self):
+        return len(self.assignments)
+
+    def tables_weights(self):
+        if not self.tables:
+            return {0: 1.0}
+        w = {t: float(len(c)) for t, c in self.tables.items()}
+        w[max(self.tables) + 1] = self.alpha
+        return w
+
+    def tables_weights_gibbs(self, table):
+        """src/hirm.py:101-108: the customer's own table loses one seat; a singleton keeps weight alpha and no
+        fresh table is offered."""
+        w = self.tables_weights()
+        w[table] -= 1
+        if w[table] == 0:
+            w[table] = self.alpha
+            del w[max(w)]
+        return w
+
+    def sample(self):
+        w = self.tables_weights()
+        return self.prng.choices(list(w), weights=list(w.values()))[0]
+
+    def incorporate(self, item, table):
+        self.tables.setdefault(table, set()).add(item)
+        self.assignments[item] = table
+
+    def unincorporate(self, item):
+        t = self.assignments.pop(item)
+        self.tables[t].discard(item)
+        if not self.tables[t]:
+            del self.tables[t]
+
+    def logp_score(self):
+        from math import lgamma, log
+        return (len(self.tables) * log(self.alpha) + sum(lgamma(len(c)) for c in self.tables.values())
+                + lgamma(self.alpha) - lgamma(self.N + self.alpha))
+
+
+class HIRM:
+    """src/hirm.py:457-571 / cxx/hirm.hh:784-1014 on the GPU engine.
+
+    Every relation-cluster IRM is an engine IRM; the entity sweeps of all of them run concurrently in one launch
+    (`transition_irms`).  The relation move (`transition_cluster_assignment_relation`) gets the data term of every
+    candidate table -- Relation.logp_score of the relation under that IRM's partitions -- from the device
+    (hirm_engine_relation_scores) without moving data; entities a candidate IRM has not seen are seated there by
+    CRP-prior draws first and stay behind as the reference's do (its remove_relation leaves them in the domain)."""
+
+    def __init__(self, schema, prng=None, engine=None, max_tables=None):
+        self.prng = prng or random
+        self.crp = RelationCRP(self.prng)
+        self.schema, self.irms = {}, {}
+        self._eng, self._max_tables = engine, max_tables
+        self._spaces = {}
+        self._seat_hook = None        # tests: {(table, domain): {entity: label}} -> seats of a fresh IRM
+        for r, ds in schema.items():
+            self.add_relation(r, ds)
+
+    def _new_irm(self, schema):
+        return IRM(schema, prng=self.prng, engine=self._eng, max_tables=self._max_tables, spaces=self._spaces)
+
+    # ---- schema / data --------------------------------------------------------------------
+    def add_relation(self, r, domains):
+        assert r not in self.schema
+        self.schema[r] = domains
+        table = self.crp.sample()
+        self.crp.incorporate(r, table)
+        if table in self.irms:
+            self.irms[table].add_relation(r, domains)
+        else:
+            self.irms[table] = self._new_irm({r: domains})
+
+    def remove_relation(self, r):
+        del self.schema[r]
+        table = self.crp.assignments[r]
+        singleton = len(self.crp.tables[table]) == 1
+        self.crp.unincorporate(r)
+        self.irms[table].remove_relation(r)
+        if singleton:
+            assert not self.irms[table].relations
+            self._drop(table)
+
+    def _drop(self, table):
+        irm = self.irms.pop(table)
+        if irm._h is not None:
+            irm._eng.irm_destroy(irm._h)
+            irm._h = None
+
+    def incorporate(self, r, items, value):
+        self.relation_to_irm(r).incorporate(r, items, value)
+
+    def unincorporate(self, r, items):
+        raise NotImplementedError()
+
+    def relation_to_table(self, r):
+        return self.crp.assignments[r]
+
+    def relation_to_irm(self, r):
+        return self.irms[self.crp.assignments[r]]
+
+    def get_relation(self, r):
+        return self.relation_to_irm(r).relations[r]
+
+    # ---- inference ---------------------------------------------------------------------------
+    def transition_cluster_assignments(self, rs=None):
+        """Relation moves (src/hirm.py:479-481): every relation once, in a prng-shuffled order."""
+        if rs is None:
+            rs = list(self.schema)
+            self.prng.shuffle(rs)
+        for r in rs:
+            self.transition_cluster_assignment_relation(r)
+
+    def _candidate_scores(self, r, tables, table_current):
+        """Relation.logp_score of r under every candidate table's IRM.  Returns (scores, {table: fresh IRM})."""
+        cur = self.irms[table_current]
+        rel = cur.relations[r]
+        dnames = [d.name for d in rel.domains]
+        cur._push()
+        self._eng = cur._eng
+        cands, fresh = [], {}
+        for t in tables:
+            if t == table_current:
+                cands.append(cur)
+                continue
+            irm = self.irms.get(t)
+            if irm is None:
+                irm = fresh[t] = self._new_irm({})
+            irm._eng = irm._eng or self._eng
+            for d in dnames:                                   # the trial add_relation + incorporate of the reference:
+                if d not in irm.domains:                       # it creates the domains and seats the unseen entities
+                    irm.domains[d] = Domain(d, irm, self._spaces.setdefault(d, CodeSpace()))
+                    irm.domain_to_relations[d] = set()
+                    irm._alpha[d] = 1.0
+                    irm._dirty = True
+            for items in rel.data:
+                for d, item in zip(dnames, items):
+                    dom = irm.domains[d]
+                    if item not in dom.items:
+                        forced = None if self._seat_hook is None else self._seat_hook.get((t, d), {}).get(item)
+                        dom.incorporate(item, forced)
+            irm._push()
+            cands.append(irm)
+        doms = [[c._dorder.index(d) for d in dnames] for c in cands]
+        scores = self._eng.relation_scores(cur._h, cur._rindex[r], [c._h for c in cands], doms)
+        return [float(x) for x in scores], fresh
+
+    def transition_cluster_assignment_relation(self, r, u=None):
+        """src/hirm.py:482-519 / cxx/hirm.hh:833-906.  Returns (tables, log-probabilities, choice)."""
+        from math import log
+        table_current = self.crp.assignments[r]
+        crp_dist = self.crp.tables_weights_gibbs(table_current)
+        tables = sorted(crp_dist)
+        scores, fresh = self._candidate_scores(r, tables, table_current)
+        logps = [log(crp_dist[t]) + s for t, s in zip(tables, scores)]
+        if u is None:
+            u = self.prng.random()
+        choice = tables[choose_index(logps, u)]
+        self._move(r, table_current, choice, fresh)
+        return tables, logps, choice
+
+    def _move(self, r, table_current, choice, fresh):
+        # candidates that were only tried keep the seats they were given (cxx/hirm.hh:766 TODO; SURVEY 8a-Q7);
+        # a fresh IRM that was not chosen is dropped (:892-898)
+        for t, irm in fresh.items():
+            if t != choice:
+                if irm._h is not None:
+                    irm._eng.irm_destroy(irm._h)
+            else:
+                self.irms[t] = irm
+        if choice != table_current:
+            cur = self.irms[table_current]
+            rel = cur.relations[r]
+            domains, data = [d.name for d in rel.domains], dict(rel.data)
+            cur.remove_relation(r)
+            if not cur.relations:
+                self._drop(table_current)
+            dst = self.irms[choice]
+            dst.add_relation(r, domains)
+            for items, value in data.items():
+                dst.incorporate(r, items, value)
+        self.crp.unincorporate(r)
+        self.crp.incorporate(r, choice)
+        assert set(self.irms) == set(self.crp.tables)
+
+    def set_cluster_assignment_gibbs(self, r, table):
+        """src/hirm.py:520-543: force relation r into `table`."""
+        cur = self.crp.assignments[r]
+        fresh = {}
+        if table not in self.irms:
+            fresh[table] = self._new_irm({})
+        self._move(r, cur, table, fresh)
+
+    def transition_irms(self, n_sweeps=1, ngrid=30):
+        """The entity sweeps + alpha moves of every IRM (cxx/hirm.cc:73-88), all IRMs concurrently."""
+        irms = list(self.irms.values())
+        for irm in irms:
+            irm._push()
+        self._eng = irms[0]._eng
+        batch = [irm for irm in irms if all(len(irm.domains[d].items) == n for d, n in zip(irm._dorder, irm._n_ent))]
+        for _ in range(n_sweeps):
+            if batch:
+                seed = batch[0]._seed
+                self._eng.sweep_all([irm._h for irm in batch], n_sweeps=1, seed=seed)
+                for irm in batch:
+                    irm._moves += sum(irm._n_ent)
+                    irm._stale = True
+            for irm in irms:
+                if irm not in batch:
+                    irm.transition_cluster_assignments()
+            self._eng.transition_alpha([irm._h for irm in irms], ngrid=ngrid, seed=irms[0]._seed)
+            for irm in irms:
+                irm._stale = True
+
+    def logp_score(self):
+        return self.crp.logp_score() + sum(irm.logp_score() for irm in self.irms.values())

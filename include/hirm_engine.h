@@ -146,6 +146,17 @@ int hirm_irm_get_alpha(hirm_engine *e, int32_t irm, int dom, double *out);
 /* CRP::tables read-back (cxx/hirm.hh:74): labels ascending and customers per table */
 int hirm_irm_get_tables(hirm_engine *e, int32_t irm, int dom, int32_t *h_labels, int32_t *h_counts, int cap, int32_t *n_tables);
 
+/* Relation::logp_score of relation (src_irm, rel) under the domain partitions of other IRMs: the data term of every
+ * candidate table in HIRM::transition_cluster_assignment_relation (cxx/hirm.hh:859-866; src/hirm.py:497-505), without
+ * moving any data (the count table under a partition is a histogram).  h_cand_doms [n_cand * HIRM_MAX_ARITY]: for
+ * each candidate, the index IN THE CANDIDATE of the domain at each position of the relation; the candidate's domains
+ * must use the same entity codes.  Entities of the relation that are absent from a candidate's domain must be seated
+ * first (hirm_irm_seat_entities), as the reference's trial incorporate does. */
+int hirm_engine_relation_scores(hirm_engine *e, int32_t src_irm, int rel, int n_cand, const int32_t *h_cand_irms,
+                                const int32_t *h_cand_doms, double *h_out);
+/* Domain::incorporate(item, table) for entities not yet in the domain (cxx/hirm.hh:194-203) */
+int hirm_irm_seat_entities(hirm_engine *e, int32_t irm, int dom, int n, const int32_t *h_items, const int32_t *h_labels);
+
 /* statistics of the last sweep: kernel launches made, which kernel ran (0 generic, 1 dense, 2 dense-cluster) */
 int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, int32_t *kernel_kind, float *kernel_ms);
 

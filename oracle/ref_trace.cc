@@ -250,6 +250,113 @@ static void traced_sweeps(IRM &irm, int sweeps, bool shuffle, bool alpha_moves, 
     printf("\n]");
 }
 
+
+// ---- HIRM relation moves (cxx/hirm.hh:833-906), traced -------------------------------------------------------
+// The body of HIRM::transition_cluster_assignment_relation restated around the reference's own calls
+// (crp.tables_weights_gibbs, IRM::add_relation / incorporate, Relation::logp_score, IRM::remove_relation), with the
+// table drawn by the engine's inversion rule from a traced uniform instead of log_choice(prng).  Dumps, per move,
+// the candidate tables (ascending), the reference's log-probabilities, and -- for the fresh IRM -- the seats the
+// reference's CRP-prior draws gave the relation's entities.
+static void dump_hirm_state(HIRM &hirm) {
+    vector<std::pair<string, int>> rt;
+    for (const auto &[r, rc] : hirm.relation_to_code) rt.push_back({r, hirm.crp.assignments.at(rc)});
+    std::sort(rt.begin(), rt.end());
+    printf("{\"relation_table\":{");
+    for (size_t k = 0; k < rt.size(); k++) printf("%s\"%s\":%d", k ? "," : "", rt[k].first.c_str(), rt[k].second);
+    printf("},\"irm_z\":{");
+    vector<int> tables;
+    for (const auto &[t, irm] : hirm.irms) tables.push_back(t);
+    std::sort(tables.begin(), tables.end());
+    for (size_t k = 0; k < tables.size(); k++) {
+        IRM *irm = hirm.irms.at(tables[k]);
+        printf("%s\"%d\":{", k ? "," : "", tables[k]);
+        vector<string> dn;
+        for (const auto &[d, dom] : irm->domains) dn.push_back(d);
+        std::sort(dn.begin(), dn.end());
+        for (size_t j = 0; j < dn.size(); j++) {
+            Domain *dom = irm->domains.at(dn[j]);
+            vector<std::pair<int, int>> za;
+            for (auto it : dom->items) za.push_back({it, dom->get_cluster_assignment(it)});
+            std::sort(za.begin(), za.end());
+            printf("%s\"%s\":{\"alpha\":%.17g,\"items\":[", j ? "," : "", dn[j].c_str(), dom->crp.alpha);
+            for (size_t q = 0; q < za.size(); q++) printf("%s[%d,%d]", q ? "," : "", za[q].first, za[q].second);
+            printf("]}");
+        }
+        printf("}");
+    }
+    printf("},\"logp_score\":%.17g}", hirm.logp_score());
+}
+
+static void traced_relation_moves(HIRM &hirm, PRNG &urng) {
+    printf("\"hirm\":{\"init\":");
+    dump_hirm_state(hirm);
+    printf(",\n\"rmoves\":[\n");
+    vector<string> rs;
+    for (const auto &[r, rc] : hirm.relation_to_code) rs.push_back(r);
+    std::sort(rs.begin(), rs.end());
+    bool first = true;
+    for (const auto &r : rs) {
+        auto rc = hirm.relation_to_code.at(r);
+        auto table_current = hirm.crp.assignments.at(rc);
+        auto relation = hirm.get_relation(r);
+        auto crp_dist = hirm.crp.tables_weights_gibbs(table_current);
+        vector<string> domains;
+        for (const auto &d : relation->domains) domains.push_back(d->name);
+        vector<int> tables;
+        for (const auto &[table, w] : crp_dist) tables.push_back(table);
+        std::sort(tables.begin(), tables.end());
+        vector<double> logps, lp_datas;
+        int table_aux = -1; IRM *irm_aux = NULL;
+        for (int table : tables) {
+            IRM *irm;
+            if (hirm.irms.count(table) == 0) { irm = new IRM({}, hirm.prng); table_aux = table; irm_aux = irm; }
+            else irm = hirm.irms.at(table);
+            if (table != table_current) {
+                irm->add_relation(r, domains);
+                for (const auto &[items, value] : relation->data) irm->incorporate(r, items, value);
+            }
+            double lp_data = irm->relations.at(r)->logp_score();
+            lp_datas.push_back(lp_data);
+            logps.push_back(log(crp_dist.at(table)) + lp_data);
+        }
+        double u = std::generate_canonical<double, 53>(urng);
+        int choice = tables[choose(logps, u)];
+        printf("%s{\"r\":\"%s\",\"cur\":%d,\"tables\":", first ? "" : ",\n", r.c_str(), table_current);
+        first = false;
+        jints(tables);
+        printf(",\"lp\":"); jdoubles(logps);
+        printf(",\"lp_data\":"); jdoubles(lp_datas);
+        printf(",\"u\":%.17g,\"choice\":%d,\"fresh\":%d", u, choice, table_aux);
+        if (irm_aux) {                                 // the seats the reference drew for the fresh IRM
+            printf(",\"fresh_z\":{");
+            bool fd = true;
+            for (const auto &[d, dom] : irm_aux->domains) {
+                vector<std::pair<int, int>> za;
+                for (auto it : dom->items) za.push_back({it, dom->get_cluster_assignment(it)});
+                std::sort(za.begin(), za.end());
+                printf("%s\"%s\":[", fd ? "" : ",", d.c_str());
+                fd = false;
+                for (size_t q = 0; q < za.size(); q++) printf("%s[%d,%d]", q ? "," : "", za[q].first, za[q].second);
+                printf("]");
+            }
+            printf("}");
+        }
+        printf("}");
+        // the rest of cxx/hirm.hh:878-901, verbatim in effect
+        for (const auto &[table, customers] : hirm.crp.tables) {
+            auto irm = hirm.irms.at(table);
+            if (table != choice) irm->remove_relation(r);
+            if (irm->relations.size() == 0) { hirm.irms.erase(table); delete irm; }
+        }
+        if (irm_aux && choice == table_aux) hirm.irms[choice] = irm_aux; else delete irm_aux;
+        hirm.crp.unincorporate(rc);
+        hirm.crp.incorporate(rc, choice);
+    }
+    printf("\n],\n\"final\":");
+    dump_hirm_state(hirm);
+    printf("}");
+}
+
 int main(int argc, char **argv) {
     if (argc < 5) {
         fprintf(stderr, "usage: ref_trace irm|hirm <path_base> <seed> <n> [shuffle] [noalpha]\n");
@@ -299,7 +406,9 @@ int main(int argc, char **argv) {
             traced_sweeps(*hirm.irms.at(tables[k]), 1, shuffle, false, urng);
             printf("}");
         }
-        printf("]}\n");
+        printf("],\n");
+        traced_relation_moves(hirm, urng);
+        printf("}\n");
         return 0;
     }
     fprintf(stderr, "unknown mode %s\n", mode.c_str());
