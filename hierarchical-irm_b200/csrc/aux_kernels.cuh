@@ -129,6 +129,21 @@ __global__ void __launch_bounds__(AUX_THREADS) rel_score_kernel(const RelCand *c
     if (threadIdx.x == 0) out[blockIdx.x] = total;
 }
 
+// debug / test hook: the dense kernel's branch-free cell score on arrays of operands (one warp-converged call per element)
+__global__ void __launch_bounds__(AUX_THREADS) debug_score_delta_kernel(const uint32_t *N, const uint32_t *sv, const uint32_t *gn, const uint32_t *gs,
+                                                                        double *out, int n) {
+    __shared__ double lf[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lf[i] = g_logfact[i];
+    __syncthreads();
+    const int nround = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (int r = 0; r < nround; r++) {
+        const int i = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        const bool ok = i < n;
+        const double v = score_delta_bf<256>(lf, ok ? N[i] : 0u, ok ? sv[i] : 0u, ok ? gn[i] : 0u, ok ? gs[i] : 0u);
+        if (ok) out[i] = v;
+    }
+}
+
 __device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; }
 
 // Sweep order (the loops of cxx/hirm.cc:45-51 / IRM::transition_cluster_assignments_all, cxx/hirm.hh:590-596): for every

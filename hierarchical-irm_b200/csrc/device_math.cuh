@@ -103,7 +103,8 @@ __device__ __forceinline__ double log_core(double v) {
     const double hfsq = 0.5 * f * f;
     return dk * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
 }
-// log((a+m)! / a!) against a table lf[LFS] of lgamma(j+1), branch-free (selects only):
+// log((a+m)! / a!) against a table lf[LFS] of lgamma(j+1), branch-free per lane (selects only; one warp-uniform
+// early exit); must be called by all 32 lanes of a converged warp (lanes without work pass m = 0):
 //   a + m < LFS          lf[a+m] - lf[a]
 //   a < LFS <= a + m     Stirling(a+m+1) - lf[a]
 //   a >= LFS             (y+m-1/2) log1p(m/y) + m (ln y - 1) + corr(y+m) - corr(y),  y = a + 1   (no cancellation)
@@ -114,6 +115,8 @@ __device__ __forceinline__ double lfact_diff_bf(const double *lf, uint32_t a, ui
     const bool small = am < (uint32_t)LFS, big = a >= (uint32_t)LFS;
     const double lfa = lf[min(a, (uint32_t)LFS - 1u)];
     const double tab = lf[min(am, (uint32_t)LFS - 1u)] - lfa;
+    // the callers' warps are converged: when no lane is beyond the table the six logarithms are skipped
+    if (!__any_sync(0xffffffffu, m != 0u && !small)) return m == 0u ? 0.0 : tab;
     const double y = (double)a + 1.0, dm = (double)m, ym = y + dm;
     const double ry = rcp_nr(y), rym = rcp_nr(ym);
     const double x = dm * ry, u = 1.0 + x;

@@ -451,7 +451,7 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
         int64_t cap = 1;
         for (int d = 0; d < irm->n_domains; d++) cap = std::max(cap, S.dom[d].max_deg);
         irm->gl_cap = cap;
-        CK(irm->gl_rel.ensure((size_t)cap)); CK(irm->gl_cell.ensure((size_t)cap));
+        CK(irm->gl_rel.ensure((size_t)cap)); CK(irm->gl_cell.ensure((size_t)cap * (sizeof(GroupRec) / sizeof(int64_t))));   // one GroupRec per group
     }
     irm->dense_ree = irm->n_domains == 1 && irm->n_relations == 1 && S.rel[0].kind == 1 && irm->kcap[0] <= 64;
     irm->scratch_ready = true; irm->desc_dirty = true;
@@ -885,7 +885,9 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
     e->last_launches = 0; e->last_kind = -1;
     CK(cudaEventRecord(e->ev0, e->stream));
     if (!plan.generic_blk.empty()) {
-        generic_sweep_kernel<<<(unsigned)plan.generic_blk.size(), GEN_THREADS, 0, e->stream>>>(args, e->s_blk.p);
+        // few IRMs: 256 threads each (shortest move); many: 128 threads, 8 CTAs per SM hide one another's memory latency
+        const int gen_threads = (int)plan.generic_blk.size() > 4 * e->num_sms ? 128 : GEN_THREADS;
+        generic_sweep_kernel<<<(unsigned)plan.generic_blk.size(), gen_threads, 0, e->stream>>>(args, e->s_blk.p);
         CK(cudaGetLastError());
         e->last_launches++; e->last_kind = 0;
     }
@@ -1087,6 +1089,23 @@ extern "C" int hirm_engine_last_dense_plan(hirm_engine *e, int32_t *ctas_per_sm,
     if (stages) *stages = e->last_stages;
     if (chunk_bytes) *chunk_bytes = e->last_chunk;
     if (smem_bytes) *smem_bytes = e->last_smem;
+    return 0;
+}
+
+// Debug / test hook: S(N+n, s+sg) - S(N, s) for arrays of operands with the kernels' own fp64 code (score_delta_bf).
+extern "C" int hirm_engine_debug_score_delta(hirm_engine *e, int n, const uint32_t *h_N, const uint32_t *h_s, const uint32_t *h_gn,
+                                             const uint32_t *h_gs, double *h_out) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n <= 0) return 0;
+    DevBuf<uint32_t> d[4]; DevBuf<double> o;
+    const uint32_t *src[4] = {h_N, h_s, h_gn, h_gs};
+    for (int k = 0; k < 4; k++) { CK(d[k].alloc((size_t)n)); CK(cudaMemcpy(d[k].p, src[k], (size_t)n * 4, cudaMemcpyHostToDevice)); }
+    CK(o.alloc((size_t)n));
+    debug_score_delta_kernel<<<std::min((n + AUX_THREADS - 1) / AUX_THREADS, 1024), AUX_THREADS, 0, e->stream>>>(d[0].p, d[1].p, d[2].p, d[3].p, o.p, n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(h_out, o.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -19,9 +19,10 @@
 
 namespace hirm {
 
-constexpr int GEN_THREADS = 256;
+constexpr int GEN_THREADS = 256;   // maximum; launched with 256 (few IRMs: shortest move) or 128 (many: 8 CTAs per SM)
 constexpr int GEN_WARPS = GEN_THREADS / 32;
 constexpr int GEN_MAXK = 256;   // kcap <= 255 candidates + 1 fresh
+constexpr int GEN_LF = 256;     // shared-memory copy of lgamma(m+1), m < 256; Stirling beyond (device_math.cuh)
 
 struct GroupRef {
     const RelationDev *R;
@@ -93,17 +94,38 @@ __device__ __forceinline__ int64_t group_cell_at(const GroupRef &g, int t) {
     return c;
 }
 
-__global__ void __launch_bounds__(GEN_THREADS) generic_sweep_kernel(SweepArgs args, const int32_t *blk_list) {
+// One decoded group, built once per move (phase B2) and read by every candidate's scoring warp.
+struct GroupRec {
+    const RelationDev *R;
+    int64_t rest_g, rest_c;   // accumulator / count-table index without the moved domain's positions
+    int64_t cellidx;          // index into R->groups
+    cell_t own;
+    int16_t a, b, da, db, kd, pad0, pad1, pad2;
+};
+static_assert(sizeof(GroupRec) == 56, "GroupRec layout (engine.cu sizes the scratch by it)");
+
+__device__ __forceinline__ GroupRef ref_of(const GroupRec &r) {
+    GroupRef g;
+    g.R = r.R; g.a = r.a; g.b = r.b; g.da = r.da; g.db = r.db; g.rest_g = r.rest_g; g.rest_c = r.rest_c; g.kd = r.kd; g.own = r.own;
+    return g;
+}
+
+__global__ void __launch_bounds__(GEN_THREADS, 4) generic_sweep_kernel(SweepArgs args, const int32_t *blk_list) {
     const int k_list = blk_list ? blk_list[blockIdx.x] : blockIdx.x;
     const IrmDev &irm = args.irms[args.irm_ids[k_list]];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = blockDim.x, NW = NT >> 5;
 
     __shared__ int32_t s_cnt[GEN_MAXK], s_lab[GEN_MAXK];
-    __shared__ int32_t s_cslot[GEN_MAXK + 1], s_clabel[GEN_MAXK + 1];
-    __shared__ double s_lp[GEN_MAXK + 1];
+    __shared__ int32_t s_cslot[GEN_MAXK + 1], s_clabel[GEN_MAXK + 1], u_slot[GEN_MAXK + 1], u_label[GEN_MAXK + 1];
+    __shared__ double s_lp[GEN_MAXK + 1], s_tmp[GEN_MAXK + 1];
+    __shared__ double s_lf[GEN_LF];
     __shared__ int32_t s_warp_tot[GEN_WARPS];
     __shared__ int32_t s_ncand, s_choice_slot, s_choice_label, s_fail;
-    __shared__ int64_t s_ngroups;
+    GroupRec *recs = reinterpret_cast<GroupRec *>(irm.gl_cell);     // [gl_cap] group records (engine scratch)
+
+    for (int k = tid; k < GEN_LF; k += NT) s_lf[k] = g_logfact[k];
+    __syncthreads();
 
     const int64_t m0 = args.move_off[k_list], m1 = args.move_off[k_list + 1];
     for (int64_t m = m0; m < m1; m++) {
@@ -120,11 +142,13 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_sweep_kernel(SweepArgs ar
             continue;
         }
         if (tid == 0) s_fail = 0;
+        const int hi = __ldcg(dd.hi);
+        for (int k = tid; k < hi; k += NT) { s_cnt[k] = __ldcg(&dd.tab_count[k]); s_lab[k] = __ldcg(&dd.tab_label[k]); }
 
-        // ---- A: remove + group ---------------------------------------------------------
+        // ---- A: remove + group (fire-and-forget reductions; completed by the fence below) -----------
         if (dd.ptr) {
             const int64_t beg = dd.ptr[item], end = dd.ptr[item + 1];
-            for (int64_t q = beg + tid; q < end; q += GEN_THREADS) {
+            for (int64_t q = beg + tid; q < end; q += NT) {
                 const uint32_t meta = dd.meta[q];
                 const int rel = meta & META_REL_MASK;
                 const uint32_t val = (meta >> META_VAL_SHIFT) & 1u, selfmask = (meta >> META_SELF_SHIFT) & 0xFu;
@@ -147,20 +171,55 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_sweep_kernel(SweepArgs ar
                 }
                 if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); continue; }
                 const cell_t one = pack_cell(1u, val);
-                const cell_t old = atomicAdd(&R->groups[gidx], one);
-                if (cell_n(old) == 0) {
-                    const int64_t bit = R->gbit0 + gidx;
-                    atomicOr(&irm.gbitmap[bit >> 6], 1ull << (bit & 63));
-                }
+                atomicAdd(&R->groups[gidx], one);
+                const int64_t bit = R->gbit0 + gidx;
+                atomicOr(&irm.gbitmap[bit >> 6], 1ull << (bit & 63));
                 atomicAdd(&R->counts[cidx], (cell_t)0 - one);
             }
         }
         __threadfence();
         __syncthreads();
 
-        // ---- B: ordered compaction of the touched accumulator cells -----------------------
+        // ---- C: candidates, CRP::tables_weights_gibbs (cxx/hirm.hh:147-161): warp 0, lanes over the tables ----
+        if (warp == 0) {
+            int maxlab = 0, freeslot = 1 << 30;        // t_max starts at 0 (cxx/hirm.hh:139)
+            for (int k = lane; k < hi; k += 32) {
+                if (s_cnt[k] > 0) maxlab = max(maxlab, s_lab[k]); else freeslot = min(freeslot, k);
+            }
+            maxlab = __reduce_max_sync(0xffffffffu, maxlab);
+            freeslot = __reduce_min_sync(0xffffffffu, freeslot);
+            if (freeslot == (1 << 30)) freeslot = hi < dd.kcap ? hi : -1;
+            const bool singleton = s_cnt[c] == 1;
+            const double logalpha = log(dd.alpha);
+            int ncount = 0;
+            for (int base = 0; base < hi; base += 32) {
+                const int k = base + lane;
+                const int cnt = k < hi ? s_cnt[k] - (k == c ? 1 : 0) : 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, cnt > 0);
+                const int pos = ncount + __popc(bal & ((1u << lane) - 1u));
+                const double lw = log((double)max(cnt, 1));
+                if (cnt > 0) { u_slot[pos] = k; u_label[pos] = s_lab[k]; s_tmp[pos] = lw; }
+                ncount += __popc(bal);
+            }
+            if (lane == 0) {
+                if (singleton) { u_slot[ncount] = c; u_label[ncount] = s_lab[c]; s_tmp[ncount] = logalpha; }   // own table at weight alpha, no fresh one (:152-159)
+                else if (freeslot >= 0) { u_slot[ncount] = freeslot; u_label[ncount] = maxlab + 1; s_tmp[ncount] = logalpha; }   // fresh table, label max+1 (:144)
+                else { raise_error(irm, KERR_NO_FREE_SLOT); s_fail = 1; }
+            }
+            const int nc = ncount + ((singleton || freeslot >= 0) ? 1 : 0);
+            __syncwarp();
+            for (int j = lane; j < nc; j += 32) {      // ascending label order: rank by counting (labels are distinct)
+                const int lb = u_label[j];
+                int rank = 0;
+                for (int i = 0; i < nc; i++) rank += u_label[i] < lb;
+                s_cslot[rank] = u_slot[j]; s_clabel[rank] = lb; s_lp[rank] = s_tmp[j];
+            }
+            if (lane == 0) s_ncand = nc;
+        }
+
+        // ---- B: ordered compaction of the touched accumulator cells ----------------------------------
         int64_t base = 0;
-        for (int64_t w0 = 0; w0 < irm.gwords; w0 += GEN_THREADS) {
+        for (int64_t w0 = 0; w0 < irm.gwords; w0 += NT) {
             const int64_t w = w0 + tid;
             unsigned long long bits = w < irm.gwords ? __ldcg(&irm.gbitmap[w]) : 0ull;
             const int cnt = __popcll(bits);
@@ -174,7 +233,7 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_sweep_kernel(SweepArgs ar
             __syncthreads();
             int woff = 0, total = 0;
 #pragma unroll
-            for (int k = 0; k < GEN_WARPS; k++) { int v = s_warp_tot[k]; if (k < warp) woff += v; total += v; }
+            for (int k = 0; k < GEN_WARPS; k++) { int v = k < NW ? s_warp_tot[k] : 0; if (k < warp) woff += v; total += v; }
             int64_t off = base + woff + incl - cnt;
             if (bits) {
                 const int rel = irm.word_rel[w];
@@ -182,8 +241,14 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_sweep_kernel(SweepArgs ar
                 while (bits) {
                     const int bpos = __ffsll((long long)bits) - 1;
                     bits &= bits - 1;
-                    if (off < irm.gl_cap) { irm.gl_rel[off] = rel; irm.gl_cell[off] = w * 64 + bpos - bit0; }
-                    else raise_error(irm, KERR_GROUP_OVERFLOW);
+                    if (off < irm.gl_cap) {            // B2: decode once, for every candidate
+                        const GroupRef gr = decode_group(irm, d, rel, w * 64 + bpos - bit0);
+                        GroupRec rc;
+                        rc.R = gr.R; rc.rest_g = gr.rest_g; rc.rest_c = gr.rest_c; rc.cellidx = w * 64 + bpos - bit0; rc.own = gr.own;
+                        rc.a = (int16_t)gr.a; rc.b = (int16_t)gr.b; rc.da = (int16_t)gr.da; rc.db = (int16_t)gr.db; rc.kd = (int16_t)gr.kd;
+                        rc.pad0 = rc.pad1 = rc.pad2 = 0;
+                        recs[off] = rc;
+                    } else raise_error(irm, KERR_GROUP_OVERFLOW);
                     off++;
                 }
             }
@@ -191,51 +256,26 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_sweep_kernel(SweepArgs ar
             __syncthreads();
         }
         const int64_t ngroups = base < irm.gl_cap ? base : irm.gl_cap;
-
-        // ---- C: candidates -------------------------------------------------------------
-        const int hi = __ldcg(dd.hi);
-        for (int k = tid; k < hi; k += GEN_THREADS) { s_cnt[k] = __ldcg(&dd.tab_count[k]); s_lab[k] = __ldcg(&dd.tab_label[k]); }
-        __syncthreads();
-        if (tid == 0) {
-            int n = 0, maxlab = 0, freeslot = -1;      // t_max starts at 0 (cxx/hirm.hh:139)
-            for (int k = 0; k < hi; k++) {
-                if (s_cnt[k] > 0) maxlab = max(maxlab, s_lab[k]);
-                else if (freeslot < 0) freeslot = k;
-            }
-            if (freeslot < 0 && hi < dd.kcap) freeslot = hi;
-            const bool singleton = s_cnt[c] == 1;
-            for (int k = 0; k < hi; k++) {
-                const int cnt = s_cnt[k] - (k == c ? 1 : 0);
-                if (cnt > 0) { s_cslot[n] = k; s_clabel[n] = s_lab[k]; s_lp[n] = log((double)cnt); n++; }
-            }
-            if (singleton) {                           // own table re-offered with weight alpha, no extra fresh table (:152-159)
-                s_cslot[n] = c; s_clabel[n] = s_lab[c]; s_lp[n] = log(dd.alpha); n++;
-            } else if (freeslot >= 0) {                // fresh table, label max+1 (:144)
-                s_cslot[n] = freeslot; s_clabel[n] = maxlab + 1; s_lp[n] = log(dd.alpha); n++;
-            } else {
-                raise_error(irm, KERR_NO_FREE_SLOT); s_fail = 1;
-            }
-            for (int i = 1; i < n; i++) {              // ascending label order
-                const int sl = s_cslot[i], lb = s_clabel[i]; const double lw = s_lp[i];
-                int j = i - 1;
-                while (j >= 0 && s_clabel[j] > lb) { s_cslot[j + 1] = s_cslot[j]; s_clabel[j + 1] = s_clabel[j]; s_lp[j + 1] = s_lp[j]; j--; }
-                s_cslot[j + 1] = sl; s_clabel[j + 1] = lb; s_lp[j + 1] = lw;
-            }
-            s_ncand = n;
-        }
         __syncthreads();
         const int ncand = s_ncand;
 
-        // ---- D: score: one warp per candidate, lanes over groups --------------------------
-        for (int t = warp; t < ncand; t += GEN_WARPS) {
+        // ---- D: score: one warp per candidate, lanes over groups (branch-free cell score) -----------------
+        for (int t = warp; t < ncand; t += NW) {
             const int slot_t = s_cslot[t];
             double acc = 0.0;
-            for (int64_t g = lane; g < ngroups; g += 32) {
-                const GroupRef gr = decode_group(irm, d, irm.gl_rel[g], irm.gl_cell[g]);
-                cell_t delta; int64_t cidx;
-                if (!group_target(gr, slot_t, delta, cidx)) continue;
-                const cell_t cur = __ldcg(&gr.R->counts[cidx]);
-                acc += score_delta(cell_n(cur), cell_s(cur), cell_n(delta), cell_s(delta));
+            for (int64_t g0 = 0; g0 < ngroups; g0 += 32) {
+                const int64_t g = g0 + lane;
+                uint32_t N = 0u, sv = 0u, gn = 0u, gs = 0u;
+                if (g < ngroups) {
+                    const GroupRef gr = ref_of(recs[g]);
+                    cell_t delta; int64_t cidx;
+                    if (group_target(gr, slot_t, delta, cidx)) {
+                        const cell_t cur = __ldcg(&gr.R->counts[cidx]);
+                        N = cell_n(cur); sv = cell_s(cur); gn = cell_n(delta); gs = cell_s(delta);
+                    }
+                }
+                __syncwarp();
+                acc += score_delta_bf<GEN_LF>(s_lf, N, sv, gn, gs);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -243,23 +283,40 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_sweep_kernel(SweepArgs ar
         }
         __syncthreads();
 
-        // ---- E: sample -----------------------------------------------------------------
-        if (tid == 0) {
+        // ---- E: sample (warp 0): log_choice (cxx/util_math.cc:58-65); exp lane-parallel, sums in index order ----
+        if (warp == 0) {
             int idx = 0;
             if (args.flags & 1u) {                     // HIRM_SWEEP_SCORE_ONLY: stay
-                for (int t = 0; t < ncand; t++) if (s_cslot[t] == c) idx = t;
-            } else {
-                const double u = args.uniforms ? args.uniforms[m]
-                                               : philox_uniform(args.seed, args.stream[k_list], args.counter0[k_list] + (uint64_t)(m - m0));
-                idx = choose_index(s_lp, ncand, u);
+                for (int t = lane; t < ncand; t += 32) if (s_cslot[t] == c) idx = t;
+                idx = __reduce_max_sync(0xffffffffu, idx);
+            } else if (ncand > 1) {
+                double mx = -1.0 / 0.0;
+                for (int t = lane; t < ncand; t += 32) mx = fmax(mx, s_lp[t]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                for (int t = lane; t < ncand; t += 32) s_tmp[t] = exp(s_lp[t] - mx);
+                __syncwarp();
+                if (lane == 0) {
+                    const double u = args.uniforms ? args.uniforms[m]
+                                                   : philox_uniform(args.seed, args.stream[k_list], args.counter0[k_list] + (uint64_t)(m - m0));
+                    double total = 0.0;
+                    for (int t = 0; t < ncand; t++) total += s_tmp[t];
+                    const double x = u * total;
+                    double cum = 0.0;
+                    idx = ncand - 1;
+                    for (int t = 0; t < ncand; t++) { cum += s_tmp[t]; if (cum > x) { idx = t; break; } }
+                }
+                idx = __shfl_sync(0xffffffffu, idx, 0);
             }
-            if (s_fail || ncand == 0) { s_choice_slot = c; s_choice_label = s_lab[c]; }
-            else { s_choice_slot = s_cslot[idx]; s_choice_label = s_clabel[idx]; }
-            if (args.out_choice) args.out_choice[m] = s_choice_label;
-            if (args.trace_cap > 0) args.trace_n[m] = ncand;
+            if (lane == 0) {
+                if (s_fail || ncand == 0) { s_choice_slot = c; s_choice_label = s_lab[c]; }
+                else { s_choice_slot = s_cslot[idx]; s_choice_label = s_clabel[idx]; }
+                if (args.out_choice) args.out_choice[m] = s_choice_label;
+                if (args.trace_cap > 0) args.trace_n[m] = ncand;
+            }
         }
         if (args.trace_cap > 0) {
-            for (int t = tid; t < ncand && t < args.trace_cap; t += GEN_THREADS) {
+            for (int t = tid; t < ncand && t < args.trace_cap; t += NT) {
                 args.trace_labels[m * args.trace_cap + t] = s_clabel[t];
                 args.trace_logps[m * args.trace_cap + t] = s_lp[t];
             }
@@ -268,12 +325,12 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_sweep_kernel(SweepArgs ar
 
         // ---- F: apply ------------------------------------------------------------------
         const int tnew = s_choice_slot;
-        for (int64_t g = tid; g < ngroups; g += GEN_THREADS) {
-            const int rel = irm.gl_rel[g]; const int64_t cellidx = irm.gl_cell[g];
-            const GroupRef gr = decode_group(irm, d, rel, cellidx);
+        for (int64_t g = tid; g < ngroups; g += NT) {
+            const GroupRec rc = recs[g];
+            const GroupRef gr = ref_of(rc);
             atomicAdd(&gr.R->counts[group_cell_at(gr, tnew)], gr.own);
-            __stcg(&gr.R->groups[cellidx], (cell_t)0);
-            __stcg(&irm.gbitmap[(gr.R->gbit0 + cellidx) >> 6], 0ull);
+            __stcg(&gr.R->groups[rc.cellidx], (cell_t)0);
+            __stcg(&irm.gbitmap[(gr.R->gbit0 + rc.cellidx) >> 6], 0ull);
         }
         if (tid == 0 && tnew != c) {
             __stcg(&dd.z[item], tnew);

@@ -31,7 +31,7 @@ EXPORTS = [
     "hirm_engine_sweep_device", "hirm_engine_last_sweep_info", "hirm_engine_transpose_u8",
     "hirm_engine_debug_phase_cycles", "hirm_engine_last_dense_plan", "hirm_engine_sweep_all", "hirm_irm_set_rng",
     "hirm_engine_logp_scores", "hirm_engine_transition_alpha", "hirm_irm_get_alpha", "hirm_irm_get_tables",
-    "hirm_engine_relation_scores", "hirm_irm_seat_entities",
+    "hirm_engine_relation_scores", "hirm_irm_seat_entities", "hirm_engine_debug_score_delta",
 ]
 
 _lib = None
@@ -91,6 +91,7 @@ def load():
     L.hirm_irm_get_tables.argtypes = [V, ctypes.c_int32, I, c_i32p, c_i32p, I, c_i32p]
     L.hirm_engine_relation_scores.argtypes = [V, ctypes.c_int32, I, I, c_i32p, c_i32p, c_f64p]
     L.hirm_irm_seat_entities.argtypes = [V, ctypes.c_int32, I, I, c_i32p, c_i32p]
+    L.hirm_engine_debug_score_delta.argtypes = [V, I, V, V, V, V, c_f64p]
     _lib = L
     return L
 
@@ -301,6 +302,13 @@ class Engine:
         it = np.ascontiguousarray(items, dtype=np.int32); lb = np.ascontiguousarray(labels, dtype=np.int32)
         assert len(it) == len(lb)
         self._ck(self.L.hirm_irm_seat_entities(self._h, irm, dom, len(it), _p(it, c_i32p), _p(lb, c_i32p)))
+
+    def debug_score_delta(self, N, s, gn, gs):
+        a = [np.ascontiguousarray(v, dtype=np.uint32) for v in (N, s, gn, gs)]
+        out = np.empty(max(len(a[0]), 1), np.float64)
+        self._ck(self.L.hirm_engine_debug_score_delta(self._h, len(a[0]), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+                                                      a[3].ctypes.data, _p(out, c_f64p)))
+        return out[:len(a[0])]
 
     def last_dense_plan(self):
         a, b, c, d = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()

@@ -168,6 +168,11 @@ int hirm_engine_last_dense_plan(hirm_engine *e, int32_t *ctas_per_sm, int32_t *s
 int hirm_engine_transpose_u8(hirm_engine *e, const uint8_t *d_in, int64_t rows, int64_t cols, int64_t pitch_in,
                              uint8_t *d_out, int64_t pitch_out);
 
+/* test hook: BetaBernoulli score difference S(N+n, s+sg) - S(N, s) (cxx/hirm.hh:52-56) for n operand quadruples,
+ * evaluated by the sweep kernels' own fp64 code */
+int hirm_engine_debug_score_delta(hirm_engine *e, int n, const uint32_t *h_N, const uint32_t *h_s, const uint32_t *h_gn,
+                                  const uint32_t *h_gs, double *h_out);
+
 /* debug hook: device buffer [n_blocks * 16] int64 that the dense kernel fills with SM cycles per role
  * (producer, accumulate warps, decision warps: see profiles/phase_breakdown.py); NULL switches it off */
 int hirm_engine_debug_phase_cycles(hirm_engine *e, long long *d_buf);

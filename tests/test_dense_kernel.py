@@ -231,3 +231,92 @@ def test_sweep_all_generic_kernel_multi_domain(eng):
     for r in range(len(spec.rnames)):
         np.testing.assert_array_equal(eng.get_counts(h, r), o.get_counts(r))
     eng.irm_destroy(h)
+
+
+def test_full_size_properties_and_scores():
+    """BASELINE config 3 at full size (n = 20000, 4e8 cells), where the oracle cannot follow: (1) after a sweep the
+    count table is still the histogram of (observations, z), bit for bit; (2) cell counts add up to n^2; (3) the
+    candidate log-probabilities of single moves equal an independent numpy / scipy evaluation of
+    logp_gibbs_exact's closed form from the table and the entity's row and column (1e-9 relative: this is where
+    the kernel's own fp64 log runs on counts of 1e8); (4) logp_score equals the sum over the table."""
+    import torch
+    from scipy.special import gammaln
+    import bench
+    n, kcap = 20000, 64
+    pitch = (n + 15) // 16 * 16
+    xh = torch.full((n, pitch), 0xFF, dtype=torch.uint8).pin_memory()
+    bench.planted_ree_into(xh.numpy(), n, seed=3)
+    x = xh.numpy()[:, :n]
+    e = E.Engine()
+    h = e.irm_create([n], [[0, 0]], max_tables=kcap)
+    e.set_observations_dense_host_ptr(h, 0, xh.data_ptr(), pitch)
+    e.finalize(h)
+    rng = np.random.default_rng(5)
+    z0 = (np.arange(n) >= n // 2).astype(np.int32)
+    z0[rng.choice(n, 40, replace=False)] = 2          # a small third table
+    z0[rng.choice(n, 300, replace=False)] = rng.integers(0, 2, 300)   # some entities in the wrong block
+    e.set_assignments(h, 0, z0)
+
+    def table_from(z):
+        K = z.max() + 1
+        oh = np.zeros((n, K), dtype=np.float64); oh[np.arange(n), z] = 1
+        cnt_ = oh.sum(0)
+        N = (cnt_[:, None] * cnt_[None, :]).astype(np.int64)
+        S = np.zeros((K, K))
+        for r0 in range(0, n, 1000):                   # float64 sums of 0/1 values are exact
+            S += oh[r0:r0 + 1000].T @ (x[r0:r0 + 1000].astype(np.float64) @ oh)
+        return N, np.rint(S).astype(np.int64)
+
+    def S_(N, s):
+        return gammaln(s + 1) + gammaln(N - s + 1) - gammaln(N + 2)
+
+    import mpmath
+    mpmath.mp.dps = 40
+
+    def S_mp(N, s):          # the same sum in 40 digits: differences of 1e9-sized sums need more than fp64
+        tot = mpmath.mpf(0)
+        for a, b in zip(np.ravel(N), np.ravel(s)):
+            a, b = int(a), int(b)
+            tot += mpmath.loggamma(b + 1) + mpmath.loggamma(a - b + 1) - mpmath.loggamma(a + 2)
+        return tot
+
+    # (3) single moves, score only
+    z = e.get_assignments(h, 0)
+    N, S = table_from(z)
+    cnt = np.bincount(z)
+    for item in [0, 7, int(np.flatnonzero(z == 2)[0]), n - 1]:
+        labels, lp = E.IrmBackend(e, h).score(0, item)
+        c = z[item]
+        zi = np.delete(z, item)
+        row, col = np.delete(x[item, :], item), np.delete(x[:, item], item)
+        K = N.shape[0]
+        rn = np.bincount(zi, minlength=K); rs = np.bincount(zi, weights=row, minlength=K).astype(np.int64)
+        cs = np.bincount(zi, weights=col, minlength=K).astype(np.int64)
+        d = int(x[item, item])
+        Nr, Sr = N.copy(), S.copy()                    # the table without the entity's observations
+        Nr[c, :] -= rn; Sr[c, :] -= rs; Nr[:, c] -= rn; Sr[:, c] -= cs; Nr[c, c] -= 1; Sr[c, c] -= d
+        want = []
+        for t in labels:
+            if t < K:
+                Nn, Sn = Nr.copy(), Sr.copy()
+                Nn[t, :] += rn; Sn[t, :] += rs; Nn[:, t] += rn; Sn[:, t] += cs; Nn[t, t] += 1; Sn[t, t] += d
+                w = cnt[t] - (t == c)
+                want.append(np.log(w if w > 0 else 1.0) + float(S_mp(Nn, Sn) - S_mp(Nr, Sr)))
+            else:                                      # the fresh table: row and column into empty cells
+                want.append(0.0 + float(S_mp(rn, rs) + S_mp(rn, cs) + S_mp([1], [d])))
+        want = np.asarray(want)
+        k = list(labels).index(c)
+        assert G.close((lp - lp[k]), (want - want[k]), rtol=1e-9), (item, lp, want)
+    # (1), (2), (4) after a sweep of 3000 moves
+    order = rng.permutation(n).astype(np.int32)[:3000]
+    e.sweep([h], [(np.zeros_like(order), order)], seed=2, streams=[0], counters=[0])
+    z = e.get_assignments(h, 0)
+    got = e.get_counts(h, 0)
+    lab, zc = np.unique(z, return_inverse=True)
+    N, S = table_from(zc)
+    want = np.asarray([[lab[a], lab[b], N[a, b], S[a, b]] for a in range(N.shape[0]) for b in range(N.shape[1]) if N[a, b] > 0], dtype=np.int64)
+    np.testing.assert_array_equal(got.astype(np.int64), want)
+    assert int(got[:, 2].sum()) == n * n
+    crp = len(lab) * np.log(1.0) + gammaln(np.bincount(zc)).sum() + gammaln(1.0) - gammaln(n + 1.0)
+    assert G.close(e.logp_score(h), S_(got[:, 2].astype(np.int64), got[:, 3].astype(np.int64)).sum() + crp, rtol=1e-12)
+    e.close()
