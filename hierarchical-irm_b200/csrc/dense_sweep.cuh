@@ -38,10 +38,9 @@
 namespace hirm {
 
 constexpr int DN_A_WARPS = 2;
-constexpr int DN_D_WARPS = 2;
+constexpr int DN_DW_SMALL = 2, DN_DW_LARGE = 6;       // decision warps of the 8-slot tier / of the larger tiers
 constexpr int DN_NA = 32 * DN_A_WARPS;
-constexpr int DN_ND = 32 * DN_D_WARPS;
-constexpr int DN_THREADS = 32 + DN_NA + DN_ND;   // warp 0 = producer, then the A warps, then the D warps
+// threads of a CTA = 32 (producer warp) + DN_NA (A warps) + 32 * DW (D warps)
 constexpr int DN_MAX_STAGES = 16;
 constexpr int DN_LF = 256;                        // shared-memory copy of lgamma(m+1), m < 256; Stirling (error < 1e-19) beyond
 
@@ -61,6 +60,7 @@ struct DenseLaunch {
                         // resumed by the next, larger tier -- see progress[] below)
     int32_t kcap;       // max_tables of the domain (slot space of the global state)
     int32_t np;         // bit planes of z kept in shared memory: 2^np >= kt
+    int32_t dw;         // decision warps of the kernel instance this layout is for
     int32_t full;       // 1: the relation has no missing cell and the domain no absent entity
     int32_t chunk;      // bytes of one row chunk (multiple of 32)
     int32_t nchunks;    // chunks per row
@@ -72,6 +72,7 @@ struct DenseLaunch {
 // Shared-memory carve-up: 8-byte things first, then 4-byte, then the ring (128-aligned).
 __host__ __device__ inline DenseLaunch dense_layout(int n, int kt, int kcap, int full, int chunk, int stages) {
     DenseLaunch L;
+    L.dw = kt <= 8 ? DN_DW_SMALL : DN_DW_LARGE;
     L.n = n; L.npad = (n + 15) & ~15; L.kt = kt; L.kcap = kcap; L.full = full;
     L.np = kt <= 8 ? 3 : kt <= 16 ? 4 : kt <= 32 ? 5 : 6;
     chunk &= ~31;
@@ -84,7 +85,7 @@ __host__ __device__ inline DenseLaunch dense_layout(int n, int kt, int kcap, int
     L.off_dbl = off;   off += 2 * (kt + 2) * 8;     // s_logcnt, s_logcntm1
     L.off_wpart = off; off += 2 * DN_A_WARPS * 4 * kt * 4;
     L.off_acc = off;   off += kt > 8 ? (full ? 1 : 2) * kt * DN_NA * 4 : 0;   // private accumulators of the > 8 tables path
-    L.off_ints = off;  off += (2 * DN_D_WARPS * 4 * kt + 3 * kt + kcap + 8) * 4;   // g[2][D warps][4kt], s_cnt, s_lab, s_order, s_map[kcap]
+    L.off_ints = off;  off += (2 * L.dw * 4 * kt + 3 * kt + kcap + 8) * 4;   // g[2][D warps][4kt], s_cnt, s_lab, s_order, s_map[kcap]
     L.off_zp = off;    off += ((n + 31) / 32) * L.np * 4;
     off = (off + 127) & ~127;
     L.off_ring = off;  off += stages * 2 * chunk;
@@ -121,7 +122,8 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 }
 __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
 // named barrier among the D warps only
-__device__ __forceinline__ void bar_d() { asm volatile("bar.sync 1, %0;" ::"n"(DN_ND) : "memory"); }
+template <int ND>
+__device__ __forceinline__ void bar_d() { asm volatile("bar.sync 1, %0;" ::"n"(ND) : "memory"); }
 
 // (n, s) of one observation byte
 __device__ __forceinline__ int byte_n(uint32_t x) { return (x & 0x80u) ? 0 : 1; }
@@ -361,7 +363,11 @@ __device__ __forceinline__ void a_move(const APar p, RingCursor &cur, const int 
     else a_move_acc<6, FULL>(p, cur, a, lane, acc, K, wp);
 }
 
-__global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArgs args, const int32_t *blk_list, DenseLaunch L) {
+// DW = decision warps: 2 for the small-table tier (most chains per SM), more for the tiers whose chains have many
+// tables (the score is K^2 cells: more lanes, fewer rounds).
+template <int DW, int MINB>
+__global__ void __launch_bounds__(32 + DN_NA + 32 * DW, MINB) dense_ree_sweep_kernel(SweepArgs args, const int32_t *blk_list, DenseLaunch L) {
+    constexpr int ND = 32 * DW, NTHREADS = 32 + DN_NA + ND;
     const int k_list = blk_list ? blk_list[blockIdx.x] : blockIdx.x;
     const IrmDev &irm = args.irms[args.irm_ids[k_list]];
     const DomainDev &dd = irm.dom[0];
@@ -389,14 +395,14 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
     int32_t *wpart = reinterpret_cast<int32_t *>(smem + L.off_wpart);            // [2][A_WARPS][4*kt] per-warp group sums
     uint32_t *acc = reinterpret_cast<uint32_t *>(smem + L.off_acc);              // [F*kt][DN_NA] (kt > 8 only)
     int32_t *g_buf = reinterpret_cast<int32_t *>(smem + L.off_ints);             // [2][D warps][4*kt]: (rn, rs, cn, cs) per other-slot, one copy per D warp
-    int32_t *s_cnt = g_buf + 2 * DN_D_WARPS * 4 * kt, *s_lab = s_cnt + kt;                        // CRP table sizes / labels per slot
+    int32_t *s_cnt = g_buf + 2 * DW * 4 * kt, *s_lab = s_cnt + kt;                        // CRP table sizes / labels per slot
     int32_t *s_order = s_lab + kt, *s_map = s_order + kt;                        // slots by ascending label; load-time slot map
     uint32_t *zp = reinterpret_cast<uint32_t *>(smem + L.off_zp);                // [G][np] bit planes of the slot of every entity
     const int NP = L.np, G = (n + 31) >> 5;
     uint8_t *ring = smem + L.off_ring;                                           // [NS][2][chunk]
     __shared__ int32_t s_K, s_KA;
     __shared__ MoveCtl s_ctl[DN_CTL];
-    __shared__ double s_val[2 * DN_ND];                   // one round of cell scores, double-buffered
+    __shared__ double s_val[2 * ND];                   // one round of cell scores, double-buffered
     __shared__ int32_t s_has_absent;
     __shared__ long long s_limit, s_issued, s_consumed, s_done;
     __shared__ long long s_ph[14];                        // profiling only   // first move NOT to be made (tier overflow); ring chunks issued / consumed
@@ -433,14 +439,14 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     #pragma unroll 1
-    for (int k = tid; k < kt * kt; k += DN_THREADS) table[k] = 0;
+    for (int k = tid; k < kt * kt; k += NTHREADS) table[k] = 0;
     #pragma unroll 1
-    for (int k = tid; k < DN_LF; k += DN_THREADS) s_lf[k] = g_logfact[k];
+    for (int k = tid; k < DN_LF; k += NTHREADS) s_lf[k] = g_logfact[k];
     __syncthreads();
     const int K0 = s_K;
     if (K0 > kt) return;                                       // more live tables than this tier holds: left to the next tier
     #pragma unroll 1
-    for (int g = warp; g < G; g += DN_THREADS / 32) {          // a warp turns 32 assignments into one word per plane
+    for (int g = warp; g < G; g += NTHREADS / 32) {          // a warp turns 32 assignments into one word per plane
         const int j = 32 * g + lane;
         const int zj = j < n ? z_g[j] : 0;
         if (zj < 0) s_has_absent = 1;                          // rare: moves must then be checked against z = -1
@@ -452,13 +458,13 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
         }
     }
     #pragma unroll 1
-    for (int k = tid; k < hi_g * hi_g; k += DN_THREADS) {
+    for (int k = tid; k < hi_g * hi_g; k += NTHREADS) {
         const int a = k % hi_g, b = k / hi_g;
         const cell_t v = R.counts[a + b * kcap_g];
         if (v) table[s_map[a] + s_map[b] * kt] = v;            // cells of dead slots are empty
     }
     #pragma unroll 1
-    for (int k = tid; k < K0; k += DN_THREADS) {
+    for (int k = tid; k < K0; k += NTHREADS) {
         int rank = 0;
         const int lb = s_lab[k];
         #pragma unroll 1
@@ -571,7 +577,7 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
         if (prof) { args.phase_cycles[blockIdx.x * 32 + 2] = clk() - a_t0; args.phase_cycles[blockIdx.x * 32 + 3] = a_go; }
     } else {
         // =============================== D: decide =========================================
-        const int d = tid - 32 - DN_NA;                        // 0..DN_ND-1
+        const int d = tid - 32 - DN_NA;                        // 0..ND-1
         const int dwarp = d >> 5;
         const double logalpha = log_nl(alpha);
         int K = K0;                                            // live slots 0..K-1 (uniform across D threads)
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
             const int64_t m = m0 + r;
             const int64_t rr = r - r_begin;                    // barrier phases count from this launch's first move
             const int buf = (int)(rr & 1);
-            int32_t *g = g_buf + (buf * DN_D_WARPS + dwarp) * 4 * kt;     // this warp's copy of the group sums
+            int32_t *g = g_buf + (buf * DW + dwarp) * 4 * kt;     // this warp's copy of the group sums
             DPHASE(5);
             mbar_wait(&bar_ready[buf], (uint32_t)((rr >> 1) & 1));
             DPHASE(0);
@@ -631,14 +637,14 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
             }
             __syncwarp();
             if (pend_dead >= 0) {
-                bar_d();
+                bar_d<ND>();
                 // ---- the table that died in move r-1 is replaced by the last slot ------------------
                 const int dead = pend_dead, last = K - 1;
                 if (dead != last) {
-                    planes_rename(zp, NP, G, last, dead, d, DN_ND);
+                    planes_rename(zp, NP, G, last, dead, d, ND);
                     // row/column `last` -> `dead` (row/column `dead` is all zero)
                     #pragma unroll 1
-                    for (int k = d; k < K; k += DN_ND) {
+                    for (int k = d; k < K; k += ND) {
                         if (k != last && k != dead) {
                             table[dead + k * kt] = table[last + k * kt]; table[last + k * kt] = 0;
                             table[k + dead * kt] = table[k + last * kt]; table[k + last * kt] = 0;
@@ -646,8 +652,8 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
                             table[dead + dead * kt] = table[last + last * kt]; table[last + last * kt] = 0;
                         }
                     }
-                    if (d < 4 * DN_D_WARPS) {
-                        int32_t *gw = g_buf + (buf * DN_D_WARPS + (d >> 2)) * 4 * kt;
+                    if (d < 4 * DW) {
+                        int32_t *gw = g_buf + (buf * DW + (d >> 2)) * 4 * kt;
                         gw[4 * dead + (d & 3)] = gw[4 * last + (d & 3)]; gw[4 * last + (d & 3)] = 0;
                     }
                     if (d == 4) {
@@ -660,7 +666,7 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
                 }
                 K -= 1;
                 pend_dead = -1;
-                bar_d();
+                bar_d<ND>();
                 if (d == 0) { s_KA = K; mbar_arrive(bar_go); }
             }
             pend_changed = false;
@@ -698,7 +704,7 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
 
             // ---- score.  logp_gibbs_exact (cxx/hirm.hh:441-461): for every candidate t the sum over its 2K+1 target
             //      cells of S(N+n, s+sg) - S(N, s), with (N, s) the cell WITHOUT i's own observations.  The
-            //      (candidate, cell) pairs are laid flat over the D lanes, DN_ND per round; a lane evaluates one
+            //      (candidate, cell) pairs are laid flat over the D lanes, ND per round; a lane evaluates one
             //      cell (branch-free, six independent log chains).  Then lane t of EVERY D warp adds up candidate
             //      t's cells in index order (a segmented reduction with a fixed order: deterministic, and identical
             //      in both warps), so that each warp can go on to draw the table by itself.
@@ -710,7 +716,7 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
                 const int IPC = 2 * K + 1, total = ncand * IPC;
                 const cell_t rem_cc = pack_cell((uint32_t)(g[4 * c] + g[4 * c + 2] + d_n), (uint32_t)(g[4 * c + 1] + g[4 * c + 3] + d_s));
                 #pragma unroll 1
-                for (int base = 0; base < total; base += DN_ND) {
+                for (int base = 0; base < total; base += ND) {
                     const int w = base + d;
                     uint32_t N = 0u, sv = 0u, gn = 0u, gs = 0u;
                     if (w < total) {                           // gather the cell's operands (cheap; lanes may diverge)
@@ -742,15 +748,15 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
                         N = cell_n(cur); sv = cell_s(cur);
                     }
                     __syncwarp();
-                    s_val[vb * DN_ND + d] = score_delta_bf<DN_LF>(s_lf, N, sv, gn, gs);
-                    bar_d();
+                    s_val[vb * ND + d] = score_delta_bf<DN_LF>(s_lf, N, sv, gn, gs);
+                    bar_d<ND>();
 #pragma unroll
                     for (int j = 0; j < MAXJ; j++) {
                         const int t = lane + 32 * j;
                         if (t < ncand) {
-                            const int w0 = max(t * IPC, base) - base, w1 = min((t + 1) * IPC, base + DN_ND) - base;
+                            const int w0 = max(t * IPC, base) - base, w1 = min((t + 1) * IPC, base + ND) - base;
                             #pragma unroll 1
-                            for (int ww = w0; ww < w1; ww++) lp[j] += s_val[vb * DN_ND + ww];
+                            for (int ww = w0; ww < w1; ww++) lp[j] += s_val[vb * ND + ww];
                         }
                     }
                     vb ^= 1;
@@ -831,9 +837,9 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
             // ---- apply, only if the table changed ------------------------------------------------------
             if (tnew != c) {
                 const bool died = singleton;
-                bar_d();                                       // both D warps have drawn: the bookkeeping below may be rewritten
+                bar_d<ND>();                                       // both D warps have drawn: the bookkeeping below may be rewritten
                 #pragma unroll 1
-                for (int k = d; k < K; k += DN_ND) {          // i's observations leave row / column c
+                for (int k = d; k < K; k += ND) {          // i's observations leave row / column c
                     if (k != c) {
                         table[c + k * kt] -= pack_cell((uint32_t)g[4 * k], (uint32_t)g[4 * k + 1]);
                         table[k + c * kt] -= pack_cell((uint32_t)g[4 * k + 2], (uint32_t)g[4 * k + 3]);
@@ -841,7 +847,7 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
                         table[c + c * kt] -= pack_cell((uint32_t)(g[4 * c] + g[4 * c + 2] + d_n), (uint32_t)(g[4 * c + 1] + g[4 * c + 3] + d_s));
                     }
                 }
-                if (d == DN_ND - 1) {                          // Domain::set_cluster_assignment_gibbs (cxx/hirm.hh:219-224)
+                if (d == ND - 1) {                          // Domain::set_cluster_assignment_gibbs (cxx/hirm.hh:219-224)
                     s_cnt[c] -= 1;
                     if (tnew == K) { s_cnt[K] = 1; s_lab[K] = newlabel; s_order[K] = K; }
                     else s_cnt[tnew] += 1;
@@ -853,10 +859,10 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
                         for (int t = pos; t + 1 < K; t++) s_order[t] = s_order[t + 1];
                     }
                 }
-                bar_d();
+                bar_d<ND>();
                 const int K2 = max(K, tnew + 1);
                 #pragma unroll 1
-                for (int k = d; k < K2; k += DN_ND) {         // ... and enter row / column tnew
+                for (int k = d; k < K2; k += ND) {         // ... and enter row / column tnew
                     if (k != tnew) {
                         table[tnew + k * kt] += pack_cell((uint32_t)g[4 * k], (uint32_t)g[4 * k + 1]);
                         table[k + tnew * kt] += pack_cell((uint32_t)g[4 * k + 2], (uint32_t)g[4 * k + 3]);
@@ -864,8 +870,8 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
                         table[tnew + tnew * kt] += pack_cell((uint32_t)(g[4 * k] + g[4 * k + 2] + d_n), (uint32_t)(g[4 * k + 1] + g[4 * k + 3] + d_s));
                     }
                 }
-                if (d >= DN_ND - 4) {                          // cached log(count), log(count - 1) of the two tables
-                    const int j = d - (DN_ND - 4);
+                if (d >= ND - 4) {                          // cached log(count), log(count - 1) of the two tables
+                    const int j = d - (ND - 4);
                     const int slot = (j & 2) ? tnew : c;
                     const int cnt = s_cnt[slot] - (j & 1);
                     const double v = log_nl((double)max(cnt, 1));
@@ -874,22 +880,22 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
                 pend_changed = true; pend_item = item; pend_old = c; pend_new = tnew;
                 if (tnew == K) K += 1;
                 if (died) pend_dead = c;
-                bar_d();                                       // the table and the cached logs are final before anyone scores again
+                bar_d<ND>();                                       // the table and the cached logs are final before anyone scores again
             }
             DPHASE(4);
         }
         if (prof) for (int i = 0; i < 14; i++) args.phase_cycles[blockIdx.x * 32 + 8 + i] = s_ph[i];
 #undef DPHASE
         // ---- finish the last move -----------------------------------------------------------------
-        bar_d();
+        bar_d<ND>();
         if (pend_changed && d == 0) planes_set(zp, NP, pend_item, pend_new);
-        bar_d();
+        bar_d<ND>();
         if (pend_dead >= 0) {
             const int dead = pend_dead, last = K - 1;
             if (dead != last) {
-                planes_rename(zp, NP, G, last, dead, d, DN_ND);
+                planes_rename(zp, NP, G, last, dead, d, ND);
                 #pragma unroll 1
-                for (int k = d; k < K; k += DN_ND) {
+                for (int k = d; k < K; k += ND) {
                     if (k != last && k != dead) {
                         table[dead + k * kt] = table[last + k * kt]; table[last + k * kt] = 0;
                         table[k + dead * kt] = table[k + last * kt]; table[k + last * kt] = 0;
@@ -917,15 +923,15 @@ __global__ void __launch_bounds__(DN_THREADS, 5) dense_ree_sweep_kernel(SweepArg
     // ---- store state (slots 0..K-1, compact) ------------------------------------------------
     const int Kf = s_K;
     #pragma unroll 1
-    for (int j = tid; j < n; j += DN_THREADS) if (z_g[j] >= 0) z_g[j] = planes_get(zp, NP, j);
+    for (int j = tid; j < n; j += NTHREADS) if (z_g[j] >= 0) z_g[j] = planes_get(zp, NP, j);
     const int span = max(hi_g, Kf);
     #pragma unroll 1
-    for (int k = tid; k < span * span; k += DN_THREADS) {
+    for (int k = tid; k < span * span; k += NTHREADS) {
         const int a = k % span, b = k / span;
         R.counts[a + b * kcap_g] = (a < Kf && b < Kf) ? table[a + b * kt] : (cell_t)0;
     }
     #pragma unroll 1
-    for (int k = tid; k < span; k += DN_THREADS) {
+    for (int k = tid; k < span; k += NTHREADS) {
         dd.tab_count[k] = k < Kf ? s_cnt[k] : 0;
         if (k < Kf) dd.tab_label[k] = s_lab[k];
     }

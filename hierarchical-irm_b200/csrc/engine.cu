@@ -113,7 +113,7 @@ struct hirm_engine {
     DevBuf<uint64_t> s_sweep0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
-    int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0, dense_static_smem = 0;
+    int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0, dense_static_smem = 0, dense_static_smem_large = 0;
     long long *d_phase_cycles = nullptr;   // debug hook (hirm_engine_debug_phase_cycles)
 };
 
@@ -148,8 +148,10 @@ extern "C" int hirm_engine_create(hirm_engine **out, int device) {
     e->num_sms = prop.multiProcessorCount;
     e->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, dense_ree_sweep_kernel));
+    CK(cudaFuncGetAttributes(&fa, dense_ree_sweep_kernel<DN_DW_SMALL, 5>));
     e->dense_static_smem = (int)fa.sharedSizeBytes + 64;
+    CK(cudaFuncGetAttributes(&fa, dense_ree_sweep_kernel<DN_DW_LARGE, 3>));
+    e->dense_static_smem_large = (int)fa.sharedSizeBytes + 64;
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
     // log-factorial table from libm's lgamma (the reference's lbeta, cxx/util_math.cc:13-15)
@@ -826,18 +828,32 @@ struct Plan {
 // Shared-memory plan of one dense tier: as many chains per SM as the launch has (up to 5: the register budget) and fit; the rest of
 // each CTA's share of the SM's shared memory goes to its TMA ring.
 static bool plan_dense_tier(hirm_engine *e, int n, int kt, int kcap, int full, int n_dense, DenseLaunch &L) {
-    int chunk = 64 * DN_NA, want = std::min(5, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
+    const DenseLaunch probe = dense_layout(n, kt, kcap, full, 32, 0);
+    const bool small = probe.dw == DN_DW_SMALL;            // kernel instance: registers allow 5 (small) / 3 (large) CTAs per SM
+    int chunk = 64 * DN_NA, want = std::min(small ? 5 : 3, std::max(1, (n_dense + e->num_sms - 1) / e->num_sms));
     if (const char *s = getenv("HIRM_DENSE_CHUNK")) chunk = std::max(32, atoi(s) & ~31);
-    if (const char *s = getenv("HIRM_DENSE_CTAS_PER_SM")) want = std::max(1, atoi(s));
+    if (const char *s = getenv("HIRM_DENSE_CTAS_PER_SM")) want = std::max(1, std::min(atoi(s), small ? 5 : 3));
     L = DenseLaunch{};
     for (; want >= 1; want--) {
-        const int budget = std::min(e->max_smem_optin, e->smem_per_sm / want - 1024) - e->dense_static_smem;   // 1 KiB reserved per CTA + the kernel's static shared memory
+        const int budget = std::min(e->max_smem_optin, e->smem_per_sm / want - 1024) - (small ? e->dense_static_smem : e->dense_static_smem_large);   // 1 KiB reserved per CTA + the kernel's static shared memory
         const DenseLaunch L0 = dense_layout(n, kt, kcap, full, chunk, 0);
         int stages = (budget - L0.total_bytes) / (2 * L0.chunk);
         stages = std::min(stages, std::min(DN_MAX_STAGES, 2 * L0.nchunks + 2));
         if (stages >= 2 || (want == 1 && stages >= 1)) { L = dense_layout(n, kt, kcap, full, chunk, stages); return true; }
     }
     return false;
+}
+
+static int launch_dense_tier(hirm_engine *e, const DenseLaunch &L, unsigned nb, const SweepArgs &a, const int32_t *blk) {
+    if (L.dw == DN_DW_SMALL) {
+        CK(cudaFuncSetAttribute(dense_ree_sweep_kernel<DN_DW_SMALL, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes));
+        dense_ree_sweep_kernel<DN_DW_SMALL, 5><<<nb, 32 + DN_NA + 32 * DN_DW_SMALL, (size_t)L.total_bytes, e->stream>>>(a, blk, L);
+    } else {
+        CK(cudaFuncSetAttribute(dense_ree_sweep_kernel<DN_DW_LARGE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes));
+        dense_ree_sweep_kernel<DN_DW_LARGE, 3><<<nb, 32 + DN_NA + 32 * DN_DW_LARGE, (size_t)L.total_bytes, e->stream>>>(a, blk, L);
+    }
+    CK(cudaGetLastError());
+    return 0;
 }
 
 static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_t flags, Plan &plan) {
@@ -899,18 +915,15 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
             CK(cudaMemsetAsync(e->s_progress.p, 0, nb * sizeof(long long), e->stream));
             a2.progress = e->s_progress.p;
         }
-        int smem_max = 0;
-        for (const DenseLaunch &L : plan.tiers) smem_max = std::max(smem_max, L.total_bytes);
-        CK(cudaFuncSetAttribute(dense_ree_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         for (const DenseLaunch &L : plan.tiers) {
-            dense_ree_sweep_kernel<<<nb, DN_THREADS, (size_t)L.total_bytes, e->stream>>>(a2, e->s_blk.p + plan.generic_blk.size(), L);
-            CK(cudaGetLastError());
+            if (launch_dense_tier(e, L, nb, a2, e->s_blk.p + plan.generic_blk.size())) return -1;
             e->last_launches++;
         }
         e->last_kind = 1;
         const DenseLaunch &L0 = plan.tiers.front();
         int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense_ree_sweep_kernel, DN_THREADS, (size_t)L0.total_bytes);
+        if (L0.dw == DN_DW_SMALL) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense_ree_sweep_kernel<DN_DW_SMALL, 5>, 32 + DN_NA + 32 * DN_DW_SMALL, (size_t)L0.total_bytes);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense_ree_sweep_kernel<DN_DW_LARGE, 3>, 32 + DN_NA + 32 * DN_DW_LARGE, (size_t)L0.total_bytes);
         e->last_occupancy = occ; e->last_stages = L0.stages; e->last_chunk = L0.chunk; e->last_smem = L0.total_bytes;
     }
     CK(cudaEventRecord(e->ev1, e->stream));
