@@ -144,6 +144,12 @@ __global__ void __launch_bounds__(AUX_THREADS) debug_score_delta_kernel(const ui
     }
 }
 
+// live-table bound (highest used slot + 1) of domain 0 of every listed IRM: the dense sweep's cost estimate per chain
+__global__ void gather_hi_kernel(const IrmDev *irms, const int32_t *ids, int n, int32_t *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = *irms[ids[k]].dom[0].hi;
+}
+
 __device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; }
 
 // Sweep order (the loops of cxx/hirm.cc:45-51 / IRM::transition_cluster_assignments_all, cxx/hirm.hh:590-596): for every

@@ -894,6 +894,26 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
             plan.generic_blk.push_back(k);
         }
     }
+    // More dense chains than fit on the GPU at once: the launch ends with its slowest chain, so the chains with the
+    // most live tables (the cost of a move grows with them) go first and the block scheduler fills in the cheap ones
+    // (longest-processing-time-first).
+    if ((int)plan.dense_blk.size() > 5 * e->num_sms) {
+        const int nd = (int)plan.dense_blk.size();
+        std::vector<int32_t> ids((size_t)nd), hi((size_t)nd);
+        for (int j = 0; j < nd; j++) ids[(size_t)j] = h_irms[plan.dense_blk[(size_t)j]];
+        CK(e->s_irm_ids.ensure((size_t)nd)); CK(e->s_choice.ensure((size_t)nd));
+        CK(cudaMemcpyAsync(e->s_irm_ids.p, ids.data(), nd * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        gather_hi_kernel<<<(nd + 255) / 256, 256, 0, e->stream>>>(e->d_irms.p, e->s_irm_ids.p, nd, e->s_choice.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(hi.data(), e->s_choice.p, nd * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        std::vector<int> order((size_t)nd);
+        for (int j = 0; j < nd; j++) order[(size_t)j] = j;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hi[(size_t)a] > hi[(size_t)b]; });
+        std::vector<int32_t> sorted((size_t)nd);
+        for (int j = 0; j < nd; j++) sorted[(size_t)j] = plan.dense_blk[(size_t)order[(size_t)j]];
+        plan.dense_blk.swap(sorted);
+    }
     return 0;
 }
 
