@@ -1,0 +1,77 @@
+"""The reference's text formats and command line on the engine (hirm.util_io, hirm.cli after cxx/util_io.cc and
+cxx/hirm.cc:92-195).  CPU: parsers and writers.  GPU: the CLI end to end on animals.unary rebuilt from the golden
+fixture -- messages, output file format, --load restart (the reference's own smoke lines, cxx/Makefile:45-47)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import golden_util as G
+from hirm import IRM, cli, util_io
+
+
+def write_dataset(tmp, case):
+    fx = G.load(case)
+    rels = {}
+    for irm in fx["irms"]:
+        for r in irm["relations"]:
+            rels[r["name"]] = (list(r["domains"]), np.asarray(r["obs"], dtype=np.int64).reshape(-1, len(r["domains"]) + 1))
+    base = os.path.join(str(tmp), case)
+    with open(base + ".schema", "w") as f:
+        for r, (ds, _) in sorted(rels.items()):
+            f.write("bernoulli %s %s\n" % (r, " ".join(ds)))
+    with open(base + ".obs", "w") as f:
+        for r, (ds, a) in sorted(rels.items()):
+            for row in a:
+                f.write("%d %s %s\n" % (row[-1], r, " ".join("%s%d" % (d[:2], x) for d, x in zip(ds, row[:-1]))))
+    return base, rels
+
+
+def test_parsers_and_irm_writer_roundtrip(tmp_path):
+    base, rels = write_dataset(tmp_path, "two_relations_irm")
+    schema = util_io.load_schema(base + ".schema")
+    obs = util_io.load_observations(base + ".obs")
+    assert set(schema) == set(rels) and all(schema[r] == rels[r][0] for r in rels)
+    assert len(obs) == sum(len(a) for _, a in rels.values()) and all(v in (0, 1) for _, _, v in obs)
+    irm = IRM(schema, prng=random.Random(2))
+    for r, items, v in obs:
+        irm.incorporate(r, items, v)
+    path = base + ".2.irm"
+    util_io.to_txt_irm(path, irm)                       # no device needed: the seats are the host CRP-prior draws
+    lines = open(path).read().splitlines()
+    assert all(len(l.split()) >= 3 and l.split()[1].isdigit() for l in lines)
+    clusters = util_io.load_clusters_irm(path)
+    for d, dom in irm.domains.items():
+        got = {t: set(items) for t, items in clusters[d].items()}
+        assert got == {t: {str(i) for i in members} for t, members in dom.crp.tables.items()}
+    again = util_io.from_txt_irm(IRM({}, prng=random.Random(3)), base + ".schema", base + ".obs", path)
+    for d in irm.domains:                               # check_irms_agree, tests/test_basic.py:96-103
+        assert again.domains[d].crp.assignments == irm.domains[d].crp.assignments
+    for r in irm.relations:
+        assert again.relations[r].data == irm.relations[r].data and again.relations[r].data_r == irm.relations[r].data_r
+
+
+@pytest.mark.gpu
+def test_cli_hirm_and_irm_end_to_end(tmp_path, capsys):
+    base, rels = write_dataset(tmp_path, "animals_unary_hirm")
+    assert cli.main(["--seed", "1", "--iters", "5", base]) == 0
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == "setting seed to 1" and out[1] == "loading schema from %s.schema" % base
+    assert "selected model is HIRM" in out and "inferring 5 iters; timeout 0" in out and out[-1] == "saving to %s.1.hirm" % base
+    relations, irms = util_io.load_clusters_hirm(base + ".1.hirm")
+    assert sorted(r for rs in relations.values() for r in rs) == sorted(rels)           # every relation in exactly one cluster
+    assert set(irms) == set(relations)
+    for t, doms in irms.items():                                                        # every animal seated once per IRM
+        members = [e for items in doms["animal"].values() for e in items]
+        assert len(members) == len(set(members)) == 50
+    # restart from the saved clusters (cxx/Makefile:47)
+    assert cli.main(["--seed", "2", "--iters", "2", "--load", base + ".1.hirm", base]) == 0
+    assert os.path.exists(base + ".2.hirm")
+    # IRM mode with --verbose
+    assert cli.main(["--mode", "irm", "--iters", "3", "--verbose", base]) == 0
+    out = capsys.readouterr().out.splitlines()
+    assert "selected model is IRM" in out and out[-1] == "saving to %s.10.irm" % base
+    clusters = util_io.load_clusters_irm(base + ".10.irm")
+    assert sum(len(v) for v in clusters["animal"].values()) == 50
+    assert cli.main(["--mode", "nope", base]) == 1
