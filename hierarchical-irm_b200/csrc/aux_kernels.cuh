@@ -129,6 +129,199 @@ __global__ void __launch_bounds__(AUX_THREADS) rel_score_kernel(const RelCand *c
     if (threadIdx.x == 0) out[blockIdx.x] = total;
 }
 
+// ---------------------------------------------------------------------------------------
+// K4 batched: the whole [relations x candidate partitions] matrix of Relation::logp_score values that one
+// sweep of HIRM::transition_cluster_assignment_relation needs (cxx/hirm.hh:859-866), in two launches.
+// The score of relation r under IRM k depends only on r's observations and k's domain partitions, never on which
+// other relations sit in k, so it can be computed for every pair before the sequential re-seating of the relations.
+// Observations are relation-owned COO arrays (caller's device buffers); a candidate is a set of slot arrays, one
+// per domain.  Work item = (relation, run of candidates, run of observations): the COO run is read once for the
+// whole run of candidates; histograms live in shared memory when (candidates x cells) fits, and are flushed to the
+// global scratch tables with integer atomics (exact, order-free).  Pass 2 sums the cell scores with a fixed tree.
+constexpr int RM_SH_CELLS = 4096;       // shared-memory histogram cells per work item (2 x uint32 each)
+struct RelDesc {
+    const int32_t *ids; const uint8_t *val; int64_t nobs;
+    int32_t arity; int32_t dom[MAX_ARITY];
+    int64_t stride[MAX_ARITY];          // scratch-table stride per position
+    int64_t ncells;
+};
+struct PartSet { const int32_t *z[MAX_DOMAINS]; };
+struct ScoreWork {
+    int32_t rel, cand0, ncand, pad;     // candidates cand0 .. cand0 + ncand - 1 of the partition-set array
+    int64_t obs0, obs1;
+    int64_t table0;                     // scratch offset of (rel, cand0); candidate c of the run sits at table0 + c * ncells
+};
+__global__ void __launch_bounds__(AUX_THREADS) relmat_hist_kernel(const RelDesc *rels, const PartSet *parts, const ScoreWork *work,
+                                                                  cell_t *tables, int32_t *error) {
+    const ScoreWork W = work[blockIdx.x];
+    const RelDesc R = rels[W.rel];
+    __shared__ uint32_t sh_n[RM_SH_CELLS], sh_s[RM_SH_CELLS];
+    const int64_t run_cells = R.ncells * W.ncand;
+    const bool use_sh = run_cells <= RM_SH_CELLS;
+    if (use_sh) {
+        for (int i = threadIdx.x; i < run_cells; i += blockDim.x) { sh_n[i] = 0u; sh_s[i] = 0u; }
+        __syncthreads();
+    }
+    for (int64_t o = W.obs0 + threadIdx.x; o < W.obs1; o += blockDim.x) {
+        int32_t id[MAX_ARITY];
+        for (int p = 0; p < R.arity; p++) id[p] = R.ids[o * R.arity + p];
+        const uint32_t v = R.val[o];
+        for (int c = 0; c < W.ncand; c++) {
+            const PartSet &P = parts[W.cand0 + c];
+            int64_t idx = 0; bool absent = false;
+            for (int p = 0; p < R.arity; p++) {
+                const int slot = P.z[R.dom[p]][id[p]];
+                if (slot < 0) absent = true;
+                idx += (slot < 0 ? 0 : slot) * R.stride[p];
+            }
+            if (absent) { atomicCAS(error, 0, KERR_ABSENT_ENTITY); continue; }
+            if (use_sh) {
+                const int j = (int)(c * R.ncells + idx);
+                atomicAdd(&sh_n[j], 1u);
+                if (v) atomicAdd(&sh_s[j], 1u);
+            } else {
+                atomicAdd(&tables[W.table0 + c * R.ncells + idx], pack_cell(1u, v));
+            }
+        }
+    }
+    if (use_sh) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < run_cells; i += blockDim.x)
+            if (sh_n[i]) atomicAdd(&tables[W.table0 + i], pack_cell(sh_n[i], sh_s[i]));
+    }
+}
+struct TableRef { int64_t off, ncells; };
+__global__ void __launch_bounds__(AUX_THREADS) relmat_score_kernel(const TableRef *refs, const cell_t *tables, double *out) {
+    const TableRef T = refs[blockIdx.x];
+    __shared__ double s_part[AUX_THREADS / 32];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < T.ncells; i += blockDim.x) {
+        const cell_t c = tables[T.off + i];
+        if (cell_n(c)) acc += cell_score(cell_n(c), cell_s(c));
+    }
+    const double total = block_sum(acc, s_part);
+    if (threadIdx.x == 0) out[blockIdx.x] = total;
+}
+
+// A draw from the sequential CRP(alpha) prior over n customers -- what Domain::incorporate (cxx/hirm.hh:194-203 ->
+// CRP::sample :101-113) does to the entities of a relation that opens a fresh IRM (:849-864) -- without the sequential
+// loop: customer i opens a table with probability alpha / (i + alpha), otherwise joins the table of a uniformly drawn
+// earlier customer (the two descriptions of the CRP are the same law); tables are labelled in order of appearance
+// (new label = tables so far, as CRP::tables_weights :133-146 gives).  One CTA per draw: Philox per customer,
+// block prefix count of the openers, in-place pointer jumping to the opener of each customer's table.
+constexpr uint64_t PRIOR_SEED_TAG = 0x7072696f72ull;    // "prior"
+constexpr int PRIOR_THREADS = 1024;
+struct PriorDraw { int32_t *z; int32_t *cum; int32_t n; int32_t kcap; uint64_t key; double alpha; };
+__global__ void __launch_bounds__(PRIOR_THREADS) crp_prior_kernel(const PriorDraw *draws, uint64_t seed, int32_t *error) {
+    const PriorDraw D = draws[blockIdx.x];
+    __shared__ int32_t s_warp[PRIOR_THREADS / 32];
+    __shared__ int32_t s_base, s_changed;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < D.n; i0 += PRIOR_THREADS) {
+        const int i = i0 + tid;
+        int opener = 0;
+        if (i < D.n) {
+            const double u = philox_uniform(seed ^ PRIOR_SEED_TAG, D.key, 2ull * (uint64_t)i);
+            const double v = philox_uniform(seed ^ PRIOR_SEED_TAG, D.key, 2ull * (uint64_t)i + 1ull);
+            opener = i == 0 || u * ((double)i + D.alpha) < D.alpha;
+            int par = i;
+            if (!opener) { par = (int)(v * (double)i); if (par >= i) par = i - 1; }
+            D.z[i] = par;
+        }
+        int incl = opener;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int w = 0; w < PRIOR_THREADS / 32; w++) { const int t = s_warp[w]; if (w < warp) woff += t; total += t; }
+        if (i < D.n) D.cum[i] = s_base + woff + incl;     // openers among customers 0..i
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
+    }
+    if (tid == 0 && s_base > D.kcap) atomicCAS(error, 0, KERR_NO_FREE_SLOT);
+    // pointer jumping: z[i] <- z[z[i]] until every customer points at an opener (pointers only move towards openers,
+    // so reading a neighbour's old or new value is equally good)
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        int changed = 0;
+        for (int i = tid; i < D.n; i += PRIOR_THREADS) {
+            const int p = ((volatile int32_t *)D.z)[i], pp = ((volatile int32_t *)D.z)[p];
+            if (pp != p) { ((volatile int32_t *)D.z)[i] = pp; changed = 1; }
+        }
+        if (changed) s_changed = 1;
+        __syncthreads();
+        if (!s_changed) break;
+    }
+    for (int i = tid; i < D.n; i += PRIOR_THREADS) {
+        const int slot = D.cum[D.z[i]] - 1;              // own entry in, own entry out: no hazard between threads
+        D.z[i] = slot < D.kcap ? slot : D.kcap - 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-entity CSR build on the device (Relation::data_r, cxx/hirm.hh:251,274-280): count, scan, fill.  An observation
+// is listed once per entity even if the entity sits at two positions of it (set semantics of data_r).  The order of
+// the entries inside a row is not specified (the sweep kernel's results do not depend on it: integer accumulators).
+struct CsrRel { const int32_t *ids; const uint8_t *val; int64_t nobs; int32_t arity; int32_t rel; int32_t dom[MAX_ARITY]; int32_t n_ent[MAX_ARITY]; };
+__global__ void coo_validate_kernel(CsrRel R, int32_t *error) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < R.nobs; o += (int64_t)gridDim.x * blockDim.x) {
+        bool bad = R.val[o] > 1;
+        for (int p = 0; p < R.arity; p++) { const int32_t v = R.ids[o * R.arity + p]; bad |= v < 0 || v >= R.n_ent[p]; }
+        if (bad) atomicCAS(error, 0, 1);
+    }
+}
+__global__ void csr_count_kernel(CsrRel R, int d, unsigned long long *deg) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < R.nobs; o += (int64_t)gridDim.x * blockDim.x) {
+        for (int p = 0; p < R.arity; p++) {
+            if (R.dom[p] != d) continue;
+            const int32_t ent = R.ids[o * R.arity + p];
+            bool dup = false;
+            for (int q = 0; q < p; q++) dup |= R.dom[q] == d && R.ids[o * R.arity + q] == ent;
+            if (!dup) atomicAdd(&deg[ent], 1ull);
+        }
+    }
+}
+// in-place exclusive scan of m 64-bit counts by one block; *max_out = the largest count
+__global__ void __launch_bounds__(1024) scan_exclusive_kernel(unsigned long long *a, int64_t m, unsigned long long *max_out) {
+    __shared__ unsigned long long s_sum[1024], s_max[1024];
+    const int64_t per = (m + 1023) / 1024, lo = threadIdx.x * per, hi = lo + per < m ? lo + per : m;
+    unsigned long long sum = 0, mx = 0;
+    for (int64_t i = lo; i < hi; i++) { sum += a[i]; mx = a[i] > mx ? a[i] : mx; }
+    s_sum[threadIdx.x] = sum; s_max[threadIdx.x] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0, gm = 0;
+        for (int t = 0; t < 1024; t++) { const unsigned long long v = s_sum[t]; s_sum[t] = run; run += v; gm = s_max[t] > gm ? s_max[t] : gm; }
+        *max_out = gm;
+    }
+    __syncthreads();
+    unsigned long long run = s_sum[threadIdx.x];
+    for (int64_t i = lo; i < hi; i++) { const unsigned long long v = a[i]; a[i] = run; run += v; }
+}
+__global__ void csr_fill_kernel(CsrRel R, int d, const int64_t *ptr, unsigned long long *cursor, uint32_t *meta, int32_t *other, int64_t nnz) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < R.nobs; o += (int64_t)gridDim.x * blockDim.x) {
+        int32_t id[MAX_ARITY];
+        for (int p = 0; p < R.arity; p++) id[p] = R.ids[o * R.arity + p];
+        for (int p = 0; p < R.arity; p++) {
+            if (R.dom[p] != d) continue;
+            const int32_t ent = id[p];
+            bool dup = false; uint32_t selfmask = 0;
+            for (int q = 0; q < R.arity; q++)
+                if (R.dom[q] == d && id[q] == ent) { if (q < p) dup = true; selfmask |= 1u << q; }
+            if (dup) continue;
+            const int64_t slot = ptr[ent] + (int64_t)atomicAdd(&cursor[ent], 1ull);
+            meta[slot] = (uint32_t)R.rel | ((uint32_t)R.val[o] << META_VAL_SHIFT) | (selfmask << META_SELF_SHIFT);
+            int oi = 0;
+            for (int q = 0; q < R.arity; q++) { if (q == p) continue; other[(int64_t)oi * nnz + slot] = id[q]; oi++; }
+        }
+    }
+}
+
 // debug / test hook: the dense kernel's branch-free cell score on arrays of operands (one warp-converged call per element)
 __global__ void __launch_bounds__(AUX_THREADS) debug_score_delta_kernel(const uint32_t *N, const uint32_t *sv, const uint32_t *gn, const uint32_t *gs,
                                                                         double *out, int n) {

@@ -54,9 +54,9 @@ struct DevBuf {
 struct RelObs {
     int kind = -1;                     // -1 unset, 0 CSR, 1 dense
     int64_t nobs = 0;
-    std::vector<int32_t> h_ids;        // host COO until finalize()
-    std::vector<uint8_t> h_val;
-    DevBuf<int32_t> coo_ids; DevBuf<uint8_t> coo_val;
+    const int32_t *ids = nullptr;      // device COO [nobs * arity]: own_ids, or the caller's buffer (set_observations_device)
+    const uint8_t *val = nullptr;
+    DevBuf<int32_t> own_ids; DevBuf<uint8_t> own_val;
     const uint8_t *slab[2] = {nullptr, nullptr};
     int64_t pitch[2] = {0, 0};
     DevBuf<uint8_t> own_slab0, own_slab1;   // set_observations_dense_host
@@ -111,6 +111,7 @@ struct hirm_engine {
     DevBuf<double> s_alpha;
     DevBuf<cell_t> s_reltab; DevBuf<RelCand> s_relcand; DevBuf<int32_t> s_relerr;
     DevBuf<uint64_t> s_sweep0;
+    DevBuf<unsigned char> s_job[5]; DevBuf<int32_t> s_prior;   // relation-score jobs: descriptors, fresh partitions
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
     int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0, dense_static_smem = 0, dense_static_smem_large = 0;
@@ -270,8 +271,51 @@ extern "C" int hirm_irm_set_observations(hirm_engine *e, int32_t id, int rel, in
     }
     RelObs &R = irm->obs->rel[rel];
     R.kind = 0; R.nobs = nobs;
-    R.h_ids.assign(h_ids, h_ids + nobs * a);
-    R.h_val.assign(h_val, h_val + nobs);
+    CK(R.own_ids.alloc((size_t)(nobs * a))); CK(R.own_val.alloc((size_t)nobs));
+    if (nobs > 0) {
+        CK(cudaMemcpy(R.own_ids.p, h_ids, (size_t)(nobs * a) * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(R.own_val.p, h_val, (size_t)nobs, cudaMemcpyHostToDevice));
+    }
+    R.ids = R.own_ids.p; R.val = R.own_val.p;
+    return 0;
+}
+
+static CsrRel csr_rel_of(const Irm *irm, int r) {
+    const RelObs &R = irm->obs->rel[r];
+    CsrRel c;
+    memset(&c, 0, sizeof(c));
+    c.ids = R.ids; c.val = R.val; c.nobs = R.nobs; c.arity = irm->arity[r]; c.rel = r;
+    for (int p = 0; p < c.arity; p++) { c.dom[p] = irm->rdom[r][p]; c.n_ent[p] = irm->n_ent[irm->rdom[r][p]]; }
+    return c;
+}
+static unsigned coo_blocks(hirm_engine *e, int64_t nobs) {
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((nobs + 255) / 256, (int64_t)e->num_sms * 8));
+}
+
+// Same with the COO arrays already in device memory (caller-owned, never copied nor freed: a relation's observations
+// can be shared by every IRM the relation visits in an HIRM, cxx/hirm.hh:859-864, and by the relation-score kernels).
+extern "C" int hirm_irm_set_observations_device(hirm_engine *e, int32_t id, int rel, int64_t nobs, const int32_t *d_ids,
+                                                const uint8_t *d_val) {
+    GET_IRM(irm, e, id);
+    if (rel < 0 || rel >= irm->n_relations) return fail("bad relation index");
+    if (irm->obs.use_count() > 1 || irm->obs->finalized) return fail("observation store is shared or finalized");
+    if (nobs < 0 || (nobs > 0 && (!d_ids || !d_val))) return fail("null observation arrays");
+    RelObs &R = irm->obs->rel[rel];
+    R.kind = 0; R.nobs = nobs; R.ids = d_ids; R.val = d_val;
+    R.own_ids.release(); R.own_val.release();
+    if (nobs > 0) {
+        CK(cudaMemsetAsync(irm->error.p, 0, sizeof(int32_t), e->stream));
+        coo_validate_kernel<<<coo_blocks(e, nobs), 256, 0, e->stream>>>(csr_rel_of(irm, rel), irm->error.p);
+        CK(cudaGetLastError());
+        int32_t bad = 0;
+        CK(cudaMemcpyAsync(&bad, irm->error.p, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (bad) {
+            CK(cudaMemsetAsync(irm->error.p, 0, sizeof(int32_t), e->stream));
+            R.kind = -1; R.nobs = 0; R.ids = nullptr; R.val = nullptr;
+            return fail("observation values must be 0 or 1 and entity codes in range");
+        }
+    }
     return 0;
 }
 
@@ -341,62 +385,54 @@ extern "C" int hirm_irm_share_observations(hirm_engine *e, int32_t dst, int32_t 
 }
 
 // Build the per-entity CSR of every domain over all CSR-stored relations (Relation::data_r,
-// cxx/hirm.hh:251,274-280) and upload the COO arrays used for count-table rebuilds.
+// cxx/hirm.hh:251,274-280) on the device: degree count, scan, fill (aux_kernels.cuh).
 static int finalize_store(hirm_engine *e, Irm *irm) {
     ObsStore &S = *irm->obs;
     if (S.finalized) return 0;
+    cudaStream_t s0 = e->stream;
     for (int r = 0; r < irm->n_relations; r++)
         if (S.rel[r].kind < 0) { S.rel[r].kind = 0; S.rel[r].nobs = 0; }   // a relation without observations
     for (int d = 0; d < irm->n_domains; d++) {
         const int n = irm->n_ent[d];
         int max_other = 0;
-        std::vector<int64_t> ptr((size_t)n + 1, 0);
-        for (int pass = 0; pass < 2; pass++) {
-            std::vector<int64_t> fill;
-            std::vector<uint32_t> meta; std::vector<int32_t> other;
-            int64_t nnz = 0;
-            if (pass == 1) {
-                for (int i = 0; i < n; i++) ptr[i + 1] += ptr[i];
-                nnz = ptr[n];
-                fill.assign(ptr.begin(), ptr.end() - 1);
-                meta.resize((size_t)nnz); other.assign((size_t)nnz * std::max(1, max_other), 0);
-            }
-            for (int r = 0; r < irm->n_relations; r++) {
-                RelObs &R = S.rel[r];
-                if (R.kind != 0 || R.nobs == 0) continue;
-                const int a = irm->arity[r];
-                bool touches = false;
-                for (int p = 0; p < a; p++) touches |= irm->rdom[r][p] == d;
-                if (!touches) continue;
-                if (pass == 0) max_other = std::max(max_other, a - 1);
-                for (int64_t k = 0; k < R.nobs; k++) {
-                    const int32_t *ids = &R.h_ids[(size_t)k * a];
-                    for (int p = 0; p < a; p++) {
-                        if (irm->rdom[r][p] != d) continue;
-                        const int32_t ent = ids[p];
-                        bool dup = false; uint32_t selfmask = 0;
-                        for (int q = 0; q < a; q++)
-                            if (irm->rdom[r][q] == d && ids[q] == ent) { if (q < p) dup = true; selfmask |= 1u << q; }
-                        if (dup) continue;          // listed once per entity (set semantics of data_r)
-                        if (pass == 0) { ptr[ent + 1]++; continue; }
-                        const int64_t slot = fill[ent]++;
-                        meta[slot] = (uint32_t)r | ((uint32_t)R.h_val[k] << META_VAL_SHIFT) | (selfmask << META_SELF_SHIFT);
-                        int oi = 0;
-                        for (int q = 0; q < a; q++) { if (q == p) continue; other[(size_t)oi * nnz + slot] = ids[q]; oi++; }
-                    }
-                }
-            }
-            if (pass == 1) {
-                DomObs &D = S.dom[d];
-                D.nnz = nnz; D.n_other = std::max(1, max_other); D.max_deg = 0;
-                for (int i = 0; i < n; i++) D.max_deg = std::max(D.max_deg, ptr[i + 1] - ptr[i]);
-                if (nnz > 0) {
-                    CK(D.ptr.alloc(ptr.size())); CK(cudaMemcpy(D.ptr.p, ptr.data(), ptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-                    CK(D.meta.alloc(meta.size())); CK(cudaMemcpy(D.meta.p, meta.data(), meta.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-                    CK(D.other.alloc(other.size())); CK(cudaMemcpy(D.other.p, other.data(), other.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-                }
-            }
+        std::vector<int> touching;
+        for (int r = 0; r < irm->n_relations; r++) {
+            RelObs &R = S.rel[r];
+            if (R.kind != 0 || R.nobs == 0) continue;
+            bool touches = false;
+            for (int p = 0; p < irm->arity[r]; p++) touches |= irm->rdom[r][p] == d;
+            if (!touches) continue;
+            touching.push_back(r);
+            max_other = std::max(max_other, irm->arity[r] - 1);
         }
+        DomObs &D = S.dom[d];
+        D.nnz = 0; D.n_other = std::max(1, max_other); D.max_deg = 0;
+        if (touching.empty() || n == 0) continue;
+        static_assert(sizeof(unsigned long long) == sizeof(int64_t), "ptr is scanned in place");
+        CK(D.ptr.alloc((size_t)n + 1));
+        CK(cudaMemsetAsync(D.ptr.p, 0, ((size_t)n + 1) * sizeof(int64_t), s0));
+        DevBuf<unsigned long long> cursor;                 // [n] fill cursors + [1] largest degree
+        CK(cursor.alloc((size_t)n + 1));
+        CK(cudaMemsetAsync(cursor.p, 0, ((size_t)n + 1) * sizeof(unsigned long long), s0));
+        for (int r : touching) {
+            csr_count_kernel<<<coo_blocks(e, S.rel[r].nobs), 256, 0, s0>>>(csr_rel_of(irm, r), d, (unsigned long long *)D.ptr.p);
+            CK(cudaGetLastError());
+        }
+        scan_exclusive_kernel<<<1, 1024, 0, s0>>>((unsigned long long *)D.ptr.p, (int64_t)n + 1, cursor.p + n);
+        CK(cudaGetLastError());
+        int64_t nnz = 0; unsigned long long maxdeg = 0;
+        CK(cudaMemcpyAsync(&nnz, D.ptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s0));
+        CK(cudaMemcpyAsync(&maxdeg, cursor.p + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
+        CK(cudaStreamSynchronize(s0));
+        D.nnz = nnz; D.max_deg = (int64_t)maxdeg;
+        if (nnz == 0) { D.ptr.release(); continue; }
+        CK(D.meta.alloc((size_t)nnz)); CK(D.other.alloc((size_t)nnz * D.n_other));
+        CK(cudaMemsetAsync(D.other.p, 0, (size_t)nnz * D.n_other * sizeof(int32_t), s0));
+        for (int r : touching) {
+            csr_fill_kernel<<<coo_blocks(e, S.rel[r].nobs), 256, 0, s0>>>(csr_rel_of(irm, r), d, D.ptr.p, cursor.p, D.meta.p, D.other.p, nnz);
+            CK(cudaGetLastError());
+        }
+        CK(cudaStreamSynchronize(s0));                     // cursor goes out of scope
     }
     for (int r = 0; r < irm->n_relations; r++) {
         RelObs &R = S.rel[r];
@@ -412,13 +448,6 @@ static int finalize_store(hirm_engine *e, Irm *irm) {
         CK(cudaMemcpyAsync(&h, flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         R.full_obs = h ? 0 : 1;
-    }
-    for (int r = 0; r < irm->n_relations; r++) {
-        RelObs &R = S.rel[r];
-        if (R.kind != 0 || R.nobs == 0) continue;
-        CK(R.coo_ids.alloc(R.h_ids.size())); CK(cudaMemcpy(R.coo_ids.p, R.h_ids.data(), R.h_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        CK(R.coo_val.alloc(R.h_val.size())); CK(cudaMemcpy(R.coo_val.p, R.h_val.data(), R.h_val.size(), cudaMemcpyHostToDevice));
-        std::vector<int32_t>().swap(R.h_ids); std::vector<uint8_t>().swap(R.h_val);
     }
     S.finalized = true;
     return 0;
@@ -487,7 +516,7 @@ static int upload_desc(hirm_engine *e, int32_t id) {
         R.counts = irm->counts[r].p; R.ncells = irm->ncells[r];
         R.groups = irm->groups[r].p; R.gcells = irm->gcells[r]; R.gbit0 = irm->gbit0[r];
         R.slab[0] = S.rel[r].slab[0]; R.slab[1] = S.rel[r].slab[1]; R.pitch[0] = S.rel[r].pitch[0]; R.pitch[1] = S.rel[r].pitch[1];
-        R.coo_ids = S.rel[r].coo_ids.p; R.coo_val = S.rel[r].coo_val.p; R.nobs = S.rel[r].nobs;
+        R.coo_ids = S.rel[r].ids; R.coo_val = S.rel[r].val; R.nobs = S.rel[r].nobs;
         R.full_obs = S.rel[r].full_obs > 0 ? 1 : 0;
     }
     CK(irm->d_rel.ensure(rd.size()));
@@ -756,7 +785,7 @@ extern "C" int hirm_engine_relation_scores(hirm_engine *e, int32_t src, int rel,
     CK(cudaMemcpyAsync(e->s_relcand.p, cands.data(), cands.size() * sizeof(RelCand), cudaMemcpyHostToDevice, s0));
     if (R.nobs > 0) {
         dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((R.nobs + AUX_THREADS - 1) / AUX_THREADS, e->num_sms * 4)), (unsigned)n_cand);
-        rel_hist_kernel<<<grid, AUX_THREADS, 0, s0>>>(R.coo_ids.p, R.coo_val.p, R.nobs, a, e->s_relcand.p, e->s_relerr.p);
+        rel_hist_kernel<<<grid, AUX_THREADS, 0, s0>>>(R.ids, R.val, R.nobs, a, e->s_relcand.p, e->s_relerr.p);
         CK(cudaGetLastError());
     }
     rel_score_kernel<<<n_cand, AUX_THREADS, 0, s0>>>(e->s_relcand.p, e->s_score.p);
@@ -766,6 +795,188 @@ extern "C" int hirm_engine_relation_scores(hirm_engine *e, int32_t src, int rel,
     CK(cudaMemcpyAsync(&err, e->s_relerr.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
     CK(cudaStreamSynchronize(s0));
     if (err) return fail(std::string("kernel error: ") + kerr_text(err) + " (seat the relation's entities in the candidate first: hirm_irm_seat_entities)");
+    return 0;
+}
+
+// ---- batched relation scores (K4, aux_kernels.cuh) ------------------------------------------------------------------
+namespace {
+struct ScoreJob {
+    std::vector<RelDesc> rels; std::vector<PartSet> parts; std::vector<ScoreWork> work; std::vector<TableRef> refs;
+    std::vector<int64_t> table0;       // scratch offset of relation r's first table
+    int64_t total_cells = 0;
+};
+constexpr int64_t RM_OBS_PER_ITEM = 65536;
+}
+
+static int job_relations(ScoreJob &J, int n_rel, const int32_t *h_arity, const int32_t *h_rel_doms, const int64_t *h_nobs,
+                         const int32_t *const *h_d_ids, const uint8_t *const *h_d_val, int n_domains, const int32_t *kcap) {
+    if (n_rel < 0 || (n_rel > 0 && (!h_arity || !h_rel_doms || !h_nobs || !h_d_ids || !h_d_val))) return fail("null relation arrays");
+    J.rels.resize((size_t)n_rel);
+    for (int r = 0; r < n_rel; r++) {
+        RelDesc &R = J.rels[(size_t)r];
+        memset(&R, 0, sizeof(R));
+        if (h_arity[r] < 1 || h_arity[r] > MAX_ARITY) return fail("arity must be in [1, HIRM_MAX_ARITY]");
+        if (h_nobs[r] < 0 || (h_nobs[r] > 0 && (!h_d_ids[r] || !h_d_val[r]))) return fail("null observation arrays");
+        R.ids = h_d_ids[r]; R.val = h_d_val[r]; R.nobs = h_nobs[r]; R.arity = h_arity[r];
+        int64_t stride = 1;
+        for (int p = 0; p < R.arity; p++) {
+            const int d = h_rel_doms[r * MAX_ARITY + p];
+            if (d < 0 || d >= n_domains) return fail("relation names a domain out of range");
+            R.dom[p] = d; R.stride[p] = stride; stride *= kcap[d];
+            if (stride > ((int64_t)1 << 27)) return fail("count table too large: lower max_tables");
+        }
+        R.ncells = stride;
+    }
+    return 0;
+}
+
+template <typename T>
+static int job_upload(hirm_engine *e, DevBuf<unsigned char> &buf, const std::vector<T> &v) {
+    CK(buf.ensure(std::max<size_t>(v.size() * sizeof(T), 16)));
+    if (!v.empty()) CK(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
+// histogram + score passes of a prepared job; h_out gets one value per J.refs entry
+static int run_score_job(hirm_engine *e, ScoreJob &J, double *h_out) {
+    cudaStream_t s0 = e->stream;
+    CK(e->s_reltab.ensure((size_t)std::max<int64_t>(J.total_cells, 1))); CK(e->s_score.ensure(std::max<size_t>(J.refs.size(), 1)));
+    CK(e->s_relerr.ensure(1));
+    CK(cudaMemsetAsync(e->s_reltab.p, 0, (size_t)J.total_cells * sizeof(cell_t), s0));
+    CK(cudaMemsetAsync(e->s_relerr.p, 0, sizeof(int32_t), s0));
+    if (job_upload(e, e->s_job[0], J.rels) || job_upload(e, e->s_job[1], J.parts) || job_upload(e, e->s_job[2], J.work) ||
+        job_upload(e, e->s_job[3], J.refs)) return -1;
+    if (!J.work.empty()) {
+        relmat_hist_kernel<<<(unsigned)J.work.size(), AUX_THREADS, 0, s0>>>((const RelDesc *)e->s_job[0].p, (const PartSet *)e->s_job[1].p,
+                                                                           (const ScoreWork *)e->s_job[2].p, e->s_reltab.p, e->s_relerr.p);
+        CK(cudaGetLastError());
+    }
+    if (!J.refs.empty()) {
+        relmat_score_kernel<<<(unsigned)J.refs.size(), AUX_THREADS, 0, s0>>>((const TableRef *)e->s_job[3].p, e->s_reltab.p, e->s_score.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_out, e->s_score.p, J.refs.size() * sizeof(double), cudaMemcpyDeviceToHost, s0));
+    }
+    int32_t err = 0;
+    CK(cudaMemcpyAsync(&err, e->s_relerr.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));                      // the job vectors are the sources of the async copies
+    if (err) return fail(std::string("kernel error: ") + kerr_text(err));
+    return 0;
+}
+
+// Relation::logp_score of every listed relation under the domain partitions of every listed IRM: the data terms of one
+// whole sweep of HIRM::transition_cluster_assignment_relation (cxx/hirm.hh:833-906; the quantity of :865).
+extern "C" int hirm_engine_relation_score_matrix(hirm_engine *e, int n_rel, const int32_t *h_arity, const int32_t *h_rel_doms,
+                                                 const int64_t *h_nobs, const int32_t *const *h_d_ids, const uint8_t *const *h_d_val,
+                                                 int n_cand, const int32_t *h_cand_irms, double *h_out) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n_rel <= 0 || n_cand <= 0) return 0;
+    if (!h_cand_irms || !h_out) return fail("null argument");
+    ScoreJob J;
+    Irm *C0 = get_irm(e, h_cand_irms[0]);
+    if (!C0) return fail("bad candidate irm id");
+    J.parts.resize((size_t)n_cand);
+    for (int c = 0; c < n_cand; c++) {
+        Irm *C = get_irm(e, h_cand_irms[c]);
+        if (!C) return fail("bad candidate irm id");
+        if (C->n_domains != C0->n_domains || C->kcap != C0->kcap || C->n_ent != C0->n_ent)
+            return fail("the candidates of one score matrix must share domains, entity codes and max_tables");
+        memset(&J.parts[(size_t)c], 0, sizeof(PartSet));
+        for (int d = 0; d < C->n_domains; d++) {
+            if (!C->have_z[d]) return fail("candidate irm without assignments");
+            if (C->has_absent[d]) return fail("candidate irm with unseated entities: seat them first (hirm_irm_seat_entities)");
+            J.parts[(size_t)c].z[d] = C->z[d].p;
+        }
+    }
+    if (job_relations(J, n_rel, h_arity, h_rel_doms, h_nobs, h_d_ids, h_d_val, C0->n_domains, C0->kcap.data())) return -1;
+    for (int r = 0; r < n_rel; r++) {
+        const RelDesc &R = J.rels[(size_t)r];
+        const int64_t t0 = J.total_cells;
+        J.total_cells += R.ncells * n_cand;
+        for (int c = 0; c < n_cand; c++) J.refs.push_back(TableRef{t0 + c * R.ncells, R.ncells});
+        const int run = R.ncells <= RM_SH_CELLS ? (int)std::max<int64_t>(1, std::min<int64_t>(n_cand, RM_SH_CELLS / R.ncells)) : n_cand;
+        for (int c0 = 0; c0 < n_cand; c0 += run)
+            for (int64_t o = 0; o < R.nobs; o += RM_OBS_PER_ITEM)
+                J.work.push_back(ScoreWork{r, c0, std::min(run, n_cand - c0), 0, o, std::min(R.nobs, o + RM_OBS_PER_ITEM), t0 + c0 * R.ncells});
+    }
+    return run_score_job(e, J, h_out);
+}
+
+static int launch_prior_draws(hirm_engine *e, const std::vector<PriorDraw> &draws, uint64_t seed) {
+    if (draws.empty()) return 0;
+    if (job_upload(e, e->s_job[4], draws)) return -1;
+    CK(e->s_relerr.ensure(1));
+    CK(cudaMemsetAsync(e->s_relerr.p, 0, sizeof(int32_t), e->stream));
+    crp_prior_kernel<<<(unsigned)draws.size(), PRIOR_THREADS, 0, e->stream>>>((const PriorDraw *)e->s_job[4].p, seed, e->s_relerr.p);
+    CK(cudaGetLastError());
+    int32_t err = 0;
+    CK(cudaMemcpyAsync(&err, e->s_relerr.p, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (err) return fail("a CRP prior draw opened more tables than max_tables");
+    return 0;
+}
+
+// The fresh-table candidate of every listed relation (cxx/hirm.hh:849-864): a new IRM whose domains are seated by
+// sequential CRP(alpha) prior draws, one independent draw per (relation, domain) identified by its Philox stream
+// h_keys[r * n_domains + d]; h_out[r] = Relation::logp_score of relation r under its own draw.  The draw can be
+// reproduced later from the key (hirm_engine_crp_prior_draw) if the relation takes the fresh table.
+extern "C" int hirm_engine_relation_scores_fresh(hirm_engine *e, int n_rel, const int32_t *h_arity, const int32_t *h_rel_doms,
+                                                 const int64_t *h_nobs, const int32_t *const *h_d_ids, const uint8_t *const *h_d_val,
+                                                 int n_domains, const int32_t *h_n_entities, const int32_t *h_max_tables, double alpha,
+                                                 uint64_t seed, const uint64_t *h_keys, double *h_out) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n_rel <= 0) return 0;
+    if (n_domains < 1 || n_domains > MAX_DOMAINS || !h_n_entities || !h_max_tables || !h_keys || !h_out) return fail("bad argument");
+    if (!(alpha > 0)) return fail("alpha must be positive");
+    ScoreJob J;
+    if (job_relations(J, n_rel, h_arity, h_rel_doms, h_nobs, h_d_ids, h_d_val, n_domains, h_max_tables)) return -1;
+    int64_t slots = 0;
+    for (int r = 0; r < n_rel; r++) {
+        bool used[MAX_DOMAINS] = {false};
+        for (int p = 0; p < J.rels[(size_t)r].arity; p++) used[J.rels[(size_t)r].dom[p]] = true;
+        for (int d = 0; d < n_domains; d++) if (used[d]) slots += h_n_entities[d];
+    }
+    CK(e->s_prior.ensure((size_t)std::max<int64_t>(2 * slots, 1)));
+    std::vector<PriorDraw> draws;
+    J.parts.resize((size_t)n_rel);
+    int64_t off = 0;
+    for (int r = 0; r < n_rel; r++) {
+        const RelDesc &R = J.rels[(size_t)r];
+        memset(&J.parts[(size_t)r], 0, sizeof(PartSet));
+        bool used[MAX_DOMAINS] = {false};
+        for (int p = 0; p < R.arity; p++) used[R.dom[p]] = true;
+        for (int d = 0; d < n_domains; d++) {
+            if (!used[d]) continue;
+            PriorDraw D;
+            D.z = e->s_prior.p + off; D.cum = e->s_prior.p + slots + off; D.n = h_n_entities[d]; D.kcap = h_max_tables[d];
+            D.key = h_keys[(size_t)r * n_domains + d]; D.alpha = alpha;
+            J.parts[(size_t)r].z[d] = D.z;
+            draws.push_back(D);
+            off += h_n_entities[d];
+        }
+        const int64_t t0 = J.total_cells;
+        J.total_cells += R.ncells;
+        J.refs.push_back(TableRef{t0, R.ncells});
+        for (int64_t o = 0; o < R.nobs; o += RM_OBS_PER_ITEM)
+            J.work.push_back(ScoreWork{r, r, 1, 0, o, std::min(R.nobs, o + RM_OBS_PER_ITEM), t0});
+    }
+    if (launch_prior_draws(e, draws, seed)) return -1;
+    return run_score_job(e, J, h_out);
+}
+
+// One draw of the sequential CRP(alpha) prior over n customers, table labels in order of appearance (Domain::incorporate
+// for every entity of a fresh domain, cxx/hirm.hh:194-203 with CRP::sample :101-113), Philox stream `key`.
+extern "C" int hirm_engine_crp_prior_draw(hirm_engine *e, int n, double alpha, int max_tables, uint64_t seed, uint64_t key, int32_t *h_labels) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n < 0 || max_tables < 1 || !(alpha > 0) || (n > 0 && !h_labels)) return fail("bad argument");
+    if (n == 0) return 0;
+    CK(e->s_prior.ensure((size_t)2 * n));
+    PriorDraw D;
+    D.z = e->s_prior.p; D.cum = e->s_prior.p + n; D.n = n; D.kcap = max_tables; D.key = key; D.alpha = alpha;
+    if (launch_prior_draws(e, std::vector<PriorDraw>{D}, seed)) return -1;
+    CK(cudaMemcpy(h_labels, e->s_prior.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -813,6 +1024,12 @@ extern "C" int hirm_irm_seat_entities(hirm_engine *e, int32_t id, int dom, int n
 extern "C" int hirm_irm_set_rng(hirm_engine *e, int32_t id, uint64_t stream, uint64_t move_counter) {
     GET_IRM(irm, e, id);
     irm->rng_stream = stream; irm->move_counter = move_counter;
+    return 0;
+}
+
+extern "C" int hirm_irm_set_rng_counters(hirm_engine *e, int32_t id, uint64_t sweep_counter, uint64_t alpha_counter) {
+    GET_IRM(irm, e, id);
+    irm->sweep_counter = sweep_counter; irm->alpha_counter = alpha_counter;
     return 0;
 }
 

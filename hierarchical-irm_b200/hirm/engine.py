@@ -32,6 +32,8 @@ EXPORTS = [
     "hirm_engine_debug_phase_cycles", "hirm_engine_last_dense_plan", "hirm_engine_sweep_all", "hirm_irm_set_rng",
     "hirm_engine_logp_scores", "hirm_engine_transition_alpha", "hirm_irm_get_alpha", "hirm_irm_get_tables",
     "hirm_engine_relation_scores", "hirm_irm_seat_entities", "hirm_engine_debug_score_delta",
+    "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
+    "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters",
 ]
 
 _lib = None
@@ -92,6 +94,13 @@ def load():
     L.hirm_engine_relation_scores.argtypes = [V, ctypes.c_int32, I, I, c_i32p, c_i32p, c_f64p]
     L.hirm_irm_seat_entities.argtypes = [V, ctypes.c_int32, I, I, c_i32p, c_i32p]
     L.hirm_engine_debug_score_delta.argtypes = [V, I, V, V, V, V, c_f64p]
+    L.hirm_irm_set_observations_device.argtypes = [V, ctypes.c_int32, I, ctypes.c_int64, V, V]
+    VP = ctypes.POINTER(V)
+    L.hirm_engine_relation_score_matrix.argtypes = [V, I, c_i32p, c_i32p, c_i64p, VP, VP, I, c_i32p, c_f64p]
+    L.hirm_engine_relation_scores_fresh.argtypes = [V, I, c_i32p, c_i32p, c_i64p, VP, VP, I, c_i32p, c_i32p, ctypes.c_double,
+                                                    ctypes.c_uint64, c_u64p, c_f64p]
+    L.hirm_irm_set_rng_counters.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
+    L.hirm_engine_crp_prior_draw.argtypes = [V, I, ctypes.c_double, I, ctypes.c_uint64, ctypes.c_uint64, c_i32p]
     _lib = L
     return L
 
@@ -257,6 +266,9 @@ class Engine:
     def set_rng(self, irm, stream, move_counter=0):
         self._ck(self.L.hirm_irm_set_rng(self._h, irm, stream, move_counter))
 
+    def set_rng_counters(self, irm, sweep_counter, alpha_counter):
+        self._ck(self.L.hirm_irm_set_rng_counters(self._h, irm, int(sweep_counter), int(alpha_counter)))
+
     def logp_scores(self, irms):
         irms = np.ascontiguousarray(irms, dtype=np.int32)
         out = np.empty(max(len(irms), 1), np.float64)
@@ -297,6 +309,52 @@ class Engine:
         out = np.empty(max(len(ci), 1), np.float64)
         self._ck(self.L.hirm_engine_relation_scores(self._h, src_irm, rel, len(ci), _p(ci, c_i32p), _p(cd, c_i32p), _p(out, c_f64p)))
         return out[:len(ci)]
+
+    def set_observations_device(self, irm, rel, nobs, d_ids_ptr, d_val_ptr):
+        """COO arrays already on the device (caller-owned buffers, e.g. torch tensors' data_ptr(); never copied)."""
+        self._ck(self.L.hirm_irm_set_observations_device(self._h, irm, rel, int(nobs), d_ids_ptr, d_val_ptr))
+
+    @staticmethod
+    def _rel_arrays(rels):
+        """rels: list of (domain indices per position, nobs, d_ids_ptr, d_val_ptr)."""
+        n = len(rels)
+        ar = np.ascontiguousarray([len(r[0]) for r in rels], dtype=np.int32)
+        rd = np.zeros((max(n, 1), MAX_ARITY), dtype=np.int32)
+        for k, r in enumerate(rels):
+            rd[k, :len(r[0])] = r[0]
+        nobs = np.ascontiguousarray([r[1] for r in rels], dtype=np.int64)
+        ids = (ctypes.c_void_p * max(n, 1))(*[r[2] or None for r in rels])
+        val = (ctypes.c_void_p * max(n, 1))(*[r[3] or None for r in rels])
+        return ar, rd, nobs, ids, val
+
+    def relation_score_matrix(self, rels, cand_irms):
+        """Relation.logp_score of every relation under every candidate IRM's partitions -> [len(rels), len(cand_irms)]."""
+        ci = np.ascontiguousarray(cand_irms, dtype=np.int32)
+        out = np.zeros((len(rels), len(ci)), np.float64)
+        if len(rels) == 0 or len(ci) == 0:
+            return out
+        ar, rd, nobs, ids, val = self._rel_arrays(rels)
+        self._ck(self.L.hirm_engine_relation_score_matrix(self._h, len(rels), _p(ar, c_i32p), _p(rd, c_i32p), _p(nobs, c_i64p), ids, val,
+                                                          len(ci), _p(ci, c_i32p), _p(out, c_f64p)))
+        return out
+
+    def relation_scores_fresh(self, rels, n_entities, max_tables, keys, seed, alpha=1.0):
+        """Relation.logp_score of every relation under its own fresh CRP(alpha)-prior partitions; keys [len(rels), n_domains]."""
+        out = np.zeros(len(rels), np.float64)
+        if len(rels) == 0:
+            return out
+        ar, rd, nobs, ids, val = self._rel_arrays(rels)
+        ne = np.ascontiguousarray(n_entities, dtype=np.int32); mt = np.ascontiguousarray(max_tables, dtype=np.int32)
+        ky = np.ascontiguousarray(keys, dtype=np.uint64).reshape(len(rels), len(ne))
+        self._ck(self.L.hirm_engine_relation_scores_fresh(self._h, len(rels), _p(ar, c_i32p), _p(rd, c_i32p), _p(nobs, c_i64p), ids, val,
+                                                          len(ne), _p(ne, c_i32p), _p(mt, c_i32p), float(alpha), int(seed), _p(ky, c_u64p),
+                                                          _p(out, c_f64p)))
+        return out
+
+    def crp_prior_draw(self, n, key, seed, alpha=1.0, max_tables=64):
+        out = np.empty(max(int(n), 1), np.int32)
+        self._ck(self.L.hirm_engine_crp_prior_draw(self._h, int(n), float(alpha), int(max_tables), int(seed), int(key), _p(out, c_i32p)))
+        return out[:int(n)]
 
     def seat_entities(self, irm, dom, items, labels):
         it = np.ascontiguousarray(items, dtype=np.int32); lb = np.ascontiguousarray(labels, dtype=np.int32)

@@ -1,0 +1,454 @@
+"""HIRM (cxx/hirm.hh:784-1014, src/hirm.py:457-571) with its relation-cluster IRMs sharded over GPUs.
+
+In an HIRM every relation cluster owns a private IRM (private domain partitions, cxx/hirm.hh:749-757,787), so the
+entity sweeps of different IRMs touch disjoint state (cxx/hirm.cc:73-88): one process per GPU, every rank owns a subset
+of the IRMs and sweeps them in one launch, no collective on that path.  The one exchange step of an HIRM iteration is
+the relation move HIRM::transition_cluster_assignment_relation (:833-906).  Its data term for relation r and candidate
+table k -- Relation::logp_score of r after re-incorporating its data into IRM k (:859-866) -- depends only on r's
+observations and on k's domain partitions, never on which other relations sit in k.  So per iteration
+
+  1. every rank computes the [relations x own IRMs] score matrix in one batched launch (hirm_engine_relation_score_matrix)
+     plus the fresh-table score of its share of the relations (hirm_engine_relation_scores_fresh);
+  2. ONE all-gather (NCCL over NVLink; gloo in the CPU tests) makes the full matrix known everywhere (R x K doubles);
+  3. the sequential CRP re-seating of the relations is O(R K) scalar work, replicated on every rank from a shared seed;
+     a relation that opens a fresh IRM adds one column for the relations still to move (one broadcast, rare);
+  4. IRMs whose relation set changed are rebuilt on their owner (the relations' COO arrays are replicated in HBM on every
+     rank, so nothing but bookkeeping moves); IRMs migrate between ranks (partitions only) to keep the load balanced.
+
+Results do not depend on the number of ranks: every random draw is keyed by (seed, IRM uid / relation, step).
+
+Differences from the reference, by design: every IRM carries every domain of the schema and seats every entity code of
+a domain (entities an IRM has no observation of move under the prior alone, cxx/hirm.hh:618 -- the reference's "ghost"
+entities, SURVEY 8a-Q7/Q8 -- and by the CRP's consistency they do not change the law of the others), so a relation can
+be scored under any IRM without trial seating; the order of the relation moves is a seeded permutation (the reference's
+is a hash-container order).
+"""
+import math
+
+import numpy as np
+
+from . import shard
+from .model import choose_index
+
+NGRID_ALPHA = 20           # CRP::transition_alpha grid of the C++ backend (cxx/hirm.hh:164)
+
+
+class Comm:
+    """The few collectives the relation step needs, over torch.distributed (nccl: one rank per GPU; gloo: CPU tests).
+    Without an initialised process group it is a world of one."""
+
+    def __init__(self, group=None):
+        self.group, self.dist, self.world, self.rank = group, None, 1, 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.dist, self.world, self.rank = dist, dist.get_world_size(group), dist.get_rank(group)
+        except ImportError:
+            pass
+        self.n_allgather = self.n_broadcast = 0
+
+    def _tensor(self, a):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+        return t.cuda() if self.dist.get_backend(self.group) == "nccl" else t
+
+    def all_gather_f64(self, a):
+        """a: float64 array, same shape on every rank -> list of arrays, one per rank."""
+        self.n_allgather += 1
+        if self.world == 1:
+            return [np.asarray(a, dtype=np.float64)]
+        import torch
+        shape = np.shape(a)
+        t = self._tensor(a).reshape(-1)
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t, group=self.group)
+        out = out.cpu().numpy().reshape((self.world,) + tuple(shape))
+        return [out[k] for k in range(self.world)]
+
+    def broadcast_f64(self, a, src):
+        self.n_broadcast += 1
+        if self.world == 1:
+            return np.asarray(a, dtype=np.float64)
+        t = self._tensor(a)
+        self.dist.broadcast(t, src=self.dist.get_global_rank(self.group, src) if self.group is not None else src, group=self.group)
+        return t.cpu().numpy()
+
+    def broadcast_obj(self, obj, src):
+        if self.world == 1:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=self.dist.get_global_rank(self.group, src) if self.group is not None else src,
+                                        group=self.group)
+        return box[0]
+
+    def all_gather_obj(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+
+class EngineBackend:
+    """Device side of one rank: the relation-owned COO arrays (torch tensors as buffers, replicated on every rank) and
+    the engine IRMs of the relation clusters this rank owns.  Every call is a C-ABI call (include/hirm_engine.h)."""
+
+    def __init__(self, n_entities, rel_domains, observations, max_tables, seed, engine=None, device=None, host_order=False):
+        import torch
+        from . import engine as E
+        if not torch.cuda.is_available():
+            raise E.EngineError("no CUDA device: the engine has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.eng = engine or E.Engine(self.device)
+        self.n_entities, self.rel_domains = [int(n) for n in n_entities], [list(map(int, ds)) for ds in rel_domains]
+        self.max_tables, self.seed, self.host_order = int(max_tables), int(seed), host_order
+        dev = torch.device("cuda", self.device)
+        self._buf, self.rels = [], []
+        for ds, (ids, val) in zip(self.rel_domains, observations):
+            ids = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1, len(ds))
+            val = np.ascontiguousarray(val, dtype=np.uint8)
+            assert len(ids) == len(val)
+            if len(val) and (val.max() > 1 or ids.min() < 0 or np.any(ids.max(axis=0) >= np.asarray([self.n_entities[d] for d in ds]))):
+                raise ValueError("observation values must be 0 or 1 and entity codes in range")
+            t_ids, t_val = torch.from_numpy(ids.reshape(-1)).to(dev), torch.from_numpy(val).to(dev)
+            self._buf.append((t_ids, t_val))
+            self.rels.append((ds, len(val), t_ids.data_ptr() if len(val) else None, t_val.data_ptr() if len(val) else None))
+        self._meta = {}
+
+    # -- IRMs -----------------------------------------------------------------------------------
+    def create_irm(self, rels, z, alpha, uid, steps):
+        """rels: global relation indices; z: labels per domain (every entity seated); steps: entity steps already made."""
+        eng = self.eng
+        h = eng.irm_create(self.n_entities, [self.rel_domains[r] for r in rels], max_tables=self.max_tables)
+        for k, r in enumerate(rels):
+            ds, nobs, pi, pv = self.rels[r]
+            eng.set_observations_device(h, k, nobs, pi, pv)
+        eng.finalize(h)
+        for d in range(len(self.n_entities)):
+            eng.set_assignments(h, d, z[d])
+            eng.set_alpha(h, d, alpha[d])
+        per = sum(self.n_entities)
+        eng.set_rng(h, uid, steps * per)
+        eng.set_rng_counters(h, steps, steps)
+        self._meta[h] = dict(uid=uid, steps=steps)
+        return h
+
+    def destroy_irm(self, h):
+        self.eng.irm_destroy(h)
+        self._meta.pop(h)
+
+    def get_state(self, h):
+        nd = len(self.n_entities)
+        return [self.eng.get_assignments(h, d).copy() for d in range(nd)], [self.eng.get_alpha(h, d) for d in range(nd)]
+
+    def get_counts(self, h, k):
+        return self.eng.get_counts(h, k)
+
+    # -- entity step: IRM::transition_cluster_assignments_all + CRP::transition_alpha of every listed IRM ------------
+    def step(self, handles):
+        if not handles:
+            return
+        eng = self.eng
+        if self.host_order:
+            moves = [host_sweep_order(self.n_entities, self.seed, self._meta[h]["uid"], self._meta[h]["steps"]) for h in handles]
+            per = sum(self.n_entities)
+            eng.sweep(handles, moves, seed=self.seed, streams=[self._meta[h]["uid"] for h in handles],
+                      counters=[self._meta[h]["steps"] * per for h in handles])
+        else:
+            eng.sweep_all(handles, n_sweeps=1, seed=self.seed)
+        eng.transition_alpha(handles, ngrid=NGRID_ALPHA, seed=self.seed)
+        for h in handles:
+            m = self._meta[h]
+            m["steps"] += 1
+            if self.host_order:
+                eng.set_rng(h, m["uid"], m["steps"] * sum(self.n_entities))
+
+    def logp_scores(self, handles):
+        return self.eng.logp_scores(handles) if handles else np.zeros(0)
+
+    # -- relation step --------------------------------------------------------------------------------------------------
+    def score_matrix(self, rels, handles):
+        return self.eng.relation_score_matrix([self.rels[r] for r in rels], handles)
+
+    def scores_fresh(self, rels, keys, chunk_slots=1 << 26):
+        out = np.zeros(len(rels), np.float64)
+        i = 0
+        while i < len(rels):                               # bounded scratch: the fresh partitions of a chunk live in HBM at once
+            j, slots = i, 0
+            while j < len(rels) and (j == i or slots + self._slots(rels[j]) <= chunk_slots):
+                slots += self._slots(rels[j]); j += 1
+            out[i:j] = self.eng.relation_scores_fresh([self.rels[r] for r in rels[i:j]], self.n_entities,
+                                                      [self.max_tables] * len(self.n_entities), keys[i:j], self.seed)
+            i = j
+        return out
+
+    def _slots(self, r):
+        return sum(self.n_entities[d] for d in set(self.rel_domains[r]))
+
+    def prior_draw(self, d, key):
+        return self.eng.crp_prior_draw(self.n_entities[d], key, self.seed, alpha=1.0, max_tables=self.max_tables)
+
+
+def host_sweep_order(n_entities, seed, uid, step):
+    """Sweep order of one entity step when the order is made on the host (parity tests): every domain in index order, a
+    seeded permutation of its entities."""
+    md, mi = [], []
+    for d, n in enumerate(n_entities):
+        perm = np.random.default_rng([int(seed), int(uid), int(step), d, 0x6F72]).permutation(n).astype(np.int32)
+        md.append(np.full(n, d, np.int32)); mi.append(perm)
+    return np.concatenate(md), np.concatenate(mi)
+
+
+class ShardedHIRM:
+    """domains: {name: number of entity codes}; schema: {relation: [domain names]}; observations: {relation: (ids
+    [nobs, arity] int32 entity codes, val [nobs] in {0, 1})}.  Entity codes are those of cxx/util_io.cc:63-96
+    (hirm.util_io encodes the reference's .obs files the same way)."""
+
+    def __init__(self, domains, schema, observations, seed=0, max_tables=64, comm=None, backend=None,
+                 relation_tables=None, partitions=None, alphas=None, rebalance=True, host_order=False, device=None):
+        self.dnames = list(domains)
+        self.n_ent = [int(domains[d]) for d in self.dnames]
+        if len(self.dnames) > 8:
+            raise ValueError("at most 8 domains (HIRM_MAX_DOMAINS)")
+        dindex = {d: k for k, d in enumerate(self.dnames)}
+        self.rnames = list(schema)
+        self.rindex = {r: k for k, r in enumerate(self.rnames)}
+        self.rel_domains = [[dindex[d] for d in schema[r]] for r in self.rnames]
+        obs = [observations[r] for r in self.rnames]
+        self.rel_weight = [max(1, len(o[1])) * len(ds) for o, ds in zip(obs, self.rel_domains)]   # CSR entries of the relation
+        self.seed, self.max_tables, self.rebalance = int(seed), int(max_tables), rebalance
+        self.comm = comm or Comm()
+        self.backend = backend or EngineBackend(self.n_ent, self.rel_domains, obs, max_tables, seed, device=device, host_order=host_order)
+        self.alpha = 1.0                                   # CRP over relations (cxx/hirm.hh:790); never transitioned by inference_hirm
+        self.irms = {}                                     # table label -> dict(uid, owner, rels, handle, steps, changed)
+        self.rel_table = {}
+        self._next_uid, self._next_key, self.iteration = 0, 1 << 40, 0
+        self.timers = dict(entity=0.0, score=0.0, gather=0.0, reseat=0.0, rebuild=0.0)
+        R = len(self.rnames)
+        rng = np.random.default_rng([self.seed, 0x696E6974])
+        if relation_tables is None:                        # HIRM::add_relation (:947-957): sequential CRP(alpha) seating
+            relation_tables, sizes = {}, {}
+            for r in self.rnames:
+                if not sizes:
+                    t = 0
+                else:
+                    tabs = sorted(sizes) + [max(sizes) + 1]
+                    w = np.array([sizes[x] for x in sorted(sizes)] + [self.alpha], dtype=np.float64)
+                    t = tabs[int(rng.choice(len(tabs), p=w / w.sum()))]
+                sizes[t] = sizes.get(t, 0) + 1
+                relation_tables[r] = t
+        for r in self.rnames:
+            self.rel_table[self.rindex[r]] = int(relation_tables[r])
+        labels = sorted(set(self.rel_table.values()))
+        members = {t: sorted(k for k, x in self.rel_table.items() if x == t) for t in labels}
+        owner, _ = shard.pack_irms([self._weight(members[t]) for t in labels], self.comm.world)
+        for t, own in zip(labels, owner):
+            keys = [self._take_key() for _ in self.dnames]
+            info = self.irms[t] = dict(uid=self._take_uid(), owner=own, rels=set(members[t]), handle=None, steps=0, changed=False)
+            if own == self.comm.rank:
+                if partitions is not None:
+                    z = [np.asarray(partitions[t][d], dtype=np.int32) for d in self.dnames]
+                else:
+                    z = [self.backend.prior_draw(d, keys[d]) for d in range(len(self.dnames))]
+                al = [1.0] * len(self.dnames) if alphas is None else [float(alphas[t][d]) for d in self.dnames]
+                info["handle"] = self.backend.create_irm(sorted(info["rels"]), z, al, info["uid"], 0)
+        assert R == len(self.rel_table)
+
+    # ---- bookkeeping ----------------------------------------------------------------------------
+    def _take_uid(self):
+        self._next_uid += 1
+        return self._next_uid - 1
+
+    def _take_key(self):
+        self._next_key += 1
+        return self._next_key - 1
+
+    def _weight(self, rels):
+        return sum(self.rel_weight[r] for r in rels) + sum(self.n_ent)
+
+    def _local(self):
+        return [t for t in sorted(self.irms) if self.irms[t]["owner"] == self.comm.rank]
+
+    def loads(self):
+        load = [0] * self.comm.world
+        for info in self.irms.values():
+            load[info["owner"]] += self._weight(info["rels"])
+        return load
+
+    def relation_to_table(self, r):
+        return self.rel_table[self.rindex[r]]
+
+    # ---- entity step (cxx/hirm.cc:73-88): no collective ---------------------------------------------------------------
+    def transition_irms(self, n_steps=1):
+        import time
+        t0 = time.perf_counter()
+        hs = [self.irms[t]["handle"] for t in self._local()]
+        for _ in range(n_steps):
+            self.backend.step(hs)
+            for info in self.irms.values():
+                info["steps"] += 1
+        self.timers["entity"] += time.perf_counter() - t0
+
+    # ---- relation step (cxx/hirm.cc:66-71 -> cxx/hirm.hh:833-906) --------------------------------------------------------
+    def score_columns(self):
+        """Steps 1-2: {table label: [R] scores of every relation under that IRM}, [R] fresh-table scores, fresh keys."""
+        import time
+        t0 = time.perf_counter()
+        R, nd, world, rank = len(self.rnames), len(self.dnames), self.comm.world, self.comm.rank
+        local = self._local()
+        m_local = self.backend.score_matrix(list(range(R)), [self.irms[t]["handle"] for t in local])
+        base = self._next_key
+        self._next_key += R * nd
+        keys = (base + np.arange(R * nd, dtype=np.uint64)).reshape(R, nd)
+        mine = [r for r in range(R) if r % world == rank]
+        f_local = self.backend.scores_fresh(mine, keys[mine]) if mine else np.zeros(0)
+        t1 = time.perf_counter()
+        per_rank = [[t for t in sorted(self.irms) if self.irms[t]["owner"] == k] for k in range(world)]
+        kmax = max(len(p) for p in per_rank)
+        buf = np.zeros((R, kmax + 1), dtype=np.float64)
+        buf[:, :len(local)] = m_local
+        buf[mine, kmax] = f_local
+        parts = self.comm.all_gather_f64(buf)
+        cols = {}
+        for k in range(world):
+            for j, t in enumerate(per_rank[k]):
+                cols[t] = parts[k][:, j].copy()
+        fresh = np.array([parts[r % world][r, kmax] for r in range(R)])
+        t2 = time.perf_counter()
+        self.timers["score"] += t1 - t0
+        self.timers["gather"] += t2 - t1
+        return cols, fresh, keys
+
+    def relation_candidates(self, r, cols, fresh_score):
+        """CRP::tables_weights_gibbs (:147-161) + the data terms: (tables ascending, log-probabilities, fresh label or None)."""
+        cur = self.rel_table[r]
+        w = {t: float(len(info["rels"])) for t, info in self.irms.items()}
+        w[cur] -= 1.0
+        fresh_label = None
+        if w[cur] == 0.0:
+            w[cur] = self.alpha                            # singleton: own table at weight alpha, no fresh one (:152-159)
+        else:
+            fresh_label = max(w) + 1
+            w[fresh_label] = self.alpha
+        tables = sorted(w)
+        lp = [math.log(w[t]) + (fresh_score if t == fresh_label else float(cols[t][r])) for t in tables]
+        return tables, lp, fresh_label
+
+    def apply_relation_choice(self, r, choice, cols, keys=None, parts=None):
+        """Re-seat relation r at table `choice` (the tail of :877-905).  A fresh table becomes an IRM whose partitions are
+        the keyed CRP-prior draws (or `parts`, {domain index: labels}, in the trace tests); its score column for the
+        other relations is computed by its owner and broadcast."""
+        cur = self.rel_table[r]
+        if choice == cur:
+            return
+        if choice not in self.irms:
+            load = self.loads()
+            own = min(range(self.comm.world), key=lambda k: (load[k], k))
+            info = self.irms[choice] = dict(uid=self._take_uid(), owner=own, rels=set(), handle=None, steps=0, changed=True)
+            latent = [self._take_key() for _ in self.dnames]          # domains the relation does not use: prior draws all the same
+            col = np.zeros(len(self.rnames))
+            if own == self.comm.rank:
+                z = []
+                for d in range(len(self.dnames)):
+                    if parts is not None and d in parts:
+                        z.append(np.asarray(parts[d], dtype=np.int32))
+                    elif keys is not None and d in self.rel_domains[r]:
+                        z.append(self.backend.prior_draw(d, int(keys[r, d])))
+                    else:
+                        z.append(self.backend.prior_draw(d, latent[d]))
+                info["handle"] = self.backend.create_irm([], z, [1.0] * len(self.dnames), info["uid"], 0)
+                col = self.backend.score_matrix(list(range(len(self.rnames))), [info["handle"]])[:, 0]
+            cols[choice] = self.comm.broadcast_f64(col, own)
+        src, dst = self.irms[cur], self.irms[choice]
+        src["rels"].discard(r); dst["rels"].add(r)
+        src["changed"] = dst["changed"] = True
+        self.rel_table[r] = choice
+        if not src["rels"]:                                # the emptied IRM is deleted (:886-890)
+            if src["handle"] is not None:
+                self.backend.destroy_irm(src["handle"])
+            del self.irms[cur]
+            cols.pop(cur, None)
+
+    def transition_relations(self):
+        """One sweep of relation moves: every relation once, in a seeded order."""
+        import time
+        cols, fresh, keys = self.score_columns()
+        t0 = time.perf_counter()
+        rng = np.random.default_rng([self.seed, self.iteration, 0x72656C])
+        order = rng.permutation(len(self.rnames))
+        us = rng.random(len(self.rnames))
+        moved = 0
+        for r, u in zip(order, us):
+            r = int(r)
+            tables, lp, fresh_label = self.relation_candidates(r, cols, float(fresh[r]))
+            choice = tables[choose_index(lp, float(u))]
+            moved += int(choice != self.rel_table[r])
+            self.apply_relation_choice(r, choice, cols, keys=keys)
+        t1 = time.perf_counter()
+        self.materialize()
+        self.timers["reseat"] += t1 - t0
+        self.timers["rebuild"] += time.perf_counter() - t1
+        self.iteration += 1
+        return moved
+
+    def materialize(self):
+        """Step 4: bring the engine IRMs in line with the bookkeeping -- rebuild those whose relation set changed, move
+        those whose owner changed (partitions, alphas and Philox positions travel; observations are everywhere)."""
+        labels = sorted(self.irms)
+        new_owner = {t: self.irms[t]["owner"] for t in labels}
+        if self.rebalance and self.comm.world > 1:
+            load = [0.0] * self.comm.world
+            for t in sorted(labels, key=lambda t: (-self._weight(self.irms[t]["rels"]), t)):
+                w, cur = self._weight(self.irms[t]["rels"]), self.irms[t]["owner"]
+                k = min(range(self.comm.world), key=lambda k: (load[k] - (0.25 * w if k == cur else 0.0), k))   # sticky LPT
+                new_owner[t] = k
+                load[k] += w
+        for t in labels:
+            info = self.irms[t]
+            old, new = info["owner"], new_owner[t]
+            if not info["changed"] and old == new:
+                continue
+            state = None
+            if old == self.comm.rank:
+                state = self.backend.get_state(info["handle"])
+                self.backend.destroy_irm(info["handle"])
+                info["handle"] = None
+            if old != new:
+                state = self.comm.broadcast_obj(state, old)
+            if new == self.comm.rank:
+                info["handle"] = self.backend.create_irm(sorted(info["rels"]), state[0], state[1], info["uid"], info["steps"])
+            info["owner"], info["changed"] = new, False
+
+    # ---- whole iterations / read-back --------------------------------------------------------------------------------
+    def iterate(self, n=1):
+        """inference_hirm (cxx/hirm.cc:61-90): relation moves, then the entity sweeps and alpha moves of every IRM."""
+        for _ in range(n):
+            self.transition_relations()
+            self.transition_irms()
+
+    def crp_logp_score(self):
+        sizes = [len(info["rels"]) for info in self.irms.values()]
+        n = sum(sizes)
+        return (len(sizes) * math.log(self.alpha) + sum(math.lgamma(c) for c in sizes) + math.lgamma(self.alpha)
+                - math.lgamma(n + self.alpha))
+
+    def logp_score(self):
+        """HIRM::logp_score (cxx/hirm.hh:998-1005); per-IRM scores gathered and summed in table order on every rank."""
+        local = self._local()
+        sc = self.backend.logp_scores([self.irms[t]["handle"] for t in local])
+        merged = {}
+        for part in self.comm.all_gather_obj({t: float(s) for t, s in zip(local, sc)}):
+            merged.update(part)
+        return self.crp_logp_score() + sum(merged[t] for t in sorted(merged))
+
+    def state(self):
+        """{table: dict(relations=[names], z={domain: labels}, alpha={domain: a})}, the same on every rank."""
+        mine = {}
+        for t in self._local():
+            z, al = self.backend.get_state(self.irms[t]["handle"])
+            mine[t] = dict(relations=[self.rnames[r] for r in sorted(self.irms[t]["rels"])],
+                           z={d: z[k] for k, d in enumerate(self.dnames)}, alpha={d: al[k] for k, d in enumerate(self.dnames)})
+        merged = {}
+        for part in self.comm.all_gather_obj(mine):
+            merged.update(part)
+        return {t: merged[t] for t in sorted(merged)}

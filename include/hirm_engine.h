@@ -66,6 +66,11 @@ int hirm_irm_destroy(hirm_engine *e, int32_t irm);
  * (cxx/hirm.hh:272).  Call for every relation, then hirm_irm_finalize(). */
 int hirm_irm_set_observations(hirm_engine *e, int32_t irm, int rel, int64_t nobs,
                               const int32_t *h_ids, const uint8_t *h_val);
+/* Same with the COO arrays already in device memory.  The buffers stay owned by the caller, are never copied and must
+ * outlive the IRM: in an HIRM one copy of a relation's observations serves every IRM the relation visits
+ * (HIRM::transition_cluster_assignment_relation re-incorporates the data into each candidate, cxx/hirm.hh:859-864). */
+int hirm_irm_set_observations_device(hirm_engine *e, int32_t irm, int rel, int64_t nobs, const int32_t *d_ids,
+                                     const uint8_t *d_val);
 /* Dense binary relation R(d0,d1) as two byte slabs in device memory (0, 1, HIRM_DENSE_MISSING):
  *   d_slab0[i*pitch0 + j] = value of (i, j)   i in d0, j in d1   ("rows by first entity")
  *   d_slab1[j*pitch1 + i] = value of (i, j)                      ("rows by second entity")
@@ -132,6 +137,9 @@ int hirm_engine_sweep_all(hirm_engine *e, int n_irms, const int32_t *h_irms, int
                           int64_t cap_moves, int32_t *h_out_dom, int32_t *h_out_item, int32_t *h_out_choice, int64_t *n_moves);
 /* Philox stream id (default: the irm id) and move counter used by hirm_engine_sweep_all / _transition_alpha */
 int hirm_irm_set_rng(hirm_engine *e, int32_t irm, uint64_t stream, uint64_t move_counter);
+/* the two other Philox positions of an IRM: sweeps made by hirm_engine_sweep_all (keys the sweep order) and calls of
+ * hirm_engine_transition_alpha; set when an IRM is re-created or moved to another GPU in the middle of a chain */
+int hirm_irm_set_rng_counters(hirm_engine *e, int32_t irm, uint64_t sweep_counter, uint64_t alpha_counter);
 
 /* IRM::logp_score for many IRMs in one launch   (cxx/hirm.hh:730-740) */
 int hirm_engine_logp_scores(hirm_engine *e, int n_irms, const int32_t *h_irms, double *h_out);
@@ -154,6 +162,26 @@ int hirm_irm_get_tables(hirm_engine *e, int32_t irm, int dom, int32_t *h_labels,
  * first (hirm_irm_seat_entities), as the reference's trial incorporate does. */
 int hirm_engine_relation_scores(hirm_engine *e, int32_t src_irm, int rel, int n_cand, const int32_t *h_cand_irms,
                                 const int32_t *h_cand_doms, double *h_out);
+/* One whole sweep of relation moves at once: Relation::logp_score (cxx/hirm.hh:516-522) of EVERY listed relation under the
+ * domain partitions of EVERY listed IRM -- the quantity of cxx/hirm.hh:865 for all (relation, candidate table) pairs.  It
+ * depends only on the relation's observations and the candidate's partitions, so the matrix can be computed (and, across
+ * GPUs, all-gathered) before the sequential re-seating of the relations.  Relations are given as device COO arrays
+ * (h_d_ids[r] / h_d_val[r] are DEVICE pointers, h_rel_doms [n_rel * HIRM_MAX_ARITY] the candidates' domain index per
+ * position); the candidates must share domains, entity codes and max_tables, with every entity seated.
+ * h_out [n_rel * n_cand], row-major. */
+int hirm_engine_relation_score_matrix(hirm_engine *e, int n_rel, const int32_t *h_arity, const int32_t *h_rel_doms,
+                                      const int64_t *h_nobs, const int32_t *const *h_d_ids, const uint8_t *const *h_d_val,
+                                      int n_cand, const int32_t *h_cand_irms, double *h_out);
+/* The fresh-table candidate of every listed relation (cxx/hirm.hh:849-864: `new IRM({}, prng)`, whose domains are seated by
+ * sequential CRP-prior draws when the relation is incorporated, :194-203): one independent CRP(alpha) draw per (relation,
+ * domain the relation uses), Philox stream h_keys[r * n_domains + d]; h_out[r] = the relation's logp_score under its draw. */
+int hirm_engine_relation_scores_fresh(hirm_engine *e, int n_rel, const int32_t *h_arity, const int32_t *h_rel_doms,
+                                      const int64_t *h_nobs, const int32_t *const *h_d_ids, const uint8_t *const *h_d_val,
+                                      int n_domains, const int32_t *h_n_entities, const int32_t *h_max_tables, double alpha,
+                                      uint64_t seed, const uint64_t *h_keys, double *h_out);
+/* The same draw again, to the host: sequential CRP(alpha) prior over n customers (Domain::incorporate for every entity of a
+ * fresh domain, cxx/hirm.hh:194-203 + CRP::sample :101-113), labels in order of appearance, Philox stream `key`. */
+int hirm_engine_crp_prior_draw(hirm_engine *e, int n, double alpha, int max_tables, uint64_t seed, uint64_t key, int32_t *h_labels);
 /* Domain::incorporate(item, table) for entities not yet in the domain (cxx/hirm.hh:194-203) */
 int hirm_irm_seat_entities(hirm_engine *e, int32_t irm, int dom, int n, const int32_t *h_items, const int32_t *h_labels);
 
