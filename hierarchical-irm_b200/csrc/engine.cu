@@ -1139,8 +1139,16 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
     CK(cudaEventRecord(e->ev0, e->stream));
     if (!plan.generic_blk.empty()) {
         // few IRMs: 256 threads each (shortest move); many: 128 threads, 8 CTAs per SM hide one another's memory latency
-        const int gen_threads = (int)plan.generic_blk.size() > 4 * e->num_sms ? 128 : GEN_THREADS;
-        generic_sweep_kernel<<<(unsigned)plan.generic_blk.size(), gen_threads, 0, e->stream>>>(args, e->s_blk.p);
+        // at most one IRM per SM: 1024 threads each (shortest move: every phase of a move is spread over the whole SM);
+        // up to 4 per SM: 256 threads; many: 128 threads, 8 CTAs per SM hide one another's memory latency
+        const int n_gen = (int)plan.generic_blk.size();
+        int gen_threads = n_gen <= e->num_sms ? 1024 : n_gen <= 4 * e->num_sms ? 256 : 128;
+        if (const char *s = getenv("HIRM_GENERIC_THREADS")) gen_threads = std::max(64, std::min(1024, atoi(s) & ~31));
+        GenericLaunch GL;
+        GL.rcap = gen_threads; GL.pcap = 4 * gen_threads;
+        const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap);
+        CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)generic_smem_bytes(1024, 4096)));
+        generic_sweep_kernel<<<(unsigned)n_gen, gen_threads, gen_smem, e->stream>>>(args, e->s_blk.p, GL);
         CK(cudaGetLastError());
         e->last_launches++; e->last_kind = 0;
     }

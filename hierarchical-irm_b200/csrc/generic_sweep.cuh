@@ -19,7 +19,7 @@
 
 namespace hirm {
 
-constexpr int GEN_THREADS = 256;   // maximum; launched with 256 (few IRMs: shortest move) or 128 (many: 8 CTAs per SM)
+constexpr int GEN_THREADS = 1024;  // maximum; launched with 1024 (at most one IRM per SM: shortest move), 256, or 128 (many IRMs: 8 CTAs per SM)
 constexpr int GEN_WARPS = GEN_THREADS / 32;
 constexpr int GEN_MAXK = 256;   // kcap <= 255 candidates + 1 fresh
 constexpr int GEN_LF = 256;     // shared-memory copy of lgamma(m+1), m < 256; Stirling beyond (device_math.cuh)
@@ -110,7 +110,20 @@ __device__ __forceinline__ GroupRef ref_of(const GroupRec &r) {
     return g;
 }
 
-__global__ void __launch_bounds__(GEN_THREADS, 4) generic_sweep_kernel(SweepArgs args, const int32_t *blk_list) {
+// S(N+1, s+x) - S(N, s) for a group of ONE observation (every group of a unary relation, most groups of a sparse one):
+// log(s + 1) - log(N + 2) if x = 1, log(N - s + 1) - log(N + 2) if x = 0 -- two logarithms instead of the general
+// form's six; gn = 0 (a lane without work) gives 0.
+__device__ __forceinline__ double score_delta_unit(uint32_t N, uint32_t sv, uint32_t gn, uint32_t gs) {
+    const double a = gs ? (double)sv + 1.0 : (double)(N - sv) + 1.0;
+    const double v = log_core(a) - log_core((double)N + 2.0);
+    return gn ? v : 0.0;
+}
+
+// Dynamic shared memory of one CTA: [rcap] group records, [rcap] touched accumulator bits, [pcap] partial sums.
+struct GenericLaunch { int32_t rcap, pcap; };
+__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap) { return (size_t)rcap * (sizeof(GroupRec) + 8) + (size_t)pcap * 8; }
+
+__global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs args, const int32_t *blk_list, GenericLaunch GL) {
     const int k_list = blk_list ? blk_list[blockIdx.x] : blockIdx.x;
     const IrmDev &irm = args.irms[args.irm_ids[k_list]];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -122,7 +135,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 4) generic_sweep_kernel(SweepArgs
     __shared__ double s_lf[GEN_LF];
     __shared__ int32_t s_warp_tot[GEN_WARPS];
     __shared__ int32_t s_ncand, s_choice_slot, s_choice_label, s_fail;
-    GroupRec *recs = reinterpret_cast<GroupRec *>(irm.gl_cell);     // [gl_cap] group records (engine scratch)
+    GroupRec *recs = reinterpret_cast<GroupRec *>(irm.gl_cell);     // [gl_cap] group records beyond the shared-memory ones (engine scratch)
+    extern __shared__ __align__(16) unsigned char gen_dyn[];
+    GroupRec *s_recs = reinterpret_cast<GroupRec *>(gen_dyn);                                  // [rcap]
+    long long *s_bits = reinterpret_cast<long long *>(gen_dyn + (size_t)GL.rcap * sizeof(GroupRec));   // [rcap]
+    double *s_part = reinterpret_cast<double *>(s_bits + GL.rcap);                              // [pcap]
+    const int RCAP = GL.rcap, PCAP = GL.pcap;
 
     for (int k = tid; k < GEN_LF; k += NT) s_lf[k] = g_logfact[k];
     __syncthreads();
@@ -217,7 +235,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 4) generic_sweep_kernel(SweepArgs
             if (lane == 0) s_ncand = nc;
         }
 
-        // ---- B: ordered compaction of the touched accumulator cells ----------------------------------
+        // ---- B1: ordered list of the touched accumulator cells (bitmap scan: ascending bit = deterministic order) ----
         int64_t base = 0;
         for (int64_t w0 = 0; w0 < irm.gwords; w0 += NT) {
             const int64_t w = w0 + tid;
@@ -235,39 +253,46 @@ __global__ void __launch_bounds__(GEN_THREADS, 4) generic_sweep_kernel(SweepArgs
 #pragma unroll
             for (int k = 0; k < GEN_WARPS; k++) { int v = k < NW ? s_warp_tot[k] : 0; if (k < warp) woff += v; total += v; }
             int64_t off = base + woff + incl - cnt;
-            if (bits) {
-                const int rel = irm.word_rel[w];
-                const int64_t bit0 = irm.rel[rel].gbit0;
-                while (bits) {
-                    const int bpos = __ffsll((long long)bits) - 1;
-                    bits &= bits - 1;
-                    if (off < irm.gl_cap) {            // B2: decode once, for every candidate
-                        const GroupRef gr = decode_group(irm, d, rel, w * 64 + bpos - bit0);
-                        GroupRec rc;
-                        rc.R = gr.R; rc.rest_g = gr.rest_g; rc.rest_c = gr.rest_c; rc.cellidx = w * 64 + bpos - bit0; rc.own = gr.own;
-                        rc.a = (int16_t)gr.a; rc.b = (int16_t)gr.b; rc.da = (int16_t)gr.da; rc.db = (int16_t)gr.db; rc.kd = (int16_t)gr.kd;
-                        rc.pad0 = rc.pad1 = rc.pad2 = 0;
-                        recs[off] = rc;
-                    } else raise_error(irm, KERR_GROUP_OVERFLOW);
-                    off++;
-                }
+            while (bits) {
+                const int bpos = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                if (off >= irm.gl_cap) raise_error(irm, KERR_GROUP_OVERFLOW);
+                else if (off < RCAP) s_bits[off] = w * 64 + bpos;
+                else recs[off].cellidx = w * 64 + bpos;
+                off++;
             }
             base += total;
             __syncthreads();
         }
         const int64_t ngroups = base < irm.gl_cap ? base : irm.gl_cap;
+        // ---- B2: decode every group once, one group per thread (for every candidate) ---------------------------------
+        for (int64_t g = tid; g < ngroups; g += NT) {
+            const int64_t bit = g < RCAP ? s_bits[g] : recs[g].cellidx;
+            const int rel = irm.word_rel[bit >> 6];
+            const int64_t cellidx = bit - irm.rel[rel].gbit0;
+            const GroupRef gr = decode_group(irm, d, rel, cellidx);
+            GroupRec rc;
+            rc.R = gr.R; rc.rest_g = gr.rest_g; rc.rest_c = gr.rest_c; rc.cellidx = cellidx; rc.own = gr.own;
+            rc.a = (int16_t)gr.a; rc.b = (int16_t)gr.b; rc.da = (int16_t)gr.da; rc.db = (int16_t)gr.db; rc.kd = (int16_t)gr.kd;
+            rc.pad0 = rc.pad1 = rc.pad2 = 0;
+            if (g < RCAP) s_recs[g] = rc; else recs[g] = rc;
+        }
         __syncthreads();
         const int ncand = s_ncand;
 
-        // ---- D: score: one warp per candidate, lanes over groups (branch-free cell score) -----------------
-        for (int t = warp; t < ncand; t += NW) {
-            const int slot_t = s_cslot[t];
-            double acc = 0.0;
-            for (int64_t g0 = 0; g0 < ngroups; g0 += 32) {
-                const int64_t g = g0 + lane;
+        // ---- D: score.  Work unit = (candidate, 32 consecutive groups), one warp each, lanes over the groups; the partial
+        //      sums are added per candidate in chunk order afterwards (fixed order: deterministic) -------------------------
+        const int nch = (int)((ngroups + 31) >> 5);
+        const bool flat = (int64_t)ncand * nch <= PCAP;
+        if (flat) {
+            const int nunits = ncand * nch;
+            for (int unit = warp; unit < nunits; unit += NW) {
+                const int t = unit / nch, ch = unit - t * nch;
+                const int slot_t = s_cslot[t];
+                const int64_t g = (int64_t)ch * 32 + lane;
                 uint32_t N = 0u, sv = 0u, gn = 0u, gs = 0u;
                 if (g < ngroups) {
-                    const GroupRef gr = ref_of(recs[g]);
+                    const GroupRef gr = ref_of(g < RCAP ? s_recs[g] : recs[g]);
                     cell_t delta; int64_t cidx;
                     if (group_target(gr, slot_t, delta, cidx)) {
                         const cell_t cur = __ldcg(&gr.R->counts[cidx]);
@@ -275,11 +300,40 @@ __global__ void __launch_bounds__(GEN_THREADS, 4) generic_sweep_kernel(SweepArgs
                     }
                 }
                 __syncwarp();
-                acc += score_delta_bf<GEN_LF>(s_lf, N, sv, gn, gs);
-            }
+                double acc = __all_sync(0xffffffffu, gn <= 1u) ? score_delta_unit(N, sv, gn, gs) : score_delta_bf<GEN_LF>(s_lf, N, sv, gn, gs);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) s_lp[t] += acc;
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) s_part[unit] = acc;
+            }
+            __syncthreads();
+            for (int t = tid; t < ncand; t += NT) {
+                double acc = 0.0;
+                for (int ch = 0; ch < nch; ch++) acc += s_part[t * nch + ch];
+                s_lp[t] += acc;
+            }
+        } else {
+            for (int t = warp; t < ncand; t += NW) {   // very many groups: one warp per candidate walks all of them
+                const int slot_t = s_cslot[t];
+                double acc = 0.0;
+                for (int64_t g0 = 0; g0 < ngroups; g0 += 32) {
+                    const int64_t g = g0 + lane;
+                    uint32_t N = 0u, sv = 0u, gn = 0u, gs = 0u;
+                    if (g < ngroups) {
+                        const GroupRef gr = ref_of(g < RCAP ? s_recs[g] : recs[g]);
+                        cell_t delta; int64_t cidx;
+                        if (group_target(gr, slot_t, delta, cidx)) {
+                            const cell_t cur = __ldcg(&gr.R->counts[cidx]);
+                            N = cell_n(cur); sv = cell_s(cur); gn = cell_n(delta); gs = cell_s(delta);
+                        }
+                    }
+                    __syncwarp();
+                    double v = __all_sync(0xffffffffu, gn <= 1u) ? score_delta_unit(N, sv, gn, gs) : score_delta_bf<GEN_LF>(s_lf, N, sv, gn, gs);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    acc += v;
+                }
+                if (lane == 0) s_lp[t] += acc;
+            }
         }
         __syncthreads();
 
@@ -326,7 +380,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 4) generic_sweep_kernel(SweepArgs
         // ---- F: apply ------------------------------------------------------------------
         const int tnew = s_choice_slot;
         for (int64_t g = tid; g < ngroups; g += NT) {
-            const GroupRec rc = recs[g];
+            const GroupRec rc = g < RCAP ? s_recs[g] : recs[g];
             const GroupRef gr = ref_of(rc);
             atomicAdd(&gr.R->counts[group_cell_at(gr, tnew)], gr.own);
             __stcg(&gr.R->groups[rc.cellidx], (cell_t)0);
