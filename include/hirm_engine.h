@@ -39,7 +39,7 @@ typedef struct hirm_engine hirm_engine;
 /* sweep flags */
 #define HIRM_SWEEP_SCORE_ONLY 1u   /* score + trace, do not sample/apply (parity hook) */
 #define HIRM_SWEEP_FORCE_GENERIC 2u /* use the CSR/generic kernel even where a fast path exists */
-#define HIRM_SWEEP_CLUSTER 4u      /* dense path: one thread-block cluster per IRM (single-chain latency mode) */
+#define HIRM_SWEEP_CLUSTER 4u      /* reserved: one thread-block cluster per IRM (single-chain latency mode); ignored today */
 
 const char *hirm_last_error(void);
 int hirm_engine_abi_version(void);
