@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NT = blockDim.x, NW = NT >> 5;
 
-    __shared__ int32_t s_cnt[GEN_MAXK], s_lab[GEN_MAXK];
+    // CRP state of every domain (table sizes, labels, highest used slot + 1), resident for the whole move list: only
+    // this CTA changes it (phase F writes shared and global copies alike)
+    __shared__ int32_t s_cnt_all[MAX_DOMAINS * GEN_MAXK], s_lab_all[MAX_DOMAINS * GEN_MAXK], s_hi_all[MAX_DOMAINS];
     __shared__ int32_t s_cslot[GEN_MAXK + 1], s_clabel[GEN_MAXK + 1], u_slot[GEN_MAXK + 1], u_label[GEN_MAXK + 1];
     __shared__ double s_lp[GEN_MAXK + 1], s_tmp[GEN_MAXK + 1];
     __shared__ double s_lf[GEN_LF];
@@ -143,14 +145,37 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     const int RCAP = GL.rcap, PCAP = GL.pcap;
 
     for (int k = tid; k < GEN_LF; k += NT) s_lf[k] = g_logfact[k];
+    for (int dk = 0; dk < irm.n_domains; dk++) {
+        const DomainDev &dq = irm.dom[dk];
+        const int h = __ldcg(dq.hi);
+        if (tid == 0) s_hi_all[dk] = h;
+        for (int k = tid; k < h; k += NT) { s_cnt_all[dk * GEN_MAXK + k] = __ldcg(&dq.tab_count[k]); s_lab_all[dk * GEN_MAXK + k] = __ldcg(&dq.tab_label[k]); }
+    }
     __syncthreads();
 
+    // A move's inputs that do not depend on the move before it (ids, CSR row bounds) and the one that almost never does
+    // (the entity's own slot) are fetched one move ahead: their L2 round trips overlap the current move.
+    struct Pref { int d, item, c; int64_t beg, end; };
     const int64_t m0 = args.move_off[k_list], m1 = args.move_off[k_list + 1];
+    auto fetch = [&](int64_t mm) {
+        Pref f; f.d = -1; f.item = -1; f.c = -1; f.beg = 0; f.end = 0;
+        if (mm >= m1) return f;
+        f.d = args.move_dom[mm]; f.item = args.move_item[mm];
+        if (f.d < 0 || f.d >= irm.n_domains || f.item < 0 || f.item >= irm.dom[f.d].n) { f.d = -1; return f; }
+        const DomainDev &dq = irm.dom[f.d];
+        f.c = __ldcg(&dq.z[f.item]);
+        if (dq.ptr) { f.beg = dq.ptr[f.item]; f.end = dq.ptr[f.item + 1]; }
+        return f;
+    };
+
+    Pref nxt = fetch(m0);
     for (int64_t m = m0; m < m1; m++) {
-        const int d = args.move_dom[m], item = args.move_item[m];
-        bool bad = d < 0 || d >= irm.n_domains || item < 0 || item >= irm.dom[d < 0 ? 0 : d].n;
-        const DomainDev &dd = irm.dom[bad ? 0 : d];
-        const int c = bad ? -1 : __ldcg(&dd.z[item]);
+        const Pref cur = nxt;
+        nxt = fetch(m + 1);
+        const bool bad = cur.d < 0;
+        const int d = bad ? 0 : cur.d, item = cur.item;
+        const DomainDev &dd = irm.dom[d];
+        const int c = bad ? -1 : cur.c;
         if (c < 0) {                                  // uniform across the block
             if (tid == 0) {
                 raise_error(irm, KERR_BAD_MOVE);
@@ -160,12 +185,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             continue;
         }
         if (tid == 0) s_fail = 0;
-        const int hi = __ldcg(dd.hi);
-        for (int k = tid; k < hi; k += NT) { s_cnt[k] = __ldcg(&dd.tab_count[k]); s_lab[k] = __ldcg(&dd.tab_label[k]); }
+        int32_t *s_cnt = s_cnt_all + d * GEN_MAXK, *s_lab = s_lab_all + d * GEN_MAXK;
+        const int hi = s_hi_all[d];
 
         // ---- A: remove + group (fire-and-forget reductions; completed by the fence below) -----------
         if (dd.ptr) {
-            const int64_t beg = dd.ptr[item], end = dd.ptr[item + 1];
+            const int64_t beg = cur.beg, end = cur.end;
             for (int64_t q = beg + tid; q < end; q += NT) {
                 const uint32_t meta = dd.meta[q];
                 const int rel = meta & META_REL_MASK;
@@ -249,9 +274,14 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             }
             if (lane == 31) s_warp_tot[warp] = incl;
             __syncthreads();
-            int woff = 0, total = 0;
+            int wv = lane < NW ? s_warp_tot[lane] : 0, wincl = wv;      // scan of the warp totals (at most 32 warps)
 #pragma unroll
-            for (int k = 0; k < GEN_WARPS; k++) { int v = k < NW ? s_warp_tot[k] : 0; if (k < warp) woff += v; total += v; }
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, wincl, o);
+                if (lane >= o) wincl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, wincl, 31);
+            const int woff = __shfl_sync(0xffffffffu, wincl - wv, warp);
             int64_t off = base + woff + incl - cnt;
             while (bits) {
                 const int bpos = __ffsll((long long)bits) - 1;
@@ -391,13 +421,15 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             __stcg(&dd.tab_count[c], s_cnt[c] - 1);
             const int newcnt = (tnew < hi ? s_cnt[tnew] : 0) + 1;
             __stcg(&dd.tab_count[tnew], newcnt);
-            if (newcnt == 1) __stcg(&dd.tab_label[tnew], s_choice_label);
+            if (newcnt == 1) { __stcg(&dd.tab_label[tnew], s_choice_label); s_lab[tnew] = s_choice_label; }
             int nhi = max(hi, tnew + 1);
             if (s_cnt[c] == 1) {                       // table c emptied: CRP::unincorporate erases it (:95-97)
                 while (nhi > 0 && (nhi - 1 == c || (nhi - 1 != tnew && (nhi - 1 >= hi || s_cnt[nhi - 1] == 0)))) nhi--;
             }
             __stcg(dd.hi, nhi);
+            s_cnt[c] -= 1; s_cnt[tnew] = newcnt; s_hi_all[d] = nhi;      // the resident copies
         }
+        if (tnew != c && nxt.d == d && nxt.item == item) nxt.c = tnew;    // the same entity again: its prefetched slot is stale
         __threadfence();
         __syncthreads();
     }

@@ -205,7 +205,7 @@ class ShardedHIRM:
     (hirm.util_io encodes the reference's .obs files the same way)."""
 
     def __init__(self, domains, schema, observations, seed=0, max_tables=64, comm=None, backend=None,
-                 relation_tables=None, partitions=None, alphas=None, rebalance=True, host_order=False, device=None):
+                 relation_tables=None, partitions=None, alphas=None, rebalance=True, host_order=False, device=None, chain=0):
         self.dnames = list(domains)
         self.n_ent = [int(domains[d]) for d in self.dnames]
         if len(self.dnames) > 8:
@@ -222,10 +222,11 @@ class ShardedHIRM:
         self.alpha = 1.0                                   # CRP over relations (cxx/hirm.hh:790); never transitioned by inference_hirm
         self.irms = {}                                     # table label -> dict(uid, owner, rels, handle, steps, changed)
         self.rel_table = {}
-        self._next_uid, self._next_key, self.iteration = 0, 1 << 40, 0
+        self.chain = int(chain)                            # independent seeded chains: disjoint Philox streams and keys
+        self._next_uid, self._next_key, self.iteration = self.chain << 24, (1 << 60) | (self.chain << 44), 0
         self.timers = dict(entity=0.0, score=0.0, gather=0.0, reseat=0.0, rebuild=0.0)
         R = len(self.rnames)
-        rng = np.random.default_rng([self.seed, 0x696E6974])
+        rng = np.random.default_rng([self.seed, self.chain, 0x696E6974])
         if relation_tables is None:                        # HIRM::add_relation (:947-957): sequential CRP(alpha) seating
             relation_tables, sizes = {}, {}
             for r in self.rnames:
@@ -374,7 +375,7 @@ class ShardedHIRM:
         import time
         cols, fresh, keys = self.score_columns()
         t0 = time.perf_counter()
-        rng = np.random.default_rng([self.seed, self.iteration, 0x72656C])
+        rng = np.random.default_rng([self.seed, self.chain, self.iteration, 0x72656C])
         order = rng.permutation(len(self.rnames))
         us = rng.random(len(self.rnames))
         moved = 0
@@ -452,3 +453,34 @@ class ShardedHIRM:
         for part in self.comm.all_gather_obj(mine):
             merged.update(part)
         return {t: merged[t] for t in sorted(merged)}
+
+
+class ChainSet:
+    """Several independent seeded chains of one HIRM over the same observations and the same ranks (BASELINE config 5:
+    "8 chains").  The chains share the replicated COO arrays; per iteration the relation steps run chain by chain (small),
+    then the entity sweeps of EVERY chain's local IRMs go out in ONE launch -- chains are what fills a GPU when an HIRM
+    has only a few IRMs per rank."""
+
+    def __init__(self, domains, schema, observations, n_chains, seed=0, max_tables=64, comm=None, backend=None, **kw):
+        first = ShardedHIRM(domains, schema, observations, seed=seed, max_tables=max_tables, comm=comm, backend=backend, chain=0, **kw)
+        self.chains = [first] + [ShardedHIRM(domains, schema, observations, seed=seed, max_tables=max_tables, comm=first.comm,
+                                             backend=first.backend, chain=c, **kw) for c in range(1, n_chains)]
+        self.backend, self.comm = first.backend, first.comm
+
+    def transition_relations(self):
+        return [h.transition_relations() for h in self.chains]
+
+    def transition_irms(self):
+        hs = [h.irms[t]["handle"] for h in self.chains for t in h._local()]
+        self.backend.step(hs)
+        for h in self.chains:
+            for info in h.irms.values():
+                info["steps"] += 1
+
+    def iterate(self, n=1):
+        for _ in range(n):
+            self.transition_relations()
+            self.transition_irms()
+
+    def logp_scores(self):
+        return [h.logp_score() for h in self.chains]

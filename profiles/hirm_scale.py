@@ -4,7 +4,7 @@ over the ranks (hirm.sharded.ShardedHIRM), relation moves from one all-gathered 
 
     python profiles/hirm_scale.py                                   # one GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 profiles/hirm_scale.py
-    env: NE NU NB BOBS (cells per binary relation) NC ITERS KCAP SEED PLANTED (1: start from the planted relation clusters)
+    env: NE NU NB BOBS (cells per binary relation) NC ITERS KCAP SEED CHAINS PLANTED (1: start from the planted relation clusters) BURN (entity-only steps before the timed iterations)
 
 Prints one JSON line per rank-0 run: entity moves/s of the whole job (max over ranks of the device-synchronised wall
 time of the entity step), the time split of the relation step, the number of collectives."""
@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from hirm.sharded import Comm, ShardedHIRM
+from hirm.sharded import ChainSet, Comm
 
 
 def env(name, default):
@@ -58,7 +58,8 @@ def main():
     domains, schema, obs, truth = make(ne, nu, nb, bobs, nc, seed)
     t0 = time.perf_counter()
     rt = {r: truth[r] for r in schema} if env("PLANTED", 1) else None
-    h = ShardedHIRM(domains, schema, obs, seed=seed, max_tables=kcap, comm=Comm(), relation_tables=rt, device=local)
+    chains = env("CHAINS", 1)
+    h = ChainSet(domains, schema, obs, chains, seed=seed, max_tables=kcap, comm=Comm(), relation_tables=rt, device=local)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
     n_obs = sum(len(v[1]) for v in obs.values())
@@ -71,30 +72,33 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    for _ in range(env("BURN", 2)):                         # entity-only steps first: the partitions of the planted clusters become informative
+        h.transition_irms()
     rows = []
     for it in range(iters):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        moved = h.transition_relations()
+        moved = sum(h.transition_relations())
         t_rel = sync_max(time.perf_counter() - t0)
-        n_irms = len(h.irms)
+        n_irms = sum(len(c.irms) for c in h.chains)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         h.transition_irms()
         t_ent = sync_max(time.perf_counter() - t0)
         rows.append(dict(iter=it, relation_step_s=t_rel, entity_step_s=t_ent, irms=n_irms, relations_moved=moved,
-                         entity_moves=n_irms * ne, loads=h.loads()))
-    score = h.logp_score()
+                         entity_moves=n_irms * ne, loads=h.chains[0].loads()))
+    score = h.logp_scores()
     if rank == 0:
         steady = rows[1:] or rows
         ent = sum(r["entity_moves"] for r in steady) / sum(r["entity_step_s"] for r in steady)
         print(json.dumps(dict(workload="scaled C5: %d unary + %d binary (%d cells each) relations over %d entities, %d planted clusters"
-                                       % (nu, nb, bobs, ne, nc), n_gpus=world, observations=n_obs, setup_s=setup_s,
+                                       % (nu, nb, bobs, ne, nc), n_gpus=world, chains=chains, observations=n_obs, setup_s=setup_s,
                               entity_moves_per_s=ent, relation_step_s=float(np.mean([r["relation_step_s"] for r in steady])),
-                              timers=h.timers, collectives=dict(all_gather=h.comm.n_allgather, broadcast=h.comm.n_broadcast),
+                              timers={k: sum(c.timers[k] for c in h.chains) for k in h.chains[0].timers},
+                              collectives=dict(all_gather=h.comm.n_allgather, broadcast=h.comm.n_broadcast),
                               logp_score=score, rows=rows)))
     if world > 1:
         dist.barrier()
