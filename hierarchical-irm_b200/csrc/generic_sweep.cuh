@@ -169,6 +169,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     };
 
     Pref nxt = fetch(m0);
+    // debug hook (hirm_engine_debug_phase_cycles): thread 0's SM cycles per phase, summed over the moves:
+    // [0] A  [1] B1 (+C)  [2] B2  [3] D  [4] E  [5] F  -- 32 slots per block, shared with the dense kernel's layout
+    const bool prof = args.phase_cycles != nullptr && tid == 0;
+    long long ph_t = prof ? clock64() : 0, ph_acc[6] = {0, 0, 0, 0, 0, 0};
+#define GEN_PHASE(i) do { if (prof) { const long long now = clock64(); ph_acc[i] += now - ph_t; ph_t = now; } } while (0)
     for (int64_t m = m0; m < m1; m++) {
         const Pref cur = nxt;
         nxt = fetch(m + 1);
@@ -222,6 +227,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         }
         __threadfence();
         __syncthreads();
+        GEN_PHASE(0);
 
         // ---- C: candidates, CRP::tables_weights_gibbs (cxx/hirm.hh:147-161): warp 0, lanes over the tables ----
         if (warp == 0) {
@@ -295,6 +301,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             __syncthreads();
         }
         const int64_t ngroups = base < irm.gl_cap ? base : irm.gl_cap;
+        GEN_PHASE(1);
         // ---- B2: decode every group once, one group per thread (for every candidate) ---------------------------------
         for (int64_t g = tid; g < ngroups; g += NT) {
             const int64_t bit = g < RCAP ? s_bits[g] : recs[g].cellidx;
@@ -308,6 +315,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             if (g < RCAP) s_recs[g] = rc; else recs[g] = rc;
         }
         __syncthreads();
+        GEN_PHASE(2);
         const int ncand = s_ncand;
 
         // ---- D: score.  Work unit = (candidate, 32 consecutive groups), one warp each, lanes over the groups; the partial
@@ -366,6 +374,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             }
         }
         __syncthreads();
+        GEN_PHASE(3);
 
         // ---- E: sample (warp 0): log_choice (cxx/util_math.cc:58-65); exp lane-parallel, sums in index order ----
         if (warp == 0) {
@@ -407,6 +416,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         }
         __syncthreads();
 
+        GEN_PHASE(4);
         // ---- F: apply ------------------------------------------------------------------
         const int tnew = s_choice_slot;
         for (int64_t g = tid; g < ngroups; g += NT) {
@@ -432,7 +442,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         if (tnew != c && nxt.d == d && nxt.item == item) nxt.c = tnew;    // the same entity again: its prefetched slot is stale
         __threadfence();
         __syncthreads();
+        GEN_PHASE(5);
     }
+    if (prof) for (int i = 0; i < 6; i++) args.phase_cycles[blockIdx.x * 32 + i] = ph_acc[i];
+#undef GEN_PHASE
 }
 
 // ---------------------------------------------------------------------------------------
