@@ -81,10 +81,12 @@ struct Irm {
     // device state
     std::vector<DevBuf<int32_t>> z, tab_count, tab_label, hi;
     std::vector<double> alpha;
-    std::vector<DevBuf<cell_t>> counts, groups;
-    std::vector<std::array<int64_t, MAX_ARITY>> cstride, gstride;
-    std::vector<int64_t> ncells, gcells, gbit0;
-    DevBuf<unsigned long long> gbitmap; DevBuf<int32_t> word_rel; int64_t gwords = 0;
+    std::vector<DevBuf<cell_t>> counts;
+    std::vector<std::array<int64_t, MAX_ARITY>> cstride;
+    std::vector<int64_t> ncells;
+    // generic kernel: compact group-accumulator spaces per (relation, domain) (engine_types.cuh: RelDom)
+    DevBuf<RelDom> rdesc; std::vector<DevBuf<int32_t>> cmap; std::vector<int32_t> ctot;
+    DevBuf<cell_t> gacc; DevBuf<uint32_t> gbm;
     DevBuf<int32_t> gl_rel; DevBuf<int64_t> gl_cell; int64_t gl_cap = 0;
     DevBuf<int32_t> error;
     DevBuf<RelationDev> d_rel;
@@ -208,13 +210,13 @@ extern "C" int hirm_irm_create(hirm_engine *e, int n_domains, const int32_t *n_e
     }
     irm->alpha.assign(n_domains, 1.0);                 // CRP::alpha default (cxx/hirm.hh:72)
     irm->have_z.assign(n_domains, false); irm->has_absent.assign(n_domains, false);
-    irm->cstride.resize(n_relations); irm->gstride.resize(n_relations);
-    irm->ncells.resize(n_relations); irm->gcells.resize(n_relations); irm->gbit0.resize(n_relations);
+    irm->cstride.resize(n_relations);
+    irm->ncells.resize(n_relations);
     const int64_t CELL_BUDGET = (int64_t)1 << 27;      // 1 GiB of packed cells per table
     for (int r = 0; r < n_relations; r++) {
         if (arity[r] < 1 || arity[r] > MAX_ARITY) return fail("arity must be in [1, HIRM_MAX_ARITY]");
         std::array<int32_t, MAX_ARITY> ds{};
-        int64_t cs = 1, gs = 1;
+        int64_t cs = 1;
         for (int p = 0; p < arity[r]; p++) {
             int d = rel_domains[r * MAX_ARITY + p];
             if (d < 0 || d >= n_domains) return fail("relation names a domain out of range");
@@ -222,11 +224,11 @@ extern "C" int hirm_irm_create(hirm_engine *e, int n_domains, const int32_t *n_e
             int occ = 0;
             for (int q = 0; q <= p; q++) occ += rel_domains[r * MAX_ARITY + q] == d;
             if (occ > 2) return fail("a domain may occur at most twice in one relation");
-            irm->cstride[r][p] = cs; irm->gstride[r][p] = gs;
-            cs *= irm->kcap[d]; gs *= irm->kcap[d] + 1;
-            if (gs > CELL_BUDGET) return fail("dense count table too large: lower max_tables (hashed tables are not built yet)");
+            irm->cstride[r][p] = cs;
+            cs *= irm->kcap[d];
+            if (cs > CELL_BUDGET) return fail("dense count table too large: lower max_tables (hashed tables are not built yet)");
         }
-        irm->ncells[r] = cs; irm->gcells[r] = gs;
+        irm->ncells[r] = cs;
         irm->arity.push_back(arity[r]); irm->rdom.push_back(ds);
     }
     irm->obs = std::make_shared<ObsStore>();
@@ -240,7 +242,7 @@ extern "C" int hirm_irm_create(hirm_engine *e, int n_domains, const int32_t *n_e
         CK(irm->tab_label[d].alloc(irm->kcap[d])); CK(cudaMemset(irm->tab_label[d].p, 0, irm->kcap[d] * sizeof(int32_t)));
         CK(irm->hi[d].alloc(1)); CK(cudaMemset(irm->hi[d].p, 0, sizeof(int32_t)));
     }
-    irm->counts.resize(n_relations); irm->groups.resize(n_relations);
+    irm->counts.resize(n_relations);
     CK(irm->error.alloc(1)); CK(cudaMemset(irm->error.p, 0, sizeof(int32_t)));
     irm->rng_stream = (uint64_t)e->irms.size();
     e->irms.push_back(std::move(irm));
@@ -456,33 +458,54 @@ static int finalize_store(hirm_engine *e, Irm *irm) {
 static int ensure_scratch(hirm_engine *e, Irm *irm) {
     if (irm->scratch_ready) return 0;
     ObsStore &S = *irm->obs;
-    int64_t bit = 0;
     bool any_csr = false;
     for (int r = 0; r < irm->n_relations; r++) {
         CK(irm->counts[r].ensure((size_t)irm->ncells[r]));
-        if (S.rel[r].kind == 0) {
-            any_csr = true;
-            CK(irm->groups[r].ensure((size_t)irm->gcells[r]));
-            CK(cudaMemsetAsync(irm->groups[r].p, 0, (size_t)irm->gcells[r] * sizeof(cell_t), e->stream));
-            irm->gbit0[r] = bit;
-            bit += (irm->gcells[r] + 63) / 64 * 64;
-        } else irm->gbit0[r] = 0;
+        any_csr |= S.rel[r].kind == 0;
     }
-    irm->gwords = bit / 64;
     if (any_csr) {
-        CK(irm->gbitmap.ensure((size_t)irm->gwords));
-        CK(cudaMemsetAsync(irm->gbitmap.p, 0, (size_t)std::max<int64_t>(irm->gwords, 1) * 8, e->stream));
-        std::vector<int32_t> wr((size_t)irm->gwords, 0);
-        for (int r = 0; r < irm->n_relations; r++) {
-            if (S.rel[r].kind != 0) continue;
-            for (int64_t w = irm->gbit0[r] / 64; w < irm->gbit0[r] / 64 + (irm->gcells[r] + 63) / 64; w++) wr[(size_t)w] = r;
+        // compact accumulator spaces: for every domain, the (relation, self pattern) blocks laid end to end
+        const int nd = irm->n_domains;
+        std::vector<RelDom> rd((size_t)irm->n_relations * nd);
+        irm->cmap.resize((size_t)nd); irm->ctot.assign((size_t)nd, 0);
+        int64_t max_ctot = 1;
+        for (int d = 0; d < nd; d++) {
+            std::vector<int32_t> cm;
+            for (int r = 0; r < irm->n_relations; r++) {
+                RelDom &D = rd[(size_t)r * nd + d];
+                memset(&D, 0, sizeof(D));
+                D.a = D.b = -1; D.rest_size = 1;
+                if (S.rel[r].kind != 0) continue;
+                for (int p = 0; p < irm->arity[r]; p++)
+                    if (irm->rdom[r][p] == d) { if (D.a < 0) D.a = p; else D.b = p; }
+                if (D.a < 0) continue;
+                int64_t rest = 1;
+                for (int p = 0; p < irm->arity[r]; p++) {
+                    if (p == D.a || p == D.b) continue;
+                    D.rstride[p] = (int32_t)rest;
+                    rest *= irm->kcap[irm->rdom[r][p]];
+                }
+                const int64_t kd = irm->kcap[d];
+                const int64_t size0 = D.b >= 0 ? rest * kd : rest, size1 = D.b >= 0 ? rest * kd : 0, size2 = D.b >= 0 ? rest : 0;
+                if ((int64_t)cm.size() + size0 + size1 + size2 > ((int64_t)1 << 27)) return fail("group accumulator too large: lower max_tables");
+                D.rest_size = (int32_t)rest;
+                D.base[0] = (int32_t)cm.size(); D.base[1] = D.base[0] + (int32_t)size0; D.base[2] = D.base[1] + (int32_t)size1;
+                cm.insert(cm.end(), (size_t)(size0 + size1 + size2), r);
+            }
+            irm->ctot[(size_t)d] = (int32_t)cm.size();
+            max_ctot = std::max<int64_t>(max_ctot, (int64_t)cm.size());
+            CK(irm->cmap[(size_t)d].ensure(cm.size()));
+            if (!cm.empty()) CK(cudaMemcpy(irm->cmap[(size_t)d].p, cm.data(), cm.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         }
-        CK(irm->word_rel.ensure(wr.size()));
-        if (!wr.empty()) CK(cudaMemcpy(irm->word_rel.p, wr.data(), wr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(irm->rdesc.ensure(rd.size()));
+        if (!rd.empty()) CK(cudaMemcpy(irm->rdesc.p, rd.data(), rd.size() * sizeof(RelDom), cudaMemcpyHostToDevice));
+        CK(irm->gacc.ensure((size_t)max_ctot)); CK(irm->gbm.ensure((size_t)(max_ctot / 32 + 1)));
+        CK(cudaMemsetAsync(irm->gacc.p, 0, (size_t)max_ctot * sizeof(cell_t), e->stream));
+        CK(cudaMemsetAsync(irm->gbm.p, 0, (size_t)(max_ctot / 32 + 1) * sizeof(uint32_t), e->stream));
         int64_t cap = 1;
         for (int d = 0; d < irm->n_domains; d++) cap = std::max(cap, S.dom[d].max_deg);
         irm->gl_cap = cap;
-        CK(irm->gl_rel.ensure((size_t)cap)); CK(irm->gl_cell.ensure((size_t)cap * (sizeof(GroupRec) / sizeof(int64_t))));   // one GroupRec per group
+        CK(irm->gl_cell.ensure((size_t)cap * (sizeof(GroupRec) / sizeof(int64_t))));   // one GroupRec per group
     }
     irm->dense_ree = irm->n_domains == 1 && irm->n_relations == 1 && S.rel[0].kind == 1 && irm->kcap[0] <= 64;
     irm->scratch_ready = true; irm->desc_dirty = true;
@@ -512,9 +535,8 @@ static int upload_desc(hirm_engine *e, int32_t id) {
         RelationDev &R = rd[r];
         memset(&R, 0, sizeof(R));
         R.arity = irm->arity[r]; R.kind = S.rel[r].kind;
-        for (int p = 0; p < MAX_ARITY; p++) { R.dom[p] = irm->rdom[r][p]; R.cstride[p] = irm->cstride[r][p]; R.gstride[p] = irm->gstride[r][p]; }
+        for (int p = 0; p < MAX_ARITY; p++) { R.dom[p] = irm->rdom[r][p]; R.cstride[p] = irm->cstride[r][p]; }
         R.counts = irm->counts[r].p; R.ncells = irm->ncells[r];
-        R.groups = irm->groups[r].p; R.gcells = irm->gcells[r]; R.gbit0 = irm->gbit0[r];
         R.slab[0] = S.rel[r].slab[0]; R.slab[1] = S.rel[r].slab[1]; R.pitch[0] = S.rel[r].pitch[0]; R.pitch[1] = S.rel[r].pitch[1];
         R.coo_ids = S.rel[r].ids; R.coo_val = S.rel[r].val; R.nobs = S.rel[r].nobs;
         R.full_obs = S.rel[r].full_obs > 0 ? 1 : 0;
@@ -533,8 +555,9 @@ static int upload_desc(hirm_engine *e, int32_t id) {
         dd.nnz = S.dom[d].nnz; dd.n_other = S.dom[d].n_other;
     }
     D.rel = irm->d_rel.p;
-    D.gbitmap = irm->gbitmap.p; D.word_rel = irm->word_rel.p; D.gwords = irm->gwords;
-    D.gl_rel = irm->gl_rel.p; D.gl_cell = irm->gl_cell.p; D.gl_cap = irm->gl_cap;
+    D.rdesc = irm->rdesc.p; D.gacc = irm->gacc.p; D.gbm = irm->gbm.p;
+    for (int d = 0; d < irm->n_domains && d < (int)irm->cmap.size(); d++) { D.cmap[d] = irm->cmap[(size_t)d].p; D.ctot[d] = irm->ctot[(size_t)d]; }
+    D.gl_rel = nullptr; D.gl_cell = irm->gl_cell.p; D.gl_cap = irm->gl_cap;
     D.error = irm->error.p;
     e->h_irms[id] = D;
     // pageable source: make the copy synchronous w.r.t. the host buffers (rd, D are locals)
@@ -1145,9 +1168,9 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         int gen_threads = n_gen <= e->num_sms ? 1024 : n_gen <= 4 * e->num_sms ? 256 : 128;
         if (const char *s = getenv("HIRM_GENERIC_THREADS")) gen_threads = std::max(64, std::min(1024, atoi(s) & ~31));
         GenericLaunch GL;
-        GL.rcap = gen_threads; GL.pcap = 4 * gen_threads;
-        const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap);
-        CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)generic_smem_bytes(1024, 4096)));
+        GL.rcap = gen_threads; GL.pcap = 4 * gen_threads; GL.scap = 4 * gen_threads;
+        const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap);
+        CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)generic_smem_bytes(1024, 4096, 4096)));
         generic_sweep_kernel<<<(unsigned)n_gen, gen_threads, gen_smem, e->stream>>>(args, e->s_blk.p, GL);
         CK(cudaGetLastError());
         e->last_launches++; e->last_kind = 0;

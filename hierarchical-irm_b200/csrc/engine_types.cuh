@@ -41,10 +41,6 @@ struct RelationDev {
     cell_t *counts;               // dense count table, index = sum_p slot_p * cstride[p]   (Relation::clusters, :246)
     int64_t cstride[MAX_ARITY];
     int64_t ncells;
-    cell_t *groups;               // per-move group accumulator, radix (kcap_p + 1), digit kcap_p = "self"
-    int64_t gstride[MAX_ARITY];
-    int64_t gcells;
-    int64_t gbit0;                // first bit of this relation in the IRM's group bitmap (multiple of 64)
     const uint8_t *slab[2];       // dense: rows by first / by second entity
     int64_t pitch[2];
     const int32_t *coo_ids;       // [nobs*arity] (CSR relations: kept for count-table rebuilds)
@@ -54,16 +50,34 @@ struct RelationDev {
     int32_t pad;
 };
 
+// Group accumulators of the generic kernel.  While entity i of domain d moves, its observations in relation r fall into
+// groups keyed by (which positions of the observation hold i itself, the tables of the other positions)
+// (get_cluster_to_items_list, cxx/hirm.hh:388-397).  The keys that can occur for (r, d) form a small space: with a, b
+// the positions of d in r (b = -1 if d occurs once) and "rest" the remaining positions,
+//   pattern 0: i at a only      cell = base[0] + rest_k + (table of the entity at b) * rest_size      (b >= 0)
+//   pattern 1: i at b only      cell = base[1] + rest_k + (table of the entity at a) * rest_size
+//   pattern 2: i at a and b     cell = base[2] + rest_k
+// rest_k = sum over the rest positions of table * rstride.  All (r, d) spaces of one domain are laid end to end
+// (`ctot[d]` cells); the accumulator of a move lives in shared memory when that fits, else in the IRM's global scratch.
+struct RelDom {
+    int32_t a, b;                 // a < 0: the relation does not touch the domain
+    int32_t base[3];
+    int32_t rest_size;
+    int32_t rstride[MAX_ARITY];   // of the rest positions
+};
+
 struct IrmDev {
     int32_t n_domains, n_relations;
     DomainDev dom[MAX_DOMAINS];
     const RelationDev *rel;       // [n_relations]
-    // generic-kernel scratch
-    unsigned long long *gbitmap;  // [gwords] one bit per group-accumulator cell that is non-zero
-    int32_t *word_rel;            // [gwords] relation owning each bitmap word
-    int64_t gwords;
-    int32_t *gl_rel;              // compacted group list
-    int64_t *gl_cell;             // index into rel.groups
+    // generic-kernel group accumulators
+    const RelDom *rdesc;          // [n_relations * n_domains]
+    const int32_t *cmap[MAX_DOMAINS];   // [ctot[d]] relation owning each accumulator cell of domain d
+    int32_t ctot[MAX_DOMAINS];
+    cell_t *gacc;                 // [max ctot] accumulator, all zero between moves       (used when ctot[d] > shared capacity)
+    uint32_t *gbm;                // [max ctot / 32] one bit per non-zero accumulator cell
+    int32_t *gl_rel;              // unused
+    int64_t *gl_cell;             // [gl_cap] group records beyond the shared-memory ones
     int64_t gl_cap;
     int32_t *error;               // [1] first error code raised by a kernel (0 = none)
 };

@@ -3,17 +3,21 @@
 // IRM are sequentially dependent, cxx/hirm.hh:606-641; IRMs are independent).
 //
 // Per move (domain d, entity i, current slot c):
-//   A  stream i's CSR row; every observation is (1) removed from its count-table cell
-//      (the "rest" counts) and (2) added to the group accumulator keyed by the cluster
-//      tuple with a SELF digit at i's own positions      -> get_cluster_to_items_list (cxx/hirm.hh:388-397)
-//   B  ordered compaction of the touched accumulator cells into the group list
+//   A  stream i's CSR row; every observation is added to the group accumulator cell keyed by (the positions holding i
+//      itself, the tables of the other positions)          -> get_cluster_to_items_list (cxx/hirm.hh:388-397).
+//      The accumulator of a move is a small compact table (engine_types.cuh: RelDom) in SHARED memory (shared-memory
+//      atomics; global scratch only if it does not fit).  Relations in which d occurs once are scored against the count
+//      table with i's observations removed VIRTUALLY (the current cell minus the group's own counts): no global atomic
+//      unless the entity really changes tables.  Relations in which d occurs twice remove i's observations from their
+//      count table for the duration of the move (the (i,i) -> (t,t) rule merges groups, cxx/hirm.hh:324-339).
+//   B  ordered list of the touched accumulator cells (bitmap scan), one group record per cell
 //   C  candidate tables + CRP prior, ascending label      -> CRP::tables_weights_gibbs (:147-161)
 //   D  lp[t] = log w_t + sum over target cells of S(N+n, s+sg) - S(N, s)
 //                                                         -> logp_gibbs_exact (:441-461)
 //   E  sample with the injected uniform / Philox          -> log_choice (cxx/util_math.cc:58-65)
-//   F  add the groups back at the chosen slot, re-seat    -> set_cluster_assignment_gibbs (:524-551, :219-224)
-// All state is mutated with integer atomics / L2 (.cg) accesses, so count tables are
-// bit-exact and, because the group list is ordered, log-probabilities are deterministic.
+//   F  move the groups to the chosen slot, re-seat        -> set_cluster_assignment_gibbs (:524-551, :219-224)
+// Count tables change by integer atomics only (bit-exact); the group list is ordered, so log-probabilities are
+// deterministic.
 #pragma once
 #include "engine_types.cuh"
 
@@ -24,90 +28,61 @@ constexpr int GEN_WARPS = GEN_THREADS / 32;
 constexpr int GEN_MAXK = 256;   // kcap <= 255 candidates + 1 fresh
 constexpr int GEN_LF = 256;     // shared-memory copy of lgamma(m+1), m < 256; Stirling beyond (device_math.cuh)
 
-struct GroupRef {
+// One group of the moving entity's observations, decoded once per move (phase B) and read by every candidate.
+struct GroupRec {
     const RelationDev *R;
-    int a, b;            // positions of the moved domain (b = -1 if it occurs once)
-    int da, db;          // digits at a, b
-    int64_t rest_g;      // accumulator index without positions a, b
-    int64_t rest_c;      // count-table index without positions a, b
-    int kd;              // SELF digit of the moved domain
-    cell_t own;
+    const RelDom *RD;
+    int64_t rest_c;           // count-table index without the moved domain's positions
+    cell_t own;               // (observations, ones) of the group
+    int32_t rest_k;           // accumulator index of the rest positions
+    int32_t cell;             // accumulator cell of the group
+    int16_t pat, dother, pad0, pad1;   // self pattern 0/1/2; table of the other end (patterns 0, 1 of a twice-occurring domain)
 };
+static_assert(sizeof(GroupRec) == 48, "GroupRec layout (engine.cu sizes the scratch by it)");
 
-__device__ __forceinline__ GroupRef decode_group(const IrmDev &irm, int d, int rel, int64_t cellidx) {
-    GroupRef g;
-    const RelationDev *R = &irm.rel[rel];
-    g.R = R; g.a = -1; g.b = -1; g.da = 0; g.db = 0; g.rest_g = 0; g.rest_c = 0;
-    g.kd = irm.dom[d].kcap;
-    int64_t rem = cellidx;
-    for (int p = 0; p < R->arity; p++) {
-        int radix = irm.dom[R->dom[p]].kcap + 1;
-        int digit = (int)(rem % radix);
-        rem /= radix;
-        if (R->dom[p] == d && g.a < 0) { g.a = p; g.da = digit; }
-        else if (R->dom[p] == d) { g.b = p; g.db = digit; }
-        else { g.rest_g += digit * R->gstride[p]; g.rest_c += digit * R->cstride[p]; }
-    }
-    g.own = __ldcg(&R->groups[cellidx]);
-    return g;
-}
-
-// Resolve the group against candidate slot t: returns false if another group owns the
-// merged target cell; otherwise the merged (n, s) to add and the count-table index.
-__device__ __forceinline__ bool group_target(const GroupRef &g, int t, cell_t &delta, int64_t &cidx) {
+// Resolve the group against candidate slot t: false if another group owns the merged target cell; otherwise the
+// (n, s) to add and the count-table index.  `acc` is the move's accumulator.
+__device__ __forceinline__ bool group_target(const GroupRec &g, const cell_t *acc, int t, cell_t &delta, int64_t &cidx) {
     const RelationDev *R = g.R;
-    if (g.b < 0) {                                   // domain occurs once: no merging
+    const RelDom *D = g.RD;
+    const int64_t ca = R->cstride[D->a];
+    if (D->b < 0) {                                  // domain occurs once: no merging
         delta = g.own;
-        cidx = g.rest_c + t * R->cstride[g.a];
+        cidx = g.rest_c + t * ca;
         return true;
     }
-    const int64_t ga = R->gstride[g.a], gb = R->gstride[g.b];
-    const int64_t ca = R->cstride[g.a], cb = R->cstride[g.b];
-    const int SELF = g.kd;
-    if (g.da == SELF && g.db == SELF) {              // (i, i): target (t, t); absorbs row/col groups whose other end sits in t
-        delta = g.own + __ldcg(&R->groups[g.rest_g + SELF * ga + t * gb]) + __ldcg(&R->groups[g.rest_g + t * ga + SELF * gb]);
+    const int64_t cb = R->cstride[D->b];
+    const int32_t row_t = D->base[0] + g.rest_k + t * D->rest_size;   // i at a, other end in slot t
+    const int32_t col_t = D->base[1] + g.rest_k + t * D->rest_size;   // i at b, other end in slot t
+    const int32_t diag = D->base[2] + g.rest_k;                       // (i, i)
+    if (g.pat == 2) {                                // (i, i): target (t, t); absorbs the row / column groups whose other end sits in t
+        delta = g.own + acc[row_t] + acc[col_t];
         cidx = g.rest_c + t * ca + t * cb;
         return true;
     }
-    if (g.da == SELF) {                              // i at position a, other end in slot db
-        if (g.db != t) { delta = g.own; cidx = g.rest_c + t * ca + g.db * cb; return true; }
-        if (cell_n(__ldcg(&R->groups[g.rest_g + SELF * ga + SELF * gb])) > 0) return false;
-        delta = g.own + __ldcg(&R->groups[g.rest_g + t * ga + SELF * gb]);
+    if (g.pat == 0) {                                // i at position a, other end in slot dother
+        if (g.dother != t) { delta = g.own; cidx = g.rest_c + t * ca + g.dother * cb; return true; }
+        if (cell_n(acc[diag]) > 0) return false;
+        delta = g.own + acc[col_t];
         cidx = g.rest_c + t * ca + t * cb;
         return true;
     }
-    // i at position b, other end in slot da
-    if (g.da != t) { delta = g.own; cidx = g.rest_c + g.da * ca + t * cb; return true; }
-    if (cell_n(__ldcg(&R->groups[g.rest_g + SELF * ga + SELF * gb])) > 0) return false;
-    if (cell_n(__ldcg(&R->groups[g.rest_g + SELF * ga + t * gb])) > 0) return false;
+    // i at position b, other end in slot dother
+    if (g.dother != t) { delta = g.own; cidx = g.rest_c + g.dother * ca + t * cb; return true; }
+    if (cell_n(acc[diag]) > 0) return false;
+    if (cell_n(acc[row_t]) > 0) return false;
     delta = g.own;
     cidx = g.rest_c + t * ca + t * cb;
     return true;
 }
 
-// count-table index of the group's cell when the entity sits in slot t (no merging: used
-// to add the groups back, where integer adds merge by themselves)
-__device__ __forceinline__ int64_t group_cell_at(const GroupRef &g, int t) {
+// count-table index of the group's cell when the entity sits in slot t (no merging: integer adds merge by themselves)
+__device__ __forceinline__ int64_t group_cell_at(const GroupRec &g, int t) {
     const RelationDev *R = g.R;
-    int64_t c = g.rest_c + (g.da == g.kd ? t : g.da) * R->cstride[g.a];
-    if (g.b >= 0) c += (g.db == g.kd ? t : g.db) * R->cstride[g.b];
+    const RelDom *D = g.RD;
+    int64_t c = g.rest_c + (g.pat == 1 ? (int)g.dother : t) * R->cstride[D->a];
+    if (D->b >= 0) c += (g.pat == 0 ? (int)g.dother : t) * R->cstride[D->b];
     return c;
-}
-
-// One decoded group, built once per move (phase B2) and read by every candidate's scoring warp.
-struct GroupRec {
-    const RelationDev *R;
-    int64_t rest_g, rest_c;   // accumulator / count-table index without the moved domain's positions
-    int64_t cellidx;          // index into R->groups
-    cell_t own;
-    int16_t a, b, da, db, kd, pad0, pad1, pad2;
-};
-static_assert(sizeof(GroupRec) == 56, "GroupRec layout (engine.cu sizes the scratch by it)");
-
-__device__ __forceinline__ GroupRef ref_of(const GroupRec &r) {
-    GroupRef g;
-    g.R = r.R; g.a = r.a; g.b = r.b; g.da = r.da; g.db = r.db; g.rest_g = r.rest_g; g.rest_c = r.rest_c; g.kd = r.kd; g.own = r.own;
-    return g;
 }
 
 // S(N+1, s+x) - S(N, s) for a group of ONE observation (every group of a unary relation, most groups of a sparse one):
@@ -119,9 +94,12 @@ __device__ __forceinline__ double score_delta_unit(uint32_t N, uint32_t sv, uint
     return gn ? v : 0.0;
 }
 
-// Dynamic shared memory of one CTA: [rcap] group records, [rcap] touched accumulator bits, [pcap] partial sums.
-struct GenericLaunch { int32_t rcap, pcap; };
-__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap) { return (size_t)rcap * (sizeof(GroupRec) + 8) + (size_t)pcap * 8; }
+// Dynamic shared memory of one CTA: [rcap] group records, [rcap] touched accumulator cells, [pcap] partial sums,
+// [scap] accumulator cells + [scap / 32] bitmap words.
+struct GenericLaunch { int32_t rcap, pcap, scap; };
+__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap) {
+    return (size_t)rcap * (sizeof(GroupRec) + 4) + (size_t)pcap * 8 + (size_t)scap * 8 + (size_t)(scap / 32 + 1) * 4 + 16;
+}
 
 __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs args, const int32_t *blk_list, GenericLaunch GL) {
     const int k_list = blk_list ? blk_list[blockIdx.x] : blockIdx.x;
@@ -139,12 +117,16 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     __shared__ int32_t s_ncand, s_choice_slot, s_choice_label, s_fail;
     GroupRec *recs = reinterpret_cast<GroupRec *>(irm.gl_cell);     // [gl_cap] group records beyond the shared-memory ones (engine scratch)
     extern __shared__ __align__(16) unsigned char gen_dyn[];
+    const int RCAP = GL.rcap, PCAP = GL.pcap, SCAP = GL.scap;
     GroupRec *s_recs = reinterpret_cast<GroupRec *>(gen_dyn);                                  // [rcap]
-    long long *s_bits = reinterpret_cast<long long *>(gen_dyn + (size_t)GL.rcap * sizeof(GroupRec));   // [rcap]
-    double *s_part = reinterpret_cast<double *>(s_bits + GL.rcap);                              // [pcap]
-    const int RCAP = GL.rcap, PCAP = GL.pcap;
+    double *s_part = reinterpret_cast<double *>(s_recs + RCAP);                                 // [pcap]
+    cell_t *s_acc = reinterpret_cast<cell_t *>(s_part + PCAP);                                  // [scap]
+    int32_t *s_bits = reinterpret_cast<int32_t *>(s_acc + SCAP);                                // [rcap]
+    uint32_t *s_bm = reinterpret_cast<uint32_t *>(s_bits + RCAP);                               // [scap / 32 + 1]
 
     for (int k = tid; k < GEN_LF; k += NT) s_lf[k] = g_logfact[k];
+    for (int k = tid; k < SCAP; k += NT) s_acc[k] = 0;
+    for (int k = tid; k < SCAP / 32 + 1; k += NT) s_bm[k] = 0u;
     for (int dk = 0; dk < irm.n_domains; dk++) {
         const DomainDev &dq = irm.dom[dk];
         const int h = __ldcg(dq.hi);
@@ -192,8 +174,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         if (tid == 0) s_fail = 0;
         int32_t *s_cnt = s_cnt_all + d * GEN_MAXK, *s_lab = s_lab_all + d * GEN_MAXK;
         const int hi = s_hi_all[d];
+        const int ctot = irm.ctot[d];
+        const bool acc_shared = ctot <= SCAP;          // the move's accumulator: shared memory, or the IRM's global scratch
+        cell_t *acc = acc_shared ? s_acc : irm.gacc;
+        uint32_t *bm = acc_shared ? s_bm : irm.gbm;
+        const RelDom *rdesc = irm.rdesc + d;           // descriptor of relation r: rdesc[r * n_domains]
 
-        // ---- A: remove + group (fire-and-forget reductions; completed by the fence below) -----------
+        // ---- A: group (and, for twice-occurring domains, remove) -------------------------------------------------
         if (dd.ptr) {
             const int64_t beg = cur.beg, end = cur.end;
             for (int64_t q = beg + tid; q < end; q += NT) {
@@ -201,28 +188,31 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 const int rel = meta & META_REL_MASK;
                 const uint32_t val = (meta >> META_VAL_SHIFT) & 1u, selfmask = (meta >> META_SELF_SHIFT) & 0xFu;
                 const RelationDev *R = &irm.rel[rel];
-                int64_t gidx = 0, cidx = 0;
+                const RelDom *D = rdesc + (int64_t)rel * irm.n_domains;
+                const bool at_a = (selfmask >> D->a) & 1u, at_b = D->b >= 0 && ((selfmask >> D->b) & 1u);
+                const int pat = at_a ? (at_b ? 2 : 0) : 1;
+                int64_t cidx = 0;
+                int32_t rest_k = 0, dother = 0;
                 int oi = 0; bool first = true, absent = false;
                 for (int p = 0; p < R->arity; p++) {
-                    int slot, gd;
+                    int slot;
                     if ((selfmask >> p) & 1u) {
                         if (first) first = false; else oi++;
-                        slot = c; gd = dd.kcap;
+                        slot = c;
                     } else {
                         const int id = dd.other[(int64_t)oi * dd.nnz + q]; oi++;
                         slot = __ldcg(&irm.dom[R->dom[p]].z[id]);
                         if (slot < 0) { absent = true; slot = 0; }
-                        gd = slot;
+                        if (p == D->a || p == D->b) dother = slot; else rest_k += slot * D->rstride[p];
                     }
-                    gidx += gd * R->gstride[p];
                     cidx += slot * R->cstride[p];
                 }
                 if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); continue; }
                 const cell_t one = pack_cell(1u, val);
-                atomicAdd(&R->groups[gidx], one);
-                const int64_t bit = R->gbit0 + gidx;
-                atomicOr(&irm.gbitmap[bit >> 6], 1ull << (bit & 63));
-                atomicAdd(&R->counts[cidx], (cell_t)0 - one);
+                const int32_t cell = D->base[pat] + rest_k + (pat < 2 ? dother * D->rest_size : 0);
+                atomicAdd(&acc[cell], one);
+                atomicOr(&bm[cell >> 5], 1u << (cell & 31));
+                if (D->b >= 0) atomicAdd(&R->counts[cidx], (cell_t)0 - one);
             }
         }
         __threadfence();
@@ -266,12 +256,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             if (lane == 0) s_ncand = nc;
         }
 
-        // ---- B1: ordered list of the touched accumulator cells (bitmap scan: ascending bit = deterministic order) ----
+        // ---- B1: ordered list of the touched accumulator cells (bitmap scan: ascending cell = deterministic order) ----
         int64_t base = 0;
-        for (int64_t w0 = 0; w0 < irm.gwords; w0 += NT) {
-            const int64_t w = w0 + tid;
-            unsigned long long bits = w < irm.gwords ? __ldcg(&irm.gbitmap[w]) : 0ull;
-            const int cnt = __popcll(bits);
+        const int nwords = (ctot + 31) >> 5;
+        for (int w0 = 0; w0 < nwords; w0 += NT) {
+            const int w = w0 + tid;
+            uint32_t bits = w < nwords ? (acc_shared ? bm[w] : __ldcg(&bm[w])) : 0u;
+            const int cnt = __popc(bits);
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -290,11 +281,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             const int woff = __shfl_sync(0xffffffffu, wincl - wv, warp);
             int64_t off = base + woff + incl - cnt;
             while (bits) {
-                const int bpos = __ffsll((long long)bits) - 1;
+                const int bpos = __ffs((int)bits) - 1;
                 bits &= bits - 1;
                 if (off >= irm.gl_cap) raise_error(irm, KERR_GROUP_OVERFLOW);
-                else if (off < RCAP) s_bits[off] = w * 64 + bpos;
-                else recs[off].cellidx = w * 64 + bpos;
+                else if (off < RCAP) s_bits[off] = w * 32 + bpos;
+                else recs[off].cell = w * 32 + bpos;
                 off++;
             }
             base += total;
@@ -304,14 +295,25 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         GEN_PHASE(1);
         // ---- B2: decode every group once, one group per thread (for every candidate) ---------------------------------
         for (int64_t g = tid; g < ngroups; g += NT) {
-            const int64_t bit = g < RCAP ? s_bits[g] : recs[g].cellidx;
-            const int rel = irm.word_rel[bit >> 6];
-            const int64_t cellidx = bit - irm.rel[rel].gbit0;
-            const GroupRef gr = decode_group(irm, d, rel, cellidx);
+            const int32_t cell = g < RCAP ? s_bits[g] : recs[g].cell;
+            const int rel = irm.cmap[d][cell];
+            const RelationDev *R = &irm.rel[rel];
+            const RelDom *D = rdesc + (int64_t)rel * irm.n_domains;
             GroupRec rc;
-            rc.R = gr.R; rc.rest_g = gr.rest_g; rc.rest_c = gr.rest_c; rc.cellidx = cellidx; rc.own = gr.own;
-            rc.a = (int16_t)gr.a; rc.b = (int16_t)gr.b; rc.da = (int16_t)gr.da; rc.db = (int16_t)gr.db; rc.kd = (int16_t)gr.kd;
-            rc.pad0 = rc.pad1 = rc.pad2 = 0;
+            rc.R = R; rc.RD = D; rc.cell = cell;
+            rc.pat = (int16_t)(D->b >= 0 && cell >= D->base[2] ? 2 : D->b >= 0 && cell >= D->base[1] ? 1 : 0);
+            const int32_t local = cell - D->base[rc.pat];
+            rc.rest_k = local % D->rest_size;
+            rc.dother = (int16_t)(local / D->rest_size);
+            int64_t rest_c = 0;
+            for (int p = 0; p < R->arity; p++) {
+                if (p == D->a || p == D->b) continue;
+                const int digit = (rc.rest_k / D->rstride[p]) % irm.dom[R->dom[p]].kcap;
+                rest_c += digit * R->cstride[p];
+            }
+            rc.rest_c = rest_c;
+            rc.own = acc_shared ? acc[cell] : __ldcg(&acc[cell]);
+            rc.pad0 = rc.pad1 = 0;
             if (g < RCAP) s_recs[g] = rc; else recs[g] = rc;
         }
         __syncthreads();
@@ -320,57 +322,50 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
 
         // ---- D: score.  Work unit = (candidate, 32 consecutive groups), one warp each, lanes over the groups; the partial
         //      sums are added per candidate in chunk order afterwards (fixed order: deterministic) -------------------------
+        auto eval = [&](int64_t g, int slot_t, uint32_t &N, uint32_t &sv, uint32_t &gn, uint32_t &gs) {
+            N = 0u; sv = 0u; gn = 0u; gs = 0u;
+            if (g >= ngroups) return;
+            const GroupRec gr = g < RCAP ? s_recs[g] : recs[g];
+            cell_t delta; int64_t cidx;
+            if (!group_target(gr, acc, slot_t, delta, cidx)) return;
+            cell_t curc = __ldcg(&gr.R->counts[cidx]);
+            if (gr.RD->b < 0 && slot_t == c) curc -= gr.own;    // virtual removal: the entity's own observations leave its current cell
+            N = cell_n(curc); sv = cell_s(curc); gn = cell_n(delta); gs = cell_s(delta);
+        };
         const int nch = (int)((ngroups + 31) >> 5);
         const bool flat = (int64_t)ncand * nch <= PCAP;
         if (flat) {
             const int nunits = ncand * nch;
             for (int unit = warp; unit < nunits; unit += NW) {
                 const int t = unit / nch, ch = unit - t * nch;
-                const int slot_t = s_cslot[t];
-                const int64_t g = (int64_t)ch * 32 + lane;
-                uint32_t N = 0u, sv = 0u, gn = 0u, gs = 0u;
-                if (g < ngroups) {
-                    const GroupRef gr = ref_of(g < RCAP ? s_recs[g] : recs[g]);
-                    cell_t delta; int64_t cidx;
-                    if (group_target(gr, slot_t, delta, cidx)) {
-                        const cell_t cur = __ldcg(&gr.R->counts[cidx]);
-                        N = cell_n(cur); sv = cell_s(cur); gn = cell_n(delta); gs = cell_s(delta);
-                    }
-                }
+                uint32_t N, sv, gn, gs;
+                eval((int64_t)ch * 32 + lane, s_cslot[t], N, sv, gn, gs);
                 __syncwarp();
-                double acc = __all_sync(0xffffffffu, gn <= 1u) ? score_delta_unit(N, sv, gn, gs) : score_delta_bf<GEN_LF>(s_lf, N, sv, gn, gs);
+                double v = __all_sync(0xffffffffu, gn <= 1u) ? score_delta_unit(N, sv, gn, gs) : score_delta_bf<GEN_LF>(s_lf, N, sv, gn, gs);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) s_part[unit] = acc;
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) s_part[unit] = v;
             }
             __syncthreads();
             for (int t = tid; t < ncand; t += NT) {
-                double acc = 0.0;
-                for (int ch = 0; ch < nch; ch++) acc += s_part[t * nch + ch];
-                s_lp[t] += acc;
+                double a2 = 0.0;
+                for (int ch = 0; ch < nch; ch++) a2 += s_part[t * nch + ch];
+                s_lp[t] += a2;
             }
         } else {
             for (int t = warp; t < ncand; t += NW) {   // very many groups: one warp per candidate walks all of them
                 const int slot_t = s_cslot[t];
-                double acc = 0.0;
+                double a2 = 0.0;
                 for (int64_t g0 = 0; g0 < ngroups; g0 += 32) {
-                    const int64_t g = g0 + lane;
-                    uint32_t N = 0u, sv = 0u, gn = 0u, gs = 0u;
-                    if (g < ngroups) {
-                        const GroupRef gr = ref_of(g < RCAP ? s_recs[g] : recs[g]);
-                        cell_t delta; int64_t cidx;
-                        if (group_target(gr, slot_t, delta, cidx)) {
-                            const cell_t cur = __ldcg(&gr.R->counts[cidx]);
-                            N = cell_n(cur); sv = cell_s(cur); gn = cell_n(delta); gs = cell_s(delta);
-                        }
-                    }
+                    uint32_t N, sv, gn, gs;
+                    eval(g0 + lane, slot_t, N, sv, gn, gs);
                     __syncwarp();
                     double v = __all_sync(0xffffffffu, gn <= 1u) ? score_delta_unit(N, sv, gn, gs) : score_delta_bf<GEN_LF>(s_lf, N, sv, gn, gs);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    acc += v;
+                    a2 += v;
                 }
-                if (lane == 0) s_lp[t] += acc;
+                if (lane == 0) s_lp[t] += a2;
             }
         }
         __syncthreads();
@@ -417,14 +412,21 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         __syncthreads();
 
         GEN_PHASE(4);
-        // ---- F: apply ------------------------------------------------------------------
+        // ---- F: apply: groups of a once-occurring domain move only if the entity does; the others are put back ----------
         const int tnew = s_choice_slot;
         for (int64_t g = tid; g < ngroups; g += NT) {
-            const GroupRec rc = g < RCAP ? s_recs[g] : recs[g];
-            const GroupRef gr = ref_of(rc);
-            atomicAdd(&gr.R->counts[group_cell_at(gr, tnew)], gr.own);
-            __stcg(&gr.R->groups[rc.cellidx], (cell_t)0);
-            __stcg(&irm.gbitmap[(gr.R->gbit0 + rc.cellidx) >> 6], 0ull);
+            const GroupRec gr = g < RCAP ? s_recs[g] : recs[g];
+            if (gr.RD->b < 0) {
+                if (tnew != c) {
+                    const int64_t ca = gr.R->cstride[gr.RD->a];
+                    atomicAdd(&gr.R->counts[gr.rest_c + c * ca], (cell_t)0 - gr.own);
+                    atomicAdd(&gr.R->counts[gr.rest_c + tnew * ca], gr.own);
+                }
+            } else {
+                atomicAdd(&gr.R->counts[group_cell_at(gr, tnew)], gr.own);
+            }
+            if (acc_shared) { acc[gr.cell] = 0; bm[gr.cell >> 5] = 0u; }
+            else { __stcg(&acc[gr.cell], (cell_t)0); __stcg(&bm[gr.cell >> 5], 0u); }
         }
         if (tid == 0 && tnew != c) {
             __stcg(&dd.z[item], tnew);
