@@ -1063,6 +1063,7 @@ struct Plan {
     std::vector<int32_t> generic_blk, dense_blk;
     std::vector<DenseLaunch> tiers;   // dense: shared-memory tiers, smallest table first; the last one holds all max_tables slots
     int n_ent = 0, kcap = 0;
+    int gen_kmax = 0, gen_ndom = 0, gen_nother = 0;   // generic kernel: largest max_tables / domain count / other-id columns of its IRMs
 };
 
 // Shared-memory plan of one dense tier: as many chains per SM as the launch has (up to 5: the register budget) and fit; the rest of
@@ -1131,6 +1132,9 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
         } else {
             for (auto &R : irm->obs->rel)
                 if (R.kind == 1) return fail("no kernel for this irm: dense slabs are supported for a single R(e,e) relation only");
+            for (int32_t kc : irm->kcap) plan.gen_kmax = std::max(plan.gen_kmax, (int)kc);
+            plan.gen_ndom = std::max(plan.gen_ndom, irm->n_domains);
+            for (auto &D : irm->obs->dom) plan.gen_nother = std::max(plan.gen_nother, D.n_other);
             plan.generic_blk.push_back(k);
         }
     }
@@ -1161,7 +1165,6 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
     e->last_launches = 0; e->last_kind = -1;
     CK(cudaEventRecord(e->ev0, e->stream));
     if (!plan.generic_blk.empty()) {
-        // few IRMs: 256 threads each (shortest move); many: 128 threads, 8 CTAs per SM hide one another's memory latency
         // at most one IRM per SM: 1024 threads each (shortest move: every phase of a move is spread over the whole SM);
         // up to 4 per SM: 256 threads; many: 128 threads, 8 CTAs per SM hide one another's memory latency
         const int n_gen = (int)plan.generic_blk.size();
@@ -1169,8 +1172,11 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         if (const char *s = getenv("HIRM_GENERIC_THREADS")) gen_threads = std::max(64, std::min(1024, atoi(s) & ~31));
         GenericLaunch GL;
         GL.rcap = gen_threads; GL.pcap = 4 * gen_threads; GL.scap = 4 * gen_threads;
-        const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap);
-        CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)generic_smem_bytes(1024, 4096, 4096)));
+        GL.kstride = (std::max(plan.gen_kmax, 2) + 2) & ~1;
+        GL.ndom = std::max(plan.gen_ndom, 1); GL.roww = 1 + std::max(plan.gen_nother, 1);
+        const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww);
+        if (gen_smem > (size_t)e->max_smem_optin) return fail("generic kernel: shared-memory plan exceeds the device limit");
+        CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem));
         generic_sweep_kernel<<<(unsigned)n_gen, gen_threads, gen_smem, e->stream>>>(args, e->s_blk.p, GL);
         CK(cudaGetLastError());
         e->last_launches++; e->last_kind = 0;

@@ -96,9 +96,15 @@ __device__ __forceinline__ double score_delta_unit(uint32_t N, uint32_t sv, uint
 
 // Dynamic shared memory of one CTA: [rcap] group records, [rcap] touched accumulator cells, [pcap] partial sums,
 // [scap] accumulator cells + [scap / 32] bitmap words.
-struct GenericLaunch { int32_t rcap, pcap, scap; };
+struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww; };   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids)
 __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap) {
     return (size_t)rcap * (sizeof(GroupRec) + 4) + (size_t)pcap * 8 + (size_t)scap * 8 + (size_t)(scap / 32 + 1) * 4 + 16;
+}
+// + [2][roww][threads] words: the first `threads` entries of the next move's CSR row (meta + other ids), copied
+// asynchronously one move ahead
+// + [ndom][kstride] (double + 2 int32): resident CRP state of every domain
+__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int threads, int kstride, int ndom, int roww) {
+    return generic_smem_bytes(rcap, pcap, scap) + (size_t)2 * roww * threads * 4 + 8 + (size_t)ndom * kstride * 16;
 }
 
 __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs args, const int32_t *blk_list, GenericLaunch GL) {
@@ -109,20 +115,28 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
 
     // CRP state of every domain (table sizes, labels, highest used slot + 1), resident for the whole move list: only
     // this CTA changes it (phase F writes shared and global copies alike)
-    __shared__ int32_t s_cnt_all[MAX_DOMAINS * GEN_MAXK], s_lab_all[MAX_DOMAINS * GEN_MAXK], s_hi_all[MAX_DOMAINS];
+    __shared__ int32_t s_hi_all[MAX_DOMAINS];     // (table sizes / labels / log sizes: dynamic shared memory, [n_domains][kstride])
     __shared__ int32_t s_cslot[GEN_MAXK + 1], s_clabel[GEN_MAXK + 1], u_slot[GEN_MAXK + 1], u_label[GEN_MAXK + 1];
     __shared__ double s_lp[GEN_MAXK + 1], s_tmp[GEN_MAXK + 1];
     __shared__ double s_lf[GEN_LF];
     __shared__ int32_t s_warp_tot[GEN_WARPS];
     __shared__ int32_t s_ncand, s_choice_slot, s_choice_label, s_fail;
+    __shared__ double s_logalpha[MAX_DOMAINS], s_u;   // log(alpha); the move's uniform
     GroupRec *recs = reinterpret_cast<GroupRec *>(irm.gl_cell);     // [gl_cap] group records beyond the shared-memory ones (engine scratch)
     extern __shared__ __align__(16) unsigned char gen_dyn[];
     const int RCAP = GL.rcap, PCAP = GL.pcap, SCAP = GL.scap;
+    const int64_t glcap = irm.gl_cap;
     GroupRec *s_recs = reinterpret_cast<GroupRec *>(gen_dyn);                                  // [rcap]
     double *s_part = reinterpret_cast<double *>(s_recs + RCAP);                                 // [pcap]
     cell_t *s_acc = reinterpret_cast<cell_t *>(s_part + PCAP);                                  // [scap]
     int32_t *s_bits = reinterpret_cast<int32_t *>(s_acc + SCAP);                                // [rcap]
     uint32_t *s_bm = reinterpret_cast<uint32_t *>(s_bits + RCAP);                               // [scap / 32 + 1]
+    uint32_t *s_row = s_bm + (SCAP / 32 + 1);                                                   // [2][roww][NT] next / current CSR row heads
+    const int KS = GL.kstride;
+    const int ROWW = GL.roww;
+    double *s_logcnt_all = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_row + 2 * ROWW * NT) + 7) & ~(uintptr_t)7);   // [ndom][KS] log(table size)
+    int32_t *s_cnt_all = reinterpret_cast<int32_t *>(s_logcnt_all + GL.ndom * KS);               // [ndom][KS]
+    int32_t *s_lab_all = s_cnt_all + GL.ndom * KS;
 
     for (int k = tid; k < GEN_LF; k += NT) s_lf[k] = g_logfact[k];
     for (int k = tid; k < SCAP; k += NT) s_acc[k] = 0;
@@ -131,26 +145,53 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         const DomainDev &dq = irm.dom[dk];
         const int h = __ldcg(dq.hi);
         if (tid == 0) s_hi_all[dk] = h;
-        for (int k = tid; k < h; k += NT) { s_cnt_all[dk * GEN_MAXK + k] = __ldcg(&dq.tab_count[k]); s_lab_all[dk * GEN_MAXK + k] = __ldcg(&dq.tab_label[k]); }
+        for (int k = tid; k < h; k += NT) {
+            const int cv = __ldcg(&dq.tab_count[k]);
+            s_cnt_all[dk * KS + k] = cv; s_lab_all[dk * KS + k] = __ldcg(&dq.tab_label[k]);
+            s_logcnt_all[dk * KS + k] = log((double)max(cv, 1));
+        }
+        if (tid == 0) s_logalpha[dk] = log(dq.alpha);
     }
     __syncthreads();
+    const int NA = NT > 32 ? NT - 32 : NT;        // threads streaming CSR rows (phase A); the last warp prepares the candidates meanwhile
+    const int cwarp = NT > 32 ? NW - 1 : 0;
 
     // A move's inputs that do not depend on the move before it (ids, CSR row bounds) and the one that almost never does
     // (the entity's own slot) are fetched one move ahead: their L2 round trips overlap the current move.
     struct Pref { int d, item, c; int64_t beg, end; };
     const int64_t m0 = args.move_off[k_list], m1 = args.move_off[k_list + 1];
-    auto fetch = [&](int64_t mm) {
-        Pref f; f.d = -1; f.item = -1; f.c = -1; f.beg = 0; f.end = 0;
-        if (mm >= m1) return f;
-        f.d = args.move_dom[mm]; f.item = args.move_item[mm];
-        if (f.d < 0 || f.d >= irm.n_domains || f.item < 0 || f.item >= irm.dom[f.d].n) { f.d = -1; return f; }
+    struct Ids { int d, item; };
+    auto fetch_ids = [&](int64_t mm) {            // stage 1: the move's ids (three moves ahead: nothing branches on them yet)
+        Ids q; q.d = -1; q.item = -1;
+        if (mm < m1) { q.d = args.move_dom[mm]; q.item = args.move_item[mm]; }
+        return q;
+    };
+    auto fetch = [&](const Ids &q) {              // stage 2: the entity's slot and CSR row bounds (two moves ahead)
+        Pref f; f.d = q.d; f.item = q.item; f.c = -1; f.beg = 0; f.end = 0;
+        if (f.d < 0) return f;
+        if (f.d >= irm.n_domains || f.item < 0 || f.item >= irm.dom[f.d].n) { f.d = -1; return f; }
         const DomainDev &dq = irm.dom[f.d];
         f.c = __ldcg(&dq.z[f.item]);
         if (dq.ptr) { f.beg = dq.ptr[f.item]; f.end = dq.ptr[f.item + 1]; }
         return f;
     };
 
-    Pref nxt = fetch(m0);
+    // asynchronous copy of the head of a CSR row (entry q = beg + tid: meta word and other-entity ids) into row buffer `buf`
+    auto prefetch_row = [&](const Pref &f, int buf) {
+        if (f.d < 0 || tid >= NA) return;
+        const DomainDev &dq = irm.dom[f.d];
+        const int64_t q = f.beg + tid;
+        if (!dq.ptr || q >= f.end) return;
+        uint32_t *dst = s_row + ((size_t)buf * ROWW) * NT + tid;
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(dq.meta + q) : "memory");
+        for (int oi = 0; oi < dq.n_other && oi < ROWW - 1; oi++)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + (uint32_t)((oi + 1) * NT * 4)), "l"(dq.other + (int64_t)oi * dq.nnz + q) : "memory");
+    };
+    Pref nxt = fetch(fetch_ids(m0)), nxt2 = fetch(fetch_ids(m0 + 1));
+    Ids ids3 = fetch_ids(m0 + 2);
+    prefetch_row(nxt, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // debug hook (hirm_engine_debug_phase_cycles): thread 0's SM cycles per phase, summed over the moves:
     // [0] A  [1] B1 (+C)  [2] B2  [3] D  [4] E  [5] F  -- 32 slots per block, shared with the dense kernel's layout
     const bool prof = args.phase_cycles != nullptr && tid == 0;
@@ -158,7 +199,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
 #define GEN_PHASE(i) do { if (prof) { const long long now = clock64(); ph_acc[i] += now - ph_t; ph_t = now; } } while (0)
     for (int64_t m = m0; m < m1; m++) {
         const Pref cur = nxt;
-        nxt = fetch(m + 1);
+        nxt = nxt2;
+        nxt2 = fetch(ids3);
+        ids3 = fetch_ids(m + 3);
+        const int rbuf = (int)((m - m0) & 1);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // this move's row head (own element: no barrier needed)
+        prefetch_row(nxt, rbuf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         const bool bad = cur.d < 0;
         const int d = bad ? 0 : cur.d, item = cur.item;
         const DomainDev &dd = irm.dom[d];
@@ -171,8 +218,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             }
             continue;
         }
-        if (tid == 0) s_fail = 0;
-        int32_t *s_cnt = s_cnt_all + d * GEN_MAXK, *s_lab = s_lab_all + d * GEN_MAXK;
+        int32_t *s_cnt = s_cnt_all + d * KS, *s_lab = s_lab_all + d * KS;
         const int hi = s_hi_all[d];
         const int ctot = irm.ctot[d];
         const bool acc_shared = ctot <= SCAP;          // the move's accumulator: shared memory, or the IRM's global scratch
@@ -180,47 +226,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         uint32_t *bm = acc_shared ? s_bm : irm.gbm;
         const RelDom *rdesc = irm.rdesc + d;           // descriptor of relation r: rdesc[r * n_domains]
 
-        // ---- A: group (and, for twice-occurring domains, remove) -------------------------------------------------
-        if (dd.ptr) {
-            const int64_t beg = cur.beg, end = cur.end;
-            for (int64_t q = beg + tid; q < end; q += NT) {
-                const uint32_t meta = dd.meta[q];
-                const int rel = meta & META_REL_MASK;
-                const uint32_t val = (meta >> META_VAL_SHIFT) & 1u, selfmask = (meta >> META_SELF_SHIFT) & 0xFu;
-                const RelationDev *R = &irm.rel[rel];
-                const RelDom *D = rdesc + (int64_t)rel * irm.n_domains;
-                const bool at_a = (selfmask >> D->a) & 1u, at_b = D->b >= 0 && ((selfmask >> D->b) & 1u);
-                const int pat = at_a ? (at_b ? 2 : 0) : 1;
-                int64_t cidx = 0;
-                int32_t rest_k = 0, dother = 0;
-                int oi = 0; bool first = true, absent = false;
-                for (int p = 0; p < R->arity; p++) {
-                    int slot;
-                    if ((selfmask >> p) & 1u) {
-                        if (first) first = false; else oi++;
-                        slot = c;
-                    } else {
-                        const int id = dd.other[(int64_t)oi * dd.nnz + q]; oi++;
-                        slot = __ldcg(&irm.dom[R->dom[p]].z[id]);
-                        if (slot < 0) { absent = true; slot = 0; }
-                        if (p == D->a || p == D->b) dother = slot; else rest_k += slot * D->rstride[p];
-                    }
-                    cidx += slot * R->cstride[p];
-                }
-                if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); continue; }
-                const cell_t one = pack_cell(1u, val);
-                const int32_t cell = D->base[pat] + rest_k + (pat < 2 ? dother * D->rest_size : 0);
-                atomicAdd(&acc[cell], one);
-                atomicOr(&bm[cell >> 5], 1u << (cell & 31));
-                if (D->b >= 0) atomicAdd(&R->counts[cidx], (cell_t)0 - one);
-            }
-        }
-        __threadfence();
-        __syncthreads();
-        GEN_PHASE(0);
-
-        // ---- C: candidates, CRP::tables_weights_gibbs (cxx/hirm.hh:147-161): warp 0, lanes over the tables ----
-        if (warp == 0) {
+        // ---- C: candidates, CRP::tables_weights_gibbs (cxx/hirm.hh:147-161): the last warp, while the others stream the row ----
+        if (warp == cwarp) {
+            if (lane == 0) s_fail = 0;
+            __syncwarp();
+            const double *s_logcnt = s_logcnt_all + d * KS;
             int maxlab = 0, freeslot = 1 << 30;        // t_max starts at 0 (cxx/hirm.hh:139)
             for (int k = lane; k < hi; k += 32) {
                 if (s_cnt[k] > 0) maxlab = max(maxlab, s_lab[k]); else freeslot = min(freeslot, k);
@@ -229,14 +239,15 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             freeslot = __reduce_min_sync(0xffffffffu, freeslot);
             if (freeslot == (1 << 30)) freeslot = hi < dd.kcap ? hi : -1;
             const bool singleton = s_cnt[c] == 1;
-            const double logalpha = log(dd.alpha);
+            const double logalpha = s_logalpha[d];
             int ncount = 0;
             for (int base = 0; base < hi; base += 32) {
                 const int k = base + lane;
                 const int cnt = k < hi ? s_cnt[k] - (k == c ? 1 : 0) : 0;
                 const unsigned bal = __ballot_sync(0xffffffffu, cnt > 0);
                 const int pos = ncount + __popc(bal & ((1u << lane) - 1u));
-                const double lw = log((double)max(cnt, 1));
+                double lw = k < hi ? s_logcnt[k] : 0.0;
+                if (k == c) lw = log((double)max(cnt, 1));      // the entity's own table counts without it
                 if (cnt > 0) { u_slot[pos] = k; u_label[pos] = s_lab[k]; s_tmp[pos] = lw; }
                 ncount += __popc(bal);
             }
@@ -253,8 +264,54 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 for (int i = 0; i < nc; i++) rank += u_label[i] < lb;
                 s_cslot[rank] = u_slot[j]; s_clabel[rank] = lb; s_lp[rank] = s_tmp[j];
             }
-            if (lane == 0) s_ncand = nc;
+            if (lane == 0) {
+                s_ncand = nc;
+                s_u = args.uniforms ? args.uniforms[m] : philox_uniform(args.seed, args.stream[k_list], args.counter0[k_list] + (uint64_t)(m - m0));
+            }
         }
+
+        // ---- A: group (and, for twice-occurring domains, remove) -------------------------------------------------
+        if (dd.ptr && tid < NA) {
+            const int64_t beg = cur.beg, end = cur.end;
+            const uint32_t *rowbuf = s_row + ((size_t)rbuf * ROWW) * NT + tid;
+            for (int64_t q = beg + tid; q < end; q += NA) {
+                const bool head = q < beg + NA;                   // prefetched into shared memory one move ahead
+                const uint32_t meta = head ? rowbuf[0] : dd.meta[q];
+                const int rel = meta & META_REL_MASK;
+                const uint32_t val = (meta >> META_VAL_SHIFT) & 1u, selfmask = (meta >> META_SELF_SHIFT) & 0xFu;
+                const RelationDev *R = &irm.rel[rel];
+                const RelDom *D = rdesc + (int64_t)rel * irm.n_domains;
+                const bool at_a = (selfmask >> D->a) & 1u, at_b = D->b >= 0 && ((selfmask >> D->b) & 1u);
+                const int pat = at_a ? (at_b ? 2 : 0) : 1;
+                int64_t cidx = 0;
+                int32_t rest_k = 0, dother = 0;
+                int oi = 0; bool first = true, absent = false;
+                for (int p = 0; p < R->arity; p++) {
+                    int slot;
+                    if ((selfmask >> p) & 1u) {
+                        if (first) first = false; else oi++;
+                        slot = c;
+                    } else {
+                        const int id = head ? (int)rowbuf[(oi + 1) * NT] : dd.other[(int64_t)oi * dd.nnz + q]; oi++;
+                        slot = __ldcg(&irm.dom[R->dom[p]].z[id]);
+                        if (slot < 0) { absent = true; slot = 0; }
+                        if (p == D->a || p == D->b) dother = slot; else rest_k += slot * D->rstride[p];
+                    }
+                    cidx += slot * R->cstride[p];
+                }
+                if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); continue; }
+                const cell_t one = pack_cell(1u, val);
+                const int32_t cell = D->base[pat] + rest_k + (pat < 2 ? dother * D->rest_size : 0);
+                atomicAdd(&acc[cell], one);
+                atomicOr(&bm[cell >> 5], 1u << (cell & 31));
+                if (D->b >= 0) atomicAdd(&R->counts[cidx], (cell_t)0 - one);
+            }
+        }
+        // One CTA owns the IRM: __syncthreads() alone makes the block's global atomics and stores visible to the block
+        // (they are performed at L2, and every mutable word is read back with ld.cg).  No __threadfence(): a gpu-scope
+        // fence would also invalidate L1 and send every descriptor load of the next phase back to L2.
+        __syncthreads();
+        GEN_PHASE(0);
 
         // ---- B1: ordered list of the touched accumulator cells (bitmap scan: ascending cell = deterministic order) ----
         int64_t base = 0;
@@ -279,19 +336,25 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             }
             const int total = __shfl_sync(0xffffffffu, wincl, 31);
             const int woff = __shfl_sync(0xffffffffu, wincl - wv, warp);
-            int64_t off = base + woff + incl - cnt;
-            while (bits) {
-                const int bpos = __ffs((int)bits) - 1;
-                bits &= bits - 1;
-                if (off >= irm.gl_cap) raise_error(irm, KERR_GROUP_OVERFLOW);
-                else if (off < RCAP) s_bits[off] = w * 32 + bpos;
-                else recs[off].cell = w * 32 + bpos;
-                off++;
+            const int off = (int)base + woff + incl - cnt;   // list position of this thread's word
+            // the warp walks its 32 words together, lanes = bit positions: cost follows the non-empty words, not the
+            // bits of the fullest one (a run of unary relations sets every bit of a word)
+            for (uint32_t nz = __ballot_sync(0xffffffffu, bits != 0u); nz; nz &= nz - 1u) {
+                const int j = __ffs((int)nz) - 1;
+                const uint32_t bj = __shfl_sync(0xffffffffu, bits, j);
+                const int oj = __shfl_sync(0xffffffffu, off, j);
+                if ((bj >> lane) & 1u) {
+                    const int pos = oj + __popc(bj & ((1u << lane) - 1u));
+                    const int cellv = (w0 + warp * 32 + j) * 32 + lane;
+                    if (pos >= glcap) raise_error(irm, KERR_GROUP_OVERFLOW);
+                    else if (pos < RCAP) s_bits[pos] = cellv;
+                    else recs[pos].cell = cellv;
+                }
             }
             base += total;
             __syncthreads();
         }
-        const int64_t ngroups = base < irm.gl_cap ? base : irm.gl_cap;
+        const int64_t ngroups = base < glcap ? base : glcap;
         GEN_PHASE(1);
         // ---- B2: decode every group once, one group per thread (for every candidate) ---------------------------------
         for (int64_t g = tid; g < ngroups; g += NT) {
@@ -385,8 +448,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 for (int t = lane; t < ncand; t += 32) s_tmp[t] = exp(s_lp[t] - mx);
                 __syncwarp();
                 if (lane == 0) {
-                    const double u = args.uniforms ? args.uniforms[m]
-                                                   : philox_uniform(args.seed, args.stream[k_list], args.counter0[k_list] + (uint64_t)(m - m0));
+                    const double u = s_u;
                     double total = 0.0;
                     for (int t = 0; t < ncand; t++) total += s_tmp[t];
                     const double x = u * total;
@@ -440,9 +502,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             }
             __stcg(dd.hi, nhi);
             s_cnt[c] -= 1; s_cnt[tnew] = newcnt; s_hi_all[d] = nhi;      // the resident copies
+            s_logcnt_all[d * KS + c] = log((double)max(s_cnt[c], 1));
+            s_logcnt_all[d * KS + tnew] = log((double)newcnt);
         }
         if (tnew != c && nxt.d == d && nxt.item == item) nxt.c = tnew;    // the same entity again: its prefetched slot is stale
-        __threadfence();
+        if (tnew != c && nxt2.d == d && nxt2.item == item) nxt2.c = tnew;
         __syncthreads();
         GEN_PHASE(5);
     }
