@@ -156,41 +156,60 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     const int NA = NT > 32 ? NT - 32 : NT;        // threads streaming CSR rows (phase A); the last warp prepares the candidates meanwhile
     const int cwarp = NT > 32 ? NW - 1 : 0;
 
-    // A move's inputs that do not depend on the move before it (ids, CSR row bounds) and the one that almost never does
-    // (the entity's own slot) are fetched one move ahead: their L2 round trips overlap the current move.
-    struct Pref { int d, item, c; int64_t beg, end; };
+    // A move's inputs are fetched ahead of it with asynchronous copies into a 4-deep shared-memory ring, by thread 0 and
+    // at no register cost: the ids three moves ahead, the CSR row bounds two moves ahead, the entity's slot and the head of
+    // the row (every thread its own entry) one move ahead.  Thread 0 waits for its copies at the end of each move,
+    // before the closing barrier, so everything issued during move m is visible to the block from move m + 1 on.
+    __shared__ int32_t s_pd[4], s_pi[4], s_pc[4];
+    __shared__ long long s_pb[4][2];
     const int64_t m0 = args.move_off[k_list], m1 = args.move_off[k_list + 1];
-    struct Ids { int d, item; };
-    auto fetch_ids = [&](int64_t mm) {            // stage 1: the move's ids (three moves ahead: nothing branches on them yet)
-        Ids q; q.d = -1; q.item = -1;
-        if (mm < m1) { q.d = args.move_dom[mm]; q.item = args.move_item[mm]; }
-        return q;
+    auto cp4 = [](void *dst, const void *src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
     };
-    auto fetch = [&](const Ids &q) {              // stage 2: the entity's slot and CSR row bounds (two moves ahead)
-        Pref f; f.d = q.d; f.item = q.item; f.c = -1; f.beg = 0; f.end = 0;
-        if (f.d < 0) return f;
-        if (f.d >= irm.n_domains || f.item < 0 || f.item >= irm.dom[f.d].n) { f.d = -1; return f; }
-        const DomainDev &dq = irm.dom[f.d];
-        f.c = __ldcg(&dq.z[f.item]);
-        if (dq.ptr) { f.beg = dq.ptr[f.item]; f.end = dq.ptr[f.item + 1]; }
-        return f;
+    auto cp8 = [](void *dst, const void *src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
     };
-
-    // asynchronous copy of the head of a CSR row (entry q = beg + tid: meta word and other-entity ids) into row buffer `buf`
-    auto prefetch_row = [&](const Pref &f, int buf) {
-        if (f.d < 0 || tid >= NA) return;
-        const DomainDev &dq = irm.dom[f.d];
-        const int64_t q = f.beg + tid;
-        if (!dq.ptr || q >= f.end) return;
+    auto issue_ids = [&](int64_t mm) {            // thread 0
+        const int k = (int)((mm - m0) & 3);
+        if (mm < m1) { cp4(&s_pd[k], args.move_dom + mm); cp4(&s_pi[k], args.move_item + mm); }
+        else s_pd[k] = -1;
+    };
+    auto issue_state = [&](int64_t mm) {          // thread 0; the ids of move mm are in the ring
+        const int k = (int)((mm - m0) & 3);
+        const int dm = s_pd[k], it = s_pi[k];
+        if (mm >= m1 || dm < 0 || dm >= irm.n_domains || it < 0 || it >= irm.dom[dm].n) { s_pd[k] = -1; s_pc[k] = -1; s_pb[k][0] = 0; s_pb[k][1] = 0; return; }
+        const DomainDev &dq = irm.dom[dm];
+        if (dq.ptr) { cp8(&s_pb[k][0], dq.ptr + it); cp8(&s_pb[k][1], dq.ptr + it + 1); }
+        else { s_pb[k][0] = 0; s_pb[k][1] = 0; }
+    };
+    // the entity's current slot is mutable state: read with ld.cg (L2) one move ahead, by one lane of the candidate warp,
+    // and patched at the end of the move if that move re-seats the very same entity
+    auto load_slot = [&](int64_t mm) {
+        const int k = (int)((mm - m0) & 3);
+        const int dm = s_pd[k];
+        if (mm < m1 && dm >= 0) s_pc[k] = __ldcg(&irm.dom[dm].z[s_pi[k]]);
+    };
+    // asynchronous copy of the head of move mm's CSR row (entry q = beg + tid: meta word and other-entity ids) into row buffer `buf`
+    auto prefetch_row = [&](int64_t mm, int buf) {
+        const int k = (int)((mm - m0) & 3);
+        const int dm = s_pd[k];
+        if (mm >= m1 || dm < 0 || tid >= NA) return;
+        const DomainDev &dq = irm.dom[dm];
+        const int64_t q = s_pb[k][0] + tid;
+        if (!dq.ptr || q >= s_pb[k][1]) return;
         uint32_t *dst = s_row + ((size_t)buf * ROWW) * NT + tid;
-        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(dq.meta + q) : "memory");
-        for (int oi = 0; oi < dq.n_other && oi < ROWW - 1; oi++)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + (uint32_t)((oi + 1) * NT * 4)), "l"(dq.other + (int64_t)oi * dq.nnz + q) : "memory");
+        cp4(dst, dq.meta + q);
+        for (int oi = 0; oi < dq.n_other && oi < ROWW - 1; oi++) cp4(dst + (oi + 1) * NT, dq.other + (int64_t)oi * dq.nnz + q);
     };
-    Pref nxt = fetch(fetch_ids(m0)), nxt2 = fetch(fetch_ids(m0 + 1));
-    Ids ids3 = fetch_ids(m0 + 2);
-    prefetch_row(nxt, 0);
+    if (tid == 0) {
+        issue_ids(m0); issue_ids(m0 + 1); issue_ids(m0 + 2);
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        issue_state(m0); issue_state(m0 + 1);
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        load_slot(m0);
+    }
+    __syncthreads();
+    prefetch_row(m0, 0);
     asm volatile("cp.async.commit_group;" ::: "memory");
     // debug hook (hirm_engine_debug_phase_cycles): thread 0's SM cycles per phase, summed over the moves:
     // [0] A  [1] B1 (+C)  [2] B2  [3] D  [4] E  [5] F  -- 32 slots per block, shared with the dense kernel's layout
@@ -198,13 +217,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     long long ph_t = prof ? clock64() : 0, ph_acc[6] = {0, 0, 0, 0, 0, 0};
 #define GEN_PHASE(i) do { if (prof) { const long long now = clock64(); ph_acc[i] += now - ph_t; ph_t = now; } } while (0)
     for (int64_t m = m0; m < m1; m++) {
-        const Pref cur = nxt;
-        nxt = nxt2;
-        nxt2 = fetch(ids3);
-        ids3 = fetch_ids(m + 3);
+        const int ring = (int)((m - m0) & 3);
+        struct { int d, item, c; int64_t beg, end; } cur;
+        cur.d = s_pd[ring]; cur.item = s_pi[ring]; cur.c = s_pc[ring]; cur.beg = s_pb[ring][0]; cur.end = s_pb[ring][1];
         const int rbuf = (int)((m - m0) & 1);
         asm volatile("cp.async.wait_group 0;" ::: "memory");      // this move's row head (own element: no barrier needed)
-        prefetch_row(nxt, rbuf ^ 1);
+        prefetch_row(m + 1, rbuf ^ 1);
+        if (tid == 0) { issue_ids(m + 3); issue_state(m + 2); }
         asm volatile("cp.async.commit_group;" ::: "memory");
         const bool bad = cur.d < 0;
         const int d = bad ? 0 : cur.d, item = cur.item;
@@ -215,7 +234,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 raise_error(irm, KERR_BAD_MOVE);
                 if (args.out_choice) args.out_choice[m] = -1;
                 if (args.trace_cap > 0) args.trace_n[m] = 0;
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                load_slot(m + 1);
             }
+            __syncthreads();
             continue;
         }
         int32_t *s_cnt = s_cnt_all + d * KS, *s_lab = s_lab_all + d * KS;
@@ -228,7 +250,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
 
         // ---- C: candidates, CRP::tables_weights_gibbs (cxx/hirm.hh:147-161): the last warp, while the others stream the row ----
         if (warp == cwarp) {
-            if (lane == 0) s_fail = 0;
+            if (lane == 0) { s_fail = 0; load_slot(m + 1); }
             __syncwarp();
             const double *s_logcnt = s_logcnt_all + d * KS;
             int maxlab = 0, freeslot = 1 << 30;        // t_max starts at 0 (cxx/hirm.hh:139)
@@ -505,8 +527,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             s_logcnt_all[d * KS + c] = log((double)max(s_cnt[c], 1));
             s_logcnt_all[d * KS + tnew] = log((double)newcnt);
         }
-        if (tnew != c && nxt.d == d && nxt.item == item) nxt.c = tnew;    // the same entity again: its prefetched slot is stale
-        if (tnew != c && nxt2.d == d && nxt2.item == item) nxt2.c = tnew;
+        if (tid == 0) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const int k1 = (ring + 1) & 3;             // the same entity again: its prefetched slot is stale
+            if (tnew != c && s_pd[k1] == d && s_pi[k1] == item) s_pc[k1] = tnew;
+        }
         __syncthreads();
         GEN_PHASE(5);
     }
