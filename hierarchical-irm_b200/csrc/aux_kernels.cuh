@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(AUX_THREADS) rel_score_kernel(const RelCand *c
 // per domain.  Work item = (relation, run of candidates, run of observations): the COO run is read once for the
 // whole run of candidates; histograms live in shared memory when (candidates x cells) fits, and are flushed to the
 // global scratch tables with integer atomics (exact, order-free).  Pass 2 sums the cell scores with a fixed tree.
-constexpr int RM_SH_CELLS = 4096;       // shared-memory histogram cells per work item (2 x uint32 each)
+constexpr int RM_SH_CELLS = 4096;       // shared-memory histogram cells per work item (2 x uint32 each) when every table is small
+constexpr int RM_SH_CELLS_BIG = 24576;  // ... when some table needs more (192 KB of shared memory, one CTA per SM)
 struct RelDesc {
     const int32_t *ids; const uint8_t *val; int64_t nobs;
     int32_t arity; int32_t dom[MAX_ARITY];
@@ -152,12 +153,13 @@ struct ScoreWork {
     int64_t table0;                     // scratch offset of (rel, cand0); candidate c of the run sits at table0 + c * ncells
 };
 __global__ void __launch_bounds__(AUX_THREADS) relmat_hist_kernel(const RelDesc *rels, const PartSet *parts, const ScoreWork *work,
-                                                                  cell_t *tables, int32_t *error) {
+                                                                  cell_t *tables, int32_t *error, int sh_cells) {
     const ScoreWork W = work[blockIdx.x];
     const RelDesc R = rels[W.rel];
-    __shared__ uint32_t sh_n[RM_SH_CELLS], sh_s[RM_SH_CELLS];
+    extern __shared__ uint32_t rm_dyn[];
+    uint32_t *sh_n = rm_dyn, *sh_s = rm_dyn + sh_cells;
     const int64_t run_cells = R.ncells * W.ncand;
-    const bool use_sh = run_cells <= RM_SH_CELLS;
+    const bool use_sh = run_cells <= sh_cells;
     if (use_sh) {
         for (int i = threadIdx.x; i < run_cells; i += blockDim.x) { sh_n[i] = 0u; sh_s[i] = 0u; }
         __syncthreads();

@@ -824,6 +824,7 @@ extern "C" int hirm_engine_relation_scores(hirm_engine *e, int32_t src, int rel,
 // ---- batched relation scores (K4, aux_kernels.cuh) ------------------------------------------------------------------
 namespace {
 struct ScoreJob {
+    int sh_cells = RM_SH_CELLS;        // shared-memory histogram cells per work item of this launch
     std::vector<RelDesc> rels; std::vector<PartSet> parts; std::vector<ScoreWork> work; std::vector<TableRef> refs;
     std::vector<int64_t> table0;       // scratch offset of relation r's first table
     int64_t total_cells = 0;
@@ -870,8 +871,10 @@ static int run_score_job(hirm_engine *e, ScoreJob &J, double *h_out) {
     if (job_upload(e, e->s_job[0], J.rels) || job_upload(e, e->s_job[1], J.parts) || job_upload(e, e->s_job[2], J.work) ||
         job_upload(e, e->s_job[3], J.refs)) return -1;
     if (!J.work.empty()) {
-        relmat_hist_kernel<<<(unsigned)J.work.size(), AUX_THREADS, 0, s0>>>((const RelDesc *)e->s_job[0].p, (const PartSet *)e->s_job[1].p,
-                                                                           (const ScoreWork *)e->s_job[2].p, e->s_reltab.p, e->s_relerr.p);
+        const size_t sh_bytes = (size_t)J.sh_cells * 2 * sizeof(uint32_t);
+        CK(cudaFuncSetAttribute(relmat_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)RM_SH_CELLS_BIG * 2 * sizeof(uint32_t))));
+        relmat_hist_kernel<<<(unsigned)J.work.size(), AUX_THREADS, sh_bytes, s0>>>((const RelDesc *)e->s_job[0].p, (const PartSet *)e->s_job[1].p,
+                                                                                  (const ScoreWork *)e->s_job[2].p, e->s_reltab.p, e->s_relerr.p, J.sh_cells);
         CK(cudaGetLastError());
     }
     if (!J.refs.empty()) {
@@ -912,12 +915,16 @@ extern "C" int hirm_engine_relation_score_matrix(hirm_engine *e, int n_rel, cons
         }
     }
     if (job_relations(J, n_rel, h_arity, h_rel_doms, h_nobs, h_d_ids, h_d_val, C0->n_domains, C0->kcap.data())) return -1;
+    for (int r = 0; r < n_rel; r++)                     // a table that does not fit the small histogram but fits the big one: big launch
+        if (J.rels[(size_t)r].ncells > RM_SH_CELLS && J.rels[(size_t)r].ncells <= RM_SH_CELLS_BIG) J.sh_cells = RM_SH_CELLS_BIG;
     for (int r = 0; r < n_rel; r++) {
         const RelDesc &R = J.rels[(size_t)r];
         const int64_t t0 = J.total_cells;
         J.total_cells += R.ncells * n_cand;
         for (int c = 0; c < n_cand; c++) J.refs.push_back(TableRef{t0 + c * R.ncells, R.ncells});
-        const int run = R.ncells <= RM_SH_CELLS ? (int)std::max<int64_t>(1, std::min<int64_t>(n_cand, RM_SH_CELLS / R.ncells)) : n_cand;
+        // candidates per work item: as many tables as fit the shared histogram; a table too big for it takes global atomics,
+        // a few candidates per item so that the grid stays wide
+        const int run = R.ncells <= J.sh_cells ? (int)std::max<int64_t>(1, std::min<int64_t>(n_cand, J.sh_cells / R.ncells)) : std::min(n_cand, 8);
         for (int c0 = 0; c0 < n_cand; c0 += run)
             for (int64_t o = 0; o < R.nobs; o += RM_OBS_PER_ITEM)
                 J.work.push_back(ScoreWork{r, c0, std::min(run, n_cand - c0), 0, o, std::min(R.nobs, o + RM_OBS_PER_ITEM), t0 + c0 * R.ncells});
@@ -954,6 +961,8 @@ extern "C" int hirm_engine_relation_scores_fresh(hirm_engine *e, int n_rel, cons
     if (!(alpha > 0)) return fail("alpha must be positive");
     ScoreJob J;
     if (job_relations(J, n_rel, h_arity, h_rel_doms, h_nobs, h_d_ids, h_d_val, n_domains, h_max_tables)) return -1;
+    for (int r = 0; r < n_rel; r++)
+        if (J.rels[(size_t)r].ncells > RM_SH_CELLS && J.rels[(size_t)r].ncells <= RM_SH_CELLS_BIG) J.sh_cells = RM_SH_CELLS_BIG;
     int64_t slots = 0;
     for (int r = 0; r < n_rel; r++) {
         bool used[MAX_DOMAINS] = {false};

@@ -291,34 +291,16 @@ class ShardedHIRM:
         self.timers["entity"] += time.perf_counter() - t0
 
     # ---- relation step (cxx/hirm.cc:66-71 -> cxx/hirm.hh:833-906) --------------------------------------------------------
-    def score_columns(self):
-        """Steps 1-2: {table label: [R] scores of every relation under that IRM}, [R] fresh-table scores, fresh keys."""
-        import time
-        t0 = time.perf_counter()
-        R, nd, world, rank = len(self.rnames), len(self.dnames), self.comm.world, self.comm.rank
-        local = self._local()
-        m_local = self.backend.score_matrix(list(range(R)), [self.irms[t]["handle"] for t in local])
+    def _fresh_keys(self):
+        """Philox streams of this relation sweep's fresh-table draws, [R, n_domains] (replicated bookkeeping)."""
+        R, nd = len(self.rnames), len(self.dnames)
         base = self._next_key
         self._next_key += R * nd
-        keys = (base + np.arange(R * nd, dtype=np.uint64)).reshape(R, nd)
-        mine = [r for r in range(R) if r % world == rank]
-        f_local = self.backend.scores_fresh(mine, keys[mine]) if mine else np.zeros(0)
-        t1 = time.perf_counter()
-        per_rank = [[t for t in sorted(self.irms) if self.irms[t]["owner"] == k] for k in range(world)]
-        kmax = max(len(p) for p in per_rank)
-        buf = np.zeros((R, kmax + 1), dtype=np.float64)
-        buf[:, :len(local)] = m_local
-        buf[mine, kmax] = f_local
-        parts = self.comm.all_gather_f64(buf)
-        cols = {}
-        for k in range(world):
-            for j, t in enumerate(per_rank[k]):
-                cols[t] = parts[k][:, j].copy()
-        fresh = np.array([parts[r % world][r, kmax] for r in range(R)])
-        t2 = time.perf_counter()
-        self.timers["score"] += t1 - t0
-        self.timers["gather"] += t2 - t1
-        return cols, fresh, keys
+        return (base + np.arange(R * nd, dtype=np.uint64)).reshape(R, nd)
+
+    def score_columns(self):
+        """Steps 1-2: {table label: [R] scores of every relation under that IRM}, [R] fresh-table scores, fresh keys."""
+        return score_columns_batched([self])[0]
 
     def relation_candidates(self, r, cols, fresh_score):
         """CRP::tables_weights_gibbs (:147-161) + the data terms: (tables ascending, log-probabilities, fresh label or None)."""
@@ -370,10 +352,11 @@ class ShardedHIRM:
             del self.irms[cur]
             cols.pop(cur, None)
 
-    def transition_relations(self):
-        """One sweep of relation moves: every relation once, in a seeded order."""
+    def transition_relations(self, scored=None):
+        """One sweep of relation moves: every relation once, in a seeded order.  `scored`: the (columns, fresh scores,
+        keys) of score_columns_batched when several chains were scored in one launch."""
         import time
-        cols, fresh, keys = self.score_columns()
+        cols, fresh, keys = scored if scored is not None else self.score_columns()
         t0 = time.perf_counter()
         rng = np.random.default_rng([self.seed, self.chain, self.iteration, 0x72656C])
         order = rng.permutation(len(self.rnames))
@@ -455,6 +438,40 @@ class ShardedHIRM:
         return {t: merged[t] for t in sorted(merged)}
 
 
+def score_columns_batched(chains):
+    """Steps 1-2 of the relation move for several chains over the same data at once: ONE score-matrix launch over every
+    chain's local IRMs, ONE fresh-table launch, ONE all-gather.  Returns [(columns, fresh scores, keys)] per chain."""
+    import time
+    t0 = time.perf_counter()
+    h0 = chains[0]
+    comm, backend = h0.comm, h0.backend
+    R, world, rank = len(h0.rnames), comm.world, comm.rank
+    mine = [r for r in range(R) if r % world == rank]
+    locals_ = [h._local() for h in chains]
+    handles = [h.irms[t]["handle"] for h, loc in zip(chains, locals_) for t in loc]
+    m_all = backend.score_matrix(list(range(R)), handles)
+    keys = [h._fresh_keys() for h in chains]
+    f_all = backend.scores_fresh(mine * len(chains), np.concatenate([k[mine] for k in keys])) if mine else np.zeros(0)
+    t1 = time.perf_counter()
+    per_rank = [[[t for t in sorted(h.irms) if h.irms[t]["owner"] == k] for k in range(world)] for h in chains]
+    kmax = max(len(p) for pr in per_rank for p in pr)
+    buf = np.zeros((len(chains), R, kmax + 1), dtype=np.float64)
+    off = 0
+    for c, loc in enumerate(locals_):
+        buf[c, :, :len(loc)] = m_all[:, off:off + len(loc)]
+        off += len(loc)
+        buf[c, mine, kmax] = f_all[c * len(mine):(c + 1) * len(mine)]
+    parts = comm.all_gather_f64(buf)
+    out = []
+    for c in range(len(chains)):
+        cols = {t: parts[k][c][:, j].copy() for k in range(world) for j, t in enumerate(per_rank[c][k])}
+        fresh = np.array([parts[r % world][c][r, kmax] for r in range(R)])
+        out.append((cols, fresh, keys[c]))
+    h0.timers["score"] += t1 - t0
+    h0.timers["gather"] += time.perf_counter() - t1
+    return out
+
+
 class ChainSet:
     """Several independent seeded chains of one HIRM over the same observations and the same ranks (BASELINE config 5:
     "8 chains").  The chains share the replicated COO arrays; per iteration the relation steps run chain by chain (small),
@@ -468,7 +485,8 @@ class ChainSet:
         self.backend, self.comm = first.backend, first.comm
 
     def transition_relations(self):
-        return [h.transition_relations() for h in self.chains]
+        scored = score_columns_batched(self.chains)
+        return [h.transition_relations(scored=sc) for h, sc in zip(self.chains, scored)]
 
     def transition_irms(self):
         hs = [h.irms[t]["handle"] for h in self.chains for t in h._local()]
