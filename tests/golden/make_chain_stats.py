@@ -5,6 +5,7 @@ cxx/hirm.cc:26-37) at the end of every iteration.  Datasets in which every domai
 that the reference's conditional is exact:
   * animals.unary as ONE IRM (cxx/assets/animals.unary.{schema,obs}: 50 animals x 85 unary relations);
   * a synthetic `bernoulli R a b` + `bernoulli U a` with planted blocks.
+  * animals.unary as an HIRM (config 1), through oracle/_ref/ref_chain.
 Writes tests/golden/chain_stats.json.gz (observations included: /root/reference does not exist on the GPU box).
 
     python tests/golden/make_chain_stats.py
@@ -95,6 +96,21 @@ def main():
                                  "ref_logp_score": scores}
         s = np.asarray(scores)[:, ITERS // 2:]
         print(name, "reference logp_score after burn-in: mean %.2f, sd of chain means %.2f" % (s.mean(), s.mean(axis=1).std()))
+    # HIRM chains: oracle/_ref/ref_chain (oracle/ref_chain.cc) runs the reference's own inference_hirm iteration and
+    # prints HIRM::logp_score and the number of IRMs at the end of every iteration
+    base = os.path.join(tmp, "animals.unary")
+    n_ent, rels, obs = read_dataset(base)
+    hs, hk = [], []
+    for seed in range(1, SEEDS + 1):
+        o = subprocess.check_output([os.path.join(ROOT, "oracle", "_ref", "ref_chain"), base, str(seed), str(ITERS)], text=True)
+        rows = [l.split() for l in o.splitlines() if l.startswith("iter")]
+        assert len(rows) == ITERS
+        hs.append([float(r[2]) for r in rows]); hk.append([int(r[3]) for r in rows])
+    out["datasets"]["animals_unary_hirm"] = {"domains": n_ent, "relations": [{"name": r, "domains": ds, "obs": obs[r]} for r, ds in rels],
+                                             "ref_logp_score": hs, "ref_n_irms": hk}
+    s = np.asarray(hs)[:, ITERS // 2:]
+    print("animals_unary_hirm reference HIRM logp_score after burn-in: mean %.2f, sd of chain means %.2f, IRMs %.2f"
+          % (s.mean(), s.mean(axis=1).std(), np.asarray(hk)[:, ITERS // 2:].mean()))
     with gzip.open(os.path.join(ROOT, "tests", "golden", "chain_stats.json.gz"), "wt") as f:
         json.dump(out, f)
     shutil.rmtree(tmp)
