@@ -34,6 +34,8 @@ EXPORTS = [
     "hirm_engine_relation_scores", "hirm_irm_seat_entities", "hirm_engine_debug_score_delta",
     "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
     "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters",
+    "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
+    "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
 ]
 
 _lib = None
@@ -101,8 +103,60 @@ def load():
                                                     ctypes.c_uint64, c_u64p, c_f64p]
     L.hirm_irm_set_rng_counters.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
     L.hirm_engine_crp_prior_draw.argtypes = [V, I, ctypes.c_double, I, ctypes.c_uint64, ctypes.c_uint64, c_i32p]
+    CP = ctypes.POINTER(ctypes.c_char_p)
+    L.hirm_dataset_last_error.restype = ctypes.c_char_p
+    L.hirm_dataset_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(V)]
+    L.hirm_dataset_free.argtypes = [V]
+    L.hirm_dataset_counts.argtypes = [V, c_i32p, c_i32p]
+    L.hirm_dataset_domain.argtypes = [V, I, CP, c_i32p]
+    L.hirm_dataset_relation.argtypes = [V, I, CP, c_i32p, c_i32p, c_i64p]
+    L.hirm_dataset_observations.argtypes = [V, I, ctypes.POINTER(c_i32p), ctypes.POINTER(c_u8p)]
+    L.hirm_dataset_entity.argtypes = [V, I, ctypes.c_int32, CP]
     _lib = L
     return L
+
+
+def load_dataset(schema_path, obs_path, with_names=True):
+    """Native reader of <base>.schema / <base>.obs (csrc/ingest.cc; cxx/util_io.cc:11-96): returns
+    (domains {name: n_entities}, schema {relation: [domain names]}, observations {relation: (ids [nobs, arity] int32,
+    val [nobs] uint8)}, names {domain: [entity name by code]} or None) -- the inputs of hirm.sharded.ShardedHIRM."""
+    L = load()
+    ds = ctypes.c_void_p()
+    if L.hirm_dataset_load(os.fsencode(schema_path), os.fsencode(obs_path), ctypes.byref(ds)):
+        raise EngineError(L.hirm_dataset_last_error().decode())
+    try:
+        nd, nr = ctypes.c_int32(), ctypes.c_int32()
+        L.hirm_dataset_counts(ds, ctypes.byref(nd), ctypes.byref(nr))
+        name, n = ctypes.c_char_p(), ctypes.c_int32()
+        dnames, domains = [], {}
+        for d in range(nd.value):
+            L.hirm_dataset_domain(ds, d, ctypes.byref(name), ctypes.byref(n))
+            dnames.append(name.value.decode()); domains[dnames[-1]] = n.value
+        schema, observations = {}, {}
+        ar, nobs, doms = ctypes.c_int32(), ctypes.c_int64(), (ctypes.c_int32 * MAX_ARITY)()
+        pi, pv = c_i32p(), c_u8p()
+        for r in range(nr.value):
+            L.hirm_dataset_relation(ds, r, ctypes.byref(name), ctypes.byref(ar), doms, ctypes.byref(nobs))
+            rn = name.value.decode()
+            schema[rn] = [dnames[doms[k]] for k in range(ar.value)]
+            L.hirm_dataset_observations(ds, r, ctypes.byref(pi), ctypes.byref(pv))
+            if nobs.value:
+                ids = np.ctypeslib.as_array(pi, shape=(nobs.value * ar.value,)).reshape(nobs.value, ar.value).copy()
+                val = np.ctypeslib.as_array(pv, shape=(nobs.value,)).copy()
+            else:
+                ids, val = np.zeros((0, ar.value), np.int32), np.zeros(0, np.uint8)
+            observations[rn] = (ids, val)
+        names = None
+        if with_names:
+            names = {}
+            for d, dn in enumerate(dnames):
+                names[dn] = []
+                for c in range(domains[dn]):
+                    L.hirm_dataset_entity(ds, d, c, ctypes.byref(name))
+                    names[dn].append(name.value.decode())
+        return domains, schema, observations, names
+    finally:
+        L.hirm_dataset_free(ds)
 
 
 def _p(a, t):

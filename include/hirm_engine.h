@@ -205,6 +205,22 @@ int hirm_engine_debug_score_delta(hirm_engine *e, int n, const uint32_t *h_N, co
  * (producer, accumulate warps, decision warps: see profiles/phase_breakdown.py); NULL switches it off */
 int hirm_engine_debug_phase_cycles(hirm_engine *e, long long *d_buf);
 
+/* ---- ingest: the reference's text formats, natively (host only; no CUDA device needed) ------------------------------
+ * load_schema (cxx/util_io.cc:11-34) + load_observations (:36-61) + encode_observations (:63-96): <base>.schema and
+ * <base>.obs -> per relation a COO array of integer entity codes (per domain 0, 1, 2... in order of first appearance, lines
+ * in file order, positions left to right) and a value array, ready for hirm_irm_set_observations.  Relations keep the
+ * schema file's order, domains the order of their first appearance in it.  Pointers returned by the accessors stay
+ * owned by the dataset (hirm_dataset_entity: until the next call). */
+typedef struct hirm_dataset hirm_dataset;
+const char *hirm_dataset_last_error(void);
+int hirm_dataset_load(const char *schema_path, const char *obs_path, hirm_dataset **out);
+int hirm_dataset_free(hirm_dataset *ds);
+int hirm_dataset_counts(const hirm_dataset *ds, int32_t *n_domains, int32_t *n_relations);
+int hirm_dataset_domain(const hirm_dataset *ds, int dom, const char **name, int32_t *n_entities);
+int hirm_dataset_relation(const hirm_dataset *ds, int rel, const char **name, int32_t *arity, int32_t *doms, int64_t *nobs);
+int hirm_dataset_observations(const hirm_dataset *ds, int rel, const int32_t **ids, const uint8_t **val);
+int hirm_dataset_entity(hirm_dataset *ds, int dom, int32_t code, const char **name);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,3 +75,38 @@ def test_cli_hirm_and_irm_end_to_end(tmp_path, capsys):
     clusters = util_io.load_clusters_irm(base + ".10.irm")
     assert sum(len(v) for v in clusters["animal"].values()) == 50
     assert cli.main(["--mode", "nope", base]) == 1
+
+
+def test_native_reader_matches_reference_encoding(tmp_path):
+    """csrc/ingest.cc against load_schema + load_observations + the first-appearance encoding of cxx/util_io.cc:63-96
+    (restated here with the Python readers); no GPU needed."""
+    import numpy as np
+    from hirm import engine as E
+    from hirm import util_io
+    base = tmp_path / "toy"
+    (tmp_path / "toy.schema").write_text("bernoulli likes person item\nbernoulli tall person\n\nbernoulli knows person person\n")
+    lines = ["1 likes ann tea", "0 likes bob tea", "1.0 tall bob", "0 knows bob ann", "1 likes ann jam", "  1 knows cat cat  ", "0.0 tall cat"]
+    (tmp_path / "toy.obs").write_text("\n".join(lines) + "\n")
+    domains, schema, obs, names = E.load_dataset(str(base) + ".schema", str(base) + ".obs")
+    assert schema == util_io.load_schema(str(base) + ".schema") == {"likes": ["person", "item"], "tall": ["person"], "knows": ["person", "person"]}
+    codes = {d: {} for d in domains}
+    want = {r: [] for r in schema}
+    for r, items, v in util_io.load_observations(str(base) + ".obs"):
+        want[r].append([codes[d].setdefault(it, len(codes[d])) for d, it in zip(schema[r], items)] + [v])
+    assert domains == {d: len(c) for d, c in codes.items()} == {"person": 3, "item": 2}
+    assert names == {d: sorted(c, key=c.get) for d, c in codes.items()}
+    for r in schema:
+        w = np.asarray(want[r]).reshape(-1, len(schema[r]) + 1)
+        np.testing.assert_array_equal(obs[r][0], w[:, :-1])
+        np.testing.assert_array_equal(obs[r][1], w[:, -1])
+    (tmp_path / "bad.obs").write_text("2 tall ann\n")
+    try:
+        E.load_dataset(str(base) + ".schema", str(tmp_path / "bad.obs"))
+        assert False
+    except E.EngineError as err:
+        assert "0 or 1" in str(err)
+    ref = "/root/reference/cxx/assets/animals.unary"
+    import os
+    if os.path.exists(ref + ".obs"):
+        d2, s2, o2, _ = E.load_dataset(ref + ".schema", ref + ".obs", with_names=False)
+        assert d2 == {"animal": 50} and len(s2) == 85 and sum(len(v[1]) for v in o2.values()) == 4250
