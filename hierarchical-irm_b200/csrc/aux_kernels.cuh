@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(AUX_THREADS) relmat_hist_kernel(const RelDesc 
             if (sh_n[i]) atomicAdd(&tables[W.table0 + i], pack_cell(sh_n[i], sh_s[i]));
     }
 }
-struct TableRef { int64_t off, ncells; };
+struct TableRef { int64_t off, ncells, out; };   // scratch table, its size, index of the score in the output array
 __global__ void __launch_bounds__(AUX_THREADS) relmat_score_kernel(const TableRef *refs, const cell_t *tables, double *out) {
     const TableRef T = refs[blockIdx.x];
     __shared__ double s_part[AUX_THREADS / 32];
@@ -202,7 +202,93 @@ __global__ void __launch_bounds__(AUX_THREADS) relmat_score_kernel(const TableRe
         if (cell_n(c)) acc += cell_score(cell_n(c), cell_s(c));
     }
     const double total = block_sum(acc, s_part);
-    if (threadIdx.x == 0) out[blockIdx.x] = total;
+    if (threadIdx.x == 0) out[T.out] = total;
+}
+
+// K4 for UNARY relations (animals.unary: all 85 relations; config 5: 2000 of 2050): no histogram at all.  A unary relation
+// over a domain of n entities is two bit vectors over the entity codes (observed, value = 1); a table of a candidate
+// partition is a member bit vector; then  N_t = popc(observed & members_t),  s_t = popc(value & members_t).
+// CTA = (candidate, block of relations).  Tables go in passes of 32 (lane = table); the entity range in tiles whose
+// member masks are built in shared memory with ballots from the candidate's slot array (coalesced) and shared by all
+// relations of the block; every lane keeps (N, s) of its table for the warp's UN_RW relations in registers across the
+// tiles -- no atomics, no reductions until the final sum of the 32 cell scores.
+constexpr int UN_THREADS = 256, UN_WARPS = UN_THREADS / 32, UN_RW = 8;   // 64 relations per CTA
+constexpr int UN_TILE = 1024;                                            // entity words per tile (32768 entities)
+struct UnaryRel { const uint32_t *obs, *val; int32_t out_row, pad; };
+__global__ void unary_bits_kernel(const int32_t *ids, const uint8_t *val, int64_t nobs, uint32_t *obs_bits, uint32_t *val_bits) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < nobs; o += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t i = ids[o];
+        atomicOr(&obs_bits[i >> 5], 1u << (i & 31));
+        if (val[o]) atomicOr(&val_bits[i >> 5], 1u << (i & 31));
+    }
+}
+__global__ void __launch_bounds__(UN_THREADS) relmat_unary_kernel(const UnaryRel *rels, int n_rels, const PartSet *parts, int dom, int n_ent,
+                                                                  int n_cand, double *out, int32_t *error) {
+    extern __shared__ uint32_t un_masks[];                 // [32][UN_TILE + 1]
+    __shared__ int32_t s_red[UN_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cand = blockIdx.x;
+    const int32_t *z = parts[cand].z[dom];
+    const int nwords = (n_ent + 31) >> 5;
+    // highest slot in use (+1) and a check that every entity is seated
+    int tmax = 0, bad = 0;
+    for (int i = tid; i < n_ent; i += UN_THREADS) { const int v = z[i]; tmax = max(tmax, v + 1); bad |= v < 0; }
+    tmax = __reduce_max_sync(0xffffffffu, tmax);
+    bad = __reduce_max_sync(0xffffffffu, bad);
+    if (lane == 0) s_red[warp] = tmax | (bad << 30);
+    __syncthreads();
+    tmax = 0;
+    for (int w = 0; w < UN_WARPS; w++) { tmax = max(tmax, s_red[w] & ((1 << 30) - 1)); bad |= s_red[w] >> 30; }
+    if (bad) { if (tid == 0) atomicCAS(error, 0, KERR_ABSENT_ENTITY); return; }
+    const int r0 = (blockIdx.y * UN_WARPS + warp) * UN_RW;          // this warp's relations r0 .. r0 + UN_RW - 1
+    double total[UN_RW];
+#pragma unroll
+    for (int k = 0; k < UN_RW; k++) total[k] = 0.0;
+    for (int t0 = 0; t0 < tmax; t0 += 32) {
+        const int tcount = min(32, tmax - t0);
+        uint32_t nacc[UN_RW], sacc[UN_RW];
+#pragma unroll
+        for (int k = 0; k < UN_RW; k++) { nacc[k] = 0u; sacc[k] = 0u; }
+        for (int w0 = 0; w0 < nwords; w0 += UN_TILE) {
+            const int wt = min(UN_TILE, nwords - w0);
+            __syncthreads();                                         // the previous tile's masks are no longer read
+            for (int w = warp; w < wt; w += UN_WARPS) {              // member masks of tables t0 .. t0 + tcount - 1
+                const int i = (w0 + w) * 32 + lane;
+                const int zl = i < n_ent ? z[i] - t0 : -1;
+                uint32_t mine = 0u;
+                for (int t = 0; t < tcount; t++) {
+                    const uint32_t b = __ballot_sync(0xffffffffu, zl == t);
+                    if (lane == t) mine = b;
+                }
+                if (lane < tcount) un_masks[lane * (UN_TILE + 1) + w] = mine;
+            }
+            __syncthreads();
+            const uint32_t *mrow = un_masks + lane * (UN_TILE + 1);
+#pragma unroll
+            for (int k = 0; k < UN_RW; k++) {
+                if (r0 + k >= n_rels) break;
+                const uint32_t *ob = rels[r0 + k].obs + w0, *vb = rels[r0 + k].val + w0;
+                uint32_t na = 0u, sa = 0u;
+                for (int w = 0; w < wt; w++) {
+                    const uint32_t m = lane < tcount ? mrow[w] : 0u;
+                    na += __popc(__ldg(ob + w) & m);
+                    sa += __popc(__ldg(vb + w) & m);
+                }
+                nacc[k] += na; sacc[k] += sa;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UN_RW; k++) {
+            if (r0 + k >= n_rels) break;
+            double v = nacc[k] ? cell_score(nacc[k], sacc[k]) : 0.0;   // BetaBernoulli::logp_score of table t0 + lane's cell
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            total[k] += v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < UN_RW; k++)
+        if (r0 + k < n_rels && lane == 0) out[(int64_t)rels[r0 + k].out_row * n_cand + cand] = total[k];
 }
 
 // A draw from the sequential CRP(alpha) prior over n customers -- what Domain::incorporate (cxx/hirm.hh:194-203 ->

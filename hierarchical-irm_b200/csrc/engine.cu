@@ -113,7 +113,10 @@ struct hirm_engine {
     DevBuf<double> s_alpha;
     DevBuf<cell_t> s_reltab; DevBuf<RelCand> s_relcand; DevBuf<int32_t> s_relerr;
     DevBuf<uint64_t> s_sweep0;
-    DevBuf<unsigned char> s_job[5]; DevBuf<int32_t> s_prior;   // relation-score jobs: descriptors, fresh partitions
+    DevBuf<unsigned char> s_job[6]; DevBuf<int32_t> s_prior;   // relation-score jobs: descriptors, fresh partitions
+    // unary relations as bit vectors over the entity codes (observed, value), built once per COO buffer
+    struct UnaryBits { DevBuf<uint32_t> obs, val; int64_t nobs = 0; int32_t n_ent = 0; const uint8_t *val_src = nullptr; };
+    std::map<const int32_t *, UnaryBits> unary_cache;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
     int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0, dense_static_smem = 0, dense_static_smem_large = 0;
@@ -825,6 +828,9 @@ extern "C" int hirm_engine_relation_scores(hirm_engine *e, int32_t src, int rel,
 namespace {
 struct ScoreJob {
     int sh_cells = RM_SH_CELLS;        // shared-memory histogram cells per work item of this launch
+    std::vector<UnaryRel> unary[MAX_DOMAINS];   // matrix mode: unary relations per domain (relmat_unary_kernel)
+    int unary_n_ent[MAX_DOMAINS] = {0}, n_cand = 0;
+    size_t out_count = 0;              // scores in the output array
     std::vector<RelDesc> rels; std::vector<PartSet> parts; std::vector<ScoreWork> work; std::vector<TableRef> refs;
     std::vector<int64_t> table0;       // scratch offset of relation r's first table
     int64_t total_cells = 0;
@@ -864,7 +870,8 @@ static int job_upload(hirm_engine *e, DevBuf<unsigned char> &buf, const std::vec
 // histogram + score passes of a prepared job; h_out gets one value per J.refs entry
 static int run_score_job(hirm_engine *e, ScoreJob &J, double *h_out) {
     cudaStream_t s0 = e->stream;
-    CK(e->s_reltab.ensure((size_t)std::max<int64_t>(J.total_cells, 1))); CK(e->s_score.ensure(std::max<size_t>(J.refs.size(), 1)));
+    if (J.out_count == 0) J.out_count = J.refs.size();
+    CK(e->s_reltab.ensure((size_t)std::max<int64_t>(J.total_cells, 1))); CK(e->s_score.ensure(std::max<size_t>(J.out_count, 1)));
     CK(e->s_relerr.ensure(1));
     CK(cudaMemsetAsync(e->s_reltab.p, 0, (size_t)J.total_cells * sizeof(cell_t), s0));
     CK(cudaMemsetAsync(e->s_relerr.p, 0, sizeof(int32_t), s0));
@@ -880,8 +887,25 @@ static int run_score_job(hirm_engine *e, ScoreJob &J, double *h_out) {
     if (!J.refs.empty()) {
         relmat_score_kernel<<<(unsigned)J.refs.size(), AUX_THREADS, 0, s0>>>((const TableRef *)e->s_job[3].p, e->s_reltab.p, e->s_score.p);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h_out, e->s_score.p, J.refs.size() * sizeof(double), cudaMemcpyDeviceToHost, s0));
     }
+    std::vector<UnaryRel> all_unary;                    // keep the upload source alive until the synchronize below
+    for (int d = 0; d < MAX_DOMAINS; d++) all_unary.insert(all_unary.end(), J.unary[d].begin(), J.unary[d].end());
+    if (!all_unary.empty()) {
+        if (job_upload(e, e->s_job[5], all_unary)) return -1;
+        const size_t sh = (size_t)32 * (UN_TILE + 1) * sizeof(uint32_t);
+        CK(cudaFuncSetAttribute(relmat_unary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        size_t off = 0;
+        for (int d = 0; d < MAX_DOMAINS; d++) {
+            const int nr = (int)J.unary[d].size();
+            if (!nr) continue;
+            dim3 grid((unsigned)J.n_cand, (unsigned)((nr + UN_WARPS * UN_RW - 1) / (UN_WARPS * UN_RW)));
+            relmat_unary_kernel<<<grid, UN_THREADS, sh, s0>>>((const UnaryRel *)e->s_job[5].p + off, nr, (const PartSet *)e->s_job[1].p, d,
+                                                              J.unary_n_ent[d], J.n_cand, e->s_score.p, e->s_relerr.p);
+            CK(cudaGetLastError());
+            off += (size_t)nr;
+        }
+    }
+    if (J.out_count) CK(cudaMemcpyAsync(h_out, e->s_score.p, J.out_count * sizeof(double), cudaMemcpyDeviceToHost, s0));
     int32_t err = 0;
     CK(cudaMemcpyAsync(&err, e->s_relerr.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
     CK(cudaStreamSynchronize(s0));                      // the job vectors are the sources of the async copies
@@ -917,11 +941,28 @@ extern "C" int hirm_engine_relation_score_matrix(hirm_engine *e, int n_rel, cons
     if (job_relations(J, n_rel, h_arity, h_rel_doms, h_nobs, h_d_ids, h_d_val, C0->n_domains, C0->kcap.data())) return -1;
     for (int r = 0; r < n_rel; r++)                     // a table that does not fit the small histogram but fits the big one: big launch
         if (J.rels[(size_t)r].ncells > RM_SH_CELLS && J.rels[(size_t)r].ncells <= RM_SH_CELLS_BIG) J.sh_cells = RM_SH_CELLS_BIG;
+    J.n_cand = n_cand; J.out_count = (size_t)n_rel * n_cand;
+    const bool use_unary = getenv("HIRM_NO_UNARY_PATH") == nullptr;
     for (int r = 0; r < n_rel; r++) {
         const RelDesc &R = J.rels[(size_t)r];
+        if (use_unary && R.arity == 1 && R.nobs > 0) {   // unary relation: bit vectors, no histogram (relmat_unary_kernel)
+            const int d = R.dom[0], n_ent = C0->n_ent[d];
+            auto &U = e->unary_cache[R.ids];
+            if (U.nobs != R.nobs || U.n_ent != n_ent || U.val_src != R.val) {
+                const size_t nw = (size_t)((n_ent + 31) / 32) + UN_TILE;   // zero padding: the kernel reads whole words only
+                CK(U.obs.alloc(nw)); CK(U.val.alloc(nw));
+                CK(cudaMemsetAsync(U.obs.p, 0, nw * sizeof(uint32_t), e->stream)); CK(cudaMemsetAsync(U.val.p, 0, nw * sizeof(uint32_t), e->stream));
+                unary_bits_kernel<<<coo_blocks(e, R.nobs), 256, 0, e->stream>>>(R.ids, R.val, R.nobs, U.obs.p, U.val.p);
+                CK(cudaGetLastError());
+                U.nobs = R.nobs; U.n_ent = n_ent; U.val_src = R.val;
+            }
+            J.unary[d].push_back(UnaryRel{U.obs.p, U.val.p, r, 0});
+            J.unary_n_ent[d] = n_ent;
+            continue;
+        }
         const int64_t t0 = J.total_cells;
         J.total_cells += R.ncells * n_cand;
-        for (int c = 0; c < n_cand; c++) J.refs.push_back(TableRef{t0 + c * R.ncells, R.ncells});
+        for (int c = 0; c < n_cand; c++) J.refs.push_back(TableRef{t0 + c * R.ncells, R.ncells, (int64_t)r * n_cand + c});
         // candidates per work item: as many tables as fit the shared histogram; a table too big for it takes global atomics,
         // a few candidates per item so that the grid stays wide
         const int run = R.ncells <= J.sh_cells ? (int)std::max<int64_t>(1, std::min<int64_t>(n_cand, J.sh_cells / R.ncells)) : std::min(n_cand, 8);
@@ -989,7 +1030,7 @@ extern "C" int hirm_engine_relation_scores_fresh(hirm_engine *e, int n_rel, cons
         }
         const int64_t t0 = J.total_cells;
         J.total_cells += R.ncells;
-        J.refs.push_back(TableRef{t0, R.ncells});
+        J.refs.push_back(TableRef{t0, R.ncells, (int64_t)r});
         for (int64_t o = 0; o < R.nobs; o += RM_OBS_PER_ITEM)
             J.work.push_back(ScoreWork{r, r, 1, 0, o, std::min(R.nobs, o + RM_OBS_PER_ITEM), t0});
     }
