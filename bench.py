@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--ref-n", type=int, default=1000, help="entities of the reference arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--burn-in", type=int, default=3, help="untimed sweeps from the CRP-prior start before the warm-up steps (state preparation)")
     return ap.parse_args()
 
 
@@ -244,7 +245,8 @@ def main_b200(args, rank, world, local_rank):
     build_s = time.perf_counter() - t0
 
     # ---- move lists resident in HBM: every chain walks its own fresh random permutation per sweep ----------
-    nsteps = args.warmup + args.steps
+    B = max(0, args.burn_in)
+    nsteps = B + args.warmup + args.steps
     gen = torch.Generator(device=dev); gen.manual_seed(7 + args.seed + rank)
     d_items = []
     for s in range(nsteps):
@@ -268,18 +270,22 @@ def main_b200(args, rank, world, local_rank):
 
     # ---- HBM-resident timing: W warm-up sweeps (the first one is the burn-in from the CRP prior), then exactly
     #      K sweeps between CUDA events ----
-    burn_ms = None
-    for s in range(args.warmup):
+    # burn-in (state preparation, untimed): the chains leave the CRP-prior start (~10 tables) for the posterior (2-3 tables)
+    burn_ms, burn_all_ms = None, []
+    for s in range(B + args.warmup):
         device_step(s)
-        if s == 0:
-            burn_ms = eng.last_sweep_info()["kernel_ms"]
+        if s < max(B, 1):
+            torch.cuda.synchronize()
+            burn_all_ms.append(eng.last_sweep_info()["kernel_ms"])
+            if s == 0:
+                burn_ms = burn_all_ms[0]
     barrier()
     launches_per_step = eng.last_sweep_info()["launches"] if args.warmup else 1
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
     ev0.record()
-    for s in range(args.warmup, nsteps):
+    for s in range(B + args.warmup, nsteps):
         device_step(s)
     ev1.record()
     torch.cuda.synchronize()
@@ -368,7 +374,8 @@ def main_b200(args, rank, world, local_rank):
                 "config": {"workload": workload_name(n), "n_entities": n, "chains_per_gpu": chains,
                            "step": "one full Gibbs sweep (%d entity moves) of each of the %d independent chains per GPU" % (M, chains),
                            "moves_per_chain_per_step": M, "max_tables": args.max_tables,
-                           "init": "sequential CRP(alpha=1) prior draw per chain; warm-up sweeps are the burn-in",
+                           "init": "sequential CRP(alpha=1) prior draw per chain, then %d untimed burn-in sweeps (state preparation), then the warm-up steps" % B,
+                           "burn_in_sweeps": B, "burn_in_sweep_ms": burn_all_ms,
                            "tables_at_start_first_chains": k0, "tables_alive_first_chains": ktabs,
                            "burn_in_first_sweep_moves_per_s": (moves_per_gpu_step / (burn_ms * 1e-3)) if burn_ms else None,
                            "l2": "inputs (2 x %d MB slabs) larger than L2; every chain streams its own random permutation of rows" % (n * pitch // 1000000),

@@ -431,6 +431,12 @@ __global__ void gather_hi_kernel(const IrmDev *irms, const int32_t *ids, int n, 
     if (k < n) out[k] = *irms[ids[k]].dom[0].hi;
 }
 
+// first kernel error word of every listed IRM in one launch (and reset): one copy back instead of one per IRM
+__global__ void gather_errors_kernel(const IrmDev *irms, const int32_t *ids, int n, int32_t *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { int32_t *w = irms[ids[k]].error; out[k] = *w; if (*w) *w = 0; }
+}
+
 __device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; }
 
 // Sweep order (the loops of cxx/hirm.cc:45-51 / IRM::transition_cluster_assignments_all, cxx/hirm.hh:590-596): for every

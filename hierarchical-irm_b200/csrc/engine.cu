@@ -112,7 +112,7 @@ struct hirm_engine {
     DevBuf<long long> s_progress;
     DevBuf<double> s_alpha;
     DevBuf<cell_t> s_reltab; DevBuf<RelCand> s_relcand; DevBuf<int32_t> s_relerr;
-    DevBuf<uint64_t> s_sweep0;
+    DevBuf<uint64_t> s_sweep0; DevBuf<int32_t> s_errs;
     DevBuf<unsigned char> s_job[6]; DevBuf<int32_t> s_prior;   // relation-score jobs: descriptors, fresh partitions
     // unary relations as bit vectors over the entity codes (observed, value), built once per COO buffer
     struct UnaryBits { DevBuf<uint32_t> obs, val; int64_t nobs = 0; int32_t n_ent = 0; const uint8_t *val_src = nullptr; };
@@ -578,6 +578,18 @@ static int check_kernel_error(hirm_engine *e, Irm *irm) {
         CK(cudaMemsetAsync(irm->error.p, 0, sizeof(int32_t), e->stream));
         return fail(std::string("kernel error: ") + kerr_text(code));
     }
+    return 0;
+}
+
+// error words of the IRMs of a sweep (e->s_irm_ids holds their ids): one gather launch, one copy
+static int check_kernel_errors(hirm_engine *e, int n_irms) {
+    std::vector<int32_t> codes((size_t)n_irms, 0);
+    CK(e->s_errs.ensure((size_t)n_irms));
+    gather_errors_kernel<<<(n_irms + 255) / 256, 256, 0, e->stream>>>(e->d_irms.p, e->s_irm_ids.p, n_irms, e->s_errs.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(codes.data(), e->s_errs.p, (size_t)n_irms * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int32_t c : codes) if (c) return fail(std::string("kernel error: ") + kerr_text(c));
     return 0;
 }
 
@@ -1316,9 +1328,7 @@ extern "C" int hirm_engine_sweep(hirm_engine *e, int n_irms, const int32_t *h_ir
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
-    for (int k = 0; k < n_irms; k++)
-        if (check_kernel_error(e, e->irms[h_irms[k]].get())) return -1;
-    return 0;
+    return check_kernel_errors(e, n_irms);
 }
 
 static int sweep_device_impl(hirm_engine *e, int n_irms, const int32_t *h_irms, const int64_t *d_move_offsets,
@@ -1403,9 +1413,7 @@ extern "C" int hirm_engine_sweep_all(hirm_engine *e, int n_irms, const int32_t *
     if (h_out_item) CK(cudaMemcpyAsync(h_out_item, e->s_move_item.p, nm * sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
     if (h_out_choice) CK(cudaMemcpyAsync(h_out_choice, e->s_choice.p, nm * sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
     CK(cudaStreamSynchronize(s0));
-    for (int k = 0; k < n_irms; k++)
-        if (check_kernel_error(e, e->irms[h_irms[k]].get())) return -1;
-    return 0;
+    return check_kernel_errors(e, n_irms);
 }
 
 extern "C" int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, int32_t *kernel_kind, float *kernel_ms) {
