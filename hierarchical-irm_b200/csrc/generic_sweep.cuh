@@ -94,6 +94,30 @@ __device__ __forceinline__ double score_delta_unit(uint32_t N, uint32_t sv, uint
     return gn ? v : 0.0;
 }
 
+// Groups of a few observations (a sparse relation's typical group): the factorial ratios written out as products,
+//   S(N+n, s+sg) - S(N, s) = log[ prod_{j<sg} (s+1+j) * prod_{j<n-sg} (N-s+1+j) ] - log[ prod_{j<n} (N+2+j) ],
+// two logarithms and 2n multiplications instead of six logarithms and nine reciprocals.  `nmax` >= every lane's gn is
+// warp-uniform and at most 16, so each product stays below 2^512.
+__device__ __forceinline__ double score_delta_small(uint32_t N, uint32_t sv, uint32_t gn, uint32_t gs, int nmax) {
+    double pnum = 1.0, pden = 1.0;
+    const uint32_t gf = gn - gs;
+    for (int j = 0; j < nmax; j++) {
+        const double a = (uint32_t)j < gs ? (double)sv + (double)(j + 1) : 1.0;
+        const double b = (uint32_t)j < gf ? (double)(N - sv) + (double)(j + 1) : 1.0;
+        const double c = (uint32_t)j < gn ? (double)N + (double)(j + 2) : 1.0;
+        pnum *= a * b;
+        pden *= c;
+    }
+    return log_core(pnum) - log_core(pden);
+}
+// the cell score of a warp's 32 groups, by the cheapest form that fits all of them (warp-uniform choice)
+__device__ __forceinline__ double score_delta_any(const double *lf, uint32_t N, uint32_t sv, uint32_t gn, uint32_t gs) {
+    const int nmax = (int)__reduce_max_sync(0xffffffffu, gn);
+    if (nmax <= 1) return score_delta_unit(N, sv, gn, gs);
+    if (nmax <= 16) return score_delta_small(N, sv, gn, gs, nmax);
+    return score_delta_bf<GEN_LF>(lf, N, sv, gn, gs);
+}
+
 // Dynamic shared memory of one CTA: [rcap] group records, [rcap] touched accumulator cells, [pcap] partial sums,
 // [scap] accumulator cells + [scap / 32] bitmap words.
 struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww; };   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids)
@@ -426,7 +450,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 uint32_t N, sv, gn, gs;
                 eval((int64_t)ch * 32 + lane, s_cslot[t], N, sv, gn, gs);
                 __syncwarp();
-                double v = __all_sync(0xffffffffu, gn <= 1u) ? score_delta_unit(N, sv, gn, gs) : score_delta_bf<GEN_LF>(s_lf, N, sv, gn, gs);
+                double v = score_delta_any(s_lf, N, sv, gn, gs);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (lane == 0) s_part[unit] = v;
@@ -445,7 +469,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                     uint32_t N, sv, gn, gs;
                     eval(g0 + lane, slot_t, N, sv, gn, gs);
                     __syncwarp();
-                    double v = __all_sync(0xffffffffu, gn <= 1u) ? score_delta_unit(N, sv, gn, gs) : score_delta_bf<GEN_LF>(s_lf, N, sv, gn, gs);
+                    double v = score_delta_any(s_lf, N, sv, gn, gs);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     a2 += v;
