@@ -361,14 +361,15 @@ class IRM:
 def choose_index(logps, u):
     """The engine's inversion rule (cxx/util_math.cc:58-65 / random.Random.choices): first index whose running
     sum of exp(lp - max) exceeds u * total, sums in index order."""
-    lp = np.asarray(logps, dtype=np.float64)
-    e = np.exp(lp - lp.max())
+    from math import exp
+    m = max(logps)
+    e = [exp(float(v) - m) for v in logps]                # plain floats: this runs once per relation move of every chain
     total = 0.0
     for v in e:
-        total += float(v)
+        total += v
     x, cum = u * total, 0.0
     for i, v in enumerate(e):
-        cum += float(v)
+        cum += v
         if cum > x:
             return i
     return len(e) - 1

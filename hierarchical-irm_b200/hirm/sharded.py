@@ -305,16 +305,16 @@ class ShardedHIRM:
     def relation_candidates(self, r, cols, fresh_score):
         """CRP::tables_weights_gibbs (:147-161) + the data terms: (tables ascending, log-probabilities, fresh label or None)."""
         cur = self.rel_table[r]
-        w = {t: float(len(info["rels"])) for t, info in self.irms.items()}
-        w[cur] -= 1.0
+        tables = sorted(self.irms)
         fresh_label = None
-        if w[cur] == 0.0:
-            w[cur] = self.alpha                            # singleton: own table at weight alpha, no fresh one (:152-159)
-        else:
-            fresh_label = max(w) + 1
-            w[fresh_label] = self.alpha
-        tables = sorted(w)
-        lp = [math.log(w[t]) + (fresh_score if t == fresh_label else float(cols[t][r])) for t in tables]
+        lp = []
+        for t in tables:
+            n = len(self.irms[t]["rels"]) - (1 if t == cur else 0)
+            lp.append((math.log(n) if n > 0 else math.log(self.alpha)) + float(cols[t][r]))   # singleton: own table at weight alpha (:152-159)
+        if len(self.irms[cur]["rels"]) > 1:                # otherwise no fresh table is offered
+            fresh_label = tables[-1] + 1
+            tables = tables + [fresh_label]
+            lp.append(math.log(self.alpha) + fresh_score)
         return tables, lp, fresh_label
 
     def apply_relation_choice(self, r, choice, cols, keys=None, parts=None):
