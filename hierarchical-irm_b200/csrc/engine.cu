@@ -1125,6 +1125,7 @@ struct Plan {
     std::vector<int32_t> generic_blk, dense_blk;
     std::vector<DenseLaunch> tiers;   // dense: shared-memory tiers, smallest table first; the last one holds all max_tables slots
     int n_ent = 0, kcap = 0;
+    int64_t gen_maxdeg = 0;
     int gen_kmax = 0, gen_ndom = 0, gen_nother = 0;   // generic kernel: largest max_tables / domain count / other-id columns of its IRMs
 };
 
@@ -1196,7 +1197,7 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
                 if (R.kind == 1) return fail("no kernel for this irm: dense slabs are supported for a single R(e,e) relation only");
             for (int32_t kc : irm->kcap) plan.gen_kmax = std::max(plan.gen_kmax, (int)kc);
             plan.gen_ndom = std::max(plan.gen_ndom, irm->n_domains);
-            for (auto &D : irm->obs->dom) plan.gen_nother = std::max(plan.gen_nother, D.n_other);
+            for (auto &D : irm->obs->dom) { plan.gen_nother = std::max(plan.gen_nother, D.n_other); plan.gen_maxdeg = std::max(plan.gen_maxdeg, D.max_deg); }
             plan.generic_blk.push_back(k);
         }
     }
@@ -1230,7 +1231,9 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         // at most one IRM per SM: 1024 threads each (shortest move: every phase of a move is spread over the whole SM);
         // up to 4 per SM: 256 threads; many: 128 threads, 8 CTAs per SM hide one another's memory latency
         const int n_gen = (int)plan.generic_blk.size();
-        int gen_threads = n_gen <= e->num_sms ? 1024 : n_gen <= 4 * e->num_sms ? 256 : 128;
+        // (128 only for short rows: a 1000-entry row needs 8 passes of 128 threads -- measured on config 4: 1184 chains at
+        //  128 threads 5.8 M moves/s, 592 at 256 threads 10.5 M)
+        int gen_threads = n_gen <= e->num_sms ? 1024 : (n_gen <= 4 * e->num_sms || plan.gen_maxdeg > 512) ? 256 : 128;
         if (const char *s = getenv("HIRM_GENERIC_THREADS")) gen_threads = std::max(64, std::min(1024, atoi(s) & ~31));
         GenericLaunch GL;
         GL.rcap = gen_threads; GL.pcap = 4 * gen_threads; GL.scap = 4 * gen_threads;
