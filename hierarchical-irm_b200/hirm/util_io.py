@@ -129,3 +129,48 @@ def from_txt_hirm(hirm, path_schema, path_obs, path_clusters):
     for r, items, v in obs:
         hirm.incorporate(r, items, v)
     return hirm
+
+
+# ---- the sharded HIRM (hirm.sharded.ShardedHIRM works on integer codes; names come from hirm.engine.load_dataset) ----
+def to_txt_hirm_state(path, state, schema, names):
+    """<base>.<seed>.hirm (cxx/util_io.cc:152-180) from ShardedHIRM.state(): relation clusters, a blank line, one
+    "irm=<table>" section per cluster listing the domains its relations use -- every IRM of the sharded model carries every
+    domain, the reference's only those of its relations (cxx/hirm.hh:742-757)."""
+    tables = sorted(state)
+    with open(path, "w") as f:
+        for t in tables:
+            f.write("%d %s\n" % (t, " ".join(state[t]["relations"])))
+        f.write("\n")
+        for j, t in enumerate(tables):
+            f.write("irm=%d\n" % t)
+            used = []
+            for r in state[t]["relations"]:
+                used += [d for d in schema[r] if d not in used]
+            for d in used:
+                z = state[t]["z"][d]
+                by_table = {}
+                for code, tab in enumerate(z):
+                    by_table.setdefault(int(tab), []).append(names[d][code])
+                for tab in sorted(by_table):
+                    f.write("%s %d %s\n" % (d, tab, " ".join(str(x) for x in by_table[tab])))
+            if j < len(tables) - 1:
+                f.write("\n")
+
+
+def sharded_init_from_txt(path_clusters, domains, schema, names):
+    """--load for the sharded HIRM (cxx/util_io.cc:342-392): (relation_tables, partitions) for ShardedHIRM(...).  Domains a
+    cluster's file section does not list (none of its relations uses them) start in one table."""
+    import numpy as np
+    relations, irms = load_clusters_hirm(path_clusters)
+    rel_tables = {r: t for t, rs in relations.items() for r in rs}
+    code = {d: {str(n): k for k, n in enumerate(ns)} for d, ns in names.items()}
+    parts = {}
+    for t in relations:
+        parts[t] = {}
+        for d in domains:
+            z = np.zeros(domains[d], dtype=np.int32)
+            for tab, items in irms.get(t, {}).get(d, {}).items():
+                for it in items:
+                    z[code[d][str(it)]] = tab
+            parts[t][d] = z
+    return rel_tables, parts

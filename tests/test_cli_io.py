@@ -75,6 +75,17 @@ def test_cli_hirm_and_irm_end_to_end(tmp_path, capsys):
     clusters = util_io.load_clusters_irm(base + ".10.irm")
     assert sum(len(v) for v in clusters["animal"].values()) == 50
     assert cli.main(["--mode", "nope", base]) == 1
+    # the sharded HIRM from the command line (a world of one here; torchrun gives one GPU per rank), and a restart from its file
+    assert cli.main(["--sharded", "--seed", "4", "--iters", "3", "--verbose", base]) == 0
+    out = capsys.readouterr().out.splitlines()
+    assert "selected model is HIRM" in out and out[-1] == "saving to %s.4.hirm" % base
+    relations, irms = util_io.load_clusters_hirm(base + ".4.hirm")
+    assert sorted(r for rs in relations.values() for r in rs) == sorted(rels) and set(irms) == set(relations)
+    for t, doms in irms.items():
+        members = [e for items in doms["animal"].values() for e in items]
+        assert len(members) == len(set(members)) == 50
+    assert cli.main(["--sharded", "--seed", "5", "--iters", "1", "--load", base + ".4.hirm", base]) == 0
+    assert os.path.exists(base + ".5.hirm")
 
 
 def test_native_reader_matches_reference_encoding(tmp_path):
@@ -110,3 +121,30 @@ def test_native_reader_matches_reference_encoding(tmp_path):
     if os.path.exists(ref + ".obs"):
         d2, s2, o2, _ = E.load_dataset(ref + ".schema", ref + ".obs", with_names=False)
         assert d2 == {"animal": 50} and len(s2) == 85 and sum(len(v[1]) for v in o2.values()) == 4250
+
+
+def test_sharded_state_writer_and_loader_roundtrip(tmp_path):
+    """.hirm file of a ShardedHIRM state (oracle backend, CPU) parsed back: same relation clusters, same partitions."""
+    import numpy as np
+    import sharded_util as SU
+    from hirm import util_io
+    from hirm.sharded import ShardedHIRM
+    domains, schema, obs, _ = SU.synthetic_hirm(n_ent=(12, 9), n_unary=4, n_binary=2, n_clusters=2, seed=3)
+    names = {d: ["%s_%d" % (d, k) for k in range(n)] for d, n in domains.items()}
+    rn, dn = list(schema), list(domains)
+    backend = SU.OracleBackend([domains[d] for d in dn], [[dn.index(d) for d in schema[r]] for r in rn], [obs[r] for r in rn], 16, 2)
+    h = ShardedHIRM(domains, schema, obs, seed=2, max_tables=16, backend=backend)
+    h.iterate(2)
+    st = h.state()
+    path = str(tmp_path / "m.2.hirm")
+    util_io.to_txt_hirm_state(path, st, schema, names)
+    rel_tables, parts = util_io.sharded_init_from_txt(path, domains, schema, names)
+    assert rel_tables == {r: h.relation_to_table(r) for r in rn}
+    for t in st:
+        used = {d for r in st[t]["relations"] for d in schema[r]}
+        for d in used:
+            np.testing.assert_array_equal(parts[t][d], st[t]["z"][d])
+    backend2 = SU.OracleBackend([domains[d] for d in dn], [[dn.index(d) for d in schema[r]] for r in rn], [obs[r] for r in rn], 16, 2)
+    h2 = ShardedHIRM(domains, schema, obs, seed=2, max_tables=16, backend=backend2, relation_tables=rel_tables, partitions=parts)
+    assert {r: h2.relation_to_table(r) for r in rn} == rel_tables
+    h2.iterate(1)
