@@ -87,7 +87,7 @@ struct Irm {
     // generic kernel: compact group-accumulator spaces per (relation, domain) (engine_types.cuh: RelDom)
     DevBuf<RelDom> rdesc; std::vector<DevBuf<int32_t>> cmap; std::vector<int32_t> ctot;
     DevBuf<cell_t> gacc; DevBuf<uint32_t> gbm;
-    DevBuf<int32_t> gl_rel; DevBuf<int64_t> gl_cell; int64_t gl_cap = 0;
+    DevBuf<int64_t> gl_cell; int64_t gl_cap = 0;      // generic kernel: group records beyond the shared-memory ones
     DevBuf<int32_t> error;
     DevBuf<RelationDev> d_rel;
     std::vector<bool> have_z, has_absent;
@@ -560,7 +560,7 @@ static int upload_desc(hirm_engine *e, int32_t id) {
     D.rel = irm->d_rel.p;
     D.rdesc = irm->rdesc.p; D.gacc = irm->gacc.p; D.gbm = irm->gbm.p;
     for (int d = 0; d < irm->n_domains && d < (int)irm->cmap.size(); d++) { D.cmap[d] = irm->cmap[(size_t)d].p; D.ctot[d] = irm->ctot[(size_t)d]; }
-    D.gl_rel = nullptr; D.gl_cell = irm->gl_cell.p; D.gl_cap = irm->gl_cap;
+    D.gl_cell = irm->gl_cell.p; D.gl_cap = irm->gl_cap;
     D.error = irm->error.p;
     e->h_irms[id] = D;
     // pageable source: make the copy synchronous w.r.t. the host buffers (rd, D are locals)
@@ -983,6 +983,16 @@ extern "C" int hirm_engine_relation_score_matrix(hirm_engine *e, int n_rel, cons
                 J.work.push_back(ScoreWork{r, c0, std::min(run, n_cand - c0), 0, o, std::min(R.nobs, o + RM_OBS_PER_ITEM), t0 + c0 * R.ncells});
     }
     return run_score_job(e, J, h_out);
+}
+
+// The unary score path keeps two bit vectors per relation, keyed by the relation's COO buffer: drop them when the caller
+// frees or rewrites such buffers while the engine lives.
+extern "C" int hirm_engine_clear_relation_cache(hirm_engine *e) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    e->unary_cache.clear();
+    return 0;
 }
 
 static int launch_prior_draws(hirm_engine *e, const std::vector<PriorDraw> &draws, uint64_t seed) {

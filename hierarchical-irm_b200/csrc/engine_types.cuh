@@ -76,7 +76,6 @@ struct IrmDev {
     int32_t ctot[MAX_DOMAINS];
     cell_t *gacc;                 // [max ctot] accumulator, all zero between moves       (used when ctot[d] > shared capacity)
     uint32_t *gbm;                // [max ctot / 32] one bit per non-zero accumulator cell
-    int32_t *gl_rel;              // unused
     int64_t *gl_cell;             // [gl_cap] group records beyond the shared-memory ones
     int64_t gl_cap;
     int32_t *error;               // [1] first error code raised by a kernel (0 = none)

@@ -33,7 +33,7 @@ EXPORTS = [
     "hirm_engine_logp_scores", "hirm_engine_transition_alpha", "hirm_irm_get_alpha", "hirm_irm_get_tables",
     "hirm_engine_relation_scores", "hirm_irm_seat_entities", "hirm_engine_debug_score_delta",
     "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
-    "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters",
+    "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters", "hirm_engine_clear_relation_cache",
     "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
     "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
 ]
@@ -101,6 +101,7 @@ def load():
     L.hirm_engine_relation_score_matrix.argtypes = [V, I, c_i32p, c_i32p, c_i64p, VP, VP, I, c_i32p, c_f64p]
     L.hirm_engine_relation_scores_fresh.argtypes = [V, I, c_i32p, c_i32p, c_i64p, VP, VP, I, c_i32p, c_i32p, ctypes.c_double,
                                                     ctypes.c_uint64, c_u64p, c_f64p]
+    L.hirm_engine_clear_relation_cache.argtypes = [V]
     L.hirm_irm_set_rng_counters.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
     L.hirm_engine_crp_prior_draw.argtypes = [V, I, ctypes.c_double, I, ctypes.c_uint64, ctypes.c_uint64, c_i32p]
     CP = ctypes.POINTER(ctypes.c_char_p)
@@ -409,6 +410,9 @@ class Engine:
         out = np.empty(max(int(n), 1), np.int32)
         self._ck(self.L.hirm_engine_crp_prior_draw(self._h, int(n), float(alpha), int(max_tables), int(seed), int(key), _p(out, c_i32p)))
         return out[:int(n)]
+
+    def clear_relation_cache(self):
+        self._ck(self.L.hirm_engine_clear_relation_cache(self._h))
 
     def seat_entities(self, irm, dom, items, labels):
         it = np.ascontiguousarray(items, dtype=np.int32); lb = np.ascontiguousarray(labels, dtype=np.int32)

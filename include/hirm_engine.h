@@ -172,6 +172,9 @@ int hirm_engine_relation_scores(hirm_engine *e, int32_t src_irm, int rel, int n_
 int hirm_engine_relation_score_matrix(hirm_engine *e, int n_rel, const int32_t *h_arity, const int32_t *h_rel_doms,
                                       const int64_t *h_nobs, const int32_t *const *h_d_ids, const uint8_t *const *h_d_val,
                                       int n_cand, const int32_t *h_cand_irms, double *h_out);
+/* Unary relations are scored from bit vectors built once per COO buffer (keyed by h_d_ids[r]); the buffers must stay
+ * unchanged while the engine uses them -- call this after freeing or rewriting one. */
+int hirm_engine_clear_relation_cache(hirm_engine *e);
 /* The fresh-table candidate of every listed relation (cxx/hirm.hh:849-864: `new IRM({}, prng)`, whose domains are seated by
  * sequential CRP-prior draws when the relation is incorporated, :194-203): one independent CRP(alpha) draw per (relation,
  * domain the relation uses), Philox stream h_keys[r * n_domains + d]; h_out[r] = the relation's logp_score under its draw. */
