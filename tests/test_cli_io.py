@@ -116,6 +116,18 @@ def test_native_reader_matches_reference_encoding(tmp_path):
         assert False
     except E.EngineError as err:
         assert "0 or 1" in str(err)
+    # tabs, CRLF line ends, blank lines; arity and relation errors are reported with the line number
+    (tmp_path / "ws.obs").write_text("1\tlikes\tann\ttea\r\n\r\n0 tall  ann\r\n")
+    d3, _, o3, n3 = E.load_dataset(str(base) + ".schema", str(tmp_path / "ws.obs"))
+    assert d3 == {"person": 1, "item": 1} and n3 == {"person": ["ann"], "item": ["tea"]} and o3["tall"][1].tolist() == [0]
+    assert o3["knows"][0].shape == (0, 2)
+    for text, needle in (("1 likes ann\n", "too few"), ("1 tall ann bob\n", "too many"), ("1 hates ann\n", "unknown relation")):
+        (tmp_path / "e.obs").write_text("0 tall ann\n" + text)
+        try:
+            E.load_dataset(str(base) + ".schema", str(tmp_path / "e.obs"))
+            assert False
+        except E.EngineError as err:
+            assert needle in str(err) and "line 2" in str(err)
     ref = "/root/reference/cxx/assets/animals.unary"
     import os
     if os.path.exists(ref + ".obs"):
