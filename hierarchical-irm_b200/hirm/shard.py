@@ -1,4 +1,5 @@
-"""Multi-GPU partition of the entity-move path: one process per GPU, no data-path collective.
+"""Multi-GPU partition of the entity-move path: one process per GPU, no data-path collective on the entity
+sweeps (the one exchange step of an HIRM iteration, the relation move, is in hirm.sharded).
 
 Moves inside one IRM are sequentially dependent; different IRMs (the relation clusters of an HIRM) and
 different seeded chains are independent.  So ranks own disjoint sets of chains / IRMs:
