@@ -68,6 +68,19 @@ def main():
     print("C1 animals.unary HIRM, %d iterations: engine %.3f s (%d entity moves, %d relation moves, %d IRMs, logp_score %.2f); "
           "reference hirm.out (1 core, whole run incl. load) %s" % (iters, dt, entity_moves, relation_moves, len(h.irms), h.logp_score(),
                                                                    "%.3f s" % ref if ref else "n/a"))
+    # the same model on the sharded-HIRM path (one score matrix per relation sweep), one chain and 64 chains in one launch
+    from hirm.sharded import ChainSet
+    domains = {"animal": 1 + max(int(a[:, :-1].max()) for _, a in rels.values())}
+    schema = {r: ds for r, (ds, _) in rels.items()}
+    obs = {r: (a[:, :-1].astype(np.int32), a[:, -1].astype(np.uint8)) for r, (ds, a) in rels.items()}
+    for n_chains in (1, 64):
+        cs = ChainSet(domains, schema, obs, n_chains, seed=10, max_tables=48)
+        cs.iterate(1)
+        t0 = time.perf_counter()
+        cs.iterate(iters)
+        dt = time.perf_counter() - t0
+        print("C1 animals.unary HIRM on hirm.sharded, %d chain(s), %d iterations: %.3f s = %.1f ms per chain-iteration (%.1f IRMs per chain)"
+              % (n_chains, iters, dt, 1e3 * dt / (iters * n_chains), np.mean([len(h.irms) for h in cs.chains])))
     # ---- config 2: nations.binary IRM (14 countries x 56 predicates x 111 features) ----
     rels = dataset("nations_binary_irm")
     irm = IRM({r: ds for r, (ds, _) in rels.items()}, prng=random.Random(12))

@@ -55,7 +55,7 @@ def test_parsers_and_irm_writer_roundtrip(tmp_path):
 @pytest.mark.gpu
 def test_cli_hirm_and_irm_end_to_end(tmp_path, capsys):
     base, rels = write_dataset(tmp_path, "animals_unary_hirm")
-    assert cli.main(["--seed", "1", "--iters", "5", base]) == 0
+    assert cli.main(["--facade", "--seed", "1", "--iters", "5", base]) == 0
     out = capsys.readouterr().out.splitlines()
     assert out[0] == "setting seed to 1" and out[1] == "loading schema from %s.schema" % base
     assert "selected model is HIRM" in out and "inferring 5 iters; timeout 0" in out and out[-1] == "saving to %s.1.hirm" % base
@@ -66,7 +66,7 @@ def test_cli_hirm_and_irm_end_to_end(tmp_path, capsys):
         members = [e for items in doms["animal"].values() for e in items]
         assert len(members) == len(set(members)) == 50
     # restart from the saved clusters (cxx/Makefile:47)
-    assert cli.main(["--seed", "2", "--iters", "2", "--load", base + ".1.hirm", base]) == 0
+    assert cli.main(["--facade", "--seed", "2", "--iters", "2", "--load", base + ".1.hirm", base]) == 0
     assert os.path.exists(base + ".2.hirm")
     # IRM mode with --verbose
     assert cli.main(["--mode", "irm", "--iters", "3", "--verbose", base]) == 0
@@ -76,7 +76,7 @@ def test_cli_hirm_and_irm_end_to_end(tmp_path, capsys):
     assert sum(len(v) for v in clusters["animal"].values()) == 50
     assert cli.main(["--mode", "nope", base]) == 1
     # the sharded HIRM from the command line (a world of one here; torchrun gives one GPU per rank), and a restart from its file
-    assert cli.main(["--sharded", "--seed", "4", "--iters", "3", "--verbose", base]) == 0
+    assert cli.main(["--seed", "4", "--iters", "3", "--verbose", base]) == 0            # the default HIRM path
     out = capsys.readouterr().out.splitlines()
     assert "selected model is HIRM" in out and out[-1] == "saving to %s.4.hirm" % base
     relations, irms = util_io.load_clusters_hirm(base + ".4.hirm")
