@@ -1,5 +1,5 @@
-"""Load tests/golden/*.json.gz (traces of the unmodified reference, see
-tests/golden/make_golden.py) and replay them against any backend exposing
+"""Load tests/golden/*.json.gz (traces of the unmodified reference -- its C++ backend through
+tests/golden/make_golden.py, its Python backend through tests/golden/make_golden_py.py) and replay them against any backend exposing
 score/move/get_assignments/get_counts/logp_score -- the CPU oracle or the CUDA engine."""
 import gzip
 import json
@@ -9,7 +9,10 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["animals_unary_irm", "nations_binary_irm", "two_relations_irm", "animals_unary_hirm",
-         "synth_ree40_irm", "synth_ternary_irm", "synth_mixed_irm"]
+         "synth_ree40_irm", "synth_ternary_irm", "synth_mixed_irm",
+         # the reference's PYTHON backend (src/hirm.py) on BASELINE config 2, 10 sweeps from random.Random(12):
+         # tests/golden/make_golden_py.py
+         "nations_binary_py"]
 RTOL = 1e-9   # north_star: candidate log-probabilities within 1e-9 relative (fp64)
 
 

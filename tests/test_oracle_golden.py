@@ -35,7 +35,10 @@ def test_oracle_replays_reference_trace(case):
     assert total["moves"] > 0 and total["changed"] > 0
     if fx["mode"] == "irm":
         assert total["alpha_moves"] > 0  # CRP::transition_alpha is pinned against the reference's grid and scores
-    if case in ("nations_binary_irm", "synth_ree40_irm", "synth_mixed_irm"):
+    if case == "nations_binary_py":
+        # BASELINE config 2 against the Python backend: 10 sweeps x 181 entities, 30-point alpha grid per domain and sweep
+        assert fx["backend"].startswith("python") and total["moves"] == 1810 and total["alpha_moves"] == 30
+    if case in ("nations_binary_irm", "nations_binary_py", "synth_ree40_irm", "synth_mixed_irm"):
         assert total["repeated"] > 0     # the Q1 (repeated-domain) path is exercised
 
 
