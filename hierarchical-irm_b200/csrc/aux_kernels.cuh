@@ -44,7 +44,14 @@ __global__ void __launch_bounds__(AUX_THREADS) logp_scores_kernel(const IrmDev *
     }
     double total = block_sum(acc, s_part);
     if (threadIdx.x == 0) {
+        // CRP terms of the domains some relation of this IRM uses: the reference's IRM holds no other domain
+        // (IRM::add_relation creates them, remove_relation drops a domain with its last relation: cxx/hirm.hh:742-782),
+        // while an IRM of the sharded HIRM carries every domain of the schema
+        uint32_t used = 0u;
+        for (int r = 0; r < irm.n_relations; r++)
+            for (int p = 0; p < irm.rel[r].arity; p++) used |= 1u << irm.rel[r].dom[p];
         for (int d = 0; d < irm.n_domains; d++) {
+            if (!((used >> d) & 1u)) continue;
             const DomainDev &dd = irm.dom[d];
             int K, N;
             const double t2 = crp_score_terms(dd.tab_count, *dd.hi, K, N);

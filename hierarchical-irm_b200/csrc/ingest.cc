@@ -14,6 +14,7 @@
 #include <string>
 #include <string_view>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 namespace {
@@ -93,6 +94,8 @@ extern "C" int hirm_dataset_load(const char *schema_path, const char *obs_path, 
     const size_t nd = ds->dom_names.size(), nr = ds->rel_names.size();
     ds->codes.resize(nd); ds->names.resize(nd); ds->ids.resize(nr); ds->val.resize(nr);
     // ---- observations
+    // an observation may be listed once: Relation::incorporate asserts `data.count(items) == 0` (cxx/hirm.hh:272)
+    std::vector<std::unordered_set<std::string>> seen(nr);
     int64_t line_no = 0;
     for (const char *p = ds->obs_buf.data(), *fe = p + ds->obs_buf.size(); p < fe;) {
         const char *le = (const char *)memchr(p, '\n', (size_t)(fe - p));
@@ -128,6 +131,10 @@ extern "C" int hirm_dataset_load(const char *schema_path, const char *obs_path, 
                 ds->ids[(size_t)r].push_back(it->second);
             }
             if (!next_token(q, le).empty()) return ifail("line " + std::to_string(line_no) + ": too many entities for relation " + std::string(rel));
+            const std::vector<int32_t> &all = ds->ids[(size_t)r];
+            const std::string key((const char *)(all.data() + all.size() - doms.size()), doms.size() * sizeof(int32_t));
+            if (!seen[(size_t)r].insert(key).second)
+                return ifail("line " + std::to_string(line_no) + ": observation listed twice for relation " + std::string(rel));
             ds->val[(size_t)r].push_back((uint8_t)value);
         }
         p = le + 1;

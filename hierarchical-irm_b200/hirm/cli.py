@@ -136,7 +136,7 @@ def main(argv=None):
                 model.incorporate(r, items, v)
         else:
             print("loading clusters from %s" % args.load)
-            model = util_io.from_txt_irm(IRM({}, prng=prng), path_schema, path_obs, args.load)
+            model = util_io.from_txt_irm(path_schema, path_obs, args.load, prng=prng)
         print("inferring %d iters; timeout %d" % (args.iters, args.timeout))
         inference_irm(model, args.iters, args.timeout, args.verbose)
         path_save += ".irm"
@@ -151,7 +151,7 @@ def main(argv=None):
             model.incorporate(r, items, v)
     else:
         print("loading clusters from %s" % args.load)
-        model = util_io.from_txt_hirm(HIRM({}, prng=prng), path_schema, path_obs, args.load)
+        model = util_io.from_txt_hirm(path_schema, path_obs, args.load, prng=prng)
     print("inferring %d iters; timeout %d" % (args.iters, args.timeout))
     inference_hirm(model, args.iters, args.timeout, args.verbose)
     path_save += ".hirm"

@@ -12,8 +12,13 @@ What runs where
   * crp.tables / crp.assignments / relation.clusters are read-back views, refreshed lazily.
   * HIRM (src/hirm.py:457-571) keeps the relation CRP on the host and gets every candidate table's data term
     from the device (hirm_engine_relation_scores).
-Out of scope: IRM.logp / HIRM.logp (predictive), plotting.
+  * Relation.logp / IRM.logp / HIRM.logp (predictive queries, src/hirm.py:310-350,428-430,553-562,573-628) are small host
+    enumerations over the read-back count tables: off the hot path, kept so that the reference's own tests and
+    examples run on the facade.
+Out of scope: plotting.
 """
+import itertools
+import math
 import random
 
 import numpy as np
@@ -30,13 +35,27 @@ def default_engine(device=-1):
 
 
 class BetaBernoulli:
-    """Read-back view of one count-table cell (src/hirm.py:17-53)."""
+    """Read-back view of one count-table cell (src/hirm.py:17-53): alpha, beta, N, s and the two closed forms."""
 
-    def __init__(self, N=0, s=0):
-        self.alpha, self.beta, self.N, self.s = 1, 1, int(N), int(s)
+    def __init__(self, alpha=1, beta=1, prng=None, N=0, s=0):
+        self.alpha, self.beta, self.N, self.s = alpha, beta, int(N), int(s)
+        self.prng = prng or random
+
+    def logp(self, x):
+        """Predictive log-probability of one more observation (src/hirm.py:35-42); -inf for a value outside {0, 1}."""
+        if x not in (0, 1):
+            return -math.inf
+        num = self.s + self.alpha if x == 1 else self.N - self.s + self.beta
+        return math.log(num) - math.log(self.N + self.alpha + self.beta)
+
+    def logp_score(self):
+        """log marginal likelihood of the cell (src/hirm.py:43-46): lbeta(s + alpha, N - s + beta) - lbeta(alpha, beta)."""
+        def lbeta(a, b):
+            return math.lgamma(a) + math.lgamma(b) - math.lgamma(a + b)
+        return lbeta(self.s + self.alpha, self.N - self.s + self.beta) - lbeta(self.alpha, self.beta)
 
     def __repr__(self):
-        return "BetaBernoulli(N=%d, s=%d)" % (self.N, self.s)
+        return "BetaBernoulli(alpha=%f, beta=%f, N=%d, s=%d)" % (self.alpha, self.beta, self.N, self.s)
 
 
 class CRP:
@@ -72,6 +91,31 @@ class CRP:
 
     def transition_alpha(self):
         self._d._irm.transition_crp_alphas([self._d.name])
+
+    def tables_weights(self):
+        """{table: customers} plus the fresh table max + 1 at weight alpha (src/hirm.py:95-100)."""
+        if self.N == 0:
+            return {0: 1}
+        w = {t: len(c) for t, c in self.tables.items()}
+        w[max(w) + 1] = self.alpha
+        return w
+
+    def tables_weights_gibbs(self, table):
+        """The same with one customer of `table` removed; a singleton keeps its table at weight alpha and no fresh table
+        is offered (src/hirm.py:101-108)."""
+        assert 0 < self.N
+        w = self.tables_weights()
+        w[table] -= 1
+        if w[table] == 0:
+            w[table] = self.alpha
+            del w[max(w)]
+        return w
+
+    def logp_score(self):
+        """src/hirm.py:92-99."""
+        sizes = [len(c) for c in self.tables.values()]
+        return (len(sizes) * math.log(self.alpha) + sum(math.lgamma(c) for c in sizes) + math.lgamma(self.alpha)
+                - math.lgamma(self.N + self.alpha))
 
 
 class CodeSpace:
@@ -140,6 +184,21 @@ class Domain:
         self._irm._pull()
         return self._z[item]
 
+    def tables_weights(self):
+        return self.crp.tables_weights()
+
+    def tables_weights_gibbs(self, item):
+        return self.crp.tables_weights_gibbs(self.get_cluster_assignment(item))
+
+    def _fresh_options(self, item):
+        """(tables, log-weights) an entity can sit at in a predictive query: its own table if it is seated, else every
+        table and the fresh one with weight / (1 + N) (src/hirm.py:322-333,589-599)."""
+        if item in self.items:
+            return (self.get_cluster_assignment(item),), (0.0,)
+        w = self.tables_weights()
+        z = math.log(1 + self.crp.N)
+        return tuple(w), tuple(math.log(v) - z for v in w.values())
+
     def __repr__(self):
         return "Domain(name=%r)" % (self.name,)
 
@@ -176,11 +235,31 @@ class Relation:
         irm._push()
         cells = irm._eng.get_counts(irm._h, irm._rindex[self.name])
         a = len(self.domains)
-        return {tuple(int(x) for x in c[:a]): BetaBernoulli(c[a], c[a + 1]) for c in cells}
+        return {tuple(int(x) for x in c[:a]): BetaBernoulli(N=c[a], s=c[a + 1]) for c in cells}
 
     def logp_score(self):
         from math import lgamma
         return sum(lgamma(c.s + 1) + lgamma(c.N - c.s + 1) - lgamma(c.N + 2) for c in self.clusters.values())
+
+    def get_cluster_assignment(self, items):
+        return tuple(d.get_cluster_assignment(i) for d, i in zip(self.domains, items))
+
+    def logp(self, items, value):
+        """Predictive log-probability of one observation (src/hirm.py:310-350): unseen entities are summed out over the
+        tables of their domain and one fresh table, position by position."""
+        assert len(items) == len(self.domains)
+        options = [d._fresh_options(i) for d, i in zip(self.domains, items)]
+        cells = self.clusters
+        empty = BetaBernoulli()
+        terms = []
+        for pick in itertools.product(*[range(len(t)) for t, _ in options]):
+            z = tuple(options[p][0][k] for p, k in enumerate(pick))
+            terms.append(sum(options[p][1][k] for p, k in enumerate(pick)) + cells.get(z, empty).logp(value))
+        from .util_math import logsumexp
+        return logsumexp(terms)
+
+    def __repr__(self):
+        return "Relation(name=%s, domains=%r)" % (self.name, self.domains)
 
 
 class IRM:
@@ -199,6 +278,7 @@ class IRM:
         self._stale = False         # device assignments changed since the last read-back
         self._seed = None
         self._moves = 0
+        self._sweeps = self._alpha_moves = 0   # Philox positions of the device sweep order / alpha moves: they survive a re-upload
         for relation, domains in schema.items():
             self.add_relation(relation, domains)
 
@@ -297,6 +377,9 @@ class IRM:
         if self._seed is None:
             self._seed = self.prng.getrandbits(62)
         self._eng.set_rng(self._h, self._seed & 0xFFFFFFFF, self._moves)
+        # a re-created engine IRM starts its sweep / alpha counters at 0: carry the mirror's on, or the next alpha move
+        # and sweep order would reuse the variates of the first ones
+        self._eng.set_rng_counters(self._h, self._sweeps, self._alpha_moves)
         self._dirty = False
 
     def _dense_candidate(self):
@@ -316,6 +399,7 @@ class IRM:
             domains = list(self._dorder)                         # some codes are not seated here: explicit lists
         if domains is None:
             self._moves += self._eng.sweep_all([self._h], n_sweeps=1, seed=self._seed)
+            self._sweeps += 1
         else:
             md, mi = [], []
             for d in domains:
@@ -345,6 +429,7 @@ class IRM:
         self._push()
         before = {d: self._eng.get_alpha(self._h, k) for k, d in enumerate(self._dorder)}
         self._eng.transition_alpha([self._h], ngrid=ngrid, seed=self._seed)
+        self._alpha_moves += 1
         for k, d in enumerate(self._dorder):
             if domains is not None and d not in domains:
                 self._eng.set_alpha(self._h, k, before[d])
@@ -355,7 +440,35 @@ class IRM:
         return float(self._eng.logp_scores([self._h])[0])
 
     def logp(self, observations):
-        raise NotImplementedError("predictive queries are outside the engine's scope (SURVEY.md section 2)")
+        """Joint predictive log-probability of (relation name, items, value) triples (src/hirm.py:428-430)."""
+        return logp_observations([(self.relations[r], tuple(i), v) for r, i, v in observations])
+
+
+def logp_observations(observations):
+    """src/hirm.py:573-628: log p of a list of (Relation, items, value) given the current state.  Every distinct unseen
+    (domain, entity) is one latent seat ranging over the domain's tables and a fresh one (weight / (1 + N)); the sum over
+    all seatings is enumerated on the host from the read-back count tables."""
+    from .util_math import logsumexp
+    seats, cells, seen = {}, {}, set()
+    for rel, items, value in observations:
+        assert (rel.name, items) not in seen
+        seen.add((rel.name, items))
+        assert len(items) == len(rel.domains)
+        for d, it in zip(rel.domains, items):
+            seats.setdefault((d.name, it), d._fresh_options(it))
+        if rel.name not in cells:
+            cells[rel.name] = rel.clusters
+    keys = list(seats)
+    empty = BetaBernoulli()
+    terms = []
+    for pick in itertools.product(*[range(len(seats[k][0])) for k in keys]):
+        at = {k: seats[k][0][j] for k, j in zip(keys, pick)}
+        lp = sum(seats[k][1][j] for k, j in zip(keys, pick))
+        for rel, items, value in observations:
+            z = tuple(at[(d.name, it)] for d, it in zip(rel.domains, items))
+            lp += cells[rel.name].get(z, empty).logp(value)
+        terms.append(lp)
+    return logsumexp(terms)
 
 
 def choose_index(logps, u):
@@ -487,6 +600,27 @@ class HIRM:
     def get_relation(self, r):
         return self.relation_to_irm(r).relations[r]
 
+    relation = get_relation                                  # src/hirm.py:476-478 names it `relation`
+
+    def transition_crp_alpha(self):
+        """CRP.transition_alpha of the relation CRP (src/hirm.py:544-545): 30-point grid, drawn with the caller's prng."""
+        from .util_math import log_choices, log_linspace
+        n = self.crp.N
+        grid = log_linspace(1 / n, n + 1, 30)
+        keep, lps = self.crp.alpha, []
+        for g in grid:
+            self.crp.alpha = g
+            lps.append(self.crp.logp_score())
+        self.crp.alpha = keep
+        self.crp.alpha = log_choices(grid, lps, prng=self.prng)[0]
+
+    def logp(self, observations):
+        """src/hirm.py:553-562: the observations of every relation cluster are scored by its IRM."""
+        by_table = {}
+        for r, items, v in observations:
+            by_table.setdefault(self.crp.assignments[r], []).append((r, items, v))
+        return sum(self.irms[t].logp(obs) for t, obs in by_table.items())
+
     # ---- inference ---------------------------------------------------------------------------
     def transition_cluster_assignments(self, rs=None):
         """Relation moves (src/hirm.py:479-481): every relation once, in a prng-shuffled order."""
@@ -589,12 +723,14 @@ class HIRM:
                 self._eng.sweep_all([irm._h for irm in batch], n_sweeps=1, seed=seed)
                 for irm in batch:
                     irm._moves += sum(irm._n_ent)
+                    irm._sweeps += 1
                     irm._stale = True
             for irm in irms:
                 if irm not in batch:
                     irm.transition_cluster_assignments()
             self._eng.transition_alpha([irm._h for irm in irms], ngrid=ngrid, seed=irms[0]._seed)
             for irm in irms:
+                irm._alpha_moves += 1
                 irm._stale = True
 
     def logp_score(self):

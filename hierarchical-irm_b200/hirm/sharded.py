@@ -100,6 +100,9 @@ class EngineBackend:
             raise E.EngineError("no CUDA device: the engine has no CPU fallback")
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.eng = engine or E.Engine(self.device)
+        # the engine caches bit vectors of unary relations by COO buffer address: a reused engine may hold those of buffers
+        # torch has freed and handed out again
+        self.eng.clear_relation_cache()
         self.n_entities, self.rel_domains = [int(n) for n in n_entities], [list(map(int, ds)) for ds in rel_domains]
         self.max_tables, self.seed, self.host_order = int(max_tables), int(seed), host_order
         dev = torch.device("cuda", self.device)
@@ -225,6 +228,7 @@ class ShardedHIRM:
         self.chain = int(chain)                            # independent seeded chains: disjoint Philox streams and keys
         self._next_uid, self._next_key, self.iteration = self.chain << 24, (1 << 60) | (self.chain << 44), 0
         self.timers = dict(entity=0.0, score=0.0, gather=0.0, reseat=0.0, rebuild=0.0)
+        self.stats = dict(relations_moved=0, fresh_irms=0, irms_deleted=0, irms_rebuilt=0, irms_migrated=0)
         R = len(self.rnames)
         rng = np.random.default_rng([self.seed, self.chain, 0x696E6974])
         if relation_tables is None:                        # HIRM::add_relation (:947-957): sequential CRP(alpha) seating
@@ -328,6 +332,7 @@ class ShardedHIRM:
             load = self.loads()
             own = min(range(self.comm.world), key=lambda k: (load[k], k))
             info = self.irms[choice] = dict(uid=self._take_uid(), owner=own, rels=set(), handle=None, steps=0, changed=True)
+            self.stats["fresh_irms"] += 1
             latent = [self._take_key() for _ in self.dnames]          # domains the relation does not use: prior draws all the same
             col = np.zeros(len(self.rnames))
             if own == self.comm.rank:
@@ -351,6 +356,7 @@ class ShardedHIRM:
                 self.backend.destroy_irm(src["handle"])
             del self.irms[cur]
             cols.pop(cur, None)
+            self.stats["irms_deleted"] += 1
 
     def transition_relations(self, scored=None):
         """One sweep of relation moves: every relation once, in a seeded order.  `scored`: the (columns, fresh scores,
@@ -369,6 +375,7 @@ class ShardedHIRM:
             moved += int(choice != self.rel_table[r])
             self.apply_relation_choice(r, choice, cols, keys=keys)
         t1 = time.perf_counter()
+        self.stats["relations_moved"] += moved
         self.materialize()
         self.timers["reseat"] += t1 - t0
         self.timers["rebuild"] += time.perf_counter() - t1
@@ -392,6 +399,8 @@ class ShardedHIRM:
             old, new = info["owner"], new_owner[t]
             if not info["changed"] and old == new:
                 continue
+            self.stats["irms_rebuilt"] += 1
+            self.stats["irms_migrated"] += int(old != new)
             state = None
             if old == self.comm.rank:
                 state = self.backend.get_state(info["handle"])
@@ -417,7 +426,9 @@ class ShardedHIRM:
                 - math.lgamma(n + self.alpha))
 
     def logp_score(self):
-        """HIRM::logp_score (cxx/hirm.hh:998-1005); per-IRM scores gathered and summed in table order on every rank."""
+        """HIRM::logp_score (cxx/hirm.hh:998-1005); per-IRM scores gathered and summed in table order on every rank.
+        An IRM's score holds the CRP term of the domains its relations use, as the reference's does (its IRMs hold no
+        other domain); the partitions this model keeps of the remaining domains are latent prior draws and add nothing."""
         local = self._local()
         sc = self.backend.logp_scores([self.irms[t]["handle"] for t in local])
         merged = {}

@@ -438,6 +438,11 @@ int64_t hirm_oracle_get_counts(hirm_oracle *o, int rel, int32_t *out, int64_t ca
 double hirm_oracle_logp_score(hirm_oracle *o) {
     double crp = 0;
     for (int d = 0; d < o->n_domains; d++) {
+        /* only the domains some relation uses: the reference's IRM holds no other (cxx/hirm.hh:742-782) */
+        int used = 0;
+        for (int r = 0; r < o->n_relations; r++)
+            for (int p = 0; p < o->rel[r].arity; p++) used |= o->rel[r].dom[p] == d;
+        if (!used) continue;
         int N = 0;
         for (int k = 0; k < o->n_tab[d]; k++) N += o->tab_count[d][k];
         if (N == 0) continue;

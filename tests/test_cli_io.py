@@ -45,7 +45,7 @@ def test_parsers_and_irm_writer_roundtrip(tmp_path):
     for d, dom in irm.domains.items():
         got = {t: set(items) for t, items in clusters[d].items()}
         assert got == {t: {str(i) for i in members} for t, members in dom.crp.tables.items()}
-    again = util_io.from_txt_irm(IRM({}, prng=random.Random(3)), base + ".schema", base + ".obs", path)
+    again = util_io.from_txt_irm(base + ".schema", base + ".obs", path, prng=random.Random(3))
     for d in irm.domains:                               # check_irms_agree, tests/test_basic.py:96-103
         assert again.domains[d].crp.assignments == irm.domains[d].crp.assignments
     for r in irm.relations:
@@ -121,7 +121,8 @@ def test_native_reader_matches_reference_encoding(tmp_path):
     d3, _, o3, n3 = E.load_dataset(str(base) + ".schema", str(tmp_path / "ws.obs"))
     assert d3 == {"person": 1, "item": 1} and n3 == {"person": ["ann"], "item": ["tea"]} and o3["tall"][1].tolist() == [0]
     assert o3["knows"][0].shape == (0, 2)
-    for text, needle in (("1 likes ann\n", "too few"), ("1 tall ann bob\n", "too many"), ("1 hates ann\n", "unknown relation")):
+    for text, needle in (("1 likes ann\n", "too few"), ("1 tall ann bob\n", "too many"), ("1 hates ann\n", "unknown relation"),
+                         ("1 tall ann\n", "listed twice")):
         (tmp_path / "e.obs").write_text("0 tall ann\n" + text)
         try:
             E.load_dataset(str(base) + ".schema", str(tmp_path / "e.obs"))

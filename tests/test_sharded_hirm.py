@@ -72,6 +72,41 @@ def test_oracle_backend_single_rank_invariants_and_recovery():
     assert h.comm.n_allgather == 6                                        # ONE all-gather per relation sweep
 
 
+def test_multi_domain_logp_score_counts_used_domains_only():
+    """HIRM::logp_score (cxx/hirm.hh:998-1005) on a schema with three domains where most relation clusters use only some
+    of them: the CRP term of an IRM covers the domains its relations use (the reference's IRM holds no other domain,
+    cxx/hirm.hh:742-782), checked against an independent numpy evaluation of the whole score."""
+    import math
+    rng = np.random.default_rng(0)
+    domains = {"a": 14, "b": 11, "c": 9}
+    schema = {"ua": ["a"], "ub": ["b"], "uc": ["c"], "ab": ["a", "b"], "cc": ["c", "c"], "abc": ["a", "b", "c"]}
+    obs = {}
+    for r, ds in schema.items():
+        grid = np.stack(np.meshgrid(*[np.arange(domains[d]) for d in ds], indexing="ij"), -1).reshape(-1, len(ds))
+        keep = grid[rng.random(len(grid)) < (1.0 if len(ds) == 1 else 0.5)].astype(np.int32)
+        obs[r] = (keep, rng.integers(0, 2, len(keep)).astype(np.uint8))
+    names, dn = list(schema), list(domains)
+    backend = SU.OracleBackend([domains[d] for d in dn], [[dn.index(d) for d in schema[r]] for r in names], [obs[r] for r in names], 16, 1)
+    h = ShardedHIRM(domains, schema, obs, seed=1, max_tables=16, backend=backend,
+                    relation_tables={"ua": 0, "ab": 0, "ub": 1, "uc": 2, "cc": 2, "abc": 3})
+    for it in range(3):
+        if it:
+            h.iterate(1)
+        st = h.state()
+        want = h.crp_logp_score()
+        for t, info in st.items():
+            used = {d for r in info["relations"] for d in schema[r]}
+            assert it or len(used) < 3 or t == 3
+            for d in used:
+                sizes = np.bincount(np.unique(info["z"][d], return_inverse=True)[1])
+                al = info["alpha"][d]
+                want += len(sizes) * math.log(al) + sum(math.lgamma(c) for c in sizes) + math.lgamma(al) - math.lgamma(sizes.sum() + al)
+            for r in info["relations"]:
+                want += SU.relation_score_numpy(*obs[r], [info["z"][d] for d in schema[r]])
+        got = h.logp_score()
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (it, got, want)
+
+
 def test_chain_set_equals_stand_alone_chains():
     """ChainSet batches the entity sweeps of several chains; every chain walks the trajectory it walks alone."""
     from hirm.sharded import ChainSet
@@ -104,7 +139,7 @@ def _gloo_worker(rank, world, port, out, iters, gen):
     owners = sorted({info["owner"] for info in h.irms.values()})
     dist.barrier()
     if rank == 0:
-        out.put((trail, owners, h.comm.n_allgather, h.comm.n_broadcast))
+        out.put((trail, owners, h.comm.n_allgather, h.comm.n_broadcast, dict(h.stats)))
     dist.destroy_process_group()
 
 
@@ -123,9 +158,13 @@ def test_two_ranks_gloo_match_one_rank():
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    trail, owners, n_ag, n_bc = q.get()
+    trail, owners, n_ag, n_bc, stats = q.get()
     _same_trail(ref, trail)
     assert n_ag == iters
+    # the exchange step really happened: relations changed tables, a fresh IRM was opened (one broadcast each), IRMs were
+    # rebuilt on their owner and at least one migrated between the ranks
+    assert stats["relations_moved"] > 0 and stats["fresh_irms"] > 0 and n_bc >= stats["fresh_irms"]
+    assert stats["irms_rebuilt"] > 0 and stats["irms_migrated"] > 0, stats
     assert owners == [0, 1] or len(trail[-1][1]) == 1                      # IRMs spread over both ranks
 
 
@@ -329,7 +368,7 @@ def _nccl_worker(rank, world, port, out, iters, gen):
     owners = sorted({info["owner"] for info in h.irms.values()})
     dist.barrier()
     if rank == 0:
-        out.put((trail, owners))
+        out.put((trail, owners, dict(h.stats), h.comm.n_broadcast))
     dist.destroy_process_group()
 
 
@@ -351,5 +390,9 @@ def test_two_gpus_nccl_match_one_gpu():
     for p in procs:
         p.join(600)
         assert p.exitcode == 0
-    trail, owners = q.get()
+    trail, owners, stats, n_bc = q.get()
     _same_trail(ref, trail, rtol=1e-9)
+    # not a planted start: relations move, fresh IRMs are opened (broadcast of their score column), IRMs are rebuilt from the
+    # replicated COO arrays and migrate between the GPUs
+    assert stats["relations_moved"] > 0 and stats["fresh_irms"] > 0 and n_bc >= stats["fresh_irms"], stats
+    assert stats["irms_rebuilt"] > 0 and stats["irms_migrated"] > 0, stats
