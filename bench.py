@@ -47,6 +47,11 @@ def parse():
     ap.add_argument("--ref-n", type=int, default=1000, help="entities of the reference arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--burn-in", type=int, default=3, help="untimed sweeps from the CRP-prior start before the warm-up steps (state preparation)")
+    ap.add_argument("--extra", default="c4,c5", help="further BASELINE configs measured into config.extra_workloads: comma list of c4, c5, ksweep; 'none' to skip")
+    ap.add_argument("--c4-chains", type=int, default=0)
+    ap.add_argument("--c4-moves", type=int, default=0, help="moves per domain per chain per step of the C4 record")
+    ap.add_argument("--c5-chains", type=int, default=8)
+    ap.add_argument("--c5-scale", type=float, default=1.0, help="scale factor on C5's entities / relations (1.0 = the stated size)")
     return ap.parse_args()
 
 
@@ -240,8 +245,8 @@ def main_b200(args, rank, world, local_rank):
     from hirm import shard
     stream_ids = shard.chain_streams(world * chains, rank, world)          # global chain index = Philox stream, whatever N
     for c, h in enumerate(hs):
-        eng.set_assignments(h, 0, crp_prior_labels_fast(n, 1.0, rng))     # Domain::incorporate: sequential CRP(1) prior draw
         eng.set_rng(h, stream_ids[c], 0)
+    eng.seat_prior(hs, seed=args.seed)            # Domain::incorporate: one sequential CRP(1) prior draw per chain, made on the device
     k0 = [len(np.unique(eng.get_assignments(h, 0))) for h in hs[:8]]
     eng.logp_scores(hs)                           # forces every chain's count-table build
     build_s = time.perf_counter() - t0
@@ -321,9 +326,14 @@ def main_b200(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
+            # NOT measured in this run: DRAM bytes per move of an earlier `ncu --set full` capture of the same kernel
+            # (profiles/traffic.json) times this launch's move count
             tj = json.load(open(tpath))
             roofline["traffic"] = tj.get("dram_bytes_per_move", 0) * moves_per_gpu_step or None
-            roofline["traffic_source"] = tj.get("source")
+            roofline["traffic_source"] = "extrapolated from " + str(tj.get("source"))
+            if roofline["traffic"]:
+                roofline["dram_gbs_from_traffic"] = roofline["traffic"] / (launch_ms * 1e-3) / 1e9
+                roofline["dram_frac_from_traffic"] = roofline["dram_gbs_from_traffic"] / peak
         except Exception:
             pass
 
@@ -365,6 +375,38 @@ def main_b200(args, rank, world, local_rank):
     lists_s = time.perf_counter() - t0
 
     ktabs = [len(np.unique(eng.get_assignments(h, 0))) for h in hs[:8]]
+    for h in hs:
+        eng.irm_destroy(h)
+    del d_items, d_dom, x_host
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, each with its own roofline record (bench_workloads.py) ------------------------------
+    extra = {}
+    want = [w for w in args.extra.split(",") if w and w != "none"]
+
+    def sync_max(x):
+        torch.cuda.synchronize()
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    import bench_workloads as W
+    if "c4" in want:
+        rec = W.bench_c4(eng, dev, peak, chains=args.c4_chains, moves_per_domain=args.c4_moves, steps=max(1, min(args.steps, 2)), warmup=1,
+                         seed=args.seed, world=world, rank=rank, barrier=barrier)
+        ms = sync_max(rec["ms_per_step"])                     # replicas: the job's step ends with the slowest rank
+        rec["n_gpus"], rec["scaling"] = world, "weak"
+        rec["value"] = world * rec["chains_per_gpu"] * rec["moves_per_chain_per_step"] / (ms * 1e-3)
+        extra["c4"] = rec
+    if "c5" in want:
+        from hirm.sharded import Comm
+        sc = args.c5_scale
+        rec = W.bench_c5(dev, peak, Comm(), chains=args.c5_chains, steps=max(1, min(args.steps, 2)), warmup=1,
+                         n=int(200_000 * sc), n_unary=int(2000 * sc), n_binary=max(1, int(50 * sc)), bobs=int(10_000_000 * sc),
+                         seed=args.seed, barrier=barrier, sync_max=sync_max)
+        extra["c5"] = rec
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline, _ = run_reference(args.ref_n, 1, 1, per_round_s=8.0)
@@ -384,14 +426,14 @@ def main_b200(args, rank, world, local_rank):
                            "parallelism": "%d independent chains per GPU (%d per SM), replicas across GPUs (no collective)" % (chains, plan["ctas_per_sm"]),
                            "sweeps_per_s": value / n, "ingest_s": ingest_s, "state_build_s": build_s,
                            "kernel_kind": info["kernel_kind"], "dense_plan": plan,
-                           "explicit_move_lists_moves_per_s": moves_per_gpu_step / lists_s},
+                           "explicit_move_lists_moves_per_s": moves_per_gpu_step / lists_s,
+                           "extra_workloads": extra},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
                 "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
     return 0
 
 

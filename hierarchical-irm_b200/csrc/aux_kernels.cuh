@@ -358,6 +358,27 @@ __global__ void __launch_bounds__(PRIOR_THREADS) crp_prior_kernel(const PriorDra
     }
 }
 
+// CRP state of a domain from its slot array: customers per slot, label = slot, highest used slot + 1 -- after a device-side
+// prior draw (hirm_engine_seat_prior).  One CTA per (irm, domain) pair listed in `pairs` (irm id, domain).
+__global__ void __launch_bounds__(256) tables_from_slots_kernel(const IrmDev *irms, const int32_t *pairs) {
+    const IrmDev &irm = irms[pairs[2 * blockIdx.x]];
+    const DomainDev &dd = irm.dom[pairs[2 * blockIdx.x + 1]];
+    __shared__ int32_t s_cnt[256];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < dd.n; i += blockDim.x) { const int zi = dd.z[i]; if (zi >= 0) atomicAdd(&s_cnt[zi], 1); }
+    __syncthreads();
+    int hi = 0;
+    for (int k = threadIdx.x; k < dd.kcap; k += blockDim.x) { dd.tab_count[k] = s_cnt[k]; dd.tab_label[k] = k; if (s_cnt[k] > 0) hi = k + 1; }
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    __shared__ int32_t s_hi;
+    if (threadIdx.x == 0) s_hi = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_hi, hi);
+    __syncthreads();
+    if (threadIdx.x == 0) *dd.hi = s_hi;
+}
+
 // ---------------------------------------------------------------------------------------
 // Per-entity CSR build on the device (Relation::data_r, cxx/hirm.hh:251,274-280): count, scan, fill.  An observation
 // is listed once per entity even if the entity sits at two positions of it (set semantics of data_r).  The order of

@@ -116,7 +116,7 @@ struct hirm_engine {
     DevBuf<unsigned char> s_job[6]; DevBuf<int32_t> s_prior;   // relation-score jobs: descriptors, fresh partitions
     // unary relations as bit vectors over the entity codes (observed, value), built once per COO buffer
     struct UnaryBits { DevBuf<uint32_t> obs, val; int64_t nobs = 0; int32_t n_ent = 0; const uint8_t *val_src = nullptr; };
-    std::map<const int32_t *, UnaryBits> unary_cache;
+    std::map<std::pair<const int32_t *, const uint8_t *>, UnaryBits> unary_cache;   // keyed by the (ids, val) buffers: relations may share an ids buffer
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
     int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0, dense_static_smem = 0, dense_static_smem_large = 0;
@@ -959,7 +959,7 @@ extern "C" int hirm_engine_relation_score_matrix(hirm_engine *e, int n_rel, cons
         const RelDesc &R = J.rels[(size_t)r];
         if (use_unary && R.arity == 1 && R.nobs > 0) {   // unary relation: bit vectors, no histogram (relmat_unary_kernel)
             const int d = R.dom[0], n_ent = C0->n_ent[d];
-            auto &U = e->unary_cache[R.ids];
+            auto &U = e->unary_cache[std::make_pair(R.ids, R.val)];
             if (U.nobs != R.nobs || U.n_ent != n_ent || U.val_src != R.val) {
                 const size_t nw = (size_t)((n_ent + 31) / 32) + UN_TILE;   // zero padding: the kernel reads whole words only
                 CK(U.obs.alloc(nw)); CK(U.val.alloc(nw));
@@ -1072,6 +1072,49 @@ extern "C" int hirm_engine_crp_prior_draw(hirm_engine *e, int n, double alpha, i
     D.z = e->s_prior.p; D.cum = e->s_prior.p + n; D.n = n; D.kcap = max_tables; D.key = key; D.alpha = alpha;
     if (launch_prior_draws(e, std::vector<PriorDraw>{D}, seed)) return -1;
     CK(cudaMemcpy(h_labels, e->s_prior.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Initial seating of whole domains on the device: what Domain::incorporate does to every entity of a new model, one
+// sequential CRP(alpha) prior draw per (irm, domain) (cxx/hirm.hh:194-203 with CRP::sample :101-113) -- the law of the seats
+// the reference's `incorporate` loop produces, drawn by crp_prior_kernel from Philox stream (irm's stream, domain) instead
+// of one `choice()` per entity.  Replaces a host loop of hirm_irm_set_assignments calls when many chains start.
+extern "C" int hirm_engine_seat_prior(hirm_engine *e, int n_irms, const int32_t *h_irms, uint64_t seed) {
+    if (!e) return fail("engine is null");
+    CK(cudaSetDevice(e->device));
+    if (n_irms <= 0) return 0;
+    if (!h_irms) return fail("null argument");
+    std::vector<PriorDraw> draws;
+    std::vector<int32_t> pairs;
+    int64_t slots = 0;
+    for (int k = 0; k < n_irms; k++) {
+        Irm *irm = get_irm(e, h_irms[k]);
+        if (!irm) return fail("bad irm id");
+        for (int d = 0; d < irm->n_domains; d++) slots += irm->n_ent[d];
+    }
+    CK(e->s_prior.ensure((size_t)std::max<int64_t>(slots, 1)));
+    int64_t off = 0;
+    for (int k = 0; k < n_irms; k++) {
+        Irm *irm = e->irms[h_irms[k]].get();
+        if (finalize_store(e, irm) || ensure_scratch(e, irm)) return -1;
+        for (int d = 0; d < irm->n_domains; d++) {
+            PriorDraw D;
+            D.z = irm->z[d].p; D.cum = e->s_prior.p + off; D.n = irm->n_ent[d]; D.kcap = irm->kcap[d];
+            D.key = (irm->rng_stream << 3) | (uint64_t)d; D.alpha = irm->alpha[d];
+            off += irm->n_ent[d];
+            if (D.n > 0) draws.push_back(D);
+            pairs.push_back(h_irms[k]); pairs.push_back(d);
+            irm->have_z[d] = true; irm->has_absent[d] = false;
+        }
+        irm->counts_dirty = true;
+        if (upload_desc(e, h_irms[k])) return -1;
+    }
+    if (launch_prior_draws(e, draws, seed)) return -1;
+    CK(e->s_blk.ensure(pairs.size()));
+    CK(cudaMemcpyAsync(e->s_blk.p, pairs.data(), pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    tables_from_slots_kernel<<<(unsigned)(pairs.size() / 2), 256, 0, e->stream>>>(e->d_irms.p, e->s_blk.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
 

@@ -34,6 +34,7 @@ EXPORTS = [
     "hirm_engine_relation_scores", "hirm_irm_seat_entities", "hirm_engine_debug_score_delta",
     "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
     "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters", "hirm_engine_clear_relation_cache",
+    "hirm_engine_seat_prior",
     "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
     "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
 ]
@@ -102,6 +103,7 @@ def load():
     L.hirm_engine_relation_scores_fresh.argtypes = [V, I, c_i32p, c_i32p, c_i64p, VP, VP, I, c_i32p, c_i32p, ctypes.c_double,
                                                     ctypes.c_uint64, c_u64p, c_f64p]
     L.hirm_engine_clear_relation_cache.argtypes = [V]
+    L.hirm_engine_seat_prior.argtypes = [V, I, c_i32p, ctypes.c_uint64]
     L.hirm_irm_set_rng_counters.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
     L.hirm_engine_crp_prior_draw.argtypes = [V, I, ctypes.c_double, I, ctypes.c_uint64, ctypes.c_uint64, c_i32p]
     CP = ctypes.POINTER(ctypes.c_char_p)
@@ -239,6 +241,11 @@ class Engine:
         labels = np.ascontiguousarray(labels, dtype=np.int32)
         assert len(labels) == self._schemas[irm][0][dom]
         self._ck(self.L.hirm_irm_set_assignments(self._h, irm, dom, _p(labels, c_i32p)))
+
+    def seat_prior(self, irms, seed=0):
+        """Seat every entity of every domain of the listed IRMs by sequential CRP(alpha) prior draws made on the device."""
+        irms = np.ascontiguousarray(irms, dtype=np.int32)
+        self._ck(self.L.hirm_engine_seat_prior(self._h, len(irms), _p(irms, c_i32p), int(seed)))
 
     def get_assignments(self, irm, dom):
         out = np.empty(max(1, self._schemas[irm][0][dom]), dtype=np.int32)

@@ -108,14 +108,21 @@ class EngineBackend:
         dev = torch.device("cuda", self.device)
         self._buf, self.rels = [], []
         for ds, (ids, val) in zip(self.rel_domains, observations):
-            ids = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1, len(ds))
-            val = np.ascontiguousarray(val, dtype=np.uint8)
-            assert len(ids) == len(val)
-            if len(val) and (val.max() > 1 or ids.min() < 0 or np.any(ids.max(axis=0) >= np.asarray([self.n_entities[d] for d in ds]))):
-                raise ValueError("observation values must be 0 or 1 and entity codes in range")
-            t_ids, t_val = torch.from_numpy(ids.reshape(-1)).to(dev), torch.from_numpy(val).to(dev)
+            if torch.is_tensor(ids):
+                # COO arrays already in this GPU's memory (int32 [nobs * arity] / uint8 [nobs], contiguous): used in place,
+                # relations may share an ids buffer; hirm_irm_set_observations_device validates codes and values
+                t_ids, t_val = ids.reshape(-1), val
+                assert t_ids.is_cuda and t_ids.dtype == torch.int32 and t_val.dtype == torch.uint8 and t_ids.is_contiguous()
+                assert t_ids.numel() == t_val.numel() * len(ds)
+            else:
+                ids = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1, len(ds))
+                val = np.ascontiguousarray(val, dtype=np.uint8)
+                assert len(ids) == len(val)
+                if len(val) and (val.max() > 1 or ids.min() < 0 or np.any(ids.max(axis=0) >= np.asarray([self.n_entities[d] for d in ds]))):
+                    raise ValueError("observation values must be 0 or 1 and entity codes in range")
+                t_ids, t_val = torch.from_numpy(ids.reshape(-1)).to(dev), torch.from_numpy(val).to(dev)
             self._buf.append((t_ids, t_val))
-            self.rels.append((ds, len(val), t_ids.data_ptr() if len(val) else None, t_val.data_ptr() if len(val) else None))
+            self.rels.append((ds, int(t_val.numel()), t_ids.data_ptr() if t_val.numel() else None, t_val.data_ptr() if t_val.numel() else None))
         self._meta = {}
 
     # -- IRMs -----------------------------------------------------------------------------------

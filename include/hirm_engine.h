@@ -90,6 +90,10 @@ int hirm_irm_finalize(hirm_engine *e, int32_t irm);
  * The count tables (Relation::clusters, cxx/hirm.hh:246) are rebuilt from (observations, z) on the
  * device at the next use: they are a histogram (cxx/hirm.hh:281-289). */
 int hirm_irm_set_assignments(hirm_engine *e, int32_t irm, int dom, const int32_t *h_labels);
+/* Domain::incorporate for every entity of every domain of the listed IRMs, seats drawn on the device: one sequential
+ * CRP(alpha) prior draw per (irm, domain) (cxx/hirm.hh:194-203 + CRP::sample :101-113), Philox stream = (the irm's stream
+ * (hirm_irm_set_rng) << 3) | domain.  The initial state the reference's incorporate loop gives a new model. */
+int hirm_engine_seat_prior(hirm_engine *e, int n_irms, const int32_t *h_irms, uint64_t seed);
 /* CRP::assignments read-back (cxx/hirm.hh:75) */
 int hirm_irm_get_assignments(hirm_engine *e, int32_t irm, int dom, int32_t *h_labels);
 /* CRP::alpha (cxx/hirm.hh:72); set by the host after CRP::transition_alpha (:162-173) */
@@ -172,8 +176,9 @@ int hirm_engine_relation_scores(hirm_engine *e, int32_t src_irm, int rel, int n_
 int hirm_engine_relation_score_matrix(hirm_engine *e, int n_rel, const int32_t *h_arity, const int32_t *h_rel_doms,
                                       const int64_t *h_nobs, const int32_t *const *h_d_ids, const uint8_t *const *h_d_val,
                                       int n_cand, const int32_t *h_cand_irms, double *h_out);
-/* Unary relations are scored from bit vectors built once per COO buffer (keyed by h_d_ids[r]); the buffers must stay
- * unchanged while the engine uses them -- call this after freeing or rewriting one. */
+/* Unary relations are scored from bit vectors built once per COO buffer pair (keyed by the addresses h_d_ids[r], h_d_val[r]).
+ * Lifetime rule: such buffers must stay allocated and unchanged while the engine may score them -- call this after freeing
+ * or rewriting one (an allocator may hand the same address to new data), and when an engine is reused for a new dataset. */
 int hirm_engine_clear_relation_cache(hirm_engine *e);
 /* The fresh-table candidate of every listed relation (cxx/hirm.hh:849-864: `new IRM({}, prng)`, whose domains are seated by
  * sequential CRP-prior draws when the relation is incorporated, :194-203): one independent CRP(alpha) draw per (relation,

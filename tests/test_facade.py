@@ -95,3 +95,64 @@ def test_dense_ree_through_the_facade():
     for members in tabs.values():                      # no table mixes the two planted blocks
         assert len({m >= n // 2 for m in members}) == 1, tabs
     assert len(tabs) <= 6 and sum(len(v) for v in tabs.values()) == n
+
+
+@pytest.mark.gpu
+def test_rebuilt_irm_keeps_its_philox_positions():
+    """A facade IRM is re-created on the device whenever the host side changed (later incorporate()s, every accepted
+    relation move of the facade HIRM).  The re-created IRM must continue the sweep-order and alpha-move Philox counters
+    where the old one stopped -- otherwise every alpha move after a rebuild would reuse the first uniform."""
+    schema, d1, d2, data = two_clusters()
+    runs = []
+    for rebuild in (False, True):
+        irm = IRM(schema, prng=random.Random(5))
+        for (i, j), v in data[::3]:
+            irm.incorporate("R1", (i, j), v)
+        trail = []
+        for it in range(4):
+            irm.transition_cluster_assignments()
+            irm.transition_crp_alphas()
+            trail.append((dict(irm.domains["D1"].crp.assignments), irm.domains["D1"].crp.alpha, irm.domains["D2"].crp.alpha))
+            if rebuild:
+                irm._pull()
+                irm._dirty = True                       # what a later incorporate() does: a fresh engine IRM at the next call
+        assert irm._sweeps == 4 and irm._alpha_moves == 4
+        runs.append(trail)
+    assert runs[0] == runs[1]
+    assert len({a for _, a, _ in runs[0]}) > 1          # the alpha moves really draw different grid points
+    # the shared predictive helpers of the reference's tests (tests/test_basic.py:58-94) on the facade
+    from hirm.util_math import logsumexp
+    p0, p1 = irm.relations["R1"].logp((0, 0), 0), irm.relations["R1"].logp((0, 0), 1)
+    assert abs(logsumexp([p0, p1])) < 1e-12
+    assert abs(irm.logp([("R1", (0, 0), 0)]) - p0) < 1e-12
+    four = [irm.logp([("R1", (100, 0), a), ("R1", (100, 1), b)]) for a in (0, 1) for b in (0, 1)]
+    assert abs(logsumexp(four)) < 1e-12
+
+
+@pytest.mark.gpu
+def test_dict_and_txt_serialisers_roundtrip(tmp_path):
+    """tests/test_basic.py:96-147 restated: to_dict_IRM -> (json) -> from_dict_IRM and to_txt_irm -> from_txt_irm give models
+    with the same seats, items and observations, and inference on them recovers the planted blocks."""
+    import json
+    from hirm.util_io import from_dict_IRM, from_txt_irm, to_dict_IRM, to_txt_irm
+    schema, d1, d2, data = two_clusters()
+    prng = random.Random(1)
+    irm = IRM(schema, prng=prng)
+    for (i, j), v in data:
+        irm.incorporate("R1", (i, j), v)
+    dd = to_dict_IRM(irm)
+    (tmp_path / "s.schema").write_text("bernoulli R1 D1 D2\n")
+    (tmp_path / "s.obs").write_text("".join("%d R1 %d %d\n" % (v, i, j) for (i, j), v in data))
+    to_txt_irm(str(tmp_path / "s.irm"), irm)
+    clones = [from_dict_IRM(dd, prng=prng), from_dict_IRM(json.loads(json.dumps(dd)), prng=prng),
+              from_txt_irm(str(tmp_path / "s.schema"), str(tmp_path / "s.obs"), str(tmp_path / "s.irm"))]
+    for x in clones:
+        for d in ("D1", "D2"):
+            assert x.domains[d].crp.assignments == irm.domains[d].crp.assignments
+            assert x.domains[d].crp.tables == irm.domains[d].crp.tables and x.domains[d].items == irm.domains[d].items
+        assert x.relations["R1"].data == irm.relations["R1"].data and x.relations["R1"].data_r == irm.relations["R1"].data_r
+        for _ in range(20):
+            x.transition_cluster_assignments()
+        t1, t2 = x.domains["D1"].crp.tables, x.domains["D2"].crp.tables
+        assert len(t1) == 2 and set(d1[0]) in t1.values() and set(d1[1]) in t1.values()
+        assert set(d2[0]) in t2.values() and set(d2[1]) in t2.values()
