@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(AUX_THREADS) logp_scores_kernel(const IrmDev *
     double acc = 0.0;
     for (int r = 0; r < irm.n_relations; r++) {
         const RelationDev *R = &irm.rel[r];
-        for (int64_t i = threadIdx.x; i < R->ncells; i += blockDim.x) {
-            const cell_t c = R->counts[i];
+        for (int64_t i = threadIdx.x, ne = table_entries(R); i < ne; i += blockDim.x) {
+            const cell_t c = table_entry(R, i);
             if (cell_n(c)) acc += cell_score(cell_n(c), cell_s(c));
         }
     }

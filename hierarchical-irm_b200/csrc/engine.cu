@@ -84,6 +84,10 @@ struct Irm {
     std::vector<DevBuf<cell_t>> counts;
     std::vector<std::array<int64_t, MAX_ARITY>> cstride;
     std::vector<int64_t> ncells;
+    std::vector<int> table_mode;       // per relation: 0 auto (hashed iff the index space exceeds the dense budget), 1 dense, 2 hashed
+    std::vector<uint32_t> hcap;        // per relation: entries of the hashed count table, 0 = dense
+    DevBuf<uint32_t> hused;            // [n_relations] entries taken (device counters)
+    bool any_hashed = false;
     // generic kernel: compact group-accumulator spaces per (relation, domain) (engine_types.cuh: RelDom)
     DevBuf<RelDom> rdesc; std::vector<DevBuf<int32_t>> cmap; std::vector<int32_t> ctot;
     DevBuf<cell_t> gacc; DevBuf<uint32_t> gbm;
@@ -129,6 +133,7 @@ static const char *kerr_text(int code) {
         case KERR_ABSENT_ENTITY: return "an observation names an entity whose assignment is -1";
         case KERR_GROUP_OVERFLOW: return "group list capacity exceeded";
         case KERR_BAD_MOVE: return "move names an entity that is not in the domain";
+        case KERR_TABLE_FULL: return "hashed count table full";
         default: return "unknown kernel error";
     }
 }
@@ -215,7 +220,7 @@ extern "C" int hirm_irm_create(hirm_engine *e, int n_domains, const int32_t *n_e
     irm->have_z.assign(n_domains, false); irm->has_absent.assign(n_domains, false);
     irm->cstride.resize(n_relations);
     irm->ncells.resize(n_relations);
-    const int64_t CELL_BUDGET = (int64_t)1 << 27;      // 1 GiB of packed cells per table
+    irm->table_mode.assign(n_relations, 0); irm->hcap.assign(n_relations, 0);
     for (int r = 0; r < n_relations; r++) {
         if (arity[r] < 1 || arity[r] > MAX_ARITY) return fail("arity must be in [1, HIRM_MAX_ARITY]");
         std::array<int32_t, MAX_ARITY> ds{};
@@ -228,8 +233,7 @@ extern "C" int hirm_irm_create(hirm_engine *e, int n_domains, const int32_t *n_e
             for (int q = 0; q <= p; q++) occ += rel_domains[r * MAX_ARITY + q] == d;
             if (occ > 2) return fail("a domain may occur at most twice in one relation");
             irm->cstride[r][p] = cs;
-            cs *= irm->kcap[d];
-            if (cs > CELL_BUDGET) return fail("dense count table too large: lower max_tables (hashed tables are not built yet)");
+            cs *= irm->kcap[d];                        // <= 255^4: no overflow; beyond the dense budget the table is hashed (ensure_scratch)
         }
         irm->ncells[r] = cs;
         irm->arity.push_back(arity[r]); irm->rdom.push_back(ds);
@@ -458,13 +462,36 @@ static int finalize_store(hirm_engine *e, Irm *irm) {
     return 0;
 }
 
+static const int64_t DENSE_CELL_BUDGET = (int64_t)1 << 27;   // 1 GiB of packed cells per dense table
+
+static uint32_t pow2_ceil(uint64_t v) { uint32_t p = 1; while (p < v && p < (1u << 30)) p <<= 1; return p; }
+
 static int ensure_scratch(hirm_engine *e, Irm *irm) {
     if (irm->scratch_ready) return 0;
     ObsStore &S = *irm->obs;
     bool any_csr = false;
+    const bool env_hashed = getenv("HIRM_HASHED_TABLES") != nullptr;   // test switch: every CSR relation on the hashed table
+    irm->any_hashed = false;
+    CK(irm->hused.ensure((size_t)std::max(irm->n_relations, 1)));
     for (int r = 0; r < irm->n_relations; r++) {
-        CK(irm->counts[r].ensure((size_t)irm->ncells[r]));
         any_csr |= S.rel[r].kind == 0;
+        const int mode = irm->table_mode[r];
+        bool hashed = S.rel[r].kind == 0 && (mode == 2 || (mode == 0 && (env_hashed || irm->ncells[r] > DENSE_CELL_BUDGET)));
+        if (mode == 1 && irm->ncells[r] > DENSE_CELL_BUDGET) return fail("dense count table too large: lower max_tables or use the hashed table");
+        if (hashed) {
+            // Relation::clusters as an open-addressing table: at most one non-empty cell per observation; 4 entries per
+            // possible cell (emptied cells linger until the host rebuilds), grown on demand (maintain_hashed)
+            const uint64_t want = 4ull * (uint64_t)std::min<int64_t>(std::max<int64_t>(S.rel[r].nobs, 1), irm->ncells[r]);
+            if (irm->hcap[r] == 0) {
+                irm->hcap[r] = std::max(1024u, std::min(pow2_ceil(want), 1u << 22));
+                if (const char *s = getenv("HIRM_HASH_INITIAL_ENTRIES")) irm->hcap[r] = std::max(64u, pow2_ceil((uint64_t)atoll(s)));   // test switch: exercise growth
+            }
+            CK(irm->counts[r].ensure((size_t)irm->hcap[r] * 2));
+            irm->any_hashed = true;
+        } else {
+            irm->hcap[r] = 0;
+            CK(irm->counts[r].ensure((size_t)irm->ncells[r]));
+        }
     }
     if (any_csr) {
         // compact accumulator spaces: for every domain, the (relation, self pattern) blocks laid end to end
@@ -540,6 +567,7 @@ static int upload_desc(hirm_engine *e, int32_t id) {
         R.arity = irm->arity[r]; R.kind = S.rel[r].kind;
         for (int p = 0; p < MAX_ARITY; p++) { R.dom[p] = irm->rdom[r][p]; R.cstride[p] = irm->cstride[r][p]; }
         R.counts = irm->counts[r].p; R.ncells = irm->ncells[r];
+        R.hcap = irm->hcap[r]; R.hused = irm->hused.p + r;
         R.slab[0] = S.rel[r].slab[0]; R.slab[1] = S.rel[r].slab[1]; R.pitch[0] = S.rel[r].pitch[0]; R.pitch[1] = S.rel[r].pitch[1];
         R.coo_ids = S.rel[r].ids; R.coo_val = S.rel[r].val; R.nobs = S.rel[r].nobs;
         R.full_obs = S.rel[r].full_obs > 0 ? 1 : 0;
@@ -570,10 +598,11 @@ static int upload_desc(hirm_engine *e, int32_t id) {
     return 0;
 }
 
-static int check_kernel_error(hirm_engine *e, Irm *irm) {
+static int check_kernel_error(hirm_engine *e, Irm *irm, int32_t *code_out = nullptr) {
     int32_t code = 0;
     CK(cudaMemcpyAsync(&code, irm->error.p, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    if (code_out) *code_out = code;
     if (code) {
         CK(cudaMemsetAsync(irm->error.p, 0, sizeof(int32_t), e->stream));
         return fail(std::string("kernel error: ") + kerr_text(code));
@@ -593,6 +622,35 @@ static int check_kernel_errors(hirm_engine *e, int n_irms) {
     return 0;
 }
 
+// Hashed count tables after a sweep: emptied cells linger as zero cells.  A table more than half full is rebuilt from
+// (observations, z) at its next use (the histogram holds the non-empty cells only); one that is still more than half
+// full right after a rebuild doubles.
+static int maintain_hashed(hirm_engine *e, Irm *irm, bool after_rebuild) {
+    if (!irm->any_hashed) return 0;
+    std::vector<uint32_t> used((size_t)irm->n_relations);
+    CK(cudaMemcpyAsync(used.data(), irm->hused.p, used.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int r = 0; r < irm->n_relations; r++) {
+        if (!irm->hcap[r] || used[(size_t)r] <= irm->hcap[r] / 2) continue;
+        if (after_rebuild) {
+            if (irm->hcap[r] >= (1u << 30)) return fail("hashed count table cannot grow further");
+            irm->hcap[r] *= 2;
+            CK(irm->counts[r].alloc((size_t)irm->hcap[r] * 2));
+            irm->desc_dirty = true;
+        }
+        irm->counts_dirty = true;
+    }
+    return 0;
+}
+
+extern "C" int hirm_irm_set_table_mode(hirm_engine *e, int32_t id, int rel, int mode) {
+    GET_IRM(irm, e, id);
+    if (rel < 0 || rel >= irm->n_relations || mode < 0 || mode > 2) return fail("bad relation index or mode");
+    if (irm->scratch_ready) return fail("set the table mode before hirm_irm_finalize");
+    irm->table_mode[rel] = mode;
+    return 0;
+}
+
 // (re)build every count table from (observations, z)
 static int ensure_counts(hirm_engine *e, int32_t id) {
     Irm *irm = e->irms[id].get();
@@ -602,8 +660,10 @@ static int ensure_counts(hirm_engine *e, int32_t id) {
     if (upload_desc(e, id)) return -1;
     if (!irm->counts_dirty) return 0;
     ObsStore &S = *irm->obs;
+    CK(cudaMemsetAsync(irm->hused.p, 0, (size_t)std::max(irm->n_relations, 1) * sizeof(uint32_t), e->stream));
     for (int r = 0; r < irm->n_relations; r++) {
-        CK(cudaMemsetAsync(irm->counts[r].p, 0, (size_t)irm->ncells[r] * sizeof(cell_t), e->stream));
+        const size_t words = irm->hcap[r] ? (size_t)irm->hcap[r] * 2 : (size_t)irm->ncells[r];
+        CK(cudaMemsetAsync(irm->counts[r].p, 0, words * sizeof(cell_t), e->stream));
         if (S.rel[r].nobs == 0) continue;
         if (S.rel[r].kind == 0) {
             int blocks = (int)std::min<int64_t>((S.rel[r].nobs + 255) / 256, 148 * 8);
@@ -619,8 +679,23 @@ static int ensure_counts(hirm_engine *e, int32_t id) {
         }
         CK(cudaGetLastError());
     }
-    if (check_kernel_error(e, irm)) return -1;
+    int32_t code = 0;
+    if (check_kernel_error(e, irm, &code)) {
+        if (code != KERR_TABLE_FULL || !irm->any_hashed) return -1;
+        for (int r = 0; r < irm->n_relations; r++) {          // the non-empty cells alone overflow a hashed table: double and rebuild
+            if (!irm->hcap[r]) continue;
+            if (irm->hcap[r] >= (1u << 30)) return fail("hashed count table cannot grow further");
+            irm->hcap[r] *= 2;
+            CK(irm->counts[r].alloc((size_t)irm->hcap[r] * 2));
+        }
+        irm->desc_dirty = true;
+        return ensure_counts(e, id);
+    }
     irm->counts_dirty = false;
+    if (irm->any_hashed) {
+        if (maintain_hashed(e, irm, true)) return -1;
+        if (irm->counts_dirty) return ensure_counts(e, id);   // a table grew: build it again
+    }
     return 0;
 }
 
@@ -674,7 +749,8 @@ extern "C" int hirm_irm_get_counts(hirm_engine *e, int32_t id, int rel, int32_t 
     if (rel < 0 || rel >= irm->n_relations || !n_cells) return fail("bad relation index");
     if (ensure_counts(e, id)) return -1;
     const int a = irm->arity[rel];
-    std::vector<cell_t> tab((size_t)irm->ncells[rel]);
+    const uint32_t hcap = irm->hcap[rel];
+    std::vector<cell_t> tab(hcap ? (size_t)hcap * 2 : (size_t)irm->ncells[rel]);
     CK(cudaMemcpy(tab.data(), irm->counts[rel].p, tab.size() * sizeof(cell_t), cudaMemcpyDeviceToHost));
     std::vector<std::vector<int32_t>> labs((size_t)a);
     for (int p = 0; p < a; p++) {
@@ -683,12 +759,16 @@ extern "C" int hirm_irm_get_counts(hirm_engine *e, int32_t id, int rel, int32_t 
         CK(cudaMemcpy(labs[p].data(), irm->tab_label[d].p, labs[p].size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     }
     std::vector<std::vector<int32_t>> cells;
-    for (int64_t k = 0; k < irm->ncells[rel]; k++) {
-        if (cell_n(tab[(size_t)k]) == 0) continue;     // emptied cells are erased in the reference (cxx/hirm.hh:534-537)
-        std::vector<int32_t> row((size_t)a + 2);
+    const int64_t n_entries = hcap ? (int64_t)hcap : irm->ncells[rel];
+    for (int64_t k = 0; k < n_entries; k++) {
         int64_t rem = k;
+        cell_t c = 0;
+        if (hcap) { if (tab[(size_t)k * 2] == 0) continue; rem = (int64_t)tab[(size_t)k * 2] - 1; c = tab[(size_t)k * 2 + 1]; }
+        else c = tab[(size_t)k];
+        if (cell_n(c) == 0) continue;                  // emptied cells are erased in the reference (cxx/hirm.hh:534-537)
+        std::vector<int32_t> row((size_t)a + 2);
         for (int p = 0; p < a; p++) { const int kc = irm->kcap[irm->rdom[rel][p]]; row[p] = labs[p][(size_t)(rem % kc)]; rem /= kc; }
-        row[a] = (int32_t)cell_n(tab[(size_t)k]); row[a + 1] = (int32_t)cell_s(tab[(size_t)k]);
+        row[a] = (int32_t)cell_n(c); row[a + 1] = (int32_t)cell_s(c);
         cells.push_back(std::move(row));
     }
     std::sort(cells.begin(), cells.end());
@@ -1219,6 +1299,7 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
         Irm *irm = get_irm(e, h_irms[k]);
         if (!irm) return fail("bad irm id in sweep list");
         for (int j = 0; j < k; j++) if (h_irms[j] == h_irms[k]) return fail("an irm may appear once per sweep");
+        if (irm->any_hashed && !irm->counts_dirty && maintain_hashed(e, irm, false)) return -1;   // a hashed table filling up with emptied cells is rebuilt
         if (ensure_counts(e, h_irms[k])) return -1;
         if (irm->dense_ree && !(flags & HIRM_SWEEP_FORCE_GENERIC)) {
             if (!have_dense) {

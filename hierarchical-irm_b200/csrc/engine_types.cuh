@@ -38,9 +38,13 @@ struct RelationDev {
     int32_t arity;
     int32_t kind;                 // 0 = CSR, 1 = dense slabs
     int32_t dom[MAX_ARITY];
-    cell_t *counts;               // dense count table, index = sum_p slot_p * cstride[p]   (Relation::clusters, :246)
+    cell_t *counts;               // count table (Relation::clusters, :246).  Dense: `ncells` cells, index = sum_p slot_p * cstride[p].
+                                  // Hashed (hcap > 0): hcap open-addressing entries {key = index + 1 (0 = empty), cell}, 16 bytes each
     int64_t cstride[MAX_ARITY];
-    int64_t ncells;
+    int64_t ncells;               // cells of the index space (prod of the domains' table slots)
+    uint32_t hcap;                // hashed: entries (a power of two); 0 = dense
+    uint32_t hpad;
+    uint32_t *hused;              // hashed: [1] entries taken so far (emptied cells stay as zero cells until the host rebuilds)
     const uint8_t *slab[2];       // dense: rows by first / by second entity
     int64_t pitch[2];
     const int32_t *coo_ids;       // [nobs*arity] (CSR relations: kept for count-table rebuilds)
@@ -88,9 +92,50 @@ enum : int32_t {
     KERR_ABSENT_ENTITY = 2,    // observation endpoint with z = -1
     KERR_GROUP_OVERFLOW = 3,   // group list capacity exceeded
     KERR_BAD_MOVE = 4,         // move names an entity outside the domain
+    KERR_TABLE_FULL = 5,       // hashed count table: no free entry
 };
 
 __device__ __forceinline__ void raise_error(const IrmDev &irm, int32_t code) { atomicCAS(irm.error, 0, code); }
+
+// ---- count-table access: dense array or open-addressing hash (linear probing) keyed by the cell index -----------------
+// Relation::clusters is a sparse map in the reference (create on demand :540-543, erase on zero :534-537).  The hashed
+// table keeps an emptied cell as a zero cell: it reads as absent (score 0, not listed by get_counts); the host drops such
+// entries when it rebuilds the table.  One 16-byte entry = {key, (N | s << 32)}: a probe is one ld.cg.v2.
+__device__ __forceinline__ uint32_t hash_slot(int64_t cidx, uint32_t mask) {
+    return (uint32_t)(((uint64_t)cidx * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+}
+__device__ __forceinline__ cell_t table_get(const RelationDev *R, int64_t cidx) {
+    if (!R->hcap) return __ldcg(&R->counts[cidx]);
+    const uint32_t mask = R->hcap - 1u;
+    const unsigned long long key = (unsigned long long)cidx + 1ull;
+    const ulonglong2 *tab = reinterpret_cast<const ulonglong2 *>(R->counts);
+    for (uint32_t i = hash_slot(cidx, mask), n = 0; n <= mask; i = (i + 1u) & mask, n++) {
+        const ulonglong2 e = __ldcg(tab + i);
+        if (e.x == key) return e.y;
+        if (e.x == 0ull) return 0ull;
+    }
+    return 0ull;
+}
+__device__ __forceinline__ void table_add(const IrmDev &irm, const RelationDev *R, int64_t cidx, cell_t delta) {
+    if (!R->hcap) { atomicAdd(&R->counts[cidx], delta); return; }
+    const uint32_t mask = R->hcap - 1u;
+    const unsigned long long key = (unsigned long long)cidx + 1ull;
+    for (uint32_t i = hash_slot(cidx, mask), n = 0; n <= mask; i = (i + 1u) & mask, n++) {
+        unsigned long long k = __ldcg(&R->counts[2 * (size_t)i]);
+        if (k == 0ull) {
+            k = atomicCAS(&R->counts[2 * (size_t)i], 0ull, key);
+            if (k == 0ull) { atomicAdd(R->hused, 1u); k = key; }
+        }
+        if (k == key) { atomicAdd(&R->counts[2 * (size_t)i + 1], delta); return; }
+    }
+    raise_error(irm, KERR_TABLE_FULL);
+}
+// iteration over the stored cells (scores, read-back): entries of the table and the cell of entry i (0 = empty)
+__device__ __forceinline__ int64_t table_entries(const RelationDev *R) { return R->hcap ? (int64_t)R->hcap : R->ncells; }
+__device__ __forceinline__ cell_t table_entry(const RelationDev *R, int64_t i) {
+    if (!R->hcap) return R->counts[i];
+    return R->counts[2 * i] ? R->counts[2 * i + 1] : 0ull;
+}
 
 struct SweepArgs {
     const IrmDev *irms;           // [all irms of the engine]

@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 const int32_t cell = D->base[pat] + rest_k + (pat < 2 ? dother * D->rest_size : 0);
                 atomicAdd(&acc[cell], one);
                 atomicOr(&bm[cell >> 5], 1u << (cell & 31));
-                if (D->b >= 0) atomicAdd(&R->counts[cidx], (cell_t)0 - one);
+                if (D->b >= 0) table_add(irm, R, cidx, (cell_t)0 - one);
             }
         }
         // One CTA owns the IRM: __syncthreads() alone makes the block's global atomics and stores visible to the block
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             const GroupRec gr = g < RCAP ? s_recs[g] : recs[g];
             cell_t delta; int64_t cidx;
             if (!group_target(gr, acc, slot_t, delta, cidx)) return;
-            cell_t curc = __ldcg(&gr.R->counts[cidx]);
+            cell_t curc = table_get(gr.R, cidx);
             if (gr.RD->b < 0 && slot_t == c) curc -= gr.own;    // virtual removal: the entity's own observations leave its current cell
             N = cell_n(curc); sv = cell_s(curc); gn = cell_n(delta); gs = cell_s(delta);
         };
@@ -527,11 +527,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             if (gr.RD->b < 0) {
                 if (tnew != c) {
                     const int64_t ca = gr.R->cstride[gr.RD->a];
-                    atomicAdd(&gr.R->counts[gr.rest_c + c * ca], (cell_t)0 - gr.own);
-                    atomicAdd(&gr.R->counts[gr.rest_c + tnew * ca], gr.own);
+                    table_add(irm, gr.R, gr.rest_c + c * ca, (cell_t)0 - gr.own);
+                    table_add(irm, gr.R, gr.rest_c + tnew * ca, gr.own);
                 }
             } else {
-                atomicAdd(&gr.R->counts[group_cell_at(gr, tnew)], gr.own);
+                table_add(irm, gr.R, group_cell_at(gr, tnew), gr.own);
             }
             if (acc_shared) { acc[gr.cell] = 0; bm[gr.cell >> 5] = 0u; }
             else { __stcg(&acc[gr.cell], (cell_t)0); __stcg(&bm[gr.cell >> 5], 0u); }
@@ -577,7 +577,7 @@ __global__ void rebuild_counts_coo_kernel(const IrmDev *irms, int irm_id, int re
             cidx += (slot < 0 ? 0 : slot) * R->cstride[p];
         }
         if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); continue; }
-        atomicAdd(&R->counts[cidx], pack_cell(1u, R->coo_val[e]));
+        table_add(irm, R, cidx, pack_cell(1u, R->coo_val[e]));
     }
 }
 
@@ -587,8 +587,8 @@ __global__ void __launch_bounds__(1024) relation_score_kernel(const IrmDev *irms
     const RelationDev *R = &irms[irm_id].rel[rel];
     __shared__ double s_part[32];
     double acc = 0.0;
-    for (int64_t i = threadIdx.x; i < R->ncells; i += blockDim.x) {
-        const cell_t c = R->counts[i];
+    for (int64_t i = threadIdx.x, ne = table_entries(R); i < ne; i += blockDim.x) {
+        const cell_t c = table_entry(R, i);
         if (cell_n(c)) acc += cell_score(cell_n(c), cell_s(c));
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

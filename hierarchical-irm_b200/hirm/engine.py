@@ -21,6 +21,7 @@ DENSE_MISSING = 0xFF
 SWEEP_SCORE_ONLY = 1
 SWEEP_FORCE_GENERIC = 2
 SWEEP_CLUSTER = 4
+TABLE_AUTO, TABLE_DENSE, TABLE_HASHED = 0, 1, 2
 
 EXPORTS = [
     "hirm_last_error", "hirm_engine_abi_version", "hirm_engine_create", "hirm_engine_destroy",
@@ -34,7 +35,7 @@ EXPORTS = [
     "hirm_engine_relation_scores", "hirm_irm_seat_entities", "hirm_engine_debug_score_delta",
     "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
     "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters", "hirm_engine_clear_relation_cache",
-    "hirm_engine_seat_prior",
+    "hirm_engine_seat_prior", "hirm_irm_set_table_mode",
     "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
     "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
 ]
@@ -104,6 +105,7 @@ def load():
                                                     ctypes.c_uint64, c_u64p, c_f64p]
     L.hirm_engine_clear_relation_cache.argtypes = [V]
     L.hirm_engine_seat_prior.argtypes = [V, I, c_i32p, ctypes.c_uint64]
+    L.hirm_irm_set_table_mode.argtypes = [V, ctypes.c_int32, I, I]
     L.hirm_irm_set_rng_counters.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
     L.hirm_engine_crp_prior_draw.argtypes = [V, I, ctypes.c_double, I, ctypes.c_uint64, ctypes.c_uint64, c_i32p]
     CP = ctypes.POINTER(ctypes.c_char_p)
@@ -229,6 +231,10 @@ class Engine:
 
     def set_observations_dense_host_ptr(self, irm, rel, ptr, pitch):
         self._ck(self.L.hirm_irm_set_observations_dense_host(self._h, irm, rel, ptr, pitch))
+
+    def set_table_mode(self, irm, rel, mode):
+        """0 auto, 1 dense, 2 hashed count table for a CSR-stored relation (before finalize)."""
+        self._ck(self.L.hirm_irm_set_table_mode(self._h, irm, rel, mode))
 
     def share_observations(self, dst, src):
         self._ck(self.L.hirm_irm_share_observations(self._h, dst, src))

@@ -83,6 +83,16 @@ int hirm_irm_set_observations_dense(hirm_engine *e, int32_t irm, int rel,
 int hirm_irm_set_observations_dense_host(hirm_engine *e, int32_t irm, int rel, const uint8_t *h_x, int64_t h_pitch);
 /* Make irm_dst use irm_src's observation store (same schema; independent chains over one dataset). */
 int hirm_irm_share_observations(hirm_engine *e, int32_t irm_dst, int32_t irm_src);
+/* Storage of Relation::clusters (cxx/hirm.hh:246; a sparse map with create-on-demand :540-543 and erase-on-zero :534-537)
+ * for a CSR-stored relation: HIRM_TABLE_DENSE = a dense array over the index space prod(max_tables) (at most 2^27 cells),
+ * HIRM_TABLE_HASHED = an open-addressing table of the non-empty cells keyed by the cluster tuple (64-bit CAS insert, 64-bit
+ * add of (N | s << 32); an emptied cell reads as absent and is dropped when the engine rebuilds the table; the table grows
+ * on demand), HIRM_TABLE_AUTO (default) = hashed iff the index space exceeds the dense budget.  Results are identical
+ * either way.  Call before hirm_irm_finalize. */
+#define HIRM_TABLE_AUTO 0
+#define HIRM_TABLE_DENSE 1
+#define HIRM_TABLE_HASHED 2
+int hirm_irm_set_table_mode(hirm_engine *e, int32_t irm, int rel, int mode);
 int hirm_irm_finalize(hirm_engine *e, int32_t irm);
 
 /* Domain::incorporate(item, table) for every entity   (cxx/hirm.hh:194-203; forced seats as in
