@@ -123,7 +123,7 @@ struct hirm_engine {
     std::map<std::pair<const int32_t *, const uint8_t *>, UnaryBits> unary_cache;   // keyed by the (ids, val) buffers: relations may share an ids buffer
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
-    int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0, dense_static_smem = 0, dense_static_smem_large = 0;
+    int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0, dense_static_smem = 0, dense_static_smem_large = 0, gen_regs = 64, gen_static_smem = 12 * 1024;
     long long *d_phase_cycles = nullptr;   // debug hook (hirm_engine_debug_phase_cycles)
 };
 
@@ -163,6 +163,8 @@ extern "C" int hirm_engine_create(hirm_engine **out, int device) {
     e->dense_static_smem = (int)fa.sharedSizeBytes + 64;
     CK(cudaFuncGetAttributes(&fa, dense_ree_sweep_kernel<DN_DW_LARGE, 3>));
     e->dense_static_smem_large = (int)fa.sharedSizeBytes + 64;
+    CK(cudaFuncGetAttributes(&fa, generic_sweep_kernel));
+    e->gen_regs = std::max(fa.numRegs, 16); e->gen_static_smem = (int)fa.sharedSizeBytes + 64;
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
     // log-factorial table from libm's lgamma (the reference's lbeta, cxx/util_math.cc:13-15)
@@ -583,7 +585,7 @@ static int upload_desc(hirm_engine *e, int32_t id) {
         dd.z = irm->z[d].p; dd.tab_count = irm->tab_count[d].p; dd.tab_label = irm->tab_label[d].p; dd.hi = irm->hi[d].p;
         dd.alpha = irm->alpha[d];
         dd.ptr = S.dom[d].nnz ? S.dom[d].ptr.p : nullptr; dd.meta = S.dom[d].meta.p; dd.other = S.dom[d].other.p;
-        dd.nnz = S.dom[d].nnz; dd.n_other = S.dom[d].n_other;
+        dd.nnz = S.dom[d].nnz; dd.n_other = S.dom[d].n_other; dd.max_deg = S.dom[d].max_deg;
     }
     D.rel = irm->d_rel.p;
     D.rdesc = irm->rdesc.p; D.gacc = irm->gacc.p; D.gbm = irm->gbm.p;
@@ -1260,6 +1262,7 @@ struct Plan {
     int n_ent = 0, kcap = 0;
     int64_t gen_maxdeg = 0;
     int gen_kmax = 0, gen_ndom = 0, gen_nother = 0;   // generic kernel: largest max_tables / domain count / other-id columns of its IRMs
+    int gen_ctot = 0; int64_t gen_groups = 0;         // ... largest accumulator space of a domain, most groups one move can have
 };
 
 // Shared-memory plan of one dense tier: as many chains per SM as the launch has (up to 5: the register budget) and fit; the rest of
@@ -1331,7 +1334,13 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
                 if (R.kind == 1) return fail("no kernel for this irm: dense slabs are supported for a single R(e,e) relation only");
             for (int32_t kc : irm->kcap) plan.gen_kmax = std::max(plan.gen_kmax, (int)kc);
             plan.gen_ndom = std::max(plan.gen_ndom, irm->n_domains);
-            for (auto &D : irm->obs->dom) { plan.gen_nother = std::max(plan.gen_nother, D.n_other); plan.gen_maxdeg = std::max(plan.gen_maxdeg, D.max_deg); }
+            for (int d = 0; d < irm->n_domains; d++) {
+                const DomObs &D = irm->obs->dom[(size_t)d];
+                plan.gen_nother = std::max(plan.gen_nother, D.n_other); plan.gen_maxdeg = std::max(plan.gen_maxdeg, D.max_deg);
+                const int ct = d < (int)irm->ctot.size() ? irm->ctot[(size_t)d] : 0;
+                plan.gen_ctot = std::max(plan.gen_ctot, ct);
+                plan.gen_groups = std::max(plan.gen_groups, std::min<int64_t>(D.max_deg, ct));
+            }
             plan.generic_blk.push_back(k);
         }
     }
@@ -1370,9 +1379,28 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         int gen_threads = n_gen <= e->num_sms ? 1024 : (n_gen <= 4 * e->num_sms || plan.gen_maxdeg > 512) ? 256 : 128;
         if (const char *s = getenv("HIRM_GENERIC_THREADS")) gen_threads = std::max(64, std::min(1024, atoi(s) & ~31));
         GenericLaunch GL;
-        GL.rcap = gen_threads; GL.pcap = 4 * gen_threads; GL.scap = 4 * gen_threads;
+        GL.pcap = 4 * gen_threads;
         GL.kstride = (std::max(plan.gen_kmax, 2) + 2) & ~1;
         GL.ndom = std::max(plan.gen_ndom, 1); GL.roww = 1 + std::max(plan.gen_nother, 1);
+        // Shared-memory plan: the move's accumulator (4 bytes per cell of the largest per-domain cell space) and its group
+        // records (52 bytes per group, at most min(longest row, cells) groups) stay on chip when they fit the CTA's share
+        // of the SM; the fewer IRMs per SM, the bigger that share.  What does not fit goes to the IRM's global scratch.
+        const int scap_want = std::max(256, (plan.gen_ctot + 31) & ~31);
+        const int rcap_want = std::max(128, (int)((std::min<int64_t>(plan.gen_groups, 1 << 20) + 31) & ~31));
+        int want_ctas = std::max(1, std::min(std::min(2048 / gen_threads, 65536 / (e->gen_regs * gen_threads)), (n_gen + e->num_sms - 1) / e->num_sms));
+        const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww) + (size_t)e->gen_static_smem;
+        for (;; want_ctas--) {
+            const size_t budget = (size_t)std::min(e->max_smem_optin, e->smem_per_sm / want_ctas - 1024);
+            if (fixed + (size_t)scap_want * 4 + (size_t)rcap_want * 52 <= budget || want_ctas == 1) {
+                const size_t room = budget > fixed ? budget - fixed : 0;
+                GL.scap = (int)std::min<size_t>((size_t)scap_want, room > 128 * 52 ? ((room - 128 * 52) / 4) & ~(size_t)31 : 0);
+                if (GL.scap < 256) GL.scap = 256;
+                const size_t left = room > (size_t)GL.scap * 4 ? room - (size_t)GL.scap * 4 : 0;
+                GL.rcap = (int)std::min<size_t>((size_t)rcap_want, (left / 52) & ~(size_t)31);
+                if (GL.rcap < 128) GL.rcap = 128;
+                break;
+            }
+        }
         const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww);
         if (gen_smem > (size_t)e->max_smem_optin) return fail("generic kernel: shared-memory plan exceeds the device limit");
         CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem));

@@ -32,6 +32,7 @@ struct DomainDev {
     int64_t nnz;
     int32_t n_other;
     int32_t pad;
+    int64_t max_deg;      // longest CSR row of the domain (bounds a move's group counts: 16-bit fields of the shared accumulator)
 };
 
 struct RelationDev {

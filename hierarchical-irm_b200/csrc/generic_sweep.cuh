@@ -40,9 +40,21 @@ struct GroupRec {
 };
 static_assert(sizeof(GroupRec) == 48, "GroupRec layout (engine.cu sizes the scratch by it)");
 
+// The accumulator of one move: 32-bit cells (observations | ones << 16) in shared memory, fed by native 32-bit shared
+// atomics (a 64-bit shared atomicAdd is a compare-and-swap spin loop: ATOMS.CAST.SPIN in the SASS), or -- when the
+// domain's cell space does not fit or a row is longer than 65534 entries -- 64-bit cells in the IRM's global scratch.
+struct AccView {
+    const uint32_t *s32;      // shared accumulator, or null
+    const cell_t *g;          // global accumulator
+    __device__ __forceinline__ cell_t operator[](int32_t c) const {
+        if (s32) { const uint32_t v = s32[c]; return pack_cell(v & 0xFFFFu, v >> 16); }
+        return __ldcg(&g[c]);
+    }
+};
+
 // Resolve the group against candidate slot t: false if another group owns the merged target cell; otherwise the
 // (n, s) to add and the count-table index.  `acc` is the move's accumulator.
-__device__ __forceinline__ bool group_target(const GroupRec &g, const cell_t *acc, int t, cell_t &delta, int64_t &cidx) {
+__device__ __forceinline__ bool group_target(const GroupRec &g, const AccView &acc, int t, cell_t &delta, int64_t &cidx) {
     const RelationDev *R = g.R;
     const RelDom *D = g.RD;
     const int64_t ca = R->cstride[D->a];
@@ -119,10 +131,10 @@ __device__ __forceinline__ double score_delta_any(const double *lf, uint32_t N, 
 }
 
 // Dynamic shared memory of one CTA: [rcap] group records, [rcap] touched accumulator cells, [pcap] partial sums,
-// [scap] accumulator cells + [scap / 32] bitmap words.
+// [scap] 32-bit accumulator cells.
 struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww; };   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids)
 __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap) {
-    return (size_t)rcap * (sizeof(GroupRec) + 4) + (size_t)pcap * 8 + (size_t)scap * 8 + (size_t)(scap / 32 + 1) * 4 + 16;
+    return (size_t)rcap * (sizeof(GroupRec) + 4) + (size_t)pcap * 8 + (size_t)scap * 4 + 16;
 }
 // + [2][roww][threads] words: the first `threads` entries of the next move's CSR row (meta + other ids), copied
 // asynchronously one move ahead
@@ -152,10 +164,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     const int64_t glcap = irm.gl_cap;
     GroupRec *s_recs = reinterpret_cast<GroupRec *>(gen_dyn);                                  // [rcap]
     double *s_part = reinterpret_cast<double *>(s_recs + RCAP);                                 // [pcap]
-    cell_t *s_acc = reinterpret_cast<cell_t *>(s_part + PCAP);                                  // [scap]
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_part + PCAP);                              // [scap] observations | ones << 16
     int32_t *s_bits = reinterpret_cast<int32_t *>(s_acc + SCAP);                                // [rcap]
-    uint32_t *s_bm = reinterpret_cast<uint32_t *>(s_bits + RCAP);                               // [scap / 32 + 1]
-    uint32_t *s_row = s_bm + (SCAP / 32 + 1);                                                   // [2][roww][NT] next / current CSR row heads
+    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_bits + RCAP);                              // [2][roww][NT] next / current CSR row heads
     const int KS = GL.kstride;
     const int ROWW = GL.roww;
     double *s_logcnt_all = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_row + 2 * ROWW * NT) + 7) & ~(uintptr_t)7);   // [ndom][KS] log(table size)
@@ -163,8 +174,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     int32_t *s_lab_all = s_cnt_all + GL.ndom * KS;
 
     for (int k = tid; k < GEN_LF; k += NT) s_lf[k] = g_logfact[k];
-    for (int k = tid; k < SCAP; k += NT) s_acc[k] = 0;
-    for (int k = tid; k < SCAP / 32 + 1; k += NT) s_bm[k] = 0u;
+    for (int k = tid; k < SCAP; k += NT) s_acc[k] = 0u;
     for (int dk = 0; dk < irm.n_domains; dk++) {
         const DomainDev &dq = irm.dom[dk];
         const int h = __ldcg(dq.hi);
@@ -267,9 +277,8 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         int32_t *s_cnt = s_cnt_all + d * KS, *s_lab = s_lab_all + d * KS;
         const int hi = s_hi_all[d];
         const int ctot = irm.ctot[d];
-        const bool acc_shared = ctot <= SCAP;          // the move's accumulator: shared memory, or the IRM's global scratch
-        cell_t *acc = acc_shared ? s_acc : irm.gacc;
-        uint32_t *bm = acc_shared ? s_bm : irm.gbm;
+        const bool acc_shared = ctot <= SCAP && dd.max_deg < 65535;   // the move's accumulator: shared memory, or the IRM's global scratch
+        const AccView acc{acc_shared ? s_acc : nullptr, irm.gacc};
         const RelDom *rdesc = irm.rdesc + d;           // descriptor of relation r: rdesc[r * n_domains]
 
         // ---- C: candidates, CRP::tables_weights_gibbs (cxx/hirm.hh:147-161): the last warp, while the others stream the row ----
@@ -348,8 +357,8 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); continue; }
                 const cell_t one = pack_cell(1u, val);
                 const int32_t cell = D->base[pat] + rest_k + (pat < 2 ? dother * D->rest_size : 0);
-                atomicAdd(&acc[cell], one);
-                atomicOr(&bm[cell >> 5], 1u << (cell & 31));
+                if (acc_shared) atomicAdd(&s_acc[cell], 1u | (val << 16));
+                else { atomicAdd(&irm.gacc[cell], one); atomicOr(&irm.gbm[cell >> 5], 1u << (cell & 31)); }
                 if (D->b >= 0) table_add(irm, R, cidx, (cell_t)0 - one);
             }
         }
@@ -364,7 +373,17 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         const int nwords = (ctot + 31) >> 5;
         for (int w0 = 0; w0 < nwords; w0 += NT) {
             const int w = w0 + tid;
-            uint32_t bits = w < nwords ? (acc_shared ? bm[w] : __ldcg(&bm[w])) : 0u;
+            uint32_t bits = 0u;
+            if (acc_shared) {
+                // word w0 + warp * 32 + j of the non-empty-cell bitmap = ballot over its 32 accumulator cells (lane = cell:
+                // conflict-free shared loads); lane j keeps word j.  No bitmap atomics in phase A.
+                const int wbase = w0 + warp * 32;
+                for (int j = 0; j < 32 && wbase + j < nwords; j++) {
+                    const int cellv = (wbase + j) * 32 + lane;
+                    const uint32_t b = __ballot_sync(0xffffffffu, cellv < ctot && s_acc[cellv] != 0u);
+                    if (lane == j) bits = b;
+                }
+            } else if (w < nwords) bits = __ldcg(&irm.gbm[w]);
             const int cnt = __popc(bits);
             int incl = cnt;
 #pragma unroll
@@ -421,7 +440,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 rest_c += digit * R->cstride[p];
             }
             rc.rest_c = rest_c;
-            rc.own = acc_shared ? acc[cell] : __ldcg(&acc[cell]);
+            rc.own = acc[cell];
             rc.pad0 = rc.pad1 = 0;
             if (g < RCAP) s_recs[g] = rc; else recs[g] = rc;
         }
@@ -431,24 +450,39 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
 
         // ---- D: score.  Work unit = (candidate, 32 consecutive groups), one warp each, lanes over the groups; the partial
         //      sums are added per candidate in chunk order afterwards (fixed order: deterministic) -------------------------
-        auto eval = [&](int64_t g, int slot_t, uint32_t &N, uint32_t &sv, uint32_t &gn, uint32_t &gs) {
-            N = 0u; sv = 0u; gn = 0u; gs = 0u;
-            if (g >= ngroups) return;
+        // operands of one (group, candidate) pair in two steps, so that the count-table load of the NEXT unit is in flight
+        // while the current unit's fp64 work runs: issue() resolves the target cell and starts the load, finish() consumes it
+        struct Pending { cell_t cur, delta, sub; };
+        auto issue = [&](int64_t g, int slot_t) -> Pending {
+            Pending p{0ull, 0ull, 0ull};
+            if (g >= ngroups) return p;
             const GroupRec gr = g < RCAP ? s_recs[g] : recs[g];
-            cell_t delta; int64_t cidx;
-            if (!group_target(gr, acc, slot_t, delta, cidx)) return;
-            cell_t curc = table_get(gr.R, cidx);
-            if (gr.RD->b < 0 && slot_t == c) curc -= gr.own;    // virtual removal: the entity's own observations leave its current cell
-            N = cell_n(curc); sv = cell_s(curc); gn = cell_n(delta); gs = cell_s(delta);
+            int64_t cidx;
+            if (!group_target(gr, acc, slot_t, p.delta, cidx)) { p.delta = 0ull; return p; }
+            p.cur = table_get(gr.R, cidx);
+            if (gr.RD->b < 0 && slot_t == c) p.sub = gr.own;     // virtual removal: the entity's own observations leave its current cell
+            return p;
+        };
+        auto finish = [&](const Pending &p, uint32_t &N, uint32_t &sv, uint32_t &gn, uint32_t &gs) {
+            const cell_t curc = p.cur - p.sub;
+            N = cell_n(curc); sv = cell_s(curc); gn = cell_n(p.delta); gs = cell_s(p.delta);
+            if (gn == 0u) { N = 0u; sv = 0u; gs = 0u; }
+        };
+        auto eval = [&](int64_t g, int slot_t, uint32_t &N, uint32_t &sv, uint32_t &gn, uint32_t &gs) {
+            finish(issue(g, slot_t), N, sv, gn, gs);
         };
         const int nch = (int)((ngroups + 31) >> 5);
         const bool flat = (int64_t)ncand * nch <= PCAP;
         if (flat) {
             const int nunits = ncand * nch;
+            Pending pend{0ull, 0ull, 0ull};
+            if (warp < nunits) { const int t0 = warp / nch; pend = issue((int64_t)(warp - t0 * nch) * 32 + lane, s_cslot[t0]); }
             for (int unit = warp; unit < nunits; unit += NW) {
-                const int t = unit / nch, ch = unit - t * nch;
+                const Pending cur = pend;
+                const int nu = unit + NW;
+                if (nu < nunits) { const int t2 = nu / nch; pend = issue((int64_t)(nu - t2 * nch) * 32 + lane, s_cslot[t2]); }
                 uint32_t N, sv, gn, gs;
-                eval((int64_t)ch * 32 + lane, s_cslot[t], N, sv, gn, gs);
+                finish(cur, N, sv, gn, gs);
                 __syncwarp();
                 double v = score_delta_any(s_lf, N, sv, gn, gs);
 #pragma unroll
@@ -533,8 +567,8 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             } else {
                 table_add(irm, gr.R, group_cell_at(gr, tnew), gr.own);
             }
-            if (acc_shared) { acc[gr.cell] = 0; bm[gr.cell >> 5] = 0u; }
-            else { __stcg(&acc[gr.cell], (cell_t)0); __stcg(&bm[gr.cell >> 5], 0u); }
+            if (acc_shared) s_acc[gr.cell] = 0u;
+            else { __stcg(&irm.gacc[gr.cell], (cell_t)0); __stcg(&irm.gbm[gr.cell >> 5], 0u); }
         }
         if (tid == 0 && tnew != c) {
             __stcg(&dd.z[item], tnew);

@@ -126,7 +126,11 @@ def test_rebuilt_irm_keeps_its_philox_positions():
     assert abs(logsumexp([p0, p1])) < 1e-12
     assert abs(irm.logp([("R1", (0, 0), 0)]) - p0) < 1e-12
     four = [irm.logp([("R1", (100, 0), a), ("R1", (100, 1), b)]) for a in (0, 1) for b in (0, 1)]
-    assert abs(logsumexp(four)) < 1e-12
+    # entity 100 is new to D1: its seat ranges over the tables and a fresh one with weights / (1 + N) (src/hirm.py:589-599),
+    # which sum to (N + alpha) / (N + 1) -- one only while alpha = 1, as in the reference
+    crp = irm.domains["D1"].crp
+    import math
+    assert abs(logsumexp(four) - math.log((crp.N + crp.alpha) / (crp.N + 1))) < 1e-12
 
 
 @pytest.mark.gpu
