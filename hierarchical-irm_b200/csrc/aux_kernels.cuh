@@ -358,6 +358,21 @@ __global__ void __launch_bounds__(PRIOR_THREADS) crp_prior_kernel(const PriorDra
     }
 }
 
+// One column of a unary block from the relation's COO arrays: bit `col` of the observed / value rows of every entity the
+// relation observes.  err: 1 = code or value out of range, 2 = an entity observed twice (cxx/hirm.hh:272 asserts distinct).
+__global__ void unary_block_fill_kernel(const int32_t *ids, const uint8_t *val, int64_t nobs, int32_t n_ent, int col, int words,
+                                        uint32_t *obs_rows, uint32_t *val_rows, int32_t *err) {
+    const uint32_t bit = 1u << (col & 31);
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < nobs; o += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t i = ids[o];
+        const uint8_t v = val[o];
+        if (i < 0 || i >= n_ent || v > 1) { atomicCAS(err, 0, 1); continue; }
+        const int64_t w = (int64_t)i * words + (col >> 5);
+        if (atomicOr(&obs_rows[w], bit) & bit) atomicCAS(err, 0, 2);
+        if (v) atomicOr(&val_rows[w], bit);
+    }
+}
+
 // CRP state of a domain from its slot array: customers per slot, label = slot, highest used slot + 1 -- after a device-side
 // prior draw (hirm_engine_seat_prior).  One CTA per (irm, domain) pair listed in `pairs` (irm id, domain).
 __global__ void __launch_bounds__(256) tables_from_slots_kernel(const IrmDev *irms, const int32_t *pairs) {

@@ -52,7 +52,8 @@ struct DevBuf {
 };
 
 struct RelObs {
-    int kind = -1;                     // -1 unset, 0 CSR, 1 dense
+    int kind = -1;                     // -1 unset, 0 CSR, 1 dense, 2 column of a unary block
+    int ub_block = -1, ub_col = -1;    // kind 2
     int64_t nobs = 0;
     const int32_t *ids = nullptr;      // device COO [nobs * arity]: own_ids, or the caller's buffer (set_observations_device)
     const uint8_t *val = nullptr;
@@ -65,6 +66,13 @@ struct RelObs {
 struct DomObs {
     DevBuf<int64_t> ptr; DevBuf<uint32_t> meta; DevBuf<int32_t> other;
     int64_t nnz = 0; int n_other = 0; int64_t max_deg = 0;
+    int ub_block = -1, n_unary = 0;    // unary-block relations of the domain (all from one block)
+};
+// Unary relations over one domain as entity-major bit rows: relation-owned, built once, shared by every IRM.
+struct UnaryBlock {
+    int32_t n_ent = 0; int n_rel = 0, words = 0;
+    DevBuf<uint32_t> obs, val;
+    std::vector<const int32_t *> ids; std::vector<const uint8_t *> vals; std::vector<int64_t> nobs;   // the columns' COO arrays (caller-owned)
 };
 // Observation store: immutable after finalize(); shared by the chains of one dataset.
 struct ObsStore {
@@ -94,6 +102,7 @@ struct Irm {
     DevBuf<int64_t> gl_cell; int64_t gl_cap = 0;      // generic kernel: group records beyond the shared-memory ones
     DevBuf<int32_t> error;
     DevBuf<RelationDev> d_rel;
+    std::vector<DevBuf<uint32_t>> ub_mask; std::vector<DevBuf<int32_t>> ub_cell;   // per domain: this IRM's view of the unary block
     std::vector<bool> have_z, has_absent;
     bool counts_dirty = true, desc_dirty = true, scratch_ready = false;
     bool alive = true;
@@ -107,6 +116,7 @@ struct hirm_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::vector<std::unique_ptr<Irm>> irms;
+    std::vector<std::unique_ptr<UnaryBlock>> ublocks;
     DevBuf<IrmDev> d_irms;
     std::vector<IrmDev> h_irms;
     // sweep scratch
@@ -330,6 +340,68 @@ extern "C" int hirm_irm_set_observations_device(hirm_engine *e, int32_t id, int 
     return 0;
 }
 
+// ---- unary blocks -----------------------------------------------------------------------------------------------------
+// The observations of many unary relations over one domain (animals.unary: 85 features of 50 animals; config 5: 2000
+// relations over 200 000 entities) as two entity-major bit matrices, built on the device from the relations' COO arrays.
+// Relation::data_r of a unary relation is "entity -> its one observation" (cxx/hirm.hh:251): the row of entity i holds
+// that for every relation at once, 2 bits per (entity, relation) instead of a CSR entry, and it does not depend on which
+// IRM a relation currently belongs to -- an IRM selects its relations with a column mask.
+extern "C" int hirm_unary_block_create(hirm_engine *e, int32_t n_entities, int n_rel, const int64_t *h_nobs,
+                                       const int32_t *const *h_d_ids, const uint8_t *const *h_d_val, int32_t *out_block) {
+    if (!e || !out_block) return fail("null argument");
+    CK(cudaSetDevice(e->device));
+    if (n_entities < 0 || n_rel < 1 || !h_nobs || !h_d_ids || !h_d_val) return fail("bad argument");
+    auto B = std::make_unique<UnaryBlock>();
+    B->n_ent = n_entities; B->n_rel = n_rel; B->words = (n_rel + 31) / 32;
+    const size_t nw = (size_t)std::max(n_entities, 1) * B->words;
+    CK(B->obs.alloc(nw)); CK(B->val.alloc(nw));
+    CK(cudaMemsetAsync(B->obs.p, 0, nw * sizeof(uint32_t), e->stream));
+    CK(cudaMemsetAsync(B->val.p, 0, nw * sizeof(uint32_t), e->stream));
+    CK(e->s_relerr.ensure(1));
+    CK(cudaMemsetAsync(e->s_relerr.p, 0, sizeof(int32_t), e->stream));
+    for (int c = 0; c < n_rel; c++) {
+        if (h_nobs[c] < 0 || (h_nobs[c] > 0 && (!h_d_ids[c] || !h_d_val[c]))) return fail("null observation arrays");
+        B->ids.push_back(h_d_ids[c]); B->vals.push_back(h_d_val[c]); B->nobs.push_back(h_nobs[c]);
+        if (h_nobs[c] == 0) continue;
+        unary_block_fill_kernel<<<coo_blocks(e, h_nobs[c]), 256, 0, e->stream>>>(h_d_ids[c], h_d_val[c], h_nobs[c], n_entities, c, B->words,
+                                                                              B->obs.p, B->val.p, e->s_relerr.p);
+        CK(cudaGetLastError());
+    }
+    int32_t err = 0;
+    CK(cudaMemcpyAsync(&err, e->s_relerr.p, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (err == 1) return fail("observation values must be 0 or 1 and entity codes in range");
+    if (err == 2) return fail("a unary relation observes an entity twice (observations must be distinct)");
+    e->ublocks.push_back(std::move(B));
+    *out_block = (int32_t)e->ublocks.size() - 1;
+    return 0;
+}
+
+extern "C" int hirm_unary_block_destroy(hirm_engine *e, int32_t block) {
+    if (!e || block < 0 || block >= (int)e->ublocks.size() || !e->ublocks[block]) return fail("bad unary block id");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    e->ublocks[block].reset();
+    return 0;
+}
+
+// Relation `rel` of the IRM (unary) = column `col` of the block: IRM::incorporate for all of that relation's observations.
+extern "C" int hirm_irm_set_observations_unary(hirm_engine *e, int32_t id, int rel, int32_t block, int col) {
+    GET_IRM(irm, e, id);
+    if (rel < 0 || rel >= irm->n_relations) return fail("bad relation index");
+    if (irm->arity[rel] != 1) return fail("a unary block holds unary relations");
+    if (irm->obs.use_count() > 1 || irm->obs->finalized) return fail("observation store is shared or finalized");
+    if (block < 0 || block >= (int)e->ublocks.size() || !e->ublocks[block]) return fail("bad unary block id");
+    const UnaryBlock &B = *e->ublocks[block];
+    if (col < 0 || col >= B.n_rel) return fail("bad unary block column");
+    if (B.n_ent != irm->n_ent[irm->rdom[rel][0]]) return fail("the block's domain size differs from the relation's");
+    RelObs &R = irm->obs->rel[rel];
+    R.kind = 2; R.ub_block = block; R.ub_col = col;
+    R.nobs = B.nobs[(size_t)col]; R.ids = B.ids[(size_t)col]; R.val = B.vals[(size_t)col];   // count-table builds and relation scores read the COO arrays
+    R.own_ids.release(); R.own_val.release();
+    return 0;
+}
+
 static int check_dense_rel(Irm *irm, int rel) {
     if (rel < 0 || rel >= irm->n_relations) return fail("bad relation index");
     if (irm->arity[rel] != 2) return fail("dense slabs are for binary relations");
@@ -418,6 +490,13 @@ static int finalize_store(hirm_engine *e, Irm *irm) {
         }
         DomObs &D = S.dom[d];
         D.nnz = 0; D.n_other = std::max(1, max_other); D.max_deg = 0;
+        D.ub_block = -1; D.n_unary = 0;
+        for (int r = 0; r < irm->n_relations; r++) {
+            if (S.rel[r].kind != 2 || irm->rdom[r][0] != d) continue;
+            if (D.ub_block >= 0 && D.ub_block != S.rel[r].ub_block) return fail("the unary-block relations of one domain must come from one block");
+            D.ub_block = S.rel[r].ub_block; D.n_unary++;
+        }
+        D.max_deg = D.n_unary;
         if (touching.empty() || n == 0) continue;
         static_assert(sizeof(unsigned long long) == sizeof(int64_t), "ptr is scanned in place");
         CK(D.ptr.alloc((size_t)n + 1));
@@ -435,7 +514,7 @@ static int finalize_store(hirm_engine *e, Irm *irm) {
         CK(cudaMemcpyAsync(&nnz, D.ptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s0));
         CK(cudaMemcpyAsync(&maxdeg, cursor.p + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
         CK(cudaStreamSynchronize(s0));
-        D.nnz = nnz; D.max_deg = (int64_t)maxdeg;
+        D.nnz = nnz; D.max_deg = (int64_t)maxdeg + D.n_unary;
         if (nnz == 0) { D.ptr.release(); continue; }
         CK(D.meta.alloc((size_t)nnz)); CK(D.other.alloc((size_t)nnz * D.n_other));
         CK(cudaMemsetAsync(D.other.p, 0, (size_t)nnz * D.n_other * sizeof(int32_t), s0));
@@ -476,7 +555,7 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
     irm->any_hashed = false;
     CK(irm->hused.ensure((size_t)std::max(irm->n_relations, 1)));
     for (int r = 0; r < irm->n_relations; r++) {
-        any_csr |= S.rel[r].kind == 0;
+        any_csr |= S.rel[r].kind == 0 || S.rel[r].kind == 2;
         const int mode = irm->table_mode[r];
         bool hashed = S.rel[r].kind == 0 && (mode == 2 || (mode == 0 && (env_hashed || irm->ncells[r] > DENSE_CELL_BUDGET)));
         if (mode == 1 && irm->ncells[r] > DENSE_CELL_BUDGET) return fail("dense count table too large: lower max_tables or use the hashed table");
@@ -507,7 +586,7 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
                 RelDom &D = rd[(size_t)r * nd + d];
                 memset(&D, 0, sizeof(D));
                 D.a = D.b = -1; D.rest_size = 1;
-                if (S.rel[r].kind != 0) continue;
+                if (S.rel[r].kind == 1) continue;
                 for (int p = 0; p < irm->arity[r]; p++)
                     if (irm->rdom[r][p] == d) { if (D.a < 0) D.a = p; else D.b = p; }
                 if (D.a < 0) continue;
@@ -531,6 +610,25 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
         }
         CK(irm->rdesc.ensure(rd.size()));
         if (!rd.empty()) CK(cudaMemcpy(irm->rdesc.p, rd.data(), rd.size() * sizeof(RelDom), cudaMemcpyHostToDevice));
+        // this IRM's view of each domain's unary block: column mask, accumulator cell per column
+        irm->ub_mask.resize((size_t)nd); irm->ub_cell.resize((size_t)nd);
+        for (int d = 0; d < nd; d++) {
+            if (S.dom[d].ub_block < 0) continue;
+            const UnaryBlock *B = e->ublocks[(size_t)S.dom[d].ub_block].get();
+            if (!B) return fail("the IRM's unary block was destroyed");
+            std::vector<uint32_t> mask((size_t)B->words, 0u);
+            std::vector<int32_t> cell((size_t)B->words * 32, -1);
+            for (int r = 0; r < irm->n_relations; r++) {
+                if (S.rel[r].kind != 2 || irm->rdom[r][0] != d) continue;
+                const int col = S.rel[r].ub_col;
+                if (cell[(size_t)col] >= 0) return fail("two relations of one IRM name the same unary-block column");
+                mask[(size_t)col >> 5] |= 1u << (col & 31);
+                cell[(size_t)col] = rd[(size_t)r * nd + d].base[0];
+            }
+            CK(irm->ub_mask[(size_t)d].ensure(mask.size())); CK(irm->ub_cell[(size_t)d].ensure(cell.size()));
+            CK(cudaMemcpy(irm->ub_mask[(size_t)d].p, mask.data(), mask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(irm->ub_cell[(size_t)d].p, cell.data(), cell.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
         CK(irm->gacc.ensure((size_t)max_ctot)); CK(irm->gbm.ensure((size_t)(max_ctot / 32 + 1)));
         CK(cudaMemsetAsync(irm->gacc.p, 0, (size_t)max_ctot * sizeof(cell_t), e->stream));
         CK(cudaMemsetAsync(irm->gbm.p, 0, (size_t)(max_ctot / 32 + 1) * sizeof(uint32_t), e->stream));
@@ -586,6 +684,12 @@ static int upload_desc(hirm_engine *e, int32_t id) {
         dd.alpha = irm->alpha[d];
         dd.ptr = S.dom[d].nnz ? S.dom[d].ptr.p : nullptr; dd.meta = S.dom[d].meta.p; dd.other = S.dom[d].other.p;
         dd.nnz = S.dom[d].nnz; dd.n_other = S.dom[d].n_other; dd.max_deg = S.dom[d].max_deg;
+        if (S.dom[d].ub_block >= 0 && d < (int)irm->ub_mask.size()) {
+            const UnaryBlock *B = e->ublocks[(size_t)S.dom[d].ub_block].get();
+            if (!B) return fail("the IRM's unary block was destroyed");
+            dd.ub_obs = B->obs.p; dd.ub_val = B->val.p; dd.ub_words = B->words;
+            dd.ub_mask = irm->ub_mask[(size_t)d].p; dd.ub_cell = irm->ub_cell[(size_t)d].p;
+        }
     }
     D.rel = irm->d_rel.p;
     D.rdesc = irm->rdesc.p; D.gacc = irm->gacc.p; D.gbm = irm->gbm.p;
@@ -667,7 +771,7 @@ static int ensure_counts(hirm_engine *e, int32_t id) {
         const size_t words = irm->hcap[r] ? (size_t)irm->hcap[r] * 2 : (size_t)irm->ncells[r];
         CK(cudaMemsetAsync(irm->counts[r].p, 0, words * sizeof(cell_t), e->stream));
         if (S.rel[r].nobs == 0) continue;
-        if (S.rel[r].kind == 0) {
+        if (S.rel[r].kind != 1) {
             int blocks = (int)std::min<int64_t>((S.rel[r].nobs + 255) / 256, 148 * 8);
             rebuild_counts_coo_kernel<<<blocks, 256, 0, e->stream>>>(e->d_irms.p, id, r);
         } else {
@@ -876,7 +980,7 @@ extern "C" int hirm_engine_relation_scores(hirm_engine *e, int32_t src, int rel,
     if (n_cand == 0) return 0;
     if (finalize_store(e, S)) return -1;
     RelObs &R = S->obs->rel[rel];
-    if (R.kind != 0) return fail("relation scores under other partitions are built for CSR-stored relations only");
+    if (R.kind == 1) return fail("relation scores under other partitions are built for COO-backed relations only");
     const int a = S->arity[rel];
     std::vector<RelCand> cands((size_t)n_cand);
     int64_t total_cells = 0;
@@ -1389,10 +1493,12 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         const int rcap_want = std::max(128, (int)((std::min<int64_t>(plan.gen_groups, 1 << 20) + 31) & ~31));
         int want_ctas = std::max(1, std::min(std::min(2048 / gen_threads, 65536 / (e->gen_regs * gen_threads)), (n_gen + e->num_sms - 1) / e->num_sms));
         const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww) + (size_t)e->gen_static_smem;
+        // the accumulator decides how many CTAs share an SM (a global accumulator costs far more than a lost CTA); the group
+        // records take what is left of the CTA's share, the rest of a long group list lives in the IRM's global scratch
         for (;; want_ctas--) {
             const size_t budget = (size_t)std::min(e->max_smem_optin, e->smem_per_sm / want_ctas - 1024);
-            if (fixed + (size_t)scap_want * 4 + (size_t)rcap_want * 52 <= budget || want_ctas == 1) {
-                const size_t room = budget > fixed ? budget - fixed : 0;
+            const size_t room = budget > fixed ? budget - fixed : 0;
+            if ((size_t)scap_want * 4 + 128 * 52 <= room || want_ctas == 1) {
                 GL.scap = (int)std::min<size_t>((size_t)scap_want, room > 128 * 52 ? ((room - 128 * 52) / 4) & ~(size_t)31 : 0);
                 if (GL.scap < 256) GL.scap = 256;
                 const size_t left = room > (size_t)GL.scap * 4 ? room - (size_t)GL.scap * 4 : 0;

@@ -32,12 +32,21 @@ struct DomainDev {
     int64_t nnz;
     int32_t n_other;
     int32_t pad;
-    int64_t max_deg;      // longest CSR row of the domain (bounds a move's group counts: 16-bit fields of the shared accumulator)
+    int64_t max_deg;      // longest CSR row of the domain + its unary-block relations (bounds a move's group count)
+    // unary relations of the domain kept as a block of entity-major bit rows (hirm_unary_block_create): row i = entity i's
+    // observations in every relation of the block, `ub_words` words per plane.  The block is relation-owned and shared
+    // by all IRMs; an IRM selects its own relations with a column mask.
+    const uint32_t *ub_obs;   // [n][ub_words] observed
+    const uint32_t *ub_val;   // [n][ub_words] value
+    const uint32_t *ub_mask;  // [ub_words] columns that are relations of this IRM
+    const int32_t *ub_cell;   // [ub_words * 32] accumulator cell of the column's relation in this IRM
+    int32_t ub_words;
+    int32_t pad2;
 };
 
 struct RelationDev {
     int32_t arity;
-    int32_t kind;                 // 0 = CSR, 1 = dense slabs
+    int32_t kind;                 // 0 = CSR, 1 = dense slabs, 2 = column of a unary block
     int32_t dom[MAX_ARITY];
     cell_t *counts;               // count table (Relation::clusters, :246).  Dense: `ncells` cells, index = sum_p slot_p * cstride[p].
                                   // Hashed (hcap > 0): hcap open-addressing entries {key = index + 1 (0 = empty), cell}, 16 bytes each

@@ -53,38 +53,52 @@ struct AccView {
 };
 
 // Resolve the group against candidate slot t: false if another group owns the merged target cell; otherwise the
-// (n, s) to add and the count-table index.  `acc` is the move's accumulator.
-__device__ __forceinline__ bool group_target(const GroupRec &g, const AccView &acc, int t, cell_t &delta, int64_t &cidx) {
+// (n, s) to add (`delta`), the count-table index of the target cell (`cidx`) and the part of that cell's CURRENT content
+// that is the moving entity's own observations (`sub`): the entity is removed from the table virtually -- the count
+// tables are not touched unless the entity really changes tables.  `acc` is the move's accumulator, c the entity's slot.
+// Twice-occurring domain (a, b): the entity's observations sit in the cells (c, y) [row group y: i at a, other end in y],
+// (x, c) [column group x] and (c, c) [(i, i)], so cell (x, y) holds  [x = c] row(y) + [y = c] col(x) + [x = y = c] diag.
+__device__ __forceinline__ bool group_target(const GroupRec &g, const AccView &acc, int t, int c, cell_t &delta, int64_t &cidx, cell_t &sub) {
     const RelationDev *R = g.R;
     const RelDom *D = g.RD;
     const int64_t ca = R->cstride[D->a];
     if (D->b < 0) {                                  // domain occurs once: no merging
         delta = g.own;
         cidx = g.rest_c + t * ca;
+        sub = t == c ? g.own : (cell_t)0;
         return true;
     }
     const int64_t cb = R->cstride[D->b];
-    const int32_t row_t = D->base[0] + g.rest_k + t * D->rest_size;   // i at a, other end in slot t
-    const int32_t col_t = D->base[1] + g.rest_k + t * D->rest_size;   // i at b, other end in slot t
+    const int32_t row0 = D->base[0] + g.rest_k, col0 = D->base[1] + g.rest_k, rs = D->rest_size;
     const int32_t diag = D->base[2] + g.rest_k;                       // (i, i)
+    auto own_at = [&](int x, int y) -> cell_t {
+        cell_t v = 0;
+        if (x == c) v += acc[row0 + y * rs];
+        if (y == c) v += acc[col0 + x * rs];
+        if (x == c && y == c) v += acc[diag];
+        return v;
+    };
     if (g.pat == 2) {                                // (i, i): target (t, t); absorbs the row / column groups whose other end sits in t
-        delta = g.own + acc[row_t] + acc[col_t];
+        delta = g.own + acc[row0 + t * rs] + acc[col0 + t * rs];
         cidx = g.rest_c + t * ca + t * cb;
+        sub = own_at(t, t);
         return true;
     }
     if (g.pat == 0) {                                // i at position a, other end in slot dother
-        if (g.dother != t) { delta = g.own; cidx = g.rest_c + t * ca + g.dother * cb; return true; }
+        if (g.dother != t) { delta = g.own; cidx = g.rest_c + t * ca + g.dother * cb; sub = own_at(t, g.dother); return true; }
         if (cell_n(acc[diag]) > 0) return false;
-        delta = g.own + acc[col_t];
+        delta = g.own + acc[col0 + t * rs];
         cidx = g.rest_c + t * ca + t * cb;
+        sub = own_at(t, t);
         return true;
     }
     // i at position b, other end in slot dother
-    if (g.dother != t) { delta = g.own; cidx = g.rest_c + g.dother * ca + t * cb; return true; }
+    if (g.dother != t) { delta = g.own; cidx = g.rest_c + g.dother * ca + t * cb; sub = own_at(g.dother, t); return true; }
     if (cell_n(acc[diag]) > 0) return false;
-    if (cell_n(acc[row_t]) > 0) return false;
+    if (cell_n(acc[row0 + t * rs]) > 0) return false;
     delta = g.own;
     cidx = g.rest_c + t * ca + t * cb;
+    sub = own_at(t, t);
     return true;
 }
 
@@ -338,7 +352,6 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 const RelDom *D = rdesc + (int64_t)rel * irm.n_domains;
                 const bool at_a = (selfmask >> D->a) & 1u, at_b = D->b >= 0 && ((selfmask >> D->b) & 1u);
                 const int pat = at_a ? (at_b ? 2 : 0) : 1;
-                int64_t cidx = 0;
                 int32_t rest_k = 0, dother = 0;
                 int oi = 0; bool first = true, absent = false;
                 for (int p = 0; p < R->arity; p++) {
@@ -352,14 +365,27 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                         if (slot < 0) { absent = true; slot = 0; }
                         if (p == D->a || p == D->b) dother = slot; else rest_k += slot * D->rstride[p];
                     }
-                    cidx += slot * R->cstride[p];
                 }
                 if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); continue; }
                 const cell_t one = pack_cell(1u, val);
                 const int32_t cell = D->base[pat] + rest_k + (pat < 2 ? dother * D->rest_size : 0);
                 if (acc_shared) atomicAdd(&s_acc[cell], 1u | (val << 16));
                 else { atomicAdd(&irm.gacc[cell], one); atomicOr(&irm.gbm[cell >> 5], 1u << (cell & 31)); }
-                if (D->b >= 0) table_add(irm, R, cidx, (cell_t)0 - one);
+            }
+        }
+        // unary-block relations: one thread per column of the entity's bit row; at most one observation per (entity, relation)
+        // and one accumulator cell per relation, so a plain store does it
+        if (dd.ub_words && tid < NA) {
+            const uint32_t *xo = dd.ub_obs + (int64_t)item * dd.ub_words, *xv = dd.ub_val + (int64_t)item * dd.ub_words;
+            for (int k = tid; k < dd.ub_words * 32; k += NA) {
+                const int w = k >> 5;
+                const uint32_t ob = __ldg(xo + w) & __ldg(dd.ub_mask + w);      // the warp reads one word: a broadcast
+                if ((ob >> (k & 31)) & 1u) {
+                    const uint32_t val = (__ldg(xv + w) >> (k & 31)) & 1u;
+                    const int32_t cell = __ldg(dd.ub_cell + k);
+                    if (acc_shared) s_acc[cell] = 1u | (val << 16);
+                    else { __stcg(&irm.gacc[cell], pack_cell(1u, val)); atomicOr(&irm.gbm[cell >> 5], 1u << (cell & 31)); }
+                }
             }
         }
         // One CTA owns the IRM: __syncthreads() alone makes the block's global atomics and stores visible to the block
@@ -458,9 +484,8 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             if (g >= ngroups) return p;
             const GroupRec gr = g < RCAP ? s_recs[g] : recs[g];
             int64_t cidx;
-            if (!group_target(gr, acc, slot_t, p.delta, cidx)) { p.delta = 0ull; return p; }
-            p.cur = table_get(gr.R, cidx);
-            if (gr.RD->b < 0 && slot_t == c) p.sub = gr.own;     // virtual removal: the entity's own observations leave its current cell
+            if (!group_target(gr, acc, slot_t, c, p.delta, cidx, p.sub)) { p.delta = 0ull; p.sub = 0ull; return p; }
+            p.cur = table_get(gr.R, cidx);             // virtual removal: finish() takes the entity's own observations out of the cell
             return p;
         };
         auto finish = [&](const Pending &p, uint32_t &N, uint32_t &sv, uint32_t &gn, uint32_t &gs) {
@@ -558,13 +583,8 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         const int tnew = s_choice_slot;
         for (int64_t g = tid; g < ngroups; g += NT) {
             const GroupRec gr = g < RCAP ? s_recs[g] : recs[g];
-            if (gr.RD->b < 0) {
-                if (tnew != c) {
-                    const int64_t ca = gr.R->cstride[gr.RD->a];
-                    table_add(irm, gr.R, gr.rest_c + c * ca, (cell_t)0 - gr.own);
-                    table_add(irm, gr.R, gr.rest_c + tnew * ca, gr.own);
-                }
-            } else {
+            if (tnew != c) {                          // Relation::set_cluster_assignment_gibbs (:524-551): every observation leaves its cell for the new one
+                table_add(irm, gr.R, group_cell_at(gr, c), (cell_t)0 - gr.own);
                 table_add(irm, gr.R, group_cell_at(gr, tnew), gr.own);
             }
             if (acc_shared) s_acc[gr.cell] = 0u;

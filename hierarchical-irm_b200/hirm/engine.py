@@ -35,7 +35,8 @@ EXPORTS = [
     "hirm_engine_relation_scores", "hirm_irm_seat_entities", "hirm_engine_debug_score_delta",
     "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
     "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters", "hirm_engine_clear_relation_cache",
-    "hirm_engine_seat_prior", "hirm_irm_set_table_mode",
+    "hirm_engine_seat_prior", "hirm_irm_set_table_mode", "hirm_unary_block_create", "hirm_unary_block_destroy",
+    "hirm_irm_set_observations_unary",
     "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
     "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
 ]
@@ -106,6 +107,9 @@ def load():
     L.hirm_engine_clear_relation_cache.argtypes = [V]
     L.hirm_engine_seat_prior.argtypes = [V, I, c_i32p, ctypes.c_uint64]
     L.hirm_irm_set_table_mode.argtypes = [V, ctypes.c_int32, I, I]
+    L.hirm_unary_block_create.argtypes = [V, ctypes.c_int32, I, c_i64p, ctypes.POINTER(V), ctypes.POINTER(V), c_i32p]
+    L.hirm_unary_block_destroy.argtypes = [V, ctypes.c_int32]
+    L.hirm_irm_set_observations_unary.argtypes = [V, ctypes.c_int32, I, ctypes.c_int32, I]
     L.hirm_irm_set_rng_counters.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
     L.hirm_engine_crp_prior_draw.argtypes = [V, I, ctypes.c_double, I, ctypes.c_uint64, ctypes.c_uint64, c_i32p]
     CP = ctypes.POINTER(ctypes.c_char_p)
@@ -235,6 +239,22 @@ class Engine:
     def set_table_mode(self, irm, rel, mode):
         """0 auto, 1 dense, 2 hashed count table for a CSR-stored relation (before finalize)."""
         self._ck(self.L.hirm_irm_set_table_mode(self._h, irm, rel, mode))
+
+    def unary_block_create(self, n_entities, cols):
+        """cols: list of (nobs, d_ids_ptr, d_val_ptr), one per unary relation -> block handle (bit rows built on the device)."""
+        n = len(cols)
+        nobs = np.ascontiguousarray([c[0] for c in cols], dtype=np.int64)
+        ids = (ctypes.c_void_p * n)(*[c[1] or None for c in cols])
+        val = (ctypes.c_void_p * n)(*[c[2] or None for c in cols])
+        out = ctypes.c_int32()
+        self._ck(self.L.hirm_unary_block_create(self._h, int(n_entities), n, _p(nobs, c_i64p), ids, val, ctypes.byref(out)))
+        return out.value
+
+    def unary_block_destroy(self, block):
+        self._ck(self.L.hirm_unary_block_destroy(self._h, block))
+
+    def set_observations_unary(self, irm, rel, block, col):
+        self._ck(self.L.hirm_irm_set_observations_unary(self._h, irm, rel, block, col))
 
     def share_observations(self, dst, src):
         self._ck(self.L.hirm_irm_share_observations(self._h, dst, src))

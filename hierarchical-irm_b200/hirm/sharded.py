@@ -93,7 +93,7 @@ class EngineBackend:
     """Device side of one rank: the relation-owned COO arrays (torch tensors as buffers, replicated on every rank) and
     the engine IRMs of the relation clusters this rank owns.  Every call is a C-ABI call (include/hirm_engine.h)."""
 
-    def __init__(self, n_entities, rel_domains, observations, max_tables, seed, engine=None, device=None, host_order=False):
+    def __init__(self, n_entities, rel_domains, observations, max_tables, seed, engine=None, device=None, host_order=False, unary_blocks=True):
         import torch
         from . import engine as E
         if not torch.cuda.is_available():
@@ -124,6 +124,20 @@ class EngineBackend:
             self._buf.append((t_ids, t_val))
             self.rels.append((ds, int(t_val.numel()), t_ids.data_ptr() if t_val.numel() else None, t_val.data_ptr() if t_val.numel() else None))
         self._meta = {}
+        # unary relations of a domain as ONE relation-owned block of entity-major bit rows (hirm_unary_block_create): an IRM
+        # picks its relations by column, so re-seating a unary relation moves no data and builds no CSR
+        self.ublock = {}                                   # relation index -> (block handle, column)
+        if unary_blocks:
+            by_dom = {}
+            for r, ds in enumerate(self.rel_domains):
+                if len(ds) == 1 and self.rels[r][1] > 0:
+                    by_dom.setdefault(ds[0], []).append(r)
+            for d, rs in by_dom.items():
+                if len(rs) < 2:
+                    continue
+                blk = self.eng.unary_block_create(self.n_entities[d], [self.rels[r][1:] for r in rs])
+                for col, r in enumerate(rs):
+                    self.ublock[r] = (blk, col)
 
     # -- IRMs -----------------------------------------------------------------------------------
     def create_irm(self, rels, z, alpha, uid, steps):
@@ -132,7 +146,10 @@ class EngineBackend:
         h = eng.irm_create(self.n_entities, [self.rel_domains[r] for r in rels], max_tables=self.max_tables)
         for k, r in enumerate(rels):
             ds, nobs, pi, pv = self.rels[r]
-            eng.set_observations_device(h, k, nobs, pi, pv)
+            if r in self.ublock:
+                eng.set_observations_unary(h, k, *self.ublock[r])
+            else:
+                eng.set_observations_device(h, k, nobs, pi, pv)
         eng.finalize(h)
         for d in range(len(self.n_entities)):
             eng.set_assignments(h, d, z[d])

@@ -71,6 +71,17 @@ int hirm_irm_set_observations(hirm_engine *e, int32_t irm, int rel, int64_t nobs
  * (HIRM::transition_cluster_assignment_relation re-incorporates the data into each candidate, cxx/hirm.hh:859-864). */
 int hirm_irm_set_observations_device(hirm_engine *e, int32_t irm, int rel, int64_t nobs, const int32_t *d_ids,
                                      const uint8_t *d_val);
+/* Many unary relations over one domain as a relation-owned block of entity-major bit rows (observed, value): row i holds
+ * entity i's observation in every relation of the block -- Relation::data_r of a unary relation is "entity -> its one
+ * observation" (cxx/hirm.hh:251), 2 bits here instead of a CSR entry.  Built once on the device from the relations' COO
+ * arrays (h_d_ids[c] / h_d_val[c]: DEVICE pointers, caller-owned, must outlive the block), shared by every IRM: moving a
+ * relation between the IRMs of an HIRM (cxx/hirm.hh:859-864 re-incorporates its data) changes a column mask, not data. */
+int hirm_unary_block_create(hirm_engine *e, int32_t n_entities, int n_rel, const int64_t *h_nobs,
+                            const int32_t *const *h_d_ids, const uint8_t *const *h_d_val, int32_t *out_block);
+int hirm_unary_block_destroy(hirm_engine *e, int32_t block);
+/* IRM::incorporate of every observation of unary relation `rel` = column `col` of the block (instead of
+ * hirm_irm_set_observations*).  All unary-block relations of one domain of an IRM must come from the same block. */
+int hirm_irm_set_observations_unary(hirm_engine *e, int32_t irm, int rel, int32_t block, int col);
 /* Dense binary relation R(d0,d1) as two byte slabs in device memory (0, 1, HIRM_DENSE_MISSING):
  *   d_slab0[i*pitch0 + j] = value of (i, j)   i in d0, j in d1   ("rows by first entity")
  *   d_slab1[j*pitch1 + i] = value of (i, j)                      ("rows by second entity")

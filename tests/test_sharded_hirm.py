@@ -214,6 +214,64 @@ def test_device_coo_store_equals_host_coo_store():
 
 
 @pytest.mark.gpu
+def test_unary_block_store_equals_coo_store():
+    """Unary relations as columns of a relation-owned bit block (hirm_unary_block_create / hirm_irm_set_observations_unary)
+    against the same relations as CSR entries: same count tables, bit-identical candidates and log-probabilities, same
+    choices; partially observed unary relations, an IRM using a subset of the block's columns, block errors."""
+    from hirm import engine as E
+    rng = np.random.default_rng(8)
+    n, m = 90, 40
+    unary = []
+    for k in range(37):                                           # more than one mask word
+        keep = np.flatnonzero(rng.random(n) < (1.0 if k % 3 else 0.6)).astype(np.int32)
+        unary.append((keep[:, None], rng.integers(0, 2, len(keep)).astype(np.uint8)))
+    grid = np.stack(np.meshgrid(np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 2)
+    b_ee = grid[rng.random(len(grid)) < 0.2].astype(np.int32)
+    grid2 = np.stack(np.meshgrid(np.arange(n), np.arange(m), indexing="ij"), -1).reshape(-1, 2)
+    b_ef = grid2[rng.random(len(grid2)) < 0.5].astype(np.int32)
+    others = [(b_ee, rng.integers(0, 2, len(b_ee)).astype(np.uint8)), (b_ef, rng.integers(0, 2, len(b_ef)).astype(np.uint8))]
+    eng = E.Engine(0)
+    dev = [_torch_coo(i, v) for i, v in unary]
+    blk = eng.unary_block_create(n, [(len(v), ti.data_ptr(), tv.data_ptr()) for (i, v), (ti, tv) in zip(unary, dev)])
+    pick = [0, 3, 4, 7, 11, 12, 20, 31, 32, 33, 36]               # the IRM holds a subset of the block's relations
+    rel_domains = [[0]] * len(pick) + [[0, 0], [0, 1]]
+    z = [rng.integers(0, 5, n).astype(np.int32), rng.integers(0, 3, m).astype(np.int32)]
+    hs = []
+    for use_block in (False, True):
+        h = eng.irm_create([n, m], rel_domains, max_tables=24)
+        for k, col in enumerate(pick):
+            if use_block:
+                eng.set_observations_unary(h, k, blk, col)
+            else:
+                eng.set_observations(h, k, *unary[col])
+        for k, (i, v) in enumerate(others):
+            eng.set_observations(h, len(pick) + k, i, v)
+        eng.finalize(h)
+        for d in range(2):
+            eng.set_assignments(h, d, z[d])
+        hs.append(h)
+    for r in range(len(rel_domains)):
+        np.testing.assert_array_equal(eng.get_counts(hs[0], r), eng.get_counts(hs[1], r))
+    for sweep in range(3):
+        md = np.concatenate([np.full(k, d, np.int32) for d, k in enumerate((n, m))])
+        mi = np.concatenate([rng.permutation(k).astype(np.int32) for k in (n, m)])
+        res = eng.sweep(hs, [(md, mi), (md, mi)], seed=9, streams=[4, 4], counters=[sweep * len(mi)] * 2, trace_cap=32)
+        np.testing.assert_array_equal(res["choice"][0], res["choice"][1])
+        np.testing.assert_array_equal(res["trace"][0][1], res["trace"][1][1])
+        np.testing.assert_array_equal(res["trace"][0][2], res["trace"][1][2])
+        for r in range(len(rel_domains)):
+            np.testing.assert_array_equal(eng.get_counts(hs[0], r), eng.get_counts(hs[1], r))
+    assert len(np.unique(eng.get_assignments(hs[1], 0))) > 1
+    # relation scores under another IRM's partitions read the block columns' COO arrays
+    sc = eng.relation_score_matrix([([0], len(unary[c][1]), dev[c][0].data_ptr(), dev[c][1].data_ptr()) for c in pick[:4]], [hs[0], hs[1]])
+    np.testing.assert_array_equal(sc[:, 0], sc[:, 1])
+    dup_i, dup_v = _torch_coo(np.array([[1], [1]], np.int32), np.array([0, 1], np.uint8))
+    with pytest.raises(E.EngineError, match="twice"):
+        eng.unary_block_create(n, [(2, dup_i.data_ptr(), dup_v.data_ptr())])
+    eng.close()
+
+
+@pytest.mark.gpu
 def test_relation_score_matrix_fresh_scores_and_prior_draw_vs_restatements():
     from hirm import engine as E
     eng = E.Engine(0)
