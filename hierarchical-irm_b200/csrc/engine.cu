@@ -132,6 +132,7 @@ struct hirm_engine {
     struct UnaryBits { DevBuf<uint32_t> obs, val; int64_t nobs = 0; int32_t n_ent = 0; const uint8_t *val_src = nullptr; };
     std::map<std::pair<const int32_t *, const uint8_t *>, UnaryBits> unary_cache;   // keyed by the (ids, val) buffers: relations may share an ids buffer
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_cluster = 1;              // CTAs per IRM of the last generic launch
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
     int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0, dense_static_smem = 0, dense_static_smem_large = 0, gen_regs = 64, gen_static_smem = 12 * 1024;
     long long *d_phase_cycles = nullptr;   // debug hook (hirm_engine_debug_phase_cycles)
@@ -1471,6 +1472,22 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
     return 0;
 }
 
+// CTAs per IRM of a generic launch: a thread-block cluster per IRM when the GPU has SMs to spare and a move is heavy
+// (long rows or many groups), or when the caller asks for it (HIRM_SWEEP_CLUSTER); results do not depend on it.
+static int pick_cluster_size(hirm_engine *e, const Plan &plan, uint32_t flags) {
+    const int n_gen = (int)plan.generic_blk.size();
+    if (const char *s = getenv("HIRM_CLUSTER_SIZE")) {
+        int c = atoi(s), p = 1;
+        while (p * 2 <= c && p < 16) p *= 2;
+        return std::max(1, p);
+    }
+    const bool heavy = plan.gen_maxdeg >= 1536 || plan.gen_groups >= 384;
+    if (!(flags & HIRM_SWEEP_CLUSTER) && !heavy) return 1;
+    int c = 1;
+    while (c < 16 && (int64_t)n_gen * c * 2 <= e->num_sms) c *= 2;
+    return c;
+}
+
 static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args) {
     e->last_launches = 0; e->last_kind = -1;
     CK(cudaEventRecord(e->ev0, e->stream));
@@ -1482,7 +1499,9 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         //  128 threads 5.8 M moves/s, 592 at 256 threads 10.5 M)
         int gen_threads = n_gen <= e->num_sms ? 1024 : (n_gen <= 4 * e->num_sms || plan.gen_maxdeg > 512) ? 256 : 128;
         if (const char *s = getenv("HIRM_GENERIC_THREADS")) gen_threads = std::max(64, std::min(1024, atoi(s) & ~31));
+        int csize = pick_cluster_size(e, plan, args.flags);
         GenericLaunch GL;
+        GL.csize = csize;
         GL.pcap = 4 * gen_threads;
         GL.kstride = (std::max(plan.gen_kmax, 2) + 2) & ~1;
         GL.ndom = std::max(plan.gen_ndom, 1); GL.roww = 1 + std::max(plan.gen_nother, 1);
@@ -1493,26 +1512,49 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         const int rcap_want = std::max(128, (int)((std::min<int64_t>(plan.gen_groups, 1 << 20) + 31) & ~31));
         int want_ctas = std::max(1, std::min(std::min(2048 / gen_threads, 65536 / (e->gen_regs * gen_threads)), (n_gen + e->num_sms - 1) / e->num_sms));
         const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww) + (size_t)e->gen_static_smem;
+        const int accs = csize > 1 ? 2 : 1;              // cluster: a local and a merged accumulator per CTA
         // the accumulator decides how many CTAs share an SM (a global accumulator costs far more than a lost CTA); the group
         // records take what is left of the CTA's share, the rest of a long group list lives in the IRM's global scratch
         for (;; want_ctas--) {
             const size_t budget = (size_t)std::min(e->max_smem_optin, e->smem_per_sm / want_ctas - 1024);
             const size_t room = budget > fixed ? budget - fixed : 0;
-            if ((size_t)scap_want * 4 + 128 * 52 <= room || want_ctas == 1) {
-                GL.scap = (int)std::min<size_t>((size_t)scap_want, room > 128 * 52 ? ((room - 128 * 52) / 4) & ~(size_t)31 : 0);
+            if ((size_t)scap_want * 4 * accs + 128 * 52 <= room || want_ctas == 1) {
+                GL.scap = (int)std::min<size_t>((size_t)scap_want, room > 128 * 52 ? ((room - 128 * 52) / (4 * accs)) & ~(size_t)31 : 0);
                 if (GL.scap < 256) GL.scap = 256;
-                const size_t left = room > (size_t)GL.scap * 4 ? room - (size_t)GL.scap * 4 : 0;
+                const size_t left = room > (size_t)GL.scap * 4 * accs ? room - (size_t)GL.scap * 4 * accs : 0;
                 GL.rcap = (int)std::min<size_t>((size_t)rcap_want, (left / 52) & ~(size_t)31);
                 if (GL.rcap < 128) GL.rcap = 128;
                 break;
             }
         }
-        const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww);
+        const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww, csize);
         if (gen_smem > (size_t)e->max_smem_optin) return fail("generic kernel: shared-memory plan exceeds the device limit");
         CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem));
-        generic_sweep_kernel<<<(unsigned)n_gen, gen_threads, gen_smem, e->stream>>>(args, e->s_blk.p, GL);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.blockDim = dim3((unsigned)gen_threads); cfg.dynamicSmemBytes = gen_smem; cfg.stream = e->stream;
+        cudaLaunchAttribute attr[1];
+        const int32_t *blk = e->s_blk.p;
+        for (;; csize /= 2) {
+            GL.csize = csize;
+            cfg.gridDim = dim3((unsigned)n_gen * (unsigned)csize);
+            cfg.numAttrs = 0; cfg.attrs = nullptr;
+            if (csize > 1) {
+                CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, csize > 8 ? 1 : 0));
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                int n_clusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&n_clusters, generic_sweep_kernel, &cfg) != cudaSuccess || n_clusters < std::min(n_gen, 1)) {
+                    cudaGetLastError();
+                    continue;                                  // this cluster size cannot be placed: halve it
+                }
+            }
+            break;
+        }
+        CK(cudaLaunchKernelEx(&cfg, generic_sweep_kernel, args, blk, GL));
         CK(cudaGetLastError());
-        e->last_launches++; e->last_kind = 0;
+        e->last_launches++; e->last_kind = 0; e->last_cluster = csize;
     }
     if (!plan.dense_blk.empty()) {
         const unsigned nb = (unsigned)plan.dense_blk.size();
@@ -1696,6 +1738,12 @@ extern "C" int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, 
         CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
         *kernel_ms = e->last_ms;
     }
+    return 0;
+}
+
+extern "C" int hirm_engine_last_cluster_size(hirm_engine *e, int32_t *ctas_per_irm) {
+    if (!e || !ctas_per_irm) return fail("null argument");
+    *ctas_per_irm = e->last_cluster;
     return 0;
 }
 

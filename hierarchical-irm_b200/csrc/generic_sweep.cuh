@@ -19,6 +19,7 @@
 // Count tables change by integer atomics only (bit-exact); the group list is ordered, so log-probabilities are
 // deterministic.
 #pragma once
+#include <cooperative_groups.h>
 #include "engine_types.cuh"
 
 namespace hirm {
@@ -146,22 +147,44 @@ __device__ __forceinline__ double score_delta_any(const double *lf, uint32_t N, 
 
 // Dynamic shared memory of one CTA: [rcap] group records, [rcap] touched accumulator cells, [pcap] partial sums,
 // [scap] 32-bit accumulator cells.
-struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww; };   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids)
-__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap) {
-    return (size_t)rcap * (sizeof(GroupRec) + 4) + (size_t)pcap * 8 + (size_t)scap * 4 + 16;
+struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww, csize; };   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids); csize: CTAs per IRM (thread-block cluster)
+__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int csize = 1) {
+    return (size_t)rcap * (sizeof(GroupRec) + 4) + (size_t)pcap * 8 + (size_t)scap * 4 * (csize > 1 ? 2 : 1) + 16;   // cluster: local + merged accumulator
 }
 // + [2][roww][threads] words: the first `threads` entries of the next move's CSR row (meta + other ids), copied
 // asynchronously one move ahead
 // + [ndom][kstride] (double + 2 int32): resident CRP state of every domain
-__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int threads, int kstride, int ndom, int roww) {
-    return generic_smem_bytes(rcap, pcap, scap) + (size_t)2 * roww * threads * 4 + 8 + (size_t)ndom * kstride * 16;
+__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int threads, int kstride, int ndom, int roww, int csize = 1) {
+    return generic_smem_bytes(rcap, pcap, scap, csize) + (size_t)2 * roww * threads * 4 + 8 + (size_t)ndom * kstride * 16;
 }
 
+// Thread-block cluster per IRM (north_star subsystem 3).  The moves of one IRM are sequential, so an IRM that is alone
+// on the GPU (an HIRM with a handful of relation clusters, a single chain) can only be made faster WITHIN a move: launched
+// as a cluster of C CTAs (C SMs), the CTAs split the entity's row (phase A) and the (candidate x group) scoring units
+// (phase D) and exchange through distributed shared memory:
+//   A   CTA q takes every C-th chunk of the CSR row / unary columns into its LOCAL accumulator
+//   --  cluster barrier; every CTA adds its non-empty cells into the MERGED accumulator of all C CTAs (remote shared
+//       atomics); cluster barrier: the merged accumulators are identical
+//   B   group list and records, redundantly per CTA from its merged accumulator (no exchange)
+//   D   unit u is scored by CTA u mod C, the partial sum stored into every CTA's s_part[u]; cluster barrier; every
+//       CTA adds the partials in unit order -- the same additions in the same order for every C, so results do not depend
+//       on the cluster size
+//   E   sampled redundantly (same log-probabilities, same uniform)
+//   F   count-table atomics of group g by CTA g mod C; z / CRP state written by every CTA (identical values), so each
+//       CTA reads back its own writes; the next cluster barrier (after the next A) orders the table updates before the
+//       next scoring
+// With C = 1 (no cluster attribute) the barriers are __syncthreads() and there is one accumulator.
+
 __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs args, const int32_t *blk_list, GenericLaunch GL) {
-    const int k_list = blk_list ? blk_list[blockIdx.x] : blockIdx.x;
+    namespace cg = cooperative_groups;
+    const int C = GL.csize > 1 ? GL.csize : 1;                 // CTAs of this IRM's cluster
+    const int crank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
+    const int k_blk = (int)blockIdx.x / C;
+    const int k_list = blk_list ? blk_list[k_blk] : k_blk;
     const IrmDev &irm = args.irms[args.irm_ids[k_list]];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NT = blockDim.x, NW = NT >> 5;
+    auto csync = [&]() { if (C > 1) cg::this_cluster().sync(); else __syncthreads(); };
 
     // CRP state of every domain (table sizes, labels, highest used slot + 1), resident for the whole move list: only
     // this CTA changes it (phase F writes shared and global copies alike)
@@ -178,8 +201,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     const int64_t glcap = irm.gl_cap;
     GroupRec *s_recs = reinterpret_cast<GroupRec *>(gen_dyn);                                  // [rcap]
     double *s_part = reinterpret_cast<double *>(s_recs + RCAP);                                 // [pcap]
-    uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_part + PCAP);                              // [scap] observations | ones << 16
-    int32_t *s_bits = reinterpret_cast<int32_t *>(s_acc + SCAP);                                // [rcap]
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_part + PCAP);                              // [scap] observations | ones << 16 (cluster: this CTA's share of the row)
+    uint32_t *s_accm = C > 1 ? s_acc + SCAP : s_acc;                                            // [scap] cluster: the merged accumulator
+    int32_t *s_bits = reinterpret_cast<int32_t *>(s_accm + SCAP);                               // [rcap]
     uint32_t *s_row = reinterpret_cast<uint32_t *>(s_bits + RCAP);                              // [2][roww][NT] next / current CSR row heads
     const int KS = GL.kstride;
     const int ROWW = GL.roww;
@@ -188,7 +212,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     int32_t *s_lab_all = s_cnt_all + GL.ndom * KS;
 
     for (int k = tid; k < GEN_LF; k += NT) s_lf[k] = g_logfact[k];
-    for (int k = tid; k < SCAP; k += NT) s_acc[k] = 0u;
+    for (int k = tid; k < SCAP; k += NT) { s_acc[k] = 0u; s_accm[k] = 0u; }
     for (int dk = 0; dk < irm.n_domains; dk++) {
         const DomainDev &dq = irm.dom[dk];
         const int h = __ldcg(dq.hi);
@@ -243,7 +267,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         const int dm = s_pd[k];
         if (mm >= m1 || dm < 0 || tid >= NA) return;
         const DomainDev &dq = irm.dom[dm];
-        const int64_t q = s_pb[k][0] + tid;
+        const int64_t q = s_pb[k][0] + (int64_t)crank * NA + tid;      // the head of this CTA's share of the row (chunk `crank`)
         if (!dq.ptr || q >= s_pb[k][1]) return;
         uint32_t *dst = s_row + ((size_t)buf * ROWW) * NT + tid;
         cp4(dst, dq.meta + q);
@@ -292,7 +316,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         const int hi = s_hi_all[d];
         const int ctot = irm.ctot[d];
         const bool acc_shared = ctot <= SCAP && dd.max_deg < 65535;   // the move's accumulator: shared memory, or the IRM's global scratch
-        const AccView acc{acc_shared ? s_acc : nullptr, irm.gacc};
+        const AccView acc{acc_shared ? s_accm : nullptr, irm.gacc};   // (phase A adds into s_acc; with C = 1 they are the same array)
         const RelDom *rdesc = irm.rdesc + d;           // descriptor of relation r: rdesc[r * n_domains]
 
         // ---- C: candidates, CRP::tables_weights_gibbs (cxx/hirm.hh:147-161): the last warp, while the others stream the row ----
@@ -341,9 +365,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
 
         // ---- A: group (and, for twice-occurring domains, remove) -------------------------------------------------
         if (dd.ptr && tid < NA) {
-            const int64_t beg = cur.beg, end = cur.end;
+            const int64_t beg = cur.beg + (int64_t)crank * NA, end = cur.end;      // cluster: CTA q takes chunks q, q + C, q + 2C, ... of NA entries
             const uint32_t *rowbuf = s_row + ((size_t)rbuf * ROWW) * NT + tid;
-            for (int64_t q = beg + tid; q < end; q += NA) {
+            for (int64_t q = beg + tid; q < end; q += (int64_t)NA * C) {
                 const bool head = q < beg + NA;                   // prefetched into shared memory one move ahead
                 const uint32_t meta = head ? rowbuf[0] : dd.meta[q];
                 const int rel = meta & META_REL_MASK;
@@ -377,7 +401,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         // and one accumulator cell per relation, so a plain store does it
         if (dd.ub_words && tid < NA) {
             const uint32_t *xo = dd.ub_obs + (int64_t)item * dd.ub_words, *xv = dd.ub_val + (int64_t)item * dd.ub_words;
-            for (int k = tid; k < dd.ub_words * 32; k += NA) {
+            for (int k = crank * NA + tid; k < dd.ub_words * 32; k += NA * C) {
                 const int w = k >> 5;
                 const uint32_t ob = __ldg(xo + w) & __ldg(dd.ub_mask + w);      // the warp reads one word: a broadcast
                 if ((ob >> (k & 31)) & 1u) {
@@ -388,10 +412,22 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 }
             }
         }
-        // One CTA owns the IRM: __syncthreads() alone makes the block's global atomics and stores visible to the block
+        // One CTA (or one cluster) owns the IRM: the barrier alone makes the global atomics and stores visible to its threads
         // (they are performed at L2, and every mutable word is read back with ld.cg).  No __threadfence(): a gpu-scope
         // fence would also invalidate L1 and send every descriptor load of the next phase back to L2.
-        __syncthreads();
+        csync();
+        if (C > 1 && acc_shared) {
+            // merge: every CTA adds its non-empty cells into the merged accumulator of all C CTAs (distributed shared memory)
+            cg::cluster_group cl = cg::this_cluster();
+            for (int cellv = tid; cellv < ctot; cellv += NT) {
+                const uint32_t v = s_acc[cellv];
+                if (v) {
+                    s_acc[cellv] = 0u;
+                    for (int r = 0; r < C; r++) atomicAdd(cl.map_shared_rank(s_accm, r) + cellv, v);
+                }
+            }
+            cl.sync();
+        }
         GEN_PHASE(0);
 
         // ---- B1: ordered list of the touched accumulator cells (bitmap scan: ascending cell = deterministic order) ----
@@ -406,7 +442,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 const int wbase = w0 + warp * 32;
                 for (int j = 0; j < 32 && wbase + j < nwords; j++) {
                     const int cellv = (wbase + j) * 32 + lane;
-                    const uint32_t b = __ballot_sync(0xffffffffu, cellv < ctot && s_acc[cellv] != 0u);
+                    const uint32_t b = __ballot_sync(0xffffffffu, cellv < ctot && s_accm[cellv] != 0u);
                     if (lane == j) bits = b;
                 }
             } else if (w < nwords) bits = __ldcg(&irm.gbm[w]);
@@ -500,11 +536,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         const bool flat = (int64_t)ncand * nch <= PCAP;
         if (flat) {
             const int nunits = ncand * nch;
+            const int u0 = crank + warp * C, ustep = NW * C;       // unit u belongs to CTA u mod C, warp (u / C) mod NW
             Pending pend{0ull, 0ull, 0ull};
-            if (warp < nunits) { const int t0 = warp / nch; pend = issue((int64_t)(warp - t0 * nch) * 32 + lane, s_cslot[t0]); }
-            for (int unit = warp; unit < nunits; unit += NW) {
+            if (u0 < nunits) { const int t0 = u0 / nch; pend = issue((int64_t)(u0 - t0 * nch) * 32 + lane, s_cslot[t0]); }
+            for (int unit = u0; unit < nunits; unit += ustep) {
                 const Pending cur = pend;
-                const int nu = unit + NW;
+                const int nu = unit + ustep;
                 if (nu < nunits) { const int t2 = nu / nch; pend = issue((int64_t)(nu - t2 * nch) * 32 + lane, s_cslot[t2]); }
                 uint32_t N, sv, gn, gs;
                 finish(cur, N, sv, gn, gs);
@@ -512,16 +549,17 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 double v = score_delta_any(s_lf, N, sv, gn, gs);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) s_part[unit] = v;
+                if (C == 1) { if (lane == 0) s_part[unit] = v; }
+                else if (lane < C) cg::this_cluster().map_shared_rank(s_part, lane)[unit] = v;     // lane r stores into CTA r's s_part
             }
-            __syncthreads();
+            csync();
             for (int t = tid; t < ncand; t += NT) {
                 double a2 = 0.0;
                 for (int ch = 0; ch < nch; ch++) a2 += s_part[t * nch + ch];
                 s_lp[t] += a2;
             }
         } else {
-            for (int t = warp; t < ncand; t += NW) {   // very many groups: one warp per candidate walks all of them
+            for (int t = crank + warp * C; t < ncand; t += NW * C) {   // very many groups: one warp per candidate walks all of them
                 const int slot_t = s_cslot[t];
                 double a2 = 0.0;
                 for (int64_t g0 = 0; g0 < ngroups; g0 += 32) {
@@ -533,8 +571,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     a2 += v;
                 }
-                if (lane == 0) s_lp[t] += a2;
+                if (C == 1) { if (lane == 0) s_part[t] = a2; }
+                else if (lane < C) cg::this_cluster().map_shared_rank(s_part, lane)[t] = a2;
             }
+            csync();
+            for (int t = tid; t < ncand; t += NT) s_lp[t] += s_part[t];
         }
         __syncthreads();
         GEN_PHASE(3);
@@ -583,13 +624,15 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         const int tnew = s_choice_slot;
         for (int64_t g = tid; g < ngroups; g += NT) {
             const GroupRec gr = g < RCAP ? s_recs[g] : recs[g];
-            if (tnew != c) {                          // Relation::set_cluster_assignment_gibbs (:524-551): every observation leaves its cell for the new one
+            const bool mine = C == 1 || (int)(g % C) == crank;       // cluster: the table updates of group g are CTA (g mod C)'s
+            if (tnew != c && mine) {                  // Relation::set_cluster_assignment_gibbs (:524-551): every observation leaves its cell for the new one
                 table_add(irm, gr.R, group_cell_at(gr, c), (cell_t)0 - gr.own);
                 table_add(irm, gr.R, group_cell_at(gr, tnew), gr.own);
             }
-            if (acc_shared) s_acc[gr.cell] = 0u;
-            else { __stcg(&irm.gacc[gr.cell], (cell_t)0); __stcg(&irm.gbm[gr.cell >> 5], 0u); }
+            if (acc_shared) s_accm[gr.cell] = 0u;     // every CTA clears its own (merged) accumulator
+            else if (mine) { __stcg(&irm.gacc[gr.cell], (cell_t)0); __stcg(&irm.gbm[gr.cell >> 5], 0u); }
         }
+        // z and the CRP state: written by every CTA of a cluster (identical values), so each CTA reads back its own writes
         if (tid == 0 && tnew != c) {
             __stcg(&dd.z[item], tnew);
             __stcg(&dd.tab_count[c], s_cnt[c] - 1);
@@ -610,10 +653,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             const int k1 = (ring + 1) & 3;             // the same entity again: its prefetched slot is stale
             if (tnew != c && s_pd[k1] == d && s_pi[k1] == item) s_pc[k1] = tnew;
         }
-        __syncthreads();
+        if (C > 1 && !acc_shared) cg::this_cluster().sync();   // global accumulator: cleared before any CTA's next phase A adds to it
+        else __syncthreads();
         GEN_PHASE(5);
     }
-    if (prof) for (int i = 0; i < 6; i++) args.phase_cycles[blockIdx.x * 32 + i] = ph_acc[i];
+    if (prof && crank == 0) for (int i = 0; i < 6; i++) args.phase_cycles[k_blk * 32 + i] = ph_acc[i];
+    if (C > 1) cg::this_cluster().sync();                      // no CTA exits while another may still address its shared memory
 #undef GEN_PHASE
 }
 

@@ -36,7 +36,7 @@ EXPORTS = [
     "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
     "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters", "hirm_engine_clear_relation_cache",
     "hirm_engine_seat_prior", "hirm_irm_set_table_mode", "hirm_unary_block_create", "hirm_unary_block_destroy",
-    "hirm_irm_set_observations_unary",
+    "hirm_irm_set_observations_unary", "hirm_engine_last_cluster_size",
     "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
     "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
 ]
@@ -110,6 +110,7 @@ def load():
     L.hirm_unary_block_create.argtypes = [V, ctypes.c_int32, I, c_i64p, ctypes.POINTER(V), ctypes.POINTER(V), c_i32p]
     L.hirm_unary_block_destroy.argtypes = [V, ctypes.c_int32]
     L.hirm_irm_set_observations_unary.argtypes = [V, ctypes.c_int32, I, ctypes.c_int32, I]
+    L.hirm_engine_last_cluster_size.argtypes = [V, c_i32p]
     L.hirm_irm_set_rng_counters.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
     L.hirm_engine_crp_prior_draw.argtypes = [V, I, ctypes.c_double, I, ctypes.c_uint64, ctypes.c_uint64, c_i32p]
     CP = ctypes.POINTER(ctypes.c_char_p)
@@ -335,7 +336,9 @@ class Engine:
     def last_sweep_info(self):
         n, k, ms = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_float()
         self._ck(self.L.hirm_engine_last_sweep_info(self._h, ctypes.byref(n), ctypes.byref(k), ctypes.byref(ms)))
-        return dict(launches=n.value, kernel_kind=k.value, kernel_ms=ms.value)
+        c = ctypes.c_int32()
+        self._ck(self.L.hirm_engine_last_cluster_size(self._h, ctypes.byref(c)))
+        return dict(launches=n.value, kernel_kind=k.value, kernel_ms=ms.value, cluster_size=c.value)
 
     def sweep_all(self, irms, n_sweeps=1, seed=0, flags=0, want_moves=False):
         """transition_cluster_assignments_all for every listed IRM, order generated on the device.
@@ -480,8 +483,8 @@ class Engine:
 class IrmBackend:
     """score/move/get_* view of one engine IRM (what tests/golden_util.replay drives)."""
 
-    def __init__(self, engine, irm):
-        self.e, self.irm = engine, irm
+    def __init__(self, engine, irm, flags=0):
+        self.e, self.irm, self.flags = engine, irm, flags      # flags: e.g. SWEEP_CLUSTER (same results, cluster launch)
 
     def set_alpha(self, dom, alpha):
         self.e.set_alpha(self.irm, dom, alpha)
@@ -508,10 +511,10 @@ class IrmBackend:
         return float(alpha[0, dom]), lp[0, dom]
 
     def score(self, dom, item, cap=256):
-        r = self.e.sweep([self.irm], [([dom], [item])], flags=SWEEP_SCORE_ONLY, trace_cap=cap)
+        r = self.e.sweep([self.irm], [([dom], [item])], flags=SWEEP_SCORE_ONLY | self.flags, trace_cap=cap)
         n, labels, lp = r["trace"][0]
         return labels[0, :n[0]].copy(), lp[0, :n[0]].copy()
 
     def move(self, dom, item, u):
-        r = self.e.sweep([self.irm], [([dom], [item])], uniforms=[[u]])
+        r = self.e.sweep([self.irm], [([dom], [item])], uniforms=[[u]], flags=self.flags)
         return int(r["choice"][0][0])

@@ -39,7 +39,9 @@ typedef struct hirm_engine hirm_engine;
 /* sweep flags */
 #define HIRM_SWEEP_SCORE_ONLY 1u   /* score + trace, do not sample/apply (parity hook) */
 #define HIRM_SWEEP_FORCE_GENERIC 2u /* use the CSR/generic kernel even where a fast path exists */
-#define HIRM_SWEEP_CLUSTER 4u      /* reserved: one thread-block cluster per IRM (single-chain latency mode); ignored today */
+#define HIRM_SWEEP_CLUSTER 4u      /* one thread-block cluster per IRM (up to 16 CTAs share a move's row and scoring units through
+                                      distributed shared memory) even when the engine's heuristic would not choose it; the engine uses
+                                      clusters by itself when few IRMs with heavy moves are swept.  Results do not depend on it. */
 
 const char *hirm_last_error(void);
 int hirm_engine_abi_version(void);
@@ -214,8 +216,11 @@ int hirm_engine_crp_prior_draw(hirm_engine *e, int n, double alpha, int max_tabl
 /* Domain::incorporate(item, table) for entities not yet in the domain (cxx/hirm.hh:194-203) */
 int hirm_irm_seat_entities(hirm_engine *e, int32_t irm, int dom, int n, const int32_t *h_items, const int32_t *h_labels);
 
-/* statistics of the last sweep: kernel launches made, which kernel ran (0 generic, 1 dense, 2 dense-cluster) */
+/* statistics of the last sweep: kernel launches made, which kernel ran (0 generic, 1 dense) */
 int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, int32_t *kernel_kind, float *kernel_ms);
+
+/* CTAs per IRM (thread-block cluster size) of the last generic launch */
+int hirm_engine_last_cluster_size(hirm_engine *e, int32_t *ctas_per_irm);
 
 /* shared-memory plan of the last dense launch: resident CTAs (chains) per SM, TMA ring stages, bytes per
  * row chunk, dynamic shared memory per CTA */
