@@ -5,10 +5,10 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "engine.cu")
-SRC_HOST = os.path.join(HERE, "csrc", "ingest.cc")
+SRC_HOST = [os.path.join(HERE, "csrc", f) for f in ("ingest.cc", "relation_moves.cc")]
 LIB = os.path.join(HERE, "libhirm_engine.so")
 DEPS = [os.path.join(HERE, "csrc", f) for f in
-        ("engine.cu", "engine_types.cuh", "device_math.cuh", "generic_sweep.cuh", "dense_sweep.cuh", "aux_kernels.cuh", "ingest.cc")] + \
+        ("engine.cu", "engine_types.cuh", "device_math.cuh", "generic_sweep.cuh", "dense_sweep.cuh", "aux_kernels.cuh", "ingest.cc", "relation_moves.cc")] + \
        [os.path.join(os.path.dirname(HERE), "include", "hirm_engine.h")]
 
 
@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build the CUDA engine (there is no CPU fallback)")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177", "-o", LIB, SRC, SRC_HOST]
+           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177", "-o", LIB, SRC] + SRC_HOST
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -14,6 +14,11 @@ namespace hirm {
 // ---------------------------------------------------------------------------------
 constexpr int LF_SIZE = 4096;
 __device__ double g_logfact[LF_SIZE];
+// log(m) for integers m < LOGTAB_SIZE (libm's log, filled once per device by the engine; 8 MB, L2-resident): the score of a
+// group of a few observations is a short sum of logarithms of integer counts -- table look-ups instead of ~45 dependent
+// fp64 instructions per logarithm.  Counts beyond the table take log_core.
+constexpr uint32_t LOGTAB_SIZE = 1u << 20;
+__device__ const double *g_logtab;
 
 __device__ __forceinline__ double stirling_corr(double y) {
     // lgamma(y) - [(y-1/2) ln y - y + ln(2 pi)/2] for y >= LF_SIZE: three terms are < 1e-30 off

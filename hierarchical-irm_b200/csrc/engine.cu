@@ -182,6 +182,22 @@ extern "C" int hirm_engine_create(hirm_engine **out, int device) {
     std::vector<double> lf(LF_SIZE);
     for (int m = 0; m < LF_SIZE; m++) lf[m] = lgamma((double)m + 1.0);
     CK(cudaMemcpyToSymbol(g_logfact, lf.data(), sizeof(double) * LF_SIZE));
+    {   // log(m), m < LOGTAB_SIZE (entry 0 unused), for the scores of small groups
+        std::vector<double> lt;
+        if (true) {
+            lt.resize(LOGTAB_SIZE);
+            lt[0] = 0.0;
+            for (uint32_t m = 1; m < LOGTAB_SIZE; m++) lt[m] = log((double)m);
+        }
+        static std::map<int, double *> tab_of_device;          // one table per device for the life of the process (engines come and go)
+        double *&p = tab_of_device[device];
+        if (!p) {
+            CK(cudaMalloc((void **)&p, sizeof(double) * LOGTAB_SIZE));
+            CK(cudaMemcpy(p, lt.data(), sizeof(double) * LOGTAB_SIZE, cudaMemcpyHostToDevice));
+        }
+        const double *cp = p;
+        CK(cudaMemcpyToSymbol(g_logtab, &cp, sizeof(cp)));
+    }
     *out = e.release();
     return 0;
 }
@@ -1104,7 +1120,7 @@ static int run_score_job(hirm_engine *e, ScoreJob &J, double *h_out) {
             off += (size_t)nr;
         }
     }
-    if (J.out_count) CK(cudaMemcpyAsync(h_out, e->s_score.p, J.out_count * sizeof(double), cudaMemcpyDeviceToHost, s0));
+    if (J.out_count) CK(cudaMemcpyAsync(h_out, e->s_score.p, J.out_count * sizeof(double), cudaMemcpyDefault, s0));   // host or device destination
     int32_t err = 0;
     CK(cudaMemcpyAsync(&err, e->s_relerr.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
     CK(cudaStreamSynchronize(s0));                      // the job vectors are the sources of the async copies

@@ -113,21 +113,33 @@ __device__ __forceinline__ int64_t group_cell_at(const GroupRec &g, int t) {
 }
 
 // S(N+1, s+x) - S(N, s) for a group of ONE observation (every group of a unary relation, most groups of a sparse one):
-// log(s + 1) - log(N + 2) if x = 1, log(N - s + 1) - log(N + 2) if x = 0 -- two logarithms instead of the general
-// form's six; gn = 0 (a lane without work) gives 0.
-__device__ __forceinline__ double score_delta_unit(uint32_t N, uint32_t sv, uint32_t gn, uint32_t gs) {
-    const double a = gs ? (double)sv + 1.0 : (double)(N - sv) + 1.0;
-    const double v = log_core(a) - log_core((double)N + 2.0);
+// log(s + 1) - log(N + 2) if x = 1, log(N - s + 1) - log(N + 2) if x = 0 -- two logarithms of integers instead of the
+// general form's six; gn = 0 (a lane without work) gives 0.  `lt` is the table of log(m), m < LOGTAB_SIZE.
+__device__ __forceinline__ double score_delta_unit(const double *lt, uint32_t N, uint32_t sv, uint32_t gn, uint32_t gs) {
+    const uint32_t a = gs ? sv + 1u : N - sv + 1u;
+    double v;
+    if (N + 2u < LOGTAB_SIZE) v = __ldg(lt + a) - __ldg(lt + N + 2u);
+    else v = log_core((double)a) - log_core((double)N + 2.0);
     return gn ? v : 0.0;
 }
 
-// Groups of a few observations (a sparse relation's typical group): the factorial ratios written out as products,
-//   S(N+n, s+sg) - S(N, s) = log[ prod_{j<sg} (s+1+j) * prod_{j<n-sg} (N-s+1+j) ] - log[ prod_{j<n} (N+2+j) ],
-// two logarithms and 2n multiplications instead of six logarithms and nine reciprocals.  `nmax` >= every lane's gn is
-// warp-uniform and at most 16, so each product stays below 2^512.
-__device__ __forceinline__ double score_delta_small(uint32_t N, uint32_t sv, uint32_t gn, uint32_t gs, int nmax) {
-    double pnum = 1.0, pden = 1.0;
+// Groups of a few observations (a sparse relation's typical group): the factorial ratios written out,
+//   S(N+n, s+sg) - S(N, s) = sum_{j<sg} log(s+1+j) + sum_{j<n-sg} log(N-s+1+j) - sum_{j<n} log(N+2+j),
+// from the table of integer logarithms (consecutive entries: one or two cache lines per sum) -- or, for counts beyond
+// the table, as products: two logarithms and 2n multiplications.  `nmax` >= every lane's gn is warp-uniform and at most
+// 16, so each product stays below 2^512.
+__device__ __forceinline__ double score_delta_small(const double *lt, uint32_t N, uint32_t sv, uint32_t gn, uint32_t gs, int nmax) {
     const uint32_t gf = gn - gs;
+    if (__all_sync(0xffffffffu, N + 18u < LOGTAB_SIZE)) {
+        double num = 0.0, den = 0.0;
+        for (int j = 0; j < nmax; j++) {
+            if ((uint32_t)j < gs) num += __ldg(lt + sv + 1u + j);
+            if ((uint32_t)j < gf) num += __ldg(lt + (N - sv) + 1u + j);
+            if ((uint32_t)j < gn) den += __ldg(lt + N + 2u + j);
+        }
+        return num - den;
+    }
+    double pnum = 1.0, pden = 1.0;
     for (int j = 0; j < nmax; j++) {
         const double a = (uint32_t)j < gs ? (double)sv + (double)(j + 1) : 1.0;
         const double b = (uint32_t)j < gf ? (double)(N - sv) + (double)(j + 1) : 1.0;
@@ -138,10 +150,10 @@ __device__ __forceinline__ double score_delta_small(uint32_t N, uint32_t sv, uin
     return log_core(pnum) - log_core(pden);
 }
 // the cell score of a warp's 32 groups, by the cheapest form that fits all of them (warp-uniform choice)
-__device__ __forceinline__ double score_delta_any(const double *lf, uint32_t N, uint32_t sv, uint32_t gn, uint32_t gs) {
+__device__ __forceinline__ double score_delta_any(const double *lf, const double *lt, uint32_t N, uint32_t sv, uint32_t gn, uint32_t gs) {
     const int nmax = (int)__reduce_max_sync(0xffffffffu, gn);
-    if (nmax <= 1) return score_delta_unit(N, sv, gn, gs);
-    if (nmax <= 16) return score_delta_small(N, sv, gn, gs, nmax);
+    if (nmax <= 1) return score_delta_unit(lt, N, sv, gn, gs);
+    if (nmax <= 16) return score_delta_small(lt, N, sv, gn, gs, nmax);
     return score_delta_bf<GEN_LF>(lf, N, sv, gn, gs);
 }
 
@@ -154,8 +166,9 @@ __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int sca
 // + [2][roww][threads] words: the first `threads` entries of the next move's CSR row (meta + other ids), copied
 // asynchronously one move ahead
 // + [ndom][kstride] (double + 2 int32): resident CRP state of every domain
+// + [threads] bitmap words and [threads] list offsets of the group-list build
 __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int threads, int kstride, int ndom, int roww, int csize = 1) {
-    return generic_smem_bytes(rcap, pcap, scap, csize) + (size_t)2 * roww * threads * 4 + 8 + (size_t)ndom * kstride * 16;
+    return generic_smem_bytes(rcap, pcap, scap, csize) + (size_t)2 * roww * threads * 4 + (size_t)2 * threads * 4 + 8 + (size_t)ndom * kstride * 16;
 }
 
 // Thread-block cluster per IRM (north_star subsystem 3).  The moves of one IRM are sequential, so an IRM that is alone
@@ -207,10 +220,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     uint32_t *s_row = reinterpret_cast<uint32_t *>(s_bits + RCAP);                              // [2][roww][NT] next / current CSR row heads
     const int KS = GL.kstride;
     const int ROWW = GL.roww;
-    double *s_logcnt_all = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_row + 2 * ROWW * NT) + 7) & ~(uintptr_t)7);   // [ndom][KS] log(table size)
+    uint32_t *s_wbits = s_row + 2 * ROWW * NT;                                                 // [NT] bitmap words of the group-list build
+    int32_t *s_woff = reinterpret_cast<int32_t *>(s_wbits + NT);                                // [NT] their list offsets
+    double *s_logcnt_all = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_woff + NT) + 7) & ~(uintptr_t)7);   // [ndom][KS] log(table size)
     int32_t *s_cnt_all = reinterpret_cast<int32_t *>(s_logcnt_all + GL.ndom * KS);               // [ndom][KS]
     int32_t *s_lab_all = s_cnt_all + GL.ndom * KS;
 
+    const double *logtab = g_logtab;
     for (int k = tid; k < GEN_LF; k += NT) s_lf[k] = g_logfact[k];
     for (int k = tid; k < SCAP; k += NT) { s_acc[k] = 0u; s_accm[k] = 0u; }
     for (int dk = 0; dk < irm.n_domains; dk++) {
@@ -430,22 +446,23 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         }
         GEN_PHASE(0);
 
-        // ---- B1: ordered list of the touched accumulator cells (bitmap scan: ascending cell = deterministic order) ----
+        // ---- B1: ordered list of the touched accumulator cells (ascending cell = deterministic order), NT bitmap words at a
+        //      time: (1) the words -- a ballot over 32 accumulator cells each, spread over the warps (no bitmap atomics in
+        //      phase A), or read from the global bitmap; (2) block scan of their popcounts; (3) every non-empty cell finds its
+        //      list position by itself (word offset + popcount of the lower bits) ----
         int64_t base = 0;
         const int nwords = (ctot + 31) >> 5;
         for (int w0 = 0; w0 < nwords; w0 += NT) {
-            const int w = w0 + tid;
-            uint32_t bits = 0u;
+            const int w = w0 + tid, nw_here = min(NT, nwords - w0);
             if (acc_shared) {
-                // word w0 + warp * 32 + j of the non-empty-cell bitmap = ballot over its 32 accumulator cells (lane = cell:
-                // conflict-free shared loads); lane j keeps word j.  No bitmap atomics in phase A.
-                const int wbase = w0 + warp * 32;
-                for (int j = 0; j < 32 && wbase + j < nwords; j++) {
-                    const int cellv = (wbase + j) * 32 + lane;
+                for (int wl = warp; wl < nw_here; wl += NW) {
+                    const int cellv = (w0 + wl) * 32 + lane;
                     const uint32_t b = __ballot_sync(0xffffffffu, cellv < ctot && s_accm[cellv] != 0u);
-                    if (lane == j) bits = b;
+                    if (lane == 0) s_wbits[wl] = b;
                 }
-            } else if (w < nwords) bits = __ldcg(&irm.gbm[w]);
+            } else if (tid < nw_here) s_wbits[tid] = __ldcg(&irm.gbm[w]);
+            __syncthreads();
+            const uint32_t bits = tid < nw_here ? s_wbits[tid] : 0u;
             const int cnt = __popc(bits);
             int incl = cnt;
 #pragma unroll
@@ -463,16 +480,14 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             }
             const int total = __shfl_sync(0xffffffffu, wincl, 31);
             const int woff = __shfl_sync(0xffffffffu, wincl - wv, warp);
-            const int off = (int)base + woff + incl - cnt;   // list position of this thread's word
-            // the warp walks its 32 words together, lanes = bit positions: cost follows the non-empty words, not the
-            // bits of the fullest one (a run of unary relations sets every bit of a word)
-            for (uint32_t nz = __ballot_sync(0xffffffffu, bits != 0u); nz; nz &= nz - 1u) {
-                const int j = __ffs((int)nz) - 1;
-                const uint32_t bj = __shfl_sync(0xffffffffu, bits, j);
-                const int oj = __shfl_sync(0xffffffffu, off, j);
-                if ((bj >> lane) & 1u) {
-                    const int pos = oj + __popc(bj & ((1u << lane) - 1u));
-                    const int cellv = (w0 + warp * 32 + j) * 32 + lane;
+            s_woff[tid] = (int)base + woff + incl - cnt;     // list position of this thread's word
+            __syncthreads();
+            for (int cl = tid; cl < nw_here * 32; cl += NT) {
+                const int wl = cl >> 5, bit = cl & 31;
+                const uint32_t bj = s_wbits[wl];
+                if ((bj >> bit) & 1u) {
+                    const int pos = s_woff[wl] + __popc(bj & ((1u << bit) - 1u));
+                    const int cellv = (w0 + wl) * 32 + bit;
                     if (pos >= glcap) raise_error(irm, KERR_GROUP_OVERFLOW);
                     else if (pos < RCAP) s_bits[pos] = cellv;
                     else recs[pos].cell = cellv;
@@ -546,7 +561,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 uint32_t N, sv, gn, gs;
                 finish(cur, N, sv, gn, gs);
                 __syncwarp();
-                double v = score_delta_any(s_lf, N, sv, gn, gs);
+                double v = score_delta_any(s_lf, logtab, N, sv, gn, gs);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (C == 1) { if (lane == 0) s_part[unit] = v; }
@@ -566,7 +581,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                     uint32_t N, sv, gn, gs;
                     eval(g0 + lane, slot_t, N, sv, gn, gs);
                     __syncwarp();
-                    double v = score_delta_any(s_lf, N, sv, gn, gs);
+                    double v = score_delta_any(s_lf, logtab, N, sv, gn, gs);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     a2 += v;

@@ -36,7 +36,7 @@ EXPORTS = [
     "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
     "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters", "hirm_engine_clear_relation_cache",
     "hirm_engine_seat_prior", "hirm_irm_set_table_mode", "hirm_unary_block_create", "hirm_unary_block_destroy",
-    "hirm_irm_set_observations_unary", "hirm_engine_last_cluster_size",
+    "hirm_irm_set_observations_unary", "hirm_engine_last_cluster_size", "hirm_relation_reseat",
     "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
     "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
 ]
@@ -101,7 +101,7 @@ def load():
     L.hirm_engine_debug_score_delta.argtypes = [V, I, V, V, V, V, c_f64p]
     L.hirm_irm_set_observations_device.argtypes = [V, ctypes.c_int32, I, ctypes.c_int64, V, V]
     VP = ctypes.POINTER(V)
-    L.hirm_engine_relation_score_matrix.argtypes = [V, I, c_i32p, c_i32p, c_i64p, VP, VP, I, c_i32p, c_f64p]
+    L.hirm_engine_relation_score_matrix.argtypes = [V, I, c_i32p, c_i32p, c_i64p, VP, VP, I, c_i32p, V]
     L.hirm_engine_relation_scores_fresh.argtypes = [V, I, c_i32p, c_i32p, c_i64p, VP, VP, I, c_i32p, c_i32p, ctypes.c_double,
                                                     ctypes.c_uint64, c_u64p, c_f64p]
     L.hirm_engine_clear_relation_cache.argtypes = [V]
@@ -111,6 +111,8 @@ def load():
     L.hirm_unary_block_destroy.argtypes = [V, ctypes.c_int32]
     L.hirm_irm_set_observations_unary.argtypes = [V, ctypes.c_int32, I, ctypes.c_int32, I]
     L.hirm_engine_last_cluster_size.argtypes = [V, c_i32p]
+    L.hirm_relation_reseat.argtypes = [I, I, c_i32p, c_i32p, c_i32p, c_f64p, ctypes.c_int64, I, c_i32p, c_f64p, I, ctypes.c_double,
+                                       c_i32p, c_i32p, c_i32p]
     L.hirm_irm_set_rng_counters.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
     L.hirm_engine_crp_prior_draw.argtypes = [V, I, ctypes.c_double, I, ctypes.c_uint64, ctypes.c_uint64, c_i32p]
     CP = ctypes.POINTER(ctypes.c_char_p)
@@ -171,6 +173,21 @@ def load_dataset(schema_path, obs_path, with_names=True):
 
 def _p(a, t):
     return a.ctypes.data_as(t) if a is not None else None
+
+
+def relation_reseat(labels, sizes, rel_table, scores, fresh_col, order, uniforms, alpha, pos):
+    """hirm_relation_reseat (csrc/relation_moves.cc; host only): sizes and rel_table (int32 arrays) are updated in place.
+    Returns (status, pos, moved, fresh_label): status 0 = done, 1 = the relation at order[pos] chose the fresh table."""
+    L = load()
+    assert labels.dtype == np.int32 and sizes.dtype == np.int32 and rel_table.dtype == np.int32 and order.dtype == np.int32
+    assert scores.dtype == np.float64 and scores.flags.c_contiguous and uniforms.dtype == np.float64
+    p, moved, fresh = ctypes.c_int32(int(pos)), ctypes.c_int32(0), ctypes.c_int32(-1)
+    rc = L.hirm_relation_reseat(len(rel_table), len(labels), _p(labels, c_i32p), _p(sizes, c_i32p), _p(rel_table, c_i32p),
+                                _p(scores, c_f64p), scores.shape[1], int(fresh_col), _p(order, c_i32p), _p(uniforms, c_f64p), len(order),
+                                float(alpha), ctypes.byref(p), ctypes.byref(moved), ctypes.byref(fresh))
+    if rc < 0:
+        raise EngineError("hirm_relation_reseat: bad argument (%d)" % rc)
+    return rc, p.value, moved.value, fresh.value
 
 
 class Engine:
@@ -418,15 +435,16 @@ class Engine:
         val = (ctypes.c_void_p * max(n, 1))(*[r[3] or None for r in rels])
         return ar, rd, nobs, ids, val
 
-    def relation_score_matrix(self, rels, cand_irms):
-        """Relation.logp_score of every relation under every candidate IRM's partitions -> [len(rels), len(cand_irms)]."""
+    def relation_score_matrix(self, rels, cand_irms, d_out_ptr=None):
+        """Relation.logp_score of every relation under every candidate IRM's partitions -> [len(rels), len(cand_irms)]
+        (numpy), or written to the device buffer `d_out_ptr` (float64, row-major) when given."""
         ci = np.ascontiguousarray(cand_irms, dtype=np.int32)
-        out = np.zeros((len(rels), len(ci)), np.float64)
+        out = None if d_out_ptr else np.zeros((len(rels), len(ci)), np.float64)
         if len(rels) == 0 or len(ci) == 0:
             return out
         ar, rd, nobs, ids, val = self._rel_arrays(rels)
         self._ck(self.L.hirm_engine_relation_score_matrix(self._h, len(rels), _p(ar, c_i32p), _p(rd, c_i32p), _p(nobs, c_i64p), ids, val,
-                                                          len(ci), _p(ci, c_i32p), _p(out, c_f64p)))
+                                                          len(ci), _p(ci, c_i32p), d_out_ptr if d_out_ptr else out.ctypes.data))
         return out
 
     def relation_scores_fresh(self, rels, n_entities, max_tables, keys, seed, alpha=1.0):

@@ -53,13 +53,15 @@ class Comm:
         return t.cuda() if self.dist.get_backend(self.group) == "nccl" else t
 
     def all_gather_f64(self, a):
-        """a: float64 array, same shape on every rank -> list of arrays, one per rank."""
+        """a: float64 array -- or a CUDA tensor, gathered where it is (ncclAllGather on the buffer the score kernels filled,
+        one device-to-host copy of the result) -- of the same shape on every rank -> list of arrays, one per rank."""
         self.n_allgather += 1
+        on_device = not isinstance(a, np.ndarray) and hasattr(a, "is_cuda") and a.is_cuda
         if self.world == 1:
-            return [np.asarray(a, dtype=np.float64)]
+            return [a.cpu().numpy() if on_device else np.asarray(a, dtype=np.float64)]
         import torch
-        shape = np.shape(a)
-        t = self._tensor(a).reshape(-1)
+        shape = tuple(a.shape) if on_device else np.shape(a)
+        t = (a.contiguous() if on_device and self.dist.get_backend(self.group) == "nccl" else self._tensor(a.cpu().numpy() if on_device else a)).reshape(-1)
         out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
         self.dist.all_gather_into_tensor(out, t, group=self.group)
         out = out.cpu().numpy().reshape((self.world,) + tuple(shape))
@@ -196,6 +198,14 @@ class EngineBackend:
     # -- relation step --------------------------------------------------------------------------------------------------
     def score_matrix(self, rels, handles):
         return self.eng.relation_score_matrix([self.rels[r] for r in rels], handles)
+
+    def score_matrix_device(self, rels, handles):
+        """The same matrix left in this GPU's memory (a torch tensor as the buffer)."""
+        import torch
+        out = torch.zeros((len(rels), len(handles)), dtype=torch.float64, device=torch.device("cuda", self.device))
+        if len(rels) and len(handles):
+            self.eng.relation_score_matrix([self.rels[r] for r in rels], handles, d_out_ptr=out.data_ptr())
+        return out
 
     def scores_fresh(self, rels, keys, chunk_slots=1 << 26):
         out = np.zeros(len(rels), np.float64)
@@ -382,9 +392,11 @@ class ShardedHIRM:
             cols.pop(cur, None)
             self.stats["irms_deleted"] += 1
 
-    def transition_relations(self, scored=None):
+    def transition_relations(self, scored=None, native=True):
         """One sweep of relation moves: every relation once, in a seeded order.  `scored`: the (columns, fresh scores,
-        keys) of score_columns_batched when several chains were scored in one launch."""
+        keys) of score_columns_batched when several chains were scored in one launch.  The sequential CRP walk runs in
+        hirm_relation_reseat (C++, csrc/relation_moves.cc) between two fresh tables; `native=False` keeps it in Python
+        (relation_candidates / apply_relation_choice: the same arithmetic, used by the trace tests)."""
         import time
         cols, fresh, keys = scored if scored is not None else self.score_columns()
         t0 = time.perf_counter()
@@ -392,12 +404,45 @@ class ShardedHIRM:
         order = rng.permutation(len(self.rnames))
         us = rng.random(len(self.rnames))
         moved = 0
-        for r, u in zip(order, us):
-            r = int(r)
-            tables, lp, fresh_label = self.relation_candidates(r, cols, float(fresh[r]))
-            choice = tables[choose_index(lp, float(u))]
-            moved += int(choice != self.rel_table[r])
-            self.apply_relation_choice(r, choice, cols, keys=keys)
+        if not native:
+            for r, u in zip(order, us):
+                r = int(r)
+                tables, lp, fresh_label = self.relation_candidates(r, cols, float(fresh[r]))
+                choice = tables[choose_index(lp, float(u))]
+                moved += int(choice != self.rel_table[r])
+                self.apply_relation_choice(r, choice, cols, keys=keys)
+        else:
+            from . import engine as E
+            R = len(self.rnames)
+            order32, us64 = np.ascontiguousarray(order, dtype=np.int32), np.ascontiguousarray(us, dtype=np.float64)
+            fresh64 = np.asarray(fresh, dtype=np.float64)
+            pos = 0
+            while pos < R:
+                labels = np.asarray(sorted(self.irms), dtype=np.int32)
+                sizes = np.asarray([len(self.irms[int(t)]["rels"]) for t in labels], dtype=np.int32)
+                rel_tab = np.asarray([self.rel_table[r] for r in range(R)], dtype=np.int32)
+                before = rel_tab.copy()
+                M = np.empty((R, len(labels) + 1), dtype=np.float64)
+                for j, t in enumerate(labels):
+                    M[:, j] = cols[int(t)]
+                M[:, len(labels)] = fresh64
+                status, pos, n_moved, fresh_label = E.relation_reseat(labels, sizes, rel_tab, M, len(labels), order32, us64, self.alpha, pos)
+                moved += n_moved
+                for r in np.flatnonzero(rel_tab != before):           # the bookkeeping of the moves just made
+                    r, src, dst = int(r), int(before[r]), int(rel_tab[r])
+                    self.irms[src]["rels"].discard(r); self.irms[dst]["rels"].add(r)
+                    self.irms[src]["changed"] = self.irms[dst]["changed"] = True
+                    self.rel_table[r] = dst
+                for t in [t for t, info in self.irms.items() if not info["rels"]]:   # emptied IRMs are deleted (:886-890)
+                    if self.irms[t]["handle"] is not None:
+                        self.backend.destroy_irm(self.irms[t]["handle"])
+                    del self.irms[t]
+                    cols.pop(t, None)
+                    self.stats["irms_deleted"] += 1
+                if status == 1:                                       # the relation at order[pos] opens a fresh table
+                    self.apply_relation_choice(int(order32[pos]), int(fresh_label), cols, keys=keys)
+                    moved += 1
+                    pos += 1
         t1 = time.perf_counter()
         self.stats["relations_moved"] += moved
         self.materialize()
@@ -484,18 +529,28 @@ def score_columns_batched(chains):
     mine = [r for r in range(R) if r % world == rank]
     locals_ = [h._local() for h in chains]
     handles = [h.irms[t]["handle"] for h, loc in zip(chains, locals_) for t in loc]
-    m_all = backend.score_matrix(list(range(R)), handles)
+    on_device = hasattr(backend, "score_matrix_device")
+    m_all = backend.score_matrix_device(list(range(R)), handles) if on_device else backend.score_matrix(list(range(R)), handles)
     keys = [h._fresh_keys() for h in chains]
     f_all = backend.scores_fresh(mine * len(chains), np.concatenate([k[mine] for k in keys])) if mine else np.zeros(0)
     t1 = time.perf_counter()
     per_rank = [[[t for t in sorted(h.irms) if h.irms[t]["owner"] == k] for k in range(world)] for h in chains]
     kmax = max(len(p) for pr in per_rank for p in pr)
-    buf = np.zeros((len(chains), R, kmax + 1), dtype=np.float64)
+    if on_device:                                          # the block stays in HBM until the gathered matrix comes back
+        import torch
+        buf = torch.zeros((len(chains), R, kmax + 1), dtype=torch.float64, device=m_all.device)
+        f_dev = torch.from_numpy(np.ascontiguousarray(f_all, dtype=np.float64)).to(m_all.device)
+        mine_dev = torch.as_tensor(mine, dtype=torch.int64, device=m_all.device)
+    else:
+        buf = np.zeros((len(chains), R, kmax + 1), dtype=np.float64)
     off = 0
     for c, loc in enumerate(locals_):
         buf[c, :, :len(loc)] = m_all[:, off:off + len(loc)]
         off += len(loc)
-        buf[c, mine, kmax] = f_all[c * len(mine):(c + 1) * len(mine)]
+        if on_device:
+            buf[c, mine_dev, kmax] = f_dev[c * len(mine):(c + 1) * len(mine)]
+        else:
+            buf[c, mine, kmax] = f_all[c * len(mine):(c + 1) * len(mine)]
     parts = comm.all_gather_f64(buf)
     out = []
     for c in range(len(chains)):

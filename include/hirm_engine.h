@@ -195,7 +195,8 @@ int hirm_engine_relation_scores(hirm_engine *e, int32_t src_irm, int rel, int n_
  * GPUs, all-gathered) before the sequential re-seating of the relations.  Relations are given as device COO arrays
  * (h_d_ids[r] / h_d_val[r] are DEVICE pointers, h_rel_doms [n_rel * HIRM_MAX_ARITY] the candidates' domain index per
  * position); the candidates must share domains, entity codes and max_tables, with every entity seated.
- * h_out [n_rel * n_cand], row-major. */
+ * h_out [n_rel * n_cand], row-major; it may also be a DEVICE buffer (unified addressing): across GPUs the matrix is then
+ * all-gathered (ncclAllGather) straight from there, without a round trip through the host. */
 int hirm_engine_relation_score_matrix(hirm_engine *e, int n_rel, const int32_t *h_arity, const int32_t *h_rel_doms,
                                       const int64_t *h_nobs, const int32_t *const *h_d_ids, const uint8_t *const *h_d_val,
                                       int n_cand, const int32_t *h_cand_irms, double *h_out);
@@ -238,6 +239,20 @@ int hirm_engine_debug_score_delta(hirm_engine *e, int n, const uint32_t *h_N, co
 /* debug hook: device buffer [n_blocks * 16] int64 that the dense kernel fills with SM cycles per role
  * (producer, accumulate warps, decision warps: see profiles/phase_breakdown.py); NULL switches it off */
 int hirm_engine_debug_phase_cycles(hirm_engine *e, long long *d_buf);
+
+/* ---- HIRM relation moves, host part (no CUDA device needed) ---------------------------------------------------------------
+ * The sequential CRP re-seating of one sweep of relation moves (HIRM::transition_cluster_assignment_relation,
+ * cxx/hirm.hh:833-906) from the [relations x candidate tables] matrix of data terms that
+ * hirm_engine_relation_score_matrix / _relation_scores_fresh computed (and, across GPUs, one all-gather made known to every
+ * rank): CRP::tables_weights_gibbs (:147-161) + log_choice with the engine's inversion rule, relation after relation.
+ * labels[n_tables] ascending; sizes[n_tables] relations per table and rel_table[n_rel] are updated in place (a table whose
+ * size reaches 0 is deleted, :886-890); scores[r * ld + j] = data term of relation r under table j, scores[r * ld +
+ * fresh_col] under its fresh table.  Processing starts at order[*pos].  Returns 0 when every listed relation has moved;
+ * 1 when the relation at order[*pos] chose the FRESH table *fresh_label (not applied: the caller makes that IRM and its
+ * score column, then calls again with the new table and *pos + 1); < 0 on a bad argument. */
+int hirm_relation_reseat(int n_rel, int n_tables, const int32_t *labels, int32_t *sizes, int32_t *rel_table,
+                         const double *scores, int64_t ld, int fresh_col, const int32_t *order, const double *uniforms,
+                         int n_order, double alpha, int32_t *pos, int32_t *n_moved, int32_t *fresh_label);
 
 /* ---- ingest: the reference's text formats, natively (host only; no CUDA device needed) ------------------------------
  * load_schema (cxx/util_io.cc:11-34) + load_observations (:36-61) + encode_observations (:63-96): <base>.schema and

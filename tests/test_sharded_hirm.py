@@ -72,6 +72,27 @@ def test_oracle_backend_single_rank_invariants_and_recovery():
     assert h.comm.n_allgather == 6                                        # ONE all-gather per relation sweep
 
 
+def test_native_reseat_walk_equals_python_walk():
+    """hirm_relation_reseat (C++) against the Python walk (relation_candidates + choose_index + apply_relation_choice): same
+    relation partitions, same entity partitions, same scores over whole iterations -- fresh tables, emptied tables and
+    singletons included (CPU, oracle backend)."""
+    gen = dict(n_ent=(30, 24), n_unary=10, n_binary=4, n_clusters=3, seed=5)
+    domains, schema, obs, _ = SU.synthetic_hirm(**gen)
+    names, dn = list(schema), list(domains)
+    trails, stats = [], []
+    for native in (False, True):
+        backend = SU.OracleBackend([domains[d] for d in dn], [[dn.index(d) for d in schema[r]] for r in names], [obs[r] for r in names], 32, 3)
+        h = ShardedHIRM(domains, schema, obs, seed=3, max_tables=32, backend=backend)
+        trail = []
+        for _ in range(6):
+            h.transition_relations(native=native)
+            h.transition_irms()
+            trail.append((dict((r, h.relation_to_table(r)) for r in names), h.state(), h.logp_score()))
+        trails.append(trail); stats.append(dict(h.stats))
+    _same_trail(trails[0], trails[1])
+    assert stats[0] == stats[1] and stats[0]["fresh_irms"] > 0 and stats[0]["irms_deleted"] > 0 and stats[0]["relations_moved"] > 10
+
+
 def test_multi_domain_logp_score_counts_used_domains_only():
     """HIRM::logp_score (cxx/hirm.hh:998-1005) on a schema with three domains where most relation clusters use only some
     of them: the CRP term of an IRM covers the domains its relations use (the reference's IRM holds no other domain,
