@@ -1383,6 +1383,7 @@ struct Plan {
     int n_ent = 0, kcap = 0;
     int64_t gen_maxdeg = 0;
     int gen_kmax = 0, gen_ndom = 0, gen_nother = 0;   // generic kernel: largest max_tables / domain count / other-id columns of its IRMs
+    int gen_ubw = 0;                                  // ... widest unary-block bit row (words)
     int gen_ctot = 0; int64_t gen_groups = 0;         // ... largest accumulator space of a domain, most groups one move can have
 };
 
@@ -1460,6 +1461,7 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
                 plan.gen_nother = std::max(plan.gen_nother, D.n_other); plan.gen_maxdeg = std::max(plan.gen_maxdeg, D.max_deg);
                 const int ct = d < (int)irm->ctot.size() ? irm->ctot[(size_t)d] : 0;
                 plan.gen_ctot = std::max(plan.gen_ctot, ct);
+                if (D.ub_block >= 0 && e->ublocks[(size_t)D.ub_block]) plan.gen_ubw = std::max(plan.gen_ubw, e->ublocks[(size_t)D.ub_block]->words);
                 plan.gen_groups = std::max(plan.gen_groups, std::min<int64_t>(D.max_deg, ct));
             }
             plan.generic_blk.push_back(k);
@@ -1518,6 +1520,7 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         int csize = pick_cluster_size(e, plan, args.flags);
         GenericLaunch GL;
         GL.csize = csize;
+        GL.ubw = 2 * plan.gen_ubw <= gen_threads ? plan.gen_ubw : 0;   // one thread copies one word of the two planes
         GL.pcap = 4 * gen_threads;
         GL.kstride = (std::max(plan.gen_kmax, 2) + 2) & ~1;
         GL.ndom = std::max(plan.gen_ndom, 1); GL.roww = 1 + std::max(plan.gen_nother, 1);
@@ -1527,23 +1530,23 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         const int scap_want = std::max(256, (plan.gen_ctot + 31) & ~31);
         const int rcap_want = std::max(128, (int)((std::min<int64_t>(plan.gen_groups, 1 << 20) + 31) & ~31));
         int want_ctas = std::max(1, std::min(std::min(2048 / gen_threads, 65536 / (e->gen_regs * gen_threads)), (n_gen + e->num_sms - 1) / e->num_sms));
-        const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww) + (size_t)e->gen_static_smem;
+        const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww, 1, GL.ubw) + (size_t)e->gen_static_smem;
         const int accs = csize > 1 ? 2 : 1;              // cluster: a local and a merged accumulator per CTA
         // the accumulator decides how many CTAs share an SM (a global accumulator costs far more than a lost CTA); the group
         // records take what is left of the CTA's share, the rest of a long group list lives in the IRM's global scratch
         for (;; want_ctas--) {
             const size_t budget = (size_t)std::min(e->max_smem_optin, e->smem_per_sm / want_ctas - 1024);
             const size_t room = budget > fixed ? budget - fixed : 0;
-            if ((size_t)scap_want * 4 * accs + 128 * 52 <= room || want_ctas == 1) {
-                GL.scap = (int)std::min<size_t>((size_t)scap_want, room > 128 * 52 ? ((room - 128 * 52) / (4 * accs)) & ~(size_t)31 : 0);
+            if ((size_t)scap_want * 4 * accs + 128 * (GROUP_REC_BYTES + 4) <= room || want_ctas == 1) {
+                GL.scap = (int)std::min<size_t>((size_t)scap_want, room > 128 * (GROUP_REC_BYTES + 4) ? ((room - 128 * (GROUP_REC_BYTES + 4)) / (4 * accs)) & ~(size_t)31 : 0);
                 if (GL.scap < 256) GL.scap = 256;
                 const size_t left = room > (size_t)GL.scap * 4 * accs ? room - (size_t)GL.scap * 4 * accs : 0;
-                GL.rcap = (int)std::min<size_t>((size_t)rcap_want, (left / 52) & ~(size_t)31);
+                GL.rcap = (int)std::min<size_t>((size_t)rcap_want, (left / (GROUP_REC_BYTES + 4)) & ~(size_t)31);
                 if (GL.rcap < 128) GL.rcap = 128;
                 break;
             }
         }
-        const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww, csize);
+        const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww, csize, GL.ubw);
         if (gen_smem > (size_t)e->max_smem_optin) return fail("generic kernel: shared-memory plan exceeds the device limit");
         CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem));
         cudaLaunchConfig_t cfg;

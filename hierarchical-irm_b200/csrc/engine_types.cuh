@@ -114,11 +114,11 @@ __device__ __forceinline__ void raise_error(const IrmDev &irm, int32_t code) { a
 __device__ __forceinline__ uint32_t hash_slot(int64_t cidx, uint32_t mask) {
     return (uint32_t)(((uint64_t)cidx * 0x9E3779B97F4A7C15ull) >> 32) & mask;
 }
-__device__ __forceinline__ cell_t table_get(const RelationDev *R, int64_t cidx) {
-    if (!R->hcap) return __ldcg(&R->counts[cidx]);
-    const uint32_t mask = R->hcap - 1u;
+__device__ __forceinline__ cell_t table_get(const cell_t *counts, uint32_t hcap, int64_t cidx) {
+    if (!hcap) return __ldcg(&counts[cidx]);
+    const uint32_t mask = hcap - 1u;
     const unsigned long long key = (unsigned long long)cidx + 1ull;
-    const ulonglong2 *tab = reinterpret_cast<const ulonglong2 *>(R->counts);
+    const ulonglong2 *tab = reinterpret_cast<const ulonglong2 *>(counts);
     for (uint32_t i = hash_slot(cidx, mask), n = 0; n <= mask; i = (i + 1u) & mask, n++) {
         const ulonglong2 e = __ldcg(tab + i);
         if (e.x == key) return e.y;
@@ -126,6 +126,7 @@ __device__ __forceinline__ cell_t table_get(const RelationDev *R, int64_t cidx) 
     }
     return 0ull;
 }
+__device__ __forceinline__ cell_t table_get(const RelationDev *R, int64_t cidx) { return table_get(R->counts, R->hcap, cidx); }
 __device__ __forceinline__ void table_add(const IrmDev &irm, const RelationDev *R, int64_t cidx, cell_t delta) {
     if (!R->hcap) { atomicAdd(&R->counts[cidx], delta); return; }
     const uint32_t mask = R->hcap - 1u;

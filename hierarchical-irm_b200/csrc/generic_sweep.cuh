@@ -29,17 +29,23 @@ constexpr int GEN_WARPS = GEN_THREADS / 32;
 constexpr int GEN_MAXK = 256;   // kcap <= 255 candidates + 1 fresh
 constexpr int GEN_LF = 256;     // shared-memory copy of lgamma(m+1), m < 256; Stirling beyond (device_math.cuh)
 
-// One group of the moving entity's observations, decoded once per move (phase B) and read by every candidate.
+// One group of the moving entity's observations, decoded once per move (phase B) and read by every candidate: everything
+// the scoring of a (group, candidate) pair needs sits in the record, so that phase D's dependent chain is one shared-memory
+// read and one count-table load (no relation / domain descriptor loads).
 struct GroupRec {
-    const RelationDev *R;
-    const RelDom *RD;
+    const RelationDev *R;     // (phase F: table updates)
+    cell_t *counts;           // R->counts
     int64_t rest_c;           // count-table index without the moved domain's positions
     cell_t own;               // (observations, ones) of the group
-    int32_t rest_k;           // accumulator index of the rest positions
+    int32_t ca, cb;           // count-table strides of the moved domain's positions (cb = 0: the domain occurs once)
+    int32_t row0, col0;       // twice-occurring domain: accumulator cell of the row / column group with the other end in slot 0
+    int32_t diag, rs;         // ... of the (i, i) group; accumulator stride per other-end slot
     int32_t cell;             // accumulator cell of the group
-    int16_t pat, dother, pad0, pad1;   // self pattern 0/1/2; table of the other end (patterns 0, 1 of a twice-occurring domain)
+    uint32_t hcap;            // R->hcap (0 = dense table)
+    int16_t pat, dother, twice, pad;   // self pattern 0/1/2; table of the other end (patterns 0, 1 of a twice-occurring domain)
 };
-static_assert(sizeof(GroupRec) == 48, "GroupRec layout (engine.cu sizes the scratch by it)");
+static_assert(sizeof(GroupRec) == 72, "GroupRec layout (engine.cu sizes the scratch by it)");
+constexpr int GROUP_REC_BYTES = 72;
 
 // The accumulator of one move: 32-bit cells (observations | ones << 16) in shared memory, fed by native 32-bit shared
 // atomics (a 64-bit shared atomicAdd is a compare-and-swap spin loop: ATOMS.CAST.SPIN in the SASS), or -- when the
@@ -60,18 +66,15 @@ struct AccView {
 // Twice-occurring domain (a, b): the entity's observations sit in the cells (c, y) [row group y: i at a, other end in y],
 // (x, c) [column group x] and (c, c) [(i, i)], so cell (x, y) holds  [x = c] row(y) + [y = c] col(x) + [x = y = c] diag.
 __device__ __forceinline__ bool group_target(const GroupRec &g, const AccView &acc, int t, int c, cell_t &delta, int64_t &cidx, cell_t &sub) {
-    const RelationDev *R = g.R;
-    const RelDom *D = g.RD;
-    const int64_t ca = R->cstride[D->a];
-    if (D->b < 0) {                                  // domain occurs once: no merging
+    const int64_t ca = g.ca;
+    if (!g.twice) {                                  // domain occurs once: no merging
         delta = g.own;
         cidx = g.rest_c + t * ca;
         sub = t == c ? g.own : (cell_t)0;
         return true;
     }
-    const int64_t cb = R->cstride[D->b];
-    const int32_t row0 = D->base[0] + g.rest_k, col0 = D->base[1] + g.rest_k, rs = D->rest_size;
-    const int32_t diag = D->base[2] + g.rest_k;                       // (i, i)
+    const int64_t cb = g.cb;
+    const int32_t row0 = g.row0, col0 = g.col0, rs = g.rs, diag = g.diag;
     auto own_at = [&](int x, int y) -> cell_t {
         cell_t v = 0;
         if (x == c) v += acc[row0 + y * rs];
@@ -105,10 +108,8 @@ __device__ __forceinline__ bool group_target(const GroupRec &g, const AccView &a
 
 // count-table index of the group's cell when the entity sits in slot t (no merging: integer adds merge by themselves)
 __device__ __forceinline__ int64_t group_cell_at(const GroupRec &g, int t) {
-    const RelationDev *R = g.R;
-    const RelDom *D = g.RD;
-    int64_t c = g.rest_c + (g.pat == 1 ? (int)g.dother : t) * R->cstride[D->a];
-    if (D->b >= 0) c += (g.pat == 0 ? (int)g.dother : t) * R->cstride[D->b];
+    int64_t c = g.rest_c + (int64_t)(g.pat == 1 ? (int)g.dother : t) * g.ca;
+    if (g.twice) c += (int64_t)(g.pat == 0 ? (int)g.dother : t) * g.cb;
     return c;
 }
 
@@ -159,7 +160,7 @@ __device__ __forceinline__ double score_delta_any(const double *lf, const double
 
 // Dynamic shared memory of one CTA: [rcap] group records, [rcap] touched accumulator cells, [pcap] partial sums,
 // [scap] 32-bit accumulator cells.
-struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww, csize; };   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids); csize: CTAs per IRM (thread-block cluster)
+struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww, csize, ubw; };   // ubw: words per unary-block bit row (0: none)   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids); csize: CTAs per IRM (thread-block cluster)
 __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int csize = 1) {
     return (size_t)rcap * (sizeof(GroupRec) + 4) + (size_t)pcap * 8 + (size_t)scap * 4 * (csize > 1 ? 2 : 1) + 16;   // cluster: local + merged accumulator
 }
@@ -167,8 +168,10 @@ __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int sca
 // asynchronously one move ahead
 // + [ndom][kstride] (double + 2 int32): resident CRP state of every domain
 // + [threads] bitmap words and [threads] list offsets of the group-list build
-__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int threads, int kstride, int ndom, int roww, int csize = 1) {
-    return generic_smem_bytes(rcap, pcap, scap, csize) + (size_t)2 * roww * threads * 4 + (size_t)2 * threads * 4 + 8 + (size_t)ndom * kstride * 16;
+// + [2][2][ubw] words: the next / current move's unary-block bit rows (observed, value), copied one move ahead
+__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int threads, int kstride, int ndom, int roww, int csize = 1, int ubw = 0) {
+    return generic_smem_bytes(rcap, pcap, scap, csize) + (size_t)2 * roww * threads * 4 + (size_t)2 * threads * 4 + (size_t)4 * ubw * 4 + 8 +
+           (size_t)ndom * kstride * 16;
 }
 
 // Thread-block cluster per IRM (north_star subsystem 3).  The moves of one IRM are sequential, so an IRM that is alone
@@ -222,7 +225,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     const int ROWW = GL.roww;
     uint32_t *s_wbits = s_row + 2 * ROWW * NT;                                                 // [NT] bitmap words of the group-list build
     int32_t *s_woff = reinterpret_cast<int32_t *>(s_wbits + NT);                                // [NT] their list offsets
-    double *s_logcnt_all = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_woff + NT) + 7) & ~(uintptr_t)7);   // [ndom][KS] log(table size)
+    const int UBW = GL.ubw;
+    uint32_t *s_ub = reinterpret_cast<uint32_t *>(s_woff + NT);                                 // [2][2][UBW] unary-block bit rows (next / current move)
+    double *s_logcnt_all = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_ub + 4 * UBW) + 7) & ~(uintptr_t)7);   // [ndom][KS] log(table size)
     int32_t *s_cnt_all = reinterpret_cast<int32_t *>(s_logcnt_all + GL.ndom * KS);               // [ndom][KS]
     int32_t *s_lab_all = s_cnt_all + GL.ndom * KS;
 
@@ -289,6 +294,17 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         cp4(dst, dq.meta + q);
         for (int oi = 0; oi < dq.n_other && oi < ROWW - 1; oi++) cp4(dst + (oi + 1) * NT, dq.other + (int64_t)oi * dq.nnz + q);
     };
+    // ... and of the entity's unary-block bit rows (both planes, every CTA of a cluster the whole row)
+    auto prefetch_ub = [&](int64_t mm, int buf) {
+        const int k = (int)((mm - m0) & 3);
+        const int dm = s_pd[k];
+        if (mm >= m1 || dm < 0) return;
+        const DomainDev &dq = irm.dom[dm];
+        const int nw = dq.ub_words;
+        if (tid >= 2 * nw || nw > UBW) return;
+        const int plane = tid >= nw, w = tid - plane * nw;
+        cp4(s_ub + (buf * 2 + plane) * UBW + w, (plane ? dq.ub_val : dq.ub_obs) + (int64_t)s_pi[k] * nw + w);
+    };
     if (tid == 0) {
         issue_ids(m0); issue_ids(m0 + 1); issue_ids(m0 + 2);
         asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
@@ -298,7 +314,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     }
     __syncthreads();
     prefetch_row(m0, 0);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    prefetch_ub(m0, 0);
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     // debug hook (hirm_engine_debug_phase_cycles): thread 0's SM cycles per phase, summed over the moves:
     // [0] A  [1] B1 (+C)  [2] B2  [3] D  [4] E  [5] F  -- 32 slots per block, shared with the dense kernel's layout
     const bool prof = args.phase_cycles != nullptr && tid == 0;
@@ -311,6 +329,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         const int rbuf = (int)((m - m0) & 1);
         asm volatile("cp.async.wait_group 0;" ::: "memory");      // this move's row head (own element: no barrier needed)
         prefetch_row(m + 1, rbuf ^ 1);
+        prefetch_ub(m + 1, rbuf ^ 1);
         if (tid == 0) { issue_ids(m + 3); issue_state(m + 2); }
         asm volatile("cp.async.commit_group;" ::: "memory");
         const bool bad = cur.d < 0;
@@ -322,9 +341,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 raise_error(irm, KERR_BAD_MOVE);
                 if (args.out_choice) args.out_choice[m] = -1;
                 if (args.trace_cap > 0) args.trace_n[m] = 0;
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                load_slot(m + 1);
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (tid == 0) load_slot(m + 1);
             __syncthreads();
             continue;
         }
@@ -416,12 +435,16 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         // unary-block relations: one thread per column of the entity's bit row; at most one observation per (entity, relation)
         // and one accumulator cell per relation, so a plain store does it
         if (dd.ub_words && tid < NA) {
-            const uint32_t *xo = dd.ub_obs + (int64_t)item * dd.ub_words, *xv = dd.ub_val + (int64_t)item * dd.ub_words;
+            // the bit rows were copied into shared memory one move ahead (by other threads: s_ub_ready orders them); rows wider
+            // than the buffer are read in place
+            const bool staged = dd.ub_words <= UBW;
+            const uint32_t *xo = staged ? s_ub + (rbuf * 2) * UBW : dd.ub_obs + (int64_t)item * dd.ub_words;
+            const uint32_t *xv = staged ? s_ub + (rbuf * 2 + 1) * UBW : dd.ub_val + (int64_t)item * dd.ub_words;
             for (int k = crank * NA + tid; k < dd.ub_words * 32; k += NA * C) {
                 const int w = k >> 5;
-                const uint32_t ob = __ldg(xo + w) & __ldg(dd.ub_mask + w);      // the warp reads one word: a broadcast
+                const uint32_t ob = xo[w] & __ldg(dd.ub_mask + w);      // the warp reads one word: a broadcast
                 if ((ob >> (k & 31)) & 1u) {
-                    const uint32_t val = (__ldg(xv + w) >> (k & 31)) & 1u;
+                    const uint32_t val = (xv[w] >> (k & 31)) & 1u;
                     const int32_t cell = __ldg(dd.ub_cell + k);
                     if (acc_shared) s_acc[cell] = 1u | (val << 16);
                     else { __stcg(&irm.gacc[cell], pack_cell(1u, val)); atomicOr(&irm.gbm[cell >> 5], 1u << (cell & 31)); }
@@ -505,20 +528,22 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             const RelationDev *R = &irm.rel[rel];
             const RelDom *D = rdesc + (int64_t)rel * irm.n_domains;
             GroupRec rc;
-            rc.R = R; rc.RD = D; rc.cell = cell;
+            rc.R = R; rc.counts = R->counts; rc.hcap = R->hcap; rc.cell = cell;
+            rc.twice = (int16_t)(D->b >= 0); rc.ca = (int32_t)R->cstride[D->a]; rc.cb = D->b >= 0 ? (int32_t)R->cstride[D->b] : 0;
             rc.pat = (int16_t)(D->b >= 0 && cell >= D->base[2] ? 2 : D->b >= 0 && cell >= D->base[1] ? 1 : 0);
             const int32_t local = cell - D->base[rc.pat];
-            rc.rest_k = local % D->rest_size;
+            const int32_t rest_k = local % D->rest_size;
             rc.dother = (int16_t)(local / D->rest_size);
             int64_t rest_c = 0;
             for (int p = 0; p < R->arity; p++) {
                 if (p == D->a || p == D->b) continue;
-                const int digit = (rc.rest_k / D->rstride[p]) % irm.dom[R->dom[p]].kcap;
+                const int digit = (rest_k / D->rstride[p]) % irm.dom[R->dom[p]].kcap;
                 rest_c += digit * R->cstride[p];
             }
             rc.rest_c = rest_c;
             rc.own = acc[cell];
-            rc.pad0 = rc.pad1 = 0;
+            rc.row0 = D->base[0] + rest_k; rc.col0 = D->base[1] + rest_k; rc.diag = D->base[2] + rest_k; rc.rs = D->rest_size;
+            rc.pad = 0;
             if (g < RCAP) s_recs[g] = rc; else recs[g] = rc;
         }
         __syncthreads();
@@ -536,7 +561,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             const GroupRec gr = g < RCAP ? s_recs[g] : recs[g];
             int64_t cidx;
             if (!group_target(gr, acc, slot_t, c, p.delta, cidx, p.sub)) { p.delta = 0ull; p.sub = 0ull; return p; }
-            p.cur = table_get(gr.R, cidx);             // virtual removal: finish() takes the entity's own observations out of the cell
+            p.cur = table_get(gr.counts, gr.hcap, cidx);   // virtual removal: finish() takes the entity's own observations out of the cell
             return p;
         };
         auto finish = [&](const Pending &p, uint32_t &N, uint32_t &sv, uint32_t &gn, uint32_t &gs) {
@@ -663,8 +688,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             s_logcnt_all[d * KS + c] = log((double)max(s_cnt[c], 1));
             s_logcnt_all[d * KS + tnew] = log((double)newcnt);
         }
+        // every thread's copies for the next move (ring entries, row head, unary bit rows -- read by OTHER threads too) have
+        // landed before the closing barrier
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (tid == 0) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
             const int k1 = (ring + 1) & 3;             // the same entity again: its prefetched slot is stale
             if (tnew != c && s_pd[k1] == d && s_pi[k1] == item) s_pc[k1] = tnew;
         }
