@@ -132,11 +132,17 @@ struct hirm_engine {
     struct UnaryBits { DevBuf<uint32_t> obs, val; int64_t nobs = 0; int32_t n_ent = 0; const uint8_t *val_src = nullptr; };
     std::map<std::pair<const int32_t *, const uint8_t *>, UnaryBits> unary_cache;   // keyed by the (ids, val) buffers: relations may share an ids buffer
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int last_cluster = 1;              // CTAs per IRM of the last generic launch
+    int last_cluster = 1;              // largest number of CTAs per IRM of the last generic launches
+    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+
     int last_launches = 0, last_kind = -1, last_occupancy = 0, last_stages = 0, last_chunk = 0, last_smem = 0; float last_ms = 0.f;
     int max_smem_optin = 0, smem_per_sm = 0, num_sms = 0, dense_static_smem = 0, dense_static_smem_large = 0, gen_regs = 64, gen_static_smem = 12 * 1024;
     long long *d_phase_cycles = nullptr;   // debug hook (hirm_engine_debug_phase_cycles)
 };
+
+// function attributes of generic_sweep_kernel are per process: remember what was set
+static int g_gen_smem_set = 0;
+static bool g_gen_nonportable = false;
 
 static const char *kerr_text(int code) {
     switch (code) {
@@ -208,6 +214,9 @@ extern "C" int hirm_engine_destroy(hirm_engine *e) {
     cudaDeviceSynchronize();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    for (auto &st : e->side) if (st) cudaStreamDestroy(st);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    for (auto &j : e->ev_join) if (j) cudaEventDestroy(j);
     delete e;
     return 0;
 }
@@ -1384,6 +1393,8 @@ struct Plan {
     int64_t gen_maxdeg = 0;
     int gen_kmax = 0, gen_ndom = 0, gen_nother = 0;   // generic kernel: largest max_tables / domain count / other-id columns of its IRMs
     int gen_ubw = 0;                                  // ... widest unary-block bit row (words)
+    std::vector<double> gen_weight;                   // per generic IRM: entries (CSR + unary columns) an average move reads
+    std::vector<std::pair<int, int>> gen_classes;     // (CTAs per IRM, number of IRMs): generic_blk is ordered by class
     int gen_ctot = 0; int64_t gen_groups = 0;         // ... largest accumulator space of a domain, most groups one move can have
 };
 
@@ -1417,6 +1428,8 @@ static int launch_dense_tier(hirm_engine *e, const DenseLaunch &L, unsigned nb, 
     CK(cudaGetLastError());
     return 0;
 }
+
+static void assign_cluster_classes(hirm_engine *e, Plan &plan, uint32_t flags);
 
 static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_t flags, Plan &plan) {
     bool have_dense = false;
@@ -1464,9 +1477,16 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
                 if (D.ub_block >= 0 && e->ublocks[(size_t)D.ub_block]) plan.gen_ubw = std::max(plan.gen_ubw, e->ublocks[(size_t)D.ub_block]->words);
                 plan.gen_groups = std::max(plan.gen_groups, std::min<int64_t>(D.max_deg, ct));
             }
+            double w = 0.0, ents = 0.0;
+            for (int d = 0; d < irm->n_domains; d++) {
+                const DomObs &D = irm->obs->dom[(size_t)d];
+                w += (double)D.nnz + (double)D.n_unary * irm->n_ent[(size_t)d]; ents += irm->n_ent[(size_t)d];
+            }
+            plan.gen_weight.push_back(w / std::max(ents, 1.0));
             plan.generic_blk.push_back(k);
         }
     }
+    assign_cluster_classes(e, plan, flags);
     // More dense chains than fit on the GPU at once: the launch ends with its slowest chain, so the chains with the
     // most live tables (the cost of a move grows with them) go first and the block scheduler fills in the cheap ones
     // (longest-processing-time-first).
@@ -1490,20 +1510,49 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
     return 0;
 }
 
-// CTAs per IRM of a generic launch: a thread-block cluster per IRM when the GPU has SMs to spare and a move is heavy
-// (long rows or many groups), or when the caller asks for it (HIRM_SWEEP_CLUSTER); results do not depend on it.
-static int pick_cluster_size(hirm_engine *e, const Plan &plan, uint32_t flags) {
+// CTAs per IRM of the generic launches: a thread-block cluster per IRM when the GPU has SMs to spare and a move is heavy
+// (long rows or many groups), or when the caller asks for it (HIRM_SWEEP_CLUSTER).  The launch ends with its slowest IRM,
+// and the IRMs of an HIRM differ widely in size (a CRP over relations makes a few big clusters and many small ones), so the
+// SMs are dealt out by weight: every IRM starts with one CTA, and the IRM with the most work per CTA doubles its cluster
+// (up to 16) while SMs are left.  IRMs of equal cluster size go out in one launch, the launches run concurrently.
+// Results do not depend on any of this.
+static void assign_cluster_classes(hirm_engine *e, Plan &plan, uint32_t flags) {
     const int n_gen = (int)plan.generic_blk.size();
+    plan.gen_classes.clear();
+    if (n_gen == 0) return;
+    std::vector<int> cs((size_t)n_gen, 1);
     if (const char *s = getenv("HIRM_CLUSTER_SIZE")) {
         int c = atoi(s), p = 1;
         while (p * 2 <= c && p < 16) p *= 2;
-        return std::max(1, p);
+        std::fill(cs.begin(), cs.end(), std::max(1, p));
+    } else {
+        const bool forced = (flags & HIRM_SWEEP_CLUSTER) != 0;
+        const bool heavy = plan.gen_maxdeg >= 1536 || plan.gen_groups >= 384;
+        if ((forced || heavy) && n_gen <= e->num_sms) {
+            int total = n_gen;
+            for (;;) {
+                int best = -1;
+                for (int i = 0; i < n_gen; i++) {
+                    if (cs[(size_t)i] >= 16 || total + cs[(size_t)i] > e->num_sms) continue;
+                    if (!forced && plan.gen_weight[(size_t)i] / cs[(size_t)i] < 192.0) continue;      // too little work per CTA to be worth a barrier
+                    if (best < 0 || plan.gen_weight[(size_t)i] / cs[(size_t)i] > plan.gen_weight[(size_t)best] / cs[(size_t)best]) best = i;
+                }
+                if (best < 0) break;
+                total += cs[(size_t)best]; cs[(size_t)best] *= 2;
+            }
+        }
     }
-    const bool heavy = plan.gen_maxdeg >= 1536 || plan.gen_groups >= 384;
-    if (!(flags & HIRM_SWEEP_CLUSTER) && !heavy) return 1;
-    int c = 1;
-    while (c < 16 && (int64_t)n_gen * c * 2 <= e->num_sms) c *= 2;
-    return c;
+    std::vector<int> order((size_t)n_gen);
+    for (int i = 0; i < n_gen; i++) order[(size_t)i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cs[(size_t)a] > cs[(size_t)b]; });
+    std::vector<int32_t> blk((size_t)n_gen); std::vector<double> wt((size_t)n_gen);
+    for (int i = 0; i < n_gen; i++) {
+        blk[(size_t)i] = plan.generic_blk[(size_t)order[(size_t)i]]; wt[(size_t)i] = plan.gen_weight[(size_t)order[(size_t)i]];
+        const int c = cs[(size_t)order[(size_t)i]];
+        if (plan.gen_classes.empty() || plan.gen_classes.back().first != c) plan.gen_classes.push_back({c, 0});
+        plan.gen_classes.back().second++;
+    }
+    plan.generic_blk.swap(blk); plan.gen_weight.swap(wt);
 }
 
 static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args) {
@@ -1517,63 +1566,78 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         //  128 threads 5.8 M moves/s, 592 at 256 threads 10.5 M)
         int gen_threads = n_gen <= e->num_sms ? 1024 : (n_gen <= 4 * e->num_sms || plan.gen_maxdeg > 512) ? 256 : 128;
         if (const char *s = getenv("HIRM_GENERIC_THREADS")) gen_threads = std::max(64, std::min(1024, atoi(s) & ~31));
-        int csize = pick_cluster_size(e, plan, args.flags);
-        GenericLaunch GL;
-        GL.csize = csize;
-        GL.ubw = 2 * plan.gen_ubw <= gen_threads ? plan.gen_ubw : 0;   // one thread copies one word of the two planes
-        GL.pcap = 4 * gen_threads;
-        GL.kstride = (std::max(plan.gen_kmax, 2) + 2) & ~1;
-        GL.ndom = std::max(plan.gen_ndom, 1); GL.roww = 1 + std::max(plan.gen_nother, 1);
-        // Shared-memory plan: the move's accumulator (4 bytes per cell of the largest per-domain cell space) and its group
-        // records (52 bytes per group, at most min(longest row, cells) groups) stay on chip when they fit the CTA's share
-        // of the SM; the fewer IRMs per SM, the bigger that share.  What does not fit goes to the IRM's global scratch.
-        const int scap_want = std::max(256, (plan.gen_ctot + 31) & ~31);
-        const int rcap_want = std::max(128, (int)((std::min<int64_t>(plan.gen_groups, 1 << 20) + 31) & ~31));
-        int want_ctas = std::max(1, std::min(std::min(2048 / gen_threads, 65536 / (e->gen_regs * gen_threads)), (n_gen + e->num_sms - 1) / e->num_sms));
-        const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww, 1, GL.ubw) + (size_t)e->gen_static_smem;
-        const int accs = csize > 1 ? 2 : 1;              // cluster: a local and a merged accumulator per CTA
-        // the accumulator decides how many CTAs share an SM (a global accumulator costs far more than a lost CTA); the group
-        // records take what is left of the CTA's share, the rest of a long group list lives in the IRM's global scratch
-        for (;; want_ctas--) {
-            const size_t budget = (size_t)std::min(e->max_smem_optin, e->smem_per_sm / want_ctas - 1024);
-            const size_t room = budget > fixed ? budget - fixed : 0;
-            if ((size_t)scap_want * 4 * accs + 128 * (GROUP_REC_BYTES + 4) <= room || want_ctas == 1) {
-                GL.scap = (int)std::min<size_t>((size_t)scap_want, room > 128 * (GROUP_REC_BYTES + 4) ? ((room - 128 * (GROUP_REC_BYTES + 4)) / (4 * accs)) & ~(size_t)31 : 0);
-                if (GL.scap < 256) GL.scap = 256;
-                const size_t left = room > (size_t)GL.scap * 4 * accs ? room - (size_t)GL.scap * 4 * accs : 0;
-                GL.rcap = (int)std::min<size_t>((size_t)rcap_want, (left / (GROUP_REC_BYTES + 4)) & ~(size_t)31);
-                if (GL.rcap < 128) GL.rcap = 128;
-                break;
-            }
+        e->last_cluster = 1;
+        int done = 0, li = 0;
+        const int n_classes = (int)plan.gen_classes.size();
+        if (n_classes > 1) {                               // the classes run side by side: fork the side streams off the engine's stream
+            for (int k = 1; k < n_classes && k <= 4; k++) if (!e->side[k - 1]) CK(cudaStreamCreateWithFlags(&e->side[k - 1], cudaStreamNonBlocking));
+            if (!e->ev_fork) { CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); for (auto &j : e->ev_join) CK(cudaEventCreateWithFlags(&j, cudaEventDisableTiming)); }
+            CK(cudaEventRecord(e->ev_fork, e->stream));
         }
-        const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww, csize, GL.ubw);
-        if (gen_smem > (size_t)e->max_smem_optin) return fail("generic kernel: shared-memory plan exceeds the device limit");
-        CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem));
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.blockDim = dim3((unsigned)gen_threads); cfg.dynamicSmemBytes = gen_smem; cfg.stream = e->stream;
-        cudaLaunchAttribute attr[1];
-        const int32_t *blk = e->s_blk.p;
-        for (;; csize /= 2) {
+        for (const auto &cls : plan.gen_classes) {
+            int csize = cls.first;
+            const int n_cls = cls.second;
+            cudaStream_t st = (li == 0 || li > 4) ? e->stream : e->side[li - 1];
+            if (st != e->stream) CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
+            GenericLaunch GL;
             GL.csize = csize;
-            cfg.gridDim = dim3((unsigned)n_gen * (unsigned)csize);
-            cfg.numAttrs = 0; cfg.attrs = nullptr;
-            if (csize > 1) {
-                CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, csize > 8 ? 1 : 0));
-                attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                cfg.attrs = attr; cfg.numAttrs = 1;
-                int n_clusters = 0;
-                if (cudaOccupancyMaxActiveClusters(&n_clusters, generic_sweep_kernel, &cfg) != cudaSuccess || n_clusters < std::min(n_gen, 1)) {
-                    cudaGetLastError();
-                    continue;                                  // this cluster size cannot be placed: halve it
+            GL.ubw = 2 * plan.gen_ubw <= gen_threads ? plan.gen_ubw : 0;   // one thread copies one word of the two planes
+            GL.pcap = 4 * gen_threads;
+            GL.kstride = (std::max(plan.gen_kmax, 2) + 2) & ~1;
+            GL.ndom = std::max(plan.gen_ndom, 1); GL.roww = 1 + std::max(plan.gen_nother, 1);
+            // Shared-memory plan: the move's accumulator (4 bytes per cell of the largest per-domain cell space) and its group
+            // records (76 bytes per group, at most min(longest row, cells) groups) stay on chip when they fit the CTA's share
+            // of the SM; the fewer IRMs per SM, the bigger that share.  What does not fit goes to the IRM's global scratch.
+            const int scap_want = std::max(256, (plan.gen_ctot + 31) & ~31);
+            const int rcap_want = std::max(128, (int)((std::min<int64_t>(plan.gen_groups, 1 << 20) + 31) & ~31));
+            int want_ctas = std::max(1, std::min(std::min(2048 / gen_threads, 65536 / (e->gen_regs * gen_threads)), (n_gen + e->num_sms - 1) / e->num_sms));
+            const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww, 1, GL.ubw) + (size_t)e->gen_static_smem;
+            const int accs = csize > 1 ? 2 : 1;              // cluster: a local and a merged accumulator per CTA
+            // the accumulator decides how many CTAs share an SM (a global accumulator costs far more than a lost CTA); the group
+            // records take what is left of the CTA's share, the rest of a long group list lives in the IRM's global scratch
+            for (;; want_ctas--) {
+                const size_t budget = (size_t)std::min(e->max_smem_optin, e->smem_per_sm / want_ctas - 1024);
+                const size_t room = budget > fixed ? budget - fixed : 0;
+                if ((size_t)scap_want * 4 * accs + 128 * (GROUP_REC_BYTES + 4) <= room || want_ctas == 1) {
+                    GL.scap = (int)std::min<size_t>((size_t)scap_want, room > 128 * (GROUP_REC_BYTES + 4) ? ((room - 128 * (GROUP_REC_BYTES + 4)) / (4 * accs)) & ~(size_t)31 : 0);
+                    if (GL.scap < 256) GL.scap = 256;
+                    const size_t left = room > (size_t)GL.scap * 4 * accs ? room - (size_t)GL.scap * 4 * accs : 0;
+                    GL.rcap = (int)std::min<size_t>((size_t)rcap_want, (left / (GROUP_REC_BYTES + 4)) & ~(size_t)31);
+                    if (GL.rcap < 128) GL.rcap = 128;
+                    break;
                 }
             }
-            break;
+            const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww, csize, GL.ubw);
+            if (gen_smem > (size_t)e->max_smem_optin) return fail("generic kernel: shared-memory plan exceeds the device limit");
+            if ((int)gen_smem > g_gen_smem_set) { CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem)); g_gen_smem_set = (int)gen_smem; }
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.blockDim = dim3((unsigned)gen_threads); cfg.dynamicSmemBytes = gen_smem; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            const int32_t *blk = e->s_blk.p + done;
+            for (;; csize /= 2) {
+                GL.csize = csize;
+                cfg.gridDim = dim3((unsigned)n_cls * (unsigned)csize);
+                cfg.numAttrs = 0; cfg.attrs = nullptr;
+                if (csize > 1) {
+                    if (csize > 8 && !g_gen_nonportable) { CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); g_gen_nonportable = true; }
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                    cfg.attrs = attr; cfg.numAttrs = 1;
+                    int n_clusters = 0;
+                    if (cudaOccupancyMaxActiveClusters(&n_clusters, generic_sweep_kernel, &cfg) != cudaSuccess || n_clusters < 1) {
+                        cudaGetLastError();
+                        continue;                                  // this cluster size cannot be placed: halve it
+                    }
+                }
+                break;
+            }
+            CK(cudaLaunchKernelEx(&cfg, generic_sweep_kernel, args, blk, GL));
+            CK(cudaGetLastError());
+            if (st != e->stream) { CK(cudaEventRecord(e->ev_join[li - 1], st)); CK(cudaStreamWaitEvent(e->stream, e->ev_join[li - 1], 0)); }
+            e->last_launches++; e->last_kind = 0; e->last_cluster = std::max(e->last_cluster, csize);
+            done += n_cls; li++;
         }
-        CK(cudaLaunchKernelEx(&cfg, generic_sweep_kernel, args, blk, GL));
-        CK(cudaGetLastError());
-        e->last_launches++; e->last_kind = 0; e->last_cluster = csize;
     }
     if (!plan.dense_blk.empty()) {
         const unsigned nb = (unsigned)plan.dense_blk.size();

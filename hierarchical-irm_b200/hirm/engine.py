@@ -39,6 +39,8 @@ EXPORTS = [
     "hirm_irm_set_observations_unary", "hirm_engine_last_cluster_size", "hirm_relation_reseat",
     "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
     "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
+    "hirm_gpu_dataset_last_error", "hirm_gpu_dataset_load", "hirm_gpu_dataset_free", "hirm_gpu_dataset_counts", "hirm_gpu_dataset_domain",
+    "hirm_gpu_dataset_relation", "hirm_gpu_dataset_entity", "hirm_gpu_dataset_copy_relation", "hirm_gpu_dataset_timings",
 ]
 
 _lib = None
@@ -124,6 +126,15 @@ def load():
     L.hirm_dataset_relation.argtypes = [V, I, CP, c_i32p, c_i32p, c_i64p]
     L.hirm_dataset_observations.argtypes = [V, I, ctypes.POINTER(c_i32p), ctypes.POINTER(c_u8p)]
     L.hirm_dataset_entity.argtypes = [V, I, ctypes.c_int32, CP]
+    L.hirm_gpu_dataset_last_error.restype = ctypes.c_char_p
+    L.hirm_gpu_dataset_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, I, ctypes.POINTER(V)]
+    L.hirm_gpu_dataset_free.argtypes = [V]
+    L.hirm_gpu_dataset_counts.argtypes = [V, c_i32p, c_i32p]
+    L.hirm_gpu_dataset_domain.argtypes = [V, I, CP, c_i32p]
+    L.hirm_gpu_dataset_relation.argtypes = [V, I, CP, c_i32p, c_i32p, c_i64p, ctypes.POINTER(V), ctypes.POINTER(V)]
+    L.hirm_gpu_dataset_entity.argtypes = [V, I, ctypes.c_int32, CP]
+    L.hirm_gpu_dataset_copy_relation.argtypes = [V, I, V, V]
+    L.hirm_gpu_dataset_timings.argtypes = [V, c_f64p]
     _lib = L
     return L
 
@@ -169,6 +180,50 @@ def load_dataset(schema_path, obs_path, with_names=True):
         return domains, schema, observations, names
     finally:
         L.hirm_dataset_free(ds)
+
+
+def load_dataset_gpu(schema_path, obs_path, device=-1, with_names=True):
+    """GPU reader of <base>.schema / <base>.obs (csrc/ingest_gpu.cu): the same encoding as load_dataset, the COO arrays as
+    torch CUDA tensors -- (domains, schema, observations {relation: (ids int32 [nobs, arity], val uint8 [nobs])}, names or
+    None, timings dict).  The observations of a relation come in an unspecified order."""
+    import torch
+    L = load()
+    ds = ctypes.c_void_p()
+    if L.hirm_gpu_dataset_load(os.fsencode(schema_path), os.fsencode(obs_path), int(device), ctypes.byref(ds)):
+        raise EngineError(L.hirm_gpu_dataset_last_error().decode())
+    try:
+        dev = torch.device("cuda", torch.cuda.current_device() if device < 0 else int(device))
+        nd, nr = ctypes.c_int32(), ctypes.c_int32()
+        L.hirm_gpu_dataset_counts(ds, ctypes.byref(nd), ctypes.byref(nr))
+        name, n = ctypes.c_char_p(), ctypes.c_int32()
+        dnames, domains = [], {}
+        for d in range(nd.value):
+            L.hirm_gpu_dataset_domain(ds, d, ctypes.byref(name), ctypes.byref(n))
+            dnames.append(name.value.decode()); domains[dnames[-1]] = n.value
+        schema, observations = {}, {}
+        ar, nobs, doms = ctypes.c_int32(), ctypes.c_int64(), (ctypes.c_int32 * MAX_ARITY)()
+        for r in range(nr.value):
+            L.hirm_gpu_dataset_relation(ds, r, ctypes.byref(name), ctypes.byref(ar), doms, ctypes.byref(nobs), None, None)
+            rn = name.value.decode()
+            schema[rn] = [dnames[doms[k]] for k in range(ar.value)]
+            ids = torch.empty((nobs.value, ar.value), dtype=torch.int32, device=dev)
+            val = torch.empty(nobs.value, dtype=torch.uint8, device=dev)
+            if L.hirm_gpu_dataset_copy_relation(ds, r, ids.data_ptr(), val.data_ptr()):
+                raise EngineError(L.hirm_gpu_dataset_last_error().decode())
+            observations[rn] = (ids, val)
+        names = None
+        if with_names:
+            names = {}
+            for d, dn in enumerate(dnames):
+                names[dn] = []
+                for c in range(domains[dn]):
+                    L.hirm_gpu_dataset_entity(ds, d, c, ctypes.byref(name))
+                    names[dn].append(name.value.decode())
+        t = (ctypes.c_double * 4)()
+        L.hirm_gpu_dataset_timings(ds, t)
+        return domains, schema, observations, names, dict(h2d_s=t[0], split_parse_s=t[1], dictionary_s=t[2], coo_s=t[3])
+    finally:
+        L.hirm_gpu_dataset_free(ds)
 
 
 def _p(a, t):

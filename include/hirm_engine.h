@@ -270,6 +270,27 @@ int hirm_dataset_relation(const hirm_dataset *ds, int rel, const char **name, in
 int hirm_dataset_observations(const hirm_dataset *ds, int rel, const int32_t **ids, const uint8_t **val);
 int hirm_dataset_entity(hirm_dataset *ds, int dom, int32_t code, const char **name);
 
+/* ---- the same reader on the GPU, for files of 1e8 lines and more (csrc/ingest_gpu.cu) -------------------------------------
+ * The .obs file is copied to the device as it is; lines are split, tokens hashed, entity names numbered per domain in order
+ * of first appearance (exactly the codes of cxx/util_io.cc:63-96 / hirm_dataset_load) and the COO arrays of every relation
+ * written by streaming kernels.  The observations of a relation come out in an unspecified order (the engine's stores do
+ * not depend on it).  Errors carry the 1-based line number, as the host reader's do: values other than 0 / 1, unknown
+ * relation, wrong number of entities, an observation listed twice (cxx/hirm.hh:272).  The returned COO arrays are DEVICE
+ * buffers owned by the dataset (valid until hirm_gpu_dataset_free); names are kept on the host for the writers. */
+typedef struct hirm_gpu_dataset hirm_gpu_dataset;
+const char *hirm_gpu_dataset_last_error(void);
+int hirm_gpu_dataset_load(const char *schema_path, const char *obs_path, int device, hirm_gpu_dataset **out);
+int hirm_gpu_dataset_free(hirm_gpu_dataset *ds);
+int hirm_gpu_dataset_counts(const hirm_gpu_dataset *ds, int32_t *n_domains, int32_t *n_relations);
+int hirm_gpu_dataset_domain(const hirm_gpu_dataset *ds, int dom, const char **name, int32_t *n_entities);
+int hirm_gpu_dataset_relation(const hirm_gpu_dataset *ds, int rel, const char **name, int32_t *arity, int32_t *doms, int64_t *nobs,
+                              const int32_t **d_ids, const uint8_t **d_val);
+int hirm_gpu_dataset_entity(const hirm_gpu_dataset *ds, int dom, int32_t code, const char **name);
+/* D2D copy of one relation's arrays into the caller's device buffers: ids [nobs * arity] int32, val [nobs] uint8 */
+int hirm_gpu_dataset_copy_relation(const hirm_gpu_dataset *ds, int rel, int32_t *d_ids_out, uint8_t *d_val_out);
+/* seconds spent: [0] host-to-device copy of the text, [1] line split + parse, [2] dictionaries, [3] COO arrays + duplicate check */
+int hirm_gpu_dataset_timings(const hirm_gpu_dataset *ds, double *seconds4);
+
 #ifdef __cplusplus
 }
 #endif
