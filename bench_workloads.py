@@ -208,3 +208,64 @@ def bench_c5(dev, peak_gbs, comm, chains=8, steps=2, warmup=1, n=200_000, n_unar
                         "frac": achieved / peak_gbs, "traffic": None, "algorithmic_bytes_per_pass_per_chain": bytes_pass,
                         "note": "per GPU: bytes of all chains' entity passes / entity-step time / n_gpus"}}
     return rec
+
+
+def bench_ksweep(eng, dev, peak_gbs, ks=(2, 4, 8, 16, 32, 64), n=20000, chains=0, moves=1000, max_tables=64, seed=0):
+    """Dense R(e, e) kernel against the number of live tables (BASELINE config 3: "up to 64 clusters"): for every K a data
+    set with K planted blocks (theta[K, K] ~ Beta(.5, .5)), chains started AT the planted partition (so K tables are alive),
+    `moves` entity moves per chain from resident move lists.  Algorithmic bytes per move = 2 n (row + column of uint8 cells)."""
+    import torch
+    props = torch.cuda.get_device_properties(dev)
+    chains = chains or 8 * props.multi_processor_count
+    pitch = (n + 15) // 16 * 16
+    out = []
+    g = torch.Generator(device=dev)
+    hs = []
+    for K in ks:
+        g.manual_seed(777 + seed + K)
+        rng = np.random.default_rng(seed + K)
+        zt = np.sort(rng.integers(0, K, n)).astype(np.int32)
+        zt[:K] = np.arange(K)                                  # every block is populated
+        theta = torch.from_numpy(rng.beta(0.5, 0.5, size=(K, K))).to(dev)
+        zd = torch.from_numpy(zt.astype(np.int64)).to(dev)
+        s0 = torch.full((n, pitch), 0xFF, dtype=torch.uint8, device=dev)
+        for r0 in range(0, n, 2000):
+            p = theta[zd[r0:r0 + 2000]][:, zd]
+            s0[r0:r0 + 2000, :n] = (torch.rand(p.shape, device=dev, generator=g, dtype=torch.float32) < p).to(torch.uint8)
+        s1 = torch.full((n, pitch), 0xFF, dtype=torch.uint8, device=dev)
+        s1[:, :n] = s0[:, :n].t()
+        torch.cuda.synchronize()
+        h0 = eng.irm_create([n], [[0, 0]], max_tables=max_tables)
+        eng.set_observations_dense(h0, 0, s0.data_ptr(), pitch, s1.data_ptr(), pitch)
+        eng.finalize(h0)
+        hs = [h0]
+        for c in range(1, chains):
+            h = eng.irm_create([n], [[0, 0]], max_tables=max_tables)
+            eng.share_observations(h, h0)
+            hs.append(h)
+        for c, h in enumerate(hs):
+            eng.set_assignments(h, 0, zt)
+            eng.set_rng(h, c | (2 << 40), 0)
+        eng.logp_scores(hs)
+        d_off = torch.arange(chains + 1, dtype=torch.int64, device=dev) * moves
+        d_dom = torch.zeros(chains * moves, dtype=torch.int32, device=dev)
+        d_stream = torch.arange(chains, dtype=torch.int64, device=dev) + (2 << 40)
+        irm_ids = np.asarray(hs, dtype=np.int32)
+        ms = []
+        for rep in range(3):
+            items = torch.randint(0, n, (chains * moves,), device=dev, generator=g, dtype=torch.int32)
+            ctr = torch.full((chains,), rep * moves, dtype=torch.int64, device=dev)
+            eng.sweep_device(irm_ids, d_off.data_ptr(), d_dom.data_ptr(), items.data_ptr(), seed, d_stream.data_ptr(), ctr.data_ptr())
+            torch.cuda.synchronize()
+            ms.append(eng.last_sweep_info()["kernel_ms"])
+        best = min(ms[1:])
+        alive = int(len(np.unique(eng.get_assignments(hs[0], 0))))
+        rate = chains * moves / (best * 1e-3)
+        out.append({"planted_tables": int(K), "tables_alive_chain0_after": alive, "moves_per_s": rate, "kernel_ms": best,
+                    "algorithmic_gbs": rate * 2.0 * n / 1e9, "frac_of_hbm_peak": rate * 2.0 * n / 1e9 / peak_gbs})
+        for h in hs:
+            eng.irm_destroy(h)
+        del s0, s1
+        torch.cuda.empty_cache()
+    return {"workload": "C3 shape, n=%d, K planted blocks, chains started at the planted partition; %d chains x %d moves, kernel time (CUDA events), best of 2 after a warm-up launch"
+                        % (n, chains, moves), "kernel": "dense_ree_sweep_kernel", "peak_gbs": peak_gbs, "rows": out}

@@ -98,6 +98,7 @@ struct Irm {
     bool any_hashed = false;
     // generic kernel: compact group-accumulator spaces per (relation, domain) (engine_types.cuh: RelDom)
     DevBuf<RelDom> rdesc; std::vector<DevBuf<int32_t>> cmap; std::vector<int32_t> ctot;
+    std::vector<DevBuf<unsigned char>> ctmpl; bool tmpl_dirty = true;   // per domain: GroupRec template per accumulator cell
     DevBuf<cell_t> gacc; DevBuf<uint32_t> gbm;
     DevBuf<int64_t> gl_cell; int64_t gl_cap = 0;      // generic kernel: group records beyond the shared-memory ones
     DevBuf<int32_t> error;
@@ -636,6 +637,12 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
         }
         CK(irm->rdesc.ensure(rd.size()));
         if (!rd.empty()) CK(cudaMemcpy(irm->rdesc.p, rd.data(), rd.size() * sizeof(RelDom), cudaMemcpyHostToDevice));
+        irm->ctmpl.resize((size_t)nd);
+        for (int d = 0; d < nd; d++) {                       // cell templates where the cell space is small (filled in ensure_counts)
+            if (irm->ctot[(size_t)d] > 0 && irm->ctot[(size_t)d] <= (1 << 16)) CK(irm->ctmpl[(size_t)d].ensure((size_t)irm->ctot[(size_t)d] * GROUP_REC_BYTES));
+            else irm->ctmpl[(size_t)d].release();
+        }
+        irm->tmpl_dirty = true;
         // this IRM's view of each domain's unary block: column mask, accumulator cell per column
         irm->ub_mask.resize((size_t)nd); irm->ub_cell.resize((size_t)nd);
         for (int d = 0; d < nd; d++) {
@@ -720,6 +727,7 @@ static int upload_desc(hirm_engine *e, int32_t id) {
     D.rel = irm->d_rel.p;
     D.rdesc = irm->rdesc.p; D.gacc = irm->gacc.p; D.gbm = irm->gbm.p;
     for (int d = 0; d < irm->n_domains && d < (int)irm->cmap.size(); d++) { D.cmap[d] = irm->cmap[(size_t)d].p; D.ctot[d] = irm->ctot[(size_t)d]; }
+    for (int d = 0; d < irm->n_domains && d < (int)irm->ctmpl.size(); d++) D.ctmpl[d] = irm->ctmpl[(size_t)d].p;
     D.gl_cell = irm->gl_cell.p; D.gl_cap = irm->gl_cap;
     D.error = irm->error.p;
     e->h_irms[id] = D;
@@ -789,7 +797,16 @@ static int ensure_counts(hirm_engine *e, int32_t id) {
     if (finalize_store(e, irm) || ensure_scratch(e, irm)) return -1;
     for (int d = 0; d < irm->n_domains; d++)
         if (!irm->have_z[d]) return fail("set_assignments has not been called for every domain");
+    const bool desc_was_dirty = irm->desc_dirty;
     if (upload_desc(e, id)) return -1;
+    if (irm->tmpl_dirty || desc_was_dirty) {             // the templates hold descriptor fields (count-table pointers, strides)
+        for (int d = 0; d < irm->n_domains && d < (int)irm->ctmpl.size(); d++) {
+            if (!irm->ctmpl[(size_t)d].p) continue;
+            build_cell_templates_kernel<<<(irm->ctot[(size_t)d] + 255) / 256, 256, 0, e->stream>>>(e->d_irms.p, id, d, (GroupRec *)irm->ctmpl[(size_t)d].p);
+            CK(cudaGetLastError());
+        }
+        irm->tmpl_dirty = false;
+    }
     if (!irm->counts_dirty) return 0;
     ObsStore &S = *irm->obs;
     CK(cudaMemsetAsync(irm->hused.p, 0, (size_t)std::max(irm->n_relations, 1) * sizeof(uint32_t), e->stream));
@@ -1625,9 +1642,12 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
                     attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
                     cfg.attrs = attr; cfg.numAttrs = 1;
                     int n_clusters = 0;
-                    if (cudaOccupancyMaxActiveClusters(&n_clusters, generic_sweep_kernel, &cfg) != cudaSuccess || n_clusters < 1) {
+                    // every cluster of the class must be resident at once (the IRMs run for the whole launch: a cluster that waits
+                    // for a free GPC slot doubles the launch time): halve the cluster size until the class fits
+                    if (cudaOccupancyMaxActiveClusters(&n_clusters, generic_sweep_kernel, &cfg) != cudaSuccess || n_clusters < n_cls) {
                         cudaGetLastError();
-                        continue;                                  // this cluster size cannot be placed: halve it
+                        if (getenv("HIRM_DEBUG_CLUSTERS")) fprintf(stderr, "[hirm] cluster size %d: %d clusters fit, %d wanted: halving\n", csize, n_clusters, n_cls);
+                        continue;
                     }
                 }
                 break;

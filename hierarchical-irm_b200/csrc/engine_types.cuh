@@ -87,6 +87,7 @@ struct IrmDev {
     // generic-kernel group accumulators
     const RelDom *rdesc;          // [n_relations * n_domains]
     const int32_t *cmap[MAX_DOMAINS];   // [ctot[d]] relation owning each accumulator cell of domain d
+    const void *ctmpl[MAX_DOMAINS];     // [ctot[d]] GroupRec template of each cell (generic_sweep.cuh), or null: decoded per move
     int32_t ctot[MAX_DOMAINS];
     cell_t *gacc;                 // [max ctot] accumulator, all zero between moves       (used when ctot[d] > shared capacity)
     uint32_t *gbm;                // [max ctot / 32] one bit per non-zero accumulator cell

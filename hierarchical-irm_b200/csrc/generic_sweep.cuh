@@ -113,6 +113,37 @@ __device__ __forceinline__ int64_t group_cell_at(const GroupRec &g, int t) {
     return c;
 }
 
+// The record of accumulator cell `cell` of domain d, all but the group's own counts: a pure function of the cell (relation,
+// self pattern, tables of the other positions) and of the IRM's descriptors -- precomputed per cell where the cell space is
+// small enough (build_cell_templates_kernel), decoded on the fly otherwise.
+__device__ __forceinline__ GroupRec decode_cell(const IrmDev &irm, int d, int32_t cell) {
+    const int rel = irm.cmap[d][cell];
+    const RelationDev *R = &irm.rel[rel];
+    const RelDom *D = irm.rdesc + (int64_t)rel * irm.n_domains + d;
+    GroupRec rc;
+    rc.R = R; rc.counts = R->counts; rc.hcap = R->hcap; rc.cell = cell;
+    rc.twice = (int16_t)(D->b >= 0); rc.ca = (int32_t)R->cstride[D->a]; rc.cb = D->b >= 0 ? (int32_t)R->cstride[D->b] : 0;
+    rc.pat = (int16_t)(D->b >= 0 && cell >= D->base[2] ? 2 : D->b >= 0 && cell >= D->base[1] ? 1 : 0);
+    const int32_t local = cell - D->base[rc.pat];
+    const int32_t rest_k = local % D->rest_size;
+    rc.dother = (int16_t)(local / D->rest_size);
+    int64_t rest_c = 0;
+    for (int p = 0; p < R->arity; p++) {
+        if (p == D->a || p == D->b) continue;
+        const int digit = (rest_k / D->rstride[p]) % irm.dom[R->dom[p]].kcap;
+        rest_c += digit * R->cstride[p];
+    }
+    rc.rest_c = rest_c;
+    rc.own = 0;
+    rc.row0 = D->base[0] + rest_k; rc.col0 = D->base[1] + rest_k; rc.diag = D->base[2] + rest_k; rc.rs = D->rest_size;
+    rc.pad = 0;
+    return rc;
+}
+__global__ void build_cell_templates_kernel(const IrmDev *irms, int irm_id, int d, GroupRec *out) {
+    const IrmDev &irm = irms[irm_id];
+    for (int32_t cell = blockIdx.x * blockDim.x + threadIdx.x; cell < irm.ctot[d]; cell += gridDim.x * blockDim.x) out[cell] = decode_cell(irm, d, cell);
+}
+
 // S(N+1, s+x) - S(N, s) for a group of ONE observation (every group of a unary relation, most groups of a sparse one):
 // log(s + 1) - log(N + 2) if x = 1, log(N - s + 1) - log(N + 2) if x = 0 -- two logarithms of integers instead of the
 // general form's six; gn = 0 (a lane without work) gives 0.  `lt` is the table of log(m), m < LOGTAB_SIZE.
@@ -522,28 +553,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         const int64_t ngroups = base < glcap ? base : glcap;
         GEN_PHASE(1);
         // ---- B2: decode every group once, one group per thread (for every candidate) ---------------------------------
+        const GroupRec *tmpl = reinterpret_cast<const GroupRec *>(irm.ctmpl[d]);
         for (int64_t g = tid; g < ngroups; g += NT) {
             const int32_t cell = g < RCAP ? s_bits[g] : recs[g].cell;
-            const int rel = irm.cmap[d][cell];
-            const RelationDev *R = &irm.rel[rel];
-            const RelDom *D = rdesc + (int64_t)rel * irm.n_domains;
-            GroupRec rc;
-            rc.R = R; rc.counts = R->counts; rc.hcap = R->hcap; rc.cell = cell;
-            rc.twice = (int16_t)(D->b >= 0); rc.ca = (int32_t)R->cstride[D->a]; rc.cb = D->b >= 0 ? (int32_t)R->cstride[D->b] : 0;
-            rc.pat = (int16_t)(D->b >= 0 && cell >= D->base[2] ? 2 : D->b >= 0 && cell >= D->base[1] ? 1 : 0);
-            const int32_t local = cell - D->base[rc.pat];
-            const int32_t rest_k = local % D->rest_size;
-            rc.dother = (int16_t)(local / D->rest_size);
-            int64_t rest_c = 0;
-            for (int p = 0; p < R->arity; p++) {
-                if (p == D->a || p == D->b) continue;
-                const int digit = (rest_k / D->rstride[p]) % irm.dom[R->dom[p]].kcap;
-                rest_c += digit * R->cstride[p];
-            }
-            rc.rest_c = rest_c;
+            GroupRec rc = tmpl ? tmpl[cell] : decode_cell(irm, d, cell);
             rc.own = acc[cell];
-            rc.row0 = D->base[0] + rest_k; rc.col0 = D->base[1] + rest_k; rc.diag = D->base[2] + rest_k; rc.rs = D->rest_size;
-            rc.pad = 0;
             if (g < RCAP) s_recs[g] = rc; else recs[g] = rc;
         }
         __syncthreads();

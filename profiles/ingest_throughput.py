@@ -14,20 +14,13 @@ from hirm import engine as E
 nl = int(float(os.environ.get("NL", 1e8)))
 d = os.environ.get("DIR", "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp")
 base = os.path.join(d, "hirm_ingest_bench")
-rng = np.random.default_rng(0)
+import subprocess
 t0 = time.perf_counter()
 with open(base + ".schema", "w") as f:
     f.write("bernoulli R a b c\n")
-with open(base + ".obs", "wb") as f:
-    chunk = 2_000_000
-    seen_total = 0
-    for c0 in range(0, nl, chunk):
-        m = min(chunk, nl - c0)
-        # distinct cells: a strided walk through the 1e15-cell cube (a permutation of Z_n^3 never repeats a cell)
-        idx = (np.arange(c0, c0 + m, dtype=np.int64) * 7_777_777_777 + 12345) % (100_000 ** 3)
-        a, b, c = idx // 10_000_000_000, (idx // 100_000) % 100_000, idx % 100_000
-        v = rng.integers(0, 2, m)
-        f.write("".join("%d R a%d b%d c%d\n" % t for t in zip(v.tolist(), a.tolist(), b.tolist(), c.tolist())).encode())
+gen = os.path.join(d, "hirm_gen_obs")
+subprocess.check_call(["gcc", "-O2", "-o", gen, os.path.join(ROOT, "profiles", "microbench", "gen_obs.c")])
+subprocess.check_call([gen, base + ".obs", str(nl)])          # distinct cells: a strided walk through the 1e15-cell cube
 size = os.path.getsize(base + ".obs")
 print("wrote %d lines, %.2f GB in %.0f s" % (nl, size / 1e9, time.perf_counter() - t0), flush=True)
 for rep in range(2):
