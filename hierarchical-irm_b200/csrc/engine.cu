@@ -67,6 +67,7 @@ struct DomObs {
     DevBuf<int64_t> ptr; DevBuf<uint32_t> meta; DevBuf<int32_t> other;
     int64_t nnz = 0; int n_other = 0; int64_t max_deg = 0;
     int ub_block = -1, n_unary = 0;    // unary-block relations of the domain (all from one block)
+    std::vector<int> touching;         // CSR relations touching the domain; a CSR entry names its relation by its position here
 };
 // Unary relations over one domain as entity-major bit rows: relation-owned, built once, shared by every IRM.
 struct UnaryBlock {
@@ -104,6 +105,7 @@ struct Irm {
     DevBuf<int32_t> error;
     DevBuf<RelationDev> d_rel;
     std::vector<DevBuf<uint32_t>> ub_mask; std::vector<DevBuf<int32_t>> ub_cell;   // per domain: this IRM's view of the unary block
+    std::vector<DevBuf<ADesc>> adesc;   // per domain: phase-A descriptors of its CSR relations, by ordinal
     std::vector<bool> have_z, has_absent;
     bool counts_dirty = true, desc_dirty = true, scratch_ready = false;
     bool alive = true;
@@ -517,6 +519,7 @@ static int finalize_store(hirm_engine *e, Irm *irm) {
         }
         DomObs &D = S.dom[d];
         D.nnz = 0; D.n_other = std::max(1, max_other); D.max_deg = 0;
+        D.touching = touching;
         D.ub_block = -1; D.n_unary = 0;
         for (int r = 0; r < irm->n_relations; r++) {
             if (S.rel[r].kind != 2 || irm->rdom[r][0] != d) continue;
@@ -545,8 +548,11 @@ static int finalize_store(hirm_engine *e, Irm *irm) {
         if (nnz == 0) { D.ptr.release(); continue; }
         CK(D.meta.alloc((size_t)nnz)); CK(D.other.alloc((size_t)nnz * D.n_other));
         CK(cudaMemsetAsync(D.other.p, 0, (size_t)nnz * D.n_other * sizeof(int32_t), s0));
-        for (int r : touching) {
-            csr_fill_kernel<<<coo_blocks(e, S.rel[r].nobs), 256, 0, s0>>>(csr_rel_of(irm, r), d, D.ptr.p, cursor.p, D.meta.p, D.other.p, nnz);
+        for (size_t o = 0; o < touching.size(); o++) {
+            const int r = touching[o];
+            CsrRel cr = csr_rel_of(irm, r);
+            cr.rel = (int32_t)o;                           // ordinal among the domain's CSR relations (ADesc index)
+            csr_fill_kernel<<<coo_blocks(e, S.rel[r].nobs), 256, 0, s0>>>(cr, d, D.ptr.p, cursor.p, D.meta.p, D.other.p, nnz);
             CK(cudaGetLastError());
         }
         CK(cudaStreamSynchronize(s0));                     // cursor goes out of scope
@@ -637,6 +643,22 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
         }
         CK(irm->rdesc.ensure(rd.size()));
         if (!rd.empty()) CK(cudaMemcpy(irm->rdesc.p, rd.data(), rd.size() * sizeof(RelDom), cudaMemcpyHostToDevice));
+        irm->adesc.resize((size_t)nd);
+        for (int d = 0; d < nd; d++) {
+            const std::vector<int> &tch = S.dom[d].touching;
+            std::vector<ADesc> ad(tch.size());
+            for (size_t o = 0; o < tch.size(); o++) {
+                const int r = tch[o];
+                const RelDom &D = rd[(size_t)r * nd + d];
+                ADesc &A = ad[o];
+                memset(&A, 0, sizeof(A));
+                A.arity = irm->arity[r];
+                for (int p = 0; p < MAX_ARITY; p++) { A.dom[p] = irm->rdom[r][p]; A.rstride[p] = D.rstride[p]; }
+                A.a = D.a; A.b = D.b; A.base[0] = D.base[0]; A.base[1] = D.base[1]; A.base[2] = D.base[2]; A.rest_size = D.rest_size;
+            }
+            CK(irm->adesc[(size_t)d].ensure(ad.size()));
+            if (!ad.empty()) CK(cudaMemcpy(irm->adesc[(size_t)d].p, ad.data(), ad.size() * sizeof(ADesc), cudaMemcpyHostToDevice));
+        }
         irm->ctmpl.resize((size_t)nd);
         for (int d = 0; d < nd; d++) {                       // cell templates where the cell space is small (filled in ensure_counts)
             if (irm->ctot[(size_t)d] > 0 && irm->ctot[(size_t)d] <= (1 << 16)) CK(irm->ctmpl[(size_t)d].ensure((size_t)irm->ctot[(size_t)d] * GROUP_REC_BYTES));
@@ -717,6 +739,7 @@ static int upload_desc(hirm_engine *e, int32_t id) {
         dd.alpha = irm->alpha[d];
         dd.ptr = S.dom[d].nnz ? S.dom[d].ptr.p : nullptr; dd.meta = S.dom[d].meta.p; dd.other = S.dom[d].other.p;
         dd.nnz = S.dom[d].nnz; dd.n_other = S.dom[d].n_other; dd.max_deg = S.dom[d].max_deg;
+        if (d < (int)irm->adesc.size()) { dd.adesc = irm->adesc[(size_t)d].p; dd.n_adesc = (int32_t)S.dom[d].touching.size(); }
         if (S.dom[d].ub_block >= 0 && d < (int)irm->ub_mask.size()) {
             const UnaryBlock *B = e->ublocks[(size_t)S.dom[d].ub_block].get();
             if (!B) return fail("the IRM's unary block was destroyed");
@@ -1410,6 +1433,7 @@ struct Plan {
     int64_t gen_maxdeg = 0;
     int gen_kmax = 0, gen_ndom = 0, gen_nother = 0;   // generic kernel: largest max_tables / domain count / other-id columns of its IRMs
     int gen_ubw = 0;                                  // ... widest unary-block bit row (words)
+    int gen_adesc = 0;                                // ... most CSR relations touching one domain
     std::vector<double> gen_weight;                   // per generic IRM: entries (CSR + unary columns) an average move reads
     std::vector<std::pair<int, int>> gen_classes;     // (CTAs per IRM, number of IRMs): generic_blk is ordered by class
     int gen_ctot = 0; int64_t gen_groups = 0;         // ... largest accumulator space of a domain, most groups one move can have
@@ -1491,6 +1515,7 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
                 plan.gen_nother = std::max(plan.gen_nother, D.n_other); plan.gen_maxdeg = std::max(plan.gen_maxdeg, D.max_deg);
                 const int ct = d < (int)irm->ctot.size() ? irm->ctot[(size_t)d] : 0;
                 plan.gen_ctot = std::max(plan.gen_ctot, ct);
+                plan.gen_adesc = std::max(plan.gen_adesc, (int)D.touching.size());
                 if (D.ub_block >= 0 && e->ublocks[(size_t)D.ub_block]) plan.gen_ubw = std::max(plan.gen_ubw, e->ublocks[(size_t)D.ub_block]->words);
                 plan.gen_groups = std::max(plan.gen_groups, std::min<int64_t>(D.max_deg, ct));
             }
@@ -1577,11 +1602,10 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
     CK(cudaEventRecord(e->ev0, e->stream));
     if (!plan.generic_blk.empty()) {
         // at most one IRM per SM: 1024 threads each (shortest move: every phase of a move is spread over the whole SM);
-        // up to 4 per SM: 256 threads; many: 128 threads, 8 CTAs per SM hide one another's memory latency
+        // more: 256 threads, 4 CTAs per SM (the register file's limit at 64 registers) hide one another's latency
         const int n_gen = (int)plan.generic_blk.size();
-        // (128 only for short rows: a 1000-entry row needs 8 passes of 128 threads -- measured on config 4: 1184 chains at
-        //  128 threads 5.8 M moves/s, 592 at 256 threads 10.5 M)
-        int gen_threads = n_gen <= e->num_sms ? 1024 : (n_gen <= 4 * e->num_sms || plan.gen_maxdeg > 512) ? 256 : 128;
+        // (measured on the scaled config 5, 2048 IRMs: 256 threads 26.4 M moves/s, 128 threads 20.2 M -- profiles/r02_notes.md)
+        int gen_threads = n_gen <= e->num_sms ? 1024 : 256;
         if (const char *s = getenv("HIRM_GENERIC_THREADS")) gen_threads = std::max(64, std::min(1024, atoi(s) & ~31));
         e->last_cluster = 1;
         int done = 0, li = 0;
@@ -1599,6 +1623,7 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
             GenericLaunch GL;
             GL.csize = csize;
             GL.ubw = 2 * plan.gen_ubw <= gen_threads ? plan.gen_ubw : 0;   // one thread copies one word of the two planes
+            GL.adcap = plan.gen_adesc <= 64 ? plan.gen_adesc : 0;
             GL.pcap = 4 * gen_threads;
             GL.kstride = (std::max(plan.gen_kmax, 2) + 2) & ~1;
             GL.ndom = std::max(plan.gen_ndom, 1); GL.roww = 1 + std::max(plan.gen_nother, 1);
@@ -1608,7 +1633,7 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
             const int scap_want = std::max(256, (plan.gen_ctot + 31) & ~31);
             const int rcap_want = std::max(128, (int)((std::min<int64_t>(plan.gen_groups, 1 << 20) + 31) & ~31));
             int want_ctas = std::max(1, std::min(std::min(2048 / gen_threads, 65536 / (e->gen_regs * gen_threads)), (n_gen + e->num_sms - 1) / e->num_sms));
-            const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww, 1, GL.ubw) + (size_t)e->gen_static_smem;
+            const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww, 1, GL.ubw, GL.adcap) + (size_t)e->gen_static_smem;
             const int accs = csize > 1 ? 2 : 1;              // cluster: a local and a merged accumulator per CTA
             // the accumulator decides how many CTAs share an SM (a global accumulator costs far more than a lost CTA); the group
             // records take what is left of the CTA's share, the rest of a long group list lives in the IRM's global scratch
@@ -1624,7 +1649,7 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
                     break;
                 }
             }
-            const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww, csize, GL.ubw);
+            const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww, csize, GL.ubw, GL.adcap);
             if (gen_smem > (size_t)e->max_smem_optin) return fail("generic kernel: shared-memory plan exceeds the device limit");
             if ((int)gen_smem > g_gen_smem_set) { CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem)); g_gen_smem_set = (int)gen_smem; }
             cudaLaunchConfig_t cfg;

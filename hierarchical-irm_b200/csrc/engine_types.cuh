@@ -17,6 +17,18 @@ constexpr uint32_t META_REL_MASK = (1u << META_REL_BITS) - 1;
 constexpr int META_VAL_SHIFT = 20;
 constexpr int META_SELF_SHIFT = 24;
 
+// What phase A of the generic kernel needs to know about a CSR relation while an entity of domain d moves (a copy of the
+// RelationDev / RelDom fields it reads, 64 bytes: kept in shared memory).  CSR entries name their relation by its ORDINAL
+// among the CSR relations touching the domain.
+struct ADesc {
+    int32_t arity, dom[4];        // positions' domains
+    int32_t a, b;                 // positions of the moved domain (b = -1: it occurs once)
+    int32_t base[3], rest_size;   // accumulator space (RelDom)
+    int32_t rstride[4];
+    int32_t pad;
+};
+static_assert(sizeof(ADesc) == 64, "ADesc layout");
+
 struct DomainDev {
     int32_t n;            // entities
     int32_t kcap;         // table slots
@@ -41,7 +53,8 @@ struct DomainDev {
     const uint32_t *ub_mask;  // [ub_words] columns that are relations of this IRM
     const int32_t *ub_cell;   // [ub_words * 32] accumulator cell of the column's relation in this IRM
     int32_t ub_words;
-    int32_t pad2;
+    int32_t n_adesc;          // CSR relations touching the domain
+    const ADesc *adesc;       // [n_adesc] by ordinal
 };
 
 struct RelationDev {

@@ -191,7 +191,7 @@ __device__ __forceinline__ double score_delta_any(const double *lf, const double
 
 // Dynamic shared memory of one CTA: [rcap] group records, [rcap] touched accumulator cells, [pcap] partial sums,
 // [scap] 32-bit accumulator cells.
-struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww, csize, ubw; };   // ubw: words per unary-block bit row (0: none)   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids); csize: CTAs per IRM (thread-block cluster)
+struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww, csize, ubw, adcap; };   // adcap: relation descriptors of the moved domain kept in shared memory   // ubw: words per unary-block bit row (0: none)   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids); csize: CTAs per IRM (thread-block cluster)
 __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int csize = 1) {
     return (size_t)rcap * (sizeof(GroupRec) + 4) + (size_t)pcap * 8 + (size_t)scap * 4 * (csize > 1 ? 2 : 1) + 16;   // cluster: local + merged accumulator
 }
@@ -200,9 +200,11 @@ __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int sca
 // + [ndom][kstride] (double + 2 int32): resident CRP state of every domain
 // + [threads] bitmap words and [threads] list offsets of the group-list build
 // + [2][2][ubw] words: the next / current move's unary-block bit rows (observed, value), copied one move ahead
-__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int threads, int kstride, int ndom, int roww, int csize = 1, int ubw = 0) {
+// + [adcap] ADesc
+__host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int threads, int kstride, int ndom, int roww, int csize = 1, int ubw = 0,
+                                                     int adcap = 0) {
     return generic_smem_bytes(rcap, pcap, scap, csize) + (size_t)2 * roww * threads * 4 + (size_t)2 * threads * 4 + (size_t)4 * ubw * 4 + 8 +
-           (size_t)ndom * kstride * 16;
+           (size_t)ndom * kstride * 16 + (size_t)adcap * sizeof(ADesc);
 }
 
 // Thread-block cluster per IRM (north_star subsystem 3).  The moves of one IRM are sequential, so an IRM that is alone
@@ -261,6 +263,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     double *s_logcnt_all = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_ub + 4 * UBW) + 7) & ~(uintptr_t)7);   // [ndom][KS] log(table size)
     int32_t *s_cnt_all = reinterpret_cast<int32_t *>(s_logcnt_all + GL.ndom * KS);               // [ndom][KS]
     int32_t *s_lab_all = s_cnt_all + GL.ndom * KS;
+    const int ADCAP = GL.adcap;
+    ADesc *s_adesc = reinterpret_cast<ADesc *>(s_lab_all + GL.ndom * KS);                       // [ADCAP] CSR relation descriptors of the domain being moved
+    __shared__ int32_t s_ad_dom;                                                                // which domain s_adesc holds
+    __shared__ int32_t *s_zptr[MAX_DOMAINS];                                                    // slot arrays of the domains
+    if (tid == 0) s_ad_dom = -1;
+    if (tid < MAX_DOMAINS) s_zptr[tid] = tid < irm.n_domains ? irm.dom[tid].z : nullptr;
 
     const double *logtab = g_logtab;
     for (int k = tid; k < GEN_LF; k += NT) s_lf[k] = g_logfact[k];
@@ -378,12 +386,20 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             __syncthreads();
             continue;
         }
+        if (dd.n_adesc > 0 && dd.n_adesc <= ADCAP && s_ad_dom != d) {     // (uniform) the moved domain changed: its relation descriptors into shared memory
+            __syncthreads();
+            const int32_t *src = reinterpret_cast<const int32_t *>(dd.adesc);
+            int32_t *dst = reinterpret_cast<int32_t *>(s_adesc);
+            for (int k = tid; k < dd.n_adesc * 16; k += NT) dst[k] = src[k];
+            if (tid == 0) s_ad_dom = d;
+            __syncthreads();
+        }
+        const ADesc *adesc = (dd.n_adesc > 0 && dd.n_adesc <= ADCAP) ? s_adesc : dd.adesc;
         int32_t *s_cnt = s_cnt_all + d * KS, *s_lab = s_lab_all + d * KS;
         const int hi = s_hi_all[d];
         const int ctot = irm.ctot[d];
         const bool acc_shared = ctot <= SCAP && dd.max_deg < 65535;   // the move's accumulator: shared memory, or the IRM's global scratch
         const AccView acc{acc_shared ? s_accm : nullptr, irm.gacc};   // (phase A adds into s_acc; with C = 1 they are the same array)
-        const RelDom *rdesc = irm.rdesc + d;           // descriptor of relation r: rdesc[r * n_domains]
 
         // ---- C: candidates, CRP::tables_weights_gibbs (cxx/hirm.hh:147-161): the last warp, while the others stream the row ----
         if (warp == cwarp) {
@@ -436,22 +452,20 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             for (int64_t q = beg + tid; q < end; q += (int64_t)NA * C) {
                 const bool head = q < beg + NA;                   // prefetched into shared memory one move ahead
                 const uint32_t meta = head ? rowbuf[0] : dd.meta[q];
-                const int rel = meta & META_REL_MASK;
                 const uint32_t val = (meta >> META_VAL_SHIFT) & 1u, selfmask = (meta >> META_SELF_SHIFT) & 0xFu;
-                const RelationDev *R = &irm.rel[rel];
-                const RelDom *D = rdesc + (int64_t)rel * irm.n_domains;
+                const ADesc *D = adesc + (meta & META_REL_MASK);      // the entry names its relation by ordinal
                 const bool at_a = (selfmask >> D->a) & 1u, at_b = D->b >= 0 && ((selfmask >> D->b) & 1u);
                 const int pat = at_a ? (at_b ? 2 : 0) : 1;
                 int32_t rest_k = 0, dother = 0;
                 int oi = 0; bool first = true, absent = false;
-                for (int p = 0; p < R->arity; p++) {
+                for (int p = 0; p < D->arity; p++) {
                     int slot;
                     if ((selfmask >> p) & 1u) {
                         if (first) first = false; else oi++;
                         slot = c;
                     } else {
                         const int id = head ? (int)rowbuf[(oi + 1) * NT] : dd.other[(int64_t)oi * dd.nnz + q]; oi++;
-                        slot = __ldcg(&irm.dom[R->dom[p]].z[id]);
+                        slot = __ldcg(&s_zptr[D->dom[p]][id]);
                         if (slot < 0) { absent = true; slot = 0; }
                         if (p == D->a || p == D->b) dother = slot; else rest_k += slot * D->rstride[p];
                     }

@@ -15,7 +15,7 @@ from hirm.sharded import ChainSet
 env = HS.env
 ne, nu, nb, bobs, nc = env("NE", 20000), env("NU", 200), env("NB", 8), env("BOBS", 1000000), env("NC", 8)
 domains, schema, obs, truth = HS.make(ne, nu, nb, bobs, nc, 0)
-h = ChainSet(domains, schema, obs, env("CHAINS", 8), seed=0, max_tables=env("KCAP", 96), relation_tables={r: truth[r] for r in schema})
+h = ChainSet(domains, schema, obs, env("CHAINS", 8), seed=0, max_tables=env("KCAP", 32), relation_tables={r: truth[r] for r in schema})
 h.transition_irms(); h.transition_irms()
 n_irms = sum(len(c.irms) for c in h.chains)
 buf = torch.zeros(n_irms * 32, dtype=torch.int64, device="cuda")
