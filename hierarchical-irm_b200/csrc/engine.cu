@@ -1571,11 +1571,14 @@ static void assign_cluster_classes(hirm_engine *e, Plan &plan, uint32_t flags) {
         const bool forced = (flags & HIRM_SWEEP_CLUSTER) != 0;
         const bool heavy = plan.gen_maxdeg >= 1536 || plan.gen_groups >= 384;
         if ((forced || heavy) && n_gen <= e->num_sms) {
+            // a cluster lives inside one GPC (16 to 20 SMs each): 8 x 16 SMs can be dealt out to clusters without any of them
+            // waiting for a slot; the remaining SMs take single CTAs only
+            const int budget = n_gen == 1 ? e->num_sms : std::max(n_gen, std::min(e->num_sms, getenv("HIRM_CLUSTER_BUDGET") ? atoi(getenv("HIRM_CLUSTER_BUDGET")) : 128));
             int total = n_gen;
             for (;;) {
                 int best = -1;
                 for (int i = 0; i < n_gen; i++) {
-                    if (cs[(size_t)i] >= 16 || total + cs[(size_t)i] > e->num_sms) continue;
+                    if (cs[(size_t)i] >= 16 || total + cs[(size_t)i] > budget) continue;
                     if (!forced && plan.gen_weight[(size_t)i] / cs[(size_t)i] < 192.0) continue;      // too little work per CTA to be worth a barrier
                     if (best < 0 || plan.gen_weight[(size_t)i] / cs[(size_t)i] > plan.gen_weight[(size_t)best] / cs[(size_t)best]) best = i;
                 }
@@ -1677,8 +1680,20 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
                 }
                 break;
             }
+            cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;
+            const bool dbg = getenv("HIRM_DEBUG_CLUSTERS") != nullptr;
+            if (dbg) { cudaEventCreate(&dbg0); cudaEventCreate(&dbg1); cudaEventRecord(dbg0, st); }
             CK(cudaLaunchKernelEx(&cfg, generic_sweep_kernel, args, blk, GL));
             CK(cudaGetLastError());
+            if (dbg) {
+                cudaEventRecord(dbg1, st); cudaEventSynchronize(dbg1);       // (serialises the classes: debugging only)
+                float ms = 0; cudaEventElapsedTime(&ms, dbg0, dbg1);
+                double wmax = 0, wsum = 0;
+                for (int i = done; i < done + n_cls; i++) { wmax = std::max(wmax, plan.gen_weight[(size_t)i]); wsum += plan.gen_weight[(size_t)i]; }
+                fprintf(stderr, "[hirm] class %d: %d IRMs x %d CTAs, weight max %.0f sum %.0f, scap %d rcap %d smem %zu: %.1f ms\n", li, n_cls, csize, wmax, wsum,
+                        GL.scap, GL.rcap, gen_smem, ms);
+                cudaEventDestroy(dbg0); cudaEventDestroy(dbg1);
+            }
             if (st != e->stream) { CK(cudaEventRecord(e->ev_join[li - 1], st)); CK(cudaStreamWaitEvent(e->stream, e->ev_join[li - 1], 0)); }
             e->last_launches++; e->last_kind = 0; e->last_cluster = std::max(e->last_cluster, csize);
             done += n_cls; li++;
