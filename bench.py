@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--ref-n", type=int, default=1000, help="entities of the reference arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--burn-in", type=int, default=3, help="untimed sweeps from the CRP-prior start before the warm-up steps (state preparation)")
-    ap.add_argument("--extra", default="c4,c5,ksweep", help="further BASELINE configs measured into config.extra_workloads: comma list of c4, c5, ksweep; 'none' to skip")
+    ap.add_argument("--extra", default="c4,c5,ksweep,refsize", help="further records measured into config.extra_workloads: comma list of c4, c5 (BASELINE configs 4, 5), ksweep (dense kernel against live tables), refsize (config 3 at the reference arm's sample size); 'none' to skip")
     ap.add_argument("--c4-chains", type=int, default=0)
     ap.add_argument("--c4-moves", type=int, default=0, help="moves per domain per chain per step of the C4 record")
     ap.add_argument("--c5-chains", type=int, default=8)
@@ -400,6 +400,8 @@ def main_b200(args, rank, world, local_rank):
         rec["n_gpus"], rec["scaling"] = world, "weak"
         rec["value"] = world * rec["chains_per_gpu"] * rec["moves_per_chain_per_step"] / (ms * 1e-3)
         extra["c4"] = rec
+    if "refsize" in want and rank == 0:
+        extra["c3_at_reference_sample_size"] = W.bench_c3_at(eng, dev, args.ref_n, seed=args.seed)
     if "ksweep" in want and rank == 0:
         extra["dense_k_sweep"] = W.bench_ksweep(eng, dev, peak, seed=args.seed)
     if world > 1:

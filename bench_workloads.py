@@ -269,3 +269,44 @@ def bench_ksweep(eng, dev, peak_gbs, ks=(2, 4, 8, 16, 32, 64), n=20000, chains=0
         torch.cuda.empty_cache()
     return {"workload": "C3 shape, n=%d, K planted blocks, chains started at the planted partition; %d chains x %d moves, kernel time (CUDA events), best of 2 after a warm-up launch"
                         % (n, chains, moves), "kernel": "dense_ree_sweep_kernel", "peak_gbs": peak_gbs, "rows": out}
+
+
+def bench_c3_at(eng, dev, n, chains=0, burn_in=3, sweeps=5, max_tables=64, seed=0):
+    """The headline workload's generator and state preparation at ANOTHER size `n` -- the size of the reference arm's bounded
+    sample (`bench.py --impl reference` runs the unmodified reference at n = 1000: it cannot load n = 20 000), so that the
+    two arms can also be compared like for like.  Same steps: planted two-block R(e, e), CRP(1)-prior seats, `burn_in` untimed
+    sweeps, then `sweeps` timed full sweeps of every chain (device-generated order, Philox), kernel + launch time by CUDA events."""
+    import torch
+    props = torch.cuda.get_device_properties(dev)
+    chains = chains or 32 * props.multi_processor_count
+    rng = np.random.default_rng(seed)
+    zs = np.arange(n) >= n // 2
+    x = (rng.random((n, n)) < np.where(zs[:, None] != zs[None, :], 0.9, 0.1)).astype(np.uint8)
+    h0 = eng.irm_create([n], [[0, 0]], max_tables=max_tables)
+    eng.set_observations_dense_host(h0, 0, x)
+    eng.finalize(h0)
+    hs = [h0]
+    for c in range(1, chains):
+        h = eng.irm_create([n], [[0, 0]], max_tables=max_tables)
+        eng.share_observations(h, h0)
+        hs.append(h)
+    for c, h in enumerate(hs):
+        eng.set_rng(h, c | (3 << 40), 0)
+    eng.seat_prior(hs, seed=seed)
+    for _ in range(burn_in):
+        eng.sweep_all(hs, n_sweeps=1, seed=seed)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(sweeps):
+        eng.sweep_all(hs, n_sweeps=1, seed=seed)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    tabs = [int(len(np.unique(eng.get_assignments(h, 0)))) for h in hs[:8]]
+    for h in hs:
+        eng.irm_destroy(h)
+    return {"workload": "C3 generator at n=%d (%d cells): the size of the reference arm's sample" % (n, n * n), "n_entities": n,
+            "chains_per_gpu": chains, "sweeps_timed": sweeps, "burn_in_sweeps": burn_in, "value_per_gpu": chains * n * sweeps / (ms * 1e-3),
+            "unit": "moves/s", "ms_per_sweep": ms / sweeps, "tables_alive_first_chains": tabs,
+            "note": "through hirm_engine_sweep_all (host call per sweep, order generated on the device); compare with `--impl reference` at the same n"}

@@ -373,6 +373,11 @@ __global__ void unary_block_fill_kernel(const int32_t *ids, const uint8_t *val, 
     }
 }
 
+// byte shadow of a slot array (DomainDev::zb)
+__global__ void slots_to_bytes_kernel(const int32_t *z, uint8_t *zb, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { const int v = z[i]; zb[i] = v < 0 ? (uint8_t)0xFF : (uint8_t)v; }
+}
+
 // CRP state of a domain from its slot array: customers per slot, label = slot, highest used slot + 1 -- after a device-side
 // prior draw (hirm_engine_seat_prior).  One CTA per (irm, domain) pair listed in `pairs` (irm id, domain).
 __global__ void __launch_bounds__(256) tables_from_slots_kernel(const IrmDev *irms, const int32_t *pairs) {

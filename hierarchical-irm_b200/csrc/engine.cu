@@ -89,6 +89,7 @@ struct Irm {
     std::shared_ptr<ObsStore> obs;
     // device state
     std::vector<DevBuf<int32_t>> z, tab_count, tab_label, hi;
+    std::vector<DevBuf<uint8_t>> zb; std::vector<bool> zb_dirty;   // byte shadow of z for the generic kernel's gathers; dirty = written by someone else
     std::vector<double> alpha;
     std::vector<DevBuf<cell_t>> counts;
     std::vector<std::array<int64_t, MAX_ARITY>> cstride;
@@ -283,8 +284,10 @@ extern "C" int hirm_irm_create(hirm_engine *e, int n_domains, const int32_t *n_e
     irm->obs->rel.resize(n_relations);
     irm->obs->dom.resize(n_domains);
     irm->z.resize(n_domains); irm->tab_count.resize(n_domains); irm->tab_label.resize(n_domains); irm->hi.resize(n_domains);
+    irm->zb.resize(n_domains); irm->zb_dirty.assign(n_domains, true);
     for (int d = 0; d < n_domains; d++) {
         CK(irm->z[d].alloc(n_entities[d]));
+        CK(irm->zb[d].alloc(n_entities[d]));
         CK(cudaMemset(irm->z[d].p, 0xFF, std::max(1, n_entities[d]) * sizeof(int32_t)));
         CK(irm->tab_count[d].alloc(irm->kcap[d])); CK(cudaMemset(irm->tab_count[d].p, 0, irm->kcap[d] * sizeof(int32_t)));
         CK(irm->tab_label[d].alloc(irm->kcap[d])); CK(cudaMemset(irm->tab_label[d].p, 0, irm->kcap[d] * sizeof(int32_t)));
@@ -735,7 +738,7 @@ static int upload_desc(hirm_engine *e, int32_t id) {
     for (int d = 0; d < irm->n_domains; d++) {
         DomainDev &dd = D.dom[d];
         dd.n = irm->n_ent[d]; dd.kcap = irm->kcap[d];
-        dd.z = irm->z[d].p; dd.tab_count = irm->tab_count[d].p; dd.tab_label = irm->tab_label[d].p; dd.hi = irm->hi[d].p;
+        dd.z = irm->z[d].p; dd.zb = irm->zb[d].p; dd.tab_count = irm->tab_count[d].p; dd.tab_label = irm->tab_label[d].p; dd.hi = irm->hi[d].p;
         dd.alpha = irm->alpha[d];
         dd.ptr = S.dom[d].nnz ? S.dom[d].ptr.p : nullptr; dd.meta = S.dom[d].meta.p; dd.other = S.dom[d].other.p;
         dd.nnz = S.dom[d].nnz; dd.n_other = S.dom[d].n_other; dd.max_deg = S.dom[d].max_deg;
@@ -890,7 +893,7 @@ extern "C" int hirm_irm_set_assignments(hirm_engine *e, int32_t id, int dom, con
     CK(cudaMemcpy(irm->tab_count[dom].p, cnt.data(), kcap * sizeof(int32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(irm->tab_label[dom].p, lab.data(), kcap * sizeof(int32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(irm->hi[dom].p, &hi, sizeof(int32_t), cudaMemcpyHostToDevice));
-    irm->have_z[dom] = true; irm->counts_dirty = true;
+    irm->have_z[dom] = true; irm->counts_dirty = true; irm->zb_dirty[dom] = true;
     irm->has_absent[dom] = false;
     for (int i = 0; i < n; i++) if (h_labels[i] < 0) irm->has_absent[dom] = true;
     return 0;
@@ -1356,7 +1359,7 @@ extern "C" int hirm_engine_seat_prior(hirm_engine *e, int n_irms, const int32_t 
             off += irm->n_ent[d];
             if (D.n > 0) draws.push_back(D);
             pairs.push_back(h_irms[k]); pairs.push_back(d);
-            irm->have_z[d] = true; irm->has_absent[d] = false;
+            irm->have_z[d] = true; irm->has_absent[d] = false; irm->zb_dirty[d] = true;
         }
         irm->counts_dirty = true;
         if (upload_desc(e, h_irms[k])) return -1;
@@ -1405,6 +1408,7 @@ extern "C" int hirm_irm_seat_entities(hirm_engine *e, int32_t id, int dom, int n
     CK(cudaMemcpy(irm->tab_count[dom].p, cnt.data(), kcap * sizeof(int32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(irm->tab_label[dom].p, lab.data(), kcap * sizeof(int32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(irm->hi[dom].p, &hi, sizeof(int32_t), cudaMemcpyHostToDevice));
+    irm->zb_dirty[dom] = true;
     bool absent = false;
     for (int i = 0; i < ne; i++) if (z[(size_t)i] < 0) absent = true;
     irm->has_absent[dom] = absent;
@@ -1504,8 +1508,18 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
             } else if (irm->n_ent[0] != plan.n_ent || irm->kcap[0] != plan.kcap) {
                 return fail("dense irms of one sweep must share a shape");
             }
+            irm->zb_dirty[0] = true;                       // the dense kernel writes z only
             plan.dense_blk.push_back(k);
         } else {
+            for (int d = 0; d < irm->n_domains; d++) {     // byte shadows of the slot arrays, where someone else wrote z
+                if (!irm->zb_dirty[(size_t)d]) continue;
+                if (irm->n_ent[(size_t)d] > 0) {
+                    slots_to_bytes_kernel<<<std::max(1, std::min((irm->n_ent[(size_t)d] + 255) / 256, e->num_sms * 8)), 256, 0, e->stream>>>(
+                        irm->z[(size_t)d].p, irm->zb[(size_t)d].p, irm->n_ent[(size_t)d]);
+                    CK(cudaGetLastError());
+                }
+                irm->zb_dirty[(size_t)d] = false;
+            }
             for (auto &R : irm->obs->rel)
                 if (R.kind == 1) return fail("no kernel for this irm: dense slabs are supported for a single R(e,e) relation only");
             for (int32_t kc : irm->kcap) plan.gen_kmax = std::max(plan.gen_kmax, (int)kc);
@@ -1766,6 +1780,9 @@ extern "C" int hirm_engine_sweep(hirm_engine *e, int n_irms, const int32_t *h_ir
     }
     if (trace_cap > 0) {
         CK(e->s_trace_n.ensure(nmz)); CK(e->s_trace_labels.ensure(nmz * trace_cap)); CK(e->s_trace_logps.ensure(nmz * trace_cap));
+        // entries beyond a move's candidates read as zero
+        CK(cudaMemsetAsync(e->s_trace_labels.p, 0, nmz * trace_cap * sizeof(int32_t), st));
+        CK(cudaMemsetAsync(e->s_trace_logps.p, 0, nmz * trace_cap * sizeof(double), st));
     }
     SweepArgs args;
     memset(&args, 0, sizeof(args));

@@ -33,6 +33,8 @@ struct DomainDev {
     int32_t n;            // entities
     int32_t kcap;         // table slots
     int32_t *z;           // [n] slot of each entity, -1 = not in the domain        (CRP::assignments, cxx/hirm.hh:75)
+    uint8_t *zb;          // [n] the same as bytes (0xFF = not in the domain): what the generic kernel's gathers read -- a quarter of the
+                          //     footprint, so that the slot arrays of hundreds of chains stay in the L2
     int32_t *tab_count;   // [kcap] customers per slot, 0 = free                     (CRP::tables sizes, :74)
     int32_t *tab_label;   // [kcap] reference table label of the slot
     int32_t *hi;          // [1] highest used slot + 1

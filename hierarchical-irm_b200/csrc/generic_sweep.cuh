@@ -266,9 +266,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     const int ADCAP = GL.adcap;
     ADesc *s_adesc = reinterpret_cast<ADesc *>(s_lab_all + GL.ndom * KS);                       // [ADCAP] CSR relation descriptors of the domain being moved
     __shared__ int32_t s_ad_dom;                                                                // which domain s_adesc holds
-    __shared__ int32_t *s_zptr[MAX_DOMAINS];                                                    // slot arrays of the domains
+    __shared__ uint8_t *s_zptr[MAX_DOMAINS];                                                    // slot arrays of the domains (the byte shadows)
     if (tid == 0) s_ad_dom = -1;
-    if (tid < MAX_DOMAINS) s_zptr[tid] = tid < irm.n_domains ? irm.dom[tid].z : nullptr;
+    if (tid < MAX_DOMAINS) s_zptr[tid] = tid < irm.n_domains ? irm.dom[tid].zb : nullptr;
 
     const double *logtab = g_logtab;
     for (int k = tid; k < GEN_LF; k += NT) s_lf[k] = g_logfact[k];
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                     } else {
                         const int id = head ? (int)rowbuf[(oi + 1) * NT] : dd.other[(int64_t)oi * dd.nnz + q]; oi++;
                         slot = __ldcg(&s_zptr[D->dom[p]][id]);
-                        if (slot < 0) { absent = true; slot = 0; }
+                        if (slot == 0xFF) { absent = true; slot = 0; }
                         if (p == D->a || p == D->b) dother = slot; else rest_k += slot * D->rstride[p];
                     }
                 }
@@ -703,6 +703,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         // z and the CRP state: written by every CTA of a cluster (identical values), so each CTA reads back its own writes
         if (tid == 0 && tnew != c) {
             __stcg(&dd.z[item], tnew);
+            __stcg(&dd.zb[item], (uint8_t)tnew);
             __stcg(&dd.tab_count[c], s_cnt[c] - 1);
             const int newcnt = (tnew < hi ? s_cnt[tnew] : 0) + 1;
             __stcg(&dd.tab_count[tnew], newcnt);
