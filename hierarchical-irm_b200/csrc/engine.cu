@@ -1585,9 +1585,8 @@ static void assign_cluster_classes(hirm_engine *e, Plan &plan, uint32_t flags) {
         const bool forced = (flags & HIRM_SWEEP_CLUSTER) != 0;
         const bool heavy = plan.gen_maxdeg >= 1536 || plan.gen_groups >= 384;
         if ((forced || heavy) && n_gen <= e->num_sms) {
-            // a cluster lives inside one GPC (16 to 20 SMs each): 8 x 16 SMs can be dealt out to clusters without any of them
-            // waiting for a slot; the remaining SMs take single CTAs only
-            const int budget = n_gen == 1 ? e->num_sms : std::max(n_gen, std::min(e->num_sms, getenv("HIRM_CLUSTER_BUDGET") ? atoi(getenv("HIRM_CLUSTER_BUDGET")) : 128));
+            // (a cluster lives inside one GPC, 16 to 20 SMs each; keeping the budget at 8 x 16 SMs made no measurable difference)
+            const int budget = std::max(n_gen, std::min(e->num_sms, getenv("HIRM_CLUSTER_BUDGET") ? atoi(getenv("HIRM_CLUSTER_BUDGET")) : e->num_sms));
             int total = n_gen;
             for (;;) {
                 int best = -1;

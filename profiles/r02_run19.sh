@@ -1,0 +1,15 @@
+#!/bin/bash
+# final-candidate run at N=1: whole GPU suite, smoke, default bench with all sub-records, launch list of the bench under ncu
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest19.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02_pytest19.log
+tail -4 gpurun_out/r02_pytest19.log
+timeout 600 python __graft_entry__.py smoke > gpurun_out/r02_smoke19.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/r02_smoke19.log
+timeout 1500 python bench.py > gpurun_out/r02_bench19.json 2> gpurun_out/r02_bench19.err; echo "bench exit $?"
+tail -c 300 gpurun_out/r02_bench19.err
+python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/r02_bench19.json') if l.startswith('{')][-1])
+print('C3', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['cpu_baseline']['value'] if d['cpu_baseline'] else None)
+for k,v in d['config']['extra_workloads'].items():
+    print(k, {a:b for a,b in v.items() if a in ('value','value_per_gpu','ms_per_step','entity_step_ms','relation_step_ms','split_s','ms_per_sweep')})
+"

@@ -40,6 +40,6 @@ def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "hierarchical-irm_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 txt = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in txt.lower() or f == "engine.py" and "oracle" not in txt.lower(), (dirpath, f)
+                assert "oracle" not in txt.lower(), (dirpath, f)      # no product file names the test infrastructure
