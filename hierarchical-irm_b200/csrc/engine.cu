@@ -1640,16 +1640,26 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
             GL.csize = csize;
             GL.ubw = 2 * plan.gen_ubw <= gen_threads ? plan.gen_ubw : 0;   // one thread copies one word of the two planes
             GL.adcap = plan.gen_adesc <= 64 ? plan.gen_adesc : 0;
+            GL.roww = 1 + std::max(plan.gen_nother, 1);
+            // chunks of the next move's row copied into shared memory a move ahead: the whole row of a CTA's share where that
+            // costs at most 24 KB (phase A then waits for the slot gathers only, not for the CSR words)
+            {
+                const int na = gen_threads > 32 ? gen_threads - 32 : gen_threads;
+                const int64_t share = (plan.gen_maxdeg + csize - 1) / csize;
+                int hk = (int)std::max<int64_t>(1, std::min<int64_t>((share + na - 1) / na, 8));
+                while (hk > 1 && (size_t)2 * hk * GL.roww * gen_threads * 4 > 24 * 1024) hk--;
+                GL.headk = hk;
+            }
             GL.pcap = 4 * gen_threads;
             GL.kstride = (std::max(plan.gen_kmax, 2) + 2) & ~1;
-            GL.ndom = std::max(plan.gen_ndom, 1); GL.roww = 1 + std::max(plan.gen_nother, 1);
+            GL.ndom = std::max(plan.gen_ndom, 1);
             // Shared-memory plan: the move's accumulator (4 bytes per cell of the largest per-domain cell space) and its group
             // records (76 bytes per group, at most min(longest row, cells) groups) stay on chip when they fit the CTA's share
             // of the SM; the fewer IRMs per SM, the bigger that share.  What does not fit goes to the IRM's global scratch.
             const int scap_want = std::max(256, (plan.gen_ctot + 31) & ~31);
             const int rcap_want = std::max(128, (int)((std::min<int64_t>(plan.gen_groups, 1 << 20) + 31) & ~31));
             int want_ctas = std::max(1, std::min(std::min(2048 / gen_threads, 65536 / (e->gen_regs * gen_threads)), (n_gen + e->num_sms - 1) / e->num_sms));
-            const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww, 1, GL.ubw, GL.adcap) + (size_t)e->gen_static_smem;
+            const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww, 1, GL.ubw, GL.adcap, GL.headk) + (size_t)e->gen_static_smem;
             const int accs = csize > 1 ? 2 : 1;              // cluster: a local and a merged accumulator per CTA
             // the accumulator decides how many CTAs share an SM (a global accumulator costs far more than a lost CTA); the group
             // records take what is left of the CTA's share, the rest of a long group list lives in the IRM's global scratch
@@ -1665,7 +1675,7 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
                     break;
                 }
             }
-            const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww, csize, GL.ubw, GL.adcap);
+            const size_t gen_smem = generic_smem_bytes(GL.rcap, GL.pcap, GL.scap, gen_threads, GL.kstride, GL.ndom, GL.roww, csize, GL.ubw, GL.adcap, GL.headk);
             if (gen_smem > (size_t)e->max_smem_optin) return fail("generic kernel: shared-memory plan exceeds the device limit");
             if ((int)gen_smem > g_gen_smem_set) { CK(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem)); g_gen_smem_set = (int)gen_smem; }
             cudaLaunchConfig_t cfg;

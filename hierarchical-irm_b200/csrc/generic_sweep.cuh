@@ -191,7 +191,7 @@ __device__ __forceinline__ double score_delta_any(const double *lf, const double
 
 // Dynamic shared memory of one CTA: [rcap] group records, [rcap] touched accumulator cells, [pcap] partial sums,
 // [scap] 32-bit accumulator cells.
-struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww, csize, ubw, adcap; };   // adcap: relation descriptors of the moved domain kept in shared memory   // ubw: words per unary-block bit row (0: none)   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids); csize: CTAs per IRM (thread-block cluster)
+struct GenericLaunch { int32_t rcap, pcap, scap, kstride, ndom, roww, csize, ubw, adcap, headk; };   // headk: chunks (of one entry per thread) of the next move's row copied ahead   // adcap: relation descriptors of the moved domain kept in shared memory   // ubw: words per unary-block bit row (0: none)   // ndom: most domains of an IRM; roww: words per prefetched row entry (1 + other ids); csize: CTAs per IRM (thread-block cluster)
 __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int csize = 1) {
     return (size_t)rcap * (sizeof(GroupRec) + 4) + (size_t)pcap * 8 + (size_t)scap * 4 * (csize > 1 ? 2 : 1) + 16;   // cluster: local + merged accumulator
 }
@@ -202,8 +202,8 @@ __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int sca
 // + [2][2][ubw] words: the next / current move's unary-block bit rows (observed, value), copied one move ahead
 // + [adcap] ADesc
 __host__ __device__ inline size_t generic_smem_bytes(int rcap, int pcap, int scap, int threads, int kstride, int ndom, int roww, int csize = 1, int ubw = 0,
-                                                     int adcap = 0) {
-    return generic_smem_bytes(rcap, pcap, scap, csize) + (size_t)2 * roww * threads * 4 + (size_t)2 * threads * 4 + (size_t)4 * ubw * 4 + 8 +
+                                                     int adcap = 0, int headk = 1) {
+    return generic_smem_bytes(rcap, pcap, scap, csize) + (size_t)2 * headk * roww * threads * 4 + (size_t)2 * threads * 4 + (size_t)4 * ubw * 4 + 8 +
            (size_t)ndom * kstride * 16 + (size_t)adcap * sizeof(ADesc);
 }
 
@@ -253,10 +253,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_part + PCAP);                              // [scap] observations | ones << 16 (cluster: this CTA's share of the row)
     uint32_t *s_accm = C > 1 ? s_acc + SCAP : s_acc;                                            // [scap] cluster: the merged accumulator
     int32_t *s_bits = reinterpret_cast<int32_t *>(s_accm + SCAP);                               // [rcap]
-    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_bits + RCAP);                              // [2][roww][NT] next / current CSR row heads
+    uint32_t *s_row = reinterpret_cast<uint32_t *>(s_bits + RCAP);                              // [2][headk][roww][NT] next / current CSR row heads
     const int KS = GL.kstride;
     const int ROWW = GL.roww;
-    uint32_t *s_wbits = s_row + 2 * ROWW * NT;                                                 // [NT] bitmap words of the group-list build
+    const int HEADK = GL.headk > 0 ? GL.headk : 1;
+    uint32_t *s_wbits = s_row + 2 * HEADK * ROWW * NT;                                         // [NT] bitmap words of the group-list build
     int32_t *s_woff = reinterpret_cast<int32_t *>(s_wbits + NT);                                // [NT] their list offsets
     const int UBW = GL.ubw;
     uint32_t *s_ub = reinterpret_cast<uint32_t *>(s_woff + NT);                                 // [2][2][UBW] unary-block bit rows (next / current move)
@@ -327,11 +328,15 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         const int dm = s_pd[k];
         if (mm >= m1 || dm < 0 || tid >= NA) return;
         const DomainDev &dq = irm.dom[dm];
-        const int64_t q = s_pb[k][0] + (int64_t)crank * NA + tid;      // the head of this CTA's share of the row (chunk `crank`)
-        if (!dq.ptr || q >= s_pb[k][1]) return;
-        uint32_t *dst = s_row + ((size_t)buf * ROWW) * NT + tid;
-        cp4(dst, dq.meta + q);
-        for (int oi = 0; oi < dq.n_other && oi < ROWW - 1; oi++) cp4(dst + (oi + 1) * NT, dq.other + (int64_t)oi * dq.nnz + q);
+        if (!dq.ptr) return;
+        // this CTA's first HEADK chunks of the row (chunks crank, crank + C, ...: one entry per thread each)
+        for (int j = 0; j < HEADK; j++) {
+            const int64_t q = s_pb[k][0] + ((int64_t)crank + (int64_t)j * C) * NA + tid;
+            if (q >= s_pb[k][1]) break;
+            uint32_t *dst = s_row + (((size_t)buf * HEADK + j) * ROWW) * NT + tid;
+            cp4(dst, dq.meta + q);
+            for (int oi = 0; oi < dq.n_other && oi < ROWW - 1; oi++) cp4(dst + (oi + 1) * NT, dq.other + (int64_t)oi * dq.nnz + q);
+        }
     };
     // ... and of the entity's unary-block bit rows (both planes, every CTA of a cluster the whole row)
     auto prefetch_ub = [&](int64_t mm, int buf) {
@@ -448,9 +453,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         // ---- A: group (and, for twice-occurring domains, remove) -------------------------------------------------
         if (dd.ptr && tid < NA) {
             const int64_t beg = cur.beg + (int64_t)crank * NA, end = cur.end;      // cluster: CTA q takes chunks q, q + C, q + 2C, ... of NA entries
-            const uint32_t *rowbuf = s_row + ((size_t)rbuf * ROWW) * NT + tid;
-            for (int64_t q = beg + tid; q < end; q += (int64_t)NA * C) {
-                const bool head = q < beg + NA;                   // prefetched into shared memory one move ahead
+            int jchunk = 0;
+            for (int64_t q = beg + tid; q < end; q += (int64_t)NA * C, jchunk++) {
+                const bool head = jchunk < HEADK;                 // prefetched into shared memory one move ahead
+                const uint32_t *rowbuf = s_row + (((size_t)rbuf * HEADK + (head ? jchunk : 0)) * ROWW) * NT + tid;
                 const uint32_t meta = head ? rowbuf[0] : dd.meta[q];
                 const uint32_t val = (meta >> META_VAL_SHIFT) & 1u, selfmask = (meta >> META_SELF_SHIFT) & 0xFu;
                 const ADesc *D = adesc + (meta & META_REL_MASK);      // the entry names its relation by ordinal
