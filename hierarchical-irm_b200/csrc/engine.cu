@@ -1648,6 +1648,7 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
                 const int64_t share = (plan.gen_maxdeg + csize - 1) / csize;
                 int hk = (int)std::max<int64_t>(1, std::min<int64_t>((share + na - 1) / na, 8));
                 while (hk > 1 && (size_t)2 * hk * GL.roww * gen_threads * 4 > 24 * 1024) hk--;
+                if (n_gen > e->num_sms) hk = 1;            // several CTAs per SM: the extra shared memory costs a resident CTA, which costs more than it saves (config 4: 12.2 -> 11.7 M moves/s)
                 GL.headk = hk;
             }
             GL.pcap = 4 * gen_threads;
