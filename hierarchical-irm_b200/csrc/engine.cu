@@ -105,7 +105,10 @@ struct Irm {
     DevBuf<int64_t> gl_cell; int64_t gl_cap = 0;      // generic kernel: group records beyond the shared-memory ones
     DevBuf<int32_t> error;
     DevBuf<RelationDev> d_rel;
-    std::vector<DevBuf<uint32_t>> ub_mask; std::vector<DevBuf<int32_t>> ub_cell;   // per domain: this IRM's view of the unary block
+    // per domain: the count tables of this IRM's unary-block relations as ONE matrix [kcap][ucp] (local column j = relation), and
+    // the block column of every local column
+    std::vector<DevBuf<cell_t>> ucount; std::vector<DevBuf<int32_t>> ucolg; std::vector<int> nu, ucp;
+    std::vector<cell_t *> cptr; std::vector<int> estride;   // per relation: its dense cells' address and the stride between them
     std::vector<DevBuf<ADesc>> adesc;   // per domain: phase-A descriptors of its CSR relations, by ordinal
     std::vector<bool> have_z, has_absent;
     bool counts_dirty = true, desc_dirty = true, scratch_ready = false;
@@ -529,7 +532,6 @@ static int finalize_store(hirm_engine *e, Irm *irm) {
             if (D.ub_block >= 0 && D.ub_block != S.rel[r].ub_block) return fail("the unary-block relations of one domain must come from one block");
             D.ub_block = S.rel[r].ub_block; D.n_unary++;
         }
-        D.max_deg = D.n_unary;
         if (touching.empty() || n == 0) continue;
         static_assert(sizeof(unsigned long long) == sizeof(int64_t), "ptr is scanned in place");
         CK(D.ptr.alloc((size_t)n + 1));
@@ -547,7 +549,7 @@ static int finalize_store(hirm_engine *e, Irm *irm) {
         CK(cudaMemcpyAsync(&nnz, D.ptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s0));
         CK(cudaMemcpyAsync(&maxdeg, cursor.p + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
         CK(cudaStreamSynchronize(s0));
-        D.nnz = nnz; D.max_deg = (int64_t)maxdeg + D.n_unary;
+        D.nnz = nnz; D.max_deg = (int64_t)maxdeg;
         if (nnz == 0) { D.ptr.release(); continue; }
         CK(D.meta.alloc((size_t)nnz)); CK(D.other.alloc((size_t)nnz * D.n_other));
         CK(cudaMemsetAsync(D.other.p, 0, (size_t)nnz * D.n_other * sizeof(int32_t), s0));
@@ -595,6 +597,7 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
         const int mode = irm->table_mode[r];
         bool hashed = S.rel[r].kind == 0 && (mode == 2 || (mode == 0 && (env_hashed || irm->ncells[r] > DENSE_CELL_BUDGET)));
         if (mode == 1 && irm->ncells[r] > DENSE_CELL_BUDGET) return fail("dense count table too large: lower max_tables or use the hashed table");
+        if (S.rel[r].kind == 2) { irm->hcap[r] = 0; irm->counts[r].release(); continue; }   // cells live in the domain's unary count matrix (below)
         if (hashed) {
             // Relation::clusters as an open-addressing table: at most one non-empty cell per observation; 4 entries per
             // possible cell (emptied cells linger until the host rebuilds), grown on demand (maintain_hashed)
@@ -622,7 +625,7 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
                 RelDom &D = rd[(size_t)r * nd + d];
                 memset(&D, 0, sizeof(D));
                 D.a = D.b = -1; D.rest_size = 1;
-                if (S.rel[r].kind == 1) continue;
+                if (S.rel[r].kind != 0) continue;          // dense slabs: own kernel; unary-block relations: scored from the count matrix, no groups
                 for (int p = 0; p < irm->arity[r]; p++)
                     if (irm->rdom[r][p] == d) { if (D.a < 0) D.a = p; else D.b = p; }
                 if (D.a < 0) continue;
@@ -668,25 +671,28 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
             else irm->ctmpl[(size_t)d].release();
         }
         irm->tmpl_dirty = true;
-        // this IRM's view of each domain's unary block: column mask, accumulator cell per column
-        irm->ub_mask.resize((size_t)nd); irm->ub_cell.resize((size_t)nd);
+        irm->adesc.resize((size_t)nd);
         for (int d = 0; d < nd; d++) {
-            if (S.dom[d].ub_block < 0) continue;
-            const UnaryBlock *B = e->ublocks[(size_t)S.dom[d].ub_block].get();
-            if (!B) return fail("the IRM's unary block was destroyed");
-            std::vector<uint32_t> mask((size_t)B->words, 0u);
-            std::vector<int32_t> cell((size_t)B->words * 32, -1);
-            for (int r = 0; r < irm->n_relations; r++) {
-                if (S.rel[r].kind != 2 || irm->rdom[r][0] != d) continue;
-                const int col = S.rel[r].ub_col;
-                if (cell[(size_t)col] >= 0) return fail("two relations of one IRM name the same unary-block column");
-                mask[(size_t)col >> 5] |= 1u << (col & 31);
-                cell[(size_t)col] = rd[(size_t)r * nd + d].base[0];
+            const std::vector<int> &tch = S.dom[d].touching;
+            std::vector<ADesc> ad(tch.size());
+            for (size_t o = 0; o < tch.size(); o++) {
+                const int r = tch[o];
+                const RelDom &D = rd[(size_t)r * nd + d];
+                ADesc &A = ad[o];
+                memset(&A, 0, sizeof(A));
+                A.arity = irm->arity[r];
+                for (int p = 0; p < MAX_ARITY; p++) { A.dom[p] = irm->rdom[r][p]; A.rstride[p] = D.rstride[p]; }
+                A.a = D.a; A.b = D.b; A.base[0] = D.base[0]; A.base[1] = D.base[1]; A.base[2] = D.base[2]; A.rest_size = D.rest_size;
             }
-            CK(irm->ub_mask[(size_t)d].ensure(mask.size())); CK(irm->ub_cell[(size_t)d].ensure(cell.size()));
-            CK(cudaMemcpy(irm->ub_mask[(size_t)d].p, mask.data(), mask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(irm->ub_cell[(size_t)d].p, cell.data(), cell.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            CK(irm->adesc[(size_t)d].ensure(ad.size()));
+            if (!ad.empty()) CK(cudaMemcpy(irm->adesc[(size_t)d].p, ad.data(), ad.size() * sizeof(ADesc), cudaMemcpyHostToDevice));
         }
+        irm->ctmpl.resize((size_t)nd);
+        for (int d = 0; d < nd; d++) {                       // cell templates where the cell space is small (filled in ensure_counts)
+            if (irm->ctot[(size_t)d] > 0 && irm->ctot[(size_t)d] <= (1 << 16)) CK(irm->ctmpl[(size_t)d].ensure((size_t)irm->ctot[(size_t)d] * GROUP_REC_BYTES));
+            else irm->ctmpl[(size_t)d].release();
+        }
+        irm->tmpl_dirty = true;
         CK(irm->gacc.ensure((size_t)max_ctot)); CK(irm->gbm.ensure((size_t)(max_ctot / 32 + 1)));
         CK(cudaMemsetAsync(irm->gacc.p, 0, (size_t)max_ctot * sizeof(cell_t), e->stream));
         CK(cudaMemsetAsync(irm->gbm.p, 0, (size_t)(max_ctot / 32 + 1) * sizeof(uint32_t), e->stream));
@@ -694,6 +700,33 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
         for (int d = 0; d < irm->n_domains; d++) cap = std::max(cap, S.dom[d].max_deg);
         irm->gl_cap = cap;
         CK(irm->gl_cell.ensure((size_t)cap * (sizeof(GroupRec) / sizeof(int64_t))));   // one GroupRec per group
+    }
+    // unary-block relations: one count matrix per domain, a column per relation
+    {
+        const int nd = irm->n_domains;
+        irm->ucount.resize((size_t)nd); irm->ucolg.resize((size_t)nd); irm->nu.assign((size_t)nd, 0); irm->ucp.assign((size_t)nd, 0);
+        irm->cptr.assign((size_t)irm->n_relations, nullptr); irm->estride.assign((size_t)irm->n_relations, 1);
+        for (int r = 0; r < irm->n_relations; r++) irm->cptr[(size_t)r] = irm->counts[r].p;
+        for (int d = 0; d < nd; d++) {
+            if (S.dom[d].ub_block < 0) continue;
+            const UnaryBlock *B = e->ublocks[(size_t)S.dom[d].ub_block].get();
+            if (!B) return fail("the IRM's unary block was destroyed");
+            std::vector<int32_t> colg;
+            std::vector<int> rels;
+            std::vector<char> seen((size_t)B->n_rel, 0);
+            for (int r = 0; r < irm->n_relations; r++) {
+                if (S.rel[r].kind != 2 || irm->rdom[r][0] != d) continue;
+                if (seen[(size_t)S.rel[r].ub_col]) return fail("two relations of one IRM name the same unary-block column");
+                seen[(size_t)S.rel[r].ub_col] = 1;
+                colg.push_back(S.rel[r].ub_col); rels.push_back(r);
+            }
+            const int nu = (int)colg.size(), ucp = (nu + 31) & ~31;
+            irm->nu[(size_t)d] = nu; irm->ucp[(size_t)d] = ucp;
+            CK(irm->ucount[(size_t)d].ensure((size_t)std::max(ucp, 32) * irm->kcap[(size_t)d]));
+            CK(irm->ucolg[(size_t)d].ensure((size_t)std::max(nu, 1)));
+            if (nu) CK(cudaMemcpy(irm->ucolg[(size_t)d].p, colg.data(), (size_t)nu * sizeof(int32_t), cudaMemcpyHostToDevice));
+            for (int j = 0; j < nu; j++) { irm->cptr[(size_t)rels[(size_t)j]] = irm->ucount[(size_t)d].p + j; irm->estride[(size_t)rels[(size_t)j]] = ucp; }
+        }
     }
     irm->dense_ree = irm->n_domains == 1 && irm->n_relations == 1 && S.rel[0].kind == 1 && irm->kcap[0] <= 64;
     irm->scratch_ready = true; irm->desc_dirty = true;
@@ -724,7 +757,9 @@ static int upload_desc(hirm_engine *e, int32_t id) {
         memset(&R, 0, sizeof(R));
         R.arity = irm->arity[r]; R.kind = S.rel[r].kind;
         for (int p = 0; p < MAX_ARITY; p++) { R.dom[p] = irm->rdom[r][p]; R.cstride[p] = irm->cstride[r][p]; }
-        R.counts = irm->counts[r].p; R.ncells = irm->ncells[r];
+        R.counts = irm->cptr[(size_t)r]; R.ncells = irm->ncells[r];
+        R.estride = (uint32_t)irm->estride[(size_t)r];
+        if (R.estride > 1) R.cstride[0] = R.estride;       // a unary-block relation's cell of slot t sits at counts[t * pitch of the count matrix]
         R.hcap = irm->hcap[r]; R.hused = irm->hused.p + r;
         R.slab[0] = S.rel[r].slab[0]; R.slab[1] = S.rel[r].slab[1]; R.pitch[0] = S.rel[r].pitch[0]; R.pitch[1] = S.rel[r].pitch[1];
         R.coo_ids = S.rel[r].ids; R.coo_val = S.rel[r].val; R.nobs = S.rel[r].nobs;
@@ -743,11 +778,11 @@ static int upload_desc(hirm_engine *e, int32_t id) {
         dd.ptr = S.dom[d].nnz ? S.dom[d].ptr.p : nullptr; dd.meta = S.dom[d].meta.p; dd.other = S.dom[d].other.p;
         dd.nnz = S.dom[d].nnz; dd.n_other = S.dom[d].n_other; dd.max_deg = S.dom[d].max_deg;
         if (d < (int)irm->adesc.size()) { dd.adesc = irm->adesc[(size_t)d].p; dd.n_adesc = (int32_t)S.dom[d].touching.size(); }
-        if (S.dom[d].ub_block >= 0 && d < (int)irm->ub_mask.size()) {
+        if (S.dom[d].ub_block >= 0 && d < (int)irm->ucount.size()) {
             const UnaryBlock *B = e->ublocks[(size_t)S.dom[d].ub_block].get();
             if (!B) return fail("the IRM's unary block was destroyed");
             dd.ub_obs = B->obs.p; dd.ub_val = B->val.p; dd.ub_words = B->words;
-            dd.ub_mask = irm->ub_mask[(size_t)d].p; dd.ub_cell = irm->ub_cell[(size_t)d].p;
+            dd.ucolg = irm->ucolg[(size_t)d].p; dd.ucount = irm->ucount[(size_t)d].p; dd.nu = irm->nu[(size_t)d]; dd.ucp = irm->ucp[(size_t)d];
         }
     }
     D.rel = irm->d_rel.p;
@@ -802,6 +837,7 @@ static int maintain_hashed(hirm_engine *e, Irm *irm, bool after_rebuild) {
             if (irm->hcap[r] >= (1u << 30)) return fail("hashed count table cannot grow further");
             irm->hcap[r] *= 2;
             CK(irm->counts[r].alloc((size_t)irm->hcap[r] * 2));
+            irm->cptr[(size_t)r] = irm->counts[r].p;
             irm->desc_dirty = true;
         }
         irm->counts_dirty = true;
@@ -836,9 +872,13 @@ static int ensure_counts(hirm_engine *e, int32_t id) {
     if (!irm->counts_dirty) return 0;
     ObsStore &S = *irm->obs;
     CK(cudaMemsetAsync(irm->hused.p, 0, (size_t)std::max(irm->n_relations, 1) * sizeof(uint32_t), e->stream));
+    for (int d = 0; d < irm->n_domains && d < (int)irm->ucount.size(); d++)
+        if (irm->ucount[(size_t)d].p) CK(cudaMemsetAsync(irm->ucount[(size_t)d].p, 0, irm->ucount[(size_t)d].n * sizeof(cell_t), e->stream));
     for (int r = 0; r < irm->n_relations; r++) {
-        const size_t words = irm->hcap[r] ? (size_t)irm->hcap[r] * 2 : (size_t)irm->ncells[r];
-        CK(cudaMemsetAsync(irm->counts[r].p, 0, words * sizeof(cell_t), e->stream));
+        if (S.rel[r].kind != 2) {
+            const size_t words = irm->hcap[r] ? (size_t)irm->hcap[r] * 2 : (size_t)irm->ncells[r];
+            CK(cudaMemsetAsync(irm->counts[r].p, 0, words * sizeof(cell_t), e->stream));
+        }
         if (S.rel[r].nobs == 0) continue;
         if (S.rel[r].kind != 1) {
             int blocks = (int)std::min<int64_t>((S.rel[r].nobs + 255) / 256, 148 * 8);
@@ -862,6 +902,7 @@ static int ensure_counts(hirm_engine *e, int32_t id) {
             if (irm->hcap[r] >= (1u << 30)) return fail("hashed count table cannot grow further");
             irm->hcap[r] *= 2;
             CK(irm->counts[r].alloc((size_t)irm->hcap[r] * 2));
+            irm->cptr[(size_t)r] = irm->counts[r].p;
         }
         irm->desc_dirty = true;
         return ensure_counts(e, id);
@@ -926,7 +967,11 @@ extern "C" int hirm_irm_get_counts(hirm_engine *e, int32_t id, int rel, int32_t 
     const int a = irm->arity[rel];
     const uint32_t hcap = irm->hcap[rel];
     std::vector<cell_t> tab(hcap ? (size_t)hcap * 2 : (size_t)irm->ncells[rel]);
-    CK(cudaMemcpy(tab.data(), irm->counts[rel].p, tab.size() * sizeof(cell_t), cudaMemcpyDeviceToHost));
+    if (irm->estride[(size_t)rel] > 1)
+        CK(cudaMemcpy2D(tab.data(), sizeof(cell_t), irm->cptr[(size_t)rel], (size_t)irm->estride[(size_t)rel] * sizeof(cell_t), sizeof(cell_t),
+                        tab.size(), cudaMemcpyDeviceToHost));
+    else
+        CK(cudaMemcpy(tab.data(), irm->counts[rel].p, tab.size() * sizeof(cell_t), cudaMemcpyDeviceToHost));
     std::vector<std::vector<int32_t>> labs((size_t)a);
     for (int p = 0; p < a; p++) {
         const int d = irm->rdom[rel][p];

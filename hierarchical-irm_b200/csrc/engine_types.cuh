@@ -49,11 +49,13 @@ struct DomainDev {
     int64_t max_deg;      // longest CSR row of the domain + its unary-block relations (bounds a move's group count)
     // unary relations of the domain kept as a block of entity-major bit rows (hirm_unary_block_create): row i = entity i's
     // observations in every relation of the block, `ub_words` words per plane.  The block is relation-owned and shared
-    // by all IRMs; an IRM selects its own relations with a column mask.
+    // by all IRMs.  An IRM holds `nu` of the block's columns (local column j = block column ucolg[j]) and keeps THEIR count
+    // tables as one matrix ucount[slot * ucp + j]: a candidate table's cells of 32 relations are one 256-byte read.
     const uint32_t *ub_obs;   // [n][ub_words] observed
     const uint32_t *ub_val;   // [n][ub_words] value
-    const uint32_t *ub_mask;  // [ub_words] columns that are relations of this IRM
-    const int32_t *ub_cell;   // [ub_words * 32] accumulator cell of the column's relation in this IRM
+    const int32_t *ucolg;     // [nu] block column of local column j
+    cell_t *ucount;           // [kcap][ucp] (N | s << 32) of (table slot, local column)
+    int32_t nu, ucp;          // local columns; row pitch of ucount (nu rounded up to 32)
     int32_t ub_words;
     int32_t n_adesc;          // CSR relations touching the domain
     const ADesc *adesc;       // [n_adesc] by ordinal
@@ -68,7 +70,7 @@ struct RelationDev {
     int64_t cstride[MAX_ARITY];
     int64_t ncells;               // cells of the index space (prod of the domains' table slots)
     uint32_t hcap;                // hashed: entries (a power of two); 0 = dense
-    uint32_t hpad;
+    uint32_t estride;             // dense table: distance between consecutive cells of the index space (1; a unary-block relation's cells are a column of its domain's count matrix)
     uint32_t *hused;              // hashed: [1] entries taken so far (emptied cells stay as zero cells until the host rebuilds)
     const uint8_t *slab[2];       // dense: rows by first / by second entity
     int64_t pitch[2];
@@ -160,7 +162,7 @@ __device__ __forceinline__ void table_add(const IrmDev &irm, const RelationDev *
 // iteration over the stored cells (scores, read-back): entries of the table and the cell of entry i (0 = empty)
 __device__ __forceinline__ int64_t table_entries(const RelationDev *R) { return R->hcap ? (int64_t)R->hcap : R->ncells; }
 __device__ __forceinline__ cell_t table_entry(const RelationDev *R, int64_t i) {
-    if (!R->hcap) return R->counts[i];
+    if (!R->hcap) return R->counts[i * (int64_t)R->estride];
     return R->counts[2 * i] ? R->counts[2 * i + 1] : 0ull;
 }
 

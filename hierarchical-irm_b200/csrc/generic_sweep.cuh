@@ -483,25 +483,6 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 else { atomicAdd(&irm.gacc[cell], one); atomicOr(&irm.gbm[cell >> 5], 1u << (cell & 31)); }
             }
         }
-        // unary-block relations: one thread per column of the entity's bit row; at most one observation per (entity, relation)
-        // and one accumulator cell per relation, so a plain store does it
-        if (dd.ub_words && tid < NA) {
-            // the bit rows were copied into shared memory one move ahead (by other threads: s_ub_ready orders them); rows wider
-            // than the buffer are read in place
-            const bool staged = dd.ub_words <= UBW;
-            const uint32_t *xo = staged ? s_ub + (rbuf * 2) * UBW : dd.ub_obs + (int64_t)item * dd.ub_words;
-            const uint32_t *xv = staged ? s_ub + (rbuf * 2 + 1) * UBW : dd.ub_val + (int64_t)item * dd.ub_words;
-            for (int k = crank * NA + tid; k < dd.ub_words * 32; k += NA * C) {
-                const int w = k >> 5;
-                const uint32_t ob = xo[w] & __ldg(dd.ub_mask + w);      // the warp reads one word: a broadcast
-                if ((ob >> (k & 31)) & 1u) {
-                    const uint32_t val = (xv[w] >> (k & 31)) & 1u;
-                    const int32_t cell = __ldg(dd.ub_cell + k);
-                    if (acc_shared) s_acc[cell] = 1u | (val << 16);
-                    else { __stcg(&irm.gacc[cell], pack_cell(1u, val)); atomicOr(&irm.gbm[cell >> 5], 1u << (cell & 31)); }
-                }
-            }
-        }
         // One CTA (or one cluster) owns the IRM: the barrier alone makes the global atomics and stores visible to its threads
         // (they are performed at L2, and every mutable word is read back with ld.cg).  No __threadfence(): a gpu-scope
         // fence would also invalidate L1 and send every descriptor load of the next phase back to L2.
@@ -606,17 +587,39 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         auto eval = [&](int64_t g, int slot_t, uint32_t &N, uint32_t &sv, uint32_t &gn, uint32_t &gs) {
             finish(issue(g, slot_t), N, sv, gn, gs);
         };
-        const int nch = (int)((ngroups + 31) >> 5);
-        const bool flat = (int64_t)ncand * nch <= PCAP;
+        // The IRM's unary-block relations are not groups: their count tables are one matrix (table slot x local column) and
+        // the entity's observations two bit rows (copied into shared memory a move ahead), so a scoring unit of 32 of them
+        // is one coalesced row read.  Units of a candidate: its nch group chunks, then its nuch unary chunks.
+        const int nu = dd.nu, nuch = (nu + 31) >> 5;
+        const bool ub_staged = dd.ub_words <= UBW;
+        const uint32_t *xo = ub_staged ? s_ub + (rbuf * 2) * UBW : dd.ub_obs + (int64_t)item * dd.ub_words;
+        const uint32_t *xv = ub_staged ? s_ub + (rbuf * 2 + 1) * UBW : dd.ub_val + (int64_t)item * dd.ub_words;
+        auto issue_unary = [&](int ch, int slot_t) -> Pending {
+            Pending p{0ull, 0ull, 0ull};
+            const int j = ch * 32 + lane;
+            if (j >= nu) return p;
+            const int gcol = __ldg(dd.ucolg + j);
+            if (!((xo[gcol >> 5] >> (gcol & 31)) & 1u)) return p;            // the relation has no observation of this entity
+            p.delta = pack_cell(1u, (xv[gcol >> 5] >> (gcol & 31)) & 1u);
+            p.cur = __ldcg(dd.ucount + (int64_t)slot_t * dd.ucp + j);
+            if (slot_t == c) p.sub = p.delta;                                // virtual removal
+            return p;
+        };
+        const int nch = (int)((ngroups + 31) >> 5), nchu = nch + nuch;
+        auto issue_unit = [&](int unit) -> Pending {                         // unit = candidate * nchu + chunk
+            const int t = unit / nchu, ch = unit - t * nchu;
+            return ch < nch ? issue((int64_t)ch * 32 + lane, s_cslot[t]) : issue_unary(ch - nch, s_cslot[t]);
+        };
+        const bool flat = (int64_t)ncand * nchu <= PCAP;
         if (flat) {
-            const int nunits = ncand * nch;
+            const int nunits = ncand * nchu;
             const int u0 = crank + warp * C, ustep = NW * C;       // unit u belongs to CTA u mod C, warp (u / C) mod NW
             Pending pend{0ull, 0ull, 0ull};
-            if (u0 < nunits) { const int t0 = u0 / nch; pend = issue((int64_t)(u0 - t0 * nch) * 32 + lane, s_cslot[t0]); }
+            if (u0 < nunits) pend = issue_unit(u0);
             for (int unit = u0; unit < nunits; unit += ustep) {
                 const Pending cur = pend;
-                const int nu = unit + ustep;
-                if (nu < nunits) { const int t2 = nu / nch; pend = issue((int64_t)(nu - t2 * nch) * 32 + lane, s_cslot[t2]); }
+                const int unext = unit + ustep;
+                if (unext < nunits) pend = issue_unit(unext);
                 uint32_t N, sv, gn, gs;
                 finish(cur, N, sv, gn, gs);
                 __syncwarp();
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             csync();
             for (int t = tid; t < ncand; t += NT) {
                 double a2 = 0.0;
-                for (int ch = 0; ch < nch; ch++) a2 += s_part[t * nch + ch];
+                for (int ch = 0; ch < nchu; ch++) a2 += s_part[t * nchu + ch];
                 s_lp[t] += a2;
             }
         } else {
@@ -641,6 +644,15 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                     eval(g0 + lane, slot_t, N, sv, gn, gs);
                     __syncwarp();
                     double v = score_delta_any(s_lf, logtab, N, sv, gn, gs);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    a2 += v;
+                }
+                for (int ch = 0; ch < nuch; ch++) {
+                    uint32_t N, sv, gn, gs;
+                    finish(issue_unary(ch, slot_t), N, sv, gn, gs);
+                    __syncwarp();
+                    double v = score_delta_unit(logtab, N, sv, gn, gs);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     a2 += v;
@@ -705,6 +717,15 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             }
             if (acc_shared) s_accm[gr.cell] = 0u;     // every CTA clears its own (merged) accumulator
             else if (mine) { __stcg(&irm.gacc[gr.cell], (cell_t)0); __stcg(&irm.gbm[gr.cell >> 5], 0u); }
+        }
+        if (tnew != c) {                                   // the unary-block relations' cells of the two tables, one thread per column
+            for (int j = crank * NT + tid; j < nu; j += NT * C) {
+                const int gcol = __ldg(dd.ucolg + j);
+                if (!((xo[gcol >> 5] >> (gcol & 31)) & 1u)) continue;
+                const cell_t one = pack_cell(1u, (xv[gcol >> 5] >> (gcol & 31)) & 1u);
+                atomicAdd(dd.ucount + (int64_t)c * dd.ucp + j, (cell_t)0 - one);
+                atomicAdd(dd.ucount + (int64_t)tnew * dd.ucp + j, one);
+            }
         }
         // z and the CRP state: written by every CTA of a cluster (identical values), so each CTA reads back its own writes
         if (tid == 0 && tnew != c) {

@@ -237,8 +237,9 @@ def test_device_coo_store_equals_host_coo_store():
 @pytest.mark.gpu
 def test_unary_block_store_equals_coo_store():
     """Unary relations as columns of a relation-owned bit block (hirm_unary_block_create / hirm_irm_set_observations_unary)
-    against the same relations as CSR entries: same count tables, bit-identical candidates and log-probabilities, same
-    choices; partially observed unary relations, an IRM using a subset of the block's columns, block errors."""
+    against the same relations as CSR entries: same count tables, same candidates, log-probabilities equal to 1e-12 (the same
+    terms in another order), same choices; partially observed unary relations, an IRM using a subset of the block's columns,
+    block errors."""
     from hirm import engine as E
     rng = np.random.default_rng(8)
     n, m = 90, 40
@@ -282,7 +283,9 @@ def test_unary_block_store_equals_coo_store():
         np.testing.assert_array_equal(na, nb)
         valid = np.arange(la.shape[1])[None, :] < na[:, None]      # entries beyond a move's candidates are not written
         np.testing.assert_array_equal(la[valid], lb[valid])
-        np.testing.assert_array_equal(pa[valid], pb[valid])         # bit-identical log-probabilities
+        # the block's relations are scored from the count matrix in column order, the CSR entries as groups in cell order:
+        # the same terms added in another order
+        assert np.all(np.abs(pa[valid] - pb[valid]) <= 1e-12 * np.maximum(1.0, np.abs(pa[valid])))
         for r in range(len(rel_domains)):
             np.testing.assert_array_equal(eng.get_counts(hs[0], r), eng.get_counts(hs[1], r))
     assert len(np.unique(eng.get_assignments(hs[1], 0))) > 1
