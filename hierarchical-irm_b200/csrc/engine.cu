@@ -18,6 +18,7 @@
 #include "engine_types.cuh"
 #include "generic_sweep.cuh"
 #include "dense_sweep.cuh"
+#include "pregroup.cuh"
 #include "aux_kernels.cuh"
 
 using namespace hirm;
@@ -110,6 +111,7 @@ struct Irm {
     std::vector<DevBuf<cell_t>> ucount; std::vector<DevBuf<int32_t>> ucolg; std::vector<int> nu, ucp;
     std::vector<cell_t *> cptr; std::vector<int> estride;   // per relation: its dense cells' address and the stride between them
     std::vector<DevBuf<ADesc>> adesc;   // per domain: phase-A descriptors of its CSR relations, by ordinal
+    std::vector<bool> pregroup;         // per domain: every CSR relation holds it once (its rows can be grouped ahead of the moves)
     std::vector<bool> have_z, has_absent;
     bool counts_dirty = true, desc_dirty = true, scratch_ready = false;
     bool alive = true;
@@ -131,6 +133,10 @@ struct hirm_engine {
     DevBuf<int64_t> s_move_off; DevBuf<double> s_uniforms, s_trace_logps, s_score;
     DevBuf<uint64_t> s_stream, s_counter;
     DevBuf<long long> s_progress;
+    // pre-grouped rows: runs of the move lists, the rounds' pieces, the staged group lists
+    DevBuf<int32_t> s_runs_n, s_runs_dom, s_pg_pre, s_pg_pitch; DevBuf<int64_t> s_runs_start, s_seg_lo, s_seg_hi, s_pg_base, s_off_host;
+    DevBuf<uint2> s_pg_data;
+    int last_rounds = 1, last_pregrouped = 0, pg_smem_set = 0;
     DevBuf<double> s_alpha;
     DevBuf<cell_t> s_reltab; DevBuf<RelCand> s_relcand; DevBuf<int32_t> s_relerr;
     DevBuf<uint64_t> s_sweep0; DevBuf<int32_t> s_errs;
@@ -649,10 +655,11 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
         }
         CK(irm->rdesc.ensure(rd.size()));
         if (!rd.empty()) CK(cudaMemcpy(irm->rdesc.p, rd.data(), rd.size() * sizeof(RelDom), cudaMemcpyHostToDevice));
-        irm->adesc.resize((size_t)nd);
+        irm->adesc.resize((size_t)nd); irm->pregroup.assign((size_t)nd, false);
         for (int d = 0; d < nd; d++) {
             const std::vector<int> &tch = S.dom[d].touching;
             std::vector<ADesc> ad(tch.size());
+            bool once = true;
             for (size_t o = 0; o < tch.size(); o++) {
                 const int r = tch[o];
                 const RelDom &D = rd[(size_t)r * nd + d];
@@ -661,29 +668,11 @@ static int ensure_scratch(hirm_engine *e, Irm *irm) {
                 A.arity = irm->arity[r];
                 for (int p = 0; p < MAX_ARITY; p++) { A.dom[p] = irm->rdom[r][p]; A.rstride[p] = D.rstride[p]; }
                 A.a = D.a; A.b = D.b; A.base[0] = D.base[0]; A.base[1] = D.base[1]; A.base[2] = D.base[2]; A.rest_size = D.rest_size;
+                if (D.b >= 0) once = false;
             }
-            CK(irm->adesc[(size_t)d].ensure(ad.size()));
-            if (!ad.empty()) CK(cudaMemcpy(irm->adesc[(size_t)d].p, ad.data(), ad.size() * sizeof(ADesc), cudaMemcpyHostToDevice));
-        }
-        irm->ctmpl.resize((size_t)nd);
-        for (int d = 0; d < nd; d++) {                       // cell templates where the cell space is small (filled in ensure_counts)
-            if (irm->ctot[(size_t)d] > 0 && irm->ctot[(size_t)d] <= (1 << 16)) CK(irm->ctmpl[(size_t)d].ensure((size_t)irm->ctot[(size_t)d] * GROUP_REC_BYTES));
-            else irm->ctmpl[(size_t)d].release();
-        }
-        irm->tmpl_dirty = true;
-        irm->adesc.resize((size_t)nd);
-        for (int d = 0; d < nd; d++) {
-            const std::vector<int> &tch = S.dom[d].touching;
-            std::vector<ADesc> ad(tch.size());
-            for (size_t o = 0; o < tch.size(); o++) {
-                const int r = tch[o];
-                const RelDom &D = rd[(size_t)r * nd + d];
-                ADesc &A = ad[o];
-                memset(&A, 0, sizeof(A));
-                A.arity = irm->arity[r];
-                for (int p = 0; p < MAX_ARITY; p++) { A.dom[p] = irm->rdom[r][p]; A.rstride[p] = D.rstride[p]; }
-                A.a = D.a; A.b = D.b; A.base[0] = D.base[0]; A.base[1] = D.base[1]; A.base[2] = D.base[2]; A.rest_size = D.rest_size;
-            }
+            // the groups of this domain's entities depend on the OTHER domains' partitions only: their rows can be grouped ahead
+            // of a run of moves of the domain (pregroup_rows_kernel)
+            irm->pregroup[(size_t)d] = once && !tch.empty() && irm->ctot[(size_t)d] <= PREGROUP_MAX_CELLS && S.dom[d].max_deg < 65535;
             CK(irm->adesc[(size_t)d].ensure(ad.size()));
             if (!ad.empty()) CK(cudaMemcpy(irm->adesc[(size_t)d].p, ad.data(), ad.size() * sizeof(ADesc), cudaMemcpyHostToDevice));
         }
@@ -1486,6 +1475,7 @@ struct Plan {
     std::vector<double> gen_weight;                   // per generic IRM: entries (CSR + unary columns) an average move reads
     std::vector<std::pair<int, int>> gen_classes;     // (CTAs per IRM, number of IRMs): generic_blk is ordered by class
     int gen_ctot = 0; int64_t gen_groups = 0;         // ... largest accumulator space of a domain, most groups one move can have
+    int pg_ctot = 0;                                  // ... largest accumulator space of a domain whose rows can be grouped ahead
 };
 
 // Shared-memory plan of one dense tier: as many chains per SM as the launch has (up to 5: the register budget) and fit; the rest of
@@ -1577,6 +1567,7 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
                 plan.gen_adesc = std::max(plan.gen_adesc, (int)D.touching.size());
                 if (D.ub_block >= 0 && e->ublocks[(size_t)D.ub_block]) plan.gen_ubw = std::max(plan.gen_ubw, e->ublocks[(size_t)D.ub_block]->words);
                 plan.gen_groups = std::max(plan.gen_groups, std::min<int64_t>(D.max_deg, ct));
+                if (d < (int)irm->pregroup.size() && irm->pregroup[(size_t)d]) plan.pg_ctot = std::max(plan.pg_ctot, ct);
             }
             double w = 0.0, ents = 0.0;
             for (int d = 0; d < irm->n_domains; d++) {
@@ -1658,9 +1649,24 @@ static void assign_cluster_classes(hirm_engine *e, Plan &plan, uint32_t flags) {
     plan.generic_blk.swap(blk); plan.gen_weight.swap(wt);
 }
 
-static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args) {
-    e->last_launches = 0; e->last_kind = -1;
-    CK(cudaEventRecord(e->ev0, e->stream));
+static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args, int round = 0) {
+    if (round == 0) {
+        e->last_launches = 0; e->last_kind = -1;
+        CK(cudaEventRecord(e->ev0, e->stream));
+    }
+    if (!plan.generic_blk.empty() && args.pg_pre) {
+        // group the rows of this round's pieces ahead of the sequential pass: one CTA per IRM, the other domains' slot bytes in
+        // shared memory
+        PregroupLaunch PL;
+        PL.scap = std::max(256, (plan.pg_ctot + 31) & ~31);
+        PL.zcap = (e->max_smem_optin - 2048 - PL.scap * 4) & ~15;
+        if (PL.zcap < 0) return fail("pre-grouping: the accumulator does not fit the shared memory");
+        const int smem = PL.scap * 4 + PL.zcap;
+        if (smem > e->pg_smem_set) { CK(cudaFuncSetAttribute(pregroup_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); e->pg_smem_set = smem; }
+        pregroup_rows_kernel<<<(unsigned)plan.generic_blk.size(), PG_THREADS, (size_t)smem, e->stream>>>(args, e->s_blk.p, PL);
+        CK(cudaGetLastError());
+        e->last_launches++;
+    }
     if (!plan.generic_blk.empty()) {
         // at most one IRM per SM: 1024 threads each (shortest move: every phase of a move is spread over the whole SM);
         // more: 256 threads, 4 CTAs per SM (the register file's limit at 64 registers) hide one another's latency
@@ -1768,7 +1774,7 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
             done += n_cls; li++;
         }
     }
-    if (!plan.dense_blk.empty()) {
+    if (!plan.dense_blk.empty() && round == 0) {
         const unsigned nb = (unsigned)plan.dense_blk.size();
         SweepArgs a2 = args;
         if (plan.tiers.size() > 1) {                   // several tiers: per-chain progress hands the stopped chains over
@@ -1788,6 +1794,120 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args)
         e->last_occupancy = occ; e->last_stages = L0.stages; e->last_chunk = L0.chunk; e->last_smem = L0.total_bytes;
     }
     CK(cudaEventRecord(e->ev1, e->stream));
+    return 0;
+}
+
+// One sweep call = one launch of every kernel, unless rows can be grouped ahead (pregroup.cuh): then the move lists are cut into
+// ROUNDS -- piece r of every IRM's list -- and each round is a pre-grouping launch followed by the sequential launch.  A
+// piece is at most `seg` moves of one run of a domain that every CSR relation of its IRM holds once; everything else (short
+// runs, twice-held domains, lists with too many runs) goes through the ordinary path, merged into as few pieces as possible.
+// h_off: the move offsets on the host, or null (read back from args.move_off).  Results do not depend on any of this.
+static int run_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args, int n_irms, const int32_t *h_irms, const int64_t *h_off) {
+    e->last_rounds = 1; e->last_pregrouped = 0;
+    const int n_gen = (int)plan.generic_blk.size();
+    int mode = -1;                                         // HIRM_PREGROUP: 0 = never, 1 = wherever possible (tests); default: many chains with long rows
+    if (const char *s = getenv("HIRM_PREGROUP")) mode = atoi(s) != 0;
+    bool want = n_gen > 0 && mode != 0 && plan.pg_ctot > 0 && plan.pg_ctot <= PREGROUP_MAX_CELLS;
+    if (want && mode < 0) {
+        want = n_gen > e->num_sms && plan.gen_maxdeg >= 128;
+        for (const auto &cls : plan.gen_classes) if (cls.first > 1) want = false;
+    }
+    if (!want) return launch_sweep(e, plan, args);
+    std::vector<int64_t> off_copy;
+    if (!h_off) {
+        off_copy.resize((size_t)n_irms + 1);
+        CK(cudaMemcpyAsync(off_copy.data(), args.move_off, ((size_t)n_irms + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+        h_off = off_copy.data();
+    }
+    const int RUNCAP = 64;
+    CK(e->s_runs_n.ensure((size_t)n_gen)); CK(e->s_runs_start.ensure((size_t)n_gen * RUNCAP)); CK(e->s_runs_dom.ensure((size_t)n_gen * RUNCAP));
+    move_runs_kernel<<<(unsigned)((n_gen * 32 + 255) / 256), 256, 0, e->stream>>>(args.move_off, args.move_dom, e->s_blk.p, n_gen, RUNCAP, e->s_runs_n.p,
+                                                                             e->s_runs_start.p, e->s_runs_dom.p);
+    CK(cudaGetLastError());
+    std::vector<int32_t> rn((size_t)n_gen), rdm((size_t)n_gen * RUNCAP);
+    std::vector<int64_t> rst((size_t)n_gen * RUNCAP);
+    CK(cudaMemcpyAsync(rn.data(), e->s_runs_n.p, rn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(rdm.data(), e->s_runs_dom.p, rdm.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(rst.data(), e->s_runs_start.p, rst.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const int64_t MINRUN = mode == 1 ? 1 : 32;            // shorter runs are not worth a launch (forced mode: every run, for the tests)
+    // which runs qualify, and the staging pitch of every IRM
+    std::vector<int32_t> pitch((size_t)n_irms, 0);
+    int64_t pitch_sum = 0; bool any = false;
+    auto run_ok = [&](const Irm *irm, int dm, int64_t len) {
+        return dm >= 0 && dm < irm->n_domains && dm < (int)irm->pregroup.size() && irm->pregroup[(size_t)dm] && len >= MINRUN;
+    };
+    for (int w = 0; w < n_gen; w++) {
+        const int k = plan.generic_blk[(size_t)w];
+        const Irm *irm = e->irms[h_irms[k]].get();
+        if (rn[(size_t)w] <= 0 || rn[(size_t)w] > RUNCAP) continue;
+        for (int j = 0; j < rn[(size_t)w]; j++) {
+            const int64_t st = rst[(size_t)w * RUNCAP + j], en = j + 1 < rn[(size_t)w] ? rst[(size_t)w * RUNCAP + j + 1] : h_off[k + 1];
+            const int dm = rdm[(size_t)w * RUNCAP + j];
+            if (!run_ok(irm, dm, en - st)) continue;
+            any = true;
+            const int64_t groups = std::min<int64_t>(irm->obs->dom[(size_t)dm].max_deg, irm->ctot[(size_t)dm]);
+            pitch[(size_t)k] = std::max(pitch[(size_t)k], (int32_t)groups + 1);
+        }
+        pitch_sum += pitch[(size_t)k];
+    }
+    if (!any) return launch_sweep(e, plan, args);
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>((free_b + e->s_pg_data.n * sizeof(uint2)) / 2, (size_t)8 << 30);
+    if (const char *s = getenv("HIRM_PREGROUP_MB")) budget = (size_t)std::max(1, atoi(s)) << 20;
+    int64_t seg = std::min<int64_t>(4096, (int64_t)(budget / sizeof(uint2)) / std::max<int64_t>(pitch_sum, 1));
+    if (const char *s = getenv("HIRM_PREGROUP_SEG")) seg = std::max(1, atoi(s));
+    else if (seg < 32) return launch_sweep(e, plan, args);
+    // pieces
+    struct Piece { int64_t lo, hi; int pre; };
+    std::vector<std::vector<Piece>> pieces((size_t)n_gen);
+    size_t n_rounds = 1;
+    for (int w = 0; w < n_gen; w++) {
+        const int k = plan.generic_blk[(size_t)w];
+        const Irm *irm = e->irms[h_irms[k]].get();
+        std::vector<Piece> &P = pieces[(size_t)w];
+        const int64_t lo = h_off[k], hi = h_off[k + 1];
+        if (lo >= hi) continue;
+        if (rn[(size_t)w] <= 0 || rn[(size_t)w] > RUNCAP) { P.push_back({lo, hi, 0}); continue; }
+        for (int j = 0; j < rn[(size_t)w]; j++) {
+            const int64_t st = rst[(size_t)w * RUNCAP + j], en = j + 1 < rn[(size_t)w] ? rst[(size_t)w * RUNCAP + j + 1] : hi;
+            if (run_ok(irm, rdm[(size_t)w * RUNCAP + j], en - st)) {
+                for (int64_t a = st; a < en; a += seg) P.push_back({a, std::min(en, a + seg), 1});
+            } else if (!P.empty() && !P.back().pre) P.back().hi = en;
+            else P.push_back({st, en, 0});
+        }
+        n_rounds = std::max(n_rounds, P.size());
+    }
+    std::vector<int64_t> lo_all(n_rounds * (size_t)n_irms, 0), hi_all(n_rounds * (size_t)n_irms, 0), base((size_t)n_irms, 0);
+    std::vector<int32_t> pre_all(n_rounds * (size_t)n_irms, 0);
+    int64_t entries = 0;
+    for (int k = 0; k < n_irms; k++) { base[(size_t)k] = entries; entries += (int64_t)pitch[(size_t)k] * seg; }
+    for (int w = 0; w < n_gen; w++) {
+        const int k = plan.generic_blk[(size_t)w];
+        for (size_t r = 0; r < pieces[(size_t)w].size(); r++) {
+            const Piece &pc = pieces[(size_t)w][r];
+            lo_all[r * n_irms + k] = pc.lo; hi_all[r * n_irms + k] = pc.hi; pre_all[r * n_irms + k] = pc.pre;
+        }
+    }
+    for (int32_t kd : plan.dense_blk) { lo_all[(size_t)kd] = h_off[kd]; hi_all[(size_t)kd] = h_off[kd + 1]; }   // (the dense kernel sweeps whole lists, in round 0)
+    CK(e->s_seg_lo.ensure(lo_all.size())); CK(e->s_seg_hi.ensure(hi_all.size())); CK(e->s_pg_pre.ensure(pre_all.size()));
+    CK(e->s_pg_base.ensure((size_t)n_irms)); CK(e->s_pg_pitch.ensure((size_t)n_irms));
+    if (e->s_pg_data.n < (size_t)entries) { e->s_pg_data.release(); CK(e->s_pg_data.alloc((size_t)entries)); }
+    cudaStream_t st = e->stream;
+    CK(cudaMemcpyAsync(e->s_seg_lo.p, lo_all.data(), lo_all.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->s_seg_hi.p, hi_all.data(), hi_all.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->s_pg_pre.p, pre_all.data(), pre_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->s_pg_base.p, base.data(), base.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->s_pg_pitch.p, pitch.data(), pitch.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                         // (the sources are locals)
+    e->last_rounds = (int)n_rounds; e->last_pregrouped = 1;
+    for (size_t r = 0; r < n_rounds; r++) {
+        SweepArgs a = args;
+        a.seg_lo = e->s_seg_lo.p + r * n_irms; a.seg_hi = e->s_seg_hi.p + r * n_irms; a.pg_pre = e->s_pg_pre.p + r * n_irms;
+        a.pg_base = e->s_pg_base.p; a.pg_pitch = e->s_pg_pitch.p; a.pg_data = e->s_pg_data.p;
+        if (launch_sweep(e, plan, a, (int)r)) return -1;
+    }
     return 0;
 }
 
@@ -1847,7 +1967,7 @@ extern "C" int hirm_engine_sweep(hirm_engine *e, int n_irms, const int32_t *h_ir
     args.seed = seed; args.stream = e->s_stream.p; args.counter0 = e->s_counter.p; args.flags = flags;
     args.out_choice = e->s_choice.p; args.phase_cycles = e->d_phase_cycles;
     args.trace_cap = trace_cap; args.trace_n = e->s_trace_n.p; args.trace_labels = e->s_trace_labels.p; args.trace_logps = e->s_trace_logps.p;
-    if (launch_sweep(e, plan, args)) return -1;
+    if (run_sweep(e, plan, args, n_irms, h_irms, h_move_offsets)) return -1;
     if (h_out_choice) CK(cudaMemcpyAsync(h_out_choice, e->s_choice.p, nm * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (trace_cap > 0) {
         CK(cudaMemcpyAsync(h_trace_n, e->s_trace_n.p, nm * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1874,7 +1994,7 @@ static int sweep_device_impl(hirm_engine *e, int n_irms, const int32_t *h_irms, 
     args.move_dom = d_move_dom; args.move_item = d_move_item; args.uniforms = nullptr;
     args.seed = seed; args.stream = d_stream; args.counter0 = d_counter0; args.flags = flags;
     args.out_choice = d_out_choice; args.trace_cap = 0; args.phase_cycles = e->d_phase_cycles;
-    return launch_sweep(e, plan, args);
+    return run_sweep(e, plan, args, n_irms, h_irms, nullptr);
 }
 
 extern "C" int hirm_engine_sweep_device(hirm_engine *e, int n_irms, const int32_t *h_irms, const int64_t *d_move_offsets,
@@ -1959,6 +2079,13 @@ extern "C" int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, 
 extern "C" int hirm_engine_last_cluster_size(hirm_engine *e, int32_t *ctas_per_irm) {
     if (!e || !ctas_per_irm) return fail("null argument");
     *ctas_per_irm = e->last_cluster;
+    return 0;
+}
+
+extern "C" int hirm_engine_last_rounds(hirm_engine *e, int32_t *rounds, int32_t *pregrouped) {
+    if (!e) return fail("engine is null");
+    if (rounds) *rounds = e->last_rounds;
+    if (pregrouped) *pregrouped = e->last_pregrouped;
     return 0;
 }
 

@@ -184,6 +184,16 @@ struct SweepArgs {
     double *trace_logps;
     long long *progress;          // nullable: [n_blocks] moves of the block's IRM already made / made so far (dense tiers)
     long long *phase_cycles;      // nullable debug hook: [n_blocks][8] SM cycles per phase (thread 0's clock64)
+    // Pre-grouped rows (pregroup.cuh).  A launch may sweep a PIECE of every IRM's move list, [seg_lo, seg_hi); where pg_pre is
+    // set, the piece is a run of moves of ONE domain whose groups do not depend on that domain's own partition, and the group
+    // list of every move of the piece has been staged: pg_pitch entries per move, entry 0 = {groups, 0}, then
+    // {accumulator cell, observations | ones << 16} in ascending cell order.
+    const int64_t *seg_lo, *seg_hi;   // nullable: [n_irms]
+    const int32_t *pg_pre;            // nullable: [n_irms]
+    const int64_t *pg_base;           // [n_irms] first staging entry of the IRM's piece
+    const int32_t *pg_pitch;          // [n_irms]
+    uint2 *pg_data;
 };
+constexpr int PREGROUP_MAX_CELLS = 1 << 15;    // accumulator cells of a domain the pre-grouping kernel keeps in shared memory
 
 }  // namespace hirm

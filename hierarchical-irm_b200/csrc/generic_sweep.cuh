@@ -295,7 +295,14 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     // before the closing barrier, so everything issued during move m is visible to the block from move m + 1 on.
     __shared__ int32_t s_pd[4], s_pi[4], s_pc[4];
     __shared__ long long s_pb[4][2];
-    const int64_t m0 = args.move_off[k_list], m1 = args.move_off[k_list + 1];
+    // this launch's piece of the IRM's move list (the whole list unless the host cut it into rounds); with `pre` the group lists
+    // of the piece's moves are staged (pregroup.cuh): phases A and B1 are skipped
+    const int64_t mbase = args.move_off[k_list];
+    const int64_t m0 = args.seg_lo ? args.seg_lo[k_list] : mbase, m1 = args.seg_hi ? args.seg_hi[k_list] : args.move_off[k_list + 1];
+    const bool pre = args.pg_pre != nullptr && args.pg_pre[k_list] != 0;
+    const int pg_pitch = pre ? args.pg_pitch[k_list] : 0;
+    const uint2 *pg_list = pre ? args.pg_data + args.pg_base[k_list] : nullptr;
+    const int PGCAP = HEADK * ROWW * NT / 2;              // staged list entries the row buffer holds
     auto cp4 = [](void *dst, const void *src) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
     };
@@ -324,6 +331,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
     };
     // asynchronous copy of the head of move mm's CSR row (entry q = beg + tid: meta word and other-entity ids) into row buffer `buf`
     auto prefetch_row = [&](int64_t mm, int buf) {
+        if (pre) {                                        // the move's staged group list (header + groups), 8 bytes per entry
+            if (mm >= m1) return;
+            const uint2 *src = pg_list + (mm - m0) * (int64_t)pg_pitch;
+            uint2 *dst = reinterpret_cast<uint2 *>(s_row + (size_t)buf * HEADK * ROWW * NT);
+            for (int j = tid; j < pg_pitch && j < PGCAP; j += NT) cp8(dst + j, src + j);
+            return;
+        }
         const int k = (int)((mm - m0) & 3);
         const int dm = s_pd[k];
         if (mm >= m1 || dm < 0 || tid >= NA) return;
@@ -446,12 +460,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             }
             if (lane == 0) {
                 s_ncand = nc;
-                s_u = args.uniforms ? args.uniforms[m] : philox_uniform(args.seed, args.stream[k_list], args.counter0[k_list] + (uint64_t)(m - m0));
+                s_u = args.uniforms ? args.uniforms[m] : philox_uniform(args.seed, args.stream[k_list], args.counter0[k_list] + (uint64_t)(m - mbase));
             }
         }
 
         // ---- A: group (and, for twice-occurring domains, remove) -------------------------------------------------
-        if (dd.ptr && tid < NA) {
+        if (!pre && dd.ptr && tid < NA) {
             const int64_t beg = cur.beg + (int64_t)crank * NA, end = cur.end;      // cluster: CTA q takes chunks q, q + C, q + 2C, ... of NA entries
             int jchunk = 0;
             for (int64_t q = beg + tid; q < end; q += (int64_t)NA * C, jchunk++) {
@@ -487,7 +501,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         // (they are performed at L2, and every mutable word is read back with ld.cg).  No __threadfence(): a gpu-scope
         // fence would also invalidate L1 and send every descriptor load of the next phase back to L2.
         csync();
-        if (C > 1 && acc_shared) {
+        if (!pre && C > 1 && acc_shared) {
             // merge: every CTA adds its non-empty cells into the merged accumulator of all C CTAs (distributed shared memory)
             cg::cluster_group cl = cg::this_cluster();
             for (int cellv = tid; cellv < ctot; cellv += NT) {
@@ -506,7 +520,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         //      phase A), or read from the global bitmap; (2) block scan of their popcounts; (3) every non-empty cell finds its
         //      list position by itself (word offset + popcount of the lower bits) ----
         int64_t base = 0;
-        const int nwords = (ctot + 31) >> 5;
+        const int nwords = pre ? 0 : (ctot + 31) >> 5;
+        const uint2 *s_pg = reinterpret_cast<const uint2 *>(s_row + (size_t)rbuf * HEADK * ROWW * NT);      // (pre) this move's staged list
+        const uint2 *g_pg = pre ? pg_list + (m - m0) * (int64_t)pg_pitch : nullptr;
+        if (pre) base = (int64_t)s_pg[0].x;
         for (int w0 = 0; w0 < nwords; w0 += NT) {
             const int w = w0 + tid, nw_here = min(NT, nwords - w0);
             if (acc_shared) {
@@ -556,9 +573,16 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
         // ---- B2: decode every group once, one group per thread (for every candidate) ---------------------------------
         const GroupRec *tmpl = reinterpret_cast<const GroupRec *>(irm.ctmpl[d]);
         for (int64_t g = tid; g < ngroups; g += NT) {
-            const int32_t cell = g < RCAP ? s_bits[g] : recs[g].cell;
+            int32_t cell; cell_t own;
+            if (pre) {
+                const uint2 ent = g + 1 < PGCAP ? s_pg[g + 1] : __ldcg(g_pg + g + 1);
+                cell = (int32_t)ent.x; own = pack_cell(ent.y & 0xFFFFu, ent.y >> 16);
+            } else {
+                cell = g < RCAP ? s_bits[g] : recs[g].cell;
+                own = acc[cell];
+            }
             GroupRec rc = tmpl ? tmpl[cell] : decode_cell(irm, d, cell);
-            rc.own = acc[cell];
+            rc.own = own;
             if (g < RCAP) s_recs[g] = rc; else recs[g] = rc;
         }
         __syncthreads();
@@ -715,6 +739,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
                 table_add(irm, gr.R, group_cell_at(gr, c), (cell_t)0 - gr.own);
                 table_add(irm, gr.R, group_cell_at(gr, tnew), gr.own);
             }
+            if (pre) continue;                        // (no accumulator in use)
             if (acc_shared) s_accm[gr.cell] = 0u;     // every CTA clears its own (merged) accumulator
             else if (mine) { __stcg(&irm.gacc[gr.cell], (cell_t)0); __stcg(&irm.gbm[gr.cell >> 5], 0u); }
         }
@@ -751,11 +776,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             const int k1 = (ring + 1) & 3;             // the same entity again: its prefetched slot is stale
             if (tnew != c && s_pd[k1] == d && s_pi[k1] == item) s_pc[k1] = tnew;
         }
-        if (C > 1 && !acc_shared) cg::this_cluster().sync();   // global accumulator: cleared before any CTA's next phase A adds to it
+        if (C > 1 && !acc_shared && !pre) cg::this_cluster().sync();   // global accumulator: cleared before any CTA's next phase A adds to it
         else __syncthreads();
         GEN_PHASE(5);
     }
-    if (prof && crank == 0) for (int i = 0; i < 6; i++) args.phase_cycles[k_blk * 32 + i] = ph_acc[i];
+    if (prof && crank == 0) for (int i = 0; i < 6; i++) args.phase_cycles[k_blk * 32 + i] += ph_acc[i];   // (summed over the rounds of a sweep)
     if (C > 1) cg::this_cluster().sync();                      // no CTA exits while another may still address its shared memory
 #undef GEN_PHASE
 }

@@ -36,7 +36,7 @@ EXPORTS = [
     "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
     "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters", "hirm_engine_clear_relation_cache",
     "hirm_engine_seat_prior", "hirm_irm_set_table_mode", "hirm_unary_block_create", "hirm_unary_block_destroy",
-    "hirm_irm_set_observations_unary", "hirm_engine_last_cluster_size", "hirm_relation_reseat",
+    "hirm_irm_set_observations_unary", "hirm_engine_last_cluster_size", "hirm_engine_last_rounds", "hirm_relation_reseat",
     "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
     "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
     "hirm_gpu_dataset_last_error", "hirm_gpu_dataset_load", "hirm_gpu_dataset_free", "hirm_gpu_dataset_counts", "hirm_gpu_dataset_domain",
@@ -113,6 +113,7 @@ def load():
     L.hirm_unary_block_destroy.argtypes = [V, ctypes.c_int32]
     L.hirm_irm_set_observations_unary.argtypes = [V, ctypes.c_int32, I, ctypes.c_int32, I]
     L.hirm_engine_last_cluster_size.argtypes = [V, c_i32p]
+    L.hirm_engine_last_rounds.argtypes = [V, c_i32p, c_i32p]
     L.hirm_relation_reseat.argtypes = [I, I, c_i32p, c_i32p, c_i32p, c_f64p, ctypes.c_int64, I, c_i32p, c_f64p, I, ctypes.c_double,
                                        c_i32p, c_i32p, c_i32p]
     L.hirm_irm_set_rng_counters.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
@@ -410,7 +411,9 @@ class Engine:
         self._ck(self.L.hirm_engine_last_sweep_info(self._h, ctypes.byref(n), ctypes.byref(k), ctypes.byref(ms)))
         c = ctypes.c_int32()
         self._ck(self.L.hirm_engine_last_cluster_size(self._h, ctypes.byref(c)))
-        return dict(launches=n.value, kernel_kind=k.value, kernel_ms=ms.value, cluster_size=c.value)
+        r, g = ctypes.c_int32(), ctypes.c_int32()
+        self._ck(self.L.hirm_engine_last_rounds(self._h, ctypes.byref(r), ctypes.byref(g)))
+        return dict(launches=n.value, kernel_kind=k.value, kernel_ms=ms.value, cluster_size=c.value, rounds=r.value, pregrouped=bool(g.value))
 
     def sweep_all(self, irms, n_sweeps=1, seed=0, flags=0, want_moves=False):
         """transition_cluster_assignments_all for every listed IRM, order generated on the device.

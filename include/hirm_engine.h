@@ -223,6 +223,15 @@ int hirm_engine_last_sweep_info(hirm_engine *e, int32_t *n_launches, int32_t *ke
 /* CTAs per IRM (thread-block cluster size) of the last generic launch */
 int hirm_engine_last_cluster_size(hirm_engine *e, int32_t *ctas_per_irm);
 
+/* Rounds of the last sweep call and whether rows were grouped ahead of the moves.  Where every CSR relation of an IRM holds
+ * a domain once, the groups of that domain's entities (get_cluster_to_items_list, cxx/hirm.hh:388-397) do not depend on the
+ * domain's own partition, so for a run of moves of the domain the engine groups the rows of ALL its moves first -- a
+ * bandwidth-bound kernel with the other domains' table slots in shared memory -- and the sequential pass reads the group
+ * lists.  The move lists are then swept in rounds (piece r of every list: a pre-grouping launch + the sequential launch).
+ * Chosen by the engine (many IRMs with long rows); HIRM_PREGROUP=0/1 in the environment forces it off / on wherever
+ * possible, HIRM_PREGROUP_SEG caps the moves per piece.  Results are bit-identical either way. */
+int hirm_engine_last_rounds(hirm_engine *e, int32_t *rounds, int32_t *pregrouped);
+
 /* shared-memory plan of the last dense launch: resident CTAs (chains) per SM, TMA ring stages, bytes per
  * row chunk, dynamic shared memory per CTA */
 int hirm_engine_last_dense_plan(hirm_engine *e, int32_t *ctas_per_sm, int32_t *stages, int32_t *chunk_bytes, int32_t *smem_bytes);
