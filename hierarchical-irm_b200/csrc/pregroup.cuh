@@ -104,8 +104,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pregroup_rows_kernel(SweepArgs 
         }
         return t;
     };
-    auto accumulate = [&](const Entry &t) {
-        if (!t.ok) return;
+    auto cell_of = [&](const Entry &t) -> int {           // accumulator cell of the entry | value << 30 (-1: an endpoint is not in its domain)
         const uint32_t val = (t.meta >> META_VAL_SHIFT) & 1u, selfmask = (t.meta >> META_SELF_SHIFT) & 0xFu;
         const ADesc *D = ad + (t.meta & META_REL_MASK);
         int32_t rest_k = 0;
@@ -120,26 +119,34 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pregroup_rows_kernel(SweepArgs 
             if (slot == 0xFF) { absent = true; slot = 0; }
             rest_k += slot * D->rstride[p];
         }
-        if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); return; }
-        atomicAdd(&s_acc[D->base[0] + rest_k], 1u | (val << 16));
+        if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); return -1; }
+        return (D->base[0] + rest_k) | (int)(val << 30);
+    };
+    // one shared-memory atomic per distinct cell of the warp's 32 entries (a CRP partition has a dominant table: most entries of a
+    // row fall into a handful of cells, and same-address shared atomics serialise)
+    auto add_cells = [&](int key) {
+        const int cell = key < 0 ? -1 : (key & 0x3FFFFFFF);
+        const unsigned peers = __match_any_sync(0xffffffffu, cell);
+        const unsigned ones = __ballot_sync(0xffffffffu, key >= 0 && ((key >> 30) & 1));
+        if (cell >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_acc[cell], (uint32_t)__popc(peers) + ((uint32_t)__popc(peers & ones) << 16));
     };
     auto bounds = [&](int it, int64_t &b, int64_t &e) {
         if (it >= 0 && it < dd.n && dd.ptr) { b = __ldg(dd.ptr + it); e = __ldg(dd.ptr + it + 1); } else { b = 0; e = 0; }
     };
-    // software pipeline over the rows: entries of row m + 1, bounds of row m + 2 and the id of row m + 3 are in flight while row m
-    // is accumulated and compacted
-    int64_t b0, e0, b1, e1;
-    bounds(__ldg(args.move_item + lo), b0, e0);
-    bounds(lo + 1 < hi ? __ldg(args.move_item + lo + 1) : -1, b1, e1);
-    int it2 = lo + 2 < hi ? __ldg(args.move_item + lo + 2) : -1;
-    Entry cur = load_entry(b0 + tid, e0);
-    for (int64_t m = lo; m < hi; m++) {
-        const Entry nxt = load_entry(b1 + tid, e1);
-        int64_t b2, e2;
-        bounds(it2, b2, e2);
-        const int it3 = m + 3 < hi ? __ldg(args.move_item + m + 3) : -1;
-        accumulate(cur);
-        for (int64_t q = b0 + tid + NT; q < e0; q += NT) accumulate(load_entry(q, e0));
+    auto item_of = [&](int64_t m) -> int { return m < hi ? __ldg(args.move_item + m) : -1; };
+    // One row: X = this row's registers (entry of this thread, bounds, and the id of the row two ahead), Y = the next row's.
+    // The next row's entries, the bounds of the row after it and an id four rows ahead are put in flight before this row is
+    // accumulated and compacted; the two register sets swap roles from row to row (the loop below is unrolled by two), so no
+    // value is touched before the row that needs it.
+    auto row = [&](int64_t m, Entry &X, int64_t &bX, int64_t &eX, int &itX, Entry &Y, const int64_t &bY, const int64_t &eY) {
+        Y = load_entry(bY + tid, eY);
+        add_cells(X.ok ? cell_of(X) : -1);
+        for (int64_t q0 = bX + NT; q0 < eX; q0 += NT) {    // (uniform trip count: the ballots inside need every lane)
+            const Entry t = load_entry(q0 + tid, eX);
+            add_cells(t.ok ? cell_of(t) : -1);
+        }
+        bounds(itX, bX, eX);                               // row m + 2
+        itX = item_of(m + 4);
         __syncthreads();
         const int c0 = tid * CPT;
         int cnt = 0;
@@ -177,7 +184,15 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pregroup_rows_kernel(SweepArgs 
             if (total > pitch - 1) raise_error(irm, KERR_GROUP_OVERFLOW);
         }
         __syncthreads();
-        cur = nxt; b0 = b1; e0 = e1; b1 = b2; e1 = e2; it2 = it3;
+    };
+    int64_t bA, eA, bB, eB;
+    bounds(item_of(lo), bA, eA);
+    bounds(item_of(lo + 1), bB, eB);
+    int itA = item_of(lo + 2), itB = item_of(lo + 3);
+    Entry A = load_entry(bA + tid, eA), B{0u, 0, 0, 0, false};
+    for (int64_t m = lo; m < hi; m += 2) {
+        row(m, A, bA, eA, itA, B, bB, eB);
+        if (m + 1 < hi) row(m + 1, B, bB, eB, itB, A, bA, eA);
     }
 }
 
