@@ -1476,6 +1476,7 @@ struct Plan {
     std::vector<std::pair<int, int>> gen_classes;     // (CTAs per IRM, number of IRMs): generic_blk is ordered by class
     int gen_ctot = 0; int64_t gen_groups = 0;         // ... largest accumulator space of a domain, most groups one move can have
     int pg_ctot = 0;                                  // ... largest accumulator space of a domain whose rows can be grouped ahead
+    int nopg_ctot = 0;                                // ... of a domain whose rows cannot
 };
 
 // Shared-memory plan of one dense tier: as many chains per SM as the launch has (up to 5: the register budget) and fit; the rest of
@@ -1568,6 +1569,7 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
                 if (D.ub_block >= 0 && e->ublocks[(size_t)D.ub_block]) plan.gen_ubw = std::max(plan.gen_ubw, e->ublocks[(size_t)D.ub_block]->words);
                 plan.gen_groups = std::max(plan.gen_groups, std::min<int64_t>(D.max_deg, ct));
                 if (d < (int)irm->pregroup.size() && irm->pregroup[(size_t)d]) plan.pg_ctot = std::max(plan.pg_ctot, ct);
+                else plan.nopg_ctot = std::max(plan.nopg_ctot, ct);
             }
             double w = 0.0, ents = 0.0;
             for (int d = 0; d < irm->n_domains; d++) {
@@ -1708,7 +1710,9 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args,
             // Shared-memory plan: the move's accumulator (4 bytes per cell of the largest per-domain cell space) and its group
             // records (76 bytes per group, at most min(longest row, cells) groups) stay on chip when they fit the CTA's share
             // of the SM; the fewer IRMs per SM, the bigger that share.  What does not fit goes to the IRM's global scratch.
-            const int scap_want = std::max(256, (plan.gen_ctot + 31) & ~31);
+            // (a pre-grouped round needs no accumulator for the domains whose rows are grouped ahead; a short run of such a domain that
+            // goes through the ordinary path anyway falls back to the IRM's global accumulator)
+            const int scap_want = std::max(256, ((args.pg_pre ? plan.nopg_ctot : plan.gen_ctot) + 31) & ~31);
             const int rcap_want = std::max(128, (int)((std::min<int64_t>(plan.gen_groups, 1 << 20) + 31) & ~31));
             int want_ctas = std::max(1, std::min(std::min(2048 / gen_threads, 65536 / (e->gen_regs * gen_threads)), (n_gen + e->num_sms - 1) / e->num_sms));
             const size_t fixed = generic_smem_bytes(0, GL.pcap, 0, gen_threads, GL.kstride, GL.ndom, GL.roww, 1, GL.ubw, GL.adcap, GL.headk) + (size_t)e->gen_static_smem;

@@ -60,3 +60,6 @@ for chains in [int(c) for c in os.environ.get("CHAINS", "148,592,1184").split(",
               % (chains, thr or "auto", info["kernel_ms"], rate / 1e6, rate * (nobs / n) * 9 / 1e9, info["kernel_ms"] * 1e3 / per, tabs), flush=True)
         for i, nm in enumerate(names):
             print("    %-46s %9.0f cycles/move  %5.1f%%" % (nm, ph[:, i].mean(), 100 * ph[:, i].mean() / tot))
+        sub = buf.cpu().numpy().reshape(chains, 32)[:, 8:24].astype(np.float64) / per      # SUBT sub-timers (temporary instrumentation)
+        if sub.any():
+            print("    sub-timers [8..23]: " + " ".join("%d:%.0f" % (8 + j, sub[:, j].mean()) for j in range(16) if sub[:, j].any()))
