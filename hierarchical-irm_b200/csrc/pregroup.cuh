@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pregroup_rows_kernel(SweepArgs 
     uint8_t *s_z = pg_dyn + (size_t)PL.scap * 4;                           // [zcap] slot bytes of the other domains
     __shared__ ADesc s_ad[PG_ADCAP];
     __shared__ int32_t s_zoff[MAX_DOMAINS];
-    __shared__ int32_t s_wtot[32];
+    __shared__ int32_t s_wtot[64];
     for (int k = tid; k < PL.scap; k += NT) s_acc[k] = 0u;
     if (tid == 0) {
         int used = 0;
@@ -148,18 +148,33 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pregroup_rows_kernel(SweepArgs 
         bounds(itX, bX, eX);                               // row m + 2
         itX = item_of(m + 4);
         __syncthreads();
+        // compaction: thread t owns the CPT consecutive cells from t * CPT (list order = thread order); it reads them once (one
+        // 16-byte load where CPT is 4), clears what it read, and after the block scan of the counts writes its groups from registers.
+        // Two barriers per row: the cells are clear again before the second one, and the next row's first barrier keeps the scan
+        // scratch apart.
         const int c0 = tid * CPT;
+        uint32_t v4[4] = {0u, 0u, 0u, 0u};
         int cnt = 0;
-        for (int j = 0; j < CPT; j++) cnt += (c0 + j < ctot && s_acc[c0 + j] != 0u) ? 1 : 0;
+        if (CPT == 4) {
+            if (c0 < ctot) {                               // (ctot is a multiple of 4 here: host pads the accumulator to 32 cells)
+                const uint4 q = *reinterpret_cast<const uint4 *>(s_acc + c0);
+                v4[0] = q.x; v4[1] = q.y; v4[2] = q.z; v4[3] = q.w;
+                cnt = (q.x != 0u) + (q.y != 0u) + (q.z != 0u) + (q.w != 0u);
+                if (cnt) *reinterpret_cast<uint4 *>(s_acc + c0) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        } else {
+            for (int j = 0; j < CPT; j++) cnt += (c0 + j < ctot && s_acc[c0 + j] != 0u) ? 1 : 0;
+        }
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        if (lane == 31) s_wtot[warp] = incl;
+        const int par = (int)(m & 1);                      // (two scan scratches, alternating: no barrier after the reads)
+        if (lane == 31) s_wtot[par * 32 + warp] = incl;
         __syncthreads();
-        const int wv = lane < NW ? s_wtot[lane] : 0;
+        const int wv = lane < NW ? s_wtot[par * 32 + lane] : 0;
         int wincl = wv;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -169,21 +184,29 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pregroup_rows_kernel(SweepArgs 
         const int total = __shfl_sync(0xffffffffu, wincl, 31);
         int pos = __shfl_sync(0xffffffffu, wincl - wv, warp) + incl - cnt;
         uint2 *slot = out + (m - lo) * (int64_t)pitch;
-        for (int j = 0; j < CPT; j++) {
-            const int cell = c0 + j;
-            if (cell >= ctot) break;
-            const uint32_t v = s_acc[cell];
-            if (v) {
-                if (pos + 1 < pitch) __stcg(slot + 1 + pos, make_uint2((uint32_t)cell, v));
-                pos++;
-                s_acc[cell] = 0u;
+        if (CPT == 4) {
+            if (cnt) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (v4[j]) { if (pos + 1 < pitch) __stcg(slot + 1 + pos, make_uint2((uint32_t)(c0 + j), v4[j])); pos++; }
+            }
+        } else {
+            for (int j = 0; j < CPT; j++) {
+                const int cell = c0 + j;
+                if (cell >= ctot) break;
+                const uint32_t v = s_acc[cell];
+                if (v) {
+                    if (pos + 1 < pitch) __stcg(slot + 1 + pos, make_uint2((uint32_t)cell, v));
+                    pos++;
+                    s_acc[cell] = 0u;
+                }
             }
         }
         if (tid == 0) {
             __stcg(slot, make_uint2((uint32_t)min(total, pitch - 1), 0u));
             if (total > pitch - 1) raise_error(irm, KERR_GROUP_OVERFLOW);
         }
-        __syncthreads();
+        if (CPT != 4) __syncthreads();                     // (general path: cells are cleared after the scan)
     };
     int64_t bA, eA, bB, eB;
     bounds(item_of(lo), bA, eA);

@@ -95,12 +95,13 @@ def _same(a, b):
         assert x[-1] == y[-1]
 
 
-@pytest.mark.parametrize("with_unary,hashed", [(True, False), (False, True)])
-def test_pregrouped_rounds_give_identical_trajectories(eng, with_unary, hashed):
+@pytest.mark.parametrize("with_unary,hashed,max_tables", [(True, False, 16), (False, True, 16), (False, False, 60)])
+def test_pregrouped_rounds_give_identical_trajectories(eng, with_unary, hashed, max_tables):
+    """(60 table slots: an accumulator space of ~3800 cells, four per thread of the pre-grouping kernel -- its vector path)"""
     rng = np.random.default_rng(23)
     extra = {"HIRM_HASHED_TABLES": 1} if hashed else {}
     with _env(**extra):
-        hs, (na, nb, nc), n_rel, keep = _irms(eng, 4, rng, with_unary=with_unary)
+        hs, (na, nb, nc), n_rel, keep = _irms(eng, 4, rng, with_unary=with_unary, max_tables=max_tables)
     z0 = [[rng.integers(0, 5, na).astype(np.int32), rng.integers(0, 4, nb).astype(np.int32), rng.integers(0, 3, nc).astype(np.int32)] for _ in hs]
     # per IRM its own list: domain blocks (two sweeps), one IRM with a short run and an interleaved stretch in the middle
     lists = []
