@@ -1661,7 +1661,7 @@ static int launch_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args,
         // shared memory
         PregroupLaunch PL;
         PL.scap = std::max(256, (plan.pg_ctot + 31) & ~31);
-        PL.zcap = (e->max_smem_optin - 2048 - PL.scap * 4) & ~15;
+        PL.zcap = (e->max_smem_optin - 3072 - PL.scap * 4) & ~15;
         if (PL.zcap < 0) return fail("pre-grouping: the accumulator does not fit the shared memory");
         const int smem = PL.scap * 4 + PL.zcap;
         if (smem > e->pg_smem_set) { CK(cudaFuncSetAttribute(pregroup_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); e->pg_smem_set = smem; }

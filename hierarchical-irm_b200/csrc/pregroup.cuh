@@ -16,7 +16,7 @@ namespace hirm {
 
 constexpr int PG_THREADS = 1024;
 constexpr int PG_ADCAP = 16;       // relation descriptors kept in shared memory
-struct PregroupLaunch { int32_t scap, zcap; };   // accumulator cells; bytes of slot arrays one CTA can stage
+struct PregroupLaunch { int32_t scap, zcap; };   // accumulator cells; bytes of slot arrays one CTA can stage   // accumulator cells; bytes of slot arrays one CTA can stage
 
 // Runs of equal domain in every listed IRM's move list: out_n[w] runs (may exceed runcap: too many to record), their first
 // moves and domains.  One warp per IRM.
@@ -57,6 +57,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pregroup_rows_kernel(SweepArgs 
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(pg_dyn);                // [scap] observations | ones << 16
     uint8_t *s_z = pg_dyn + (size_t)PL.scap * 4;                           // [zcap] slot bytes of the other domains
     __shared__ ADesc s_ad[PG_ADCAP];
+    // per relation (by ordinal): what an entry's other-id columns are gathered from -- offset of the domain's slot bytes in shared
+    // memory (-1: not staged, read from the L2), accumulator stride -- so that an entry costs a handful of instructions per column
+    struct GatherPlan { int32_t zoff[3], rstride[3], dom[3], n, base, pad; };
+    __shared__ GatherPlan s_plan[PG_ADCAP];
     __shared__ int32_t s_zoff[MAX_DOMAINS];
     __shared__ int32_t s_wtot[64];
     for (int k = tid; k < PL.scap; k += NT) s_acc[k] = 0u;
@@ -90,6 +94,19 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pregroup_rows_kernel(SweepArgs 
     }
     __syncthreads();
     const ADesc *ad = ad_shared ? s_ad : dd.adesc;
+    if (ad_shared && tid < dd.n_adesc) {
+        const ADesc &A = s_ad[tid];
+        GatherPlan P;
+        P.n = 0; P.base = A.base[0]; P.pad = 0;
+        for (int j = 0; j < 3; j++) { P.zoff[j] = -1; P.rstride[j] = 0; P.dom[j] = 0; }
+        for (int p = 0; p < A.arity; p++) {
+            if (p == A.a) continue;                        // (the domain occurs once: every other position has an id column, in order)
+            if (P.n < 3) { P.zoff[P.n] = s_zoff[A.dom[p]]; P.rstride[P.n] = A.rstride[p]; P.dom[P.n] = A.dom[p]; }
+            P.n++;
+        }
+        s_plan[tid] = P;
+    }
+    __syncthreads();
     const int n_other = dd.n_other;
     const int CPT = (ctot + NT - 1) / NT;                  // accumulator cells per thread of the compaction (consecutive: list order = thread order)
 
@@ -105,6 +122,20 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pregroup_rows_kernel(SweepArgs 
         return t;
     };
     auto cell_of = [&](const Entry &t) -> int {           // accumulator cell of the entry | value << 30 (-1: an endpoint is not in its domain)
+        if (ad_shared) {
+            const GatherPlan &P = s_plan[t.meta & META_REL_MASK];
+            int32_t cell = P.base; bool absent = false;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                if (j >= P.n) break;
+                const int id = j == 0 ? t.id0 : j == 1 ? t.id1 : t.id2, zo = P.zoff[j];
+                int slot = zo >= 0 ? (int)s_z[zo + id] : (int)__ldcg(irm.dom[P.dom[j]].zb + id);
+                if (slot == 0xFF) { absent = true; slot = 0; }
+                cell += slot * P.rstride[j];
+            }
+            if (absent) { raise_error(irm, KERR_ABSENT_ENTITY); return -1; }
+            return cell | (int)(((t.meta >> META_VAL_SHIFT) & 1u) << 30);
+        }
         const uint32_t val = (t.meta >> META_VAL_SHIFT) & 1u, selfmask = (t.meta >> META_SELF_SHIFT) & 0xFu;
         const ADesc *D = ad + (t.meta & META_REL_MASK);
         int32_t rest_k = 0;
@@ -123,7 +154,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) pregroup_rows_kernel(SweepArgs 
         return (D->base[0] + rest_k) | (int)(val << 30);
     };
     // one shared-memory atomic per distinct cell of the warp's 32 entries (a CRP partition has a dominant table: most entries of a
-    // row fall into a handful of cells, and same-address shared atomics serialise)
+    // row fall into a handful of cells, and same-address shared atomics serialise; on config 4's CRP-prior partitions it measures
+    // the same as plain atomics, it is the skewed partitions it is for)
     auto add_cells = [&](int key) {
         const int cell = key < 0 ? -1 : (key & 0x3FFFFFFF);
         const unsigned peers = __match_any_sync(0xffffffffu, cell);
