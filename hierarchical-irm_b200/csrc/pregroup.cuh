@@ -16,7 +16,7 @@ namespace hirm {
 
 constexpr int PG_THREADS = 1024;
 constexpr int PG_ADCAP = 16;       // relation descriptors kept in shared memory
-struct PregroupLaunch { int32_t scap, zcap; };   // accumulator cells; bytes of slot arrays one CTA can stage   // accumulator cells; bytes of slot arrays one CTA can stage
+struct PregroupLaunch { int32_t scap, zcap; };   // accumulator cells; bytes of slot arrays one CTA can stage
 
 // Runs of equal domain in every listed IRM's move list: out_n[w] runs (may exceed runcap: too many to record), their first
 // moves and domains.  One warp per IRM.
