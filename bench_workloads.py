@@ -138,8 +138,10 @@ def bench_c4(eng, dev, peak_gbs, chains=0, moves_per_domain=0, steps=2, warmup=1
            "step": "%d moves in each of the 3 domains of every chain (explicit move lists in HBM, uniform random entities)" % m,
            "init": "CRP(1) prior seats drawn on the device (hirm_engine_seat_prior); no burn-in", "tables_alive_chain0": tabs,
            "max_tables": max_tables, "kernel_kind": info["kernel_kind"], "gpu_launches": int(info["launches"] * steps),
+           "rounds_per_step": int(info.get("rounds", 1)), "rows_grouped_ahead": bool(info.get("pregrouped", False)),
            "gen_s": gen_s, "ingest_s": ingest_s, "state_build_s": build_s,
-           "roofline": {"bound": "hbm", "kernel": "generic_sweep_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+           "roofline": {"bound": "hbm", "kernel": "pregroup_rows_kernel + generic_sweep_kernel" if info.get("pregrouped") else "generic_sweep_kernel",
+                        "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                         "frac": achieved / peak_gbs, "traffic": None,
                         "algorithmic_bytes_per_move": bytes_per_move, "algorithmic_bytes_per_launch": moves * bytes_per_move,
                         "launch_ms": ms}}
