@@ -479,6 +479,21 @@ __global__ void gather_hi_kernel(const IrmDev *irms, const int32_t *ids, int n, 
     if (k < n) out[k] = *irms[ids[k]].dom[0].hi;
 }
 
+// cost estimate of a generic-kernel chain: candidates x groups a move scores, from the live-table bounds of its domains
+// (sum over the domains of (tables + 1) x product of the other domains' tables, capped)
+__global__ void gather_generic_cost_kernel(const IrmDev *irms, const int32_t *ids, int n, int32_t *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const IrmDev &irm = irms[ids[k]];
+    double cost = 0.0;
+    for (int d = 0; d < irm.n_domains; d++) {
+        double others = 1.0;
+        for (int q = 0; q < irm.n_domains; q++) if (q != d) others *= (double)max(*irm.dom[q].hi, 1);
+        cost += (double)(*irm.dom[d].hi + 1) * others * (double)max(irm.dom[d].n, 1);
+    }
+    out[k] = (int32_t)fmin(cost / 1024.0, 2.0e9);
+}
+
 // first kernel error word of every listed IRM in one launch (and reset): one copy back instead of one per IRM
 __global__ void gather_errors_kernel(const IrmDev *irms, const int32_t *ids, int n, int32_t *out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -136,6 +136,7 @@ struct hirm_engine {
     // pre-grouped rows: runs of the move lists, the rounds' pieces, the staged group lists
     DevBuf<int32_t> s_runs_n, s_runs_dom, s_pg_pre, s_pg_pitch; DevBuf<int64_t> s_runs_start, s_seg_lo, s_seg_hi, s_pg_base, s_off_host;
     DevBuf<uint2> s_pg_data;
+    DevBuf<int32_t> s_cost;
     int last_rounds = 1, last_pregrouped = 0, pg_smem_set = 0;
     DevBuf<double> s_alpha;
     DevBuf<cell_t> s_reltab; DevBuf<RelCand> s_relcand; DevBuf<int32_t> s_relerr;
@@ -1581,6 +1582,27 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
         }
     }
     assign_cluster_classes(e, plan, flags);
+    // More single-CTA generic chains than the GPU holds at once: the launch (every round of it) ends with its slowest chain, and a
+    // chain's cost per move grows with the product of its domains' live tables -- chains drawn from a CRP prior differ by 2x.
+    // Heaviest first, the block scheduler fills in the light ones (longest-processing-time-first).  Results do not depend on the order.
+    if ((int)plan.generic_blk.size() > 4 * e->num_sms && plan.gen_classes.size() == 1 && plan.gen_classes[0].first == 1) {
+        const int ng = (int)plan.generic_blk.size();
+        std::vector<int32_t> ids((size_t)ng), cost((size_t)ng);
+        for (int j = 0; j < ng; j++) ids[(size_t)j] = h_irms[plan.generic_blk[(size_t)j]];
+        for (int j = 0; j < ng; j++) if (upload_desc(e, ids[(size_t)j])) return -1;      // (descriptors on the device before the kernel reads them)
+        CK(e->s_cost.ensure((size_t)ng * 2));              // (own scratch: the callers' buffers are already bound to the launch)
+        CK(cudaMemcpyAsync(e->s_cost.p, ids.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        gather_generic_cost_kernel<<<(ng + 255) / 256, 256, 0, e->stream>>>(e->d_irms.p, e->s_cost.p, ng, e->s_cost.p + ng);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(cost.data(), e->s_cost.p + ng, ng * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        std::vector<int> order((size_t)ng);
+        for (int j = 0; j < ng; j++) order[(size_t)j] = j;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+        std::vector<int32_t> sorted((size_t)ng); std::vector<double> wt((size_t)ng);
+        for (int j = 0; j < ng; j++) { sorted[(size_t)j] = plan.generic_blk[(size_t)order[(size_t)j]]; wt[(size_t)j] = plan.gen_weight[(size_t)order[(size_t)j]]; }
+        plan.generic_blk.swap(sorted); plan.gen_weight.swap(wt);
+    }
     // More dense chains than fit on the GPU at once: the launch ends with its slowest chain, so the chains with the
     // most live tables (the cost of a move grows with them) go first and the block scheduler fills in the cheap ones
     // (longest-processing-time-first).
