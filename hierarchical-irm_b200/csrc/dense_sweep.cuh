@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(32 + DN_NA + 32 * DW, MINB) dense_ree_sweep_ke
     __shared__ int32_t s_K, s_KA;
     __shared__ MoveCtl s_ctl[DN_CTL];
     __shared__ double s_val[2 * ND];                   // one round of cell scores, double-buffered
+    __shared__ double s_lpbuf[68];                     // the candidates' log-probabilities, from the lanes that added them up to every D warp
     __shared__ int32_t s_has_absent;
     __shared__ long long s_limit, s_issued, s_consumed, s_done;
     __shared__ long long s_ph[14];                        // profiling only   // first move NOT to be made (tier overflow); ring chunks issued / consumed
@@ -705,15 +706,17 @@ __global__ void __launch_bounds__(32 + DN_NA + 32 * DW, MINB) dense_ree_sweep_ke
             // ---- score.  logp_gibbs_exact (cxx/hirm.hh:441-461): for every candidate t the sum over its 2K+1 target
             //      cells of S(N+n, s+sg) - S(N, s), with (N, s) the cell WITHOUT i's own observations.  The
             //      (candidate, cell) pairs are laid flat over the D lanes, ND per round; a lane evaluates one
-            //      cell (branch-free, six independent log chains).  Then lane t of EVERY D warp adds up candidate
-            //      t's cells in index order (a segmented reduction with a fixed order: deterministic, and identical
-            //      in both warps), so that each warp can go on to draw the table by itself.
+            //      cell (branch-free, six independent log chains).  Candidate t's cells are added up in index order (a segmented
+            //      reduction with a fixed order: deterministic) by one lane, the sums handed to every D warp through shared memory,
+            //      so that each warp can go on to draw the table by itself.
             constexpr int MAXJ = 3;                            // candidates per lane: t = lane + 32 j (at most 64 tables + a fresh one)
             double lp[MAXJ];
 #pragma unroll
             for (int j = 0; j < MAXJ; j++) lp[j] = 0.0;
             {
                 const int IPC = 2 * K + 1, total = ncand * IPC;
+                const int t_own = lane * DW + (d >> 5);        // the candidate this lane adds up (d = index among the D threads)
+                double lp_own = 0.0;
                 const cell_t rem_cc = pack_cell((uint32_t)(g[4 * c] + g[4 * c + 2] + d_n), (uint32_t)(g[4 * c + 1] + g[4 * c + 3] + d_s));
                 #pragma unroll 1
                 for (int base = 0; base < total; base += ND) {
@@ -750,24 +753,31 @@ __global__ void __launch_bounds__(32 + DN_NA + 32 * DW, MINB) dense_ree_sweep_ke
                     __syncwarp();
                     s_val[vb * ND + d] = score_delta_bf<DN_LF>(s_lf, N, sv, gn, gs);
                     bar_d<ND>();
-#pragma unroll
-                    for (int j = 0; j < MAXJ; j++) {
-                        const int t = lane + 32 * j;
-                        if (t < ncand) {
-                            const int w0 = max(t * IPC, base) - base, w1 = min((t + 1) * IPC, base + ND) - base;
-                            #pragma unroll 1
-                            for (int ww = w0; ww < w1; ww++) lp[j] += s_val[vb * ND + ww];
+                    // candidate t's cells of this round, in index order: ONE lane per candidate (lane t / DW of D warp t mod DW: the
+                    // candidates' sums run side by side on all D warps instead of six times over), values loaded four at a time
+                    if (t_own < ncand) {
+                        const int w0 = max(t_own * IPC, base) - base, w1 = min((t_own + 1) * IPC, base + ND) - base;
+                        const double *v = s_val + vb * ND;
+                        int ww = w0;
+                        #pragma unroll 1
+                        for (; ww + 4 <= w1; ww += 4) {
+                            const double a0 = v[ww], a1 = v[ww + 1], a2 = v[ww + 2], a3 = v[ww + 3];
+                            lp_own += a0; lp_own += a1; lp_own += a2; lp_own += a3;
                         }
+                        #pragma unroll 1
+                        for (; ww < w1; ww++) lp_own += v[ww];
                     }
                     vb ^= 1;
                 }
+                if (t_own < ncand) {
+                    const int st = t_own < K ? s_order[t_own] : K;
+                    s_lpbuf[t_own] = lp_own + (st == c ? (singleton ? logalpha : s_logcntm1[c]) : (t_own < K ? s_logcnt[st] : logalpha));
+                }
+                bar_d<ND>();                                   // every D warp reads all candidates' sums
 #pragma unroll
                 for (int j = 0; j < MAXJ; j++) {
                     const int t = lane + 32 * j;
-                    if (t < ncand) {
-                        const int st = t < K ? s_order[t] : K;
-                        lp[j] += st == c ? (singleton ? logalpha : s_logcntm1[c]) : (t < K ? s_logcnt[st] : logalpha);
-                    }
+                    if (t < ncand) lp[j] = s_lpbuf[t];
                 }
             }
             DPHASE(2);

@@ -17,6 +17,7 @@ for c in range(1, chains):
 rng = np.random.default_rng(1)
 for h in hs:
     if os.environ.get('INIT', 'crp') == 'crp': z = bench.crp_prior_labels_fast(n, 1.0, rng)
+    elif os.environ.get('INIT', 'crp').startswith('blocks'): z = (np.arange(n) * int(os.environ['INIT'][6:]) // n).astype(np.int32)
     else: z = (np.arange(n) >= n//2).astype(np.int32)
     eng.set_assignments(h, 0, z)
 buf = torch.zeros(chains*32, dtype=torch.int64, device='cuda')

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/r02_pytest37.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02_pytest37.log
+tail -5 gpurun_out/r02_pytest37.log
+for K in 2 8 16; do
+  INIT=blocks$K CHAINS=1184 M=300 timeout 600 python profiles/phase_breakdown.py 2>&1 | grep -E "kernel_ms|D score|A total"
+done
+CHAINS=1184 THREADS=0 MOVES=1024 timeout 900 python profiles/phase_breakdown_c4.py 2>&1 | grep -E "chains|D score"

@@ -22,7 +22,7 @@ def exact(N, s, gn, gs):
 def test_score_delta_matches_mpmath():
     rng = np.random.default_rng(0)
     N, s, gn, gs = [], [], [], []
-    for scale, gscale in [(40, 10), (250, 20), (300, 300), (5000, 50), (10 ** 6, 2000), (10 ** 8, 1), (10 ** 8, 40000), (4 * 10 ** 8, 20000)]:
+    for scale, gscale in [(40, 10), (250, 20), (300, 300), (5000, 50), (20000, 300), (3 * 10 ** 5, 3000), (10 ** 6, 2000), (10 ** 8, 1), (10 ** 8, 40000), (4 * 10 ** 8, 20000)]:
         for _ in range(250):
             n_ = int(rng.integers(0, scale + 1)); s_ = int(rng.integers(0, n_ + 1))
             g_ = int(rng.integers(0, gscale + 1)); t_ = int(rng.integers(0, g_ + 1))
