@@ -365,7 +365,9 @@ __device__ __forceinline__ void a_move(const APar p, RingCursor &cur, const int 
 
 // DW = decision warps: 2 for the small-table tier (most chains per SM), more for the tiers whose chains have many
 // tables (the score is K^2 cells: more lanes, fewer rounds).
-template <int DW, int MINB>
+// BYC: lay-out of a scoring round (see phase D): false = (candidate, cell) pairs flat over the lanes, true = some cells of every
+// candidate per round (the instance of the last tier, whose chains have more than 32 tables).
+template <int DW, int MINB, bool BYC = false>
 __global__ void __launch_bounds__(32 + DN_NA + 32 * DW, MINB) dense_ree_sweep_kernel(SweepArgs args, const int32_t *blk_list, DenseLaunch L) {
     constexpr int ND = 32 * DW, NTHREADS = 32 + DN_NA + ND;
     const int k_list = blk_list ? blk_list[blockIdx.x] : blockIdx.x;
@@ -714,16 +716,25 @@ __global__ void __launch_bounds__(32 + DN_NA + 32 * DW, MINB) dense_ree_sweep_ke
 #pragma unroll
             for (int j = 0; j < MAXJ; j++) lp[j] = 0.0;
             {
+                // Lay-out of a round.  Tiers of up to 32 tables: the (candidate, cell) pairs flat over the lanes.
+                // Last tier (BYC): QR consecutive cells of EVERY candidate (lane d: candidate d / QR, cell r QR + d mod QR), so that the
+                // ordered sums of a round are QR additions per candidate, all candidates side by side -- with whole candidates per round
+                // three lanes add 65 values each at K = 32 while 189 wait -- and a lane's candidate is fixed for the move.
                 const int IPC = 2 * K + 1, total = ncand * IPC;
+                constexpr bool BYCAND = BYC;
+                const int QR = BYCAND ? ND / ncand : 1;        // >= 1: at most 65 candidates on 192 lanes
+                const int t_mine = BYCAND ? d / QR : 0, q_mine = d - t_mine * QR;
+                const int nround = BYCAND ? (IPC + QR - 1) / QR : (total + ND - 1) / ND;
                 const int t_own = lane * DW + (d >> 5);        // the candidate this lane adds up (d = index among the D threads)
                 double lp_own = 0.0;
                 const cell_t rem_cc = pack_cell((uint32_t)(g[4 * c] + g[4 * c + 2] + d_n), (uint32_t)(g[4 * c + 1] + g[4 * c + 3] + d_s));
                 #pragma unroll 1
-                for (int base = 0; base < total; base += ND) {
-                    const int w = base + d;
+                for (int r = 0; r < nround; r++) {
+                    int t, q; bool valid;
+                    if (BYCAND) { t = t_mine; q = r * QR + q_mine; valid = t < ncand && q < IPC; }
+                    else { const int w = r * ND + d; valid = w < total; t = w / IPC; q = w - t * IPC; }
                     uint32_t N = 0u, sv = 0u, gn = 0u, gs = 0u;
-                    if (w < total) {                           // gather the cell's operands (cheap; lanes may diverge)
-                        const int t = w / IPC, q = w - t * IPC;
+                    if (valid) {                               // gather the cell's operands (cheap; lanes may diverge)
                         const int st = t < K ? s_order[t] : K;
                         cell_t cur = 0;
                         if (q == 2 * K) {                      // the (t, t) cell of the fresh slot: the diagonal only
@@ -756,7 +767,9 @@ __global__ void __launch_bounds__(32 + DN_NA + 32 * DW, MINB) dense_ree_sweep_ke
                     // candidate t's cells of this round, in index order: ONE lane per candidate (lane t / DW of D warp t mod DW: the
                     // candidates' sums run side by side on all D warps instead of six times over), values loaded four at a time
                     if (t_own < ncand) {
-                        const int w0 = max(t_own * IPC, base) - base, w1 = min((t_own + 1) * IPC, base + ND) - base;
+                        int w0, w1;
+                        if (BYCAND) { w0 = t_own * QR; w1 = w0 + min(QR, IPC - r * QR); }
+                        else { const int base = r * ND; w0 = max(t_own * IPC, base) - base; w1 = min((t_own + 1) * IPC, base + ND) - base; }
                         const double *v = s_val + vb * ND;
                         int ww = w0;
                         #pragma unroll 1

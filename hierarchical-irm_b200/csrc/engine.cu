@@ -1504,8 +1504,13 @@ static int launch_dense_tier(hirm_engine *e, const DenseLaunch &L, unsigned nb, 
         CK(cudaFuncSetAttribute(dense_ree_sweep_kernel<DN_DW_SMALL, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes));
         dense_ree_sweep_kernel<DN_DW_SMALL, 5><<<nb, 32 + DN_NA + 32 * DN_DW_SMALL, (size_t)L.total_bytes, e->stream>>>(a, blk, L);
     } else {
-        CK(cudaFuncSetAttribute(dense_ree_sweep_kernel<DN_DW_LARGE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes));
-        dense_ree_sweep_kernel<DN_DW_LARGE, 3><<<nb, 32 + DN_NA + 32 * DN_DW_LARGE, (size_t)L.total_bytes, e->stream>>>(a, blk, L);
+        if (L.kt > 32) {                               // the last tier: chains with more than 32 tables (scoring rounds laid out by candidate)
+            CK(cudaFuncSetAttribute(dense_ree_sweep_kernel<DN_DW_LARGE, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes));
+            dense_ree_sweep_kernel<DN_DW_LARGE, 3, true><<<nb, 32 + DN_NA + 32 * DN_DW_LARGE, (size_t)L.total_bytes, e->stream>>>(a, blk, L);
+        } else {
+            CK(cudaFuncSetAttribute(dense_ree_sweep_kernel<DN_DW_LARGE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes));
+            dense_ree_sweep_kernel<DN_DW_LARGE, 3><<<nb, 32 + DN_NA + 32 * DN_DW_LARGE, (size_t)L.total_bytes, e->stream>>>(a, blk, L);
+        }
     }
     CK(cudaGetLastError());
     return 0;
