@@ -494,6 +494,16 @@ __global__ void gather_generic_cost_kernel(const IrmDev *irms, const int32_t *id
     out[k] = (int32_t)fmin(cost / 1024.0, 2.0e9);
 }
 
+// most live tables (highest used slot + 1) over the domains of every listed IRM: the cluster sizes of a sweep are dealt out by it
+__global__ void gather_max_tables_kernel(const IrmDev *irms, const int32_t *ids, int n, int32_t *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const IrmDev &irm = irms[ids[k]];
+    int hi = 1;
+    for (int d = 0; d < irm.n_domains; d++) hi = max(hi, *irm.dom[d].hi);
+    out[k] = hi;
+}
+
 // first kernel error word of every listed IRM in one launch (and reset): one copy back instead of one per IRM
 __global__ void gather_errors_kernel(const IrmDev *irms, const int32_t *ids, int n, int32_t *out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1474,6 +1474,7 @@ struct Plan {
     int gen_ubw = 0;                                  // ... widest unary-block bit row (words)
     int gen_adesc = 0;                                // ... most CSR relations touching one domain
     std::vector<double> gen_weight;                   // per generic IRM: entries (CSR + unary columns) an average move reads
+    std::vector<int> gen_tables;                      // ... most live tables of a domain (read back when cluster sizes are dealt out)
     std::vector<std::pair<int, int>> gen_classes;     // (CTAs per IRM, number of IRMs): generic_blk is ordered by class
     int gen_ctot = 0; int64_t gen_groups = 0;         // ... largest accumulator space of a domain, most groups one move can have
     int pg_ctot = 0;                                  // ... largest accumulator space of a domain whose rows can be grouped ahead
@@ -1586,6 +1587,19 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
             plan.generic_blk.push_back(k);
         }
     }
+    // live tables of the IRMs that may get a cluster: a move's scoring work grows with them as much as with the row length
+    if (!plan.generic_blk.empty() && (int)plan.generic_blk.size() <= e->num_sms) {
+        const int ng = (int)plan.generic_blk.size();
+        std::vector<int32_t> ids((size_t)ng), tabs((size_t)ng);
+        for (int j = 0; j < ng; j++) ids[(size_t)j] = h_irms[plan.generic_blk[(size_t)j]];
+        CK(e->s_cost.ensure((size_t)ng * 2));
+        CK(cudaMemcpyAsync(e->s_cost.p, ids.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        gather_max_tables_kernel<<<(ng + 255) / 256, 256, 0, e->stream>>>(e->d_irms.p, e->s_cost.p, ng, e->s_cost.p + ng);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(tabs.data(), e->s_cost.p + ng, ng * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        plan.gen_tables.assign(tabs.begin(), tabs.end());
+    }
     assign_cluster_classes(e, plan, flags);
     // More single-CTA generic chains than the GPU holds at once: the launch (every round of it) ends with its slowest chain, and a
     // chain's cost per move grows with the product of its domains' live tables -- chains drawn from a CRP prior differ by 2x.
@@ -1652,13 +1666,20 @@ static void assign_cluster_classes(hirm_engine *e, Plan &plan, uint32_t flags) {
         if ((forced || heavy) && n_gen <= e->num_sms) {
             // (a cluster lives inside one GPC, 16 to 20 SMs each; keeping the budget at 8 x 16 SMs made no measurable difference)
             const int budget = std::max(n_gen, std::min(e->num_sms, getenv("HIRM_CLUSTER_BUDGET") ? atoi(getenv("HIRM_CLUSTER_BUDGET")) : e->num_sms));
+            // Work of a move ~ the entries it reads x the live tables it scores them against (config 5's IRMs swept alone, 16 CTAs each:
+            // 25 us per move with 6000 entries and 9 tables, 42 us with 3400 entries and 47 tables -- profiles/r02_c5_irm_costs.txt).  The launch
+            // ends with its slowest IRM: the IRM with the most work per CTA doubles its cluster while SMs are left.
+            auto work = [&](int i) {
+                const double tabs = i < (int)plan.gen_tables.size() ? (double)plan.gen_tables[(size_t)i] : 8.0;
+                return plan.gen_weight[(size_t)i] * std::max(1.0, tabs / 8.0);
+            };
             int total = n_gen;
             for (;;) {
                 int best = -1;
                 for (int i = 0; i < n_gen; i++) {
                     if (cs[(size_t)i] >= 16 || total + cs[(size_t)i] > budget) continue;
-                    if (!forced && plan.gen_weight[(size_t)i] / cs[(size_t)i] < 192.0) continue;      // too little work per CTA to be worth a barrier
-                    if (best < 0 || plan.gen_weight[(size_t)i] / cs[(size_t)i] > plan.gen_weight[(size_t)best] / cs[(size_t)best]) best = i;
+                    if (!forced && work(i) / cs[(size_t)i] < 192.0) continue;    // too little work per CTA to be worth a barrier
+                    if (best < 0 || work(i) / cs[(size_t)i] > work(best) / cs[(size_t)best]) best = i;
                 }
                 if (best < 0) break;
                 total += cs[(size_t)best]; cs[(size_t)best] *= 2;

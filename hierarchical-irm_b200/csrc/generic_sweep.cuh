@@ -630,34 +630,45 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) generic_sweep_kernel(SweepArgs
             return p;
         };
         const int nch = (int)((ngroups + 31) >> 5), nchu = nch + nuch;
-        auto issue_unit = [&](int unit) -> Pending {                         // unit = candidate * nchu + chunk
-            const int t = unit / nchu, ch = unit - t * nchu;
-            return ch < nch ? issue((int64_t)ch * 32 + lane, s_cslot[t]) : issue_unary(ch - nch, s_cslot[t]);
+        auto issue_unit = [&](int t0, int unit) -> Pending {                 // unit = (candidate - t0) * nchu + chunk
+            const int tb = unit / nchu, ch = unit - tb * nchu;
+            return ch < nch ? issue((int64_t)ch * 32 + lane, s_cslot[t0 + tb]) : issue_unary(ch - nch, s_cslot[t0 + tb]);
         };
-        const bool flat = (int64_t)ncand * nchu <= PCAP;
+        // The units of ALL candidates at once where their partial sums fit the buffer; otherwise in batches of whole candidates that
+        // alternate between the two halves of the buffer (a half is rewritten two batches later, behind the barrier of the batch in
+        // between: one cluster barrier per batch).  An IRM early in a chain can have 40+ tables: 48 candidates x 90 units, which the
+        // one-warp-per-candidate fallback below would leave to 48 of a cluster's 512 warps.
+        const int HP = PCAP >> 1;
+        const bool flat = nchu <= HP;
         if (flat) {
-            const int nunits = ncand * nchu;
-            const int u0 = crank + warp * C, ustep = NW * C;       // unit u belongs to CTA u mod C, warp (u / C) mod NW
-            Pending pend{0ull, 0ull, 0ull};
-            if (u0 < nunits) pend = issue_unit(u0);
-            for (int unit = u0; unit < nunits; unit += ustep) {
-                const Pending cur = pend;
-                const int unext = unit + ustep;
-                if (unext < nunits) pend = issue_unit(unext);
-                uint32_t N, sv, gn, gs;
-                finish(cur, N, sv, gn, gs);
-                __syncwarp();
-                double v = score_delta_any(s_lf, logtab, N, sv, gn, gs);
+            const bool one = (int64_t)ncand * nchu <= PCAP;
+            const int TB = one ? ncand : HP / nchu;            // candidates per batch
+            int half = 0;
+            for (int t0 = 0; t0 < ncand; t0 += TB, half ^= 1) {
+                const int tbn = min(TB, ncand - t0), nunits = tbn * nchu;
+                double *part = s_part + (one ? 0 : half * HP);
+                const int u0 = crank + warp * C, ustep = NW * C;       // unit u belongs to CTA u mod C, warp (u / C) mod NW
+                Pending pend{0ull, 0ull, 0ull};
+                if (u0 < nunits) pend = issue_unit(t0, u0);
+                for (int unit = u0; unit < nunits; unit += ustep) {
+                    const Pending cur = pend;
+                    const int unext = unit + ustep;
+                    if (unext < nunits) pend = issue_unit(t0, unext);
+                    uint32_t N, sv, gn, gs;
+                    finish(cur, N, sv, gn, gs);
+                    __syncwarp();
+                    double v = score_delta_any(s_lf, logtab, N, sv, gn, gs);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (C == 1) { if (lane == 0) s_part[unit] = v; }
-                else if (lane < C) cg::this_cluster().map_shared_rank(s_part, lane)[unit] = v;     // lane r stores into CTA r's s_part
-            }
-            csync();
-            for (int t = tid; t < ncand; t += NT) {
-                double a2 = 0.0;
-                for (int ch = 0; ch < nchu; ch++) a2 += s_part[t * nchu + ch];
-                s_lp[t] += a2;
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (C == 1) { if (lane == 0) part[unit] = v; }
+                    else if (lane < C) cg::this_cluster().map_shared_rank(part, lane)[unit] = v;     // lane r stores into CTA r's buffer
+                }
+                csync();
+                for (int tb = tid; tb < tbn; tb += NT) {
+                    double a2 = 0.0;
+                    for (int ch = 0; ch < nchu; ch++) a2 += part[tb * nchu + ch];
+                    s_lp[t0 + tb] += a2;
+                }
             }
         } else {
             for (int t = crank + warp * C; t < ncand; t += NW * C) {   // very many groups: one warp per candidate walks all of them

@@ -22,10 +22,16 @@ ne, nu, nb, bobs, moves, kcap = env("NE", 200000), env("NU", 2000), env("NB", 50
 names = ["A group (CSR row, z gather, smem atomics)", "B1 bitmap scan (+C candidates)", "B2 group decode", "D score", "E sample", "F apply"]
 for nc in [int(x) for x in os.environ.get("NC", "8,2").split(",")]:
     domains, schema, obs, truth = W.c5_hirm(dev, n=ne, n_unary=nu, n_binary=nb, bobs=bobs, n_clusters=nc, seed=0)
-    h = ChainSet(domains, schema, obs, 1, seed=0, max_tables=kcap, relation_tables={r: truth[r] for r in schema}, device=0)
+    nchains = env("CHAINS", 1)
+    h = ChainSet(domains, schema, obs, nchains, seed=0, max_tables=kcap, relation_tables={r: truth[r] for r in schema}, device=0)
     eng = h.backend.eng
-    hs = [h.chains[0].irms[t]["handle"] for t in sorted(h.chains[0].irms)]
+    hs = [ch.irms[t]["handle"] for ch in h.chains for t in sorted(ch.irms)]
     rng = np.random.default_rng(1)
+    if os.environ.get("ZTABLES"):                         # every IRM re-seated into ZTABLES tables of random sizes (a fresh IRM's CRP-prior-like state)
+        kt = int(os.environ["ZTABLES"])
+        for hh in hs:
+            w = rng.dirichlet(np.ones(kt) * 0.7)
+            eng.set_assignments(hh, 0, rng.choice(kt, size=ne, p=w).astype(np.int32))
     mv = [(np.zeros(moves, np.int32), rng.permutation(ne)[:moves].astype(np.int32)) for _ in hs]
     eng.sweep(hs, mv, seed=1)
     buf = torch.zeros(len(hs) * 32, dtype=torch.int64, device=dev)

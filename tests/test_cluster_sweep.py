@@ -138,3 +138,46 @@ def test_cluster_launch_with_big_cell_spaces(eng, n_rel, nobs):
     np.testing.assert_array_equal(outs[0][2], outs[1][2])
     for a, b in zip(outs[0][3], outs[1][3]):
         np.testing.assert_array_equal(a, b)
+
+
+def test_candidate_batches_give_identical_results(eng):
+    """More (candidate x chunk) scoring units than the partial-sum buffer holds (an IRM with dozens of tables early in a chain): the
+    candidates are scored in batches that alternate between the halves of the buffer.  Forced here with 64-thread CTAs (a buffer
+    of 256 units) and 30 tables; results must equal the single-batch launch bit for bit, with and without a cluster."""
+    rng = np.random.default_rng(21)
+    hs, (n, m), n_rel, keep = _mixed_irms(eng, 2, rng, max_tables=40)
+    z0 = [[rng.integers(0, 30, n).astype(np.int32), rng.integers(0, 12, m).astype(np.int32)] for _ in hs]
+    md = np.concatenate([np.full(n, 0, np.int32), np.full(m, 1, np.int32)])
+    mi = np.concatenate([rng.permutation(n), rng.permutation(m)]).astype(np.int32)
+    runs = []
+    for env in ({}, {"HIRM_GENERIC_THREADS": "64"}, {"HIRM_GENERIC_THREADS": "64", "HIRM_CLUSTER_SIZE": "4"}):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            for h, z in zip(hs, z0):
+                for d in range(2):
+                    eng.set_assignments(h, d, z[d])
+            res = eng.sweep(hs, [(md, mi)] * len(hs), seed=8, streams=list(range(len(hs))), counters=[0] * len(hs), trace_cap=48)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        out = []
+        for k, h in enumerate(hs):
+            nn, ll, pp = res["trace"][k]
+            assert nn.max() >= 25                               # dozens of candidates: 64-thread CTAs need several batches
+            valid = np.arange(ll.shape[1])[None, :] < nn[:, None]
+            out.append((res["choice"][k].copy(), nn.copy(), ll[valid].copy(), pp[valid].copy(), eng.get_assignments(h, 0).copy(),
+                        [eng.get_counts(h, r).copy() for r in range(n_rel)], eng.logp_score(h)))
+        runs.append(out)
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            for u, v in zip(a[:5], b[:5]):
+                np.testing.assert_array_equal(u, v)
+            for u, v in zip(a[5], b[5]):
+                np.testing.assert_array_equal(u, v)
+            assert a[6] == b[6]
+    for h in hs:
+        eng.irm_destroy(h)
