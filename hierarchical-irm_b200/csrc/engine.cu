@@ -1947,7 +1947,14 @@ static int run_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args, in
     for (int32_t kd : plan.dense_blk) { lo_all[(size_t)kd] = h_off[kd]; hi_all[(size_t)kd] = h_off[kd + 1]; }   // (the dense kernel sweeps whole lists, in round 0)
     CK(e->s_seg_lo.ensure(lo_all.size())); CK(e->s_seg_hi.ensure(hi_all.size())); CK(e->s_pg_pre.ensure(pre_all.size()));
     CK(e->s_pg_base.ensure((size_t)n_irms)); CK(e->s_pg_pitch.ensure((size_t)n_irms));
-    if (e->s_pg_data.n < (size_t)entries) { e->s_pg_data.release(); CK(e->s_pg_data.alloc((size_t)entries)); }
+    if (e->s_pg_data.n < (size_t)entries) {
+        e->s_pg_data.release();
+        if (e->s_pg_data.alloc((size_t)entries) != cudaSuccess) {      // no room for the staging buffer: the ordinary path needs none
+            cudaGetLastError();
+            e->s_pg_data.p = nullptr; e->s_pg_data.n = 0;
+            return launch_sweep(e, plan, args);
+        }
+    }
     cudaStream_t st = e->stream;
     CK(cudaMemcpyAsync(e->s_seg_lo.p, lo_all.data(), lo_all.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(e->s_seg_hi.p, hi_all.data(), hi_all.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
