@@ -1590,7 +1590,8 @@ static int plan_sweep(hirm_engine *e, int n_irms, const int32_t *h_irms, uint32_
         }
     }
     // live tables of the IRMs that may get a cluster: a move's scoring work grows with them as much as with the row length
-    if (!plan.generic_blk.empty() && (int)plan.generic_blk.size() <= e->num_sms) {
+    if (!plan.generic_blk.empty() && (int)plan.generic_blk.size() <= e->num_sms && !getenv("HIRM_CLUSTER_SIZE") &&
+        ((flags & HIRM_SWEEP_CLUSTER) || plan.gen_maxdeg >= 1536 || plan.gen_groups >= 384)) {      // (the conditions under which assign_cluster_classes deals SMs out)
         const int ng = (int)plan.generic_blk.size();
         std::vector<int32_t> ids((size_t)ng), tabs((size_t)ng);
         for (int j = 0; j < ng; j++) ids[(size_t)j] = h_irms[plan.generic_blk[(size_t)j]];
