@@ -5,10 +5,10 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "engine.cu")
-SRC_HOST = [os.path.join(HERE, "csrc", f) for f in ("ingest.cc", "relation_moves.cc", "ingest_gpu.cu")]
+SRC_HOST = [os.path.join(HERE, "csrc", f) for f in ("ingest.cc", "relation_moves.cc", "sweep_rounds.cc", "ingest_gpu.cu")]
 LIB = os.path.join(HERE, "libhirm_engine.so")
 DEPS = [os.path.join(HERE, "csrc", f) for f in
-        ("engine.cu", "engine_types.cuh", "device_math.cuh", "generic_sweep.cuh", "dense_sweep.cuh", "pregroup.cuh", "aux_kernels.cuh", "ingest.cc", "relation_moves.cc", "ingest_gpu.cu")] + \
+        ("engine.cu", "engine_types.cuh", "device_math.cuh", "generic_sweep.cuh", "dense_sweep.cuh", "pregroup.cuh", "aux_kernels.cuh", "ingest.cc", "relation_moves.cc", "sweep_rounds.cc", "ingest_gpu.cu")] + \
        [os.path.join(os.path.dirname(HERE), "include", "hirm_engine.h")]
 
 

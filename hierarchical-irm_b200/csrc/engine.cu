@@ -1914,35 +1914,41 @@ static int run_sweep(hirm_engine *e, const Plan &plan, const SweepArgs &args, in
     int64_t seg = std::min<int64_t>(4096, (int64_t)(budget / sizeof(uint2)) / std::max<int64_t>(pitch_sum, 1));
     if (const char *s = getenv("HIRM_PREGROUP_SEG")) seg = std::max(1, atoi(s));
     else if (seg < 32) return launch_sweep(e, plan, args);
-    // pieces
-    struct Piece { int64_t lo, hi; int pre; };
-    std::vector<std::vector<Piece>> pieces((size_t)n_gen);
-    size_t n_rounds = 1;
+    // pieces (csrc/sweep_rounds.cc), over the generic IRMs in launch order; then scattered to the sweep's IRM index
+    std::vector<int64_t> goff((size_t)n_gen + 1, 0);
+    std::vector<int32_t> rok((size_t)n_gen * RUNCAP, 0);
+    // the planner works on lists laid end to end in launch order; the runs' positions are shifted accordingly
+    std::vector<int64_t> shift((size_t)n_gen, 0), rst_g(rst.size(), 0);
     for (int w = 0; w < n_gen; w++) {
         const int k = plan.generic_blk[(size_t)w];
         const Irm *irm = e->irms[h_irms[k]].get();
-        std::vector<Piece> &P = pieces[(size_t)w];
-        const int64_t lo = h_off[k], hi = h_off[k + 1];
-        if (lo >= hi) continue;
-        if (rn[(size_t)w] <= 0 || rn[(size_t)w] > RUNCAP) { P.push_back({lo, hi, 0}); continue; }
+        goff[(size_t)w + 1] = goff[(size_t)w] + (h_off[k + 1] - h_off[k]);
+        shift[(size_t)w] = goff[(size_t)w] - h_off[k];
+        if (rn[(size_t)w] <= 0 || rn[(size_t)w] > RUNCAP) continue;
         for (int j = 0; j < rn[(size_t)w]; j++) {
-            const int64_t st = rst[(size_t)w * RUNCAP + j], en = j + 1 < rn[(size_t)w] ? rst[(size_t)w * RUNCAP + j + 1] : hi;
-            if (run_ok(irm, rdm[(size_t)w * RUNCAP + j], en - st)) {
-                for (int64_t a = st; a < en; a += seg) P.push_back({a, std::min(en, a + seg), 1});
-            } else if (!P.empty() && !P.back().pre) P.back().hi = en;
-            else P.push_back({st, en, 0});
+            const int64_t st = rst[(size_t)w * RUNCAP + j], en = j + 1 < rn[(size_t)w] ? rst[(size_t)w * RUNCAP + j + 1] : h_off[k + 1];
+            rok[(size_t)w * RUNCAP + j] = run_ok(irm, rdm[(size_t)w * RUNCAP + j], en - st) ? 1 : 0;
+            rst_g[(size_t)w * RUNCAP + j] = st + shift[(size_t)w];
         }
-        n_rounds = std::max(n_rounds, P.size());
     }
+    int32_t nr32 = 1;
+    if (hirm_plan_rounds(n_gen, goff.data(), rn.data(), RUNCAP, rst_g.data(), rok.data(), seg, &nr32, nullptr, nullptr, nullptr, 0))
+        return fail("pre-grouping: inconsistent runs of the move lists");
+    const size_t n_rounds = (size_t)nr32;
+    std::vector<int64_t> glo(n_rounds * (size_t)n_gen), ghi(n_rounds * (size_t)n_gen);
+    std::vector<int32_t> gpre(n_rounds * (size_t)n_gen);
+    if (hirm_plan_rounds(n_gen, goff.data(), rn.data(), RUNCAP, rst_g.data(), rok.data(), seg, &nr32, glo.data(), ghi.data(), gpre.data(), (int)n_rounds))
+        return fail("pre-grouping: inconsistent runs of the move lists");
     std::vector<int64_t> lo_all(n_rounds * (size_t)n_irms, 0), hi_all(n_rounds * (size_t)n_irms, 0), base((size_t)n_irms, 0);
     std::vector<int32_t> pre_all(n_rounds * (size_t)n_irms, 0);
     int64_t entries = 0;
     for (int k = 0; k < n_irms; k++) { base[(size_t)k] = entries; entries += (int64_t)pitch[(size_t)k] * seg; }
     for (int w = 0; w < n_gen; w++) {
         const int k = plan.generic_blk[(size_t)w];
-        for (size_t r = 0; r < pieces[(size_t)w].size(); r++) {
-            const Piece &pc = pieces[(size_t)w][r];
-            lo_all[r * n_irms + k] = pc.lo; hi_all[r * n_irms + k] = pc.hi; pre_all[r * n_irms + k] = pc.pre;
+        for (size_t r = 0; r < n_rounds; r++) {
+            const int64_t a = glo[r * n_gen + w], b = ghi[r * n_gen + w];
+            if (a >= b) continue;
+            lo_all[r * n_irms + k] = a - shift[(size_t)w]; hi_all[r * n_irms + k] = b - shift[(size_t)w]; pre_all[r * n_irms + k] = gpre[r * n_gen + w];
         }
     }
     for (int32_t kd : plan.dense_blk) { lo_all[(size_t)kd] = h_off[kd]; hi_all[(size_t)kd] = h_off[kd + 1]; }   // (the dense kernel sweeps whole lists, in round 0)

@@ -36,7 +36,7 @@ EXPORTS = [
     "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
     "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters", "hirm_engine_clear_relation_cache",
     "hirm_engine_seat_prior", "hirm_irm_set_table_mode", "hirm_unary_block_create", "hirm_unary_block_destroy",
-    "hirm_irm_set_observations_unary", "hirm_engine_last_cluster_size", "hirm_engine_last_rounds", "hirm_relation_reseat",
+    "hirm_irm_set_observations_unary", "hirm_engine_last_cluster_size", "hirm_engine_last_rounds", "hirm_plan_rounds", "hirm_relation_reseat",
     "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
     "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
     "hirm_gpu_dataset_last_error", "hirm_gpu_dataset_load", "hirm_gpu_dataset_free", "hirm_gpu_dataset_counts", "hirm_gpu_dataset_domain",
@@ -114,6 +114,7 @@ def load():
     L.hirm_irm_set_observations_unary.argtypes = [V, ctypes.c_int32, I, ctypes.c_int32, I]
     L.hirm_engine_last_cluster_size.argtypes = [V, c_i32p]
     L.hirm_engine_last_rounds.argtypes = [V, c_i32p, c_i32p]
+    L.hirm_plan_rounds.argtypes = [ctypes.c_int, c_i64p, c_i32p, ctypes.c_int, c_i64p, c_i32p, ctypes.c_int64, c_i32p, c_i64p, c_i64p, c_i32p, ctypes.c_int]
     L.hirm_relation_reseat.argtypes = [I, I, c_i32p, c_i32p, c_i32p, c_f64p, ctypes.c_int64, I, c_i32p, c_f64p, I, ctypes.c_double,
                                        c_i32p, c_i32p, c_i32p]
     L.hirm_irm_set_rng_counters.argtypes = [V, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64]
@@ -244,6 +245,33 @@ def relation_reseat(labels, sizes, rel_table, scores, fresh_col, order, uniforms
     if rc < 0:
         raise EngineError("hirm_relation_reseat: bad argument (%d)" % rc)
     return rc, p.value, moved.value, fresh.value
+
+
+def plan_rounds(offsets, runs, seg, runcap=64):
+    """hirm_plan_rounds (csrc/sweep_rounds.cc; host only): `offsets` [n + 1] of the move lists, `runs` = per list a sequence of
+    (start, qualifies) pairs of its runs of equal domain, or None for "unknown".  Returns a list of rounds, each a list of
+    (lo, hi, pre) per move list (lo == hi: nothing to do in that round)."""
+    L = load()
+    n = len(offsets) - 1
+    off = np.ascontiguousarray(offsets, dtype=np.int64)
+    n_runs = np.zeros(max(n, 1), np.int32)
+    start = np.zeros((max(n, 1), runcap), np.int64); ok = np.zeros((max(n, 1), runcap), np.int32)
+    for k in range(n):
+        if runs[k] is None:
+            n_runs[k] = -1
+            continue
+        n_runs[k] = len(runs[k])
+        for j, (st, q) in enumerate(runs[k][:runcap]):
+            start[k, j] = st; ok[k, j] = int(bool(q))
+    nr = ctypes.c_int32(0)
+    if L.hirm_plan_rounds(n, _p(off, c_i64p), _p(n_runs, c_i32p), runcap, _p(start, c_i64p), _p(ok, c_i32p), int(seg), ctypes.byref(nr),
+                          None, None, None, 0):
+        raise EngineError("hirm_plan_rounds: bad argument")
+    lo = np.zeros((nr.value, max(n, 1)), np.int64); hi = np.zeros_like(lo); pre = np.zeros((nr.value, max(n, 1)), np.int32)
+    if L.hirm_plan_rounds(n, _p(off, c_i64p), _p(n_runs, c_i32p), runcap, _p(start, c_i64p), _p(ok, c_i32p), int(seg), ctypes.byref(nr),
+                          _p(lo, c_i64p), _p(hi, c_i64p), _p(pre, c_i32p), nr.value):
+        raise EngineError("hirm_plan_rounds: bad argument")
+    return [[(int(lo[r, k]), int(hi[r, k]), int(pre[r, k])) for k in range(n)] for r in range(nr.value)]
 
 
 class Engine:

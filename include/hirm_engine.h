@@ -232,6 +232,14 @@ int hirm_engine_last_cluster_size(hirm_engine *e, int32_t *ctas_per_irm);
  * possible, HIRM_PREGROUP_SEG caps the moves per piece.  Results are bit-identical either way. */
 int hirm_engine_last_rounds(hirm_engine *e, int32_t *rounds, int32_t *pregrouped);
 
+/* The host part of that (csrc/sweep_rounds.cc, no CUDA): cut n_lists move lists -- list k = moves [off[k], off[k+1]), run j of its
+ * n_runs[k] runs of equal domain starting at run_start[k * runcap + j] and qualifying for pre-grouping iff run_ok[k * runcap + j] -- into
+ * pieces: at most `seg` moves of one qualifying run (pre = 1), or everything between two such runs, merged (pre = 0).  n_runs[k] <= 0 or
+ * > runcap: the list is one ordinary piece.  Pass 1 (lo == NULL) returns the number of rounds (most pieces of a list, at least 1);
+ * pass 2 fills lo / hi / pre [round * n_lists + k] (rounds beyond a list's last piece: empty). */
+int hirm_plan_rounds(int n_lists, const int64_t *off, const int32_t *n_runs, int runcap, const int64_t *run_start, const int32_t *run_ok,
+                     int64_t seg, int32_t *n_rounds, int64_t *lo, int64_t *hi, int32_t *pre, int max_rounds);
+
 /* shared-memory plan of the last dense launch: resident CTAs (chains) per SM, TMA ring stages, bytes per
  * row chunk, dynamic shared memory per CTA */
 int hirm_engine_last_dense_plan(hirm_engine *e, int32_t *ctas_per_sm, int32_t *stages, int32_t *chunk_bytes, int32_t *smem_bytes);
