@@ -1669,24 +1669,11 @@ static void assign_cluster_classes(hirm_engine *e, Plan &plan, uint32_t flags) {
         if ((forced || heavy) && n_gen <= e->num_sms) {
             // (a cluster lives inside one GPC, 16 to 20 SMs each; keeping the budget at 8 x 16 SMs made no measurable difference)
             const int budget = std::max(n_gen, std::min(e->num_sms, getenv("HIRM_CLUSTER_BUDGET") ? atoi(getenv("HIRM_CLUSTER_BUDGET")) : e->num_sms));
-            // Work of a move ~ the entries it reads x the live tables it scores them against (config 5's IRMs swept alone, 16 CTAs each:
-            // 25 us per move with 6000 entries and 9 tables, 42 us with 3400 entries and 47 tables -- profiles/r02_c5_irm_costs.txt).  The launch
-            // ends with its slowest IRM: the IRM with the most work per CTA doubles its cluster while SMs are left.
-            auto work = [&](int i) {
-                const double tabs = i < (int)plan.gen_tables.size() ? (double)plan.gen_tables[(size_t)i] : 8.0;
-                return plan.gen_weight[(size_t)i] * std::max(1.0, tabs / 8.0);
-            };
-            int total = n_gen;
-            for (;;) {
-                int best = -1;
-                for (int i = 0; i < n_gen; i++) {
-                    if (cs[(size_t)i] >= 16 || total + cs[(size_t)i] > budget) continue;
-                    if (!forced && work(i) / cs[(size_t)i] < 192.0) continue;    // too little work per CTA to be worth a barrier
-                    if (best < 0 || work(i) / cs[(size_t)i] > work(best) / cs[(size_t)best]) best = i;
-                }
-                if (best < 0) break;
-                total += cs[(size_t)best]; cs[(size_t)best] *= 2;
-            }
+            // by work per CTA = entries x live tables (hirm_plan_clusters, csrc/sweep_rounds.cc: host only, covered on the CPU)
+            std::vector<int32_t> tabs((size_t)n_gen, 8), out((size_t)n_gen, 1);
+            for (int i = 0; i < n_gen && i < (int)plan.gen_tables.size(); i++) tabs[(size_t)i] = plan.gen_tables[(size_t)i];
+            hirm_plan_clusters(n_gen, plan.gen_weight.data(), tabs.data(), budget, forced ? 1 : 0, out.data());
+            for (int i = 0; i < n_gen; i++) cs[(size_t)i] = out[(size_t)i];
         }
     }
     std::vector<int> order((size_t)n_gen);

@@ -53,3 +53,27 @@ extern "C" int hirm_plan_rounds(int n_lists, const int64_t *off, const int32_t *
     *n_rounds = rounds;
     return 0;
 }
+
+// CTAs per IRM (thread-block cluster sizes) of a generic launch of n IRMs on `budget` SMs.  Work of a move ~ the entries it reads
+// (entries[i]: CSR entries + unary columns / 16 of an average move) x the live tables it scores them against (tables[i], or NULL:
+// 8 each): config 5's IRMs swept alone on 16 CTAs cost 25 us per move with 6000 entries and 9 tables, 42 us with 3400 entries and
+// 47 tables (profiles/r02_c5_irm_costs.txt).  The launch ends with its slowest IRM: every IRM starts with one CTA, and the IRM with
+// the most work per CTA doubles its cluster (up to 16, a power of two) while SMs are left; unless `forced`, not below 192 units of
+// work per CTA (too little to be worth a cluster barrier).  Returns the CTAs in use, or -1 on bad arguments.
+extern "C" int hirm_plan_clusters(int n, const double *entries, const int32_t *tables, int budget, int forced, int32_t *ctas) {
+    if (n < 0 || (n > 0 && (!entries || !ctas))) return -1;
+    auto work = [&](int i) { return entries[i] * std::max(1.0, (tables ? (double)tables[i] : 8.0) / 8.0); };
+    for (int i = 0; i < n; i++) ctas[i] = 1;
+    int total = n;
+    for (;;) {
+        int best = -1;
+        for (int i = 0; i < n; i++) {
+            if (ctas[i] >= 16 || total + ctas[i] > budget) continue;
+            if (!forced && work(i) / ctas[i] < 192.0) continue;
+            if (best < 0 || work(i) / ctas[i] > work(best) / ctas[best]) best = i;
+        }
+        if (best < 0) break;
+        total += ctas[best]; ctas[best] *= 2;
+    }
+    return total;
+}

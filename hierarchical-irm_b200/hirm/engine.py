@@ -36,7 +36,7 @@ EXPORTS = [
     "hirm_irm_set_observations_device", "hirm_engine_relation_score_matrix", "hirm_engine_relation_scores_fresh",
     "hirm_engine_crp_prior_draw", "hirm_irm_set_rng_counters", "hirm_engine_clear_relation_cache",
     "hirm_engine_seat_prior", "hirm_irm_set_table_mode", "hirm_unary_block_create", "hirm_unary_block_destroy",
-    "hirm_irm_set_observations_unary", "hirm_engine_last_cluster_size", "hirm_engine_last_rounds", "hirm_plan_rounds", "hirm_relation_reseat",
+    "hirm_irm_set_observations_unary", "hirm_engine_last_cluster_size", "hirm_engine_last_rounds", "hirm_plan_rounds", "hirm_plan_clusters", "hirm_relation_reseat",
     "hirm_dataset_last_error", "hirm_dataset_load", "hirm_dataset_free", "hirm_dataset_counts", "hirm_dataset_domain",
     "hirm_dataset_relation", "hirm_dataset_observations", "hirm_dataset_entity",
     "hirm_gpu_dataset_last_error", "hirm_gpu_dataset_load", "hirm_gpu_dataset_free", "hirm_gpu_dataset_counts", "hirm_gpu_dataset_domain",
@@ -114,6 +114,7 @@ def load():
     L.hirm_irm_set_observations_unary.argtypes = [V, ctypes.c_int32, I, ctypes.c_int32, I]
     L.hirm_engine_last_cluster_size.argtypes = [V, c_i32p]
     L.hirm_engine_last_rounds.argtypes = [V, c_i32p, c_i32p]
+    L.hirm_plan_clusters.argtypes = [ctypes.c_int, c_f64p, c_i32p, ctypes.c_int, ctypes.c_int, c_i32p]
     L.hirm_plan_rounds.argtypes = [ctypes.c_int, c_i64p, c_i32p, ctypes.c_int, c_i64p, c_i32p, ctypes.c_int64, c_i32p, c_i64p, c_i64p, c_i32p, ctypes.c_int]
     L.hirm_relation_reseat.argtypes = [I, I, c_i32p, c_i32p, c_i32p, c_f64p, ctypes.c_int64, I, c_i32p, c_f64p, I, ctypes.c_double,
                                        c_i32p, c_i32p, c_i32p]
@@ -245,6 +246,18 @@ def relation_reseat(labels, sizes, rel_table, scores, fresh_col, order, uniforms
     if rc < 0:
         raise EngineError("hirm_relation_reseat: bad argument (%d)" % rc)
     return rc, p.value, moved.value, fresh.value
+
+
+def plan_clusters(entries, tables, budget, forced=False):
+    """hirm_plan_clusters (csrc/sweep_rounds.cc; host only): CTAs per IRM of a generic launch."""
+    L = load()
+    ent = np.ascontiguousarray(entries, dtype=np.float64)
+    tab = None if tables is None else np.ascontiguousarray(tables, dtype=np.int32)
+    out = np.ones(max(len(ent), 1), np.int32)
+    total = L.hirm_plan_clusters(len(ent), _p(ent, c_f64p), None if tab is None else _p(tab, c_i32p), int(budget), int(bool(forced)), _p(out, c_i32p))
+    if total < 0:
+        raise EngineError("hirm_plan_clusters: bad argument")
+    return out[:len(ent)].copy(), total
 
 
 def plan_rounds(offsets, runs, seg, runcap=64):

@@ -240,6 +240,12 @@ int hirm_engine_last_rounds(hirm_engine *e, int32_t *rounds, int32_t *pregrouped
 int hirm_plan_rounds(int n_lists, const int64_t *off, const int32_t *n_runs, int runcap, const int64_t *run_start, const int32_t *run_ok,
                      int64_t seg, int32_t *n_rounds, int64_t *lo, int64_t *hi, int32_t *pre, int max_rounds);
 
+/* Cluster sizes of a generic launch (host only): n IRMs on `budget` SMs, entries[i] = CSR entries (+ unary columns / 16) an average move of
+ * IRM i reads, tables[i] = its live tables (NULL: 8 each).  Every IRM starts with one CTA; the IRM with the most work per CTA (entries x
+ * max(1, tables / 8)) doubles its cluster, up to 16, while SMs are left -- unless `forced`, not below 192 units of work per CTA.  Returns
+ * the CTAs in use. */
+int hirm_plan_clusters(int n, const double *entries, const int32_t *tables, int budget, int forced, int32_t *ctas);
+
 /* shared-memory plan of the last dense launch: resident CTAs (chains) per SM, TMA ring stages, bytes per
  * row chunk, dynamic shared memory per CTA */
 int hirm_engine_last_dense_plan(hirm_engine *e, int32_t *ctas_per_sm, int32_t *stages, int32_t *chunk_bytes, int32_t *smem_bytes);

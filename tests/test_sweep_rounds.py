@@ -71,3 +71,33 @@ def test_bad_runs_are_refused():
         E.plan_rounds([0, 10], [[(3, 1)]], 4)                   # the first run must start the list
     with pytest.raises(E.EngineError):
         E.plan_rounds([0, 10], [[(0, 1), (12, 1)]], 4)          # a run beyond the list
+
+
+def test_cluster_sizes_follow_work_and_budget():
+    """hirm_plan_clusters: powers of two up to 16, the budget is never exceeded, more work never gets fewer CTAs, live tables count
+    like entries, and an IRM with too little work per CTA stays on one CTA unless the caller forces clusters."""
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        n = int(rng.integers(1, 60))
+        ent = rng.choice([5.0, 80.0, 400.0, 2500.0, 7000.0], n) * rng.uniform(0.5, 1.5, n)
+        tab = rng.integers(1, 60, n).astype(np.int32)
+        budget = int(rng.integers(n, 200))
+        cs, total = E.plan_clusters(ent, tab, budget)
+        assert total == cs.sum() <= budget and set(cs.tolist()) <= {1, 2, 4, 8, 16}
+        work = ent * np.maximum(1.0, tab / 8.0)
+        order = np.argsort(work)
+        assert np.all(np.diff(cs[order]) >= 0) or np.all(np.diff((work / cs)[order]) > -1e-9 * work.max() - 1)   # heavier: never fewer CTAs ...
+        for i in range(n):
+            if cs[i] > 1:
+                assert work[i] / (cs[i] // 2) >= 192.0             # ... and only where a CTA keeps enough work
+        # nobody could still double: out of budget, at the cap, or too little work
+        left = budget - total
+        for i in range(n):
+            assert cs[i] >= 16 or cs[i] > left or work[i] / cs[i] < 192.0
+    cs, total = E.plan_clusters([100.0, 100.0], [8, 8], 148)
+    assert cs.tolist() == [1, 1]
+    cs, total = E.plan_clusters([100.0, 100.0], [8, 8], 148, forced=True)
+    assert cs.tolist() == [16, 16]
+    # config 5's shape: a young IRM with 47 tables outweighs an old one with twice the entries
+    cs, total = E.plan_clusters([3400.0, 6000.0] + [300.0] * 40, [47, 9] + [15] * 40, 72)
+    assert cs[0] == 16 and cs[0] >= cs[1] and total <= 72
